@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Benchmark of the UNet2DS hot path (BASELINE.json metric: UNet2DS 512^2 images/sec with 8x TTA,
+plus train crops/sec and the projection's GB/s as extra keys on the same JSON line).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA kernels)
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: oracle port of the Keras graph
+
+A step = one 512x512 summary image through the full 8x-TTA prediction on every rank (independent
+images per rank: weak scaling, no data-path collective).  `value` is device-timed with the input
+already in HBM; `e2e` goes through UNet2DSummary.predict with host buffers in and the mask out.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, 'deep-calcium_b200'), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+os.environ.setdefault('DEEP_CALCIUM_HOME', '/tmp/deep-calcium-home')
+
+import numpy as np  # noqa: E402
+
+METRIC = 'UNet2DS 512x512 images/sec (8x TTA)'
+WORKLOAD = 'unet2ds_512x512_tta8_nfb32_random_init'
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return dict(hbm=float(p['hbm_gbs']), tf=float(p['bf16_tflops']), tf_sus=float(p['bf16_tflops_sustained']),
+                    src='measured (MEASURED_PEAKS.json)')
+    except Exception:
+        return dict(hbm=6650.0, tf=1590.0, tf_sus=1400.0, src='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler(object):
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == 'active'})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_forward_tta(w, s, spec, n_images):
+    """oracle port of predict(augmentation=True) (unet_2d_summary.py:585-595) in float32 on all host cores"""
+    import torch
+    import oracle
+    t0 = time.perf_counter()
+    for _ in range(n_images):
+        oracle.tta_predict(w, s, spec, augmentation=True, dtype=torch.float32)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    import torch
+    import oracle
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    spec = oracle.UNetSpec(32)
+    w = oracle.init_weights(spec, seed=7535)
+    s = np.random.default_rng(865).standard_normal((512, 512)).astype(np.float32)
+    for _ in range(min(args.warmup, 1)):
+        cpu_forward_tta(w, s, spec, 1)
+    dt = cpu_forward_tta(w, s, spec, args.steps)
+    val = args.steps / dt
+    cores = torch.get_num_threads()
+    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'images/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': 1e3 * dt / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'window': 512, 'tta': 8, 'weights': 'random-init seed 7535'},
+            'cpu_baseline': {'value': val, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                             'sample': '%d TTA images (8 forwards each) of the torch-CPU fp32 oracle port of the Keras '
+                                       'graph; Keras 2.0.6/TF 1.2.1 are not installable' % args.steps},
+            'e2e': {'value': val, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def per_layer_profile(eng, sess, spec, NB, H, W):
+    """device time of every contraction launch of one forward pass (CUDA events on the launch stream,
+    eager mode) -> (rows, total conv flops, total conv ms)."""
+    import torch
+    from deepcalcium.engine import ops
+    rows = []
+    orig = {}
+    names = ['conv3x3_fwd', 'convT2x2_fwd', 'conv3x3_c1_fwd', 'maxpool2x2', 'head_fwd']
+    events = []
+
+    def wrap(name):
+        f = getattr(ops, name)
+        orig[name] = f
+
+        def g(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            f(*a, **k)
+            e1.record()
+            events.append((name, a, e0, e1))
+        setattr(ops, name, g)
+
+    for n in names:
+        wrap(n)
+    try:
+        for _ in range(3):
+            del events[:]
+            eng._forward_inference(sess)
+            torch.cuda.synchronize()
+    finally:
+        for n, f in orig.items():
+            setattr(ops, n, f)
+    tot_f, tot_ms = 0.0, 0.0
+    for name, a, e0, e1 in events:
+        ms = e0.elapsed_time(e1)
+        fl = 0.0
+        if name == 'conv3x3_fwd':
+            src0, src1, wgt, out = a[0], a[1], a[2], a[3]
+            cin = src0.shape[3] + (src1.shape[3] if src1 is not None else 0)
+            fl = 2.0 * out.shape[0] * out.shape[1] * out.shape[2] * 9 * cin * out.shape[3]
+            tag = 'conv3x3 %dx%d %d->%d' % (out.shape[1], out.shape[2], cin, out.shape[3])
+        elif name == 'convT2x2_fwd':
+            src, out = a[0], a[2]
+            fl = 2.0 * src.shape[0] * src.shape[1] * src.shape[2] * 4 * src.shape[3] * out.shape[3]
+            tag = 'convT2x2 %dx%d %d->%d' % (src.shape[1], src.shape[2], src.shape[3], out.shape[3])
+        else:
+            tag = name
+        if fl:
+            tot_f += fl
+            tot_ms += ms
+        rows.append({'op': tag, 'ms': round(ms, 4), 'tflops': round(fl / ms / 1e9, 1) if fl else None})
+    return rows, tot_f, tot_ms
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from deepcalcium import _native as nat
+    from deepcalcium.engine.graph import GraphSpec
+    from deepcalcium.engine.unet_engine import UNetEngine
+    from deepcalcium.engine.graph import he_normal_weights
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+    pk = peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    spec = GraphSpec(32)
+    w = he_normal_weights(spec, seed=7535)
+    rng = np.random.default_rng(7535)
+    for blk in spec.blocks:          # randomised BN statistics so that the folded BN is not the identity
+        if blk.kind != 'head':
+            w[blk.name + '/moving_mean'] = (0.1 * rng.standard_normal(blk.cout)).astype(np.float32)
+            w[blk.name + '/moving_var'] = rng.uniform(0.5, 1.5, blk.cout).astype(np.float32)
+    eng = UNetEngine(spec, precision=args.precision)
+    eng.set_weights_dict(w)
+    n_img = 4
+    imgs = [torch.from_numpy(np.random.default_rng(865 + rank * 100 + i).standard_normal((512, 512)).astype(np.float32)).to(dev)
+            for i in range(n_img)]
+
+    # ---- kernel-only arm: inputs resident in HBM, device-timed
+    for i in range(max(args.warmup, 3)):
+        eng.predict_tta(imgs[i % n_img])
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        eng.predict_tta(imgs[i % n_img])
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = eng.launches - launches0
+    value = world * args.steps / (ms / 1e3)
+
+    # ---- e2e arm: the reference-facing API with host buffers (UNet2DSummary.predict, :532)
+    from deepcalcium.models.neurons import UNet2DSummary
+    from deepcalcium.models.neurons.unet_2d_summary import UNetModel
+    host_imgs = {('img%d' % i): imgs[i].cpu().numpy() for i in range(n_img)}
+    model = UNetModel.__new__(UNetModel)
+    model.window_shape, model.spec, model.engine = (512, 512), spec, eng
+    api = UNet2DSummary(cpdir='/tmp/deep-calcium-bench-cp', dataset_name_func=lambda p: p,
+                        series_summary_func=lambda p: host_imgs[p])
+    paths = [('img%d' % (i % n_img)) for i in range(args.steps)]
+    api.predict(paths[:3], model, augmentation=True)
+    barrier()
+    t0 = time.perf_counter()
+    Mp, _ = api.predict(paths, model, augmentation=True)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = {'value': world * args.steps / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': 512 * 512 * 4,
+           'd2h_bytes_per_step': int(Mp[0].nbytes)}
+
+    line = {'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'window': 512, 'tta': 8, 'batch_per_step': 8,
+                       'weights': 'random-init he_normal seed 7535', 'parallelism': 'independent images per rank',
+                       'l2': 'per-step activation footprint ~1.2 GB >> 126 MB L2; 4 rotating inputs'},
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches)}
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel family (the conv tap-GEMMs), timed live with CUDA events
+        try:
+            sess = eng._session(8, 512, 512, False)
+            rows, tot_f, tot_ms = per_layer_profile(eng, sess, spec, 8, 512, 512)
+            ach = tot_f / tot_ms / 1e9
+            line['roofline'] = {'bound': 'tensor', 'achieved': ach, 'peak': pk['tf'], 'unit': 'TFLOP/s',
+                                'frac': ach / pk['tf'], 'traffic': None, 'peak_source': pk['src'],
+                                'kernel': 'tap-GEMM conv3x3/convT2x2 (all 22 launches of one 8-image forward)',
+                                'flops_per_step': tot_f, 'conv_ms_per_step': tot_ms,
+                                'whole_step_frac': (8 * spec.flops_forward(512, 512) / (ms / args.steps) / 1e9) / pk['tf_sus']}
+            line['per_layer'] = rows
+        except Exception as ex:   # noqa: BLE001
+            line['roofline'] = {'error': repr(ex)}
+        # ---- extras: projection (C2) and training (C3)
+        line['extra'] = {}
+        for name, fn in (('projection', bench_projection), ('train', bench_train)):
+            try:
+                line['extra'][name] = fn(args, pk)
+            except Exception as ex:   # noqa: BLE001
+                line['extra'][name] = {'error': repr(ex)}
+        # ---- CPU baseline on this box's host cores (bounded sample)
+        try:
+            import oracle
+            ow = oracle.init_weights(oracle.UNetSpec(32), seed=7535)
+            s = imgs[0].cpu().numpy()
+            cpu_forward_tta(ow, s[:128, :128].copy(), oracle.UNetSpec(32), 1)
+            n_cpu = 2
+            dt = cpu_forward_tta(ow, s, oracle.UNetSpec(32), n_cpu)
+            line['cpu_baseline'] = {'value': n_cpu / dt, 'unit': 'images/s', 'cores': torch.get_num_threads(),
+                                    'kind': 'port', 'sample': '%d TTA images (16 fp32 forwards) of the torch-CPU '
+                                    'oracle port of the Keras graph' % n_cpu}
+        except Exception as ex:   # noqa: BLE001
+            line['cpu_baseline'] = {'error': repr(ex)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_projection(args, pk):
+    """BASELINE config C2: mean/max projection of a 3000x512x512 float32 movie resident in HBM."""
+    import torch
+    from deepcalcium.datasets.nf import summarize_movie_device
+    from deepcalcium.engine import ops
+    T, H, W = 3000, 512, 512
+    g = torch.Generator(device='cuda'); g.manual_seed(7535)
+    movie = torch.rand((T, H, W), device='cuda', generator=g) * 4096
+    out = (torch.empty(H, W, device='cuda'), torch.empty(H, W, device='cuda'))
+    ws = torch.empty(ops.proj_workspace_bytes(T, H, W), dtype=torch.uint8, device='cuda')
+    for _ in range(3):
+        summarize_movie_device(movie, out=out, workspace=ws)
+    torch.cuda.synchronize()
+    n = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        summarize_movie_device(movie, out=out, workspace=ws)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    nbytes = T * H * W * 4 + 2 * H * W * 4
+    res = {'ms': ms, 'movies_per_s': 1e3 / ms, 'roofline': {'bound': 'hbm', 'achieved': nbytes / ms / 1e6, 'peak': pk['hbm'],
+                                                            'unit': 'GB/s', 'frac': nbytes / ms / 1e6 / pk['hbm'],
+                                                            'bytes': nbytes, 'note': '3.1 GB input >> L2'}}
+    # numpy baseline on a bounded sample (300 frames)
+    sub = movie[:300].cpu().numpy()
+    t0 = time.perf_counter()
+    sub.mean(0, dtype=np.float64); sub.max(0)
+    dt = time.perf_counter() - t0
+    res['cpu_baseline'] = {'value': sub.nbytes / dt / 1e9, 'unit': 'GB/s', 'cores': 1, 'kind': 'port',
+                           'sample': '300 of 3000 frames, numpy mean(float64)+max'}
+    del movie
+    return res
+
+
+def bench_train(args, pk):
+    """BASELINE config C3: 128x128 crops, batch 32, dice loss, Adam(0.002), dropout on."""
+    import torch
+    from deepcalcium.engine.graph import GraphSpec, he_normal_weights
+    from deepcalcium.engine.unet_engine import UNetEngine
+    spec = GraphSpec(32)
+    eng = UNetEngine(spec, precision=args.precision)
+    eng.set_weights_dict(he_normal_weights(spec, seed=7535))
+    rng = np.random.default_rng(865)
+    B = 32
+    xs = [torch.from_numpy(rng.standard_normal((B, 128, 128)).astype(np.float32)).cuda() for _ in range(4)]
+    ys = [torch.from_numpy((rng.random((B, 128, 128)) < 0.126).astype(np.uint8)).cuda() for _ in range(4)]
+    for i in range(5):
+        eng.train_step(xs[i % 4], ys[i % 4], loss='dice_loss', lr=0.002, dropout=True)
+    torch.cuda.synchronize()
+    n = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        m = eng.train_step(xs[i % 4], ys[i % 4], loss='dice_loss', lr=0.002, dropout=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    fl = B * spec.flops_train(128, 128)
+    return {'crops_per_s': B * 1e3 / ms, 'ms_per_step': ms, 'batch': B, 'crop': 128, 'loss': 'dice_loss',
+            'final_loss': float(m[0].item()), 'tflops': fl / ms / 1e9, 'frac_of_bf16_peak': fl / ms / 1e9 / pk['tf_sus'],
+            'flops_per_step': fl}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

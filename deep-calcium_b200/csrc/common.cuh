@@ -1,0 +1,64 @@
+// Shared helpers for the dcb200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+
+#include "../../include/dcb200.h"
+
+namespace dcb {
+
+// thread-local last-error text returned by dcb_last_error()
+char* last_error_buf();
+int fail(int code, const char* fmt, ...);
+
+#define DCB_CHECK_ARG(cond, ...)                                   \
+  do { if (!(cond)) return ::dcb::fail(DCB_ERR_INVALID_ARGUMENT, __VA_ARGS__); } while (0)
+
+#define DCB_CUDA_OK(expr)                                                              \
+  do { cudaError_t _e = (expr);                                                        \
+       if (_e != cudaSuccess)                                                          \
+         return ::dcb::fail(DCB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,              \
+                            cudaGetErrorString(_e), __FILE__, __LINE__); } while (0)
+
+// Launch check that does not synchronise (graph-capturable).
+#define DCB_LAUNCH_OK(name)                                                            \
+  do { cudaError_t _e = cudaPeekAtLastError();                                         \
+       if (_e != cudaSuccess)                                                          \
+         return ::dcb::fail(DCB_ERR_CUDA, "launch of %s failed: %s", name,             \
+                            cudaGetErrorString(_e)); } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+int sm_count();   // cached multiprocessor count of the current device
+
+// ---- device helpers ----
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace dcb

@@ -1,0 +1,183 @@
+// C-ABI entry points of the dense contractions (conv3x3 / convT2x2, fwd / dgrad / wgrad)
+// and the weight-layout preparation.  DCB_F32 routes to the CUDA-core check kernels
+// (tapgemm_f32.cu), DCB_BF16 to the tcgen05/TMEM/TMA kernels (tapgemm_tc.cu).
+#include "common.cuh"
+#include "tapgeom.h"
+
+namespace dcb {
+extern unsigned long long g_launches;
+
+void geom_conv3x3(TapGeom& g, int N, int H, int W);
+void geom_convT_fwd(TapGeom& g, int N, int h, int w);
+void geom_convT_dgrad(TapGeom& g, int N, int h, int w);
+int run_f32_fwd(const TapGeom& g, const float* s0, int C0, const float* s1, int C1, const float* B, int Nout,
+                float* out, const float* scale, const float* shift, int relu, cudaStream_t st);
+int f32_wgrad_splits(const TapGeom& g, int K, int Nout);
+int run_f32_wgrad(const TapGeom& g, const float* s0, int C0, const float* s1, int C1, const float* G, int Nout,
+                  float* dW, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// tcgen05 path (tapgemm_tc.cu)
+int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* B, int Nout, void* out,
+               const float* scale, const float* shift, int relu, cudaStream_t st);
+int run_tc_wgrad(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* G, int Nout, float* dW,
+                 void* ws, size_t ws_bytes, cudaStream_t st);
+size_t tc_wgrad_workspace(const TapGeom& g, int K, int Nout);
+
+// ---- weight preparation ----
+// conv3x3: w[t][ci][co] (t = kh*3+kw)
+template <typename T>
+__global__ void prep_conv3x3_kernel(const float* __restrict__ w, int Cin, int Cout, T* __restrict__ wf,
+                                    T* __restrict__ wd, int nmajor) {
+  const long long n = 9LL * Cin * Cout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout), ci = (int)((i / Cout) % Cin), t = (int)(i / ((long long)Cout * Cin));
+    const float v = w[i];
+    if (nmajor) {
+      if (wf) wf[((long long)co * 9 + t) * Cin + ci] = from_f32<T>(v);            // [Cout][9][Cin]
+      if (wd) wd[((long long)ci * 9 + (8 - t)) * Cout + co] = from_f32<T>(v);      // [Cin][9][Cout], taps flipped
+    } else {
+      if (wf) wf[i] = from_f32<T>(v);                                              // [9][Cin][Cout]
+      if (wd) wd[((long long)(8 - t) * Cout + co) * Cin + ci] = from_f32<T>(v);    // [9][Cout][Cin], taps flipped
+    }
+  }
+}
+// convT: w[t][co][ci] (t = a*2+b)
+template <typename T>
+__global__ void prep_convT_kernel(const float* __restrict__ w, int Cin, int Cout, T* __restrict__ wf,
+                                  T* __restrict__ wd, int nmajor) {
+  const long long n = 4LL * Cin * Cout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin), co = (int)((i / Cin) % Cout), t = (int)(i / ((long long)Cout * Cin));
+    const float v = w[i];
+    if (nmajor) {
+      if (wf) wf[i] = from_f32<T>(v);                                              // [4][Cout][Cin]
+      if (wd) wd[((long long)ci * 4 + t) * Cout + co] = from_f32<T>(v);            // [Cin][4][Cout]
+    } else {
+      if (wf) wf[((long long)t * Cin + ci) * Cout + co] = from_f32<T>(v);          // [4][Cin][Cout]
+      if (wd) wd[i] = from_f32<T>(v);                                              // [4][Cout][Cin]
+    }
+  }
+}
+
+}  // namespace dcb
+
+using namespace dcb;
+
+extern "C" int dcb_prep_conv3x3_weights(int dtype, const float* w, int Cin, int Cout, void* w_fwd, void* w_dgrad,
+                                        dcb_stream_t stream) {
+  DCB_CHECK_ARG(w && Cin > 0 && Cout > 0 && (w_fwd || w_dgrad), "dcb_prep_conv3x3_weights: bad arguments");
+  const long long n = 9LL * Cin * Cout;
+  const int grid = cdiv(n, 256) > 4096 ? 4096 : cdiv(n, 256);
+  if (dtype == DCB_F32)
+    prep_conv3x3_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(w, Cin, Cout, (float*)w_fwd, (float*)w_dgrad, 0);
+  else if (dtype == DCB_BF16)
+    prep_conv3x3_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(w, Cin, Cout, (__nv_bfloat16*)w_fwd,
+                                                                              (__nv_bfloat16*)w_dgrad, 1);
+  else return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+  g_launches += 1;
+  DCB_LAUNCH_OK("prep_conv3x3_kernel");
+  return DCB_OK;
+}
+
+extern "C" int dcb_prep_convT2x2_weights(int dtype, const float* w, int Cin, int Cout, void* w_fwd, void* w_dgrad,
+                                         dcb_stream_t stream) {
+  DCB_CHECK_ARG(w && Cin > 0 && Cout > 0 && (w_fwd || w_dgrad), "dcb_prep_convT2x2_weights: bad arguments");
+  const long long n = 4LL * Cin * Cout;
+  const int grid = cdiv(n, 256) > 4096 ? 4096 : cdiv(n, 256);
+  if (dtype == DCB_F32)
+    prep_convT_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(w, Cin, Cout, (float*)w_fwd, (float*)w_dgrad, 0);
+  else if (dtype == DCB_BF16)
+    prep_convT_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(w, Cin, Cout, (__nv_bfloat16*)w_fwd,
+                                                                            (__nv_bfloat16*)w_dgrad, 1);
+  else return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+  g_launches += 1;
+  DCB_LAUNCH_OK("prep_convT_kernel");
+  return DCB_OK;
+}
+
+extern "C" int dcb_conv3x3_fwd(int dtype, const void* src0, int C0, const void* src1, int C1, int N, int H, int W,
+                               const void* wgt, int Cout, const float* scale, const float* shift, int relu, void* out,
+                               dcb_stream_t stream) {
+  DCB_CHECK_ARG(src0 && wgt && out, "dcb_conv3x3_fwd: null pointer");
+  DCB_CHECK_ARG(N > 0 && H > 0 && W > 0 && C0 > 0 && C1 >= 0 && Cout > 0 && (C1 == 0 || src1),
+                "dcb_conv3x3_fwd: bad shape N=%d H=%d W=%d C0=%d C1=%d Cout=%d", N, H, W, C0, C1, Cout);
+  TapGeom g;
+  geom_conv3x3(g, N, H, W);
+  if (dtype == DCB_F32)
+    return run_f32_fwd(g, (const float*)src0, C0, (const float*)src1, C1, (const float*)wgt, Cout, (float*)out, scale,
+                       shift, relu, (cudaStream_t)stream);
+  if (dtype == DCB_BF16)
+    return run_tc_fwd(g, src0, C0, src1, C1, wgt, Cout, out, scale, shift, relu, (cudaStream_t)stream);
+  return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+}
+
+extern "C" int dcb_convT2x2_fwd(int dtype, const void* src, int Cin, int N, int h, int w, const void* wgt, int Cout,
+                                const float* scale, const float* shift, int relu, void* out, dcb_stream_t stream) {
+  DCB_CHECK_ARG(src && wgt && out && N > 0 && h > 0 && w > 0 && Cin > 0 && Cout > 0, "dcb_convT2x2_fwd: bad arguments");
+  TapGeom g;
+  geom_convT_fwd(g, N, h, w);
+  if (dtype == DCB_F32)
+    return run_f32_fwd(g, (const float*)src, Cin, nullptr, 0, (const float*)wgt, Cout, (float*)out, scale, shift, relu,
+                       (cudaStream_t)stream);
+  if (dtype == DCB_BF16)
+    return run_tc_fwd(g, src, Cin, nullptr, 0, wgt, Cout, out, scale, shift, relu, (cudaStream_t)stream);
+  return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+}
+
+extern "C" int dcb_convT2x2_dgrad(int dtype, const void* dy, int Cout, int N, int h, int w, const void* wgt, int Cin,
+                                  void* dx, dcb_stream_t stream) {
+  DCB_CHECK_ARG(dy && wgt && dx && N > 0 && h > 0 && w > 0 && Cin > 0 && Cout > 0, "dcb_convT2x2_dgrad: bad arguments");
+  TapGeom g;
+  geom_convT_dgrad(g, N, h, w);
+  if (dtype == DCB_F32)
+    return run_f32_fwd(g, (const float*)dy, Cout, nullptr, 0, (const float*)wgt, Cin, (float*)dx, nullptr, nullptr, 0,
+                       (cudaStream_t)stream);
+  if (dtype == DCB_BF16)
+    return run_tc_fwd(g, dy, Cout, nullptr, 0, wgt, Cin, dx, nullptr, nullptr, 0, (cudaStream_t)stream);
+  return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+}
+
+extern "C" int dcb_conv3x3_wgrad_workspace_bytes(int dtype, int N, int H, int W, int Cin, int Cout, size_t* bytes) {
+  DCB_CHECK_ARG(bytes && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "dcb_conv3x3_wgrad_workspace_bytes: bad arguments");
+  TapGeom g;
+  geom_conv3x3(g, N, H, W);
+  if (dtype == DCB_F32) *bytes = (size_t)f32_wgrad_splits(g, Cin, Cout) * 9 * Cin * Cout * sizeof(float);
+  else *bytes = tc_wgrad_workspace(g, Cin, Cout);
+  return DCB_OK;
+}
+
+extern "C" int dcb_conv3x3_wgrad(int dtype, const void* src0, int C0, const void* src1, int C1, int N, int H, int W,
+                                 const void* dy, int Cout, float* dW, void* ws, size_t ws_bytes, dcb_stream_t stream) {
+  DCB_CHECK_ARG(src0 && dy && dW && N > 0 && H > 0 && W > 0 && C0 > 0 && C1 >= 0 && Cout > 0 && (C1 == 0 || src1),
+                "dcb_conv3x3_wgrad: bad arguments");
+  TapGeom g;
+  geom_conv3x3(g, N, H, W);
+  if (dtype == DCB_F32)
+    return run_f32_wgrad(g, (const float*)src0, C0, (const float*)src1, C1, (const float*)dy, Cout, dW, ws, ws_bytes,
+                         (cudaStream_t)stream);
+  if (dtype == DCB_BF16) return run_tc_wgrad(g, src0, C0, src1, C1, dy, Cout, dW, ws, ws_bytes, (cudaStream_t)stream);
+  return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+}
+
+extern "C" int dcb_convT2x2_wgrad_workspace_bytes(int dtype, int N, int h, int w, int Cin, int Cout, size_t* bytes) {
+  DCB_CHECK_ARG(bytes && N > 0 && h > 0 && w > 0 && Cin > 0 && Cout > 0, "dcb_convT2x2_wgrad_workspace_bytes: bad arguments");
+  TapGeom g;
+  geom_convT_dgrad(g, N, h, w);
+  if (dtype == DCB_F32) *bytes = (size_t)f32_wgrad_splits(g, Cout, Cin) * 4 * Cin * Cout * sizeof(float);
+  else *bytes = tc_wgrad_workspace(g, Cout, Cin);
+  return DCB_OK;
+}
+
+// dW[a,b][co][ci] = sum_{n,i,j} dy[n,2i+a,2j+b,co] * x[n,i,j,ci]: the gathered operand is dy, the
+// per-position operand is x
+extern "C" int dcb_convT2x2_wgrad(int dtype, const void* x, int Cin, int N, int h, int w, const void* dy, int Cout,
+                                  float* dW, void* ws, size_t ws_bytes, dcb_stream_t stream) {
+  DCB_CHECK_ARG(x && dy && dW && N > 0 && h > 0 && w > 0 && Cin > 0 && Cout > 0, "dcb_convT2x2_wgrad: bad arguments");
+  TapGeom g;
+  geom_convT_dgrad(g, N, h, w);
+  if (dtype == DCB_F32)
+    return run_f32_wgrad(g, (const float*)dy, Cout, nullptr, 0, (const float*)x, Cin, dW, ws, ws_bytes,
+                         (cudaStream_t)stream);
+  if (dtype == DCB_BF16) return run_tc_wgrad(g, dy, Cout, nullptr, 0, x, Cin, dW, ws, ws_bytes, (cudaStream_t)stream);
+  return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+}

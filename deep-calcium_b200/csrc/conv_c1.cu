@@ -1,0 +1,142 @@
+// First layer of the U-Net: Conv2D(3x3,'same') on the 1-channel summary image
+// (unet_2d_summary.py:169-172).  K = 9 is far too small for the tensor pipe; the layer is
+// bound by writing its [N,H,W,Cout] output, so it runs on CUDA cores: one thread per pixel,
+// weights broadcast from shared memory, 16-byte coalesced stores.
+#include "elementwise.cuh"
+
+namespace dcb {
+extern unsigned long long g_launches;
+void launch_reduce_splits(const float* part, int splits, size_t n, float* out, cudaStream_t st);
+
+template <typename T, int COUT>
+__global__ void __launch_bounds__(256)
+conv3x3_c1_fwd_kernel(const float* __restrict__ x, int N, int H, int W, const float* __restrict__ w,
+                      const float* __restrict__ scale, const float* __restrict__ shift, int relu, T* __restrict__ out) {
+  __shared__ float ws[9 * COUT];
+  __shared__ float sc[COUT], sh[COUT];
+  for (int i = threadIdx.x; i < 9 * COUT; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) { sc[i] = scale ? scale[i] : 1.f; sh[i] = shift ? shift[i] : 0.f; }
+  __syncthreads();
+  const long long M = (long long)N * H * W;
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    const int wq = (int)(m % W), hq = (int)((m / W) % H);
+    const float* img = x + (m - (long long)hq * W - wq);
+    float v[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int ih = hq + t / 3 - 1, iw = wq + t % 3 - 1;
+      v[t] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? img[(long long)ih * W + iw] : 0.f;
+    }
+#pragma unroll
+    for (int c0 = 0; c0 < COUT; c0 += 4) {
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = fmaf(v[t], ws[t * COUT + c0 + j], a[j]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a[j] = fmaf(a[j], sc[c0 + j], sh[c0 + j]);
+        if (relu) a[j] = fmaxf(a[j], 0.f);
+      }
+      store4<T>(out + m * COUT + c0, make_float4(a[0], a[1], a[2], a[3]));
+    }
+  }
+}
+
+// dW[t][co] = sum_pixels x[pixel + tap t] * dy[pixel][co]: lane = output channel (COUT <= 32 per pass),
+// a warp walks pixels; per-CTA partials then a fixed-order reduce.
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv3x3_c1_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, int N, int H, int W, int Cout,
+                        float* __restrict__ part) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long M = (long long)N * H * W;
+  const long long per_cta = (M + gridDim.x - 1) / gridDim.x;
+  const long long m0 = (long long)blockIdx.x * per_cta;
+  long long m1 = m0 + per_cta; if (m1 > M) m1 = M;
+  __shared__ float red[8][9][32];
+  for (int cbase = 0; cbase < Cout; cbase += 32) {
+    float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const int c = cbase + lane;
+    for (long long m = m0 + warp; m < m1; m += 8) {
+      const int wq = (int)(m % W), hq = (int)((m / W) % H);
+      const float* img = x + (m - (long long)hq * W - wq);
+      const float g = (c < Cout) ? to_f32<T>(dy[m * Cout + c]) : 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int ih = hq + t / 3 - 1, iw = wq + t % 3 - 1;
+        const float v = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? img[(long long)ih * W + iw] : 0.f;
+        acc[t] = fmaf(v, g, acc[t]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) red[warp][t][lane] = acc[t];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * 32; i += blockDim.x) {
+      const int t = i / 32, l = i % 32;
+      float s = 0.f;
+      for (int wv = 0; wv < 8; ++wv) s += red[wv][t][l];
+      if (cbase + l < Cout) part[((size_t)blockIdx.x * 9 + t) * Cout + cbase + l] = s;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace dcb
+
+using namespace dcb;
+
+template <typename T>
+static int launch_c1_fwd(const float* x, int N, int H, int W, const float* w, int Cout, const float* scale,
+                         const float* shift, int relu, T* out, cudaStream_t st) {
+  const long long M = (long long)N * H * W;
+  long long grid = (M + 255) / 256;
+  if (grid > (long long)sm_count() * 16) grid = (long long)sm_count() * 16;
+  switch (Cout) {
+    case 8: conv3x3_c1_fwd_kernel<T, 8><<<(int)grid, 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break;
+    case 16: conv3x3_c1_fwd_kernel<T, 16><<<(int)grid, 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break;
+    case 32: conv3x3_c1_fwd_kernel<T, 32><<<(int)grid, 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break;
+    case 64: conv3x3_c1_fwd_kernel<T, 64><<<(int)grid, 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break;
+    default: return fail(DCB_ERR_UNSUPPORTED, "dcb_conv3x3_c1_fwd: Cout=%d unsupported (8,16,32,64)", Cout);
+  }
+  g_launches += 1;
+  DCB_LAUNCH_OK("conv3x3_c1_fwd_kernel");
+  return DCB_OK;
+}
+
+extern "C" int dcb_conv3x3_c1_fwd(int dtype, const float* x, int N, int H, int W, const float* w, int Cout,
+                                  const float* scale, const float* shift, int relu, void* out, dcb_stream_t stream) {
+  DCB_CHECK_ARG(x && w && out && N > 0 && H > 0 && W > 0, "dcb_conv3x3_c1_fwd: bad arguments");
+  if (dtype == DCB_F32) return launch_c1_fwd<float>(x, N, H, W, w, Cout, scale, shift, relu, (float*)out, (cudaStream_t)stream);
+  if (dtype == DCB_BF16)
+    return launch_c1_fwd<__nv_bfloat16>(x, N, H, W, w, Cout, scale, shift, relu, (__nv_bfloat16*)out, (cudaStream_t)stream);
+  return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+}
+
+static int c1_wgrad_ctas() { return sm_count() * 4; }
+
+extern "C" int dcb_conv3x3_c1_wgrad_workspace_bytes(int Cout, size_t* bytes) {
+  DCB_CHECK_ARG(bytes && Cout > 0, "dcb_conv3x3_c1_wgrad_workspace_bytes: bad arguments");
+  *bytes = (size_t)c1_wgrad_ctas() * 9 * Cout * sizeof(float);
+  return DCB_OK;
+}
+
+extern "C" int dcb_conv3x3_c1_wgrad(int dtype, const float* x, const void* dy, int N, int H, int W, int Cout, float* dW,
+                                    void* ws, size_t ws_bytes, dcb_stream_t stream) {
+  DCB_CHECK_ARG(x && dy && dW && N > 0 && H > 0 && W > 0 && Cout > 0, "dcb_conv3x3_c1_wgrad: bad arguments");
+  const int grid = c1_wgrad_ctas();
+  const size_t need = (size_t)grid * 9 * Cout * sizeof(float);
+  if (!ws || ws_bytes < need) return fail(DCB_ERR_WORKSPACE, "dcb_conv3x3_c1_wgrad: workspace %zu B < %zu B", ws_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DCB_F32) conv3x3_c1_wgrad_kernel<float><<<grid, 256, 0, st>>>(x, (const float*)dy, N, H, W, Cout, (float*)ws);
+  else if (dtype == DCB_BF16)
+    conv3x3_c1_wgrad_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, (const __nv_bfloat16*)dy, N, H, W, Cout, (float*)ws);
+  else return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+  DCB_LAUNCH_OK("conv3x3_c1_wgrad_kernel");
+  const size_t n = (size_t)9 * Cout;
+  launch_reduce_splits((const float*)ws, grid, n, dW, st);
+  g_launches += 2;
+  DCB_LAUNCH_OK("reduce_splits_kernel");
+  return DCB_OK;
+}

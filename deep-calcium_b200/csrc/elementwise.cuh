@@ -1,0 +1,56 @@
+// Small device helpers shared by the memory-bound kernels.
+#pragma once
+#include "common.cuh"
+
+namespace dcb {
+
+template <typename T> __device__ __forceinline__ float4 load4(const T* p);
+template <> __device__ __forceinline__ float4 load4<float>(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+template <> __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, float4 v);
+template <> __device__ __forceinline__ void store4<float>(float* p, float4 v) {
+  *reinterpret_cast<float4*>(p) = v;
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// Philox4x32-10 counter-based RNG (Salmon et al. 2011); one call -> 4 x uint32.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0; key.y += W1;
+  }
+  return ctr;
+}
+
+// keep-mask scale for 4 consecutive elements starting at flat index `idx4*4`:
+// 1/keep if uniform >= p_drop else 0.   (seed, layer id) -> key; element index -> counter.
+__device__ __forceinline__ float4 dropout_scale4(unsigned long long seed, uint32_t layer, unsigned long long idx4,
+                                                 float p_drop) {
+  uint4 r = philox4x32_10(make_uint4((uint32_t)idx4, (uint32_t)(idx4 >> 32), layer, 0u),
+                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float inv = 1.f / (1.f - p_drop);
+  const float u0 = r.x * 2.3283064365386963e-10f, u1 = r.y * 2.3283064365386963e-10f;
+  const float u2 = r.z * 2.3283064365386963e-10f, u3 = r.w * 2.3283064365386963e-10f;
+  return make_float4(u0 >= p_drop ? inv : 0.f, u1 >= p_drop ? inv : 0.f, u2 >= p_drop ? inv : 0.f,
+                     u3 >= p_drop ? inv : 0.f);
+}
+
+}  // namespace dcb

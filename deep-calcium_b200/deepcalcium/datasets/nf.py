@@ -1,0 +1,146 @@
+"""Dataset preparation of the reference (deepcalcium/datasets/nf.py), hot-path part only:
+the per-pixel temporal mean / max projection of a movie (nf.py:115-130; twin loop at
+examples/neurons/unet2ds_sj.py:67-85) runs as one streaming CUDA kernel.
+
+``summarize_movie`` is the projection as a function (movie in, (mean, max) out);
+``make_dataset`` writes the reference's dataset schema (series/mean, series/max, masks/raw,
+masks/max, attr name, nf.py:39-44) into an ``.npz`` container (h5py is optional: when it is
+importable, ``*.hdf5`` / ``*.h5`` paths are read and written with the reference's layout).
+Neurofinder download / unzip / TIFF decode (nf.py:73-97, 126-127) are out of scope (no network).
+"""
+import logging
+import os
+
+import numpy as np
+
+from ..utils.runtime import funcname
+
+NEUROFINDER_NAMES = sorted([
+    'neurofinder.00.00', 'neurofinder.00.01', 'neurofinder.00.02', 'neurofinder.00.03', 'neurofinder.00.04',
+    'neurofinder.00.05', 'neurofinder.00.06', 'neurofinder.00.07', 'neurofinder.00.08', 'neurofinder.00.09',
+    'neurofinder.00.10', 'neurofinder.00.11', 'neurofinder.01.00', 'neurofinder.01.01', 'neurofinder.02.00',
+    'neurofinder.02.01', 'neurofinder.03.00', 'neurofinder.04.00', 'neurofinder.04.01',
+    'neurofinder.00.00.test', 'neurofinder.00.01.test', 'neurofinder.01.00.test', 'neurofinder.01.01.test',
+    'neurofinder.02.00.test', 'neurofinder.02.01.test', 'neurofinder.03.00.test', 'neurofinder.04.00.test',
+    'neurofinder.04.01.test'])
+
+
+def summarize_movie_device(movie_dev, floor_max_at_zero=False, variant=-1, t_splits=0, out=None, workspace=None):
+    """movie_dev: float32 CUDA tensor [T,H,W].  Returns (mean, max) float32 CUDA tensors [H,W]."""
+    import torch
+    from ..engine import ops
+    if movie_dev.dim() != 3:
+        raise ValueError('movie must be [T,H,W], got shape %s' % (tuple(movie_dev.shape),))
+    if movie_dev.shape[0] == 0:
+        raise ValueError('movie has no frames')
+    if movie_dev.dtype != torch.float32 or not movie_dev.is_cuda:
+        raise TypeError('summarize_movie_device needs a float32 CUDA tensor')
+    movie_dev = movie_dev.contiguous()
+    T, H, W = movie_dev.shape
+    if out is None:
+        out = (torch.empty(H, W, dtype=torch.float32, device=movie_dev.device),
+               torch.empty(H, W, dtype=torch.float32, device=movie_dev.device))
+    if workspace is None:
+        workspace = torch.empty(ops.proj_workspace_bytes(T, H, W), dtype=torch.uint8, device=movie_dev.device)
+    ops.proj_mean_max(movie_dev, out[0], out[1], workspace, floor_max_at_zero, variant, t_splits)
+    return out
+
+
+def summarize_movie(movie, floor_max_at_zero=False):
+    """Mean / max projection of a [T,H,W] movie given as a numpy array (any real dtype; the
+    reference's TIFF frames are int16, nf.py:121) -> (mean float32 [H,W], max float32 [H,W]).
+    ``floor_max_at_zero=True`` reproduces the reference's zero-initialised running max (nf.py:125)."""
+    import torch
+    from .. import _native as nat
+    nat.require_cuda()
+    movie = np.asarray(movie)
+    if movie.ndim != 3:
+        raise ValueError('movie must be [T,H,W], got shape %s' % (movie.shape,))
+    dev = torch.from_numpy(np.ascontiguousarray(movie, dtype=np.float32)).cuda()
+    mean, mx = summarize_movie_device(dev, floor_max_at_zero)
+    return mean.cpu().numpy(), mx.cpu().numpy()
+
+
+# ------------------------------------------------------------------ dataset container
+def _is_hdf5(path):
+    return path.endswith(('.hdf5', '.h5'))
+
+
+def open_dataset(path):
+    """Read a dataset file into a dict {'name', 'series/mean', 'series/max', 'masks/raw', ...}."""
+    if _is_hdf5(path):
+        try:
+            import h5py
+        except ImportError:
+            raise ImportError('reading %s needs h5py, which is not installed; use the .npz container '
+                              '(deepcalcium.datasets.nf.make_dataset)' % path)
+        out = {}
+        with h5py.File(path, 'r') as fp:
+            out['name'] = fp.attrs['name']
+            for grp in ('series', 'masks'):
+                if grp in fp:
+                    for k in fp[grp]:
+                        if k != 'raw' or grp == 'masks':
+                            out['%s/%s' % (grp, k)] = fp[grp][k][...]
+        return out
+    with np.load(path, allow_pickle=False) as z:
+        out = {k.replace('__', '/'): z[k] for k in z.files}
+    out['name'] = str(out['name'])
+    return out
+
+
+def make_dataset(path, name, movie=None, mean=None, mx=None, masks=None):
+    """Write the reference's dataset schema.  Either ``movie`` ([T,H,W], projected on the GPU) or
+    precomputed ``mean``/``mx`` must be given.  series/mean is stored as float16 and series/max as
+    int16 like the reference (nf.py:122-125); masks/raw int8 [n,H,W], masks/max int8 [H,W]."""
+    if movie is not None:
+        mean, mx = summarize_movie(movie, floor_max_at_zero=True)
+    d = {'name': np.asarray(name), 'series__mean': np.asarray(mean).astype(np.float16),
+         'series__max': np.asarray(mx).astype(np.int16)}
+    if masks is not None:
+        masks = np.asarray(masks).astype(np.int8)
+        d['masks__raw'] = masks
+        d['masks__max'] = masks.max(axis=0)
+    if _is_hdf5(path):
+        import h5py
+        with h5py.File(path, 'w') as fp:
+            fp.attrs['name'] = name
+            for k, v in d.items():
+                if k != 'name':
+                    fp.create_dataset(k.replace('__', '/'), data=v)
+    else:
+        np.savez(path, **d)
+    return path
+
+
+def nf_load_hdf5(names, datasets_dir=None):
+    """Reference entry point (nf.py:37).  Downloading Neurofinder needs network access and TIFF /
+    HDF5 libraries that are outside this build's scope; datasets that were already prepared
+    (``<datasets_dir>/<name>/dataset.hdf5`` or ``dataset.npz``) are returned, otherwise an error
+    says what is missing."""
+    logger = logging.getLogger(funcname())
+    if datasets_dir is None:
+        from ..utils.config import DATASETS_DIR
+        datasets_dir = '%s/neurons_nf' % DATASETS_DIR
+    if isinstance(names, str) and names.lower() == 'all':
+        dataset_names = NEUROFINDER_NAMES
+    elif isinstance(names, str) and names.lower() == 'all_train':
+        dataset_names = sorted([n for n in NEUROFINDER_NAMES if '.test' not in n])
+    elif isinstance(names, str) and names.lower() == 'all_test':
+        dataset_names = sorted([n for n in NEUROFINDER_NAMES if '.test' in n])
+    elif isinstance(names, str):
+        dataset_names = names.split(',')
+    else:
+        dataset_names = names
+    paths = []
+    for name in dataset_names:
+        for fn in ('dataset.hdf5', 'dataset.npz'):
+            p = '%s/%s/%s' % (datasets_dir, name, fn)
+            if os.path.exists(p):
+                logger.info('%s already prepared.' % p)
+                paths.append(p)
+                break
+        else:
+            raise FileNotFoundError('%s/%s: no prepared dataset; download + TIFF decode (nf.py:73-127) are out '
+                                    'of scope here - build one with make_dataset()' % (datasets_dir, name))
+    return paths

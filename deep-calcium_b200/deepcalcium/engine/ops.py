@@ -1,0 +1,236 @@
+"""Thin torch-tensor wrappers over the dcb200 C ABI (include/dcb200.h).
+
+torch is plumbing here: it owns device memory and the current stream; every
+arithmetic op below is one call into libdcb200.so.  Nothing falls back to torch
+or numpy arithmetic.
+"""
+import ctypes
+
+import torch
+
+from .. import _native as nat
+from .._native import c_int, c_ll, c_f, c_p, c_sz, ptr, stream_ptr, call
+
+DT = {torch.float32: nat.DCB_F32, torch.bfloat16: nat.DCB_BF16}
+c_ull = ctypes.c_ulonglong
+c_uint = ctypes.c_uint
+
+
+def _dt(t):
+    return c_int(DT[t.dtype])
+
+
+def _chk(t, dtype=None):
+    assert t.is_cuda and t.is_contiguous(), 'dcb ops need contiguous CUDA tensors'
+    if dtype is not None:
+        assert t.dtype == dtype, (t.dtype, dtype)
+    return t
+
+
+# ---------------------------------------------------------------- projection (nf.py:115-130)
+def proj_workspace_bytes(T, H, W):
+    out = c_sz(0)
+    call('dcb_proj_workspace_bytes', c_int(T), c_int(H), c_int(W), ctypes.byref(out))
+    return out.value
+
+
+def proj_mean_max(movie, mean, mx, workspace, floor_max_at_zero=False, variant=-1, t_splits=0):
+    _chk(movie, torch.float32); _chk(mean, torch.float32); _chk(mx, torch.float32)
+    T, H, W = movie.shape
+    call('dcb_proj_mean_max_f32_variant', ptr(movie), c_int(T), c_int(H), c_int(W), ptr(mean), ptr(mx),
+         c_int(int(floor_max_at_zero)), ptr(workspace),
+         c_sz(workspace.numel() * workspace.element_size() if workspace is not None else 0),
+         c_int(variant), c_int(t_splits), stream_ptr())
+
+
+def standardize(x, out, stats=None):
+    _chk(x, torch.float32); _chk(out, torch.float32)
+    call('dcb_standardize_f32', ptr(x), c_ll(x.numel()), ptr(out), ptr(stats), stream_ptr())
+
+
+# ---------------------------------------------------------------- contractions
+def conv3x3_fwd(src0, src1, wgt, out, scale=None, shift=None, relu=False):
+    N, H, W, C0 = src0.shape
+    C1 = 0 if src1 is None else src1.shape[3]
+    Cout = out.shape[3]
+    call('dcb_conv3x3_fwd', _dt(src0), ptr(src0), c_int(C0), ptr(src1), c_int(C1), c_int(N), c_int(H), c_int(W),
+         ptr(wgt), c_int(Cout), ptr(scale), ptr(shift), c_int(int(relu)), ptr(out), stream_ptr())
+
+
+def convT2x2_fwd(src, wgt, out, scale=None, shift=None, relu=False):
+    N, h, w, Cin = src.shape
+    Cout = out.shape[3]
+    call('dcb_convT2x2_fwd', _dt(src), ptr(src), c_int(Cin), c_int(N), c_int(h), c_int(w), ptr(wgt), c_int(Cout),
+         ptr(scale), ptr(shift), c_int(int(relu)), ptr(out), stream_ptr())
+
+
+def convT2x2_dgrad(dy, wgt, dx):
+    N, h, w, Cin = dx.shape
+    Cout = dy.shape[3]
+    call('dcb_convT2x2_dgrad', _dt(dy), ptr(dy), c_int(Cout), c_int(N), c_int(h), c_int(w), ptr(wgt), c_int(Cin),
+         ptr(dx), stream_ptr())
+
+
+def conv3x3_wgrad_workspace_bytes(dtype, N, H, W, Cin, Cout):
+    out = c_sz(0)
+    call('dcb_conv3x3_wgrad_workspace_bytes', c_int(DT[dtype]), c_int(N), c_int(H), c_int(W), c_int(Cin), c_int(Cout),
+         ctypes.byref(out))
+    return out.value
+
+
+def conv3x3_wgrad(src0, src1, dy, dW, workspace):
+    N, H, W, C0 = src0.shape
+    C1 = 0 if src1 is None else src1.shape[3]
+    Cout = dy.shape[3]
+    _chk(dW, torch.float32)
+    call('dcb_conv3x3_wgrad', _dt(src0), ptr(src0), c_int(C0), ptr(src1), c_int(C1), c_int(N), c_int(H), c_int(W),
+         ptr(dy), c_int(Cout), ptr(dW), ptr(workspace), c_sz(workspace.numel() * workspace.element_size()), stream_ptr())
+
+
+def convT2x2_wgrad_workspace_bytes(dtype, N, h, w, Cin, Cout):
+    out = c_sz(0)
+    call('dcb_convT2x2_wgrad_workspace_bytes', c_int(DT[dtype]), c_int(N), c_int(h), c_int(w), c_int(Cin), c_int(Cout),
+         ctypes.byref(out))
+    return out.value
+
+
+def convT2x2_wgrad(x, dy, dW, workspace):
+    N, h, w, Cin = x.shape
+    Cout = dy.shape[3]
+    call('dcb_convT2x2_wgrad', _dt(x), ptr(x), c_int(Cin), c_int(N), c_int(h), c_int(w), ptr(dy), c_int(Cout), ptr(dW),
+         ptr(workspace), c_sz(workspace.numel() * workspace.element_size()), stream_ptr())
+
+
+def conv3x3_c1_fwd(x, w, out, scale=None, shift=None, relu=False):
+    """x: fp32 [N,H,W]; w: fp32 [3,3,1,Cout]; out: [N,H,W,Cout] in the activation dtype."""
+    _chk(x, torch.float32); _chk(w, torch.float32)
+    N, H, W = x.shape
+    call('dcb_conv3x3_c1_fwd', _dt(out), ptr(x), c_int(N), c_int(H), c_int(W), ptr(w), c_int(out.shape[3]),
+         ptr(scale), ptr(shift), c_int(int(relu)), ptr(out), stream_ptr())
+
+
+def conv3x3_c1_wgrad_workspace_bytes(Cout):
+    out = c_sz(0)
+    call('dcb_conv3x3_c1_wgrad_workspace_bytes', c_int(Cout), ctypes.byref(out))
+    return out.value
+
+
+def conv3x3_c1_wgrad(x, dy, dW, workspace):
+    N, H, W = x.shape
+    call('dcb_conv3x3_c1_wgrad', _dt(dy), ptr(x), ptr(dy), c_int(N), c_int(H), c_int(W), c_int(dy.shape[3]), ptr(dW),
+         ptr(workspace), c_sz(workspace.numel() * workspace.element_size()), stream_ptr())
+
+
+def prep_conv3x3_weights(w, w_fwd, w_dgrad, dtype):
+    _chk(w, torch.float32)
+    Cin, Cout = w.shape[2], w.shape[3]
+    call('dcb_prep_conv3x3_weights', c_int(DT[dtype]), ptr(w), c_int(Cin), c_int(Cout), ptr(w_fwd), ptr(w_dgrad),
+         stream_ptr())
+
+
+def prep_convT2x2_weights(w, w_fwd, w_dgrad, dtype):
+    _chk(w, torch.float32)
+    Cout, Cin = w.shape[2], w.shape[3]
+    call('dcb_prep_convT2x2_weights', c_int(DT[dtype]), ptr(w), c_int(Cin), c_int(Cout), ptr(w_fwd), ptr(w_dgrad),
+         stream_ptr())
+
+
+# ---------------------------------------------------------------- BatchNorm
+def bn_fold(gamma, beta, mean, var, bias, scale, shift, eps=1e-3):
+    call('dcb_bn_fold', ptr(gamma), ptr(beta), ptr(mean), ptr(var), ptr(bias), c_int(gamma.numel()), c_f(eps),
+         ptr(scale), ptr(shift), stream_ptr())
+
+
+def bn_stats(x, sums):
+    C = x.shape[-1]
+    call('dcb_bn_stats', _dt(x), ptr(x), c_ll(x.numel() // C), c_int(C), ptr(sums), stream_ptr())
+
+
+def bn_finalize(sums, M, gamma, beta, momentum, moving_mean, moving_var, scale, shift, mean, rstd, eps=1e-3):
+    call('dcb_bn_finalize', ptr(sums), c_ll(M), c_int(gamma.numel()), ptr(gamma), ptr(beta), c_f(eps), c_f(momentum),
+         ptr(moving_mean), ptr(moving_var), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), stream_ptr())
+
+
+def bn_apply(x, scale, shift, y, relu=True, p_drop=0., seed=0, seed_dev=None, layer=0):
+    C = x.shape[-1]
+    call('dcb_bn_apply', _dt(x), ptr(x), c_ll(x.numel() // C), c_int(C), ptr(scale), ptr(shift), c_int(int(relu)),
+         c_f(p_drop), c_ull(seed), ptr(seed_dev), c_uint(layer), ptr(y), stream_ptr())
+
+
+def bn_bwd_reduce(dy, ldy, offy, x, scale, shift, mean, rstd, sums, p_drop=0., seed=0, seed_dev=None, layer=0):
+    C = x.shape[-1]
+    call('dcb_bn_bwd_reduce', _dt(x), ptr(dy), c_int(ldy), c_int(offy), ptr(x), c_ll(x.numel() // C), c_int(C),
+         ptr(scale), ptr(shift), ptr(mean), ptr(rstd), c_f(p_drop), c_ull(seed), ptr(seed_dev), c_uint(layer),
+         ptr(sums), stream_ptr())
+
+
+def bn_bwd_apply(dy, ldy, offy, x, scale, shift, mean, rstd, sums, draw, dgamma, dbeta, p_drop=0., seed=0,
+                 seed_dev=None, layer=0):
+    C = x.shape[-1]
+    call('dcb_bn_bwd_apply', _dt(x), ptr(dy), c_int(ldy), c_int(offy), ptr(x), c_ll(x.numel() // C), c_int(C),
+         ptr(scale), ptr(shift), ptr(mean), ptr(rstd), c_f(p_drop), c_ull(seed), ptr(seed_dev), c_uint(layer),
+         ptr(sums), ptr(draw), ptr(dgamma), ptr(dbeta), stream_ptr())
+
+
+# ---------------------------------------------------------------- pooling
+def maxpool2x2(x, y):
+    N, H, W, C = x.shape
+    call('dcb_maxpool2x2', _dt(x), ptr(x), c_int(N), c_int(H), c_int(W), c_int(C), ptr(y), stream_ptr())
+
+
+def pool_bwd_add(skipgrad, lds, offs, y, pooled, dpool, out):
+    N, H, W, C = y.shape
+    call('dcb_pool_bwd_add', _dt(y), ptr(skipgrad), c_int(lds), c_int(offs), ptr(y), ptr(pooled), ptr(dpool),
+         c_int(N), c_int(H), c_int(W), c_int(C), ptr(out), stream_ptr())
+
+
+# ---------------------------------------------------------------- head / loss
+def head_fwd(x, w, b, logit, prob):
+    C = x.shape[-1]
+    call('dcb_head_fwd', _dt(x), ptr(x), c_ll(x.numel() // C), c_int(C), ptr(w), ptr(b), ptr(logit), ptr(prob),
+         stream_ptr())
+
+
+def head_loss_fwd(x, w, b, yt, prob, sums):
+    C = x.shape[-1]
+    _chk(yt, torch.uint8)
+    call('dcb_head_loss_fwd', _dt(x), ptr(x), c_ll(x.numel() // C), c_int(C), ptr(w), ptr(b), ptr(yt), ptr(prob),
+         ptr(sums), stream_ptr())
+
+
+def head_loss_bwd(x, w, yt, prob, sums, loss_id, dx, dwb_accum, dw_out, metrics_out):
+    C = x.shape[-1]
+    call('dcb_head_loss_bwd', _dt(x), ptr(x), c_ll(x.numel() // C), c_int(C), ptr(w), ptr(yt), ptr(prob), ptr(sums),
+         c_int(loss_id), ptr(dx), ptr(dwb_accum), ptr(dw_out), ptr(metrics_out), stream_ptr())
+
+
+# ---------------------------------------------------------------- TTA
+def tta_make_batch(s, S, first, count, out):
+    _chk(s, torch.float32)
+    hs, ws = s.shape
+    call('dcb_tta_make_batch', _dt(out), ptr(s), c_int(hs), c_int(ws), c_int(S), c_int(first), c_int(count), ptr(out),
+         stream_ptr())
+
+
+def tta_combine(probs, S, hs, ws, threshold, n_aug, act, mask):
+    _chk(probs, torch.float32); _chk(mask, torch.uint8)
+    call('dcb_tta_combine', ptr(probs), c_int(S), c_int(hs), c_int(ws), c_f(threshold), c_int(n_aug), ptr(act),
+         ptr(mask), stream_ptr())
+
+
+# ---------------------------------------------------------------- optimiser
+def adam_step(p, g, m, v, lr_t=0., lr_t_dev=None, beta1=0.9, beta2=0.999, eps=1e-8):
+    call('dcb_adam_step', ptr(p), ptr(g), ptr(m), ptr(v), c_ll(p.numel()), c_f(lr_t), ptr(lr_t_dev), c_f(beta1),
+         c_f(beta2), c_f(eps), stream_ptr())
+
+
+def step_advance(state, lr, beta1, beta2, lr_t_out):
+    call('dcb_step_advance', ptr(state), c_f(lr), c_f(beta1), c_f(beta2), ptr(lr_t_out), stream_ptr())
+
+
+def cast_from_f32(x, out):
+    call('dcb_cast_from_f32', _dt(out), ptr(x), c_ll(x.numel()), ptr(out), stream_ptr())
+
+
+def cast_to_f32(x, out):
+    call('dcb_cast_to_f32', _dt(x), ptr(x), c_ll(x.numel()), ptr(out), stream_ptr())

@@ -1,0 +1,420 @@
+"""Executor of the UNet2DS graph on one B200: sequences libdcb200 kernels for inference
+(BatchNorm folded into the conv epilogues, optional 8x TTA) and for one Keras-style
+``train_on_batch`` (batch-statistic BatchNorm, dropout, loss, backward, Adam), each
+captured once into a CUDA graph and replayed.
+
+Reference behaviour: deepcalcium/models/neurons/unet_2d_summary.py:123-224 (graph),
+:429 (fit_generator -> train_on_batch), :585-595 (predict with TTA).
+torch only owns memory / streams / graphs here; there is no torch arithmetic on the path.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from .. import _native as nat
+from . import ops
+from .graph import GraphSpec, BN_EPS, BN_MOMENTUM_CONV, BN_MOMENTUM_UP, TRAINABLE, he_normal_weights
+
+_PRECISIONS = {'bf16': torch.bfloat16, 'fp32': torch.float32, 'f32': torch.float32}
+
+
+def _align4(n):
+    return (n + 3) // 4 * 4
+
+
+class UNetEngine(object):
+    def __init__(self, spec=None, precision='bf16', device=None, use_graphs=True):
+        nat.require_cuda()
+        self.spec = spec or GraphSpec()
+        if self.spec.up_mode != 'transpose':
+            raise NotImplementedError("upsampling_or_transpose='upsampling' is not built yet; the reference "
+                                      "default 'transpose' (unet_2d_summary.py:124) is")
+        self.dtype = _PRECISIONS[precision]
+        self.precision = 'bf16' if self.dtype == torch.bfloat16 else 'fp32'
+        self.dev = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
+        self.use_graphs = use_graphs
+        self._build_param_storage()
+        self._build_derived()
+        self._inputs = self._wire()
+        self._weights_dirty = True
+        self._sessions = {}
+        self.iteration = 0
+        self.launches = 0
+        self.set_weights_dict(he_normal_weights(self.spec, seed=0))
+
+    # ------------------------------------------------------------------ parameter storage
+    def _build_param_storage(self):
+        off_t, off_n = 0, 0
+        self._slots = OrderedDict()        # key -> (trainable?, offset, shape)
+        for blk in self.spec.blocks:
+            for p, shp in blk.param_shapes().items():
+                n = int(np.prod(shp))
+                if p in TRAINABLE:
+                    self._slots['%s/%s' % (blk.name, p)] = (True, off_t, shp)
+                    off_t += _align4(n)
+                else:
+                    self._slots['%s/%s' % (blk.name, p)] = (False, off_n, shp)
+                    off_n += _align4(n)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.params = torch.zeros(off_t, **f32)
+        self.grads = torch.zeros(off_t, **f32)
+        self.adam_m = torch.zeros(off_t, **f32)
+        self.adam_v = torch.zeros(off_t, **f32)
+        self.nontrain = torch.zeros(max(off_n, 4), **f32)
+        self.P, self.G = OrderedDict(), OrderedDict()
+        for key, (tr, off, shp) in self._slots.items():
+            n = int(np.prod(shp))
+            base = self.params if tr else self.nontrain
+            self.P[key] = base[off:off + n].view(*shp)
+            if tr:
+                self.G[key] = self.grads[off:off + n].view(*shp)
+        # device-resident step state {iteration, dropout seed} and lr_t (see dcb_step_advance)
+        self.step_state = torch.zeros(2, dtype=torch.int64, device=self.dev)
+        self.lr_t = torch.zeros(1, **f32)
+
+    def _build_derived(self):
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        T = dict(dtype=self.dtype, device=self.dev)
+        self.w_fwd, self.w_dgrad = {}, {}
+        self.inf_scale, self.inf_shift = {}, {}
+        self.bn = {}
+        n_dbl = 0
+        for blk in self.spec.blocks:
+            if blk.kind == 'head':
+                continue
+            nk = int(np.prod(blk.kernel_shape()))
+            k = self.P[blk.name + '/kernel']
+            if blk.kind == 'conv':
+                if blk.cin == 1 and self.dtype == torch.bfloat16:
+                    self.w_fwd[blk.name] = k                     # c1 kernel reads the fp32 master
+                    self.w_dgrad[blk.name] = None
+                elif self.dtype == torch.float32:
+                    self.w_fwd[blk.name] = k                     # fp32 layout == Keras HWIO
+                    self.w_dgrad[blk.name] = torch.empty(nk, **T) if blk.cin > 1 else None
+                else:
+                    self.w_fwd[blk.name] = torch.empty(nk, **T)
+                    self.w_dgrad[blk.name] = torch.empty(nk, **T)
+            else:
+                if self.dtype == torch.float32:
+                    self.w_fwd[blk.name] = torch.empty(nk, **T)
+                    self.w_dgrad[blk.name] = k                   # fp32 dgrad layout == Keras (2,2,Cout,Cin)
+                else:
+                    self.w_fwd[blk.name] = torch.empty(nk, **T)
+                    self.w_dgrad[blk.name] = torch.empty(nk, **T)
+            self.inf_scale[blk.name] = torch.empty(blk.cout, **f32)
+            self.inf_shift[blk.name] = torch.empty(blk.cout, **f32)
+            self.bn[blk.name] = dict(scale=torch.empty(blk.cout, **f32), shift=torch.empty(blk.cout, **f32),
+                                     mean=torch.empty(blk.cout, **f32), rstd=torch.empty(blk.cout, **f32),
+                                     off_f=n_dbl, off_b=n_dbl + 2 * blk.cout)
+            n_dbl += 4 * blk.cout
+        self._off_head_sums = n_dbl
+        self._off_head_dwb = n_dbl + 8
+        n_dbl += 8 + 2 * self.spec.nfb + 2
+        self.dbl = torch.zeros(n_dbl, dtype=torch.float64, device=self.dev)
+        self.metrics = torch.zeros(8, **f32)
+        self._wgrad_ws = None
+
+    def _wire(self):
+        inp = OrderedDict()
+        inp['enc0a'] = ('x', None); inp['enc0b'] = ('enc0a', None)
+        for l in (1, 2, 3):
+            inp['enc%da' % l] = ('pool%d' % (l - 1), None); inp['enc%db' % l] = ('enc%da' % l, None)
+        inp['bota'] = ('pool3', None); inp['botb'] = ('bota', None)
+        prev = 'botb'
+        for l in (3, 2, 1, 0):
+            inp['up%d' % l] = (prev, None)
+            inp['dec%da' % l] = ('up%d' % l, 'enc%db' % l)
+            inp['dec%db' % l] = ('dec%da' % l, None)
+            prev = 'dec%db' % l
+        inp['head'] = ('dec0b', None)
+        return inp
+
+    # ------------------------------------------------------------------ weights in / out (Keras layouts)
+    def set_weights_dict(self, w):
+        for key, (tr, off, shp) in self._slots.items():
+            a = np.ascontiguousarray(np.asarray(w[key], dtype=np.float32))
+            if tuple(a.shape) != tuple(shp):
+                raise ValueError('weight %s: expected shape %s, got %s' % (key, shp, a.shape))
+            self.P[key].copy_(torch.from_numpy(a))
+        self._weights_dirty = True
+
+    def get_weights_dict(self):
+        torch.cuda.synchronize(self.dev)
+        return OrderedDict((key, self.P[key].detach().cpu().numpy().copy()) for key in self._slots)
+
+    def reset_optimizer(self):
+        self.adam_m.zero_(); self.adam_v.zero_()
+        self.step_state.zero_()
+        self.iteration = 0
+
+    def _prepare_weights(self, for_training):
+        """fold BN for inference and (re)build the kernel-layout weight copies."""
+        for blk in self.spec.blocks:
+            if blk.kind == 'head':
+                continue
+            n = blk.name
+            k = self.P[n + '/kernel']
+            if blk.kind == 'conv':
+                wf = self.w_fwd[n] if self.w_fwd[n] is not k else None
+                wd = self.w_dgrad[n] if for_training else None
+                if wf is not None or wd is not None:
+                    ops.prep_conv3x3_weights(k, wf, wd, self.dtype)
+            else:
+                wf = self.w_fwd[n]
+                wd = self.w_dgrad[n] if (for_training and self.w_dgrad[n] is not k) else None
+                ops.prep_convT2x2_weights(k, wf, wd, self.dtype)
+            if not for_training:
+                ops.bn_fold(self.P[n + '/gamma'], self.P[n + '/beta'], self.P[n + '/moving_mean'],
+                            self.P[n + '/moving_var'], self.P[n + '/bias'], self.inf_scale[n], self.inf_shift[n], BN_EPS)
+
+    # ------------------------------------------------------------------ activation buffers
+    def _session(self, NB, H, W, training):
+        key = (NB, H, W, training)
+        s = self._sessions.get(key)
+        if s is not None:
+            return s
+        if H % 16 or W % 16:
+            raise ValueError('window %dx%d must be a multiple of 16 (four 2x2 poolings)' % (H, W))
+        T = dict(dtype=self.dtype, device=self.dev)
+        s = dict(NB=NB, H=H, W=W, training=training, act={}, raw={}, dx={}, graph=None, tta_graphs={})
+        s['x'] = torch.zeros(NB, H, W, dtype=torch.float32, device=self.dev)
+        if self.dtype == torch.float32:
+            s['act']['x'] = s['x'].view(NB, H, W, 1)
+        for blk in self.spec.blocks:
+            if blk.kind == 'head':
+                continue
+            h, w = H >> blk.level, W >> blk.level
+            s['act'][blk.name] = torch.empty(NB, h, w, blk.cout, **T)
+            if training:
+                s['raw'][blk.name] = torch.empty(NB, h, w, blk.cout, **T)
+                if blk.name != 'enc0a':
+                    if blk.kind == 'conv':
+                        s['dx'][blk.name] = torch.empty(NB, h, w, blk.cin, **T)
+                    else:
+                        s['dx'][blk.name] = torch.empty(NB, h // 2, w // 2, blk.cin, **T)
+        for l in range(4):
+            c = self.spec.nfb << l
+            s['act']['pool%d' % l] = torch.empty(NB, H >> (l + 1), W >> (l + 1), c, **T)
+            if training:
+                s['dx']['skip%d' % l] = torch.empty(NB, H >> l, W >> l, c, **T)
+        s['logit'] = torch.empty(NB, H, W, dtype=torch.float32, device=self.dev)
+        s['prob'] = torch.empty(NB, H, W, dtype=torch.float32, device=self.dev)
+        if training:
+            s['y'] = torch.zeros(NB, H, W, dtype=torch.uint8, device=self.dev)
+            s['dhead'] = torch.empty(NB, H, W, self.spec.nfb, **T)
+            need = 0
+            for blk in self.spec.blocks:
+                h, w = H >> blk.level, W >> blk.level
+                if blk.kind == 'conv':
+                    if blk.cin == 1 and self.dtype == torch.bfloat16:
+                        need = max(need, ops.conv3x3_c1_wgrad_workspace_bytes(blk.cout))
+                    else:
+                        need = max(need, ops.conv3x3_wgrad_workspace_bytes(self.dtype, NB, h, w, blk.cin, blk.cout))
+                elif blk.kind == 'up':
+                    need = max(need, ops.convT2x2_wgrad_workspace_bytes(self.dtype, NB, h // 2, w // 2, blk.cin, blk.cout))
+            if self._wgrad_ws is None or self._wgrad_ws.numel() < need:
+                self._wgrad_ws = torch.empty(max(need, 16), dtype=torch.uint8, device=self.dev)
+        self._sessions[key] = s
+        return s
+
+    # ------------------------------------------------------------------ inference
+    def _forward_inference(self, s):
+        """enqueue the forward pass reading s['x'] (fp32 [NB,H,W]); writes s['logit'], s['prob']."""
+        act = s['act']
+        for blk in self.spec.blocks:
+            n = blk.name
+            if blk.kind == 'head':
+                ops.head_fwd(act['dec0b'], self.P['head/kernel'], self.P['head/bias'], s['logit'], s['prob'])
+                continue
+            a, b = self._inputs[n]
+            sc, sh = self.inf_scale[n], self.inf_shift[n]
+            if blk.kind == 'conv':
+                if blk.cin == 1 and self.dtype == torch.bfloat16:
+                    ops.conv3x3_c1_fwd(s['x'], self.w_fwd[n], act[n], sc, sh, True)
+                else:
+                    ops.conv3x3_fwd(act[a], act[b] if b else None, self.w_fwd[n], act[n], sc, sh, True)
+            else:
+                ops.convT2x2_fwd(act[a], self.w_fwd[n], act[n], sc, sh, True)
+            if n in ('enc0b', 'enc1b', 'enc2b', 'enc3b'):
+                ops.maxpool2x2(act[n], act['pool%d' % blk.level])
+
+    def _ensure_inference_ready(self):
+        if self._weights_dirty:
+            self._prepare_weights(for_training=False)
+            self._weights_dirty = False
+
+    def _run_graphed(self, holder, key, fn):
+        """run fn() through a CUDA graph cached in holder[key] (first call: eager warm-up then capture)."""
+        # Every call executes fn's work exactly once (a training step mutates state):
+        # call 1 runs eagerly (also builds the TMA descriptor caches), call 2 captures and replays,
+        # later calls replay.
+        # self.launches counts the library's kernel launches including those replayed from graphs.
+        c0 = nat.launch_count()
+        if not self.use_graphs:
+            fn()
+            self.launches += nat.launch_count() - c0
+            return
+        g = holder.get(key)
+        if g is None:
+            fn()
+            self.launches += nat.launch_count() - c0
+            holder[key] = 'warm'
+            return
+        if isinstance(g, str):
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            g.dcb_launches = nat.launch_count() - c0
+            holder[key] = g
+        g.replay()
+        self.launches += g.dcb_launches
+
+    def infer(self, x_dev):
+        """x_dev: fp32 CUDA tensor [NB,H,W].  Returns (prob, logit) fp32 [NB,H,W] (views of static buffers)."""
+        NB, H, W = x_dev.shape
+        s = self._session(NB, H, W, False)
+        self._ensure_inference_ready()
+        s['x'].copy_(x_dev)
+        self._run_graphed(s, 'graph', lambda: self._forward_inference(s))
+        return s['prob'], s['logit']
+
+    def predict_tta(self, summ_dev, window=512, augmentation=True, threshold=0.5, transforms=None):
+        """unet_2d_summary.py:578-595 for one summary image already on the device (fp32 [hs,ws]).
+        Returns (mask uint8 [hs,ws], act float64 [hs,ws]) as device tensors (static buffers).
+        ``transforms`` = (first, count) restricts the batch to a slice of the 8 transforms and skips
+        the combine (multi-GPU sharding, returns the raw probabilities [count,S,S])."""
+        hs, ws = summ_dev.shape
+        n_aug = 8 if augmentation else 1
+        first, count = transforms if transforms is not None else (0, n_aug)
+        s = self._session(count, window, window, False)
+        self._ensure_inference_ready()
+        key = (hs, ws, n_aug, first, count, float(threshold), transforms is None)
+        st = s['tta_graphs'].get(('bufs',) + key)
+        if st is None:
+            st = dict(summ=torch.zeros(hs, ws, dtype=torch.float32, device=self.dev),
+                      mask=torch.zeros(hs, ws, dtype=torch.uint8, device=self.dev),
+                      act=torch.zeros(hs, ws, dtype=torch.float64, device=self.dev))
+            s['tta_graphs'][('bufs',) + key] = st
+        st['summ'].copy_(summ_dev)
+
+        def run():
+            ops.tta_make_batch(st['summ'], window, first, count, s['x'])
+            self._forward_inference(s)
+            if transforms is None:
+                ops.tta_combine(s['prob'], window, hs, ws, threshold, n_aug, st['act'], st['mask'])
+
+        self._run_graphed(s['tta_graphs'], key, run)
+        if transforms is not None:
+            return s['prob']
+        return st['mask'], st['act']
+
+    # ------------------------------------------------------------------ training
+    def _dropout_p(self, name, enabled):
+        return float(self.spec.dropout_after().get(name, 0.)) if enabled else 0.
+
+    def _train_step_enqueue(self, s, loss_id, lr, dropout, beta1, beta2, eps):
+        spec, act, raw, dxb = self.spec, s['act'], s['raw'], s['dx']
+        seed_dev = self.step_state[1:2]
+        ops.step_advance(self.step_state, lr, beta1, beta2, self.lr_t)
+        self.dbl.zero_()
+        self._prepare_weights(for_training=True)
+        layer_id = {blk.name: i for i, blk in enumerate(spec.blocks)}
+        # ---------------- forward (batch-statistic BN)
+        for blk in spec.blocks:
+            n = blk.name
+            if blk.kind == 'head':
+                continue
+            a, b = self._inputs[n]
+            bias = self.P[n + '/bias']
+            if blk.kind == 'conv':
+                if blk.cin == 1 and self.dtype == torch.bfloat16:
+                    ops.conv3x3_c1_fwd(s['x'], self.w_fwd[n], raw[n], None, bias, False)
+                else:
+                    ops.conv3x3_fwd(act[a], act[b] if b else None, self.w_fwd[n], raw[n], None, bias, False)
+                mom = BN_MOMENTUM_CONV
+            else:
+                ops.convT2x2_fwd(act[a], self.w_fwd[n], raw[n], None, bias, False)
+                mom = BN_MOMENTUM_UP
+            st = self.bn[n]
+            M = raw[n].numel() // blk.cout
+            sums = self.dbl[st['off_f']:st['off_f'] + 2 * blk.cout]
+            ops.bn_stats(raw[n], sums)
+            ops.bn_finalize(sums, M, self.P[n + '/gamma'], self.P[n + '/beta'], mom, self.P[n + '/moving_mean'],
+                            self.P[n + '/moving_var'], st['scale'], st['shift'], st['mean'], st['rstd'], BN_EPS)
+            ops.bn_apply(raw[n], st['scale'], st['shift'], act[n], True, self._dropout_p(n, dropout), 0, seed_dev,
+                         layer_id[n])
+            if n in ('enc0b', 'enc1b', 'enc2b', 'enc3b'):
+                ops.maxpool2x2(act[n], act['pool%d' % blk.level])
+        # ---------------- head + loss + its gradient
+        hs = self.dbl[self._off_head_sums:self._off_head_sums + 8]
+        hd = self.dbl[self._off_head_dwb:self._off_head_dwb + 2 * spec.nfb + 2]
+        ops.head_loss_fwd(act['dec0b'], self.P['head/kernel'], self.P['head/bias'], s['y'], s['prob'], hs)
+        # head kernel [1,1,C,2] and bias [2] are adjacent in the flat gradient buffer
+        off_k = self._slots['head/kernel'][1]
+        dw_out = self.grads[off_k:off_k + 2 * spec.nfb + 2]
+        assert self._slots['head/bias'][1] == off_k + 2 * spec.nfb
+        ops.head_loss_bwd(act['dec0b'], self.P['head/kernel'], s['y'], s['prob'], hs, loss_id, s['dhead'], hd, dw_out,
+                          self.metrics)
+        # ---------------- backward
+        grad_of = {'dec0b': (s['dhead'], spec.nfb, 0)}
+        skip_grad = {}
+        for blk in reversed(spec.blocks):
+            n = blk.name
+            if blk.kind == 'head':
+                continue
+            a, b = self._inputs[n]
+            dy, ldy, offy = grad_of[n]
+            st = self.bn[n]
+            sums = self.dbl[st['off_b']:st['off_b'] + 2 * blk.cout]
+            p = self._dropout_p(n, dropout)
+            ops.bn_bwd_reduce(dy, ldy, offy, raw[n], st['scale'], st['shift'], st['mean'], st['rstd'], sums, p, 0,
+                              seed_dev, layer_id[n])
+            draw = raw[n]      # in place: raw is dead after this point
+            ops.bn_bwd_apply(dy, ldy, offy, raw[n], st['scale'], st['shift'], st['mean'], st['rstd'], sums, draw,
+                             self.G[n + '/gamma'], self.G[n + '/beta'], p, 0, seed_dev, layer_id[n])
+            if blk.kind == 'conv':
+                if blk.cin == 1 and self.dtype == torch.bfloat16:
+                    ops.conv3x3_c1_wgrad(s['x'], draw, self.G[n + '/kernel'], self._wgrad_ws)
+                else:
+                    ops.conv3x3_wgrad(act[a], act[b] if b else None, draw, self.G[n + '/kernel'], self._wgrad_ws)
+                if n == 'enc0a':
+                    continue
+                dX = dxb[n]
+                ops.conv3x3_fwd(draw, None, self.w_dgrad[n], dX, None, None, False)
+                if b is not None:                       # concat [up, skip]
+                    c0 = act[a].shape[3]
+                    grad_of[a] = (dX, blk.cin, 0)
+                    skip_grad[b] = (dX, blk.cin, c0)
+                elif a.startswith('pool'):
+                    l = int(a[4:])
+                    enc = 'enc%db' % l
+                    sg, lds, offs = skip_grad[enc]
+                    out = dxb['skip%d' % l]
+                    ops.pool_bwd_add(sg, lds, offs, act[enc], act[a], dX, out)
+                    grad_of[enc] = (out, out.shape[3], 0)
+                else:
+                    grad_of[a] = (dX, blk.cin, 0)
+            else:
+                ops.convT2x2_wgrad(act[a], draw, self.G[n + '/kernel'], self._wgrad_ws)
+                dX = dxb[n]
+                ops.convT2x2_dgrad(draw, self.w_dgrad[n], dX)
+                grad_of[a] = (dX, blk.cin, 0)
+        # ---------------- Keras-form Adam over the flat parameter buffer
+        ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, 0., self.lr_t, beta1, beta2, eps)
+
+    def train_step(self, x_dev, y_dev, loss='dice_loss', lr=0.002, dropout=True, beta1=0.9, beta2=0.999, eps=1e-8):
+        """One train_on_batch.  x_dev fp32 [B,h,w], y_dev uint8 [B,h,w] on the device.
+        Returns the device tensor [loss, F1, prec, reca, dice, dicesq, posyt, posyp] (static buffer)."""
+        B, H, W = x_dev.shape
+        s = self._session(B, H, W, True)
+        s['x'].copy_(x_dev)
+        s['y'].copy_(y_dev)
+        loss_id = nat.LOSS_IDS[loss] if isinstance(loss, str) else int(loss)
+        key = ('train', loss_id, float(lr), bool(dropout), beta1, beta2, eps)
+        self._run_graphed(s['tta_graphs'], key,
+                          lambda: self._train_step_enqueue(s, loss_id, lr, dropout, beta1, beta2, eps))
+        self.iteration += 1
+        self._weights_dirty = True
+        return self.metrics

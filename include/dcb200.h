@@ -1,0 +1,183 @@
+/* dcb200 - C ABI of the B200-native deep-calcium UNet2DS hot path.
+ *
+ * Every entry point replaces one piece of arithmetic that the reference
+ * (alexklibisz/deep-calcium) delegates to numpy/h5py or Keras-2.0.6/TF-1.2.1;
+ * the reference file:line each one stands in for is cited on the declaration.
+ * Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     the parameter name starts with h_ ;
+ *   - the caller owns every buffer (including workspaces); the library keeps no
+ *     persistent device allocations; host-side it caches only shape-keyed TMA
+ *     descriptors;
+ *   - all work is enqueued on `stream` (a cudaStream_t), no host synchronisation,
+ *     CUDA-graph capturable;
+ *   - return 0 on success, a negative dcb_status otherwise; dcb_last_error()
+ *     gives the thread-local message of the last failure.
+ * Activations are NHWC; `dtype` selects fp32 ("check mode", CUDA-core kernels)
+ * or bf16 (tcgen05/TMEM/TMA kernels, fp32 accumulate).
+ */
+#ifndef DCB200_H_
+#define DCB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dcb_stream_t; /* cudaStream_t */
+
+enum dcb_status {
+  DCB_OK = 0,
+  DCB_ERR_INVALID_ARGUMENT = -1,
+  DCB_ERR_CUDA = -2,
+  DCB_ERR_WORKSPACE = -3,
+  DCB_ERR_UNSUPPORTED = -4
+};
+
+enum dcb_dtype { DCB_F32 = 0, DCB_BF16 = 1 };
+
+/* loss ids: unet_2d_summary.py:372-377 */
+enum dcb_loss { DCB_LOSS_BCE = 0, DCB_LOSS_WBCE = 1, DCB_LOSS_DICE = 2, DCB_LOSS_DICESQ = 3 };
+
+int dcb_version(void);
+const char* dcb_last_error(void);
+/* number of kernels this library has launched from the calling process (bench.py's gpu_launches) */
+unsigned long long dcb_launch_count(void);
+
+/* ---- a1: datasets/nf.py:115-130 (twin: examples/neurons/unet2ds_sj.py:67-85) ----
+ * Per-pixel temporal mean and max of movie[T][H][W] (float32).  mean/max are
+ * float32 [H][W].  floor_max_at_zero != 0 reproduces the reference's
+ * zero-initialised running max (nf.py:125,130).  Sums are float64 internally. */
+int dcb_proj_workspace_bytes(int T, int H, int W, size_t* bytes);
+int dcb_proj_mean_max_f32(const float* movie, int T, int H, int W, float* mean, float* max,
+                          int floor_max_at_zero, void* workspace, size_t workspace_bytes,
+                          dcb_stream_t stream);
+/* tuning hook used by bench/sweeps: variant<0 = default heuristic */
+int dcb_proj_mean_max_f32_variant(const float* movie, int T, int H, int W, float* mean, float* max,
+                                  int floor_max_at_zero, void* workspace, size_t workspace_bytes,
+                                  int variant, int t_splits, dcb_stream_t stream);
+
+/* ---- a2: unet_2d_summary.py:238-239 (_summarize_series) ----
+ * out = (in - mean(in)) / std(in), population std, n = H*W elements.
+ * stats (optional, 2 doubles on device) receives mean and std. */
+int dcb_standardize_f32(const float* in, long long n, float* out, double* stats, dcb_stream_t stream);
+
+/* ---- a3/a4/a8: every Conv2D(3x3,'same') / Conv2DTranspose(2x2,s2) of unet() and their
+ * Keras-autodiff gradients (unet_2d_summary.py:154-167; arithmetic in TF 1.2.1).
+ * Activations NHWC.  The input may be the channel concatenation [src0 | src1]
+ * (unet_2d_summary.py:200,206,212,218); pass src1 = NULL, C1 = 0 otherwise.
+ * Epilogue: out = act(acc * scale[c] + shift[c]) with scale/shift optional (NULL = 1 / 0)
+ * and relu != 0 selecting max(0, .): inference folds bias + BatchNorm (eps 1e-3) + ReLU
+ * into it, training passes shift = bias only and normalises after the batch statistics.
+ *
+ * Weight layouts (prepared once per weight update by dcb_prep_* below):
+ *   DCB_F32 : conv3x3  B[9][Cin][Cout]   (= Keras HWIO)     convT fwd  B[4][Cin][Cout]
+ *             conv3x3 dgrad B[9][Cout][Cin] (taps flipped)  convT dgrad B[4][Cout][Cin] (= Keras)
+ *   DCB_BF16: the same matrices stored N-major ("K-major B"): [taps][N][K] -> see dcb_prep_*.
+ */
+int dcb_conv3x3_fwd(int dtype, const void* src0, int C0, const void* src1, int C1, int N, int H, int W,
+                    const void* wgt, int Cout, const float* scale, const float* shift, int relu,
+                    void* out, dcb_stream_t stream);
+/* input h x w -> output 2h x 2w */
+int dcb_convT2x2_fwd(int dtype, const void* src, int Cin, int N, int h, int w, const void* wgt, int Cout,
+                     const float* scale, const float* shift, int relu, void* out, dcb_stream_t stream);
+/* dy is [N][2h][2w][Cout]; dx is [N][h][w][Cin] */
+int dcb_convT2x2_dgrad(int dtype, const void* dy, int Cout, int N, int h, int w, const void* wgt, int Cin,
+                       void* dx, dcb_stream_t stream);
+/* dW[9][Cin][Cout] (fp32, Keras HWIO) = sum over pixels of x (shifted) * dy ; x may be [src0|src1] */
+int dcb_conv3x3_wgrad_workspace_bytes(int dtype, int N, int H, int W, int Cin, int Cout, size_t* bytes);
+int dcb_conv3x3_wgrad(int dtype, const void* src0, int C0, const void* src1, int C1, int N, int H, int W,
+                      const void* dy, int Cout, float* dW, void* workspace, size_t workspace_bytes,
+                      dcb_stream_t stream);
+/* dW[2][2][Cout][Cin] (fp32, Keras layout); x is [N][h][w][Cin], dy is [N][2h][2w][Cout] */
+int dcb_convT2x2_wgrad_workspace_bytes(int dtype, int N, int h, int w, int Cin, int Cout, size_t* bytes);
+int dcb_convT2x2_wgrad(int dtype, const void* x, int Cin, int N, int h, int w, const void* dy, int Cout,
+                       float* dW, void* workspace, size_t workspace_bytes, dcb_stream_t stream);
+/* first layer (unet_2d_summary.py:169-172): 1-channel fp32 image x[N][H][W], w[9][Cout] fp32 (Keras
+ * HWIO with Cin = 1), CUDA-core kernel (K = 9 is below any tensor-core tile); same epilogue as above */
+int dcb_conv3x3_c1_fwd(int dtype, const float* x, int N, int H, int W, const float* w, int Cout,
+                       const float* scale, const float* shift, int relu, void* out, dcb_stream_t stream);
+int dcb_conv3x3_c1_wgrad_workspace_bytes(int Cout, size_t* bytes);
+int dcb_conv3x3_c1_wgrad(int dtype, const float* x, const void* dy, int N, int H, int W, int Cout, float* dW,
+                         void* workspace, size_t workspace_bytes, dcb_stream_t stream);
+/* weight preparation from the fp32 Keras-layout master copies.
+ *   conv3x3: w [3][3][Cin][Cout] -> fwd and dgrad operands for `dtype` (either may be NULL)
+ *   convT  : w [2][2][Cout][Cin] -> fwd and dgrad operands */
+int dcb_prep_conv3x3_weights(int dtype, const float* w, int Cin, int Cout, void* w_fwd, void* w_dgrad,
+                             dcb_stream_t stream);
+int dcb_prep_convT2x2_weights(int dtype, const float* w, int Cin, int Cout, void* w_fwd, void* w_dgrad,
+                              dcb_stream_t stream);
+
+/* ---- BatchNormalization (Keras 2.0.6: eps 1e-3, biased batch variance) ---- */
+/* inference fold: scale = gamma*rsqrt(var+eps), shift = beta + (bias - mean)*scale */
+int dcb_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, const float* bias,
+                int C, float eps, float* scale, float* shift, dcb_stream_t stream);
+/* sums[0..C) += sum_m x, sums[C..2C) += sum_m x^2 over x[M][C] (double; caller zeroes) */
+int dcb_bn_stats(int dtype, const void* x, long long M, int C, double* sums, dcb_stream_t stream);
+/* batch mean / rstd, scale/shift for dcb_bn_apply, momentum update of the moving statistics
+ * (moving_* may be NULL) */
+int dcb_bn_finalize(const double* sums, long long M, int C, const float* gamma, const float* beta, float eps,
+                    float momentum, float* moving_mean, float* moving_var, float* scale, float* shift,
+                    float* mean, float* rstd, dcb_stream_t stream);
+/* y = relu?(x*scale + shift), then inverted dropout (Philox keyed by seed ^ *seed_dev and layer; p_drop = 0 disables;
+ * unet_2d_summary.py:179-216) */
+int dcb_bn_apply(int dtype, const void* x, long long M, int C, const float* scale, const float* shift, int relu,
+                 float p_drop, unsigned long long seed, const unsigned long long* seed_dev, unsigned layer, void* y,
+                 dcb_stream_t stream);
+/* backward of dropout+ReLU+BN given dy (row stride ldy, channel offset offy) and the raw conv output x:
+ * reduce accumulates sums[0..C)=sum dz, sums[C..2C)=sum dz*xhat; apply writes d_raw and dgamma/dbeta */
+int dcb_bn_bwd_reduce(int dtype, const void* dy, int ldy, int offy, const void* x, long long M, int C,
+                      const float* scale, const float* shift, const float* mean, const float* rstd,
+                      float p_drop, unsigned long long seed, const unsigned long long* seed_dev, unsigned layer,
+                      double* sums, dcb_stream_t stream);
+int dcb_bn_bwd_apply(int dtype, const void* dy, int ldy, int offy, const void* x, long long M, int C,
+                     const float* scale, const float* shift, const float* mean, const float* rstd,
+                     float p_drop, unsigned long long seed, const unsigned long long* seed_dev, unsigned layer,
+                     const double* sums, void* draw, float* dgamma, float* dbeta, dcb_stream_t stream);
+
+/* ---- a5: MaxPooling2D(2,2) fwd and bwd (gradient to the first maximum of the window), the bwd
+ * fused with the add of the skip-connection gradient (a channel slice of a concat gradient) ---- */
+int dcb_maxpool2x2(int dtype, const void* x, int N, int H, int W, int C, void* y, dcb_stream_t stream);
+int dcb_pool_bwd_add(int dtype, const void* skipgrad, int lds, int offs, const void* y, const void* pooled,
+                     const void* dpool, int N, int H, int W, int C, void* out, dcb_stream_t stream);
+
+/* ---- a6/a7: Conv2D(2,1,softmax)[..., -1] head (unet_2d_summary.py:221-222), losses and the
+ * seven batch metrics (utils/neurons.py:13-106).  w is [C][2], b is [2] (Keras layout). ---- */
+int dcb_head_fwd(int dtype, const void* x, long long M, int C, const float* w, const float* b, float* logit,
+                 float* prob, dcb_stream_t stream);
+/* sums[8] (double, caller zeroes): sum yt, p, yt*p, p^2, round(p), yt*round(p), BCE, weighted BCE */
+int dcb_head_loss_fwd(int dtype, const void* x, long long M, int C, const float* w, const float* b,
+                      const uint8_t* yt, float* prob, double* sums, dcb_stream_t stream);
+/* dx[M][C] = dL/dx; dw_out[2C+2] = dL/d(kernel [C][2], bias [2]); metrics_out[8] =
+ * loss, F1, prec, reca, dice, dicesq, posyt, posyp; dwb_accum[2C+2] double scratch (caller zeroes) */
+int dcb_head_loss_bwd(int dtype, const void* x, long long M, int C, const float* w, const uint8_t* yt,
+                      const float* prob, const double* sums, int loss, void* dx, double* dwb_accum,
+                      float* dw_out, float* metrics_out, dcb_stream_t stream);
+
+/* ---- a10: 8x test-time augmentation (utils/neurons.py:112-137, unet_2d_summary.py:569-595) ----
+ * make_batch: reflect-pad s[hs][ws] to S x S and write transforms first..first+count-1 as [count][S][S];
+ * combine: act = sum_k float32(inv_k(p_k) / n_aug) in float64, cropped to hs x ws; mask = act > threshold */
+int dcb_tta_make_batch(int dtype, const float* s, int hs, int ws, int S, int first, int count, void* out,
+                       dcb_stream_t stream);
+int dcb_tta_combine(const float* probs, int S, int hs, int ws, float threshold, int n_aug, double* act,
+                    uint8_t* mask, dcb_stream_t stream);
+
+/* ---- a9: keras.optimizers.Adam (2.0.6) over one flat fp32 parameter buffer;
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller (unet_2d_summary.py:335) ---- */
+int dcb_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr_t, const float* lr_t_dev,
+                  float beta1, float beta2, float eps, dcb_stream_t stream);
+/* device-resident step state {iteration, dropout seed}: iteration += 1, seed advances, lr_t_out gets the
+ * bias-corrected step size; dropout kernels xor *seed_dev into their seed, Adam reads *lr_t_dev
+ * (both optional, NULL = use the by-value argument) so a captured CUDA graph stays valid across steps */
+int dcb_step_advance(unsigned long long* state, float lr, float beta1, float beta2, float* lr_t_out,
+                     dcb_stream_t stream);
+
+int dcb_cast_from_f32(int dtype, const float* in, long long n, void* out, dcb_stream_t stream);
+int dcb_cast_to_f32(int dtype, const void* in, long long n, float* out, dcb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCB200_H_ */

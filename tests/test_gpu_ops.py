@@ -1,0 +1,311 @@
+"""Per-kernel parity on the GPU through the C ABI (deepcalcium.engine.ops) against float64 CPU
+references built from the oracle's layer arithmetic (torch CPU + autograd).
+fp32 = CUDA-core check kernels (tolerance 1e-4 class), bf16 = tcgen05 kernels (bf16 tolerance)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+from oracle import losses as ol
+
+pytestmark = pytest.mark.gpu
+
+DT = {'fp32': torch.float32, 'bf16': torch.bfloat16}
+
+
+def dev(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a)).to(dtype).cuda().contiguous()
+
+
+def q(a, precision):
+    """round an input through the activation dtype so the reference sees the same operand values"""
+    t = torch.as_tensor(np.asarray(a, dtype=np.float32))
+    return t.to(DT[precision]).to(torch.float64).numpy()
+
+
+def tol(precision, scale=1.0):
+    return dict(fp32=2e-4, bf16=3e-2)[precision] * scale
+
+
+def nhwc_to_nchw(a):
+    return torch.as_tensor(a).permute(0, 3, 1, 2).contiguous()
+
+
+CONV_CASES = [
+    # N, H, W, C0, C1, Cout
+    (1, 16, 16, 32, 0, 32),
+    (2, 8, 24, 64, 0, 64),
+    (1, 16, 16, 32, 32, 32),
+    (2, 8, 8, 128, 128, 128),
+    (3, 4, 4, 256, 0, 512),
+    (1, 32, 32, 64, 64, 64),
+    (1, 2, 2, 512, 0, 512),
+]
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv3x3_fwd_dgrad_wgrad(cuda, precision, case):
+    from deepcalcium.engine import ops
+    N, H, W, C0, C1, Cout = case
+    dt = DT[precision]
+    rng = np.random.default_rng(hash(case) % 2**31)
+    Cin = C0 + C1
+    x = q(rng.standard_normal((N, H, W, Cin)), precision)
+    w = q(rng.standard_normal((3, 3, Cin, Cout)) * np.sqrt(2. / (9 * Cin)), precision)
+    scale = rng.uniform(0.5, 1.5, Cout).astype(np.float32)
+    shift = rng.standard_normal(Cout).astype(np.float32)
+    xt = nhwc_to_nchw(x).requires_grad_(True)
+    wt = torch.tensor(w, requires_grad=True)
+    conv = F.conv2d(xt, wt.permute(3, 2, 0, 1), padding=1)
+    ref = torch.relu(conv * torch.tensor(scale, dtype=torch.float64)[None, :, None, None]
+                     + torch.tensor(shift, dtype=torch.float64)[None, :, None, None])
+    # forward (+ concat + epilogue)
+    x0 = dev(x[..., :C0], dt)
+    x1 = dev(x[..., C0:], dt) if C1 else None
+    wm = dev(w)
+    wf = torch.empty(9 * Cin * Cout, dtype=dt, device='cuda')
+    wd = torch.empty(9 * Cin * Cout, dtype=dt, device='cuda')
+    ops.prep_conv3x3_weights(wm, wf, wd, dt)
+    out = torch.empty(N, H, W, Cout, dtype=dt, device='cuda')
+    ops.conv3x3_fwd(x0, x1, wf, out, dev(scale), dev(shift), True)
+    got = out.float().cpu().permute(0, 3, 1, 2).double()
+    assert torch.max(torch.abs(got - ref)).item() < tol(precision, 1 + ref.abs().max().item())
+    # plain conv (no epilogue), dgrad and wgrad against autograd
+    dy = q(rng.standard_normal((N, H, W, Cout)), precision)
+    conv.backward(nhwc_to_nchw(dy))
+    dx = torch.empty(N, H, W, Cin, dtype=dt, device='cuda')
+    ops.conv3x3_fwd(dev(dy, dt), None, wd, dx, None, None, False)
+    gx = dx.float().cpu().permute(0, 3, 1, 2).double()
+    assert torch.max(torch.abs(gx - xt.grad)).item() < tol(precision, 1 + xt.grad.abs().max().item())
+    dW = torch.empty(3, 3, Cin, Cout, dtype=torch.float32, device='cuda')
+    ws = torch.empty(max(16, ops.conv3x3_wgrad_workspace_bytes(dt, N, H, W, Cin, Cout)), dtype=torch.uint8, device='cuda')
+    ops.conv3x3_wgrad(x0, x1, dev(dy, dt), dW, ws)
+    gw = dW.cpu().double()
+    assert torch.max(torch.abs(gw - wt.grad)).item() < tol(precision, 1 + wt.grad.abs().max().item())
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('case', [(1, 8, 8, 64, 32), (2, 4, 4, 512, 256), (1, 16, 16, 128, 64), (3, 2, 2, 256, 128)])
+def test_convT2x2_fwd_dgrad_wgrad(cuda, precision, case):
+    from deepcalcium.engine import ops
+    N, h, w_, Cin, Cout = case
+    dt = DT[precision]
+    rng = np.random.default_rng(hash(case) % 2**31)
+    x = q(rng.standard_normal((N, h, w_, Cin)), precision)
+    k = q(rng.standard_normal((2, 2, Cout, Cin)) * np.sqrt(2. / (4 * Cout)), precision)
+    bias = rng.standard_normal(Cout).astype(np.float32)
+    xt = nhwc_to_nchw(x).requires_grad_(True)
+    kt = torch.tensor(k, requires_grad=True)
+    ref = F.conv_transpose2d(xt, kt.permute(3, 2, 0, 1), torch.tensor(bias, dtype=torch.float64), stride=2)
+    wf = torch.empty(4 * Cin * Cout, dtype=dt, device='cuda')
+    wd = torch.empty(4 * Cin * Cout, dtype=dt, device='cuda')
+    ops.prep_convT2x2_weights(dev(k), wf, wd, dt)
+    out = torch.empty(N, 2 * h, 2 * w_, Cout, dtype=dt, device='cuda')
+    ops.convT2x2_fwd(dev(x, dt), wf, out, None, dev(bias), False)
+    got = out.float().cpu().permute(0, 3, 1, 2).double()
+    assert torch.max(torch.abs(got - ref)).item() < tol(precision, 1 + ref.abs().max().item())
+    dy = q(rng.standard_normal((N, 2 * h, 2 * w_, Cout)), precision)
+    ref.backward(nhwc_to_nchw(dy))
+    dx = torch.empty(N, h, w_, Cin, dtype=dt, device='cuda')
+    ops.convT2x2_dgrad(dev(dy, dt), wd, dx)
+    assert torch.max(torch.abs(dx.float().cpu().permute(0, 3, 1, 2).double() - xt.grad)).item() < \
+        tol(precision, 1 + xt.grad.abs().max().item())
+    dW = torch.empty(2, 2, Cout, Cin, dtype=torch.float32, device='cuda')
+    ws = torch.empty(max(16, ops.convT2x2_wgrad_workspace_bytes(dt, N, h, w_, Cin, Cout)), dtype=torch.uint8, device='cuda')
+    ops.convT2x2_wgrad(dev(x, dt), dev(dy, dt), dW, ws)
+    assert torch.max(torch.abs(dW.cpu().double() - kt.grad)).item() < tol(precision, 1 + kt.grad.abs().max().item())
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_conv3x3_first_layer_c1(cuda, precision):
+    from deepcalcium.engine import ops
+    dt = DT[precision]
+    rng = np.random.default_rng(11)
+    N, H, W, Cout = 2, 24, 40, 32
+    x = rng.standard_normal((N, H, W)).astype(np.float32)
+    w = (rng.standard_normal((3, 3, 1, Cout)) * 0.5).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    xt = torch.tensor(x, dtype=torch.float64)[:, None]
+    wt = torch.tensor(w, dtype=torch.float64, requires_grad=True)
+    ref = F.conv2d(xt, wt.permute(3, 2, 0, 1), torch.tensor(b, dtype=torch.float64), padding=1)
+    out = torch.empty(N, H, W, Cout, dtype=dt, device='cuda')
+    ops.conv3x3_c1_fwd(dev(x), dev(w), out, None, dev(b), False)
+    assert torch.max(torch.abs(out.float().cpu().permute(0, 3, 1, 2).double() - ref)).item() < tol(precision, 4)
+    dy = q(rng.standard_normal((N, H, W, Cout)), precision)
+    ref.backward(nhwc_to_nchw(dy))
+    dW = torch.empty(3, 3, 1, Cout, dtype=torch.float32, device='cuda')
+    ws = torch.empty(ops.conv3x3_c1_wgrad_workspace_bytes(Cout), dtype=torch.uint8, device='cuda')
+    ops.conv3x3_c1_wgrad(dev(x), dev(dy, dt), dW, ws)
+    assert torch.max(torch.abs(dW.cpu().double() - wt.grad)).item() < 2e-3 * (1 + wt.grad.abs().max().item())
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('C', [32, 128, 512])
+def test_batchnorm_train_forward_backward(cuda, precision, C):
+    """stats -> finalize -> apply and the two backward kernels against autograd of the Keras formula
+    (eps 1e-3, biased variance, momentum update), including the strided dy view of a concat gradient."""
+    from deepcalcium.engine import ops
+    dt = DT[precision]
+    rng = np.random.default_rng(C)
+    M = 1000
+    x = q(rng.standard_normal((M, C)) * 2 + 0.5, precision)
+    gamma = rng.uniform(0.5, 1.5, C).astype(np.float32); beta = (0.1 * rng.standard_normal(C)).astype(np.float32)
+    mm = rng.standard_normal(C).astype(np.float32); mv = rng.uniform(0.5, 1.5, C).astype(np.float32)
+    xt = torch.tensor(x, requires_grad=True)
+    gt = torch.tensor(gamma, dtype=torch.float64, requires_grad=True)
+    bt = torch.tensor(beta, dtype=torch.float64, requires_grad=True)
+    mean = xt.mean(0); var = ((xt - mean) ** 2).mean(0)
+    y = torch.relu((xt - mean) * torch.rsqrt(var + 1e-3) * gt + bt)
+    xd = dev(x, dt).view(1, 1, M, C)
+    sums = torch.zeros(4 * C, dtype=torch.float64, device='cuda')
+    f = lambda: torch.empty(C, device='cuda')
+    scale, shift, mean_d, rstd_d = f(), f(), f(), f()
+    mmd, mvd = dev(mm), dev(mv)
+    ops.bn_stats(xd, sums[:2 * C])
+    ops.bn_finalize(sums[:2 * C], M, dev(gamma), dev(beta), 0.5, mmd, mvd, scale, shift, mean_d, rstd_d)
+    yd = torch.empty_like(xd)
+    ops.bn_apply(xd, scale, shift, yd, True)
+    assert torch.max(torch.abs(yd.float().cpu().view(M, C).double() - y.detach())).item() < tol(precision, 4)
+    assert np.allclose(mean_d.cpu().numpy(), mean.detach().numpy(), atol=1e-5)
+    assert np.allclose(mmd.cpu().numpy(), mm * 0.5 + mean.detach().numpy() * 0.5, atol=1e-5)
+    assert np.allclose(mvd.cpu().numpy(), mv * 0.5 + var.detach().numpy() * 0.5, atol=1e-4)
+    # backward with dy living at channel offset C/2.. of a wider tensor (row stride 2C)
+    dy_wide = q(rng.standard_normal((M, 2 * C)), precision)
+    off = C // 2 if (C // 2) % 4 == 0 else 0
+    dy = dy_wide[:, off:off + C]
+    y.backward(torch.tensor(dy))
+    draw = torch.empty_like(xd)
+    dg, db = f(), f()
+    dyd = dev(dy_wide, dt)
+    ops.bn_bwd_reduce(dyd, 2 * C, off, xd, scale, shift, mean_d, rstd_d, sums[2 * C:])
+    ops.bn_bwd_apply(dyd, 2 * C, off, xd, scale, shift, mean_d, rstd_d, sums[2 * C:], draw, dg, db)
+    t = tol(precision, 4)
+    assert torch.max(torch.abs(draw.float().cpu().view(M, C).double() - xt.grad)).item() < t
+    assert np.allclose(dg.cpu().numpy(), gt.grad.numpy(), atol=t * 30, rtol=1e-2 if precision == 'bf16' else 1e-4)
+    assert np.allclose(db.cpu().numpy(), bt.grad.numpy(), atol=t * 30, rtol=1e-2 if precision == 'bf16' else 1e-4)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_dropout_is_consistent_between_forward_and_backward(cuda, precision):
+    from deepcalcium.engine import ops
+    dt = DT[precision]
+    M, C = 4096, 64
+    x = torch.ones(1, 1, M, C, dtype=dt, device='cuda')
+    one, zero = torch.ones(C, device='cuda'), torch.zeros(C, device='cuda')
+    y = torch.empty_like(x)
+    seed_dev = torch.tensor([12345], dtype=torch.int64, device='cuda')
+    ops.bn_apply(x, one, zero, y, True, 0.5, 7, seed_dev, 3)
+    keep = (y.float() > 0)
+    frac = keep.float().mean().item()
+    assert 0.47 < frac < 0.53 and torch.all(y.float()[keep] == 2.0)
+    y2 = torch.empty_like(x)
+    ops.bn_apply(x, one, zero, y2, True, 0.5, 7, seed_dev, 4)       # another layer -> another mask
+    assert (y2 != y).float().mean().item() > 0.3
+    # backward sees the same mask: sum dz over rows == 2 * kept count per channel (dy = 1, xhat = 0)
+    sums = torch.zeros(2 * C, dtype=torch.float64, device='cuda')
+    ops.bn_bwd_reduce(x, C, 0, x, one, zero, one, one, sums, 0.5, 7, seed_dev, 3)
+    assert torch.allclose(sums[:C], 2.0 * keep.view(M, C).double().sum(0))
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_maxpool_forward_and_backward_routing(cuda, precision):
+    from deepcalcium.engine import ops
+    dt = DT[precision]
+    rng = np.random.default_rng(3)
+    N, H, W, C = 2, 8, 12, 32
+    x = q(np.maximum(rng.standard_normal((N, H, W, C)), 0), precision)     # ReLU output: many tied zeros
+    xt = nhwc_to_nchw(x).requires_grad_(True)
+    ref = F.max_pool2d(xt, 2)
+    xd = dev(x, dt)
+    yd = torch.empty(N, H // 2, W // 2, C, dtype=dt, device='cuda')
+    ops.maxpool2x2(xd, yd)
+    assert torch.equal(yd.float().cpu().permute(0, 3, 1, 2).double(), ref.detach())
+    dp = q(rng.standard_normal((N, H // 2, W // 2, C)), precision)
+    skip_wide = q(rng.standard_normal((N, H, W, 2 * C)), precision)
+    ref.backward(nhwc_to_nchw(dp))
+    out = torch.empty(N, H, W, C, dtype=dt, device='cuda')
+    ops.pool_bwd_add(dev(skip_wide, dt), 2 * C, C, xd, yd, dev(dp, dt), out)
+    exp = xt.grad + nhwc_to_nchw(skip_wide[..., C:])
+    # every pooled gradient lands on exactly one input pixel (torch also picks the first maximum)
+    assert torch.max(torch.abs(out.float().cpu().permute(0, 3, 1, 2).double() - exp)).item() < tol(precision, 4)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('loss', ['dice_loss', 'binary_crossentropy', 'dicesq_loss', 'weighted_binary_crossentropy'])
+def test_head_loss_metrics_and_gradient(cuda, precision, loss):
+    from deepcalcium.engine import ops
+    from deepcalcium import _native as nat
+    dt = DT[precision]
+    rng = np.random.default_rng(17)
+    M, C = 3000, 32
+    x = q(rng.standard_normal((M, C)), precision)
+    w = (rng.standard_normal((C, 2)) * 0.3).astype(np.float32); b = np.array([0.1, -0.2], np.float32)
+    yt = (rng.random(M) < 0.126).astype(np.uint8)
+    xt = torch.tensor(x, requires_grad=True)
+    wt = torch.tensor(w, dtype=torch.float64, requires_grad=True); bt = torch.tensor(b, dtype=torch.float64, requires_grad=True)
+    p = torch.softmax(xt @ wt + bt, dim=1)[:, -1]
+    L = ol.LOSSES[loss](torch.tensor(yt, dtype=torch.float64), p)
+    L.backward()
+    xd = dev(x, dt).view(1, 1, M, C)
+    prob = torch.empty(M, device='cuda'); logit = torch.empty(M, device='cuda')
+    ops.head_fwd(xd, dev(w), dev(b), logit, prob)
+    assert np.allclose(prob.cpu().numpy(), p.detach().numpy(), atol=1e-5)
+    sums = torch.zeros(8, dtype=torch.float64, device='cuda'); dwb = torch.zeros(2 * C + 2, dtype=torch.float64, device='cuda')
+    ops.head_loss_fwd(xd, dev(w), dev(b), dev(yt, torch.uint8), prob, sums)
+    dx = torch.empty_like(xd); dw = torch.empty(2 * C + 2, device='cuda'); met = torch.empty(8, device='cuda')
+    ops.head_loss_bwd(xd, dev(w), dev(yt, torch.uint8), prob, sums, nat.LOSS_IDS[loss], dx, dwb, dw, met)
+    met = met.cpu().numpy()
+    assert abs(met[0] - L.item()) < 2e-5 * max(1, abs(L.item()))
+    om = ol.batch_metrics(yt, p.detach().numpy())
+    for i, k in enumerate(['F1', 'prec', 'reca', 'dice', 'dicesq', 'posyt', 'posyp']):
+        assert abs(met[1 + i] - om[k]) < 1e-4, k
+    gscale = xt.grad.abs().max().item()
+    assert torch.max(torch.abs(dx.float().cpu().view(M, C).double() - xt.grad)).item() < (1e-2 if precision == 'bf16' else 1e-4) * gscale + 1e-9
+    assert np.allclose(dw[:2 * C].cpu().numpy().reshape(C, 2), wt.grad.numpy(), rtol=1e-3, atol=1e-5 * (1 + wt.grad.abs().max().item()))
+    assert np.allclose(dw[2 * C:].cpu().numpy(), bt.grad.numpy(), rtol=1e-3, atol=1e-6)
+
+
+def test_tta_batch_and_combine_match_the_reference_table(cuda):
+    from deepcalcium.engine import ops
+    from deepcalcium.utils.neurons import INVERTIBLE_2D_AUGMENTATIONS as TABLE
+    rng = np.random.default_rng(4)
+    S, hs, ws = 32, 27, 30
+    s = rng.standard_normal((hs, ws)).astype(np.float32)
+    padded = oracle.reflect_pad(s, S, S)[None]
+    out = torch.empty(8, S, S, device='cuda')
+    ops.tta_make_batch(dev(s), S, 0, 8, out)
+    for k, (name, aug, inv) in enumerate(TABLE):
+        assert np.array_equal(out[k].cpu().numpy(), aug(padded)[0]), name
+    sub = torch.empty(3, S, S, device='cuda')
+    ops.tta_make_batch(dev(s), S, 4, 3, sub)
+    assert torch.equal(sub, out[4:7])
+    probs = rng.random((8, S, S)).astype(np.float32)
+    mp = np.zeros((hs, ws))
+    for k, (name, aug, inv) in enumerate(TABLE):
+        mp += inv(probs[k:k + 1])[0, :hs, :ws] / len(TABLE)
+    act = torch.empty(hs, ws, dtype=torch.float64, device='cuda'); mask = torch.empty(hs, ws, dtype=torch.uint8, device='cuda')
+    ops.tta_combine(dev(probs), S, hs, ws, 0.5, 8, act, mask)
+    assert np.array_equal(act.cpu().numpy(), mp)                       # same fp32 /8 then fp64 adds, same order
+    assert np.array_equal(mask.cpu().numpy(), (mp > 0.5).astype(np.uint8))
+    ops.tta_combine(dev(probs), S, hs, ws, 0.5, 1, act, mask)
+    assert np.array_equal(mask.cpu().numpy(), (probs[0, :hs, :ws] > 0.5).astype(np.uint8))
+
+
+def test_keras_adam_kernel(cuda):
+    from deepcalcium.engine import ops
+    rng = np.random.default_rng(9)
+    n = 10001
+    p = rng.standard_normal(n); g = rng.standard_normal(n) * 1e-3
+    m = np.zeros(n); v = np.zeros(n)
+    pd, md, vd = dev(p), dev(m), dev(v)
+    state = torch.zeros(2, dtype=torch.int64, device='cuda'); lr_t = torch.zeros(1, device='cuda')
+    for it in range(3):
+        gi = g * (it + 1)
+        p, m, v = oracle.keras_adam_update(p, gi, m, v, it, lr=0.002)
+        ops.step_advance(state, 0.002, 0.9, 0.999, lr_t)
+        ops.adam_step(pd, dev(gi), md, vd, 0., lr_t)
+    assert state[0].item() == 3
+    assert np.allclose(pd.cpu().numpy(), p, atol=2e-6)
+    assert np.allclose(vd.cpu().numpy(), v, rtol=1e-4, atol=1e-12)

@@ -1,0 +1,107 @@
+"""K1 / K1b parity on the GPU: projection max bit-exact, mean <= 1e-6 relative, standardise."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _proj(movie, **kw):
+    from deepcalcium.datasets.nf import summarize_movie_device
+    mean, mx = summarize_movie_device(torch.from_numpy(movie).cuda(), **kw)
+    torch.cuda.synchronize()
+    return mean.cpu().numpy(), mx.cpu().numpy()
+
+
+def test_golden_projection(cuda, golden_dir):
+    z = np.load(golden_dir + '/projection_small.npz')
+    mean, mx = _proj(z['movie'])
+    assert np.array_equal(mx, z['max'])
+    assert np.max(np.abs(mean - z['mean']) / np.abs(z['mean'])) <= 1e-6
+
+
+@pytest.mark.parametrize('variant', [0, 1, 2, 3])
+@pytest.mark.parametrize('t_splits', [1, 3, 8])
+def test_projection_variants_and_splits(cuda, variant, t_splits):
+    rng = np.random.default_rng(variant * 10 + t_splits)
+    movie = (rng.random((211, 64, 96), dtype=np.float32) * 4096).astype(np.float32)
+    mean, mx = _proj(movie, variant=variant, t_splits=t_splits)
+    omean, omx = oracle.project_mean_max(movie)
+    assert np.array_equal(mx, omx)
+    assert np.max(np.abs(mean - omean) / np.abs(omean)) <= 1e-6
+
+
+@pytest.mark.parametrize('shape', [(1, 8, 8), (5, 3, 7), (300, 16, 20), (17, 512, 512), (64, 31, 33)])
+def test_projection_ragged_shapes(cuda, shape):
+    rng = np.random.default_rng(sum(shape))
+    movie = (rng.standard_normal(shape) * 100).astype(np.float32)        # signed data
+    mean, mx = _proj(movie)
+    omean, omx = oracle.project_mean_max(movie)
+    assert np.array_equal(mx, omx)
+    scale = np.abs(movie).mean(0, dtype=np.float64)
+    assert np.max(np.abs(mean - omean) / scale) <= 1e-6
+
+
+def test_projection_floor_and_nan_and_int16_like(cuda):
+    rng = np.random.default_rng(1)
+    movie = rng.integers(-500, 3000, size=(100, 32, 32)).astype(np.float32)
+    movie[:, 0, 0] = -7.0
+    mean, mx = _proj(movie, floor_max_at_zero=True)
+    omean, omx = oracle.project_mean_max(movie, floor_max_at_zero=True)
+    assert np.array_equal(mx, omx) and mx[0, 0] == 0.0
+    movie[3, 5, 5] = np.nan
+    mean, mx = _proj(movie)
+    assert np.isnan(mx[5, 5]) and np.isnan(mean[5, 5])          # numpy semantics: NaN propagates
+    assert np.isfinite(np.delete(mx.ravel(), 5 * 32 + 5)).all()
+
+
+def test_projection_bad_arguments_raise(cuda):
+    from deepcalcium.datasets.nf import summarize_movie_device
+    with pytest.raises(ValueError):
+        summarize_movie_device(torch.zeros(4, 4, device='cuda'))
+    with pytest.raises(ValueError):
+        summarize_movie_device(torch.zeros(0, 4, 4, device='cuda'))
+    with pytest.raises(TypeError):
+        summarize_movie_device(torch.zeros(2, 4, 4, device='cuda', dtype=torch.float64))
+
+
+def test_projection_full_size_properties(cuda):
+    """BASELINE config C2 size (3000x512x512 fp32 = 3.1 GB): checked through size-independent
+    properties - constant movie, linearity in a per-frame offset, max of a planted spike - plus a
+    strided oracle check on a subset of pixels."""
+    from deepcalcium.datasets.nf import summarize_movie_device
+    T, H, W = 3000, 512, 512
+    g = torch.Generator(device='cuda'); g.manual_seed(7535)
+    movie = torch.rand((T, H, W), device='cuda', generator=g) * 4096
+    movie[1234, 100, 200] = 5000.0
+    mean, mx = summarize_movie_device(movie)
+    assert mx[100, 200].item() == 5000.0
+    sub = movie[:, ::64, ::64].cpu().numpy()
+    omean, omx = oracle.project_mean_max(sub)
+    assert np.array_equal(mx[::64, ::64].cpu().numpy(), omx)
+    assert np.max(np.abs(mean[::64, ::64].cpu().numpy() - omean) / omean) <= 1e-6
+    # idempotence / determinism: a second run is bit-identical
+    mean2, mx2 = summarize_movie_device(movie)
+    assert torch.equal(mean, mean2) and torch.equal(mx, mx2)
+    del movie
+    const = torch.full((T, 64, 64), 3.25, device='cuda')
+    mean, mx = summarize_movie_device(const)
+    assert torch.all(mean == 3.25) and torch.all(mx == 3.25)
+
+
+def test_standardize_matches_summarize_series(cuda, golden_dir):
+    from deepcalcium.engine import ops
+    z = np.load(golden_dir + '/projection_small.npz')
+    x = z['mean'].astype(np.float16).astype(np.float32)
+    xd = torch.from_numpy(x).cuda()
+    out = torch.empty_like(xd)
+    stats = torch.zeros(2, dtype=torch.float64, device='cuda')
+    ops.standardize(xd, out, stats)
+    assert np.allclose(out.cpu().numpy(), z['summary'], atol=2e-6, rtol=1e-6)
+    assert abs(stats[0].item() - x.astype(np.float64).mean()) < 1e-9 * abs(x.mean()) + 1e-9
+    img = np.random.default_rng(0).standard_normal((512, 512)).astype(np.float32) * 37 + 500
+    out = torch.empty(512, 512, device='cuda')
+    ops.standardize(torch.from_numpy(img).cuda(), out)
+    assert np.allclose(out.cpu().numpy(), oracle.summarize_series(img), atol=2e-6, rtol=1e-5)

