@@ -126,7 +126,7 @@ def test_train_step_nfb32_against_oracle(cuda, precision):
         got = eng.G[key].cpu().numpy().astype(np.float64)
         rel = np.linalg.norm(got - g_ref) / (np.linalg.norm(g_ref) + 1e-30)
         worst = max(worst, rel)
-        assert rel < (2e-3 if precision == 'fp32' else 0.15), (key, rel)
+        assert rel < (5e-3 if precision == "fp32" else 0.15), (key, rel)
     new = eng.get_weights_dict()
     for key in ('enc2b/moving_mean', 'up0/moving_var', 'dec1a/moving_var'):
         assert np.allclose(new[key], nw[key], atol=1e-4 if precision == 'fp32' else 2e-2), key
