@@ -1,17 +1,653 @@
-// bf16 tcgen05/TMEM/TMA tap-GEMM kernels (placeholder until the first kernel lands).
-#include "common.cuh"
+// bf16 tap-GEMM on the 5th-generation tensor cores (tcgen05.mma, fp32 accumulators in TMEM,
+// operands staged in shared memory by TMA).  One persistent, warp-specialised kernel serves every
+// dense contraction of the UNet2DS forward / input-gradient path (tapgeom.h):
+//   conv3x3 'same' fwd + dgrad : 9 shifted [128 px x BK ch] activation boxes per K block, loaded by
+//                                TMA from the NHWC tensor with out-of-bounds zero fill (= the padding)
+//   convT2x2 fwd               : 1 tap, output rows scattered to (2h+a, 2w+b)
+//   convT2x2 dgrad             : 4 taps read through a 5-D strided view of dy
+// The channel concatenation [up | skip] (unet_2d_summary.py:200-218) is never materialised: the
+// K loop walks two tensor maps.  Epilogue: acc*scale[c] + shift[c], optional ReLU, bf16 store
+// (bias + BatchNorm(eps 1e-3) + ReLU folded for inference; bias only for training).
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-5 epilogue.
+// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM double buffer full/empty (MMA <-> epilogue),
+// static round-robin tile schedule (tile = blockIdx.x + i * gridDim.x).
+#include <mutex>
+#include <map>
+#include <vector>
+#include <tuple>
+
+#include "tc_common.cuh"
 #include "tapgeom.h"
 
 namespace dcb {
+extern unsigned long long g_launches;
+using namespace tc;
 
-int run_tc_fwd(const TapGeom&, const void*, int, const void*, int, const void*, int, void*, const float*, const float*,
-               int, cudaStream_t) {
-  return fail(DCB_ERR_UNSUPPORTED, "bf16 tcgen05 forward tap-GEMM not built yet");
+constexpr int TC_BM = 128;          // pixels per tile (= UMMA M, one TMEM lane per pixel)
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_THREADS = 192;
+
+struct TcFwdParams {
+  int mode;                 // 0: 4-D halo box (conv3x3)  1: 3-D merged rows (convT fwd)  2: 5-D strided (convT dgrad)
+  int N, GH, GW;            // iteration grid
+  int bw, bh, bn;           // tile box in iteration-grid units (mode 1/2: bh rows of the merged N*GH axis, bn = 1)
+  int tiles_w, tiles_h, tiles_n;
+  int ntaps;
+  int dy[9], dx[9];
+  int C0, C1;               // channels of the two sources
+  int BK;                   // K block (64 -> 128B swizzle, 32 -> 64B swizzle)
+  int Ntot;                 // rows of the weight matrix (GEMM N over all sub-positions)
+  int BN;                   // N tile (= UMMA N)
+  int Cz;                   // output channels per sub-position (convT fwd: Cout, else Ntot)
+  int OH, OW, OC;           // output tensor
+  int osy, osx, ody, odx;   // output pixel = g * os + od (+ sub-position for convT fwd)
+  int relu;
+  int stages;
+  __nv_bfloat16* out;
+  const float* scale;
+  const float* shift;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                      const __grid_constant__ CUtensorMap mapB, const TcFwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_scale[512], s_shift[512];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // dynamic smem: 1024-byte aligned stage buffers (swizzle atoms are address based)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_bytes = TC_BM * p.BK * 2, b_bytes = p.BN * p.BK * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const int kb0 = p.C0 / p.BK, kb1 = p.C1 / p.BK;
+  const int kb_per_tap = kb0 + kb1;
+  const int num_kb = p.ntaps * kb_per_tap;
+  const int Ktap = p.C0 + p.C1;
+  const int num_ntiles = p.Ntot / p.BN;
+  const int num_mtiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int num_tiles = num_mtiles * num_ntiles;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * p.BN) tmem_cols <<= 1;
+
+  for (int i = threadIdx.x; i < p.Cz; i += blockDim.x) {
+    s_scale[i] = p.scale ? p.scale[i] : 1.f;
+    s_shift[i] = p.shift ? p.shift[i] : 0.f;
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA0);
+    if (p.C1 > 0) tma_prefetch_desc(&mapA1);
+    tma_prefetch_desc(&mapB);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 4); }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = tile % num_ntiles, mt = tile / num_ntiles;
+        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / kb_per_tap, kk = kb % kb_per_tap;
+          const bool second = kk >= kb0;
+          const int c0 = (second ? kk - kb0 : kk) * p.BK;
+          const CUtensorMap* mA = second ? &mapA1 : &mapA0;
+          mbar_wait(&bar_empty[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
+          mbar_arrive_expect_tx(&bar_full[stage], stage_bytes);
+          if (p.mode == 0) tma_load_4d(mA, &bar_full[stage], sa, c0, w0 + p.dx[tap], h0 + p.dy[tap], n0);
+          else if (p.mode == 1) tma_load_3d(mA, &bar_full[stage], sa, c0, w0, h0);
+          else tma_load_5d(mA, &bar_full[stage], sa, c0, p.dx[tap], w0, p.dy[tap], h0);
+          tma_load_2d(&mapB, &bar_full[stage], sb, tap * Ktap + (second ? p.C0 : 0) + c0, nt * p.BN);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (single thread)
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(TC_BM, p.BN, 0, 0);
+      const uint32_t swz = (p.BK == 64) ? SWZ_128B : SWZ_64B;
+      const uint32_t sbo = 8u * p.BK * 2u;          // 8 rows of BK bf16
+      const int ksteps = p.BK / 16;
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&bar_full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
+          const uint64_t da = make_smem_desc(sa, 16, sbo, swz);
+          const uint64_t db = make_smem_desc(sb, 16, sbo, swz);
+          for (int k = 0; k < ksteps; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&bar_empty[stage]);            // smem slot free once these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&bar_tfull[acc]);                // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================================== epilogue warps (TMEM -> regs -> global)
+    const int quarter = warp & 3;                    // TMEM lanes [32*quarter, 32*quarter+32)
+    const int m = quarter * 32 + lane;               // row of the tile = pixel
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int nt = tile % num_ntiles, mt = tile / num_ntiles;
+      const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+      // pixel of this row
+      int n, gh, gw;
+      bool valid;
+      if (p.mode == 0) {
+        gw = tw * p.bw + m % p.bw;
+        gh = th * p.bh + (m / p.bw) % p.bh;
+        n = tn * p.bn + m / (p.bw * p.bh);
+        valid = gw < p.GW && gh < p.GH && n < p.N;
+      } else {
+        gw = tw * p.bw + m % p.bw;
+        const int r = th * p.bh + m / p.bw;
+        n = r / p.GH; gh = r % p.GH;
+        valid = gw < p.GW && r < p.N * p.GH;
+      }
+      const int ng0 = nt * p.BN;                     // first GEMM column of this tile
+      const int z = ng0 / p.Cz, cbase = ng0 % p.Cz;  // sub-position (convT fwd) and channel base
+      const int ody = p.Cz < p.Ntot ? (z >> 1) : p.ody, odx = p.Cz < p.Ntot ? (z & 1) : p.odx;
+      __nv_bfloat16* orow = p.out + (((size_t)n * p.OH + (gh * p.osy + ody)) * p.OW + (gw * p.osx + odx)) * p.OC + cbase;
+
+      mbar_wait(&bar_tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN);
+      for (int c = 0; c < p.BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_addr + c, r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int ch = cbase + c + j + 2 * q;
+              float v0 = fmaf(__uint_as_float(r[j + 2 * q]), s_scale[ch], s_shift[ch]);
+              float v1 = fmaf(__uint_as_float(r[j + 2 * q + 1]), s_scale[ch + 1], s_shift[ch + 1]);
+              if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+              pk[q] = *reinterpret_cast<uint32_t*>(&b2);
+            }
+            *reinterpret_cast<uint4*>(orow + c + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
 }
-int run_tc_wgrad(const TapGeom&, const void*, int, const void*, int, const void*, int, float*, void*, size_t,
-                 cudaStream_t) {
-  return fail(DCB_ERR_UNSUPPORTED, "bf16 tcgen05 wgrad tap-GEMM not built yet");
+
+// ---------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
 }
-size_t tc_wgrad_workspace(const TapGeom&, int, int) { return 0; }
+
+// bf16 tensor map; dims/strides innermost first; strides[i] is the byte stride of dim i+1
+static int make_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, int swizzle_bytes) {
+  typedef std::tuple<const void*, int, std::vector<uint64_t>, std::vector<uint64_t>, std::vector<uint32_t>, int> Key;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  Key key(ptr, rank, std::vector<uint64_t>(dims, dims + rank), std::vector<uint64_t>(strides_bytes, strides_bytes + rank - 1),
+          std::vector<uint32_t>(box, box + rank), swizzle_bytes);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return DCB_OK; }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(DCB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available from the driver");
+  cuuint64_t gdim[5]; cuuint64_t gstr[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return fail(DCB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,..] box [%u,%u,%u,..] swizzle %d",
+                (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0,
+                swizzle_bytes);
+  }
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = *out;
+  return DCB_OK;
+}
+
+static int pick_pow2_box(int extent, int maxbox) {
+  // power-of-two box <= maxbox covering `extent` with the least padding (ties -> larger box);
+  // boxes below 8 are only used when the extent itself is smaller
+  int lo = 1;
+  while (lo < 8 && lo < extent) lo <<= 1;
+  if (lo > maxbox) lo = maxbox;
+  int best = lo; double best_waste = 1e30;
+  for (int b = lo; b <= maxbox; b <<= 1) {
+    int tiles = (extent + b - 1) / b;
+    double waste = (double)tiles * b / extent;
+    if (waste <= best_waste + 1e-9) { best_waste = waste; best = b; }
+  }
+  return best;
+}
+
+int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* B, int Nout, void* out,
+               const float* scale, const float* shift, int relu, cudaStream_t st) {
+  if (C0 % 32 != 0 || C1 % 32 != 0 || Nout % 32 != 0)
+    return fail(DCB_ERR_UNSUPPORTED, "bf16 tensor-core path needs channel counts that are multiples of 32 "
+                "(got C0=%d C1=%d Cout=%d); use the fp32 check mode for other widths", C0, C1, Nout);
+  if (Nout > 512) return fail(DCB_ERR_UNSUPPORTED, "bf16 tensor-core path supports at most 512 output channels (got %d)", Nout);
+  TcFwdParams p;
+  memset(&p, 0, sizeof(p));
+  const int ntaps = g.ntaps;
+  const bool convT_fwd = g.zsub > 1;
+  const bool convT_dgrad = (g.sy == 2);
+  p.mode = convT_fwd ? 1 : (convT_dgrad ? 2 : 0);
+  p.N = g.N; p.GH = g.GH; p.GW = g.GW;
+  p.ntaps = ntaps;
+  for (int t = 0; t < ntaps; ++t) { p.dy[t] = g.dy[t]; p.dx[t] = g.dx[t]; }
+  p.C0 = C0; p.C1 = C1;
+  p.BK = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
+  const int swz = p.BK * 2;
+  p.Cz = Nout;
+  p.Ntot = convT_fwd ? 4 * Nout : Nout;
+  p.OH = g.OH; p.OW = g.OW; p.OC = Nout;
+  p.osy = g.osy; p.osx = g.osx; p.ody = g.ody; p.odx = g.odx;
+  p.relu = relu; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.scale = scale; p.shift = shift;
+
+  // ---- M tiling
+  if (p.mode == 0) {
+    p.bw = pick_pow2_box(g.GW, TC_BM);
+    p.bh = pick_pow2_box(g.GH, TC_BM / p.bw);
+    p.bn = TC_BM / (p.bw * p.bh);
+    p.tiles_w = cdiv(g.GW, p.bw); p.tiles_h = cdiv(g.GH, p.bh); p.tiles_n = cdiv(g.N, p.bn);
+  } else {
+    p.bw = pick_pow2_box(g.GW, TC_BM);
+    p.bh = TC_BM / p.bw; p.bn = 1;
+    p.tiles_w = cdiv(g.GW, p.bw); p.tiles_h = cdiv((long long)g.N * g.GH, p.bh); p.tiles_n = 1;
+  }
+  const int num_mtiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  // ---- N tiling: largest tile that still gives every SM work
+  int BN = p.Cz < 256 ? p.Cz : 256;
+  while (BN > 64 && (long long)num_mtiles * (p.Ntot / BN) < sm_count() && p.Cz % (BN / 2) == 0) BN /= 2;
+  if (p.Cz % BN != 0) BN = 32;
+  p.BN = BN;
+  const size_t stage_bytes = (size_t)TC_BM * p.BK * 2 + (size_t)BN * p.BK * 2;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (stages < 2) return fail(DCB_ERR_UNSUPPORTED, "tile does not fit shared memory");
+  p.stages = stages;
+  const size_t dyn_smem = stages * stage_bytes + 1024;
+
+  // ---- tensor maps
+  CUtensorMap mA0, mA1, mB;
+  auto make_src_map = [&](CUtensorMap* m, const void* ptr, int C) -> int {
+    if (p.mode == 0) {
+      uint64_t dims[4] = {(uint64_t)C, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.N};
+      uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)g.IW * C * 2, (uint64_t)g.IH * g.IW * C * 2};
+      uint32_t box[4] = {(uint32_t)p.BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+      return make_map(m, ptr, 4, dims, str, box, swz);
+    } else if (p.mode == 1) {
+      uint64_t dims[3] = {(uint64_t)C, (uint64_t)g.IW, (uint64_t)g.N * g.IH};
+      uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)g.IW * C * 2};
+      uint32_t box[3] = {(uint32_t)p.BK, (uint32_t)p.bw, (uint32_t)p.bh};
+      return make_map(m, ptr, 3, dims, str, box, swz);
+    } else {
+      // dy [N][2h][2w][C] viewed as [N*h][a=2][w][b=2][C] -> innermost first {C, b, w, a, N*h}
+      uint64_t dims[5] = {(uint64_t)C, 2, (uint64_t)g.GW, 2, (uint64_t)g.N * g.GH};
+      uint64_t str[4] = {(uint64_t)C * 2, (uint64_t)2 * C * 2, (uint64_t)g.IW * C * 2, (uint64_t)2 * g.IW * C * 2};
+      uint32_t box[5] = {(uint32_t)p.BK, 1, (uint32_t)p.bw, 1, (uint32_t)p.bh};
+      return make_map(m, ptr, 5, dims, str, box, swz);
+    }
+  };
+  if (int e = make_src_map(&mA0, s0, C0)) return e;
+  if (C1 > 0) { if (int e = make_src_map(&mA1, s1, C1)) return e; }
+  else mA1 = mA0;
+  {
+    const int Ktot = ntaps * (C0 + C1);
+    uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)p.Ntot};
+    uint64_t str[1] = {(uint64_t)Ktot * 2};
+    uint32_t box[2] = {(uint32_t)p.BK, (uint32_t)BN};
+    if (int e = make_map(&mB, B, 2, dims, str, box, swz)) return e;
+  }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int num_tiles = num_mtiles * (p.Ntot / BN);
+  const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  tapgemm_tc_fwd_kernel<<<grid, TC_THREADS, dyn_smem, st>>>(mA0, mA1, mB, p);
+  g_launches += 1;
+  DCB_LAUNCH_OK("tapgemm_tc_fwd_kernel");
+  return DCB_OK;
+}
+
+// ====================================================================================== wgrad
+// part[split][tap][k][n] = sum over the split's pixels of A(pixel, tap, k) * G(pixel, n)
+// UMMA: D[128 k-channels x BN n-channels] += A_sm^T * G_sm with the PIXEL axis as the MMA K dimension.
+// Both operands sit in shared memory exactly as TMA delivers an NHWC box ([pixel rows][CB channels],
+// swizzled), i.e. MN-major for the MMA: column blocks of CB channels are LBO apart, 8-pixel groups SBO apart.
+constexpr int WG_P = 64;            // pixels per pipeline stage (4 UMMA K-steps of 16)
+
+struct TcWgradParams {
+  int mode;                 // 0: conv3x3 (4-D halo box for A, 4-D box for G)  2: convT (5-D strided A, 3-D merged G)
+  int N, GH, GW;
+  int bw, bh, bn;           // pixel box (bw*bh*bn = WG_P); mode 2: bh rows of the merged axis
+  int tiles_w, tiles_h, tiles_n;
+  int ntaps;
+  int dy[9], dx[9];
+  int C0, C1, CB;           // gathered operand: channels per source, channels per TMA box
+  int Nout, CBG, BN;        // per-position operand: channels, channels per TMA box, n tile
+  int splits;
+  int stages;
+  float* part;              // [splits][ntaps][K][Nout]
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tapgemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                        const __grid_constant__ CUtensorMap mapG, const TcWgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_base_smem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int K = p.C0 + p.C1;
+  const int ktiles = (K + 127) / 128, ntiles = p.Nout / p.BN;
+  const int num_ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int num_items = ktiles * ntiles * p.ntaps * p.splits;
+  const uint32_t a_blk_bytes = WG_P * p.CB * 2, g_blk_bytes = WG_P * p.CBG * 2;
+  const uint32_t a_bytes = WG_P * 128 * 2, g_bytes = WG_P * p.BN * 2;
+  const uint32_t stage_bytes = a_bytes + g_bytes;
+  const int a_blks = 128 / p.CB, g_blks = p.BN / p.CBG;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * p.BN) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA0);
+    if (p.C1 > 0) tma_prefetch_desc(&mapA1);
+    tma_prefetch_desc(&mapG);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 4); }
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(&tmem_base_smem, tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  // item -> (ktile, ntile, tap, split): ktile fastest so neighbouring CTAs share the G tile in L2
+  auto decode = [&](int item, int& kt, int& nt, int& tap, int& split) {
+    kt = item % ktiles; item /= ktiles;
+    nt = item % ntiles; item /= ntiles;
+    tap = item % p.ntaps; split = item / p.ntaps;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int kt, nt, tap, split;
+        decode(item, kt, nt, tap, split);
+        const int pt0 = (int)(((long long)num_ptiles * split) / p.splits);
+        const int pt1 = (int)(((long long)num_ptiles * (split + 1)) / p.splits);
+        // real column blocks of this k tile
+        int nreal = 0;
+        for (int b = 0; b < a_blks; ++b) if (kt * 128 + b * p.CB < K) ++nreal;
+        const uint32_t tx = nreal * a_blk_bytes + g_bytes;
+        for (int pt = pt0; pt < pt1; ++pt) {
+          const int tw = pt % p.tiles_w, th = (pt / p.tiles_w) % p.tiles_h, tn = pt / (p.tiles_w * p.tiles_h);
+          const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+          mbar_wait(&bar_empty[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          uint8_t* sg = sa + a_bytes;
+          mbar_arrive_expect_tx(&bar_full[stage], tx);
+          for (int b = 0; b < a_blks; ++b) {
+            const int kg = kt * 128 + b * p.CB;
+            if (kg >= K) break;
+            const bool second = kg >= p.C0;
+            const int c0 = second ? kg - p.C0 : kg;
+            const CUtensorMap* mA = second ? &mapA1 : &mapA0;
+            if (p.mode == 0) tma_load_4d(mA, &bar_full[stage], sa + b * a_blk_bytes, c0, w0 + p.dx[tap], h0 + p.dy[tap], n0);
+            else tma_load_5d(mA, &bar_full[stage], sa + b * a_blk_bytes, c0, p.dx[tap], w0, p.dy[tap], h0);
+          }
+          for (int b = 0; b < g_blks; ++b) {
+            const int c0 = nt * p.BN + b * p.CBG;
+            if (p.mode == 0) tma_load_4d(&mapG, &bar_full[stage], sg + b * g_blk_bytes, c0, w0, h0, n0);
+            else tma_load_3d(&mapG, &bar_full[stage], sg + b * g_blk_bytes, c0, w0, h0);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(128, p.BN, 1, 1);
+      const uint32_t swz_a = (p.CB == 64) ? SWZ_128B : SWZ_64B, swz_g = (p.CBG == 64) ? SWZ_128B : SWZ_64B;
+      const uint32_t sbo_a = 8u * p.CB * 2u, sbo_g = 8u * p.CBG * 2u;
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int kt, nt, tap, split;
+        decode(item, kt, nt, tap, split);
+        const int pt0 = (int)(((long long)num_ptiles * split) / p.splits);
+        const int pt1 = (int)(((long long)num_ptiles * (split + 1)) / p.splits);
+        mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+        for (int pt = pt0; pt < pt1; ++pt) {
+          mbar_wait(&bar_full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sg = sa + a_bytes;
+#pragma unroll
+          for (int k = 0; k < WG_P / 16; ++k) {
+            // 16 pixels = two 8-row groups further down the box
+            const uint64_t da = make_smem_desc(sa + k * 2 * sbo_a, a_blk_bytes, sbo_a, swz_a);
+            const uint64_t dg = make_smem_desc(sg + k * 2 * sbo_g, g_blk_bytes, sbo_g, swz_g);
+            umma_bf16(d_tmem, da, dg, idesc, (pt > pt0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&bar_empty[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&bar_tfull[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;             // k channel within the tile
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int kt, nt, tap, split;
+      decode(item, kt, nt, tap, split);
+      const int pt0 = (int)(((long long)num_ptiles * split) / p.splits);
+      const int pt1 = (int)(((long long)num_ptiles * (split + 1)) / p.splits);
+      const int kg = kt * 128 + row;
+      float* dst = p.part + (((size_t)split * p.ntaps + tap) * K + kg) * p.Nout + nt * p.BN;
+      mbar_wait(&bar_tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN);
+      for (int c = 0; c < p.BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_addr + c, r);
+        tmem_ld_wait();
+        if (kg < K) {
+          if (pt1 > pt0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<uint4*>(dst + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+          } else {                                   // empty split: nothing was accumulated
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(dst + c + j) = make_uint4(0, 0, 0, 0);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+void launch_reduce_splits(const float* part, int splits, size_t n, float* out, cudaStream_t st);
+
+struct WgradPlan { int BN, splits, CB, CBG, bw, bh, bn, tiles_w, tiles_h, tiles_n, stages; size_t ws_bytes; };
+
+static WgradPlan plan_wgrad(const TapGeom& g, int K, int C0, int C1, int Nout) {
+  WgradPlan w;
+  const bool convT = (g.sy == 2);
+  w.CB = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
+  w.CBG = (Nout % 64 == 0) ? 64 : 32;
+  w.BN = Nout < 256 ? Nout : 256;
+  if (Nout % w.BN != 0) w.BN = 32;
+  if (!convT) {
+    w.bw = pick_pow2_box(g.GW, WG_P);
+    w.bh = pick_pow2_box(g.GH, WG_P / w.bw);
+    w.bn = WG_P / (w.bw * w.bh);
+    w.tiles_w = cdiv(g.GW, w.bw); w.tiles_h = cdiv(g.GH, w.bh); w.tiles_n = cdiv(g.N, w.bn);
+  } else {
+    w.bw = pick_pow2_box(g.GW, WG_P);
+    w.bh = WG_P / w.bw; w.bn = 1;
+    w.tiles_w = cdiv(g.GW, w.bw); w.tiles_h = cdiv((long long)g.N * g.GH, w.bh); w.tiles_n = 1;
+  }
+  const int num_ptiles = w.tiles_w * w.tiles_h * w.tiles_n;
+  const int base_items = cdiv(K, 128) * (Nout / w.BN) * g.ntaps;
+  int splits = cdiv(2 * sm_count(), base_items);
+  if (splits > num_ptiles) splits = num_ptiles;
+  if (splits > 64) splits = 64;
+  if (splits < 1) splits = 1;
+  w.splits = splits;
+  const size_t stage_bytes = (size_t)WG_P * 128 * 2 + (size_t)WG_P * w.BN * 2;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  w.stages = stages;
+  w.ws_bytes = (size_t)splits * g.ntaps * K * Nout * sizeof(float);
+  return w;
+}
+
+size_t tc_wgrad_workspace(const TapGeom& g, int K, int Nout) {
+  // C0/C1 split does not change the split count; use a conservative plan
+  return plan_wgrad(g, K, K, 0, Nout).ws_bytes;
+}
+
+int run_tc_wgrad(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* G, int Nout, float* dW,
+                 void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (C0 % 32 != 0 || C1 % 32 != 0 || Nout % 32 != 0)
+    return fail(DCB_ERR_UNSUPPORTED, "bf16 tensor-core wgrad needs channel counts that are multiples of 32 "
+                "(got C0=%d C1=%d N=%d)", C0, C1, Nout);
+  const int K = C0 + C1;
+  const WgradPlan w = plan_wgrad(g, K, C0, C1, Nout);
+  if (!ws || ws_bytes < w.ws_bytes) return fail(DCB_ERR_WORKSPACE, "wgrad (bf16): workspace %zu B < required %zu B", ws_bytes, w.ws_bytes);
+  const bool convT = (g.sy == 2);
+  TcWgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = convT ? 2 : 0;
+  p.N = g.N; p.GH = g.GH; p.GW = g.GW;
+  p.bw = w.bw; p.bh = w.bh; p.bn = w.bn; p.tiles_w = w.tiles_w; p.tiles_h = w.tiles_h; p.tiles_n = w.tiles_n;
+  p.ntaps = g.ntaps;
+  for (int t = 0; t < g.ntaps; ++t) { p.dy[t] = g.dy[t]; p.dx[t] = g.dx[t]; }
+  p.C0 = C0; p.C1 = C1; p.CB = w.CB; p.Nout = Nout; p.CBG = w.CBG; p.BN = w.BN;
+  p.splits = w.splits; p.stages = w.stages; p.part = reinterpret_cast<float*>(ws);
+
+  CUtensorMap mA0, mA1, mG;
+  auto make_a = [&](CUtensorMap* m, const void* ptr, int C) -> int {
+    if (!convT) {
+      uint64_t dims[4] = {(uint64_t)C, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.N};
+      uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)g.IW * C * 2, (uint64_t)g.IH * g.IW * C * 2};
+      uint32_t box[4] = {(uint32_t)w.CB, (uint32_t)w.bw, (uint32_t)w.bh, (uint32_t)w.bn};
+      return make_map(m, ptr, 4, dims, str, box, w.CB * 2);
+    }
+    uint64_t dims[5] = {(uint64_t)C, 2, (uint64_t)g.GW, 2, (uint64_t)g.N * g.GH};
+    uint64_t str[4] = {(uint64_t)C * 2, (uint64_t)2 * C * 2, (uint64_t)g.IW * C * 2, (uint64_t)2 * g.IW * C * 2};
+    uint32_t box[5] = {(uint32_t)w.CB, 1, (uint32_t)w.bw, 1, (uint32_t)w.bh};
+    return make_map(m, ptr, 5, dims, str, box, w.CB * 2);
+  };
+  if (int e = make_a(&mA0, s0, C0)) return e;
+  if (C1 > 0) { if (int e = make_a(&mA1, s1, C1)) return e; } else mA1 = mA0;
+  if (!convT) {
+    uint64_t dims[4] = {(uint64_t)Nout, (uint64_t)g.GW, (uint64_t)g.GH, (uint64_t)g.N};
+    uint64_t str[3] = {(uint64_t)Nout * 2, (uint64_t)g.GW * Nout * 2, (uint64_t)g.GH * g.GW * Nout * 2};
+    uint32_t box[4] = {(uint32_t)w.CBG, (uint32_t)w.bw, (uint32_t)w.bh, (uint32_t)w.bn};
+    if (int e = make_map(&mG, G, 4, dims, str, box, w.CBG * 2)) return e;
+  } else {
+    uint64_t dims[3] = {(uint64_t)Nout, (uint64_t)g.GW, (uint64_t)g.N * g.GH};
+    uint64_t str[2] = {(uint64_t)Nout * 2, (uint64_t)g.GW * Nout * 2};
+    uint32_t box[3] = {(uint32_t)w.CBG, (uint32_t)w.bw, (uint32_t)w.bh};
+    if (int e = make_map(&mG, G, 3, dims, str, box, w.CBG * 2)) return e;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const size_t stage_bytes = (size_t)WG_P * 128 * 2 + (size_t)WG_P * w.BN * 2;
+  const size_t dyn_smem = w.stages * stage_bytes + 1024;
+  const int num_items = cdiv(K, 128) * (Nout / w.BN) * g.ntaps * w.splits;
+  const int grid = num_items < sm_count() ? num_items : sm_count();
+  tapgemm_tc_wgrad_kernel<<<grid, TC_THREADS, dyn_smem, st>>>(mA0, mA1, mG, p);
+  DCB_LAUNCH_OK("tapgemm_tc_wgrad_kernel");
+  launch_reduce_splits(p.part, w.splits, (size_t)g.ntaps * K * Nout, dW, st);
+  g_launches += 2;
+  DCB_LAUNCH_OK("reduce_splits_kernel");
+  return DCB_OK;
+}
 
 }  // namespace dcb
