@@ -362,7 +362,7 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
     if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -634,7 +634,7 @@ int run_tc_wgrad(const TapGeom& g, const void* s0, int C0, const void* s1, int C
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
     if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
