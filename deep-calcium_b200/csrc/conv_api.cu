@@ -18,7 +18,7 @@ int run_f32_wgrad(const TapGeom& g, const float* s0, int C0, const float* s1, in
 
 // tcgen05 path (tapgemm_tc.cu)
 int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* B, int Nout, void* out,
-               const float* scale, const float* shift, int relu, cudaStream_t st);
+               const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st);
 int run_tc_wgrad(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* G, int Nout, float* dW,
                  void* ws, size_t ws_bytes, cudaStream_t st);
 size_t tc_wgrad_workspace(const TapGeom& g, int K, int Nout);
@@ -107,7 +107,20 @@ extern "C" int dcb_conv3x3_fwd(int dtype, const void* src0, int C0, const void* 
     return run_f32_fwd(g, (const float*)src0, C0, (const float*)src1, C1, (const float*)wgt, Cout, (float*)out, scale,
                        shift, relu, (cudaStream_t)stream);
   if (dtype == DCB_BF16)
-    return run_tc_fwd(g, src0, C0, src1, C1, wgt, Cout, out, scale, shift, relu, (cudaStream_t)stream);
+    return run_tc_fwd(g, src0, C0, src1, C1, wgt, Cout, out, scale, shift, relu, 0, (cudaStream_t)stream);
+  return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+}
+
+extern "C" int dcb_conv3x3_dgrad(int dtype, const void* dy, int Cout, int N, int H, int W, const void* wgt_dgrad, int Cin,
+                                 float* dx, dcb_stream_t stream) {
+  DCB_CHECK_ARG(dy && wgt_dgrad && dx && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "dcb_conv3x3_dgrad: bad arguments");
+  TapGeom g;
+  geom_conv3x3(g, N, H, W);
+  if (dtype == DCB_F32)
+    return run_f32_fwd(g, (const float*)dy, Cout, nullptr, 0, (const float*)wgt_dgrad, Cin, dx, nullptr, nullptr, 0,
+                       (cudaStream_t)stream);
+  if (dtype == DCB_BF16)
+    return run_tc_fwd(g, dy, Cout, nullptr, 0, wgt_dgrad, Cin, dx, nullptr, nullptr, 0, 1, (cudaStream_t)stream);
   return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
 }
 
@@ -120,20 +133,20 @@ extern "C" int dcb_convT2x2_fwd(int dtype, const void* src, int Cin, int N, int 
     return run_f32_fwd(g, (const float*)src, Cin, nullptr, 0, (const float*)wgt, Cout, (float*)out, scale, shift, relu,
                        (cudaStream_t)stream);
   if (dtype == DCB_BF16)
-    return run_tc_fwd(g, src, Cin, nullptr, 0, wgt, Cout, out, scale, shift, relu, (cudaStream_t)stream);
+    return run_tc_fwd(g, src, Cin, nullptr, 0, wgt, Cout, out, scale, shift, relu, 0, (cudaStream_t)stream);
   return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
 }
 
 extern "C" int dcb_convT2x2_dgrad(int dtype, const void* dy, int Cout, int N, int h, int w, const void* wgt, int Cin,
-                                  void* dx, dcb_stream_t stream) {
+                                  float* dx, dcb_stream_t stream) {
   DCB_CHECK_ARG(dy && wgt && dx && N > 0 && h > 0 && w > 0 && Cin > 0 && Cout > 0, "dcb_convT2x2_dgrad: bad arguments");
   TapGeom g;
   geom_convT_dgrad(g, N, h, w);
   if (dtype == DCB_F32)
-    return run_f32_fwd(g, (const float*)dy, Cout, nullptr, 0, (const float*)wgt, Cin, (float*)dx, nullptr, nullptr, 0,
+    return run_f32_fwd(g, (const float*)dy, Cout, nullptr, 0, (const float*)wgt, Cin, dx, nullptr, nullptr, 0,
                        (cudaStream_t)stream);
   if (dtype == DCB_BF16)
-    return run_tc_fwd(g, dy, Cout, nullptr, 0, wgt, Cin, dx, nullptr, nullptr, 0, (cudaStream_t)stream);
+    return run_tc_fwd(g, dy, Cout, nullptr, 0, wgt, Cin, dx, nullptr, nullptr, 0, 1, (cudaStream_t)stream);
   return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
 }
 

@@ -117,7 +117,7 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, long long M, int C, con
 // dz = dY * keepscale * [x*scale+shift > 0];  sums[c] += dz ; sums[C+c] += dz * xhat, xhat = (x-mean)*rstd
 template <typename T>
 __global__ void __launch_bounds__(256)
-bn_bwd_reduce_kernel(const T* __restrict__ dy, int ldy, int offy, const T* __restrict__ x, long long M, int C,
+bn_bwd_reduce_kernel(const float* __restrict__ dy, int ldy, int offy, const T* __restrict__ x, long long M, int C,
                      const float* __restrict__ scale, const float* __restrict__ shift,
                      const float* __restrict__ mean, const float* __restrict__ rstd, float p_drop,
                      unsigned long long seed, const unsigned long long* __restrict__ seed_dev, uint32_t layer,
@@ -135,7 +135,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, int ldy, int offy, const T* __res
     const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
     const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
     for (long long r = r0 + tr; r < r1; r += rows_par) {
-      float4 g = load4<T>(dy + r * ldy + offy + c);
+      float4 g = load4<float>(dy + r * ldy + offy + c);
       const float4 v = load4<T>(x + r * C + c);
       if (p_drop > 0.f) {
         const float4 k = dropout_scale4(seed, layer, (unsigned long long)((r * C + c) >> 2), p_drop);
@@ -164,26 +164,27 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, int ldy, int offy, const T* __res
 
 // d_raw = scale * (dz - mean(dz) - xhat * mean(dz*xhat));  block 0 also emits dgamma/dbeta
 template <typename T>
-__global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, int ldy, int offy, const T* __restrict__ x, long long M,
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int ldy, int offy, const T* __restrict__ x, long long M,
                                     int C, const float* __restrict__ scale, const float* __restrict__ shift,
                                     const float* __restrict__ mean, const float* __restrict__ rstd, float p_drop,
                                     unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
-                                    uint32_t layer, const double* __restrict__ sums,
-                                    T* __restrict__ draw, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                    uint32_t layer, const double* __restrict__ sums, long long M_total,
+                                    float dgb_scale, T* __restrict__ draw, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta) {
   if (seed_dev) seed ^= *seed_dev;
   if (blockIdx.x == 0) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      if (dbeta) dbeta[c] = (float)sums[c];
-      if (dgamma) dgamma[c] = (float)sums[C + c];
+      if (dbeta) dbeta[c] = (float)(sums[c] * (double)dgb_scale);
+      if (dgamma) dgamma[c] = (float)(sums[C + c] * (double)dgb_scale);
     }
   }
-  const double invM = 1.0 / (double)M;
+  const double invM = 1.0 / (double)M_total;
   const long long n4 = M * (C >> 2);
   const int c4n = C >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / c4n;
     const int c = (int)(i % c4n) * 4;
-    float4 g = load4<T>(dy + r * ldy + offy + c);
+    float4 g = load4<float>(dy + r * ldy + offy + c);
     const float4 v = load4<T>(x + r * C + c);
     if (p_drop > 0.f) {
       const float4 k = dropout_scale4(seed, layer, (unsigned long long)i, p_drop);
@@ -225,9 +226,9 @@ __global__ void maxpool2x2_kernel(const T* __restrict__ x, int N, int H, int W, 
 
 // out[n,h,w,c] = skipgrad[n,h,w, off+c] + (first position in the 2x2 window whose y equals the pooled max ? dpool : 0)
 template <typename T>
-__global__ void pool_bwd_add_kernel(const T* __restrict__ skipgrad, int lds, int offs, const T* __restrict__ y,
-                                    const T* __restrict__ pooled, const T* __restrict__ dpool, int N, int H, int W,
-                                    int C, T* __restrict__ out) {
+__global__ void pool_bwd_add_kernel(const float* __restrict__ skipgrad, int lds, int offs, const T* __restrict__ y,
+                                    const T* __restrict__ pooled, const float* __restrict__ dpool, int N, int H, int W,
+                                    int C, float* __restrict__ out) {
   const int OH = H / 2, OW = W / 2, c4n = C >> 2;
   const long long n4 = (long long)N * OH * OW * c4n;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -236,18 +237,18 @@ __global__ void pool_bwd_add_kernel(const T* __restrict__ skipgrad, int lds, int
     const int ow = (int)(t % OW); t /= OW;
     const int oh = (int)(t % OH); const int n = (int)(t / OH);
     const float4 pm = load4<T>(pooled + i * 4);
-    const float4 dp = load4<T>(dpool + i * 4);
+    const float4 dp = load4<float>(dpool + i * 4);
     bool done[4] = {false, false, false, false};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const long long pix = ((long long)n * H + 2 * oh + (q >> 1)) * W + 2 * ow + (q & 1);
       const float4 v = load4<T>(y + pix * C + c);
-      float4 g = skipgrad ? load4<T>(skipgrad + pix * lds + offs + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 g = skipgrad ? load4<float>(skipgrad + pix * lds + offs + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       if (!done[0] && v.x == pm.x) { g.x += dp.x; done[0] = true; }
       if (!done[1] && v.y == pm.y) { g.y += dp.y; done[1] = true; }
       if (!done[2] && v.z == pm.z) { g.z += dp.z; done[2] = true; }
       if (!done[3] && v.w == pm.w) { g.w += dp.w; done[3] = true; }
-      store4<T>(out + pix * C + c, g);
+      store4<float>(out + pix * C + c, g);
     }
   }
 }
@@ -343,14 +344,14 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 head_loss_bwd_kernel(const T* __restrict__ x, long long M, int C, const float* __restrict__ w,
                      const uint8_t* __restrict__ yt, const float* __restrict__ prob, const double* __restrict__ sums,
-                     int loss, T* __restrict__ dx, double* __restrict__ dwb) {
+                     int loss, long long M_total, float* __restrict__ dx, double* __restrict__ dwb) {
   __shared__ float wd[512];
   __shared__ float accw[512];
   __shared__ float accb;
   for (int c = threadIdx.x; c < C; c += blockDim.x) { wd[c] = w[c * 2 + 1] - w[c * 2]; accw[c] = 0.f; }
   if (threadIdx.x == 0) accb = 0.f;
   __syncthreads();
-  const double invM = 1.0 / (double)M;
+  const double invM = 1.0 / (double)M_total;
   const int lane = threadIdx.x & 31;
   float myw[16];                 // lane l owns channels l, l+32, ... (C <= 512)
 #pragma unroll
@@ -371,7 +372,7 @@ head_loss_bwd_kernel(const T* __restrict__ x, long long M, int C, const float* _
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (valid) {
         v = load4<T>(x + m * C + c);
-        store4<T>(dx + m * C + c, make_float4(dz1 * wd[c], dz1 * wd[c + 1], dz1 * wd[c + 2], dz1 * wd[c + 3]));
+        store4<float>(dx + m * C + c, make_float4(dz1 * wd[c], dz1 * wd[c + 1], dz1 * wd[c + 2], dz1 * wd[c + 3]));
       }
       const float r0 = warp_sum(v.x * dz1), r1 = warp_sum(v.y * dz1), r2 = warp_sum(v.z * dz1), r3 = warp_sum(v.w * dz1);
       const int slot = c >> 5, l0 = c & 31;
@@ -592,7 +593,7 @@ extern "C" int dcb_bn_apply(int dtype, const void* x, long long M, int C, const 
   return DCB_OK;
 }
 
-extern "C" int dcb_bn_bwd_reduce(int dtype, const void* dy, int ldy, int offy, const void* x, long long M, int C,
+extern "C" int dcb_bn_bwd_reduce(int dtype, const float* dy, int ldy, int offy, const void* x, long long M, int C,
                                  const float* scale, const float* shift, const float* mean, const float* rstd,
                                  float p_drop, unsigned long long seed, const unsigned long long* seed_dev, unsigned layer,
                                  double* sums, dcb_stream_t stream) {
@@ -601,20 +602,22 @@ extern "C" int dcb_bn_bwd_reduce(int dtype, const void* dy, int ldy, int offy, c
   if (int e = check_c(C, "dcb_bn_bwd_reduce")) return e;
   int grid = (int)((M + 255) / 256); if (grid > sm_count() * 8) grid = sm_count() * 8;
   DISPATCH_T(dtype, bn_bwd_reduce_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const T*)dy, ldy, offy, (const T*)x, M, C, scale, shift, mean, rstd, p_drop, seed, seed_dev, layer, sums);)
+      (const float*)dy, ldy, offy, (const T*)x, M, C, scale, shift, mean, rstd, p_drop, seed, seed_dev, layer, sums);)
   g_launches += 1;
   DCB_LAUNCH_OK("bn_bwd_reduce_kernel");
   return DCB_OK;
 }
 
-extern "C" int dcb_bn_bwd_apply(int dtype, const void* dy, int ldy, int offy, const void* x, long long M, int C,
+extern "C" int dcb_bn_bwd_apply(int dtype, const float* dy, int ldy, int offy, const void* x, long long M, int C,
                                 const float* scale, const float* shift, const float* mean, const float* rstd,
                                 float p_drop, unsigned long long seed, const unsigned long long* seed_dev, unsigned layer,
-                                const double* sums, void* draw, float* dgamma, float* dbeta, dcb_stream_t stream) {
+                                const double* sums, long long M_total, float dgb_scale, void* draw, float* dgamma,
+                                float* dbeta, dcb_stream_t stream) {
+  if (M_total <= 0) M_total = M;
   DCB_CHECK_ARG(dy && x && scale && shift && mean && rstd && sums && draw && M > 0, "dcb_bn_bwd_apply: bad arguments");
   DCB_CHECK_ARG(ldy % 4 == 0 && offy % 4 == 0 && offy + C <= ldy && C % 4 == 0, "dcb_bn_bwd_apply: bad dy view");
   DISPATCH_T(dtype, bn_bwd_apply_kernel<T><<<ew_grid(M * C / 4, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const T*)dy, ldy, offy, (const T*)x, M, C, scale, shift, mean, rstd, p_drop, seed, seed_dev, layer, sums, (T*)draw, dgamma, dbeta);)
+      (const float*)dy, ldy, offy, (const T*)x, M, C, scale, shift, mean, rstd, p_drop, seed, seed_dev, layer, sums, M_total, dgb_scale, (T*)draw, dgamma, dbeta);)
   g_launches += 1;
   DCB_LAUNCH_OK("bn_bwd_apply_kernel");
   return DCB_OK;
@@ -629,12 +632,12 @@ extern "C" int dcb_maxpool2x2(int dtype, const void* x, int N, int H, int W, int
   return DCB_OK;
 }
 
-extern "C" int dcb_pool_bwd_add(int dtype, const void* skipgrad, int lds, int offs, const void* y, const void* pooled,
-                                const void* dpool, int N, int H, int W, int C, void* out, dcb_stream_t stream) {
+extern "C" int dcb_pool_bwd_add(int dtype, const float* skipgrad, int lds, int offs, const void* y, const void* pooled,
+                                const float* dpool, int N, int H, int W, int C, float* out, dcb_stream_t stream) {
   DCB_CHECK_ARG(y && pooled && dpool && out && N > 0 && H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "dcb_pool_bwd_add: bad arguments");
   DCB_CHECK_ARG(!skipgrad || (lds % 4 == 0 && offs % 4 == 0 && offs + C <= lds), "dcb_pool_bwd_add: bad skip-gradient view");
   DISPATCH_T(dtype, pool_bwd_add_kernel<T><<<ew_grid((long long)N * (H / 2) * (W / 2) * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(
-      (const T*)skipgrad, lds, offs, (const T*)y, (const T*)pooled, (const T*)dpool, N, H, W, C, (T*)out);)
+      (const float*)skipgrad, lds, offs, (const T*)y, (const T*)pooled, (const float*)dpool, N, H, W, C, (float*)out);)
   g_launches += 1;
   DCB_LAUNCH_OK("pool_bwd_add_kernel");
   return DCB_OK;
@@ -659,15 +662,16 @@ extern "C" int dcb_head_loss_fwd(int dtype, const void* x, long long M, int C, c
 }
 
 extern "C" int dcb_head_loss_bwd(int dtype, const void* x, long long M, int C, const float* w, const uint8_t* yt,
-                                 const float* prob, const double* sums, int loss, void* dx, double* dwb_accum,
-                                 float* dw_out, float* metrics_out, dcb_stream_t stream) {
+                                 const float* prob, const double* sums, int loss, long long M_total, float* dx,
+                                 double* dwb_accum, float* dw_out, float* metrics_out, dcb_stream_t stream) {
+  if (M_total <= 0) M_total = M;
   DCB_CHECK_ARG(x && w && yt && prob && sums && dx && dwb_accum && dw_out && metrics_out && M > 0 && C % 4 == 0 && C <= 512,
                 "dcb_head_loss_bwd: bad arguments");
   DCB_CHECK_ARG(loss >= 0 && loss <= 3, "dcb_head_loss_bwd: unknown loss id %d", loss);
   int grid = ew_grid(M, 256); if (grid > sm_count() * 4) grid = sm_count() * 4;
-  DISPATCH_T(dtype, head_loss_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, M, C, w, yt, prob, sums, loss, (T*)dx, dwb_accum);)
+  DISPATCH_T(dtype, head_loss_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, M, C, w, yt, prob, sums, loss, M_total, (float*)dx, dwb_accum);)
   DCB_LAUNCH_OK("head_loss_bwd_kernel");
-  head_metrics_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(sums, M, loss, metrics_out, dwb_accum, C, dw_out);
+  head_metrics_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(sums, M_total, loss, metrics_out, dwb_accum, C, dw_out);
   g_launches += 2;
   DCB_LAUNCH_OK("head_metrics_kernel");
   return DCB_OK;

@@ -43,6 +43,7 @@ struct TcFwdParams {
   int OH, OW, OC;           // output tensor
   int osy, osx, ody, odx;   // output pixel = g * os + od (+ sub-position for convT fwd)
   int relu;
+  int out_f32;              // 1: store fp32 (gradient tensors), 0: store bf16 (activations)
   int stages;
   __nv_bfloat16* out;
   const float* scale;
@@ -174,7 +175,9 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
       const int ng0 = nt * p.BN;                     // first GEMM column of this tile
       const int z = ng0 / p.Cz, cbase = ng0 % p.Cz;  // sub-position (convT fwd) and channel base
       const int ody = p.Cz < p.Ntot ? (z >> 1) : p.ody, odx = p.Cz < p.Ntot ? (z & 1) : p.odx;
-      __nv_bfloat16* orow = p.out + (((size_t)n * p.OH + (gh * p.osy + ody)) * p.OW + (gw * p.osx + odx)) * p.OC + cbase;
+      const size_t oidx = (((size_t)n * p.OH + (gh * p.osy + ody)) * p.OW + (gw * p.osx + odx)) * p.OC + cbase;
+      __nv_bfloat16* orow = p.out + oidx;
+      float* orow_f = reinterpret_cast<float*>(p.out) + oidx;
 
       mbar_wait(&bar_tfull[acc], acc_phase);
       tc_fence_after();
@@ -183,7 +186,19 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_addr + c, r);
         tmem_ld_wait();
-        if (valid) {
+        if (valid && p.out_f32) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int ch = cbase + c + j + q;
+              v[q] = fmaf(__uint_as_float(r[j + q]), s_scale[ch], s_shift[ch]);
+              if (p.relu) v[q] = fmaxf(v[q], 0.f);
+            }
+            *reinterpret_cast<float4*>(orow_f + c + j) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        } else if (valid) {
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             uint32_t pk[4];
@@ -281,7 +296,7 @@ static int pick_pow2_box(int extent, int maxbox) {
 }
 
 int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* B, int Nout, void* out,
-               const float* scale, const float* shift, int relu, cudaStream_t st) {
+               const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st) {
   if (C0 % 32 != 0 || C1 % 32 != 0 || Nout % 32 != 0)
     return fail(DCB_ERR_UNSUPPORTED, "bf16 tensor-core path needs channel counts that are multiples of 32 "
                 "(got C0=%d C1=%d Cout=%d); use the fp32 check mode for other widths", C0, C1, Nout);
@@ -302,7 +317,7 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
   p.Ntot = convT_fwd ? 4 * Nout : Nout;
   p.OH = g.OH; p.OW = g.OW; p.OC = Nout;
   p.osy = g.osy; p.osx = g.osx; p.ody = g.ody; p.odx = g.odx;
-  p.relu = relu; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.scale = scale; p.shift = shift;
+  p.relu = relu; p.out_f32 = out_f32; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.scale = scale; p.shift = shift;
 
   // ---- M tiling
   if (p.mode == 0) {

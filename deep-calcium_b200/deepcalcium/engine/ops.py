@@ -57,6 +57,14 @@ def conv3x3_fwd(src0, src1, wgt, out, scale=None, shift=None, relu=False):
          ptr(wgt), c_int(Cout), ptr(scale), ptr(shift), c_int(int(relu)), ptr(out), stream_ptr())
 
 
+def conv3x3_dgrad(dy, wgt_dgrad, dx):
+    """dy: [N,H,W,Cout] activation dtype (gradient w.r.t. the raw conv output); dx: fp32 [N,H,W,Cin]."""
+    N, H, W, Cout = dy.shape
+    _chk(dx, torch.float32)
+    call('dcb_conv3x3_dgrad', _dt(dy), ptr(dy), c_int(Cout), c_int(N), c_int(H), c_int(W), ptr(wgt_dgrad),
+         c_int(dx.shape[3]), ptr(dx), stream_ptr())
+
+
 def convT2x2_fwd(src, wgt, out, scale=None, shift=None, relu=False):
     N, h, w, Cin = src.shape
     Cout = out.shape[3]
@@ -65,6 +73,7 @@ def convT2x2_fwd(src, wgt, out, scale=None, shift=None, relu=False):
 
 
 def convT2x2_dgrad(dy, wgt, dx):
+    _chk(dx, torch.float32)
     N, h, w, Cin = dx.shape
     Cout = dy.shape[3]
     call('dcb_convT2x2_dgrad', _dt(dy), ptr(dy), c_int(Cout), c_int(N), c_int(h), c_int(w), ptr(wgt), c_int(Cin),
@@ -165,11 +174,11 @@ def bn_bwd_reduce(dy, ldy, offy, x, scale, shift, mean, rstd, sums, p_drop=0., s
 
 
 def bn_bwd_apply(dy, ldy, offy, x, scale, shift, mean, rstd, sums, draw, dgamma, dbeta, p_drop=0., seed=0,
-                 seed_dev=None, layer=0):
+                 seed_dev=None, layer=0, M_total=0, dgb_scale=1.0):
     C = x.shape[-1]
     call('dcb_bn_bwd_apply', _dt(x), ptr(dy), c_int(ldy), c_int(offy), ptr(x), c_ll(x.numel() // C), c_int(C),
          ptr(scale), ptr(shift), ptr(mean), ptr(rstd), c_f(p_drop), c_ull(seed), ptr(seed_dev), c_uint(layer),
-         ptr(sums), ptr(draw), ptr(dgamma), ptr(dbeta), stream_ptr())
+         ptr(sums), c_ll(M_total), c_f(dgb_scale), ptr(draw), ptr(dgamma), ptr(dbeta), stream_ptr())
 
 
 # ---------------------------------------------------------------- pooling
@@ -198,10 +207,10 @@ def head_loss_fwd(x, w, b, yt, prob, sums):
          ptr(sums), stream_ptr())
 
 
-def head_loss_bwd(x, w, yt, prob, sums, loss_id, dx, dwb_accum, dw_out, metrics_out):
+def head_loss_bwd(x, w, yt, prob, sums, loss_id, dx, dwb_accum, dw_out, metrics_out, M_total=0):
     C = x.shape[-1]
     call('dcb_head_loss_bwd', _dt(x), ptr(x), c_ll(x.numel() // C), c_int(C), ptr(w), ptr(yt), ptr(prob), ptr(sums),
-         c_int(loss_id), ptr(dx), ptr(dwb_accum), ptr(dw_out), ptr(metrics_out), stream_ptr())
+         c_int(loss_id), c_ll(M_total), ptr(dx), ptr(dwb_accum), ptr(dw_out), ptr(metrics_out), stream_ptr())
 
 
 # ---------------------------------------------------------------- TTA

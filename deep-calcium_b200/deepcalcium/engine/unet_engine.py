@@ -41,6 +41,7 @@ class UNetEngine(object):
         self._sessions = {}
         self.iteration = 0
         self.launches = 0
+        self.comm = None          # engine.dist.Comm for data-parallel training (None = single GPU)
         self.set_weights_dict(he_normal_weights(self.spec, seed=0))
 
     # ------------------------------------------------------------------ parameter storage
@@ -189,20 +190,21 @@ class UNetEngine(object):
             if training:
                 s['raw'][blk.name] = torch.empty(NB, h, w, blk.cout, **T)
                 if blk.name != 'enc0a':
+                    # gradient tensors are fp32 in both precisions (see dcb_conv3x3_dgrad)
                     if blk.kind == 'conv':
-                        s['dx'][blk.name] = torch.empty(NB, h, w, blk.cin, **T)
+                        s['dx'][blk.name] = torch.empty(NB, h, w, blk.cin, dtype=torch.float32, device=self.dev)
                     else:
-                        s['dx'][blk.name] = torch.empty(NB, h // 2, w // 2, blk.cin, **T)
+                        s['dx'][blk.name] = torch.empty(NB, h // 2, w // 2, blk.cin, dtype=torch.float32, device=self.dev)
         for l in range(4):
             c = self.spec.nfb << l
             s['act']['pool%d' % l] = torch.empty(NB, H >> (l + 1), W >> (l + 1), c, **T)
             if training:
-                s['dx']['skip%d' % l] = torch.empty(NB, H >> l, W >> l, c, **T)
+                s['dx']['skip%d' % l] = torch.empty(NB, H >> l, W >> l, c, dtype=torch.float32, device=self.dev)
         s['logit'] = torch.empty(NB, H, W, dtype=torch.float32, device=self.dev)
         s['prob'] = torch.empty(NB, H, W, dtype=torch.float32, device=self.dev)
         if training:
             s['y'] = torch.zeros(NB, H, W, dtype=torch.uint8, device=self.dev)
-            s['dhead'] = torch.empty(NB, H, W, self.spec.nfb, **T)
+            s['dhead'] = torch.empty(NB, H, W, self.spec.nfb, dtype=torch.float32, device=self.dev)
             need = 0
             for blk in self.spec.blocks:
                 h, w = H >> blk.level, W >> blk.level
@@ -314,8 +316,15 @@ class UNetEngine(object):
     def _dropout_p(self, name, enabled):
         return float(self.spec.dropout_after().get(name, 0.)) if enabled else 0.
 
+    def _allreduce(self, t):
+        if self.comm is not None and self.comm.world > 1:
+            self.comm.allreduce_sum(t)
+
     def _train_step_enqueue(self, s, loss_id, lr, dropout, beta1, beta2, eps):
         spec, act, raw, dxb = self.spec, s['act'], s['raw'], s['dx']
+        world = self.comm.world if self.comm is not None else 1
+        # ranks draw different dropout masks for their own crops
+        seed_base = (self.comm.rank if self.comm is not None else 0) * 0x9E3779B1
         seed_dev = self.step_state[1:2]
         ops.step_advance(self.step_state, lr, beta1, beta2, self.lr_t)
         self.dbl.zero_()
@@ -341,9 +350,10 @@ class UNetEngine(object):
             M = raw[n].numel() // blk.cout
             sums = self.dbl[st['off_f']:st['off_f'] + 2 * blk.cout]
             ops.bn_stats(raw[n], sums)
-            ops.bn_finalize(sums, M, self.P[n + '/gamma'], self.P[n + '/beta'], mom, self.P[n + '/moving_mean'],
+            self._allreduce(sums)                       # SyncBN: statistics of the global batch
+            ops.bn_finalize(sums, M * world, self.P[n + '/gamma'], self.P[n + '/beta'], mom, self.P[n + '/moving_mean'],
                             self.P[n + '/moving_var'], st['scale'], st['shift'], st['mean'], st['rstd'], BN_EPS)
-            ops.bn_apply(raw[n], st['scale'], st['shift'], act[n], True, self._dropout_p(n, dropout), 0, seed_dev,
+            ops.bn_apply(raw[n], st['scale'], st['shift'], act[n], True, self._dropout_p(n, dropout), seed_base, seed_dev,
                          layer_id[n])
             if n in ('enc0b', 'enc1b', 'enc2b', 'enc3b'):
                 ops.maxpool2x2(act[n], act['pool%d' % blk.level])
@@ -351,12 +361,13 @@ class UNetEngine(object):
         hs = self.dbl[self._off_head_sums:self._off_head_sums + 8]
         hd = self.dbl[self._off_head_dwb:self._off_head_dwb + 2 * spec.nfb + 2]
         ops.head_loss_fwd(act['dec0b'], self.P['head/kernel'], self.P['head/bias'], s['y'], s['prob'], hs)
+        self._allreduce(hs)                             # loss / metric sums of the global batch
         # head kernel [1,1,C,2] and bias [2] are adjacent in the flat gradient buffer
         off_k = self._slots['head/kernel'][1]
         dw_out = self.grads[off_k:off_k + 2 * spec.nfb + 2]
         assert self._slots['head/bias'][1] == off_k + 2 * spec.nfb
         ops.head_loss_bwd(act['dec0b'], self.P['head/kernel'], s['y'], s['prob'], hs, loss_id, s['dhead'], hd, dw_out,
-                          self.metrics)
+                          self.metrics, M_total=s['prob'].numel() * world)
         # ---------------- backward
         grad_of = {'dec0b': (s['dhead'], spec.nfb, 0)}
         skip_grad = {}
@@ -369,11 +380,13 @@ class UNetEngine(object):
             st = self.bn[n]
             sums = self.dbl[st['off_b']:st['off_b'] + 2 * blk.cout]
             p = self._dropout_p(n, dropout)
-            ops.bn_bwd_reduce(dy, ldy, offy, raw[n], st['scale'], st['shift'], st['mean'], st['rstd'], sums, p, 0,
+            ops.bn_bwd_reduce(dy, ldy, offy, raw[n], st['scale'], st['shift'], st['mean'], st['rstd'], sums, p, seed_base,
                               seed_dev, layer_id[n])
+            self._allreduce(sums)
             draw = raw[n]      # in place: raw is dead after this point
             ops.bn_bwd_apply(dy, ldy, offy, raw[n], st['scale'], st['shift'], st['mean'], st['rstd'], sums, draw,
-                             self.G[n + '/gamma'], self.G[n + '/beta'], p, 0, seed_dev, layer_id[n])
+                             self.G[n + '/gamma'], self.G[n + '/beta'], p, seed_base, seed_dev, layer_id[n],
+                             M_total=(raw[n].numel() // blk.cout) * world, dgb_scale=1.0 / world)
             if blk.kind == 'conv':
                 if blk.cin == 1 and self.dtype == torch.bfloat16:
                     ops.conv3x3_c1_wgrad(s['x'], draw, self.G[n + '/kernel'], self._wgrad_ws)
@@ -382,7 +395,7 @@ class UNetEngine(object):
                 if n == 'enc0a':
                     continue
                 dX = dxb[n]
-                ops.conv3x3_fwd(draw, None, self.w_dgrad[n], dX, None, None, False)
+                ops.conv3x3_dgrad(draw, self.w_dgrad[n], dX)
                 if b is not None:                       # concat [up, skip]
                     c0 = act[a].shape[3]
                     grad_of[a] = (dX, blk.cin, 0)
@@ -402,6 +415,7 @@ class UNetEngine(object):
                 ops.convT2x2_dgrad(draw, self.w_dgrad[n], dX)
                 grad_of[a] = (dX, blk.cin, 0)
         # ---------------- Keras-form Adam over the flat parameter buffer
+        self._allreduce(self.grads)                     # 31 MB fp32: gradient of the global-batch loss
         ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, 0., self.lr_t, beta1, beta2, eps)
 
     def train_step(self, x_dev, y_dev, loss='dice_loss', lr=0.002, dropout=True, beta1=0.9, beta2=0.999, eps=1e-8):

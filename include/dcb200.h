@@ -83,9 +83,15 @@ int dcb_conv3x3_fwd(int dtype, const void* src0, int C0, const void* src1, int C
 /* input h x w -> output 2h x 2w */
 int dcb_convT2x2_fwd(int dtype, const void* src, int Cin, int N, int h, int w, const void* wgt, int Cout,
                      const float* scale, const float* shift, int relu, void* out, dcb_stream_t stream);
+/* input gradients.  dy is the gradient w.r.t. the raw conv output in the activation dtype (it feeds the
+ * tensor cores); dx is ALWAYS fp32: gradient tensors stay fp32 between layers because the BatchNorm
+ * backward subtracts their per-channel mean (a bf16-rounded dx would lose most of its significant bits
+ * there).  wgt is the *_dgrad operand of dcb_prep_*. */
+int dcb_conv3x3_dgrad(int dtype, const void* dy, int Cout, int N, int H, int W, const void* wgt_dgrad, int Cin,
+                      float* dx, dcb_stream_t stream);
 /* dy is [N][2h][2w][Cout]; dx is [N][h][w][Cin] */
 int dcb_convT2x2_dgrad(int dtype, const void* dy, int Cout, int N, int h, int w, const void* wgt, int Cin,
-                       void* dx, dcb_stream_t stream);
+                       float* dx, dcb_stream_t stream);
 /* dW[9][Cin][Cout] (fp32, Keras HWIO) = sum over pixels of x (shifted) * dy ; x may be [src0|src1] */
 int dcb_conv3x3_wgrad_workspace_bytes(int dtype, int N, int H, int W, int Cin, int Cout, size_t* bytes);
 int dcb_conv3x3_wgrad(int dtype, const void* src0, int C0, const void* src1, int C1, int N, int H, int W,
@@ -126,22 +132,25 @@ int dcb_bn_finalize(const double* sums, long long M, int C, const float* gamma, 
 int dcb_bn_apply(int dtype, const void* x, long long M, int C, const float* scale, const float* shift, int relu,
                  float p_drop, unsigned long long seed, const unsigned long long* seed_dev, unsigned layer, void* y,
                  dcb_stream_t stream);
-/* backward of dropout+ReLU+BN given dy (row stride ldy, channel offset offy) and the raw conv output x:
- * reduce accumulates sums[0..C)=sum dz, sums[C..2C)=sum dz*xhat; apply writes d_raw and dgamma/dbeta */
-int dcb_bn_bwd_reduce(int dtype, const void* dy, int ldy, int offy, const void* x, long long M, int C,
+/* backward of dropout+ReLU+BN given dy (fp32, row stride ldy, channel offset offy) and the raw conv output x:
+ * reduce accumulates sums[0..C)=sum dz, sums[C..2C)=sum dz*xhat; apply writes d_raw and dgamma/dbeta.
+ * Data-parallel use: all-reduce `sums` between the two calls, pass M_total = rows over all ranks
+ * (0 = M) and dgb_scale = 1/world so that the later gradient all-reduce(sum) restores dgamma/dbeta */
+int dcb_bn_bwd_reduce(int dtype, const float* dy, int ldy, int offy, const void* x, long long M, int C,
                       const float* scale, const float* shift, const float* mean, const float* rstd,
                       float p_drop, unsigned long long seed, const unsigned long long* seed_dev, unsigned layer,
                       double* sums, dcb_stream_t stream);
-int dcb_bn_bwd_apply(int dtype, const void* dy, int ldy, int offy, const void* x, long long M, int C,
+int dcb_bn_bwd_apply(int dtype, const float* dy, int ldy, int offy, const void* x, long long M, int C,
                      const float* scale, const float* shift, const float* mean, const float* rstd,
                      float p_drop, unsigned long long seed, const unsigned long long* seed_dev, unsigned layer,
-                     const double* sums, void* draw, float* dgamma, float* dbeta, dcb_stream_t stream);
+                     const double* sums, long long M_total, float dgb_scale, void* draw, float* dgamma,
+                     float* dbeta, dcb_stream_t stream);
 
 /* ---- a5: MaxPooling2D(2,2) fwd and bwd (gradient to the first maximum of the window), the bwd
  * fused with the add of the skip-connection gradient (a channel slice of a concat gradient) ---- */
 int dcb_maxpool2x2(int dtype, const void* x, int N, int H, int W, int C, void* y, dcb_stream_t stream);
-int dcb_pool_bwd_add(int dtype, const void* skipgrad, int lds, int offs, const void* y, const void* pooled,
-                     const void* dpool, int N, int H, int W, int C, void* out, dcb_stream_t stream);
+int dcb_pool_bwd_add(int dtype, const float* skipgrad, int lds, int offs, const void* y, const void* pooled,
+                     const float* dpool, int N, int H, int W, int C, float* out, dcb_stream_t stream);
 
 /* ---- a6/a7: Conv2D(2,1,softmax)[..., -1] head (unet_2d_summary.py:221-222), losses and the
  * seven batch metrics (utils/neurons.py:13-106).  w is [C][2], b is [2] (Keras layout). ---- */
@@ -153,8 +162,8 @@ int dcb_head_loss_fwd(int dtype, const void* x, long long M, int C, const float*
 /* dx[M][C] = dL/dx; dw_out[2C+2] = dL/d(kernel [C][2], bias [2]); metrics_out[8] =
  * loss, F1, prec, reca, dice, dicesq, posyt, posyp; dwb_accum[2C+2] double scratch (caller zeroes) */
 int dcb_head_loss_bwd(int dtype, const void* x, long long M, int C, const float* w, const uint8_t* yt,
-                      const float* prob, const double* sums, int loss, void* dx, double* dwb_accum,
-                      float* dw_out, float* metrics_out, dcb_stream_t stream);
+                      const float* prob, const double* sums, int loss, long long M_total, float* dx,
+                      double* dwb_accum, float* dw_out, float* metrics_out, dcb_stream_t stream);
 
 /* ---- a10: 8x test-time augmentation (utils/neurons.py:112-137, unet_2d_summary.py:569-595) ----
  * make_batch: reflect-pad s[hs][ws] to S x S and write transforms first..first+count-1 as [count][S][S];

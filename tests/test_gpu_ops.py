@@ -75,8 +75,8 @@ def test_conv3x3_fwd_dgrad_wgrad(cuda, precision, case):
     # plain conv (no epilogue), dgrad and wgrad against autograd
     dy = q(rng.standard_normal((N, H, W, Cout)), precision)
     conv.backward(nhwc_to_nchw(dy))
-    dx = torch.empty(N, H, W, Cin, dtype=dt, device='cuda')
-    ops.conv3x3_fwd(dev(dy, dt), None, wd, dx, None, None, False)
+    dx = torch.empty(N, H, W, Cin, dtype=torch.float32, device='cuda')       # gradients are fp32 in both modes
+    ops.conv3x3_dgrad(dev(dy, dt), wd, dx)
     gx = dx.float().cpu().permute(0, 3, 1, 2).double()
     assert torch.max(torch.abs(gx - xt.grad)).item() < tol(precision, 1 + xt.grad.abs().max().item())
     dW = torch.empty(3, 3, Cin, Cout, dtype=torch.float32, device='cuda')
@@ -108,7 +108,7 @@ def test_convT2x2_fwd_dgrad_wgrad(cuda, precision, case):
     assert torch.max(torch.abs(got - ref)).item() < tol(precision, 1 + ref.abs().max().item())
     dy = q(rng.standard_normal((N, 2 * h, 2 * w_, Cout)), precision)
     ref.backward(nhwc_to_nchw(dy))
-    dx = torch.empty(N, h, w_, Cin, dtype=dt, device='cuda')
+    dx = torch.empty(N, h, w_, Cin, dtype=torch.float32, device='cuda')
     ops.convT2x2_dgrad(dev(dy, dt), wd, dx)
     assert torch.max(torch.abs(dx.float().cpu().permute(0, 3, 1, 2).double() - xt.grad)).item() < \
         tol(precision, 1 + xt.grad.abs().max().item())
@@ -178,7 +178,7 @@ def test_batchnorm_train_forward_backward(cuda, precision, C):
     y.backward(torch.tensor(dy))
     draw = torch.empty_like(xd)
     dg, db = f(), f()
-    dyd = dev(dy_wide, dt)
+    dyd = dev(dy_wide)                                   # gradient tensors are fp32
     ops.bn_bwd_reduce(dyd, 2 * C, off, xd, scale, shift, mean_d, rstd_d, sums[2 * C:])
     ops.bn_bwd_apply(dyd, 2 * C, off, xd, scale, shift, mean_d, rstd_d, sums[2 * C:], draw, dg, db)
     t = tol(precision, 4)
@@ -205,7 +205,7 @@ def test_dropout_is_consistent_between_forward_and_backward(cuda, precision):
     assert (y2 != y).float().mean().item() > 0.3
     # backward sees the same mask: sum dz over rows == 2 * kept count per channel (dy = 1, xhat = 0)
     sums = torch.zeros(2 * C, dtype=torch.float64, device='cuda')
-    ops.bn_bwd_reduce(x, C, 0, x, one, zero, one, one, sums, 0.5, 7, seed_dev, 3)
+    ops.bn_bwd_reduce(x.float(), C, 0, x, one, zero, one, one, sums, 0.5, 7, seed_dev, 3)
     assert torch.allclose(sums[:C], 2.0 * keep.view(M, C).double().sum(0))
 
 
@@ -225,8 +225,8 @@ def test_maxpool_forward_and_backward_routing(cuda, precision):
     dp = q(rng.standard_normal((N, H // 2, W // 2, C)), precision)
     skip_wide = q(rng.standard_normal((N, H, W, 2 * C)), precision)
     ref.backward(nhwc_to_nchw(dp))
-    out = torch.empty(N, H, W, C, dtype=dt, device='cuda')
-    ops.pool_bwd_add(dev(skip_wide, dt), 2 * C, C, xd, yd, dev(dp, dt), out)
+    out = torch.empty(N, H, W, C, dtype=torch.float32, device='cuda')
+    ops.pool_bwd_add(dev(skip_wide), 2 * C, C, xd, yd, dev(dp), out)
     exp = xt.grad + nhwc_to_nchw(skip_wide[..., C:])
     # every pooled gradient lands on exactly one input pixel (torch also picks the first maximum)
     assert torch.max(torch.abs(out.float().cpu().permute(0, 3, 1, 2).double() - exp)).item() < tol(precision, 4)
@@ -254,7 +254,7 @@ def test_head_loss_metrics_and_gradient(cuda, precision, loss):
     assert np.allclose(prob.cpu().numpy(), p.detach().numpy(), atol=1e-5)
     sums = torch.zeros(8, dtype=torch.float64, device='cuda'); dwb = torch.zeros(2 * C + 2, dtype=torch.float64, device='cuda')
     ops.head_loss_fwd(xd, dev(w), dev(b), dev(yt, torch.uint8), prob, sums)
-    dx = torch.empty_like(xd); dw = torch.empty(2 * C + 2, device='cuda'); met = torch.empty(8, device='cuda')
+    dx = torch.empty(1, 1, M, C, device='cuda'); dw = torch.empty(2 * C + 2, device='cuda'); met = torch.empty(8, device='cuda')
     ops.head_loss_bwd(xd, dev(w), dev(yt, torch.uint8), prob, sums, nat.LOSS_IDS[loss], dx, dwb, dw, met)
     met = met.cpu().numpy()
     assert abs(met[0] - L.item()) < 2e-5 * max(1, abs(L.item()))
