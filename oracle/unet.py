@@ -115,6 +115,19 @@ def keras_list_to_weights(lst, spec=UNetSpec()):
     return OrderedDict(zip(keys, lst))
 
 
+class _RoundBF16(torch.autograd.Function):
+    """Round-to-nearest-even to bfloat16 with a straight-through gradient: models the bf16 storage of
+    weights / raw conv outputs / activations in the tensor-core mode (accumulation stays exact)."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.to(torch.bfloat16).to(t.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 def _conv3x3(x, k, b):
     return F.conv2d(x, k.permute(3, 2, 0, 1), b, padding=1)
 
@@ -136,14 +149,21 @@ def _bn(x, g, be, mm, mv, training, stats_out, name):
 
 
 def unet_forward(w, x, spec=UNetSpec(), training=False, dropout_keep=None, dtype=torch.float64,
-                 return_intermediates=False, requires_grad=False):
+                 return_intermediates=False, requires_grad=False, emulate_bf16=False):
     """Forward pass.  ``x``: [N,H,W] array.  Returns dict with
       'logit' = z1 - z0 (so prob = sigmoid(logit) = softmax(z)[..., -1]),
       'prob', and (training) 'bn_stats' {layer: (batch_mean, batch_var)}.
     ``dropout_keep``: {tensor name: 0/1 keep mask [N,C,H,W]} or None (= dropout
     off, the parity configuration).  With ``requires_grad`` the returned
     'params' dict holds leaf tensors for autograd.
+    ``emulate_bf16``: round to bfloat16 exactly where the GPU's tensor-core mode stores bf16 - the
+    kernels of every layer with Cin > 1, each raw conv output (after the bias) and each activation
+    (after BN/ReLU/dropout) - keeping all arithmetic in ``dtype``.  This is the reference the bf16
+    training path is compared with: the fp64 gradient of this randomly initialised dice-loss network is
+    ill-conditioned w.r.t. 2^-9 perturbations of the activations (tens of percent), so only a
+    reference with the same storage rounding isolates implementation errors.
     """
+    rb = _RoundBF16.apply if emulate_bf16 else (lambda t: t)
     tw = OrderedDict((k, torch.tensor(np.asarray(v), dtype=dtype, requires_grad=(
         requires_grad and k.rsplit('/', 1)[1] in TRAINABLE))) for k, v in w.items())
     t = torch.as_tensor(np.ascontiguousarray(x), dtype=dtype)[:, None]   # NCHW, Cin=1 (:169-170)
@@ -152,15 +172,22 @@ def unet_forward(w, x, spec=UNetSpec(), training=False, dropout_keep=None, dtype
 
     def block(name, t):
         kind = 'up' if name.startswith('up') else 'conv'
+        k = tw[name + '/kernel']
+        if k.shape[2] > 1:          # the Cin = 1 first layer reads fp32 weights on the GPU as well
+            k = rb(k)
         if kind == 'conv':
-            t = _conv3x3(t, tw[name + '/kernel'], tw[name + '/bias'])
+            t = _conv3x3(t, k, tw[name + '/bias'])
         else:
-            t = _convT2x2(t, tw[name + '/kernel'], tw[name + '/bias'])
+            t = _convT2x2(t, k, tw[name + '/bias'])
+        if training:                # the raw output is only materialised (in bf16) for batch-stat BN
+            t = rb(t)
         if return_intermediates:
             inter[name + '/raw'] = t
         t = _bn(t, tw[name + '/gamma'], tw[name + '/beta'], tw[name + '/moving_mean'],
                 tw[name + '/moving_var'], training, stats, name)
         t = torch.relu(t)
+        if name not in drops or not (training and dropout_keep is not None):
+            t = rb(t)
         if return_intermediates:
             inter[name] = t
         return t
@@ -169,7 +196,7 @@ def unet_forward(w, x, spec=UNetSpec(), training=False, dropout_keep=None, dtype
         if training and dropout_keep is not None and name in dropout_keep:
             keep = 1. - drops[name]
             t = t * torch.as_tensor(dropout_keep[name], dtype=dtype) / keep
-        return t
+        return rb(t)                # activations are stored after ReLU (+ dropout)
 
     def up(lvl, t):
         if spec.upsampling_or_transpose == 'transpose':
@@ -233,11 +260,12 @@ def keras_adam_update(p, g, m, v, iteration, lr=0.002, beta_1=0.9, beta_2=0.999,
 
 
 def train_step(w, x, y, opt_state=None, spec=UNetSpec(), loss='dice_loss', lr=0.002,
-               dropout_keep=None, dtype=torch.float64):
+               dropout_keep=None, dtype=torch.float64, emulate_bf16=False):
     """One ``train_on_batch``: forward with batch-stat BN, loss, autograd,
     Keras-Adam on the trainable tensors, momentum update of the BN moving stats.
     Returns (loss, new_weights, new_opt_state, grads, forward_out)."""
-    out = unet_forward(w, x, spec, training=True, dropout_keep=dropout_keep, dtype=dtype, requires_grad=True)
+    out = unet_forward(w, x, spec, training=True, dropout_keep=dropout_keep, dtype=dtype, requires_grad=True,
+                       emulate_bf16=emulate_bf16)
     yt = torch.as_tensor(np.asarray(y), dtype=dtype)
     L = LOSSES[loss](yt, out['prob'])
     params = {k: t for k, t in out['params'].items() if t.requires_grad}
