@@ -12,6 +12,7 @@
 // CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-5 epilogue.
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM double buffer full/empty (MMA <-> epilogue),
 // static round-robin tile schedule (tile = blockIdx.x + i * gridDim.x).
+#include <cstdlib>
 #include <mutex>
 #include <map>
 #include <vector>
@@ -230,6 +231,206 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
   }
 }
 
+// ====================================================================================== strip kernel
+// conv3x3 for the wide, shallow layers (W % 128 == 0, 9*Cin*Cout*2 bytes of weights fit in smem):
+// the layers where the generic kernel is bound by re-loading the activations 9x (once per tap).
+//   * all 9 x nkc weight tiles stay resident in shared memory for the whole (persistent) CTA;
+//   * a work item is a strip of R output rows x 128 pixels; the producer streams its R+2 halo rows
+//     ([130 px x BK ch] TMA boxes, zero filled outside the image) through a ring, so every activation
+//     row is fetched once per strip (1 + 2/R instead of 9 times);
+//   * the three horizontal taps read the SAME halo row: the A descriptor simply starts dx pixels
+//     (dx * row pitch bytes) further into the swizzled tile.  The swizzle XOR is a function of the
+//     absolute smem address, so a row-shifted start address needs no base-offset correction
+//     (verified on B200: profiles/r1_umma_row_shift_probe.log);
+//   * the three vertical taps read three consecutive ring rows.
+constexpr int ST_MAX_RING = 12;
+
+struct TcStripParams {
+  int N, H, W;
+  int C0, C1, BK, nkc;
+  int Cout;
+  int R, ring, wsegs, hchunks;
+  int slot_bytes;           // 130 * BK * 2 rounded up to 1024
+  int relu, out_f32;
+  __nv_bfloat16* out;
+  const float* scale;
+  const float* shift;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                        const __grid_constant__ CUtensorMap mapB, const TcStripParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t bar_w, row_full[ST_MAX_RING], row_empty[ST_MAX_RING], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_scale[128], s_shift[128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int K = p.C0 + p.C1;
+  const uint32_t wblk_bytes = p.Cout * p.BK * 2;                 // one (tap, kc) weight tile
+  const uint32_t w_bytes = 9u * p.nkc * wblk_bytes;
+  uint8_t* s_w = smem;
+  uint8_t* s_ring = smem + ((w_bytes + 1023) & ~1023u);
+  const uint32_t row_bytes = (uint32_t)p.nkc * p.slot_bytes;     // one halo row = nkc chunk boxes
+  const uint32_t box_bytes = 130u * p.BK * 2u;
+  const int num_items = p.N * p.hchunks * p.wsegs;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * p.Cout) tmem_cols <<= 1;
+
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
+    s_scale[i] = p.scale ? p.scale[i] : 1.f;
+    s_shift[i] = p.shift ? p.shift[i] : 0.f;
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA0);
+    if (p.C1 > 0) tma_prefetch_desc(&mapA1);
+    tma_prefetch_desc(&mapB);
+    mbar_init(&bar_w, 1);
+    for (int s = 0; s < p.ring; ++s) { mbar_init(&row_full[s], 1); mbar_init(&row_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 4); }
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(&tmem_base_smem, tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  auto decode = [&](int item, int& n, int& h0, int& rows, int& w0) {
+    const int ws = item % p.wsegs; item /= p.wsegs;
+    const int hc = item % p.hchunks; n = item / p.hchunks;
+    h0 = hc * p.R; rows = p.H - h0 < p.R ? p.H - h0 : p.R; w0 = ws * 128;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // resident weights: B tile (tap, kc) = rows [0, Cout) x cols [tap*K + kc*BK, +BK) of the weight matrix
+      mbar_arrive_expect_tx(&bar_w, w_bytes);
+      for (int tap = 0; tap < 9; ++tap)
+        for (int kc = 0; kc < p.nkc; ++kc)
+          tma_load_2d(&mapB, &bar_w, s_w + (size_t)(tap * p.nkc + kc) * wblk_bytes, tap * K + kc * p.BK, 0);
+      uint32_t cnt = 0;                                          // halo rows issued so far
+      const int kc0 = p.C0 / p.BK;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int n, h0, rows, w0;
+        decode(item, n, h0, rows, w0);
+        for (int rr = -1; rr <= rows; ++rr, ++cnt) {
+          const int pos = cnt % p.ring;
+          mbar_wait(&row_empty[pos], ((cnt / p.ring) & 1) ^ 1);
+          mbar_arrive_expect_tx(&row_full[pos], p.nkc * box_bytes);
+          uint8_t* dst = s_ring + (size_t)pos * row_bytes;
+          for (int kc = 0; kc < p.nkc; ++kc) {
+            const bool second = kc >= kc0;
+            tma_load_4d(second ? &mapA1 : &mapA0, &row_full[pos], dst + (size_t)kc * p.slot_bytes,
+                        (second ? kc - kc0 : kc) * p.BK, w0 - 1, h0 + rr, n);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(TC_BM, p.Cout, 0, 0);
+      const uint32_t swz = (p.BK == 64) ? SWZ_128B : SWZ_64B;
+      const uint32_t pitch = p.BK * 2u, sbo = 8u * pitch;
+      const int ksteps = p.BK / 16;
+      const uint32_t ring_base = smem_u32(s_ring), w_base = smem_u32(s_w);
+      mbar_wait(&bar_w, 0);
+      tc_fence_after();
+      uint32_t cnt = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int n, h0, rows, w0;
+        decode(item, n, h0, rows, w0);
+        const uint32_t c0 = cnt;
+        mbar_wait(&row_full[c0 % p.ring], (c0 / p.ring) & 1);
+        mbar_wait(&row_full[(c0 + 1) % p.ring], ((c0 + 1) / p.ring) & 1);
+        for (int t = 0; t < rows; ++t) {
+          mbar_wait(&row_full[(c0 + t + 2) % p.ring], ((c0 + t + 2) / p.ring) & 1);
+          mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Cout);
+          uint32_t first = 1;
+          for (int dy = 0; dy < 3; ++dy) {
+            const uint32_t row_addr = ring_base + ((c0 + t + dy) % p.ring) * row_bytes;
+            for (int kc = 0; kc < p.nkc; ++kc) {
+              for (int dx = 0; dx < 3; ++dx) {
+                const uint32_t a_addr = row_addr + kc * p.slot_bytes + dx * pitch;   // halo box starts at pixel w0-1
+                const uint32_t b_addr = w_base + ((dy * 3 + dx) * p.nkc + kc) * wblk_bytes;
+                for (int k = 0; k < ksteps; ++k) {
+                  umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32, 16, sbo, swz),
+                            make_smem_desc(b_addr + k * 32, 16, sbo, swz), idesc, first ? 0u : 1u);
+                  first = 0;
+                }
+              }
+            }
+          }
+          umma_commit(&bar_tfull[acc]);
+          umma_commit(&row_empty[(c0 + t) % p.ring]);            // halo row t is not needed by later tiles
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        umma_commit(&row_empty[(c0 + rows) % p.ring]);
+        umma_commit(&row_empty[(c0 + rows + 1) % p.ring]);
+        cnt = c0 + rows + 2;
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int n, h0, rows, w0;
+      decode(item, n, h0, rows, w0);
+      for (int t = 0; t < rows; ++t) {
+        const size_t oidx = (((size_t)n * p.H + (h0 + t)) * p.W + (w0 + m)) * p.Cout;
+        __nv_bfloat16* orow = p.out + oidx;
+        float* orow_f = reinterpret_cast<float*>(p.out) + oidx;
+        mbar_wait(&bar_tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.Cout);
+        for (int c = 0; c < p.Cout; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_addr + c, r);
+          tmem_ld_wait();
+          if (p.out_f32) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float v[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                v[q] = fmaf(__uint_as_float(r[j + q]), s_scale[c + j + q], s_shift[c + j + q]);
+                if (p.relu) v[q] = fmaxf(v[q], 0.f);
+              }
+              *reinterpret_cast<float4*>(orow_f + c + j) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int ch = c + j + 2 * q;
+                float v0 = fmaf(__uint_as_float(r[j + 2 * q]), s_scale[ch], s_shift[ch]);
+                float v1 = fmaf(__uint_as_float(r[j + 2 * q + 1]), s_scale[ch + 1], s_shift[ch + 1]);
+                if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+                pk[q] = *reinterpret_cast<uint32_t*>(&b2);
+              }
+              *reinterpret_cast<uint4*>(orow + c + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
 // ---------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -295,12 +496,72 @@ static int pick_pow2_box(int extent, int maxbox) {
   return best;
 }
 
+// strip kernel plan; returns false when the layer is not eligible
+static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, TcStripParams& p, size_t& dyn_smem) {
+  static const bool disabled = getenv("DCB_NO_STRIP") != nullptr;
+  if (disabled) return false;
+  if (g.ntaps != 9 || g.zsub > 1 || g.sy != 1) return false;
+  if (g.GW % 128 != 0 || Nout > 128 || Nout % 32 != 0) return false;
+  const int K = C0 + C1;
+  const int BK = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
+  const int nkc = K / BK;
+  const size_t w_bytes = ((size_t)9 * K * Nout * 2 + 1023) & ~(size_t)1023;
+  const int slot = (130 * BK * 2 + 1023) & ~1023;
+  const size_t budget = 200 * 1024;
+  if (w_bytes + (size_t)5 * nkc * slot > budget) return false;
+  int ring = (int)((budget - w_bytes) / ((size_t)nkc * slot));
+  if (ring > ST_MAX_RING) ring = ST_MAX_RING;
+  memset(&p, 0, sizeof(p));
+  p.N = g.N; p.H = g.GH; p.W = g.GW; p.C0 = C0; p.C1 = C1; p.BK = BK; p.nkc = nkc; p.Cout = Nout;
+  p.ring = ring; p.slot_bytes = slot; p.wsegs = g.GW / 128;
+  int R = 32;
+  while (R > 8 && (long long)g.N * cdiv(g.GH, R) * p.wsegs < 4LL * sm_count()) R >>= 1;
+  p.R = R; p.hchunks = cdiv(g.GH, R);
+  dyn_smem = w_bytes + (size_t)ring * nkc * slot + 1024;
+  return true;
+}
+
 int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* B, int Nout, void* out,
                const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st) {
   if (C0 % 32 != 0 || C1 % 32 != 0 || Nout % 32 != 0)
     return fail(DCB_ERR_UNSUPPORTED, "bf16 tensor-core path needs channel counts that are multiples of 32 "
                 "(got C0=%d C1=%d Cout=%d); use the fp32 check mode for other widths", C0, C1, Nout);
   if (Nout > 512) return fail(DCB_ERR_UNSUPPORTED, "bf16 tensor-core path supports at most 512 output channels (got %d)", Nout);
+  {
+    TcStripParams sp;
+    size_t dyn = 0;
+    if (plan_strip(g, C0, C1, Nout, sp, dyn)) {
+      sp.relu = relu; sp.out_f32 = out_f32; sp.out = reinterpret_cast<__nv_bfloat16*>(out); sp.scale = scale; sp.shift = shift;
+      CUtensorMap mA0, mA1, mB;
+      auto mk = [&](CUtensorMap* m, const void* ptr, int C) -> int {
+        uint64_t dims[4] = {(uint64_t)C, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.N};
+        uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)g.IW * C * 2, (uint64_t)g.IH * g.IW * C * 2};
+        uint32_t box[4] = {(uint32_t)sp.BK, 130u, 1u, 1u};
+        return make_map(m, ptr, 4, dims, str, box, sp.BK * 2);
+      };
+      if (int e = mk(&mA0, s0, C0)) return e;
+      if (C1 > 0) { if (int e = mk(&mA1, s1, C1)) return e; } else mA1 = mA0;
+      {
+        const int Ktot = 9 * (C0 + C1);
+        uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)Nout};
+        uint64_t str[1] = {(uint64_t)Ktot * 2};
+        uint32_t box[2] = {(uint32_t)sp.BK, (uint32_t)Nout};
+        if (int e = make_map(&mB, B, 2, dims, str, box, sp.BK * 2)) return e;
+      }
+      static bool attr_set_strip = false;
+      if (!attr_set_strip) {
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
+        if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
+        attr_set_strip = true;
+      }
+      const int items = sp.N * sp.hchunks * sp.wsegs;
+      const int grid = items < sm_count() ? items : sm_count();
+      tapgemm_tc_strip_kernel<<<grid, TC_THREADS, dyn, st>>>(mA0, mA1, mB, sp);
+      g_launches += 1;
+      DCB_LAUNCH_OK("tapgemm_tc_strip_kernel");
+      return DCB_OK;
+    }
+  }
   TcFwdParams p;
   memset(&p, 0, sizeof(p));
   const int ntaps = g.ntaps;

@@ -41,6 +41,12 @@ CONV_CASES = [
     (3, 4, 4, 256, 0, 512),
     (1, 32, 32, 64, 64, 64),
     (1, 2, 2, 512, 0, 512),
+    # wide rows (W % 128 == 0): the halo-strip kernel in bf16 mode
+    (1, 8, 128, 32, 0, 32),
+    (2, 5, 256, 64, 0, 64),
+    (1, 20, 128, 32, 32, 32),
+    (1, 1, 128, 32, 0, 64),
+    (3, 37, 128, 64, 0, 32),
 ]
 
 
