@@ -39,35 +39,47 @@ __global__ void bn_fold_kernel(const float* gamma, const float* beta, const floa
 }
 
 // ---------------------------------------------------------------- BN batch statistics
-// x [M][C]; each thread owns 4 consecutive channels; CTA walks a contiguous row range.
-template <typename T>
+// x [M][C]; each thread owns 8 consecutive channels (one 16-byte bf16 load); the CTA walks a contiguous
+// row range with 4 independent row loads in flight per thread.
+template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const T* __restrict__ x, long long M, int C, double* __restrict__ sums) {
-  const int lanes_c = C >> 2;                 // threads per row
+  const int lanes_c = C / VEC;                // threads per row
   const int rows_par = 256 / lanes_c;         // rows processed in parallel by the CTA
   const int tc = threadIdx.x % lanes_c, tr = threadIdx.x / lanes_c;
   const long long rows_per_cta = (M + gridDim.x - 1) / gridDim.x;
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   long long r1 = r0 + rows_per_cta; if (r1 > M) r1 = M;
-  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
-  if (tr < rows_par) {
-    for (long long r = r0 + tr; r < r1; r += rows_par) {
-      float4 v = load4<T>(x + r * C + tc * 4);
-      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-      q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]); q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
-    }
-  }
-  __shared__ float sh[256 * 8];
+  float s[VEC], q[VEC];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { sh[threadIdx.x * 8 + i] = s[i]; sh[threadIdx.x * 8 + 4 + i] = q[i]; }
+  for (int i = 0; i < VEC; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  const T* base = x + tc * VEC;
+  long long r = r0 + tr;
+  for (; r + 3LL * rows_par < r1; r += 4LL * rows_par) {
+    float v[4][VEC];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) loadv<T, VEC>(base + (r + (long long)u * rows_par) * C, v[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { s[i] += v[u][i]; q[i] = fmaf(v[u][i], v[u][i], q[i]); }
+  }
+  for (; r < r1; r += rows_par) {
+    float v[VEC];
+    loadv<T, VEC>(base + r * C, v);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { s[i] += v[i]; q[i] = fmaf(v[i], v[i], q[i]); }
+  }
+  __shared__ float sh[256 * 2 * VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { sh[threadIdx.x * 2 * VEC + i] = s[i]; sh[threadIdx.x * 2 * VEC + VEC + i] = q[i]; }
   __syncthreads();
-  // threads 0..lanes_c*8-1: (channel-lane, component) pairs; sum over the row-parallel copies
-  for (int idx = threadIdx.x; idx < lanes_c * 8; idx += 256) {
-    const int lc = idx >> 3, comp = idx & 7;
+  // (channel-lane, component) pairs; sum over the row-parallel copies, one fp64 atomic per channel and CTA
+  for (int idx = threadIdx.x; idx < lanes_c * 2 * VEC; idx += 256) {
+    const int lc = idx / (2 * VEC), comp = idx % (2 * VEC);
     double acc = 0;
-    for (int r = 0; r < rows_par; ++r) acc += (double)sh[(r * lanes_c + lc) * 8 + comp];
-    const int c = lc * 4 + (comp & 3);
-    atomicAdd(&sums[(comp >> 2) * C + c], acc);
+    for (int rr = 0; rr < rows_par; ++rr) acc += (double)sh[(rr * lanes_c + lc) * 2 * VEC + comp];
+    atomicAdd(&sums[(comp / VEC) * C + lc * VEC + (comp % VEC)], acc);
   }
 }
 
@@ -115,7 +127,8 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, long long M, int C, con
 
 // ---------------------------------------------------------------- BN + ReLU (+dropout) backward
 // dz = dY * keepscale * [x*scale+shift > 0];  sums[c] += dz ; sums[C+c] += dz * xhat, xhat = (x-mean)*rstd
-template <typename T>
+// 8 channels per thread, 2 independent rows in flight.
+template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ dy, int ldy, int offy, const T* __restrict__ x, long long M, int C,
                      const float* __restrict__ scale, const float* __restrict__ shift,
@@ -123,42 +136,61 @@ bn_bwd_reduce_kernel(const float* __restrict__ dy, int ldy, int offy, const T* _
                      unsigned long long seed, const unsigned long long* __restrict__ seed_dev, uint32_t layer,
                      double* __restrict__ sums) {
   if (seed_dev) seed ^= *seed_dev;
-  const int lanes_c = C >> 2;
+  const int lanes_c = C / VEC;
   const int rows_par = 256 / lanes_c;
   const int tc = threadIdx.x % lanes_c, tr = threadIdx.x / lanes_c;
   const long long rows_per_cta = (M + gridDim.x - 1) / gridDim.x;
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   long long r1 = r0 + rows_per_cta; if (r1 > M) r1 = M;
-  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
-  if (tr < rows_par) {
-    const int c = tc * 4;
-    const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
-    const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
-    for (long long r = r0 + tr; r < r1; r += rows_par) {
-      float4 g = load4<float>(dy + r * ldy + offy + c);
-      const float4 v = load4<T>(x + r * C + c);
-      if (p_drop > 0.f) {
-        const float4 k = dropout_scale4(seed, layer, (unsigned long long)((r * C + c) >> 2), p_drop);
-        g.x *= k.x; g.y *= k.y; g.z *= k.z; g.w *= k.w;
-      }
-      if (fmaf(v.x, sc.x, sh.x) <= 0.f) g.x = 0.f;
-      if (fmaf(v.y, sc.y, sh.y) <= 0.f) g.y = 0.f;
-      if (fmaf(v.z, sc.z, sh.z) <= 0.f) g.z = 0.f;
-      if (fmaf(v.w, sc.w, sh.w) <= 0.f) g.w = 0.f;
-      s[0] += g.x; s[1] += g.y; s[2] += g.z; s[3] += g.w;
-      q[0] = fmaf(g.x, (v.x - mu.x) * rs.x, q[0]); q[1] = fmaf(g.y, (v.y - mu.y) * rs.y, q[1]);
-      q[2] = fmaf(g.z, (v.z - mu.z) * rs.z, q[2]); q[3] = fmaf(g.w, (v.w - mu.w) * rs.w, q[3]);
-    }
-  }
-  __shared__ float shm[256 * 8];
+  const int c = tc * VEC;
+  float sc[VEC], sh[VEC], mu[VEC], rs[VEC], s[VEC], q[VEC];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { shm[threadIdx.x * 8 + i] = s[i]; shm[threadIdx.x * 8 + 4 + i] = q[i]; }
+  for (int i = 0; i < VEC; ++i) { sc[i] = scale[c + i]; sh[i] = shift[c + i]; mu[i] = mean[c + i]; rs[i] = rstd[c + i]; s[i] = 0.f; q[i] = 0.f; }
+  auto accumulate = [&](long long r, const float (&g8)[VEC], const float (&v)[VEC]) {
+    float g[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) g[i] = g8[i];
+    if (p_drop > 0.f) {
+      const unsigned long long i4 = (unsigned long long)((r * C + c) >> 2);
+      const float4 k0 = dropout_scale4(seed, layer, i4, p_drop);
+      g[0] *= k0.x; g[1] *= k0.y; g[2] *= k0.z; g[3] *= k0.w;
+      if constexpr (VEC == 8) {
+        const float4 k1 = dropout_scale4(seed, layer, i4 + 1, p_drop);
+        g[4] *= k1.x; g[5] *= k1.y; g[6] *= k1.z; g[7] *= k1.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      if (fmaf(v[i], sc[i], sh[i]) <= 0.f) g[i] = 0.f;
+      s[i] += g[i];
+      q[i] = fmaf(g[i], (v[i] - mu[i]) * rs[i], q[i]);
+    }
+  };
+  long long r = r0 + tr;
+  for (; r + rows_par < r1; r += 2LL * rows_par) {
+    float g0[VEC], g1[VEC], v0[VEC], v1[VEC];
+    loadv<float, VEC>(dy + r * ldy + offy + c, g0);
+    loadv<float, VEC>(dy + (r + rows_par) * ldy + offy + c, g1);
+    loadv<T, VEC>(x + r * C + c, v0);
+    loadv<T, VEC>(x + (r + rows_par) * C + c, v1);
+    accumulate(r, g0, v0);
+    accumulate(r + rows_par, g1, v1);
+  }
+  for (; r < r1; r += rows_par) {
+    float g0[VEC], v0[VEC];
+    loadv<float, VEC>(dy + r * ldy + offy + c, g0);
+    loadv<T, VEC>(x + r * C + c, v0);
+    accumulate(r, g0, v0);
+  }
+  __shared__ float shm[256 * 2 * VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { shm[threadIdx.x * 2 * VEC + i] = s[i]; shm[threadIdx.x * 2 * VEC + VEC + i] = q[i]; }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < lanes_c * 8; idx += 256) {
-    const int lc = idx >> 3, comp = idx & 7;
+  for (int idx = threadIdx.x; idx < lanes_c * 2 * VEC; idx += 256) {
+    const int lc = idx / (2 * VEC), comp = idx % (2 * VEC);
     double acc = 0;
-    for (int r = 0; r < rows_par; ++r) acc += (double)shm[(r * lanes_c + lc) * 8 + comp];
-    atomicAdd(&sums[(comp >> 2) * C + lc * 4 + (comp & 3)], acc);
+    for (int rr = 0; rr < rows_par; ++rr) acc += (double)shm[(rr * lanes_c + lc) * 2 * VEC + comp];
+    atomicAdd(&sums[(comp / VEC) * C + lc * VEC + (comp % VEC)], acc);
   }
 }
 
@@ -555,8 +587,9 @@ extern "C" int dcb_bn_fold(const float* gamma, const float* beta, const float* m
 }
 
 static int check_c(int C, const char* who) {
-  if (C < 4 || C % 4 != 0 || C > 1024 || 256 % (C / 4) != 0)
-    return fail(DCB_ERR_INVALID_ARGUMENT, "%s: channel count %d unsupported (need C/4 to divide 256)", who, C);
+  const int vec = (C % 8 == 0 && 256 % (C / 8) == 0) ? 8 : 4;
+  if (C < 4 || C % 4 != 0 || C > 2048 || 256 % (C / vec) != 0)
+    return fail(DCB_ERR_INVALID_ARGUMENT, "%s: channel count %d unsupported (need C/4 or C/8 to divide 256)", who, C);
   return DCB_OK;
 }
 
@@ -564,7 +597,11 @@ extern "C" int dcb_bn_stats(int dtype, const void* x, long long M, int C, double
   DCB_CHECK_ARG(x && sums && M > 0, "dcb_bn_stats: bad arguments");
   if (int e = check_c(C, "dcb_bn_stats")) return e;
   int grid = (int)((M + 255) / 256); if (grid > sm_count() * 8) grid = sm_count() * 8;
-  DISPATCH_T(dtype, bn_stats_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, M, C, sums);)
+  if (C % 8 == 0 && 256 % (C / 8) == 0) {
+    DISPATCH_T(dtype, bn_stats_kernel<T, 8><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, M, C, sums);)
+  } else {
+    DISPATCH_T(dtype, bn_stats_kernel<T, 4><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, M, C, sums);)
+  }
   g_launches += 1;
   DCB_LAUNCH_OK("bn_stats_kernel");
   return DCB_OK;
@@ -599,10 +636,16 @@ extern "C" int dcb_bn_bwd_reduce(int dtype, const float* dy, int ldy, int offy, 
                                  double* sums, dcb_stream_t stream) {
   DCB_CHECK_ARG(dy && x && scale && shift && mean && rstd && sums && M > 0, "dcb_bn_bwd_reduce: bad arguments");
   DCB_CHECK_ARG(ldy % 4 == 0 && offy % 4 == 0 && offy + C <= ldy, "dcb_bn_bwd_reduce: bad dy view (ld %d off %d C %d)", ldy, offy, C);
+  DCB_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0, "dcb_bn_bwd_reduce: pointers must be 16-byte aligned");
   if (int e = check_c(C, "dcb_bn_bwd_reduce")) return e;
   int grid = (int)((M + 255) / 256); if (grid > sm_count() * 8) grid = sm_count() * 8;
-  DISPATCH_T(dtype, bn_bwd_reduce_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const float*)dy, ldy, offy, (const T*)x, M, C, scale, shift, mean, rstd, p_drop, seed, seed_dev, layer, sums);)
+  if (C % 8 == 0 && 256 % (C / 8) == 0) {
+    DISPATCH_T(dtype, bn_bwd_reduce_kernel<T, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const float*)dy, ldy, offy, (const T*)x, M, C, scale, shift, mean, rstd, p_drop, seed, seed_dev, layer, sums);)
+  } else {
+    DISPATCH_T(dtype, bn_bwd_reduce_kernel<T, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const float*)dy, ldy, offy, (const T*)x, M, C, scale, shift, mean, rstd, p_drop, seed, seed_dev, layer, sums);)
+  }
   g_launches += 1;
   DCB_LAUNCH_OK("bn_bwd_reduce_kernel");
   return DCB_OK;

@@ -45,11 +45,64 @@ struct TcFwdParams {
   int osy, osx, ody, odx;   // output pixel = g * os + od (+ sub-position for convT fwd)
   int relu;
   int out_f32;              // 1: store fp32 (gradient tensors), 0: store bf16 (activations)
+  int swap;                 // 1: weights are the MMA A operand (M = 128 channel rows), pixels the B operand (N = 256)
   int stages;
   __nv_bfloat16* out;
   const float* scale;
   const float* shift;
 };
+
+// Epilogue of the "swapped" orientation (TMEM lane = output channel, TMEM column = pixel): each thread
+// owns one channel and receives 32 consecutive pixels per tcgen05.ld; the 32 x 32 block is transposed
+// through a per-warp shared-memory tile so that global stores stay NHWC-contiguous (64 B of bf16 or
+// 128 B of fp32 per pixel and warp).  pix_index(m) returns the element index of pixel m's first
+// channel of this warp, or -1 when the pixel lies outside the tensor.
+template <typename PixFn>
+__device__ __forceinline__ void epilogue_swapped(uint32_t t_addr, int npix, bool warp_valid, float sc, float sh, int relu,
+                                                 int out_f32, void* out_base, uint8_t* stage, int lane, PixFn pix_index) {
+  for (int j = 0; j < npix; j += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(t_addr + j, r);
+    tmem_ld_wait();
+    if (!warp_valid) continue;
+    __syncwarp();
+    if (out_f32) {
+      float* st = reinterpret_cast<float*>(stage);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float v = fmaf(__uint_as_float(r[i]), sc, sh);
+        if (relu) v = fmaxf(v, 0.f);
+        st[i * 32 + lane] = v;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int idx = lane + 32 * q, px = idx >> 3, chunk = idx & 7;
+        const long long o = pix_index(j + px);
+        if (o >= 0)
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_base) + o + chunk * 4) =
+              *reinterpret_cast<const float4*>(st + px * 32 + chunk * 4);
+      }
+    } else {
+      __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(stage);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float v = fmaf(__uint_as_float(r[i]), sc, sh);
+        if (relu) v = fmaxf(v, 0.f);
+        st[i * 32 + lane] = __float2bfloat16_rn(v);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int idx = lane + 32 * q, px = idx >> 2, chunk = idx & 3;
+        const long long o = pix_index(j + px);
+        if (o >= 0)
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_base) + o + chunk * 8) =
+              *reinterpret_cast<const uint4*>(st + px * 32 + chunk * 8);
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
@@ -62,17 +115,21 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // dynamic smem: 1024-byte aligned stage buffers (swizzle atoms are address based)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t a_bytes = TC_BM * p.BK * 2, b_bytes = p.BN * p.BK * 2;
+  // pixel tile: 128 rows (normal) or 256 rows (swapped); weight tile: BN rows (normal) or 128 rows (swapped)
+  const int PX = p.swap ? 256 : TC_BM;
+  const uint32_t a_bytes = PX * p.BK * 2, b_bytes = (p.swap ? 128 : p.BN) * p.BK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const int kb0 = p.C0 / p.BK, kb1 = p.C1 / p.BK;
   const int kb_per_tap = kb0 + kb1;
   const int num_kb = p.ntaps * kb_per_tap;
   const int Ktap = p.C0 + p.C1;
-  const int num_ntiles = p.Ntot / p.BN;
+  const int num_ntiles = p.swap ? (p.Ntot + 127) / 128 : p.Ntot / p.BN;
   const int num_mtiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int num_tiles = num_mtiles * num_ntiles;
+  const int acc_cols = p.swap ? 256 : p.BN;          // TMEM columns per accumulator stage
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2u * p.BN) tmem_cols <<= 1;
+  while (tmem_cols < 2u * acc_cols) tmem_cols <<= 1;
+  __shared__ __align__(16) uint8_t s_stage[4][4096];  // per-epilogue-warp transpose tiles (swapped mode)
 
   for (int i = threadIdx.x; i < p.Cz; i += blockDim.x) {
     s_scale[i] = p.scale ? p.scale[i] : 1.f;
@@ -111,11 +168,14 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
           mbar_wait(&bar_empty[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           uint8_t* sb = sa + a_bytes;
-          mbar_arrive_expect_tx(&bar_full[stage], stage_bytes);
+          // swapped: the weight box holds min(128, rows left) rows; the rest of the 128-row A tile is stale
+          // shared memory that only feeds accumulator lanes nobody reads
+          const int wrows = p.swap ? (p.Ntot - nt * 128 < 128 ? p.Ntot - nt * 128 : 128) : p.BN;
+          mbar_arrive_expect_tx(&bar_full[stage], a_bytes + (uint32_t)wrows * p.BK * 2);
           if (p.mode == 0) tma_load_4d(mA, &bar_full[stage], sa, c0, w0 + p.dx[tap], h0 + p.dy[tap], n0);
           else if (p.mode == 1) tma_load_3d(mA, &bar_full[stage], sa, c0, w0, h0);
           else tma_load_5d(mA, &bar_full[stage], sa, c0, p.dx[tap], w0, p.dy[tap], h0);
-          tma_load_2d(&mapB, &bar_full[stage], sb, tap * Ktap + (second ? p.C0 : 0) + c0, nt * p.BN);
+          tma_load_2d(&mapB, &bar_full[stage], sb, tap * Ktap + (second ? p.C0 : 0) + c0, nt * (p.swap ? 128 : p.BN));
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -123,7 +183,7 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
   } else if (warp == 1) {
     // ===================================================== MMA issuer (single thread)
     if (elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(TC_BM, p.BN, 0, 0);
+      const uint32_t idesc = p.swap ? make_idesc_bf16(128, 256, 0, 0) : make_idesc_bf16(TC_BM, p.BN, 0, 0);
       const uint32_t swz = (p.BK == 64) ? SWZ_128B : SWZ_64B;
       const uint32_t sbo = 8u * p.BK * 2u;          // 8 rows of BK bf16
       const int ksteps = p.BK / 16;
@@ -132,14 +192,15 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&bar_full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint32_t sb = sa + a_bytes;
-          const uint64_t da = make_smem_desc(sa, 16, sbo, swz);
-          const uint64_t db = make_smem_desc(sb, 16, sbo, swz);
+          // swapped: A = weight tile, B = pixel tile
+          const uint64_t da = make_smem_desc(p.swap ? sb : sa, 16, sbo, swz);
+          const uint64_t db = make_smem_desc(p.swap ? sa : sb, 16, sbo, swz);
           for (int k = 0; k < ksteps; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
             umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
@@ -159,6 +220,38 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int nt = tile % num_ntiles, mt = tile / num_ntiles;
       const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+      if (p.swap) {
+        // lane = GEMM row (output channel incl. convT sub-position), column = pixel of the 256-pixel tile
+        const int grow = nt * 128 + quarter * 32;          // first GEMM row of this warp
+        const bool warp_valid = grow < p.Ntot;
+        const int z = grow / p.Cz, cw = grow % p.Cz;
+        const int ody = p.Cz < p.Ntot ? (z >> 1) : p.ody, odx = p.Cz < p.Ntot ? (z & 1) : p.odx;
+        const float sc = warp_valid ? s_scale[cw + lane] : 0.f, sh = warp_valid ? s_shift[cw + lane] : 0.f;
+        auto pix_index = [&](int mm) -> long long {
+          int n2, gh2, gw2;
+          if (p.mode == 0) {
+            gw2 = tw * p.bw + mm % p.bw;
+            gh2 = th * p.bh + (mm / p.bw) % p.bh;
+            n2 = tn * p.bn + mm / (p.bw * p.bh);
+            if (gw2 >= p.GW || gh2 >= p.GH || n2 >= p.N) return -1;
+          } else {
+            gw2 = tw * p.bw + mm % p.bw;
+            const int r2 = th * p.bh + mm / p.bw;
+            if (gw2 >= p.GW || r2 >= p.N * p.GH) return -1;
+            n2 = r2 / p.GH; gh2 = r2 % p.GH;
+          }
+          return (long long)((((size_t)n2 * p.OH + (gh2 * p.osy + ody)) * p.OW + (gw2 * p.osx + odx)) * p.OC + cw);
+        };
+        mbar_wait(&bar_tfull[acc], acc_phase);
+        tc_fence_after();
+        epilogue_swapped(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols), 256, warp_valid, sc, sh,
+                         p.relu, p.out_f32, p.out, s_stage[quarter], lane, pix_index);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       // pixel of this row
       int n, gh, gw;
       bool valid;
@@ -250,7 +343,8 @@ struct TcStripParams {
   int C0, C1, BK, nkc;
   int Cout;
   int R, ring, wsegs, hchunks;
-  int slot_bytes;           // 130 * BK * 2 rounded up to 1024
+  int slot_bytes;           // (PX + 2) * BK * 2 rounded up to 1024
+  int swap;                 // 1: 256-pixel segments, weights as the MMA A operand (see TcFwdParams::swap)
   int relu, out_f32;
   __nv_bfloat16* out;
   const float* scale;
@@ -259,12 +353,15 @@ struct TcStripParams {
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                        const __grid_constant__ CUtensorMap mapT0, const __grid_constant__ CUtensorMap mapT1,
                         const __grid_constant__ CUtensorMap mapB, const TcStripParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t bar_w, row_full[ST_MAX_RING], row_empty[ST_MAX_RING], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_scale[128], s_shift[128];
+  __shared__ __align__(16) uint8_t s_stage[4][4096];             // transpose tiles of the swapped epilogue
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int PX = p.swap ? 256 : 128;                             // pixels per tile (one image-row segment)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int K = p.C0 + p.C1;
   const uint32_t wblk_bytes = p.Cout * p.BK * 2;                 // one (tap, kc) weight tile
@@ -272,10 +369,11 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   uint8_t* s_w = smem;
   uint8_t* s_ring = smem + ((w_bytes + 1023) & ~1023u);
   const uint32_t row_bytes = (uint32_t)p.nkc * p.slot_bytes;     // one halo row = nkc chunk boxes
-  const uint32_t box_bytes = 130u * p.BK * 2u;
+  const uint32_t box_bytes = (uint32_t)(PX + 2) * p.BK * 2u;
   const int num_items = p.N * p.hchunks * p.wsegs;
+  const int acc_cols = p.swap ? 256 : p.Cout;
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2u * p.Cout) tmem_cols <<= 1;
+  while (tmem_cols < 2u * acc_cols) tmem_cols <<= 1;
 
   for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
     s_scale[i] = p.scale ? p.scale[i] : 1.f;
@@ -299,7 +397,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   auto decode = [&](int item, int& n, int& h0, int& rows, int& w0) {
     const int ws = item % p.wsegs; item /= p.wsegs;
     const int hc = item % p.hchunks; n = item / p.hchunks;
-    h0 = hc * p.R; rows = p.H - h0 < p.R ? p.H - h0 : p.R; w0 = ws * 128;
+    h0 = hc * p.R; rows = p.H - h0 < p.R ? p.H - h0 : p.R; w0 = ws * PX;
   };
 
   if (warp == 0) {
@@ -321,15 +419,21 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
           uint8_t* dst = s_ring + (size_t)pos * row_bytes;
           for (int kc = 0; kc < p.nkc; ++kc) {
             const bool second = kc >= kc0;
-            tma_load_4d(second ? &mapA1 : &mapA0, &row_full[pos], dst + (size_t)kc * p.slot_bytes,
-                        (second ? kc - kc0 : kc) * p.BK, w0 - 1, h0 + rr, n);
+            const int cc = (second ? kc - kc0 : kc) * p.BK;
+            if (!p.swap) {
+              tma_load_4d(second ? &mapA1 : &mapA0, &row_full[pos], dst + (size_t)kc * p.slot_bytes, cc, w0 - 1, h0 + rr, n);
+            } else {   // 258-pixel halo row = a 256-pixel box + a 2-pixel box (TMA boxes are limited to 256 per dim)
+              tma_load_4d(second ? &mapA1 : &mapA0, &row_full[pos], dst + (size_t)kc * p.slot_bytes, cc, w0 - 1, h0 + rr, n);
+              tma_load_4d(second ? &mapT1 : &mapT0, &row_full[pos], dst + (size_t)kc * p.slot_bytes + 256u * p.BK * 2u, cc,
+                          w0 + 255, h0 + rr, n);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(TC_BM, p.Cout, 0, 0);
+      const uint32_t idesc = p.swap ? make_idesc_bf16(128, 256, 0, 0) : make_idesc_bf16(TC_BM, p.Cout, 0, 0);
       const uint32_t swz = (p.BK == 64) ? SWZ_128B : SWZ_64B;
       const uint32_t pitch = p.BK * 2u, sbo = 8u * pitch;
       const int ksteps = p.BK / 16;
@@ -348,7 +452,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
           mbar_wait(&row_full[(c0 + t + 2) % p.ring], ((c0 + t + 2) / p.ring) & 1);
           mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Cout);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
           uint32_t first = 1;
           for (int dy = 0; dy < 3; ++dy) {
             const uint32_t row_addr = ring_base + ((c0 + t + dy) % p.ring) * row_bytes;
@@ -357,8 +461,10 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
                 const uint32_t a_addr = row_addr + kc * p.slot_bytes + dx * pitch;   // halo box starts at pixel w0-1
                 const uint32_t b_addr = w_base + ((dy * 3 + dx) * p.nkc + kc) * wblk_bytes;
                 for (int k = 0; k < ksteps; ++k) {
-                  umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32, 16, sbo, swz),
-                            make_smem_desc(b_addr + k * 32, 16, sbo, swz), idesc, first ? 0u : 1u);
+                  const uint64_t dpx = make_smem_desc(a_addr + k * 32, 16, sbo, swz);   // pixels
+                  const uint64_t dwt = make_smem_desc(b_addr + k * 32, 16, sbo, swz);   // weights
+                  if (p.swap) umma_bf16(d_tmem, dwt, dpx, idesc, first ? 0u : 1u);
+                  else umma_bf16(d_tmem, dpx, dwt, idesc, first ? 0u : 1u);
                   first = 0;
                 }
               }
@@ -381,6 +487,21 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
       int n, h0, rows, w0;
       decode(item, n, h0, rows, w0);
       for (int t = 0; t < rows; ++t) {
+        if (p.swap) {
+          const bool warp_valid = quarter * 32 < p.Cout;
+          const float sc = warp_valid ? s_scale[quarter * 32 + lane] : 0.f, sh = warp_valid ? s_shift[quarter * 32 + lane] : 0.f;
+          const size_t row0 = (((size_t)n * p.H + (h0 + t)) * p.W + w0) * p.Cout + quarter * 32;
+          auto pix_index = [&](int mm) -> long long { return (long long)(row0 + (size_t)mm * p.Cout); };
+          mbar_wait(&bar_tfull[acc], acc_phase);
+          tc_fence_after();
+          epilogue_swapped(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols), 256, warp_valid, sc, sh,
+                           p.relu, p.out_f32, p.out, s_stage[quarter], lane, pix_index);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
         const size_t oidx = (((size_t)n * p.H + (h0 + t)) * p.W + (w0 + m)) * p.Cout;
         __nv_bfloat16* orow = p.out + oidx;
         float* orow_f = reinterpret_cast<float*>(p.out) + oidx;
@@ -499,6 +620,7 @@ static int pick_pow2_box(int extent, int maxbox) {
 // strip kernel plan; returns false when the layer is not eligible
 static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, TcStripParams& p, size_t& dyn_smem) {
   static const bool disabled = getenv("DCB_NO_STRIP") != nullptr;
+  static const bool no_swap = getenv("DCB_NO_SWAP") != nullptr;
   if (disabled) return false;
   if (g.ntaps != 9 || g.zsub > 1 || g.sy != 1) return false;
   if (g.GW % 128 != 0 || Nout > 128 || Nout % 32 != 0) return false;
@@ -506,14 +628,21 @@ static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, TcStripParams
   const int BK = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
   const int nkc = K / BK;
   const size_t w_bytes = ((size_t)9 * K * Nout * 2 + 1023) & ~(size_t)1023;
-  const int slot = (130 * BK * 2 + 1023) & ~1023;
-  const size_t budget = 200 * 1024;
-  if (w_bytes + (size_t)5 * nkc * slot > budget) return false;
-  int ring = (int)((budget - w_bytes) / ((size_t)nkc * slot));
+  const size_t budget = 207 * 1024;
+  // swapped orientation (256-pixel segments, N = 256 per MMA) whenever the image is wide enough
+  int swap = (!no_swap && g.GW % 256 == 0) ? 1 : 0;
+  int slot = 0, ring = 0;
+  for (; swap >= 0; --swap) {
+    const int px = swap ? 256 : 128;
+    slot = ((px + 2) * BK * 2 + 1023) & ~1023;
+    // the MMA reads 128 weight rows starting at each (tap, kc) block: keep those reads inside the allocation
+    if (w_bytes + (size_t)4 * nkc * slot <= budget) { ring = (int)((budget - w_bytes) / ((size_t)nkc * slot)); break; }
+  }
+  if (swap < 0) return false;
   if (ring > ST_MAX_RING) ring = ST_MAX_RING;
   memset(&p, 0, sizeof(p));
   p.N = g.N; p.H = g.GH; p.W = g.GW; p.C0 = C0; p.C1 = C1; p.BK = BK; p.nkc = nkc; p.Cout = Nout;
-  p.ring = ring; p.slot_bytes = slot; p.wsegs = g.GW / 128;
+  p.ring = ring; p.slot_bytes = slot; p.swap = swap; p.wsegs = g.GW / (swap ? 256 : 128);
   int R = 32;
   while (R > 8 && (long long)g.N * cdiv(g.GH, R) * p.wsegs < 4LL * sm_count()) R >>= 1;
   p.R = R; p.hchunks = cdiv(g.GH, R);
@@ -532,15 +661,18 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
     size_t dyn = 0;
     if (plan_strip(g, C0, C1, Nout, sp, dyn)) {
       sp.relu = relu; sp.out_f32 = out_f32; sp.out = reinterpret_cast<__nv_bfloat16*>(out); sp.scale = scale; sp.shift = shift;
-      CUtensorMap mA0, mA1, mB;
-      auto mk = [&](CUtensorMap* m, const void* ptr, int C) -> int {
+      CUtensorMap mA0, mA1, mT0, mT1, mB;
+      auto mk = [&](CUtensorMap* m, const void* ptr, int C, uint32_t boxw) -> int {
         uint64_t dims[4] = {(uint64_t)C, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.N};
         uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)g.IW * C * 2, (uint64_t)g.IH * g.IW * C * 2};
-        uint32_t box[4] = {(uint32_t)sp.BK, 130u, 1u, 1u};
+        uint32_t box[4] = {(uint32_t)sp.BK, boxw, 1u, 1u};
         return make_map(m, ptr, 4, dims, str, box, sp.BK * 2);
       };
-      if (int e = mk(&mA0, s0, C0)) return e;
-      if (C1 > 0) { if (int e = mk(&mA1, s1, C1)) return e; } else mA1 = mA0;
+      const uint32_t mainw = sp.swap ? 256u : 130u;
+      if (int e = mk(&mA0, s0, C0, mainw)) return e;
+      if (int e = mk(&mT0, s0, C0, 2u)) return e;
+      if (C1 > 0) { if (int e = mk(&mA1, s1, C1, mainw)) return e; if (int e = mk(&mT1, s1, C1, 2u)) return e; }
+      else { mA1 = mA0; mT1 = mT0; }
       {
         const int Ktot = 9 * (C0 + C1);
         uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)Nout};
@@ -550,13 +682,13 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
       }
       static bool attr_set_strip = false;
       if (!attr_set_strip) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
         if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
         attr_set_strip = true;
       }
       const int items = sp.N * sp.hchunks * sp.wsegs;
       const int grid = items < sm_count() ? items : sm_count();
-      tapgemm_tc_strip_kernel<<<grid, TC_THREADS, dyn, st>>>(mA0, mA1, mB, sp);
+      tapgemm_tc_strip_kernel<<<grid, TC_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
       g_launches += 1;
       DCB_LAUNCH_OK("tapgemm_tc_strip_kernel");
       return DCB_OK;
@@ -579,16 +711,23 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
   p.OH = g.OH; p.OW = g.OW; p.OC = Nout;
   p.osy = g.osy; p.osx = g.osx; p.ody = g.ody; p.odx = g.odx;
   p.relu = relu; p.out_f32 = out_f32; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.scale = scale; p.shift = shift;
-
+  // Swapped orientation for narrow outputs: with <= 128 output channels the normal orientation spends the
+  // A-operand read time (128 pixel rows per MMA) on an N of 32..128; swapped, every MMA covers 256 pixels.
+  {
+    static const bool no_swap = getenv("DCB_NO_SWAP") != nullptr;
+    const long long px = (long long)g.N * g.GH * g.GW;
+    p.swap = (!no_swap && Nout <= 128 && px / 256 * cdiv(p.Ntot, 128) >= sm_count() / 2) ? 1 : 0;
+  }
+  const int TM = p.swap ? 256 : TC_BM;
   // ---- M tiling
   if (p.mode == 0) {
-    p.bw = pick_pow2_box(g.GW, TC_BM);
-    p.bh = pick_pow2_box(g.GH, TC_BM / p.bw);
-    p.bn = TC_BM / (p.bw * p.bh);
+    p.bw = pick_pow2_box(g.GW, TM);
+    p.bh = pick_pow2_box(g.GH, TM / p.bw);
+    p.bn = TM / (p.bw * p.bh);
     p.tiles_w = cdiv(g.GW, p.bw); p.tiles_h = cdiv(g.GH, p.bh); p.tiles_n = cdiv(g.N, p.bn);
   } else {
-    p.bw = pick_pow2_box(g.GW, TC_BM);
-    p.bh = TC_BM / p.bw; p.bn = 1;
+    p.bw = pick_pow2_box(g.GW, TM);
+    p.bh = TM / p.bw; p.bn = 1;
     p.tiles_w = cdiv(g.GW, p.bw); p.tiles_h = cdiv((long long)g.N * g.GH, p.bh); p.tiles_n = 1;
   }
   const int num_mtiles = p.tiles_w * p.tiles_h * p.tiles_n;
@@ -596,8 +735,9 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
   int BN = p.Cz < 256 ? p.Cz : 256;
   while (BN > 64 && (long long)num_mtiles * (p.Ntot / BN) < sm_count() && p.Cz % (BN / 2) == 0) BN /= 2;
   if (p.Cz % BN != 0) BN = 32;
+  if (p.swap) BN = p.Ntot < 128 ? p.Ntot : 128;       // rows of the weight TMA box
   p.BN = BN;
-  const size_t stage_bytes = (size_t)TC_BM * p.BK * 2 + (size_t)BN * p.BK * 2;
+  const size_t stage_bytes = (size_t)TM * p.BK * 2 + (size_t)(p.swap ? 128 : BN) * p.BK * 2;
   int stages = (int)((200 * 1024) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages < 2) return fail(DCB_ERR_UNSUPPORTED, "tile does not fit shared memory");
@@ -642,7 +782,7 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
     if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int num_tiles = num_mtiles * (p.Ntot / BN);
+  const int num_tiles = num_mtiles * (p.swap ? cdiv(p.Ntot, 128) : p.Ntot / BN);
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
   tapgemm_tc_fwd_kernel<<<grid, TC_THREADS, dyn_smem, st>>>(mA0, mA1, mB, p);
   g_launches += 1;

@@ -47,6 +47,10 @@ CONV_CASES = [
     (1, 20, 128, 32, 32, 32),
     (1, 1, 128, 32, 0, 64),
     (3, 37, 128, 64, 0, 32),
+    (1, 9, 512, 32, 32, 32),
+    # enough 256-pixel tiles for the swapped (weights-as-A) orientation of the generic kernel
+    (8, 64, 64, 64, 0, 128),
+    (5, 48, 80, 64, 64, 64),
 ]
 
 
@@ -93,7 +97,8 @@ def test_conv3x3_fwd_dgrad_wgrad(cuda, precision, case):
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
-@pytest.mark.parametrize('case', [(1, 8, 8, 64, 32), (2, 4, 4, 512, 256), (1, 16, 16, 128, 64), (3, 2, 2, 256, 128)])
+@pytest.mark.parametrize('case', [(1, 8, 8, 64, 32), (2, 4, 4, 512, 256), (1, 16, 16, 128, 64), (3, 2, 2, 256, 128),
+                                  (4, 64, 64, 128, 64), (8, 64, 64, 64, 32)])
 def test_convT2x2_fwd_dgrad_wgrad(cuda, precision, case):
     from deepcalcium.engine import ops
     N, h, w_, Cin, Cout = case
