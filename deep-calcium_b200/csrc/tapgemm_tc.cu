@@ -27,7 +27,8 @@ using namespace tc;
 
 constexpr int TC_BM = 128;          // pixels per tile (= UMMA M, one TMEM lane per pixel)
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 64 + 16 * 32;   // TMA warp + MMA warp + 16 epilogue warps (4 per TMEM lane quarter)
+constexpr int WG_THREADS = 192;
 
 struct TcFwdParams {
   int mode;                 // 0: 4-D halo box (conv3x3)  1: 3-D merged rows (convT fwd)  2: 5-D strided (convT dgrad)
@@ -53,52 +54,35 @@ struct TcFwdParams {
 };
 
 // Epilogue of the "swapped" orientation (TMEM lane = output channel, TMEM column = pixel): each thread
-// owns one channel and receives 32 consecutive pixels per tcgen05.ld; the 32 x 32 block is transposed
-// through a per-warp shared-memory tile so that global stores stay NHWC-contiguous (64 B of bf16 or
-// 128 B of fp32 per pixel and warp).  pix_index(m) returns the element index of pixel m's first
-// channel of this warp, or -1 when the pixel lies outside the tensor.
+// owns one channel and receives 32 consecutive pixels per tcgen05.ld.  The 32 lanes of a warp hold 32
+// consecutive channels of the SAME pixel, so one store instruction per pixel writes 64 contiguous bytes
+// of bf16 (128 of fp32) - NHWC-coalesced without a transpose.  pix_index(m) returns the element index
+// of pixel m's first channel of this warp, or -1 when the pixel lies outside the tensor.
 template <typename PixFn>
-__device__ __forceinline__ void epilogue_swapped(uint32_t t_addr, int npix, bool warp_valid, float sc, float sh, int relu,
-                                                 int out_f32, void* out_base, uint8_t* stage, int lane, PixFn pix_index) {
-  for (int j = 0; j < npix; j += 32) {
+__device__ __forceinline__ void epilogue_swapped(uint32_t t_addr, int col0, int ncols, bool warp_valid, float sc, float sh,
+                                                 int relu, int out_f32, void* out_base, int lane, PixFn pix_index) {
+  for (int j = col0; j < col0 + ncols; j += 32) {
     uint32_t r[32];
     tmem_ld_32x32b_x32(t_addr + j, r);
     tmem_ld_wait();
     if (!warp_valid) continue;
-    __syncwarp();
     if (out_f32) {
-      float* st = reinterpret_cast<float*>(stage);
+      float* ob = reinterpret_cast<float*>(out_base);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         float v = fmaf(__uint_as_float(r[i]), sc, sh);
         if (relu) v = fmaxf(v, 0.f);
-        st[i * 32 + lane] = v;
-      }
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int idx = lane + 32 * q, px = idx >> 3, chunk = idx & 7;
-        const long long o = pix_index(j + px);
-        if (o >= 0)
-          *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_base) + o + chunk * 4) =
-              *reinterpret_cast<const float4*>(st + px * 32 + chunk * 4);
+        const long long o = pix_index(j + i);
+        if (o >= 0) ob[o + lane] = v;
       }
     } else {
-      __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(stage);
+      __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out_base);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         float v = fmaf(__uint_as_float(r[i]), sc, sh);
         if (relu) v = fmaxf(v, 0.f);
-        st[i * 32 + lane] = __float2bfloat16_rn(v);
-      }
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int idx = lane + 32 * q, px = idx >> 2, chunk = idx & 3;
-        const long long o = pix_index(j + px);
-        if (o >= 0)
-          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_base) + o + chunk * 8) =
-              *reinterpret_cast<const uint4*>(st + px * 32 + chunk * 8);
+        const long long o = pix_index(j + i);
+        if (o >= 0) ob[o + lane] = __float2bfloat16_rn(v);
       }
     }
   }
@@ -129,7 +113,6 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
   const int acc_cols = p.swap ? 256 : p.BN;          // TMEM columns per accumulator stage
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2u * acc_cols) tmem_cols <<= 1;
-  __shared__ __align__(16) uint8_t s_stage[4][4096];  // per-epilogue-warp transpose tiles (swapped mode)
 
   for (int i = threadIdx.x; i < p.Cz; i += blockDim.x) {
     s_scale[i] = p.scale ? p.scale[i] : 1.f;
@@ -140,7 +123,8 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
     if (p.C1 > 0) tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapB);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 4); }
+    // normal mode: the 4 warps of epilogue group 0 drain a tile; swapped mode: all 16 epilogue warps do
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], p.swap ? 16 : 4); }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -215,9 +199,10 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
   } else {
     // ===================================================== epilogue warps (TMEM -> regs -> global)
     const int quarter = warp & 3;                    // TMEM lanes [32*quarter, 32*quarter+32)
+    const int egroup = (warp - 2) >> 2;              // 4 epilogue warps share a lane quarter and split the columns
     const int m = quarter * 32 + lane;               // row of the tile = pixel
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < num_tiles && (p.swap || egroup == 0); tile += gridDim.x) {
       const int nt = tile % num_ntiles, mt = tile / num_ntiles;
       const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
       if (p.swap) {
@@ -227,25 +212,28 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
         const int z = grow / p.Cz, cw = grow % p.Cz;
         const int ody = p.Cz < p.Ntot ? (z >> 1) : p.ody, odx = p.Cz < p.Ntot ? (z & 1) : p.odx;
         const float sc = warp_valid ? s_scale[cw + lane] : 0.f, sh = warp_valid ? s_shift[cw + lane] : 0.f;
+        // box extents are powers of two: decode a tile pixel with shifts
+        const int bw_sh = 31 - __clz(p.bw), bh_sh = 31 - __clz(p.bh);
         auto pix_index = [&](int mm) -> long long {
-          int n2, gh2, gw2;
+          const int gw2 = tw * p.bw + (mm & (p.bw - 1));
+          if (gw2 >= p.GW) return -1;
+          size_t orow;                                  // output row index n * OH + oh
           if (p.mode == 0) {
-            gw2 = tw * p.bw + mm % p.bw;
-            gh2 = th * p.bh + (mm / p.bw) % p.bh;
-            n2 = tn * p.bn + mm / (p.bw * p.bh);
-            if (gw2 >= p.GW || gh2 >= p.GH || n2 >= p.N) return -1;
-          } else {
-            gw2 = tw * p.bw + mm % p.bw;
-            const int r2 = th * p.bh + mm / p.bw;
-            if (gw2 >= p.GW || r2 >= p.N * p.GH) return -1;
-            n2 = r2 / p.GH; gh2 = r2 % p.GH;
+            const int gh2 = th * p.bh + ((mm >> bw_sh) & (p.bh - 1));
+            const int n2 = tn * p.bn + (mm >> (bw_sh + bh_sh));
+            if (gh2 >= p.GH || n2 >= p.N) return -1;
+            orow = (size_t)n2 * p.OH + (gh2 * p.osy + ody);
+          } else {                                      // merged (n, gh) rows: OH == GH * osy
+            const int r2 = th * p.bh + (mm >> bw_sh);
+            if (r2 >= p.N * p.GH) return -1;
+            orow = (size_t)r2 * p.osy + ody;
           }
-          return (long long)((((size_t)n2 * p.OH + (gh2 * p.osy + ody)) * p.OW + (gw2 * p.osx + odx)) * p.OC + cw);
+          return (long long)((orow * p.OW + (gw2 * p.osx + odx)) * p.OC + cw);
         };
         mbar_wait(&bar_tfull[acc], acc_phase);
         tc_fence_after();
-        epilogue_swapped(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols), 256, warp_valid, sc, sh,
-                         p.relu, p.out_f32, p.out, s_stage[quarter], lane, pix_index);
+        epilogue_swapped(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols), egroup * 64, 64, warp_valid,
+                         sc, sh, p.relu, p.out_f32, p.out, lane, pix_index);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_tempty[acc]);
@@ -359,7 +347,6 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   __shared__ uint64_t bar_w, row_full[ST_MAX_RING], row_empty[ST_MAX_RING], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_scale[128], s_shift[128];
-  __shared__ __align__(16) uint8_t s_stage[4][4096];             // transpose tiles of the swapped epilogue
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int PX = p.swap ? 256 : 128;                             // pixels per tile (one image-row segment)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -385,7 +372,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
     tma_prefetch_desc(&mapB);
     mbar_init(&bar_w, 1);
     for (int s = 0; s < p.ring; ++s) { mbar_init(&row_full[s], 1); mbar_init(&row_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], p.swap ? 16 : 4); }
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(&tmem_base_smem, tmem_cols); tmem_relinquish(); }
@@ -481,9 +468,10 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
     }
   } else {
     const int quarter = warp & 3;
+    const int egroup = (warp - 2) >> 2;
     const int m = quarter * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    for (int item = blockIdx.x; item < num_items && (p.swap || egroup == 0); item += gridDim.x) {
       int n, h0, rows, w0;
       decode(item, n, h0, rows, w0);
       for (int t = 0; t < rows; ++t) {
@@ -494,8 +482,8 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
           auto pix_index = [&](int mm) -> long long { return (long long)(row0 + (size_t)mm * p.Cout); };
           mbar_wait(&bar_tfull[acc], acc_phase);
           tc_fence_after();
-          epilogue_swapped(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols), 256, warp_valid, sc, sh,
-                           p.relu, p.out_f32, p.out, s_stage[quarter], lane, pix_index);
+          epilogue_swapped(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols), egroup * 64, 64,
+                           warp_valid, sc, sh, p.relu, p.out_f32, p.out, lane, pix_index);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_tempty[acc]);
@@ -811,7 +799,7 @@ struct TcWgradParams {
   float* part;              // [splits][ntaps][K][Nout]
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 tapgemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                         const __grid_constant__ CUtensorMap mapG, const TcWgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1058,7 +1046,7 @@ int run_tc_wgrad(const TapGeom& g, const void* s0, int C0, const void* s1, int C
   const size_t dyn_smem = w.stages * stage_bytes + 1024;
   const int num_items = cdiv(K, 128) * (Nout / w.BN) * g.ntaps * w.splits;
   const int grid = num_items < sm_count() ? num_items : sm_count();
-  tapgemm_tc_wgrad_kernel<<<grid, TC_THREADS, dyn_smem, st>>>(mA0, mA1, mG, p);
+  tapgemm_tc_wgrad_kernel<<<grid, WG_THREADS, dyn_smem, st>>>(mA0, mA1, mG, p);
   DCB_LAUNCH_OK("tapgemm_tc_wgrad_kernel");
   launch_reduce_splits(p.part, w.splits, (size_t)g.ntaps * K * Nout, dW, st);
   g_launches += 2;
