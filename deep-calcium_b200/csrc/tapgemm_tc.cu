@@ -27,8 +27,7 @@ using namespace tc;
 
 constexpr int TC_BM = 128;          // pixels per tile (= UMMA M, one TMEM lane per pixel)
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_THREADS = 64 + 16 * 32;   // TMA warp + MMA warp + 16 epilogue warps (4 per TMEM lane quarter)
-constexpr int WG_THREADS = 192;
+constexpr int TC_THREADS = 192;
 
 struct TcFwdParams {
   int mode;                 // 0: 4-D halo box (conv3x3)  1: 3-D merged rows (convT fwd)  2: 5-D strided (convT dgrad)
@@ -54,35 +53,52 @@ struct TcFwdParams {
 };
 
 // Epilogue of the "swapped" orientation (TMEM lane = output channel, TMEM column = pixel): each thread
-// owns one channel and receives 32 consecutive pixels per tcgen05.ld.  The 32 lanes of a warp hold 32
-// consecutive channels of the SAME pixel, so one store instruction per pixel writes 64 contiguous bytes
-// of bf16 (128 of fp32) - NHWC-coalesced without a transpose.  pix_index(m) returns the element index
-// of pixel m's first channel of this warp, or -1 when the pixel lies outside the tensor.
+// owns one channel and receives 32 consecutive pixels per tcgen05.ld; the 32 x 32 block is transposed
+// through a per-warp shared-memory tile so that global stores stay NHWC-contiguous (64 B of bf16 or
+// 128 B of fp32 per pixel and warp).  pix_index(m) returns the element index of pixel m's first
+// channel of this warp, or -1 when the pixel lies outside the tensor.
 template <typename PixFn>
-__device__ __forceinline__ void epilogue_swapped(uint32_t t_addr, int col0, int ncols, bool warp_valid, float sc, float sh,
-                                                 int relu, int out_f32, void* out_base, int lane, PixFn pix_index) {
-  for (int j = col0; j < col0 + ncols; j += 32) {
+__device__ __forceinline__ void epilogue_swapped(uint32_t t_addr, int npix, bool warp_valid, float sc, float sh, int relu,
+                                                 int out_f32, void* out_base, uint8_t* stage, int lane, PixFn pix_index) {
+  for (int j = 0; j < npix; j += 32) {
     uint32_t r[32];
     tmem_ld_32x32b_x32(t_addr + j, r);
     tmem_ld_wait();
     if (!warp_valid) continue;
+    __syncwarp();
     if (out_f32) {
-      float* ob = reinterpret_cast<float*>(out_base);
+      float* st = reinterpret_cast<float*>(stage);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         float v = fmaf(__uint_as_float(r[i]), sc, sh);
         if (relu) v = fmaxf(v, 0.f);
-        const long long o = pix_index(j + i);
-        if (o >= 0) ob[o + lane] = v;
+        st[i * 32 + lane] = v;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int idx = lane + 32 * q, px = idx >> 3, chunk = idx & 7;
+        const long long o = pix_index(j + px);
+        if (o >= 0)
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_base) + o + chunk * 4) =
+              *reinterpret_cast<const float4*>(st + px * 32 + chunk * 4);
       }
     } else {
-      __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out_base);
+      __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(stage);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         float v = fmaf(__uint_as_float(r[i]), sc, sh);
         if (relu) v = fmaxf(v, 0.f);
-        const long long o = pix_index(j + i);
-        if (o >= 0) ob[o + lane] = __float2bfloat16_rn(v);
+        st[i * 32 + lane] = __float2bfloat16_rn(v);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int idx = lane + 32 * q, px = idx >> 2, chunk = idx & 3;
+        const long long o = pix_index(j + px);
+        if (o >= 0)
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_base) + o + chunk * 8) =
+              *reinterpret_cast<const uint4*>(st + px * 32 + chunk * 8);
       }
     }
   }
@@ -113,6 +129,7 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
   const int acc_cols = p.swap ? 256 : p.BN;          // TMEM columns per accumulator stage
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2u * acc_cols) tmem_cols <<= 1;
+  __shared__ __align__(16) uint8_t s_stage[4][4096];  // per-epilogue-warp transpose tiles (swapped mode)
 
   for (int i = threadIdx.x; i < p.Cz; i += blockDim.x) {
     s_scale[i] = p.scale ? p.scale[i] : 1.f;
@@ -123,8 +140,7 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
     if (p.C1 > 0) tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapB);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
-    // normal mode: the 4 warps of epilogue group 0 drain a tile; swapped mode: all 16 epilogue warps do
-    for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], p.swap ? 16 : 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 4); }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -171,6 +187,8 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
       const uint32_t swz = (p.BK == 64) ? SWZ_128B : SWZ_64B;
       const uint32_t sbo = 8u * p.BK * 2u;          // 8 rows of BK bf16
       const int ksteps = p.BK / 16;
+      const uint64_t dbase = make_smem_desc(0, 16, sbo, swz);
+      const uint32_t smem16 = smem_u32(smem) >> 4, stage16 = stage_bytes >> 4, a16 = a_bytes >> 4;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -180,14 +198,15 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&bar_full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t sb = sa + a_bytes;
-          // swapped: A = weight tile, B = pixel tile
-          const uint64_t da = make_smem_desc(p.swap ? sb : sa, 16, sbo, swz);
-          const uint64_t db = make_smem_desc(p.swap ? sa : sb, 16, sbo, swz);
-          for (int k = 0; k < ksteps; ++k) {
+          // descriptors differ only in the 14-bit start-address field: one add per operand and K step keeps
+          // the single issuing thread far below the ~89-128 cycles an MMA occupies the tensor pipe
+          const uint32_t sa16 = smem16 + (uint32_t)stage * stage16, sb16 = sa16 + a16;
+          const uint64_t da = dbase + (p.swap ? sb16 : sa16);   // swapped: A = weight tile, B = pixel tile
+          const uint64_t db = dbase + (p.swap ? sa16 : sb16);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            if (k < ksteps) umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&bar_empty[stage]);            // smem slot free once these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -199,10 +218,9 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
   } else {
     // ===================================================== epilogue warps (TMEM -> regs -> global)
     const int quarter = warp & 3;                    // TMEM lanes [32*quarter, 32*quarter+32)
-    const int egroup = (warp - 2) >> 2;              // 4 epilogue warps share a lane quarter and split the columns
     const int m = quarter * 32 + lane;               // row of the tile = pixel
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles && (p.swap || egroup == 0); tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int nt = tile % num_ntiles, mt = tile / num_ntiles;
       const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
       if (p.swap) {
@@ -212,28 +230,25 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
         const int z = grow / p.Cz, cw = grow % p.Cz;
         const int ody = p.Cz < p.Ntot ? (z >> 1) : p.ody, odx = p.Cz < p.Ntot ? (z & 1) : p.odx;
         const float sc = warp_valid ? s_scale[cw + lane] : 0.f, sh = warp_valid ? s_shift[cw + lane] : 0.f;
-        // box extents are powers of two: decode a tile pixel with shifts
-        const int bw_sh = 31 - __clz(p.bw), bh_sh = 31 - __clz(p.bh);
         auto pix_index = [&](int mm) -> long long {
-          const int gw2 = tw * p.bw + (mm & (p.bw - 1));
-          if (gw2 >= p.GW) return -1;
-          size_t orow;                                  // output row index n * OH + oh
+          int n2, gh2, gw2;
           if (p.mode == 0) {
-            const int gh2 = th * p.bh + ((mm >> bw_sh) & (p.bh - 1));
-            const int n2 = tn * p.bn + (mm >> (bw_sh + bh_sh));
-            if (gh2 >= p.GH || n2 >= p.N) return -1;
-            orow = (size_t)n2 * p.OH + (gh2 * p.osy + ody);
-          } else {                                      // merged (n, gh) rows: OH == GH * osy
-            const int r2 = th * p.bh + (mm >> bw_sh);
-            if (r2 >= p.N * p.GH) return -1;
-            orow = (size_t)r2 * p.osy + ody;
+            gw2 = tw * p.bw + mm % p.bw;
+            gh2 = th * p.bh + (mm / p.bw) % p.bh;
+            n2 = tn * p.bn + mm / (p.bw * p.bh);
+            if (gw2 >= p.GW || gh2 >= p.GH || n2 >= p.N) return -1;
+          } else {
+            gw2 = tw * p.bw + mm % p.bw;
+            const int r2 = th * p.bh + mm / p.bw;
+            if (gw2 >= p.GW || r2 >= p.N * p.GH) return -1;
+            n2 = r2 / p.GH; gh2 = r2 % p.GH;
           }
-          return (long long)((orow * p.OW + (gw2 * p.osx + odx)) * p.OC + cw);
+          return (long long)((((size_t)n2 * p.OH + (gh2 * p.osy + ody)) * p.OW + (gw2 * p.osx + odx)) * p.OC + cw);
         };
         mbar_wait(&bar_tfull[acc], acc_phase);
         tc_fence_after();
-        epilogue_swapped(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols), egroup * 64, 64, warp_valid,
-                         sc, sh, p.relu, p.out_f32, p.out, lane, pix_index);
+        epilogue_swapped(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols), 256, warp_valid, sc, sh,
+                         p.relu, p.out_f32, p.out, s_stage[quarter], lane, pix_index);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_tempty[acc]);
@@ -347,6 +362,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   __shared__ uint64_t bar_w, row_full[ST_MAX_RING], row_empty[ST_MAX_RING], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_scale[128], s_shift[128];
+  __shared__ __align__(16) uint8_t s_stage[4][4096];             // transpose tiles of the swapped epilogue
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int PX = p.swap ? 256 : 128;                             // pixels per tile (one image-row segment)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -372,7 +388,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
     tma_prefetch_desc(&mapB);
     mbar_init(&bar_w, 1);
     for (int s = 0; s < p.ring; ++s) { mbar_init(&row_full[s], 1); mbar_init(&row_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], p.swap ? 16 : 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 4); }
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(&tmem_base_smem, tmem_cols); tmem_relinquish(); }
@@ -424,7 +440,9 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
       const uint32_t swz = (p.BK == 64) ? SWZ_128B : SWZ_64B;
       const uint32_t pitch = p.BK * 2u, sbo = 8u * pitch;
       const int ksteps = p.BK / 16;
-      const uint32_t ring_base = smem_u32(s_ring), w_base = smem_u32(s_w);
+      const uint64_t dbase = make_smem_desc(0, 16, sbo, swz);
+      const uint32_t ring16 = smem_u32(s_ring) >> 4, w16 = smem_u32(s_w) >> 4, rowb16 = row_bytes >> 4;
+      const uint32_t slot16 = (uint32_t)p.slot_bytes >> 4, pitch16 = pitch >> 4, wblk16 = wblk_bytes >> 4;
       mbar_wait(&bar_w, 0);
       tc_fence_after();
       uint32_t cnt = 0;
@@ -442,17 +460,20 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
           uint32_t first = 1;
           for (int dy = 0; dy < 3; ++dy) {
-            const uint32_t row_addr = ring_base + ((c0 + t + dy) % p.ring) * row_bytes;
+            const uint32_t row16 = ring16 + ((c0 + t + dy) % p.ring) * rowb16;
             for (int kc = 0; kc < p.nkc; ++kc) {
+#pragma unroll
               for (int dx = 0; dx < 3; ++dx) {
-                const uint32_t a_addr = row_addr + kc * p.slot_bytes + dx * pitch;   // halo box starts at pixel w0-1
-                const uint32_t b_addr = w_base + ((dy * 3 + dx) * p.nkc + kc) * wblk_bytes;
-                for (int k = 0; k < ksteps; ++k) {
-                  const uint64_t dpx = make_smem_desc(a_addr + k * 32, 16, sbo, swz);   // pixels
-                  const uint64_t dwt = make_smem_desc(b_addr + k * 32, 16, sbo, swz);   // weights
-                  if (p.swap) umma_bf16(d_tmem, dwt, dpx, idesc, first ? 0u : 1u);
-                  else umma_bf16(d_tmem, dpx, dwt, idesc, first ? 0u : 1u);
-                  first = 0;
+                // halo box starts at pixel w0-1: tap dx reads the same rows shifted by dx pixels
+                const uint64_t dpx = dbase + (row16 + kc * slot16 + dx * pitch16);
+                const uint64_t dwt = dbase + (w16 + ((dy * 3 + dx) * p.nkc + kc) * wblk16);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (k < ksteps) {
+                    if (p.swap) umma_bf16(d_tmem, dwt + (uint64_t)(2 * k), dpx + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
+                    else umma_bf16(d_tmem, dpx + (uint64_t)(2 * k), dwt + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
+                    first = 0;
+                  }
                 }
               }
             }
@@ -468,10 +489,9 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
     }
   } else {
     const int quarter = warp & 3;
-    const int egroup = (warp - 2) >> 2;
     const int m = quarter * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < num_items && (p.swap || egroup == 0); item += gridDim.x) {
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       int n, h0, rows, w0;
       decode(item, n, h0, rows, w0);
       for (int t = 0; t < rows; ++t) {
@@ -482,8 +502,8 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
           auto pix_index = [&](int mm) -> long long { return (long long)(row0 + (size_t)mm * p.Cout); };
           mbar_wait(&bar_tfull[acc], acc_phase);
           tc_fence_after();
-          epilogue_swapped(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols), egroup * 64, 64,
-                           warp_valid, sc, sh, p.relu, p.out_f32, p.out, lane, pix_index);
+          epilogue_swapped(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols), 256, warp_valid, sc, sh,
+                           p.relu, p.out_f32, p.out, s_stage[quarter], lane, pix_index);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_tempty[acc]);
@@ -605,10 +625,22 @@ static int pick_pow2_box(int extent, int maxbox) {
   return best;
 }
 
+// swapped orientation policy: DCB_SWAP_MIN_COUT = smallest Cout for which the swapped orientation is used
+// (<= 128 always required); 0 disables.  Default chosen from per-layer measurements (profiles/).
+static int swap_min_cout() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DCB_SWAP_MIN_COUT");
+    v = e ? atoi(e) : 128;
+    if (getenv("DCB_NO_SWAP")) v = 0;
+  }
+  return v;
+}
+static bool swap_allowed(int Nout) { return swap_min_cout() > 0 && Nout >= swap_min_cout() && Nout <= 128; }
+
 // strip kernel plan; returns false when the layer is not eligible
 static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, TcStripParams& p, size_t& dyn_smem) {
   static const bool disabled = getenv("DCB_NO_STRIP") != nullptr;
-  static const bool no_swap = getenv("DCB_NO_SWAP") != nullptr;
   if (disabled) return false;
   if (g.ntaps != 9 || g.zsub > 1 || g.sy != 1) return false;
   if (g.GW % 128 != 0 || Nout > 128 || Nout % 32 != 0) return false;
@@ -618,7 +650,7 @@ static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, TcStripParams
   const size_t w_bytes = ((size_t)9 * K * Nout * 2 + 1023) & ~(size_t)1023;
   const size_t budget = 207 * 1024;
   // swapped orientation (256-pixel segments, N = 256 per MMA) whenever the image is wide enough
-  int swap = (!no_swap && g.GW % 256 == 0) ? 1 : 0;
+  int swap = (swap_allowed(Nout) && g.GW % 256 == 0) ? 1 : 0;
   int slot = 0, ring = 0;
   for (; swap >= 0; --swap) {
     const int px = swap ? 256 : 128;
@@ -702,9 +734,8 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
   // Swapped orientation for narrow outputs: with <= 128 output channels the normal orientation spends the
   // A-operand read time (128 pixel rows per MMA) on an N of 32..128; swapped, every MMA covers 256 pixels.
   {
-    static const bool no_swap = getenv("DCB_NO_SWAP") != nullptr;
     const long long px = (long long)g.N * g.GH * g.GW;
-    p.swap = (!no_swap && Nout <= 128 && px / 256 * cdiv(p.Ntot, 128) >= sm_count() / 2) ? 1 : 0;
+    p.swap = (swap_allowed(Nout) && px / 256 * cdiv(p.Ntot, 128) >= sm_count() / 2) ? 1 : 0;
   }
   const int TM = p.swap ? 256 : TC_BM;
   // ---- M tiling
@@ -799,7 +830,7 @@ struct TcWgradParams {
   float* part;              // [splits][ntaps][K][Nout]
 };
 
-__global__ void __launch_bounds__(WG_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 tapgemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                         const __grid_constant__ CUtensorMap mapG, const TcWgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -881,6 +912,7 @@ tapgemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
       const uint32_t idesc = make_idesc_bf16(128, p.BN, 1, 1);
       const uint32_t swz_a = (p.CB == 64) ? SWZ_128B : SWZ_64B, swz_g = (p.CBG == 64) ? SWZ_128B : SWZ_64B;
       const uint32_t sbo_a = 8u * p.CB * 2u, sbo_g = 8u * p.CBG * 2u;
+      const uint64_t dbase_a = make_smem_desc(0, a_blk_bytes, sbo_a, swz_a), dbase_g = make_smem_desc(0, g_blk_bytes, sbo_g, swz_g);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -899,8 +931,8 @@ tapgemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
 #pragma unroll
           for (int k = 0; k < WG_P / 16; ++k) {
             // 16 pixels = two 8-row groups further down the box
-            const uint64_t da = make_smem_desc(sa + k * 2 * sbo_a, a_blk_bytes, sbo_a, swz_a);
-            const uint64_t dg = make_smem_desc(sg + k * 2 * sbo_g, g_blk_bytes, sbo_g, swz_g);
+            const uint64_t da = dbase_a + ((sa + k * 2 * sbo_a) >> 4);
+            const uint64_t dg = dbase_g + ((sg + k * 2 * sbo_g) >> 4);
             umma_bf16(d_tmem, da, dg, idesc, (pt > pt0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&bar_empty[stage]);
@@ -1046,7 +1078,7 @@ int run_tc_wgrad(const TapGeom& g, const void* s0, int C0, const void* s1, int C
   const size_t dyn_smem = w.stages * stage_bytes + 1024;
   const int num_items = cdiv(K, 128) * (Nout / w.BN) * g.ntaps * w.splits;
   const int grid = num_items < sm_count() ? num_items : sm_count();
-  tapgemm_tc_wgrad_kernel<<<grid, WG_THREADS, dyn_smem, st>>>(mA0, mA1, mG, p);
+  tapgemm_tc_wgrad_kernel<<<grid, TC_THREADS, dyn_smem, st>>>(mA0, mA1, mG, p);
   DCB_LAUNCH_OK("tapgemm_tc_wgrad_kernel");
   launch_reduce_splits(p.part, w.splits, (size_t)g.ntaps * K * Nout, dW, st);
   g_launches += 2;
