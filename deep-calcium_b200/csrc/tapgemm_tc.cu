@@ -160,23 +160,24 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
         const int nt = tile % num_ntiles, mt = tile / num_ntiles;
         const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / kb_per_tap, kk = kb % kb_per_tap;
-          const bool second = kk >= kb0;
-          const int c0 = (second ? kk - kb0 : kk) * p.BK;
-          const CUtensorMap* mA = second ? &mapA1 : &mapA0;
-          mbar_wait(&bar_empty[stage], phase ^ 1);
-          uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          uint8_t* sb = sa + a_bytes;
-          // swapped: the weight box holds min(128, rows left) rows; the rest of the 128-row A tile is stale
-          // shared memory that only feeds accumulator lanes nobody reads
-          const int wrows = p.swap ? (p.Ntot - nt * 128 < 128 ? p.Ntot - nt * 128 : 128) : p.BN;
-          mbar_arrive_expect_tx(&bar_full[stage], a_bytes + (uint32_t)wrows * p.BK * 2);
-          if (p.mode == 0) tma_load_4d(mA, &bar_full[stage], sa, c0, w0 + p.dx[tap], h0 + p.dy[tap], n0);
-          else if (p.mode == 1) tma_load_3d(mA, &bar_full[stage], sa, c0, w0, h0);
-          else tma_load_5d(mA, &bar_full[stage], sa, c0, p.dx[tap], w0, p.dy[tap], h0);
-          tma_load_2d(&mapB, &bar_full[stage], sb, tap * Ktap + (second ? p.C0 : 0) + c0, nt * (p.swap ? 128 : p.BN));
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          for (int kk = 0; kk < kb_per_tap; ++kk) {
+            const bool second = kk >= kb0;
+            const int c0 = (second ? kk - kb0 : kk) * p.BK;
+            const CUtensorMap* mA = second ? &mapA1 : &mapA0;
+            mbar_wait(&bar_empty[stage], phase ^ 1);
+            uint8_t* sa = smem + (size_t)stage * stage_bytes;
+            uint8_t* sb = sa + a_bytes;
+            // swapped: the weight box holds min(128, rows left) rows; the rest of the 128-row A tile is stale
+            // shared memory that only feeds accumulator lanes nobody reads
+            const int wrows = p.swap ? (p.Ntot - nt * 128 < 128 ? p.Ntot - nt * 128 : 128) : p.BN;
+            mbar_arrive_expect_tx(&bar_full[stage], a_bytes + (uint32_t)wrows * p.BK * 2);
+            if (p.mode == 0) tma_load_4d(mA, &bar_full[stage], sa, c0, w0 + p.dx[tap], h0 + p.dy[tap], n0);
+            else if (p.mode == 1) tma_load_3d(mA, &bar_full[stage], sa, c0, w0, h0);
+            else tma_load_5d(mA, &bar_full[stage], sa, c0, p.dx[tap], w0, p.dy[tap], h0);
+            tma_load_2d(&mapB, &bar_full[stage], sb, tap * Ktap + (second ? p.C0 : 0) + c0, nt * (p.swap ? 128 : p.BN));
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -339,6 +340,34 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
 //     absolute smem address, so a row-shifted start address needs no base-offset correction
 //     (verified on B200: profiles/r1_umma_row_shift_probe.log);
 //   * the three vertical taps read three consecutive ring rows.
+// MMA issue of one strip tile: 9 taps x nkc channel chunks x KSTEPS MMAs.  Templated so that the single issuing
+// thread runs straight-line code (every extra dependent instruction between two tcgen05.mma shows up directly
+// in the tensor-pipe utilisation of these short-K tiles).  Weight tiles are laid out (tap, kc)-major, so the
+// weight descriptor simply advances by one tile per step.
+template <int KSTEPS, bool SWAP>
+__device__ __forceinline__ void strip_issue_tile(uint32_t d_tmem, uint64_t dbase, const uint32_t (&row16)[3], uint32_t w16,
+                                                 int nkc, uint32_t slot16, uint32_t pitch16, uint32_t wblk16, uint32_t idesc) {
+  uint64_t dwt = dbase + w16;
+  uint32_t accf = 0;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      uint64_t dpx = dbase + (row16[dy] + dx * pitch16);     // halo box starts at pixel w0-1: tap dx = rows shifted by dx
+      for (int kc = 0; kc < nkc; ++kc) {
+#pragma unroll
+        for (int k = 0; k < KSTEPS; ++k) {
+          if (SWAP) umma_bf16(d_tmem, dwt + (uint64_t)(2 * k), dpx + (uint64_t)(2 * k), idesc, accf);
+          else umma_bf16(d_tmem, dpx + (uint64_t)(2 * k), dwt + (uint64_t)(2 * k), idesc, accf);
+          accf = 1;
+        }
+        dpx += slot16;
+        dwt += wblk16;
+      }
+    }
+  }
+}
+
 constexpr int ST_MAX_RING = 12;
 
 struct TcStripParams {
@@ -410,27 +439,25 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
       for (int tap = 0; tap < 9; ++tap)
         for (int kc = 0; kc < p.nkc; ++kc)
           tma_load_2d(&mapB, &bar_w, s_w + (size_t)(tap * p.nkc + kc) * wblk_bytes, tap * K + kc * p.BK, 0);
-      uint32_t cnt = 0;                                          // halo rows issued so far
+      int pos = 0; uint32_t empty_parity = 0xffffffffu;          // bit i: parity to wait for on row_empty[i]
       const int kc0 = p.C0 / p.BK;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         int n, h0, rows, w0;
         decode(item, n, h0, rows, w0);
-        for (int rr = -1; rr <= rows; ++rr, ++cnt) {
-          const int pos = cnt % p.ring;
-          mbar_wait(&row_empty[pos], ((cnt / p.ring) & 1) ^ 1);
+        for (int rr = -1; rr <= rows; ++rr) {
+          mbar_wait(&row_empty[pos], (empty_parity >> pos) & 1u);
+          empty_parity ^= 1u << pos;
           mbar_arrive_expect_tx(&row_full[pos], p.nkc * box_bytes);
           uint8_t* dst = s_ring + (size_t)pos * row_bytes;
           for (int kc = 0; kc < p.nkc; ++kc) {
             const bool second = kc >= kc0;
             const int cc = (second ? kc - kc0 : kc) * p.BK;
-            if (!p.swap) {
-              tma_load_4d(second ? &mapA1 : &mapA0, &row_full[pos], dst + (size_t)kc * p.slot_bytes, cc, w0 - 1, h0 + rr, n);
-            } else {   // 258-pixel halo row = a 256-pixel box + a 2-pixel box (TMA boxes are limited to 256 per dim)
-              tma_load_4d(second ? &mapA1 : &mapA0, &row_full[pos], dst + (size_t)kc * p.slot_bytes, cc, w0 - 1, h0 + rr, n);
+            tma_load_4d(second ? &mapA1 : &mapA0, &row_full[pos], dst + (size_t)kc * p.slot_bytes, cc, w0 - 1, h0 + rr, n);
+            if (p.swap)   // 258-pixel halo row = a 256-pixel box + a 2-pixel box (TMA boxes are limited to 256 per dim)
               tma_load_4d(second ? &mapT1 : &mapT0, &row_full[pos], dst + (size_t)kc * p.slot_bytes + 256u * p.BK * 2u, cc,
                           w0 + 255, h0 + rr, n);
-            }
           }
+          if (++pos == p.ring) pos = 0;
         }
       }
     }
@@ -445,46 +472,39 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
       const uint32_t slot16 = (uint32_t)p.slot_bytes >> 4, pitch16 = pitch >> 4, wblk16 = wblk_bytes >> 4;
       mbar_wait(&bar_w, 0);
       tc_fence_after();
-      uint32_t cnt = 0;
+      int pos_next = 0; uint32_t full_parity = 0;                // bit i: parity to wait for on row_full[i]
+      auto wait_next_row = [&]() -> int {
+        const int ps = pos_next;
+        mbar_wait(&row_full[ps], (full_parity >> ps) & 1u);
+        full_parity ^= 1u << ps;
+        pos_next = (ps + 1 == p.ring) ? 0 : ps + 1;
+        return ps;
+      };
       int acc = 0; uint32_t acc_phase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         int n, h0, rows, w0;
         decode(item, n, h0, rows, w0);
-        const uint32_t c0 = cnt;
-        mbar_wait(&row_full[c0 % p.ring], (c0 / p.ring) & 1);
-        mbar_wait(&row_full[(c0 + 1) % p.ring], ((c0 + 1) / p.ring) & 1);
+        int p0 = wait_next_row(), p1 = wait_next_row();          // halo rows h0-1 and h0
         for (int t = 0; t < rows; ++t) {
-          mbar_wait(&row_full[(c0 + t + 2) % p.ring], ((c0 + t + 2) / p.ring) & 1);
+          const int p2 = wait_next_row();                         // halo row h0+t+1
           mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
-          uint32_t first = 1;
-          for (int dy = 0; dy < 3; ++dy) {
-            const uint32_t row16 = ring16 + ((c0 + t + dy) % p.ring) * rowb16;
-            for (int kc = 0; kc < p.nkc; ++kc) {
-#pragma unroll
-              for (int dx = 0; dx < 3; ++dx) {
-                // halo box starts at pixel w0-1: tap dx reads the same rows shifted by dx pixels
-                const uint64_t dpx = dbase + (row16 + kc * slot16 + dx * pitch16);
-                const uint64_t dwt = dbase + (w16 + ((dy * 3 + dx) * p.nkc + kc) * wblk16);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  if (k < ksteps) {
-                    if (p.swap) umma_bf16(d_tmem, dwt + (uint64_t)(2 * k), dpx + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
-                    else umma_bf16(d_tmem, dpx + (uint64_t)(2 * k), dwt + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
-                    first = 0;
-                  }
-                }
-              }
-            }
+          const uint32_t row16[3] = {ring16 + p0 * rowb16, ring16 + p1 * rowb16, ring16 + p2 * rowb16};
+          if (p.swap) {
+            if (ksteps == 4) strip_issue_tile<4, true>(d_tmem, dbase, row16, w16, p.nkc, slot16, pitch16, wblk16, idesc);
+            else strip_issue_tile<2, true>(d_tmem, dbase, row16, w16, p.nkc, slot16, pitch16, wblk16, idesc);
+          } else {
+            if (ksteps == 4) strip_issue_tile<4, false>(d_tmem, dbase, row16, w16, p.nkc, slot16, pitch16, wblk16, idesc);
+            else strip_issue_tile<2, false>(d_tmem, dbase, row16, w16, p.nkc, slot16, pitch16, wblk16, idesc);
           }
           umma_commit(&bar_tfull[acc]);
-          umma_commit(&row_empty[(c0 + t) % p.ring]);            // halo row t is not needed by later tiles
+          umma_commit(&row_empty[p0]);                            // halo row t is not needed by later tiles
+          p0 = p1; p1 = p2;
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        umma_commit(&row_empty[(c0 + rows) % p.ring]);
-        umma_commit(&row_empty[(c0 + rows + 1) % p.ring]);
-        cnt = c0 + rows + 2;
+        umma_commit(&row_empty[p0]);
+        umma_commit(&row_empty[p1]);
       }
     }
   } else {
