@@ -651,7 +651,7 @@ static int swap_min_cout() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("DCB_SWAP_MIN_COUT");
-    v = e ? atoi(e) : 128;
+    v = e ? atoi(e) : 64;
     if (getenv("DCB_NO_SWAP")) v = 0;
   }
   return v;
@@ -755,7 +755,8 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
   // A-operand read time (128 pixel rows per MMA) on an N of 32..128; swapped, every MMA covers 256 pixels.
   {
     const long long px = (long long)g.N * g.GH * g.GW;
-    p.swap = (swap_allowed(Nout) && px / 256 * cdiv(p.Ntot, 128) >= sm_count() / 2) ? 1 : 0;
+    // measured (profiles/r1_layer_ab.txt): pays for conv3x3 with 64..128 output channels, not for the 1-tap convT GEMMs
+    p.swap = (p.mode == 0 && swap_allowed(Nout) && px / 256 * cdiv(p.Ntot, 128) >= sm_count() / 2) ? 1 : 0;
   }
   const int TM = p.swap ? 256 : TC_BM;
   // ---- M tiling
