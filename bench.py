@@ -255,6 +255,14 @@ def run_ours(args):
                        'l2': 'per-step activation footprint ~1.2 GB >> 126 MB L2; 4 rotating inputs'},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches)}
 
+    # ---- multi-GPU extras (every rank takes part in the collectives)
+    dist_extra = {}
+    if world > 1:
+        for name, fn in (('tta_sharded', bench_tta_sharded), ('train_dp', bench_train_dp)):
+            try:
+                dist_extra[name] = fn(args, pk, eng, imgs, max_over_ranks, barrier)
+            except Exception as ex:   # noqa: BLE001
+                dist_extra[name] = {'error': repr(ex)}
     if rank == 0:
         # ---- roofline of the dominant kernel family (the conv tap-GEMMs), timed live with CUDA events
         try:
@@ -270,7 +278,7 @@ def run_ours(args):
         except Exception as ex:   # noqa: BLE001
             line['roofline'] = {'error': repr(ex)}
         # ---- extras: projection (C2) and training (C3)
-        line['extra'] = {}
+        line['extra'] = dict(dist_extra)
         for name, fn in (('projection', bench_projection), ('train', bench_train)):
             try:
                 line['extra'][name] = fn(args, pk)
@@ -293,6 +301,59 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_tta_sharded(args, pk, eng, imgs, max_over_ranks, barrier):
+    """BASELINE config C4: ONE 512x512 image, its 8 TTA transforms sharded over the ranks, probability maps
+    gathered to rank 0 (NCCL all_gather over NVLink), fixed-order combine -> latency per image."""
+    import torch
+    from deepcalcium.engine.dist import Comm, predict_tta_sharded
+    comm = Comm()
+    for i in range(4):
+        predict_tta_sharded(eng, imgs[0], comm)
+    barrier()
+    n = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        predict_tta_sharded(eng, imgs[i % len(imgs)], comm)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / n
+    return {'ms_per_image': ms, 'images_per_s': 1e3 / ms, 'ranks': comm.world,
+            'note': 'strong scaling of one image: transforms k -> rank, all_gather of 1 MiB probability maps'}
+
+
+def bench_train_dp(args, pk, eng_unused, imgs, max_over_ranks, barrier):
+    """BASELINE config C5: data-parallel training, 32 crops of 128x128 per GPU, SyncBN + loss sums + gradient
+    all-reduce (31 MB fp32) over NCCL."""
+    import torch
+    from deepcalcium.engine.graph import GraphSpec, he_normal_weights
+    from deepcalcium.engine.unet_engine import UNetEngine
+    from deepcalcium.engine.dist import Comm, sync_parameters
+    comm = Comm()
+    spec = GraphSpec(32)
+    eng = UNetEngine(spec, precision=args.precision, use_graphs=False)   # NCCL calls are issued eagerly
+    eng.set_weights_dict(he_normal_weights(spec, seed=7535))
+    eng.comm = comm
+    sync_parameters(eng, comm)
+    rng = np.random.default_rng(865 + comm.rank)
+    B = 32
+    x = torch.from_numpy(rng.standard_normal((B, 128, 128)).astype(np.float32)).cuda()
+    y = torch.from_numpy((rng.random((B, 128, 128)) < 0.126).astype(np.uint8)).cuda()
+    for i in range(3):
+        eng.train_step(x, y, loss='dice_loss', lr=0.002, dropout=True)
+    barrier()
+    n = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        eng.train_step(x, y, loss='dice_loss', lr=0.002, dropout=True)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / n
+    return {'crops_per_s': comm.world * B * 1e3 / ms, 'ms_per_step': ms, 'global_batch': comm.world * B, 'ranks': comm.world,
+            'note': 'eager launch (no CUDA graph) because of the interleaved NCCL collectives'}
 
 
 def bench_projection(args, pk):
