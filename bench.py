@@ -235,7 +235,7 @@ def run_ours(args):
     host_imgs = {('img%d' % i): imgs[i].cpu().numpy() for i in range(n_img)}
     model = UNetModel.__new__(UNetModel)
     model.window_shape, model.spec, model.engine = (512, 512), spec, eng
-    api = UNet2DSummary(cpdir='/tmp/deep-calcium-bench-cp', dataset_name_func=lambda p: p,
+    api = UNet2DSummary(cpdir='/tmp/deep-calcium-bench-cp-%d' % rank, dataset_name_func=lambda p: p,
                         series_summary_func=lambda p: host_imgs[p])
     paths = [('img%d' % (i % n_img)) for i in range(args.steps)]
     api.predict(paths[:3], model, augmentation=True)

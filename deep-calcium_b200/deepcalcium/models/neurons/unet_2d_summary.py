@@ -210,8 +210,7 @@ class UNet2DSummary(object):
         self.series_summary_func = series_summary_func
         self.mask_summary_func = mask_summary_func
         self.net_builder_func = net_builder_func
-        if not path.exists(self.cpdir):
-            os.makedirs(self.cpdir)
+        os.makedirs(self.cpdir, exist_ok=True)
         cobj = [F1, prec, reca, dice, dicesq, posyt, posyp, dice_loss, dicesq_loss]
         self.custom_objects = {x.__name__: x for x in cobj}
 
