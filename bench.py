@@ -122,7 +122,7 @@ def per_layer_profile(eng, sess, spec, NB, H, W):
     from deepcalcium.engine import ops
     rows = []
     orig = {}
-    names = ['conv3x3_fwd', 'convT2x2_fwd', 'conv3x3_c1_fwd', 'maxpool2x2', 'head_fwd']
+    names = ['conv3x3_fwd', 'conv3x3_fwd_fused', 'convT2x2_fwd', 'conv3x3_c1_fwd', 'maxpool2x2', 'head_fwd']
     events = []
 
     def wrap(name):
@@ -151,11 +151,11 @@ def per_layer_profile(eng, sess, spec, NB, H, W):
     for name, a, e0, e1 in events:
         ms = e0.elapsed_time(e1)
         fl = 0.0
-        if name == 'conv3x3_fwd':
+        if name in ('conv3x3_fwd', 'conv3x3_fwd_fused'):
             src0, src1, wgt, out = a[0], a[1], a[2], a[3]
             cin = src0.shape[3] + (src1.shape[3] if src1 is not None else 0)
             fl = 2.0 * out.shape[0] * out.shape[1] * out.shape[2] * 9 * cin * out.shape[3]
-            tag = 'conv3x3 %dx%d %d->%d' % (out.shape[1], out.shape[2], cin, out.shape[3])
+            tag = 'conv3x3%s %dx%d %d->%d' % ('+fused' if name.endswith('fused') else '', out.shape[1], out.shape[2], cin, out.shape[3])
         elif name == 'convT2x2_fwd':
             src, out = a[0], a[2]
             fl = 2.0 * src.shape[0] * src.shape[1] * src.shape[2] * 4 * src.shape[3] * out.shape[3]
@@ -271,7 +271,7 @@ def run_ours(args):
             ach = tot_f / tot_ms / 1e9
             line['roofline'] = {'bound': 'tensor', 'achieved': ach, 'peak': pk['tf'], 'unit': 'TFLOP/s',
                                 'frac': ach / pk['tf'], 'traffic': None, 'peak_source': pk['src'],
-                                'kernel': 'tap-GEMM conv3x3/convT2x2 (all 22 launches of one 8-image forward)',
+                                'kernel': 'tcgen05 tap-GEMM conv3x3/convT2x2 (the 21 tensor-core launches of one 8-image forward)',
                                 'flops_per_step': tot_f, 'conv_ms_per_step': tot_ms,
                                 'whole_step_frac': (8 * spec.flops_forward(512, 512) / (ms / args.steps) / 1e9) / pk['tf_sus']}
             line['per_layer'] = rows

@@ -17,8 +17,11 @@ int run_f32_wgrad(const TapGeom& g, const float* s0, int C0, const float* s1, in
                   float* dW, void* ws, size_t ws_bytes, cudaStream_t st);
 
 // tcgen05 path (tapgemm_tc.cu)
+struct TcFusion {
+  const float* head_kernel; const float* head_bias; float* logit; float* prob; int need_y; void* pool_out;
+};
 int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* B, int Nout, void* out,
-               const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st);
+               const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st, const TcFusion* fuse = nullptr);
 int run_tc_wgrad(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* G, int Nout, float* dW,
                  void* ws, size_t ws_bytes, cudaStream_t st);
 size_t tc_wgrad_workspace(const TapGeom& g, int K, int Nout);
@@ -109,6 +112,29 @@ extern "C" int dcb_conv3x3_fwd(int dtype, const void* src0, int C0, const void* 
   if (dtype == DCB_BF16)
     return run_tc_fwd(g, src0, C0, src1, C1, wgt, Cout, out, scale, shift, relu, 0, (cudaStream_t)stream);
   return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+}
+
+extern "C" int dcb_conv3x3_fwd_fused(int dtype, const void* src0, int C0, const void* src1, int C1, int N, int H, int W,
+                                     const void* wgt, int Cout, const float* scale, const float* shift, int relu, void* out,
+                                     const dcb_conv_fusion_t* fuse, dcb_stream_t stream) {
+  DCB_CHECK_ARG(src0 && wgt && out && fuse, "dcb_conv3x3_fwd_fused: null pointer");
+  DCB_CHECK_ARG(N > 0 && H > 0 && W > 0 && C0 > 0 && C1 >= 0 && Cout > 0 && (C1 == 0 || src1), "dcb_conv3x3_fwd_fused: bad shape");
+  DCB_CHECK_ARG(!fuse->head_kernel || (fuse->head_bias && (fuse->logit || fuse->prob)), "dcb_conv3x3_fwd_fused: incomplete head arguments");
+  DCB_CHECK_ARG(!fuse->pool_out || (H % 2 == 0 && W % 2 == 0), "dcb_conv3x3_fwd_fused: pooling needs even H and W");
+  if (dtype == DCB_BF16) {
+    TapGeom g;
+    geom_conv3x3(g, N, H, W);
+    TcFusion f = {fuse->head_kernel, fuse->head_bias, fuse->logit, fuse->prob, fuse->need_y, fuse->pool_out};
+    const int rc = run_tc_fwd(g, src0, C0, src1, C1, wgt, Cout, out, scale, shift, relu, 0, (cudaStream_t)stream, &f);
+    if (rc != DCB_ERR_UNSUPPORTED) return rc;
+  }
+  // unfused composition (fp32 check mode, or a shape the fused epilogue does not cover)
+  if (int e = dcb_conv3x3_fwd(dtype, src0, C0, src1, C1, N, H, W, wgt, Cout, scale, shift, relu, out, stream)) return e;
+  if (fuse->pool_out)
+    if (int e = dcb_maxpool2x2(dtype, out, N, H, W, Cout, fuse->pool_out, stream)) return e;
+  if (fuse->head_kernel)
+    if (int e = dcb_head_fwd(dtype, out, (long long)N * H * W, Cout, fuse->head_kernel, fuse->head_bias, fuse->logit, fuse->prob, stream)) return e;
+  return DCB_OK;
 }
 
 extern "C" int dcb_conv3x3_dgrad(int dtype, const void* dy, int Cout, int N, int H, int W, const void* wgt_dgrad, int Cin,

@@ -29,6 +29,11 @@ constexpr int TC_BM = 128;          // pixels per tile (= UMMA M, one TMEM lane 
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_THREADS = 192;
 
+// optional epilogue fusions requested through dcb_conv3x3_fwd_fused (mirrors dcb_conv_fusion_t)
+struct TcFusion {
+  const float* head_kernel; const float* head_bias; float* logit; float* prob; int need_y; void* pool_out;
+};
+
 struct TcFwdParams {
   int mode;                 // 0: 4-D halo box (conv3x3)  1: 3-D merged rows (convT fwd)  2: 5-D strided (convT dgrad)
   int N, GH, GW;            // iteration grid
@@ -377,6 +382,12 @@ struct TcStripParams {
   int R, ring, wsegs, hchunks;
   int slot_bytes;           // (PX + 2) * BK * 2 rounded up to 1024
   int swap;                 // 1: 256-pixel segments, weights as the MMA A operand (see TcFwdParams::swap)
+  // optional epilogue fusions (normal orientation only)
+  const float* head_kernel; // [Cout][2] softmax head (unet_2d_summary.py:221-222): emit logit / prob per pixel
+  const float* head_bias;   // [2]
+  float* logit; float* prob;
+  int need_y;               // 0: the activation itself is not stored (head fused, nobody else reads it)
+  __nv_bfloat16* pool_out;  // 2x2 max-pooled copy [N][H/2][W/2][Cout] (unet_2d_summary.py:176-194) or null
   int relu, out_f32;
   __nv_bfloat16* out;
   const float* scale;
@@ -390,7 +401,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t bar_w, row_full[ST_MAX_RING], row_empty[ST_MAX_RING], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_scale[128], s_shift[128];
+  __shared__ float s_scale[128], s_shift[128], s_wd[128];
   __shared__ __align__(16) uint8_t s_stage[4][4096];             // transpose tiles of the swapped epilogue
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int PX = p.swap ? 256 : 128;                             // pixels per tile (one image-row segment)
@@ -410,6 +421,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
     s_scale[i] = p.scale ? p.scale[i] : 1.f;
     s_shift[i] = p.shift ? p.shift[i] : 0.f;
+    s_wd[i] = p.head_kernel ? p.head_kernel[2 * i + 1] - p.head_kernel[2 * i] : 0.f;
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
@@ -510,6 +522,9 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   } else {
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
+    uint32_t pool_prev[2][16];                                   // previous row (bf16 pairs) for the fused 2x2 max-pool
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { pool_prev[0][q] = 0; pool_prev[1][q] = 0; }
     int acc = 0; uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       int n, h0, rows, w0;
@@ -530,13 +545,18 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
           continue;
         }
-        const size_t oidx = (((size_t)n * p.H + (h0 + t)) * p.W + (w0 + m)) * p.Cout;
+        const size_t opix = ((size_t)n * p.H + (h0 + t)) * p.W + (w0 + m);
+        const size_t oidx = opix * p.Cout;
         __nv_bfloat16* orow = p.out + oidx;
         float* orow_f = reinterpret_cast<float*>(p.out) + oidx;
         mbar_wait(&bar_tfull[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.Cout);
-        for (int c = 0; c < p.Cout; c += 32) {
+        float zacc = p.head_kernel ? (p.head_bias[1] - p.head_bias[0]) : 0.f;
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+          const int c = cb * 32;
+          if (c >= p.Cout) break;
           uint32_t r[32];
           tmem_ld_32x32b_x32(t_addr + c, r);
           tmem_ld_wait();
@@ -552,21 +572,56 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
               *reinterpret_cast<float4*>(orow_f + c + j) = make_float4(v[0], v[1], v[2], v[3]);
             }
           } else {
+            uint32_t pk[16];
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint32_t pk[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const int ch = c + j + 2 * q;
-                float v0 = fmaf(__uint_as_float(r[j + 2 * q]), s_scale[ch], s_shift[ch]);
-                float v1 = fmaf(__uint_as_float(r[j + 2 * q + 1]), s_scale[ch + 1], s_shift[ch + 1]);
-                if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-                __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
-                pk[q] = *reinterpret_cast<uint32_t*>(&b2);
+            for (int q = 0; q < 16; ++q) {
+              const int ch = c + 2 * q;
+              float v0 = fmaf(__uint_as_float(r[2 * q]), s_scale[ch], s_shift[ch]);
+              float v1 = fmaf(__uint_as_float(r[2 * q + 1]), s_scale[ch + 1], s_shift[ch + 1]);
+              if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+              pk[q] = *reinterpret_cast<uint32_t*>(&b2);
+              if (p.head_kernel) {          // same operand values and order as head_fwd_kernel on the stored bf16 tensor
+                const float2 f = __bfloat1622float2(b2);
+                zacc = fmaf(f.x, s_wd[ch], zacc);
+                zacc = fmaf(f.y, s_wd[ch + 1], zacc);
               }
-              *reinterpret_cast<uint4*>(orow + c + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            if (p.need_y) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(orow + c + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            }
+            if (p.pool_out && cb < 2) {
+              // 2x2 max-pool: vertical partner = the previous tile of this warp (row h0+t-1, kept in registers),
+              // horizontal partner = the neighbouring lane.  R and H are even, so pairs never straddle work items.
+              if ((t & 1) == 0) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) pool_prev[cb][q] = pk[q];
+              } else {
+                uint32_t mx[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                  __nv_bfloat162 a2 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&pk[q]),
+                                              *reinterpret_cast<__nv_bfloat162*>(&pool_prev[cb][q]));
+                  uint32_t au = *reinterpret_cast<uint32_t*>(&a2);
+                  uint32_t bu = __shfl_xor_sync(0xffffffffu, au, 1);
+                  __nv_bfloat162 m2 = __hmax2(a2, *reinterpret_cast<__nv_bfloat162*>(&bu));
+                  mx[q] = *reinterpret_cast<uint32_t*>(&m2);
+                }
+                if ((lane & 1) == 0) {
+                  __nv_bfloat16* prow = p.pool_out + ((((size_t)n * (p.H >> 1) + ((h0 + t) >> 1)) * (p.W >> 1) + ((w0 + m) >> 1)) * p.Cout + c);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(prow + 8 * j) = make_uint4(mx[4 * j], mx[4 * j + 1], mx[4 * j + 2], mx[4 * j + 3]);
+                }
+              }
             }
           }
+        }
+        if (p.head_kernel) {
+          if (p.logit) p.logit[opix] = zacc;
+          if (p.prob) p.prob[opix] = 1.f / (1.f + __expf(-zacc));
         }
         tc_fence_before();
         __syncwarp();
@@ -659,7 +714,7 @@ static int swap_min_cout() {
 static bool swap_allowed(int Nout) { return swap_min_cout() > 0 && Nout >= swap_min_cout() && Nout <= 128; }
 
 // strip kernel plan; returns false when the layer is not eligible
-static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, TcStripParams& p, size_t& dyn_smem) {
+static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, bool fused, TcStripParams& p, size_t& dyn_smem) {
   static const bool disabled = getenv("DCB_NO_STRIP") != nullptr;
   if (disabled) return false;
   if (g.ntaps != 9 || g.zsub > 1 || g.sy != 1) return false;
@@ -670,7 +725,8 @@ static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, TcStripParams
   const size_t w_bytes = ((size_t)9 * K * Nout * 2 + 1023) & ~(size_t)1023;
   const size_t budget = 207 * 1024;
   // swapped orientation (256-pixel segments, N = 256 per MMA) whenever the image is wide enough
-  int swap = (swap_allowed(Nout) && g.GW % 256 == 0) ? 1 : 0;
+  // the fused head / pool epilogues exist for the normal orientation only
+  int swap = (!fused && swap_allowed(Nout) && g.GW % 256 == 0) ? 1 : 0;
   int slot = 0, ring = 0;
   for (; swap >= 0; --swap) {
     const int px = swap ? 256 : 128;
@@ -685,13 +741,16 @@ static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, TcStripParams
   p.ring = ring; p.slot_bytes = slot; p.swap = swap; p.wsegs = g.GW / (swap ? 256 : 128);
   int R = 32;
   while (R > 8 && (long long)g.N * cdiv(g.GH, R) * p.wsegs < 4LL * sm_count()) R >>= 1;
+  if (fused && (g.GH % 2 != 0)) return false;          // row pairs of the fused pool must not straddle items
   p.R = R; p.hchunks = cdiv(g.GH, R);
   dyn_smem = w_bytes + (size_t)ring * nkc * slot + 1024;
   return true;
 }
 
+// fuse != nullptr: the caller wants the head and/or the 2x2 max-pool computed in the conv epilogue; returns
+// DCB_ERR_UNSUPPORTED (without launching) when this layer shape cannot take the fused path.
 int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* B, int Nout, void* out,
-               const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st) {
+               const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st, const TcFusion* fuse) {
   if (C0 % 32 != 0 || C1 % 32 != 0 || Nout % 32 != 0)
     return fail(DCB_ERR_UNSUPPORTED, "bf16 tensor-core path needs channel counts that are multiples of 32 "
                 "(got C0=%d C1=%d Cout=%d); use the fp32 check mode for other widths", C0, C1, Nout);
@@ -699,8 +758,17 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
   {
     TcStripParams sp;
     size_t dyn = 0;
-    if (plan_strip(g, C0, C1, Nout, sp, dyn)) {
+    const bool fused = fuse != nullptr;
+    if (fused && (out_f32 || (fuse->pool_out && Nout > 64))) return fail(DCB_ERR_UNSUPPORTED, "fused epilogue not available for this layer");
+    const bool strip_ok = plan_strip(g, C0, C1, Nout, fused, sp, dyn);
+    if (fused && !strip_ok) return fail(DCB_ERR_UNSUPPORTED, "fused epilogue not available for this layer");
+    if (strip_ok) {
       sp.relu = relu; sp.out_f32 = out_f32; sp.out = reinterpret_cast<__nv_bfloat16*>(out); sp.scale = scale; sp.shift = shift;
+      sp.need_y = 1;
+      if (fused) {
+        sp.head_kernel = fuse->head_kernel; sp.head_bias = fuse->head_bias; sp.logit = fuse->logit; sp.prob = fuse->prob;
+        sp.need_y = fuse->need_y; sp.pool_out = reinterpret_cast<__nv_bfloat16*>(fuse->pool_out);
+      }
       CUtensorMap mA0, mA1, mT0, mT1, mB;
       auto mk = [&](CUtensorMap* m, const void* ptr, int C, uint32_t boxw) -> int {
         uint64_t dims[4] = {(uint64_t)C, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.N};

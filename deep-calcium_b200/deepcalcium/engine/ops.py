@@ -57,6 +57,21 @@ def conv3x3_fwd(src0, src1, wgt, out, scale=None, shift=None, relu=False):
          ptr(wgt), c_int(Cout), ptr(scale), ptr(shift), c_int(int(relu)), ptr(out), stream_ptr())
 
 
+class ConvFusion(ctypes.Structure):
+    _fields_ = [('head_kernel', c_p), ('head_bias', c_p), ('logit', c_p), ('prob', c_p), ('need_y', c_int),
+                ('pool_out', c_p)]
+
+
+def conv3x3_fwd_fused(src0, src1, wgt, out, scale=None, shift=None, relu=False, head_kernel=None, head_bias=None,
+                      logit=None, prob=None, need_y=True, pool_out=None):
+    """conv3x3 with the following max-pool and/or the softmax head folded into its epilogue."""
+    N, H, W, C0 = src0.shape
+    C1 = 0 if src1 is None else src1.shape[3]
+    f = ConvFusion(ptr(head_kernel), ptr(head_bias), ptr(logit), ptr(prob), int(bool(need_y)), ptr(pool_out))
+    call('dcb_conv3x3_fwd_fused', _dt(src0), ptr(src0), c_int(C0), ptr(src1), c_int(C1), c_int(N), c_int(H), c_int(W),
+         ptr(wgt), c_int(out.shape[3]), ptr(scale), ptr(shift), c_int(int(relu)), ptr(out), ctypes.byref(f), stream_ptr())
+
+
 def conv3x3_dgrad(dy, wgt_dgrad, dx):
     """dy: [N,H,W,Cout] activation dtype (gradient w.r.t. the raw conv output); dx: fp32 [N,H,W,Cin]."""
     N, H, W, Cout = dy.shape

@@ -222,24 +222,31 @@ class UNetEngine(object):
 
     # ------------------------------------------------------------------ inference
     def _forward_inference(self, s):
-        """enqueue the forward pass reading s['x'] (fp32 [NB,H,W]); writes s['logit'], s['prob']."""
+        """enqueue the forward pass reading s['x'] (fp32 [NB,H,W]); writes s['logit'], s['prob'].
+        The max-pool after each encoder block and the softmax head are folded into the producing conv's
+        epilogue (dcb_conv3x3_fwd_fused) - the library falls back to the separate kernels where the fused
+        epilogue does not apply."""
         act = s['act']
         for blk in self.spec.blocks:
             n = blk.name
             if blk.kind == 'head':
-                ops.head_fwd(act['dec0b'], self.P['head/kernel'], self.P['head/bias'], s['logit'], s['prob'])
-                continue
+                continue                                  # fused into dec0b below
             a, b = self._inputs[n]
             sc, sh = self.inf_scale[n], self.inf_shift[n]
             if blk.kind == 'conv':
                 if blk.cin == 1 and self.dtype == torch.bfloat16:
                     ops.conv3x3_c1_fwd(s['x'], self.w_fwd[n], act[n], sc, sh, True)
+                elif n == 'dec0b':
+                    ops.conv3x3_fwd_fused(act[a], None, self.w_fwd[n], act[n], sc, sh, True,
+                                          head_kernel=self.P['head/kernel'], head_bias=self.P['head/bias'],
+                                          logit=s['logit'], prob=s['prob'], need_y=False)
+                elif n in ('enc0b', 'enc1b', 'enc2b', 'enc3b'):
+                    ops.conv3x3_fwd_fused(act[a], None, self.w_fwd[n], act[n], sc, sh, True,
+                                          pool_out=act['pool%d' % blk.level])
                 else:
                     ops.conv3x3_fwd(act[a], act[b] if b else None, self.w_fwd[n], act[n], sc, sh, True)
             else:
                 ops.convT2x2_fwd(act[a], self.w_fwd[n], act[n], sc, sh, True)
-            if n in ('enc0b', 'enc1b', 'enc2b', 'enc3b'):
-                ops.maxpool2x2(act[n], act['pool%d' % blk.level])
 
     def _ensure_inference_ready(self):
         if self._weights_dirty:

@@ -80,6 +80,22 @@ int dcb_standardize_f32(const float* in, long long n, float* out, double* stats,
 int dcb_conv3x3_fwd(int dtype, const void* src0, int C0, const void* src1, int C1, int N, int H, int W,
                     const void* wgt, int Cout, const float* scale, const float* shift, int relu,
                     void* out, dcb_stream_t stream);
+/* conv3x3 + epilogue with the next memory-bound op(s) of the graph folded in, so their input is not re-read
+ * (and, for the head, never written): the 2x2/2 max-pool that follows an encoder block
+ * (unet_2d_summary.py:176,182,188,194) and/or the 1x1 softmax head (:221-222).  `out` must always be a valid
+ * [N][H][W][Cout] buffer; with need_y = 0 the library may leave it untouched.  Shapes the fused tensor-core
+ * epilogue does not cover (and the fp32 check mode) run the unfused composition with identical results. */
+typedef struct dcb_conv_fusion {
+  const float* head_kernel; /* [Cout][2] or NULL */
+  const float* head_bias;   /* [2] */
+  float* logit;             /* [N*H*W] z1 - z0, may be NULL */
+  float* prob;              /* [N*H*W] softmax(z)[1], may be NULL */
+  int need_y;               /* 0: the caller never reads `out` */
+  void* pool_out;           /* [N][H/2][W/2][Cout] or NULL */
+} dcb_conv_fusion_t;
+int dcb_conv3x3_fwd_fused(int dtype, const void* src0, int C0, const void* src1, int C1, int N, int H, int W,
+                          const void* wgt, int Cout, const float* scale, const float* shift, int relu,
+                          void* out, const dcb_conv_fusion_t* fuse, dcb_stream_t stream);
 /* input h x w -> output 2h x 2w */
 int dcb_convT2x2_fwd(int dtype, const void* src, int Cin, int N, int h, int w, const void* wgt, int Cout,
                      const float* scale, const float* shift, int relu, void* out, dcb_stream_t stream);

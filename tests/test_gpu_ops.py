@@ -130,6 +130,36 @@ def test_convT2x2_fwd_dgrad_wgrad(cuda, precision, case):
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('shape', [(2, 16, 128, 32, 32), (1, 6, 256, 64, 64), (1, 8, 24, 32, 32)])
+def test_conv3x3_fused_pool_and_head_equal_the_unfused_composition(cuda, precision, shape):
+    """dcb_conv3x3_fwd_fused (max-pool / softmax head folded into the conv epilogue) must reproduce the separate
+    kernels exactly - including shapes where the library falls back to the unfused composition."""
+    from deepcalcium.engine import ops
+    N, H, W, Cin, Cout = shape
+    dt = DT[precision]
+    rng = np.random.default_rng(5)
+    x = dev(rng.standard_normal((N, H, W, Cin)), dt)
+    w = dev(rng.standard_normal((3, 3, Cin, Cout)) * np.sqrt(2. / (9 * Cin)))
+    wf = torch.empty(9 * Cin * Cout, dtype=dt, device='cuda')
+    ops.prep_conv3x3_weights(w, wf, None, dt)
+    scale = dev(rng.uniform(0.5, 1.5, Cout)); shift = dev(rng.standard_normal(Cout))
+    hk = dev(rng.standard_normal((Cout, 2)) * 0.3); hb = dev(np.array([0.1, -0.2]))
+    y = torch.empty(N, H, W, Cout, dtype=dt, device='cuda')
+    ops.conv3x3_fwd(x, None, wf, y, scale, shift, True)
+    pool = torch.empty(N, H // 2, W // 2, Cout, dtype=dt, device='cuda')
+    ops.maxpool2x2(y, pool)
+    logit = torch.empty(N, H, W, device='cuda'); prob = torch.empty(N, H, W, device='cuda')
+    ops.head_fwd(y, hk, hb, logit, prob)
+    y2 = torch.empty_like(y); pool2 = torch.empty_like(pool)
+    ops.conv3x3_fwd_fused(x, None, wf, y2, scale, shift, True, pool_out=pool2)
+    assert torch.equal(y2, y) and torch.equal(pool2, pool)
+    y3 = torch.full_like(y, 7.0); logit3 = torch.empty_like(logit); prob3 = torch.empty_like(prob)
+    ops.conv3x3_fwd_fused(x, None, wf, y3, scale, shift, True, head_kernel=hk, head_bias=hb, logit=logit3, prob=prob3,
+                          need_y=False)
+    assert torch.allclose(logit3, logit, atol=1e-5, rtol=1e-5) and torch.allclose(prob3, prob, atol=1e-6)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 def test_conv3x3_first_layer_c1(cuda, precision):
     from deepcalcium.engine import ops
     dt = DT[precision]
