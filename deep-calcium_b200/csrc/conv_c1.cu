@@ -8,46 +8,39 @@ namespace dcb {
 extern unsigned long long g_launches;
 void launch_reduce_splits(const float* part, int splits, size_t n, float* out, cudaStream_t st);
 
-// COUT/8 threads per pixel, each holding the 9 x 8 weights of its 8 output channels in registers (no shared
-// memory traffic in the inner loop); a warp writes 32/(COUT/8) pixels x COUT channels = one contiguous run.
 template <typename T, int COUT>
 __global__ void __launch_bounds__(256)
 conv3x3_c1_fwd_kernel(const float* __restrict__ x, int N, int H, int W, const float* __restrict__ w,
                       const float* __restrict__ scale, const float* __restrict__ shift, int relu, T* __restrict__ out) {
-  constexpr int TPP = COUT / 8;                       // threads per pixel
-  const int cg = (threadIdx.x % TPP) * 8;             // first of my 8 channels
-  float wr[9][8], sc[8], sh[8];
-#pragma unroll
-  for (int t = 0; t < 9; ++t)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) wr[t][j] = w[t * COUT + cg + j];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { sc[j] = scale ? scale[cg + j] : 1.f; sh[j] = shift ? shift[cg + j] : 0.f; }
+  __shared__ float ws[9 * COUT];
+  __shared__ float sc[COUT], sh[COUT];
+  for (int i = threadIdx.x; i < 9 * COUT; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) { sc[i] = scale ? scale[i] : 1.f; sh[i] = shift ? shift[i] : 0.f; }
+  __syncthreads();
   const long long M = (long long)N * H * W;
-  const long long stride = (long long)gridDim.x * (blockDim.x / TPP);
-  for (long long m = (long long)blockIdx.x * (blockDim.x / TPP) + threadIdx.x / TPP; m < M; m += stride) {
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
     const int wq = (int)(m % W), hq = (int)((m / W) % H);
     const float* img = x + (m - (long long)hq * W - wq);
     float v[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int ih = hq + t / 3 - 1, iw = wq + t % 3 - 1;
-      v[t] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(img + (long long)ih * W + iw) : 0.f;
+      v[t] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? img[(long long)ih * W + iw] : 0.f;
     }
-    float a[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = 0.f;
+    for (int c0 = 0; c0 < COUT; c0 += 4) {
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
+      for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) a[j] = fmaf(v[t], wr[t][j], a[j]);
+        for (int j = 0; j < 4; ++j) a[j] = fmaf(v[t], ws[t * COUT + c0 + j], a[j]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      a[j] = fmaf(a[j], sc[j], sh[j]);
-      if (relu) a[j] = fmaxf(a[j], 0.f);
+      for (int j = 0; j < 4; ++j) {
+        a[j] = fmaf(a[j], sc[c0 + j], sh[c0 + j]);
+        if (relu) a[j] = fmaxf(a[j], 0.f);
+      }
+      store4<T>(out + m * COUT + c0, make_float4(a[0], a[1], a[2], a[3]));
     }
-    store4<T>(out + m * COUT + cg, make_float4(a[0], a[1], a[2], a[3]));
-    store4<T>(out + m * COUT + cg + 4, make_float4(a[4], a[5], a[6], a[7]));
   }
 }
 
@@ -98,8 +91,8 @@ template <typename T>
 static int launch_c1_fwd(const float* x, int N, int H, int W, const float* w, int Cout, const float* scale,
                          const float* shift, int relu, T* out, cudaStream_t st) {
   const long long M = (long long)N * H * W;
-  long long grid = (M * (Cout / 8) + 255) / 256;
-  if (grid > (long long)sm_count() * 8) grid = (long long)sm_count() * 8;
+  long long grid = (M + 255) / 256;
+  if (grid > (long long)sm_count() * 16) grid = (long long)sm_count() * 16;
   switch (Cout) {
     case 8: conv3x3_c1_fwd_kernel<T, 8><<<(int)grid, 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break;
     case 16: conv3x3_c1_fwd_kernel<T, 16><<<(int)grid, 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break;

@@ -394,6 +394,7 @@ struct TcStripParams {
   const float* shift;
 };
 
+template <bool FUSED>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                         const __grid_constant__ CUtensorMap mapT0, const __grid_constant__ CUtensorMap mapT1,
@@ -545,83 +546,124 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
           continue;
         }
-        const size_t opix = ((size_t)n * p.H + (h0 + t)) * p.W + (w0 + m);
-        const size_t oidx = opix * p.Cout;
-        __nv_bfloat16* orow = p.out + oidx;
-        float* orow_f = reinterpret_cast<float*>(p.out) + oidx;
-        mbar_wait(&bar_tfull[acc], acc_phase);
-        tc_fence_after();
-        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.Cout);
-        float zacc = p.head_kernel ? (p.head_bias[1] - p.head_bias[0]) : 0.f;
-#pragma unroll
-        for (int cb = 0; cb < 4; ++cb) {
-          const int c = cb * 32;
-          if (c >= p.Cout) break;
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(t_addr + c, r);
-          tmem_ld_wait();
-          if (p.out_f32) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float v[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                v[q] = fmaf(__uint_as_float(r[j + q]), s_scale[c + j + q], s_shift[c + j + q]);
-                if (p.relu) v[q] = fmaxf(v[q], 0.f);
-              }
-              *reinterpret_cast<float4*>(orow_f + c + j) = make_float4(v[0], v[1], v[2], v[3]);
-            }
-          } else {
-            uint32_t pk[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-              const int ch = c + 2 * q;
-              float v0 = fmaf(__uint_as_float(r[2 * q]), s_scale[ch], s_shift[ch]);
-              float v1 = fmaf(__uint_as_float(r[2 * q + 1]), s_scale[ch + 1], s_shift[ch + 1]);
-              if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-              __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
-              pk[q] = *reinterpret_cast<uint32_t*>(&b2);
-              if (p.head_kernel) {          // same operand values and order as head_fwd_kernel on the stored bf16 tensor
-                const float2 f = __bfloat1622float2(b2);
-                zacc = fmaf(f.x, s_wd[ch], zacc);
-                zacc = fmaf(f.y, s_wd[ch + 1], zacc);
-              }
-            }
-            if (p.need_y) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<uint4*>(orow + c + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-            }
-            if (p.pool_out && cb < 2) {
-              // 2x2 max-pool: vertical partner = the previous tile of this warp (row h0+t-1, kept in registers),
-              // horizontal partner = the neighbouring lane.  R and H are even, so pairs never straddle work items.
-              if ((t & 1) == 0) {
-#pragma unroll
-                for (int q = 0; q < 16; ++q) pool_prev[cb][q] = pk[q];
-              } else {
-                uint32_t mx[16];
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                  __nv_bfloat162 a2 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&pk[q]),
-                                              *reinterpret_cast<__nv_bfloat162*>(&pool_prev[cb][q]));
-                  uint32_t au = *reinterpret_cast<uint32_t*>(&a2);
-                  uint32_t bu = __shfl_xor_sync(0xffffffffu, au, 1);
-                  __nv_bfloat162 m2 = __hmax2(a2, *reinterpret_cast<__nv_bfloat162*>(&bu));
-                  mx[q] = *reinterpret_cast<uint32_t*>(&m2);
+        if constexpr (!FUSED) {
+          const size_t oidx = (((size_t)n * p.H + (h0 + t)) * p.W + (w0 + m)) * p.Cout;
+          __nv_bfloat16* orow = p.out + oidx;
+          float* orow_f = reinterpret_cast<float*>(p.out) + oidx;
+          mbar_wait(&bar_tfull[acc], acc_phase);
+          tc_fence_after();
+          const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.Cout);
+          for (int c = 0; c < p.Cout; c += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_addr + c, r);
+            tmem_ld_wait();
+            if (p.out_f32) {
+  #pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float v[4];
+  #pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  v[q] = fmaf(__uint_as_float(r[j + q]), s_scale[c + j + q], s_shift[c + j + q]);
+                  if (p.relu) v[q] = fmaxf(v[q], 0.f);
                 }
-                if ((lane & 1) == 0) {
-                  __nv_bfloat16* prow = p.pool_out + ((((size_t)n * (p.H >> 1) + ((h0 + t) >> 1)) * (p.W >> 1) + ((w0 + m) >> 1)) * p.Cout + c);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<uint4*>(prow + 8 * j) = make_uint4(mx[4 * j], mx[4 * j + 1], mx[4 * j + 2], mx[4 * j + 3]);
+                *reinterpret_cast<float4*>(orow_f + c + j) = make_float4(v[0], v[1], v[2], v[3]);
+              }
+            } else {
+  #pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint32_t pk[4];
+  #pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const int ch = c + j + 2 * q;
+                  float v0 = fmaf(__uint_as_float(r[j + 2 * q]), s_scale[ch], s_shift[ch]);
+                  float v1 = fmaf(__uint_as_float(r[j + 2 * q + 1]), s_scale[ch + 1], s_shift[ch + 1]);
+                  if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                  __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+                  pk[q] = *reinterpret_cast<uint32_t*>(&b2);
+                }
+                *reinterpret_cast<uint4*>(orow + c + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+          }
+        } else {
+          const size_t opix = ((size_t)n * p.H + (h0 + t)) * p.W + (w0 + m);
+          const size_t oidx = opix * p.Cout;
+          __nv_bfloat16* orow = p.out + oidx;
+          float* orow_f = reinterpret_cast<float*>(p.out) + oidx;
+          mbar_wait(&bar_tfull[acc], acc_phase);
+          tc_fence_after();
+          const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.Cout);
+          float zacc = p.head_kernel ? (p.head_bias[1] - p.head_bias[0]) : 0.f;
+  #pragma unroll
+          for (int cb = 0; cb < 4; ++cb) {
+            const int c = cb * 32;
+            if (c >= p.Cout) break;
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_addr + c, r);
+            tmem_ld_wait();
+            if (p.out_f32) {
+  #pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float v[4];
+  #pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  v[q] = fmaf(__uint_as_float(r[j + q]), s_scale[c + j + q], s_shift[c + j + q]);
+                  if (p.relu) v[q] = fmaxf(v[q], 0.f);
+                }
+                *reinterpret_cast<float4*>(orow_f + c + j) = make_float4(v[0], v[1], v[2], v[3]);
+              }
+            } else {
+              uint32_t pk[16];
+  #pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const int ch = c + 2 * q;
+                float v0 = fmaf(__uint_as_float(r[2 * q]), s_scale[ch], s_shift[ch]);
+                float v1 = fmaf(__uint_as_float(r[2 * q + 1]), s_scale[ch + 1], s_shift[ch + 1]);
+                if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+                pk[q] = *reinterpret_cast<uint32_t*>(&b2);
+                if (p.head_kernel) {          // same operand values and order as head_fwd_kernel on the stored bf16 tensor
+                  const float2 f = __bfloat1622float2(b2);
+                  zacc = fmaf(f.x, s_wd[ch], zacc);
+                  zacc = fmaf(f.y, s_wd[ch + 1], zacc);
+                }
+              }
+              if (p.need_y) {
+  #pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  *reinterpret_cast<uint4*>(orow + c + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              }
+              if (p.pool_out && cb < 2) {
+                // 2x2 max-pool: vertical partner = the previous tile of this warp (row h0+t-1, kept in registers),
+                // horizontal partner = the neighbouring lane.  R and H are even, so pairs never straddle work items.
+                if ((t & 1) == 0) {
+  #pragma unroll
+                  for (int q = 0; q < 16; ++q) pool_prev[cb][q] = pk[q];
+                } else {
+                  uint32_t mx[16];
+  #pragma unroll
+                  for (int q = 0; q < 16; ++q) {
+                    __nv_bfloat162 a2 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&pk[q]),
+                                                *reinterpret_cast<__nv_bfloat162*>(&pool_prev[cb][q]));
+                    uint32_t au = *reinterpret_cast<uint32_t*>(&a2);
+                    uint32_t bu = __shfl_xor_sync(0xffffffffu, au, 1);
+                    __nv_bfloat162 m2 = __hmax2(a2, *reinterpret_cast<__nv_bfloat162*>(&bu));
+                    mx[q] = *reinterpret_cast<uint32_t*>(&m2);
+                  }
+                  if ((lane & 1) == 0) {
+                    __nv_bfloat16* prow = p.pool_out + ((((size_t)n * (p.H >> 1) + ((h0 + t) >> 1)) * (p.W >> 1) + ((w0 + m) >> 1)) * p.Cout + c);
+  #pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                      *reinterpret_cast<uint4*>(prow + 8 * j) = make_uint4(mx[4 * j], mx[4 * j + 1], mx[4 * j + 2], mx[4 * j + 3]);
+                  }
                 }
               }
             }
           }
-        }
-        if (p.head_kernel) {
-          if (p.logit) p.logit[opix] = zacc;
-          if (p.prob) p.prob[opix] = 1.f / (1.f + __expf(-zacc));
+          if (p.head_kernel) {
+            if (p.logit) p.logit[opix] = zacc;
+            if (p.prob) p.prob[opix] = 1.f / (1.f + __expf(-zacc));
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -790,13 +832,15 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
       }
       static bool attr_set_strip = false;
       if (!attr_set_strip) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
         if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
         attr_set_strip = true;
       }
       const int items = sp.N * sp.hchunks * sp.wsegs;
       const int grid = items < sm_count() ? items : sm_count();
-      tapgemm_tc_strip_kernel<<<grid, TC_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
+      if (fused) tapgemm_tc_strip_kernel<true><<<grid, TC_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
+      else tapgemm_tc_strip_kernel<false><<<grid, TC_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
       g_launches += 1;
       DCB_LAUNCH_OK("tapgemm_tc_strip_kernel");
       return DCB_OK;

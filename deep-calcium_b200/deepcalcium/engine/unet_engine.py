@@ -240,11 +240,13 @@ class UNetEngine(object):
                     ops.conv3x3_fwd_fused(act[a], None, self.w_fwd[n], act[n], sc, sh, True,
                                           head_kernel=self.P['head/kernel'], head_bias=self.P['head/bias'],
                                           logit=s['logit'], prob=s['prob'], need_y=False)
-                elif n in ('enc0b', 'enc1b', 'enc2b', 'enc3b'):
-                    ops.conv3x3_fwd_fused(act[a], None, self.w_fwd[n], act[n], sc, sh, True,
-                                          pool_out=act['pool%d' % blk.level])
+                elif n == 'enc0b':
+                    # measured: folding the pool pays at full resolution only (profiles/r1_layer_ab.txt)
+                    ops.conv3x3_fwd_fused(act[a], None, self.w_fwd[n], act[n], sc, sh, True, pool_out=act['pool0'])
                 else:
                     ops.conv3x3_fwd(act[a], act[b] if b else None, self.w_fwd[n], act[n], sc, sh, True)
+                    if n in ('enc1b', 'enc2b', 'enc3b'):
+                        ops.maxpool2x2(act[n], act['pool%d' % blk.level])
             else:
                 ops.convT2x2_fwd(act[a], self.w_fwd[n], act[n], sc, sh, True)
 
