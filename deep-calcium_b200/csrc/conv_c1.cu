@@ -44,40 +44,56 @@ conv3x3_c1_fwd_kernel(const float* __restrict__ x, int N, int H, int W, const fl
   }
 }
 
-// dW[t][co] = sum_pixels x[pixel + tap t] * dy[pixel][co]: lane = output channel (COUT <= 32 per pass),
-// a warp walks pixels; per-CTA partials then a fixed-order reduce.
+// dW[t][co] = sum_pixels x[pixel + tap t] * dy[pixel][co].  A warp takes 4 consecutive pixels per step:
+// lane l reads 4 channels ((l & 7) * 4 ..) of pixel (l >> 3) - one contiguous 256-byte (bf16) row of dy per
+// warp load - and keeps 9 taps x 4 channels of partial sums.  Per-CTA partials, then a fixed-order reduce.
 template <typename T>
 __global__ void __launch_bounds__(256)
 conv3x3_c1_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, int N, int H, int W, int Cout,
                         float* __restrict__ part) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int psub = lane >> 3, c4 = (lane & 7) * 4;
   const long long M = (long long)N * H * W;
-  const long long per_cta = (M + gridDim.x - 1) / gridDim.x;
+  const long long per_cta = ((M + gridDim.x - 1) / gridDim.x + 3) & ~3LL;
   const long long m0 = (long long)blockIdx.x * per_cta;
   long long m1 = m0 + per_cta; if (m1 > M) m1 = M;
   __shared__ float red[8][9][32];
   for (int cbase = 0; cbase < Cout; cbase += 32) {
-    float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    const int c = cbase + lane;
-    for (long long m = m0 + warp; m < m1; m += 8) {
-      const int wq = (int)(m % W), hq = (int)((m / W) % H);
-      const float* img = x + (m - (long long)hq * W - wq);
-      const float g = (c < Cout) ? to_f32<T>(dy[m * Cout + c]) : 0.f;
+    float acc[9][4];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int ih = hq + t / 3 - 1, iw = wq + t % 3 - 1;
-        const float v = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? img[(long long)ih * W + iw] : 0.f;
-        acc[t] = fmaf(v, g, acc[t]);
+    for (int t = 0; t < 9; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
+    const bool cvalid = cbase + c4 < Cout;
+    for (long long mb = m0 + warp * 4; mb < m1; mb += 32) {
+      const long long m = mb + psub;
+      if (m < m1 && cvalid) {
+        const int wq = (int)(m % W), hq = (int)((m / W) % H);
+        const float* img = x + (m - (long long)hq * W - wq);
+        const float4 g = load4<T>(dy + m * Cout + cbase + c4);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int ih = hq + t / 3 - 1, iw = wq + t % 3 - 1;
+          const float v = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(img + (long long)ih * W + iw) : 0.f;
+          acc[t][0] = fmaf(v, g.x, acc[t][0]); acc[t][1] = fmaf(v, g.y, acc[t][1]);
+          acc[t][2] = fmaf(v, g.z, acc[t][2]); acc[t][3] = fmaf(v, g.w, acc[t][3]);
+        }
       }
     }
+    // combine the 4 pixel sub-groups of the warp, then the 8 warps
 #pragma unroll
-    for (int t = 0; t < 9; ++t) red[warp][t][lane] = acc[t];
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = acc[t][j];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (psub == 0) red[warp][t][c4 + j] = v;
+      }
     __syncthreads();
     for (int i = threadIdx.x; i < 9 * 32; i += blockDim.x) {
       const int t = i / 32, l = i % 32;
-      float s = 0.f;
-      for (int wv = 0; wv < 8; ++wv) s += red[wv][t][l];
-      if (cbase + l < Cout) part[((size_t)blockIdx.x * 9 + t) * Cout + cbase + l] = s;
+      float sacc = 0.f;
+      for (int wv = 0; wv < 8; ++wv) sacc += red[wv][t][l];
+      if (cbase + l < Cout) part[((size_t)blockIdx.x * 9 + t) * Cout + cbase + l] = sacc;
     }
     __syncthreads();
   }
@@ -114,7 +130,7 @@ extern "C" int dcb_conv3x3_c1_fwd(int dtype, const float* x, int N, int H, int W
   return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
 }
 
-static int c1_wgrad_ctas() { return sm_count() * 4; }
+static int c1_wgrad_ctas() { return sm_count() * 8; }
 
 extern "C" int dcb_conv3x3_c1_wgrad_workspace_bytes(int Cout, size_t* bytes) {
   DCB_CHECK_ARG(bytes && Cout > 0, "dcb_conv3x3_c1_wgrad_workspace_bytes: bad arguments");

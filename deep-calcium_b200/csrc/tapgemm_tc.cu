@@ -276,16 +276,21 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
         valid = gw < p.GW && r < p.N * p.GH;
       }
       const int ng0 = nt * p.BN;                     // first GEMM column of this tile
-      const int z = ng0 / p.Cz, cbase = ng0 % p.Cz;  // sub-position (convT fwd) and channel base
-      const int ody = p.Cz < p.Ntot ? (z >> 1) : p.ody, odx = p.Cz < p.Ntot ? (z & 1) : p.odx;
-      const size_t oidx = (((size_t)n * p.OH + (gh * p.osy + ody)) * p.OW + (gw * p.osx + odx)) * p.OC + cbase;
-      __nv_bfloat16* orow = p.out + oidx;
-      float* orow_f = reinterpret_cast<float*>(p.out) + oidx;
+      // pixel part of the output index; the sub-position (convT fwd) depends on the 32-column block
+      const size_t orow_y = (size_t)n * p.OH + gh * p.osy;
+      const int ocol_x = gw * p.osx;
 
       mbar_wait(&bar_tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN);
       for (int c = 0; c < p.BN; c += 32) {
+        // a 32-column block never straddles a sub-position because Cz % 32 == 0
+        const int gcol = ng0 + c;
+        const int z = gcol / p.Cz, cbase = gcol % p.Cz - c;   // cbase + c = channel of the block's first column
+        const int ody = p.Cz < p.Ntot ? (z >> 1) : p.ody, odx = p.Cz < p.Ntot ? (z & 1) : p.odx;
+        const size_t oidx = ((orow_y + ody) * p.OW + (ocol_x + odx)) * p.OC + cbase;
+        __nv_bfloat16* orow = p.out + oidx;
+        float* orow_f = reinterpret_cast<float*>(p.out) + oidx;
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_addr + c, r);
         tmem_ld_wait();
@@ -884,9 +889,10 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
   }
   const int num_mtiles = p.tiles_w * p.tiles_h * p.tiles_n;
   // ---- N tiling: largest tile that still gives every SM work
-  int BN = p.Cz < 256 ? p.Cz : 256;
-  while (BN > 64 && (long long)num_mtiles * (p.Ntot / BN) < sm_count() && p.Cz % (BN / 2) == 0) BN /= 2;
-  if (p.Cz % BN != 0) BN = 32;
+  // an N tile may span several convT sub-positions (the epilogue resolves them per 32-column block)
+  int BN = p.Ntot < 256 ? p.Ntot : 256;
+  while (BN > 64 && (long long)num_mtiles * (p.Ntot / BN) < sm_count() && BN % 64 == 0) BN /= 2;
+  if (p.Ntot % BN != 0) BN = 32;
   if (p.swap) BN = p.Ntot < 128 ? p.Ntot : 128;       // rows of the weight TMA box
   p.BN = BN;
   const size_t stage_bytes = (size_t)TM * p.BK * 2 + (size_t)(p.swap ? 128 : BN) * p.BK * 2;
@@ -1115,6 +1121,163 @@ tapgemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
+// ====================================================================================== wgrad strip kernel
+// Weight gradient of the full-resolution 32-channel layers (enc0b, dec0a, dec0b: 3 of the 18 conv layers but
+// two thirds of the generic wgrad time, because a 32-channel operand fills a quarter of the 128-row MMA and
+// every tap re-loaded both operands).  Here:
+//   * activation halo rows [66 px x 32 ch] stream through a ring exactly like the forward strip kernel;
+//   * ONE MMA covers the three horizontal taps: the A operand is MN-major, its four 32-channel column blocks
+//     are declared LBO = one pixel (64 B) apart, i.e. blocks 0..2 are the same halo row shifted by dx = 0..2
+//     pixels (block 3 only feeds accumulator lanes 96..127, which are never read);
+//   * the accumulators D[(dx, cin) x cout] for the 3 vertical taps (x sources) live in TMEM for the whole life
+//     of the persistent CTA; each CTA writes a single partial at the end (fixed-order reduce afterwards).
+constexpr int WS_PX = 64;             // pixels per step (4 MMA K-steps of 16)
+constexpr int WS_RING = 8;            // halo rows in flight
+constexpr int WS_GRING = 6;           // gradient rows in flight
+
+struct TcWgradStripParams {
+  int N, H, W;
+  int nsrc;                 // 1 or 2 sources of 32 channels each
+  int Nout;                 // 32 (64 B rows, SWIZZLE_64B) or 64 (128 B rows, SWIZZLE_128B)
+  int R, wsegs, hchunks;
+  float* part;              // [gridDim.x][9][32 * nsrc][Nout]
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+tapgemm_tc_wgrad_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                              const __grid_constant__ CUtensorMap mapG, const TcWgradStripParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t row_full[WS_RING], row_empty[WS_RING], g_full[WS_GRING], g_empty[WS_GRING], bar_done;
+  __shared__ uint32_t tmem_base_smem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr uint32_t A_SLOT = 5120;                       // 66 (+ spill) rows x 64 B, 1024-aligned
+  const uint32_t row_bytes = (uint32_t)p.nsrc * A_SLOT;
+  const uint32_t g_slot = (uint32_t)WS_PX * p.Nout * 2;   // 4 KB or 8 KB
+  uint8_t* s_ring = smem;
+  uint8_t* s_g = smem + (size_t)WS_RING * row_bytes;
+  const int num_items = p.N * p.hchunks * p.wsegs;
+  const int nacc = 3 * p.nsrc;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(nacc * p.Nout)) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA0);
+    if (p.nsrc > 1) tma_prefetch_desc(&mapA1);
+    tma_prefetch_desc(&mapG);
+    for (int i = 0; i < WS_RING; ++i) { mbar_init(&row_full[i], 1); mbar_init(&row_empty[i], 1); }
+    for (int i = 0; i < WS_GRING; ++i) { mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], 1); }
+    mbar_init(&bar_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(&tmem_base_smem, tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  auto decode = [&](int item, int& n, int& h0, int& rows, int& w0) {
+    const int ws = item % p.wsegs; item /= p.wsegs;
+    const int hc = item % p.hchunks; n = item / p.hchunks;
+    h0 = hc * p.R; rows = p.H - h0 < p.R ? p.H - h0 : p.R; w0 = ws * WS_PX;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int pos = 0, gpos = 0; uint32_t ep = 0xffffffffu, gp = 0xffffffffu;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int n, h0, rows, w0;
+        decode(item, n, h0, rows, w0);
+        for (int rr = -1; rr <= rows; ++rr) {
+          mbar_wait(&row_empty[pos], (ep >> pos) & 1u); ep ^= 1u << pos;
+          mbar_arrive_expect_tx(&row_full[pos], (uint32_t)p.nsrc * 66u * 64u);
+          for (int sidx = 0; sidx < p.nsrc; ++sidx)
+            tma_load_4d(sidx ? &mapA1 : &mapA0, &row_full[pos], s_ring + (size_t)pos * row_bytes + sidx * A_SLOT, 0, w0 - 1, h0 + rr, n);
+          if (++pos == WS_RING) pos = 0;
+          if (rr >= 0 && rr < rows) {
+            mbar_wait(&g_empty[gpos], (gp >> gpos) & 1u); gp ^= 1u << gpos;
+            mbar_arrive_expect_tx(&g_full[gpos], g_slot);
+            tma_load_4d(&mapG, &g_full[gpos], s_g + (size_t)gpos * g_slot, 0, w0, h0 + rr, n);
+            if (++gpos == WS_GRING) gpos = 0;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // A: MN-major, 64 B rows (SWIZZLE_64B); column blocks (32 channels) one pixel apart -> LBO = 64 B; 8-pixel groups SBO = 512 B
+      const uint64_t dbase_a = make_smem_desc(0, 64, 512, SWZ_64B);
+      const uint32_t g_pitch = (uint32_t)p.Nout * 2;
+      const uint64_t dbase_g = make_smem_desc(0, g_slot, 8 * g_pitch, p.Nout == 64 ? SWZ_128B : SWZ_64B);
+      const uint32_t idesc = make_idesc_bf16(128, p.Nout, 1, 1);
+      const uint32_t ring16 = smem_u32(s_ring) >> 4, g16 = smem_u32(s_g) >> 4;
+      const uint32_t rowb16 = row_bytes >> 4, gslot16 = g_slot >> 4;
+      int pos_next = 0, gpos = 0; uint32_t fp = 0, gfp = 0;
+      auto wait_next_row = [&]() -> int {
+        const int ps = pos_next;
+        mbar_wait(&row_full[ps], (fp >> ps) & 1u); fp ^= 1u << ps;
+        pos_next = (ps + 1 == WS_RING) ? 0 : ps + 1;
+        return ps;
+      };
+      uint32_t accf = 0;                                       // first MMA of every accumulator overwrites
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int n, h0, rows, w0;
+        decode(item, n, h0, rows, w0);
+        int p0 = wait_next_row(), p1 = wait_next_row();
+        for (int t = 0; t < rows; ++t) {
+          const int p2 = wait_next_row();
+          mbar_wait(&g_full[gpos], (gfp >> gpos) & 1u); gfp ^= 1u << gpos;
+          tc_fence_after();
+          const uint32_t rows16[3] = {ring16 + p0 * rowb16, ring16 + p1 * rowb16, ring16 + p2 * rowb16};
+          const uint64_t dg0 = dbase_g + (g16 + gpos * gslot16);
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            for (int sidx = 0; sidx < p.nsrc; ++sidx) {
+              const uint32_t d_tmem = tmem_base + (uint32_t)((dy * p.nsrc + sidx) * p.Nout);
+              const uint64_t da0 = dbase_a + (rows16[dy] + sidx * (A_SLOT >> 4));
+#pragma unroll
+              for (int k = 0; k < WS_PX / 16; ++k)            // 16 pixels further down: 16 rows of 64 B / of g_pitch
+                umma_bf16(d_tmem, da0 + (uint64_t)(k * 64), dg0 + (uint64_t)(k * g_pitch), idesc, (accf | (uint32_t)k) ? 1u : 0u);
+            }
+          }
+          accf = 1;
+          umma_commit(&g_empty[gpos]);
+          umma_commit(&row_empty[p0]);
+          if (++gpos == WS_GRING) gpos = 0;
+          p0 = p1; p1 = p2;
+        }
+        umma_commit(&row_empty[p0]);
+        umma_commit(&row_empty[p1]);
+      }
+      umma_commit(&bar_done);
+    }
+  } else {
+    // one dump of the accumulators at the very end: lane = dx * 32 + cin
+    const int quarter = warp & 3;
+    mbar_wait(&bar_done, 0);
+    tc_fence_after();
+    const bool has_work = blockIdx.x < num_items;
+    const int K = 32 * p.nsrc;
+    for (int a = 0; a < nacc; ++a) {
+      const int dy = a / p.nsrc, sidx = a % p.nsrc;
+      for (int c = 0; c < p.Nout; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.Nout + c), r);
+        tmem_ld_wait();
+        if (quarter < 3) {
+          float* dst = p.part + (((size_t)blockIdx.x * 9 + (dy * 3 + quarter)) * K + sidx * 32 + lane) * p.Nout + c;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(dst + j) = has_work ? make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]) : make_uint4(0, 0, 0, 0);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
 void launch_reduce_splits(const float* part, int splits, size_t n, float* out, cudaStream_t st);
 
 struct WgradPlan { int BN, splits, CB, CBG, bw, bh, bn, tiles_w, tiles_h, tiles_n, stages; size_t ws_bytes; };
@@ -1151,9 +1314,65 @@ static WgradPlan plan_wgrad(const TapGeom& g, int K, int C0, int C1, int Nout) {
   return w;
 }
 
+static bool wgrad_strip_ok(const TapGeom& g, int C0, int C1, int Nout) {
+  static const bool disabled = getenv("DCB_NO_WGRAD_STRIP") != nullptr;
+  return !disabled && g.ntaps == 9 && g.sy == 1 && C0 == 32 && (C1 == 0 || C1 == 32) && (Nout == 32 || Nout == 64) &&
+         g.GW % WS_PX == 0;
+}
+
 size_t tc_wgrad_workspace(const TapGeom& g, int K, int Nout) {
   // C0/C1 split does not change the split count; use a conservative plan
-  return plan_wgrad(g, K, K, 0, Nout).ws_bytes;
+  size_t ws = plan_wgrad(g, K, K, 0, Nout).ws_bytes;
+  if ((K == 32 || K == 64) && wgrad_strip_ok(g, 32, K - 32, Nout)) {
+    const size_t strip = (size_t)sm_count() * 9 * K * Nout * sizeof(float);
+    if (strip > ws) ws = strip;
+  }
+  return ws;
+}
+
+static int run_tc_wgrad_strip(const TapGeom& g, const void* s0, const void* s1, int nsrc, const void* G, int Nout, float* dW,
+                              void* ws, size_t ws_bytes, cudaStream_t st) {
+  TcWgradStripParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = g.N; p.H = g.GH; p.W = g.GW; p.nsrc = nsrc; p.Nout = Nout;
+  p.wsegs = g.GW / WS_PX;
+  int R = 32;
+  while (R > 8 && (long long)g.N * cdiv(g.GH, R) * p.wsegs < 3LL * sm_count()) R >>= 1;
+  p.R = R; p.hchunks = cdiv(g.GH, R);
+  const int items = p.N * p.hchunks * p.wsegs;
+  const int grid = items < sm_count() ? items : sm_count();
+  const int K = 32 * nsrc;
+  const size_t need = (size_t)grid * 9 * K * Nout * sizeof(float);
+  if (!ws || ws_bytes < need) return fail(DCB_ERR_WORKSPACE, "wgrad (bf16 strip): workspace %zu B < required %zu B", ws_bytes, need);
+  p.part = reinterpret_cast<float*>(ws);
+  CUtensorMap mA0, mA1, mG;
+  auto mk = [&](CUtensorMap* m, const void* ptr) -> int {
+    uint64_t dims[4] = {32, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.N};
+    uint64_t str[3] = {64, (uint64_t)g.IW * 64, (uint64_t)g.IH * g.IW * 64};
+    uint32_t box[4] = {32, 66, 1, 1};
+    return make_map(m, ptr, 4, dims, str, box, 64);
+  };
+  if (int e = mk(&mA0, s0)) return e;
+  if (nsrc > 1) { if (int e = mk(&mA1, s1)) return e; } else mA1 = mA0;
+  {
+    uint64_t dims[4] = {(uint64_t)Nout, (uint64_t)g.GW, (uint64_t)g.GH, (uint64_t)g.N};
+    uint64_t str[3] = {(uint64_t)Nout * 2, (uint64_t)g.GW * Nout * 2, (uint64_t)g.GH * g.GW * Nout * 2};
+    uint32_t box[4] = {(uint32_t)Nout, (uint32_t)WS_PX, 1, 1};
+    if (int e = make_map(&mG, G, 4, dims, str, box, Nout * 2)) return e;
+  }
+  const size_t dyn = (size_t)WS_RING * nsrc * 5120 + (size_t)WS_GRING * WS_PX * Nout * 2 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_wgrad_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  tapgemm_tc_wgrad_strip_kernel<<<grid, WG_THREADS, dyn, st>>>(mA0, mA1, mG, p);
+  DCB_LAUNCH_OK("tapgemm_tc_wgrad_strip_kernel");
+  launch_reduce_splits(p.part, grid, (size_t)9 * K * Nout, dW, st);
+  g_launches += 2;
+  DCB_LAUNCH_OK("reduce_splits_kernel");
+  return DCB_OK;
 }
 
 int run_tc_wgrad(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* G, int Nout, float* dW,
@@ -1162,6 +1381,7 @@ int run_tc_wgrad(const TapGeom& g, const void* s0, int C0, const void* s1, int C
     return fail(DCB_ERR_UNSUPPORTED, "bf16 tensor-core wgrad needs channel counts that are multiples of 32 "
                 "(got C0=%d C1=%d N=%d)", C0, C1, Nout);
   const int K = C0 + C1;
+  if (wgrad_strip_ok(g, C0, C1, Nout)) return run_tc_wgrad_strip(g, s0, s1, C1 > 0 ? 2 : 1, G, Nout, dW, ws, ws_bytes, st);
   const WgradPlan w = plan_wgrad(g, K, C0, C1, Nout);
   if (!ws || ws_bytes < w.ws_bytes) return fail(DCB_ERR_WORKSPACE, "wgrad (bf16): workspace %zu B < required %zu B", ws_bytes, w.ws_bytes);
   const bool convT = (g.sy == 2);

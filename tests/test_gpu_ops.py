@@ -48,6 +48,8 @@ CONV_CASES = [
     (1, 1, 128, 32, 0, 64),
     (3, 37, 128, 64, 0, 32),
     (1, 9, 512, 32, 32, 32),
+    (2, 11, 64, 32, 0, 64),
+    (4, 128, 128, 32, 32, 32),
     # enough 256-pixel tiles for the swapped (weights-as-A) orientation of the generic kernel
     (8, 64, 64, 64, 0, 128),
     (5, 48, 80, 64, 64, 64),
