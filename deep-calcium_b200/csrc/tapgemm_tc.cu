@@ -28,6 +28,7 @@ using namespace tc;
 constexpr int TC_BM = 128;          // pixels per tile (= UMMA M, one TMEM lane per pixel)
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_THREADS = 192;
+constexpr int WG_THREADS = 192;
 
 // optional epilogue fusions requested through dcb_conv3x3_fwd_fused (mirrors dcb_conv_fusion_t)
 struct TcFusion {
