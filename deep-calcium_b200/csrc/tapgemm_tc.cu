@@ -28,6 +28,7 @@ using namespace tc;
 constexpr int TC_BM = 128;          // pixels per tile (= UMMA M, one TMEM lane per pixel)
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_THREADS = 192;
+constexpr int ST_THREADS = 64 + 8 * 32;   // strip kernel: TMA warp, MMA warp, two epilogue quartets
 constexpr int WG_THREADS = 192;
 
 // optional epilogue fusions requested through dcb_conv3x3_fwd_fused (mirrors dcb_conv_fusion_t)
@@ -401,12 +402,12 @@ struct TcStripParams {
 };
 
 template <bool FUSED>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(ST_THREADS, 1)
 tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                         const __grid_constant__ CUtensorMap mapT0, const __grid_constant__ CUtensorMap mapT1,
                         const __grid_constant__ CUtensorMap mapB, const TcStripParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t bar_w, row_full[ST_MAX_RING], row_empty[ST_MAX_RING], bar_tfull[2], bar_tempty[2];
+  __shared__ uint64_t bar_w, row_full[ST_MAX_RING], row_empty[ST_MAX_RING], bar_tfull[4], bar_tempty[4];
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_scale[128], s_shift[128], s_wd[128];
   __shared__ __align__(16) uint8_t s_stage[4][4096];             // transpose tiles of the swapped epilogue
@@ -422,8 +423,12 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   const uint32_t box_bytes = (uint32_t)(PX + 2) * p.BK * 2u;
   const int num_items = p.N * p.hchunks * p.wsegs;
   const int acc_cols = p.swap ? 256 : p.Cout;
+  // Normal orientation: draining a [128 px x Cout] accumulator (TMEM load latency + convert + stores) takes a warp
+  // quartet ~2x longer than the tensor pipe needs to fill it (measured, profiles/r1_strip_scaling.txt), so TWO
+  // quartets drain alternate tile pairs and FOUR accumulator stages keep the pipe busy.  Swapped: 2 x 256 columns.
+  const int nacc = p.swap ? 2 : 4, nacc_sh = p.swap ? 1 : 2, nsets = p.swap ? 1 : 2;
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2u * acc_cols) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(nacc * acc_cols)) tmem_cols <<= 1;
 
   for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
     s_scale[i] = p.scale ? p.scale[i] : 1.f;
@@ -436,7 +441,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
     tma_prefetch_desc(&mapB);
     mbar_init(&bar_w, 1);
     for (int s = 0; s < p.ring; ++s) { mbar_init(&row_full[s], 1); mbar_init(&row_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 4); }
+    for (int s = 0; s < nacc; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 4); }
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(&tmem_base_smem, tmem_cols); tmem_relinquish(); }
@@ -499,13 +504,15 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
         pos_next = (ps + 1 == p.ring) ? 0 : ps + 1;
         return ps;
       };
-      int acc = 0; uint32_t acc_phase = 0;
+      uint32_t j = 0;                                            // tile counter of this CTA
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         int n, h0, rows, w0;
         decode(item, n, h0, rows, w0);
         int p0 = wait_next_row(), p1 = wait_next_row();          // halo rows h0-1 and h0
-        for (int t = 0; t < rows; ++t) {
+        for (int t = 0; t < rows; ++t, ++j) {
           const int p2 = wait_next_row();                         // halo row h0+t+1
+          const int acc = j & (nacc - 1);
+          const uint32_t acc_phase = (j >> nacc_sh) & 1u;
           mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
@@ -520,7 +527,6 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
           umma_commit(&bar_tfull[acc]);
           umma_commit(&row_empty[p0]);                            // halo row t is not needed by later tiles
           p0 = p1; p1 = p2;
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         umma_commit(&row_empty[p0]);
         umma_commit(&row_empty[p1]);
@@ -528,15 +534,19 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
     }
   } else {
     const int quarter = warp & 3;
+    const int eset = (warp - 2) >> 2;                            // epilogue quartet: drains the tile pairs (j >> 1) % nsets == eset
     const int m = quarter * 32 + lane;
     uint32_t pool_prev[2][16];                                   // previous row (bf16 pairs) for the fused 2x2 max-pool
 #pragma unroll
     for (int q = 0; q < 16; ++q) { pool_prev[0][q] = 0; pool_prev[1][q] = 0; }
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    uint32_t j = 0;
+    for (int item = blockIdx.x; item < num_items && eset < nsets; item += gridDim.x) {
       int n, h0, rows, w0;
       decode(item, n, h0, rows, w0);
-      for (int t = 0; t < rows; ++t) {
+      for (int t = 0; t < rows; ++t, ++j) {
+        if ((int)((j >> 1) & (uint32_t)(nsets - 1)) != eset) continue;
+        const int acc = j & (nacc - 1);
+        const uint32_t acc_phase = (j >> nacc_sh) & 1u;
         if (p.swap) {
           const bool warp_valid = quarter * 32 < p.Cout;
           const float sc = warp_valid ? s_scale[quarter * 32 + lane] : 0.f, sh = warp_valid ? s_shift[quarter * 32 + lane] : 0.f;
@@ -549,7 +559,6 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_tempty[acc]);
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
           continue;
         }
         if constexpr (!FUSED) {
@@ -674,7 +683,6 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_tempty[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   }
@@ -845,8 +853,8 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
       }
       const int items = sp.N * sp.hchunks * sp.wsegs;
       const int grid = items < sm_count() ? items : sm_count();
-      if (fused) tapgemm_tc_strip_kernel<true><<<grid, TC_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
-      else tapgemm_tc_strip_kernel<false><<<grid, TC_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
+      if (fused) tapgemm_tc_strip_kernel<true><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
+      else tapgemm_tc_strip_kernel<false><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
       g_launches += 1;
       DCB_LAUNCH_OK("tapgemm_tc_strip_kernel");
       return DCB_OK;
