@@ -359,22 +359,23 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
 template <int KSTEPS, bool SWAP>
 __device__ __forceinline__ void strip_issue_tile(uint32_t d_tmem, uint64_t dbase, const uint32_t (&row16)[3], uint32_t w16,
                                                  int nkc, uint32_t slot16, uint32_t pitch16, uint32_t wblk16, uint32_t idesc) {
-  uint64_t dwt = dbase + w16;
+  // Order: consecutive MMAs read DIFFERENT halo rows (dy innermost).  Back-to-back MMAs whose A operands are the
+  // same rows shifted by one pixel issue ~2x slower (measured, profiles/r1_strip_scaling.txt).
+  const uint32_t wtap16 = (uint32_t)nkc * wblk16;
   uint32_t accf = 0;
-#pragma unroll
-  for (int dy = 0; dy < 3; ++dy) {
+  for (int kc = 0; kc < nkc; ++kc) {
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx) {
-      uint64_t dpx = dbase + (row16[dy] + dx * pitch16);     // halo box starts at pixel w0-1: tap dx = rows shifted by dx
-      for (int kc = 0; kc < nkc; ++kc) {
 #pragma unroll
-        for (int k = 0; k < KSTEPS; ++k) {
-          if (SWAP) umma_bf16(d_tmem, dwt + (uint64_t)(2 * k), dpx + (uint64_t)(2 * k), idesc, accf);
-          else umma_bf16(d_tmem, dpx + (uint64_t)(2 * k), dwt + (uint64_t)(2 * k), idesc, accf);
+      for (int k = 0; k < KSTEPS; ++k) {
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          const uint64_t dpx = dbase + (row16[dy] + kc * slot16 + dx * pitch16 + 2 * k);
+          const uint64_t dwt = dbase + (w16 + (dy * 3 + dx) * wtap16 + kc * wblk16 + 2 * k);
+          if (SWAP) umma_bf16(d_tmem, dwt, dpx, idesc, accf);
+          else umma_bf16(d_tmem, dpx, dwt, idesc, accf);
           accf = 1;
         }
-        dpx += slot16;
-        dwt += wblk16;
       }
     }
   }
