@@ -8,39 +8,64 @@ namespace dcb {
 extern unsigned long long g_launches;
 void launch_reduce_splits(const float* part, int splits, size_t n, float* out, cudaStream_t st);
 
+// One thread per pixel, weights broadcast from shared memory.  A warp's 32 pixels x COUT channels form ONE
+// contiguous run of the NHWC output, so the results are staged through a per-warp shared-memory tile and written
+// with fully coalesced 16-byte stores (a direct per-thread store would issue 32 partial-sector requests per
+// instruction and is ~3x slower for this write-bound layer).
 template <typename T, int COUT>
 __global__ void __launch_bounds__(256)
 conv3x3_c1_fwd_kernel(const float* __restrict__ x, int N, int H, int W, const float* __restrict__ w,
                       const float* __restrict__ scale, const float* __restrict__ shift, int relu, T* __restrict__ out) {
   __shared__ float ws[9 * COUT];
   __shared__ float sc[COUT], sh[COUT];
+  constexpr int ROWB = COUT * (int)sizeof(T);                 // bytes per pixel
+  constexpr int PITCH = ROWB + 16;                            // padded row: conflict-free 16-byte accesses
+  __shared__ __align__(16) uint8_t stage[8][32 * PITCH];
   for (int i = threadIdx.x; i < 9 * COUT; i += blockDim.x) ws[i] = w[i];
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) { sc[i] = scale ? scale[i] : 1.f; sh[i] = shift ? shift[i] : 0.f; }
   __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* st = stage[warp];
   const long long M = (long long)N * H * W;
-  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
-    const int wq = (int)(m % W), hq = (int)((m / W) % H);
-    const float* img = x + (m - (long long)hq * W - wq);
-    float v[9];
+  // block-uniform trip count: every warp handles 32 consecutive pixels per iteration
+  for (long long base = ((long long)blockIdx.x * 8 + warp) * 32; base < M; base += (long long)gridDim.x * 256) {
+    const long long m = base + lane;
+    if (m < M) {
+      const int wq = (int)(m % W), hq = (int)((m / W) % H);
+      const float* img = x + (m - (long long)hq * W - wq);
+      float v[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int ih = hq + t / 3 - 1, iw = wq + t % 3 - 1;
-      v[t] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? img[(long long)ih * W + iw] : 0.f;
-    }
-#pragma unroll
-    for (int c0 = 0; c0 < COUT; c0 += 4) {
-      float a[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int t = 0; t < 9; ++t)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) a[j] = fmaf(v[t], ws[t * COUT + c0 + j], a[j]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        a[j] = fmaf(a[j], sc[c0 + j], sh[c0 + j]);
-        if (relu) a[j] = fmaxf(a[j], 0.f);
+      for (int t = 0; t < 9; ++t) {
+        const int ih = hq + t / 3 - 1, iw = wq + t % 3 - 1;
+        v[t] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? img[(long long)ih * W + iw] : 0.f;
       }
-      store4<T>(out + m * COUT + c0, make_float4(a[0], a[1], a[2], a[3]));
+#pragma unroll
+      for (int c0 = 0; c0 < COUT; c0 += 4) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a[j] = fmaf(v[t], ws[t * COUT + c0 + j], a[j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          a[j] = fmaf(a[j], sc[c0 + j], sh[c0 + j]);
+          if (relu) a[j] = fmaxf(a[j], 0.f);
+        }
+        store4<T>(reinterpret_cast<T*>(st + lane * PITCH) + c0, make_float4(a[0], a[1], a[2], a[3]));
+      }
     }
+    __syncwarp();
+    // 32 pixels x ROWB bytes = one contiguous block of the output
+    const long long npix = (M - base) < 32 ? (M - base) : 32;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(out + base * COUT);
+#pragma unroll
+    for (int q = 0; q < ROWB / 16; ++q) {
+      const int idx = q * 32 + lane;                           // 16-byte chunk index within the block
+      const int px = idx / (ROWB / 16), ch = idx % (ROWB / 16);
+      if (px < npix)
+        *reinterpret_cast<uint4*>(dst + (size_t)idx * 16) = *reinterpret_cast<const uint4*>(st + px * PITCH + ch * 16);
+    }
+    __syncwarp();
   }
 }
 
@@ -113,7 +138,9 @@ static int launch_c1_fwd(const float* x, int N, int H, int W, const float* w, in
     case 8: conv3x3_c1_fwd_kernel<T, 8><<<(int)grid, 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break;
     case 16: conv3x3_c1_fwd_kernel<T, 16><<<(int)grid, 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break;
     case 32: conv3x3_c1_fwd_kernel<T, 32><<<(int)grid, 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break;
-    case 64: conv3x3_c1_fwd_kernel<T, 64><<<(int)grid, 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break;
+    case 64:
+      if constexpr (sizeof(T) == 2) { conv3x3_c1_fwd_kernel<T, 64><<<(int)grid, 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break; }
+      return fail(DCB_ERR_UNSUPPORTED, "dcb_conv3x3_c1_fwd: Cout=64 is built for bf16 output only");
     default: return fail(DCB_ERR_UNSUPPORTED, "dcb_conv3x3_c1_fwd: Cout=%d unsupported (8,16,32,64)", Cout);
   }
   g_launches += 1;
