@@ -103,25 +103,36 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, long long M,
   }
 }
 
-// y = relu(x*scale + shift) [* dropout keep-scale]
-template <typename T>
-__global__ void bn_apply_kernel(const T* __restrict__ x, long long M, int C, const float* __restrict__ scale,
-                                const float* __restrict__ shift, int relu, float p_drop, unsigned long long seed,
-                                const unsigned long long* __restrict__ seed_dev, uint32_t layer, T* __restrict__ y) {
+// y = relu(x*scale + shift) [* dropout keep-scale]; per-channel coefficients staged in shared memory,
+// VEC (4 or 8) channels per thread and iteration
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const T* __restrict__ x, long long M, int C, const float* __restrict__ scale,
+                const float* __restrict__ shift, int relu, float p_drop, unsigned long long seed,
+                const unsigned long long* __restrict__ seed_dev, uint32_t layer, T* __restrict__ y) {
+  extern __shared__ float s_coef[];
+  float* s_sc = s_coef; float* s_sh = s_coef + C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { s_sc[c] = scale[c]; s_sh[c] = shift[c]; }
+  __syncthreads();
   if (seed_dev) seed ^= *seed_dev;
-  const long long n4 = M * C / 4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)((i * 4) % C);
-    float4 v = load4<T>(x + i * 4);
-    const float4 sc = *reinterpret_cast<const float4*>(scale + c);
-    const float4 sh = *reinterpret_cast<const float4*>(shift + c);
-    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-    if (p_drop > 0.f) {
-      const float4 k = dropout_scale4(seed, layer, (unsigned long long)i, p_drop);
-      v.x *= k.x; v.y *= k.y; v.z *= k.z; v.w *= k.w;
+  const long long nv = M * C / VEC;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i * VEC) % C);
+    float v[VEC];
+    loadv<T, VEC>(x + i * VEC, v);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      v[j] = fmaf(v[j], s_sc[c + j], s_sh[c + j]);
+      if (relu) v[j] = fmaxf(v[j], 0.f);
     }
-    store4<T>(y + i * 4, v);
+    if (p_drop > 0.f) {
+#pragma unroll
+      for (int h = 0; h < VEC / 4; ++h) {
+        const float4 k = dropout_scale4(seed, layer, (unsigned long long)(i * (VEC / 4) + h), p_drop);
+        v[4 * h] *= k.x; v[4 * h + 1] *= k.y; v[4 * h + 2] *= k.z; v[4 * h + 3] *= k.w;
+      }
+    }
+    storev<T, VEC>(y + i * VEC, v);
   }
 }
 
@@ -194,46 +205,56 @@ bn_bwd_reduce_kernel(const float* __restrict__ dy, int ldy, int offy, const T* _
   }
 }
 
-// d_raw = scale * (dz - mean(dz) - xhat * mean(dz*xhat));  block 0 also emits dgamma/dbeta
-template <typename T>
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int ldy, int offy, const T* __restrict__ x, long long M,
-                                    int C, const float* __restrict__ scale, const float* __restrict__ shift,
-                                    const float* __restrict__ mean, const float* __restrict__ rstd, float p_drop,
-                                    unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
-                                    uint32_t layer, const double* __restrict__ sums, long long M_total,
-                                    float dgb_scale, T* __restrict__ draw, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta) {
-  if (seed_dev) seed ^= *seed_dev;
-  if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+// d_raw = scale * (dz - mean(dz) - xhat * mean(dz*xhat)) = scale*dz + k1*x + k0 with per-channel
+//   k1 = -scale*rstd*mean(dz*xhat),  k0 = -scale*mean(dz) - k1*mean          (fp64 once per CTA, then fp32 FMAs)
+// block 0 also emits dgamma/dbeta
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ dy, int ldy, int offy, const T* __restrict__ x, long long M,
+                    int C, const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, float p_drop,
+                    unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
+                    uint32_t layer, const double* __restrict__ sums, long long M_total,
+                    float dgb_scale, T* __restrict__ draw, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta) {
+  extern __shared__ float s_coef[];
+  float* s_sc = s_coef; float* s_sh = s_coef + C; float* s_k1 = s_coef + 2 * C; float* s_k0 = s_coef + 3 * C;
+  const double invM = 1.0 / (double)M_total;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double sc = scale[c], m1 = sums[c] * invM, m2 = sums[C + c] * invM;
+    const double k1 = -sc * (double)rstd[c] * m2;
+    s_sc[c] = scale[c]; s_sh[c] = shift[c];
+    s_k1[c] = (float)k1;
+    s_k0[c] = (float)(-sc * m1 - k1 * (double)mean[c]);
+    if (blockIdx.x == 0) {
       if (dbeta) dbeta[c] = (float)(sums[c] * (double)dgb_scale);
       if (dgamma) dgamma[c] = (float)(sums[C + c] * (double)dgb_scale);
     }
   }
-  const double invM = 1.0 / (double)M_total;
-  const long long n4 = M * (C >> 2);
-  const int c4n = C >> 2;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / c4n;
-    const int c = (int)(i % c4n) * 4;
-    float4 g = load4<float>(dy + r * ldy + offy + c);
-    const float4 v = load4<T>(x + r * C + c);
+  __syncthreads();
+  if (seed_dev) seed ^= *seed_dev;
+  const int cvn = C / VEC;
+  const long long nv = M * cvn;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cvn;
+    const int c = (int)(i % cvn) * VEC;
+    float g[VEC], v[VEC];
+    loadv<float, VEC>(dy + r * ldy + offy + c, g);
+    loadv<T, VEC>(x + r * C + c, v);
     if (p_drop > 0.f) {
-      const float4 k = dropout_scale4(seed, layer, (unsigned long long)i, p_drop);
-      g.x *= k.x; g.y *= k.y; g.z *= k.z; g.w *= k.w;
+#pragma unroll
+      for (int h = 0; h < VEC / 4; ++h) {
+        const float4 k = dropout_scale4(seed, layer, (unsigned long long)(i * (VEC / 4) + h), p_drop);
+        g[4 * h] *= k.x; g[4 * h + 1] *= k.y; g[4 * h + 2] *= k.z; g[4 * h + 3] *= k.w;
+      }
     }
-    const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
-    const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
-    if (fmaf(v.x, sc.x, sh.x) <= 0.f) g.x = 0.f;
-    if (fmaf(v.y, sc.y, sh.y) <= 0.f) g.y = 0.f;
-    if (fmaf(v.z, sc.z, sh.z) <= 0.f) g.z = 0.f;
-    if (fmaf(v.w, sc.w, sh.w) <= 0.f) g.w = 0.f;
-    float4 o;
-    o.x = sc.x * (g.x - (float)(sums[c + 0] * invM) - (v.x - mu.x) * rs.x * (float)(sums[C + c + 0] * invM));
-    o.y = sc.y * (g.y - (float)(sums[c + 1] * invM) - (v.y - mu.y) * rs.y * (float)(sums[C + c + 1] * invM));
-    o.z = sc.z * (g.z - (float)(sums[c + 2] * invM) - (v.z - mu.z) * rs.z * (float)(sums[C + c + 2] * invM));
-    o.w = sc.w * (g.w - (float)(sums[c + 3] * invM) - (v.w - mu.w) * rs.w * (float)(sums[C + c + 3] * invM));
-    store4<T>(draw + r * C + c, o);
+    float o[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float gz = fmaf(v[j], s_sc[c + j], s_sh[c + j]) <= 0.f ? 0.f : g[j];
+      o[j] = fmaf(s_sc[c + j], gz, fmaf(s_k1[c + j], v[j], s_k0[c + j]));
+    }
+    storev<T, VEC>(draw + r * C + c, o);
   }
 }
 
@@ -596,7 +617,8 @@ static int check_c(int C, const char* who) {
 extern "C" int dcb_bn_stats(int dtype, const void* x, long long M, int C, double* sums, dcb_stream_t stream) {
   DCB_CHECK_ARG(x && sums && M > 0, "dcb_bn_stats: bad arguments");
   if (int e = check_c(C, "dcb_bn_stats")) return e;
-  int grid = (int)((M + 255) / 256); if (grid > sm_count() * 8) grid = sm_count() * 8;
+  // every CTA ends with 2*C fp64 atomics on the same addresses: keep the CTA count low (2 per SM)
+  int grid = (int)((M + 511) / 512); if (grid > sm_count() * 2) grid = sm_count() * 2; if (grid < 1) grid = 1;
   if (C % 8 == 0 && 256 % (C / 8) == 0) {
     DISPATCH_T(dtype, bn_stats_kernel<T, 8><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, M, C, sums);)
   } else {
@@ -623,8 +645,14 @@ extern "C" int dcb_bn_apply(int dtype, const void* x, long long M, int C, const 
                             dcb_stream_t stream) {
   DCB_CHECK_ARG(x && y && scale && shift && M > 0 && C % 4 == 0, "dcb_bn_apply: bad arguments");
   DCB_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "dcb_bn_apply: p_drop must be in [0,1)");
-  DISPATCH_T(dtype, bn_apply_kernel<T><<<ew_grid(M * C / 4, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const T*)x, M, C, scale, shift, relu, p_drop, seed, seed_dev, layer, (T*)y);)
+  const size_t coef_smem = 2 * (size_t)C * sizeof(float);
+  if (C % 8 == 0) {
+    DISPATCH_T(dtype, bn_apply_kernel<T, 8><<<ew_grid(M * C / 8, 256), 256, coef_smem, (cudaStream_t)stream>>>(
+        (const T*)x, M, C, scale, shift, relu, p_drop, seed, seed_dev, layer, (T*)y);)
+  } else {
+    DISPATCH_T(dtype, bn_apply_kernel<T, 4><<<ew_grid(M * C / 4, 256), 256, coef_smem, (cudaStream_t)stream>>>(
+        (const T*)x, M, C, scale, shift, relu, p_drop, seed, seed_dev, layer, (T*)y);)
+  }
   g_launches += 1;
   DCB_LAUNCH_OK("bn_apply_kernel");
   return DCB_OK;
@@ -638,7 +666,8 @@ extern "C" int dcb_bn_bwd_reduce(int dtype, const float* dy, int ldy, int offy, 
   DCB_CHECK_ARG(ldy % 4 == 0 && offy % 4 == 0 && offy + C <= ldy, "dcb_bn_bwd_reduce: bad dy view (ld %d off %d C %d)", ldy, offy, C);
   DCB_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0, "dcb_bn_bwd_reduce: pointers must be 16-byte aligned");
   if (int e = check_c(C, "dcb_bn_bwd_reduce")) return e;
-  int grid = (int)((M + 255) / 256); if (grid > sm_count() * 8) grid = sm_count() * 8;
+  // every CTA ends with 2*C fp64 atomics on the same addresses: keep the CTA count low (2 per SM)
+  int grid = (int)((M + 511) / 512); if (grid > sm_count() * 2) grid = sm_count() * 2; if (grid < 1) grid = 1;
   if (C % 8 == 0 && 256 % (C / 8) == 0) {
     DISPATCH_T(dtype, bn_bwd_reduce_kernel<T, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(
         (const float*)dy, ldy, offy, (const T*)x, M, C, scale, shift, mean, rstd, p_drop, seed, seed_dev, layer, sums);)
@@ -659,8 +688,14 @@ extern "C" int dcb_bn_bwd_apply(int dtype, const float* dy, int ldy, int offy, c
   if (M_total <= 0) M_total = M;
   DCB_CHECK_ARG(dy && x && scale && shift && mean && rstd && sums && draw && M > 0, "dcb_bn_bwd_apply: bad arguments");
   DCB_CHECK_ARG(ldy % 4 == 0 && offy % 4 == 0 && offy + C <= ldy && C % 4 == 0, "dcb_bn_bwd_apply: bad dy view");
-  DISPATCH_T(dtype, bn_bwd_apply_kernel<T><<<ew_grid(M * C / 4, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const float*)dy, ldy, offy, (const T*)x, M, C, scale, shift, mean, rstd, p_drop, seed, seed_dev, layer, sums, M_total, dgb_scale, (T*)draw, dgamma, dbeta);)
+  const size_t coef_smem = 4 * (size_t)C * sizeof(float);
+  if (C % 8 == 0) {
+    DISPATCH_T(dtype, bn_bwd_apply_kernel<T, 8><<<ew_grid(M * C / 8, 256), 256, coef_smem, (cudaStream_t)stream>>>(
+        (const float*)dy, ldy, offy, (const T*)x, M, C, scale, shift, mean, rstd, p_drop, seed, seed_dev, layer, sums, M_total, dgb_scale, (T*)draw, dgamma, dbeta);)
+  } else {
+    DISPATCH_T(dtype, bn_bwd_apply_kernel<T, 4><<<ew_grid(M * C / 4, 256), 256, coef_smem, (cudaStream_t)stream>>>(
+        (const float*)dy, ldy, offy, (const T*)x, M, C, scale, shift, mean, rstd, p_drop, seed, seed_dev, layer, sums, M_total, dgb_scale, (T*)draw, dgamma, dbeta);)
+  }
   g_launches += 1;
   DCB_LAUNCH_OK("bn_bwd_apply_kernel");
   return DCB_OK;

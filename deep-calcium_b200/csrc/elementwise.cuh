@@ -43,6 +43,25 @@ template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bflo
   }
 }
 
+template <typename T> __device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&b);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+template <typename T, int VEC> __device__ __forceinline__ void storev(T* p, const float (&v)[VEC]) {
+  if constexpr (VEC == 8) store8<T>(p, v);
+  else store4<T>(p, make_float4(v[0], v[1], v[2], v[3]));
+}
+
 template <typename T, int VEC> __device__ __forceinline__ void loadv(const T* p, float (&v)[VEC]) {
   if constexpr (VEC == 8) {
     load8<T>(p, v);

@@ -195,8 +195,32 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, int splits,
   out[i] = s;
 }
 
+// many splits over a small tensor (the strip wgrad's one-partial-per-CTA layout): 32 elements x 8 split lanes
+// per CTA, lane j sums splits j, j+8, ... and the 8 lane sums are combined in a fixed order (deterministic)
+__global__ void __launch_bounds__(256)
+reduce_splits_wide_kernel(const float* __restrict__ part, int splits, size_t n, float* __restrict__ out) {
+  __shared__ float s_part[8][32];
+  const int e = threadIdx.x & 31, j = threadIdx.x >> 5;
+  const size_t i = (size_t)blockIdx.x * 32 + e;
+  float a0 = 0.f, a1 = 0.f;
+  if (i < n) {
+    int k = j;
+    for (; k + 8 < splits; k += 16) { a0 += part[(size_t)k * n + i]; a1 += part[(size_t)(k + 8) * n + i]; }
+    if (k < splits) a0 += part[(size_t)k * n + i];
+  }
+  s_part[j][e] = a0 + a1;
+  __syncthreads();
+  if (j == 0 && i < n) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += s_part[q][e];
+    out[i] = s;
+  }
+}
+
 void launch_reduce_splits(const float* part, int splits, size_t n, float* out, cudaStream_t st) {
-  reduce_splits_kernel<<<cdiv((long long)n, 256), 256, 0, st>>>(part, splits, n, out);
+  if (splits >= 16) reduce_splits_wide_kernel<<<cdiv((long long)n, 32), 256, 0, st>>>(part, splits, n, out);
+  else reduce_splits_kernel<<<cdiv((long long)n, 256), 256, 0, st>>>(part, splits, n, out);
 }
 
 void geom_conv3x3(TapGeom& g, int N, int H, int W) {
@@ -254,7 +278,7 @@ int run_f32_wgrad(const TapGeom& g, const float* s0, int C0, const float* s1, in
   dim3 grid((unsigned)(cdiv(K, FM) * cdiv(Nout, FN)), (unsigned)g.ntaps, (unsigned)S);
   tapgemm_f32_wgrad_kernel<<<grid, 256, 0, st>>>(p);
   DCB_LAUNCH_OK("tapgemm_f32_wgrad_kernel");
-  reduce_splits_kernel<<<cdiv((long long)n, 256), 256, 0, st>>>(p.part, S, n, dW);
+  launch_reduce_splits(p.part, S, n, dW, st);
   g_launches += 2;
   DCB_LAUNCH_OK("reduce_splits_kernel");
   return DCB_OK;
