@@ -3,6 +3,7 @@
 // the 8x dihedral test-time augmentation, Keras-form Adam.
 // Reference sites: unet_2d_summary.py:154-222 (layers), :585-595 (TTA), utils/neurons.py:13-137
 // (losses, metrics, TTA table); Keras 2.0.6 semantics as listed in SURVEY.md section 3.5.
+#include <cstdlib>
 #include "elementwise.cuh"
 
 namespace dcb {
@@ -205,8 +206,8 @@ bn_bwd_reduce_kernel(const float* __restrict__ dy, int ldy, int offy, const T* _
   }
 }
 
-// d_raw = scale * (dz - mean(dz) - xhat * mean(dz*xhat)) = scale*dz + k1*x + k0 with per-channel
-//   k1 = -scale*rstd*mean(dz*xhat),  k0 = -scale*mean(dz) - k1*mean          (fp64 once per CTA, then fp32 FMAs)
+// d_raw = scale * (dz - mean(dz) - xhat * mean(dz*xhat)) = scale*dz + k1*(x - mean) + k0 with per-channel
+//   k1 = -scale*rstd*mean(dz*xhat),  k0 = -scale*mean(dz)                    (fp64 once per CTA, then fp32 FMAs)
 // block 0 also emits dgamma/dbeta
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
@@ -219,13 +220,15 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, int ldy, int offy, const T* __
                     float* __restrict__ dbeta) {
   extern __shared__ float s_coef[];
   float* s_sc = s_coef; float* s_sh = s_coef + C; float* s_k1 = s_coef + 2 * C; float* s_k0 = s_coef + 3 * C;
+  float* s_mu = s_coef + 4 * C;
   const double invM = 1.0 / (double)M_total;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const double sc = scale[c], m1 = sums[c] * invM, m2 = sums[C + c] * invM;
     const double k1 = -sc * (double)rstd[c] * m2;
     s_sc[c] = scale[c]; s_sh[c] = shift[c];
     s_k1[c] = (float)k1;
-    s_k0[c] = (float)(-sc * m1 - k1 * (double)mean[c]);
+    s_k0[c] = (float)(-sc * m1);
+    s_mu[c] = mean[c];
     if (blockIdx.x == 0) {
       if (dbeta) dbeta[c] = (float)(sums[c] * (double)dgb_scale);
       if (dgamma) dgamma[c] = (float)(sums[C + c] * (double)dgb_scale);
@@ -252,7 +255,7 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, int ldy, int offy, const T* __
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const float gz = fmaf(v[j], s_sc[c + j], s_sh[c + j]) <= 0.f ? 0.f : g[j];
-      o[j] = fmaf(s_sc[c + j], gz, fmaf(s_k1[c + j], v[j], s_k0[c + j]));
+      o[j] = fmaf(s_sc[c + j], gz, fmaf(s_k1[c + j], v[j] - s_mu[c + j], s_k0[c + j]));
     }
     storev<T, VEC>(draw + r * C + c, o);
   }
@@ -614,11 +617,21 @@ static int check_c(int C, const char* who) {
   return DCB_OK;
 }
 
+// Grid for the two per-channel reductions: a CTA covers rows_par = 256/(C/VEC) rows per pass and should get at
+// least one 4-deep unrolled pass (4*rows_par rows); at most 4 CTAs per SM (each CTA ends with 2*C fp64 atomics).
+static int bn_reduce_grid(long long M, int C) {
+  const int vec = (C % 8 == 0 && 256 % (C / 8) == 0) ? 8 : 4;
+  const int rows_par = 256 / (C / vec) > 0 ? 256 / (C / vec) : 1;
+  long long grid = (M + 4LL * rows_par - 1) / (4LL * rows_par);
+  static const int per_sm = [] { const char* e = getenv("DCB_BN_CTAS_PER_SM"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 4; }();
+  if (grid > (long long)sm_count() * per_sm) grid = (long long)sm_count() * per_sm;
+  return grid < 1 ? 1 : (int)grid;
+}
+
 extern "C" int dcb_bn_stats(int dtype, const void* x, long long M, int C, double* sums, dcb_stream_t stream) {
   DCB_CHECK_ARG(x && sums && M > 0, "dcb_bn_stats: bad arguments");
   if (int e = check_c(C, "dcb_bn_stats")) return e;
-  // every CTA ends with 2*C fp64 atomics on the same addresses: keep the CTA count low (2 per SM)
-  int grid = (int)((M + 511) / 512); if (grid > sm_count() * 2) grid = sm_count() * 2; if (grid < 1) grid = 1;
+  const int grid = bn_reduce_grid(M, C);
   if (C % 8 == 0 && 256 % (C / 8) == 0) {
     DISPATCH_T(dtype, bn_stats_kernel<T, 8><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, M, C, sums);)
   } else {
@@ -666,8 +679,7 @@ extern "C" int dcb_bn_bwd_reduce(int dtype, const float* dy, int ldy, int offy, 
   DCB_CHECK_ARG(ldy % 4 == 0 && offy % 4 == 0 && offy + C <= ldy, "dcb_bn_bwd_reduce: bad dy view (ld %d off %d C %d)", ldy, offy, C);
   DCB_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0, "dcb_bn_bwd_reduce: pointers must be 16-byte aligned");
   if (int e = check_c(C, "dcb_bn_bwd_reduce")) return e;
-  // every CTA ends with 2*C fp64 atomics on the same addresses: keep the CTA count low (2 per SM)
-  int grid = (int)((M + 511) / 512); if (grid > sm_count() * 2) grid = sm_count() * 2; if (grid < 1) grid = 1;
+  const int grid = bn_reduce_grid(M, C);
   if (C % 8 == 0 && 256 % (C / 8) == 0) {
     DISPATCH_T(dtype, bn_bwd_reduce_kernel<T, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(
         (const float*)dy, ldy, offy, (const T*)x, M, C, scale, shift, mean, rstd, p_drop, seed, seed_dev, layer, sums);)
@@ -688,7 +700,7 @@ extern "C" int dcb_bn_bwd_apply(int dtype, const float* dy, int ldy, int offy, c
   if (M_total <= 0) M_total = M;
   DCB_CHECK_ARG(dy && x && scale && shift && mean && rstd && sums && draw && M > 0, "dcb_bn_bwd_apply: bad arguments");
   DCB_CHECK_ARG(ldy % 4 == 0 && offy % 4 == 0 && offy + C <= ldy && C % 4 == 0, "dcb_bn_bwd_apply: bad dy view");
-  const size_t coef_smem = 4 * (size_t)C * sizeof(float);
+  const size_t coef_smem = 5 * (size_t)C * sizeof(float);
   if (C % 8 == 0) {
     DISPATCH_T(dtype, bn_bwd_apply_kernel<T, 8><<<ew_grid(M * C / 8, 256), 256, coef_smem, (cudaStream_t)stream>>>(
         (const float*)dy, ldy, offy, (const T*)x, M, C, scale, shift, mean, rstd, p_drop, seed, seed_dev, layer, sums, M_total, dgb_scale, (T*)draw, dgamma, dbeta);)

@@ -381,6 +381,25 @@ __device__ __forceinline__ void strip_issue_tile(uint32_t d_tmem, uint64_t dbase
   }
 }
 
+// Folded mode (see the strip kernel): all steps of one halo row except the first; each step is one MMA (or two when
+// the accumulator ring wraps inside the span).  Weight groups are (kc, dx)-major: three stacked tiles per group.
+template <int KSTEPS, bool TWO>
+__device__ __forceinline__ void fold_issue_rest(uint32_t d0, uint32_t d1, uint64_t dA, uint64_t dW0, uint64_t dW1, uint32_t idesc0,
+                                                uint32_t idesc1, int nkc, uint32_t slot16, uint32_t pitch16, uint32_t wblk16) {
+  for (int kc = 0; kc < nkc; ++kc) {
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+      for (int k = 0; k < KSTEPS; ++k) {
+        if (kc == 0 && dx == 0 && k == 0) continue;
+        const uint32_t ao = kc * slot16 + dx * pitch16 + 2 * k, wo = (uint32_t)(kc * 3 + dx) * 3u * wblk16 + 2 * k;
+        umma_bf16(d0, dA + ao, dW0 + wo, idesc0, 1u);
+        if (TWO) umma_bf16(d1, dA + ao, dW1 + wo, idesc1, 1u);
+      }
+    }
+  }
+}
+
 constexpr int ST_MAX_RING = 12;
 
 struct TcStripParams {
@@ -390,6 +409,7 @@ struct TcStripParams {
   int R, ring, wsegs, hchunks;
   int slot_bytes;           // (PX + 2) * BK * 2 rounded up to 1024
   int swap;                 // 1: 256-pixel segments, weights as the MMA A operand (see TcFwdParams::swap)
+  int fold;                 // 1: the three vertical taps are folded into the MMA N dimension (see the kernel comment)
   // optional epilogue fusions (normal orientation only)
   const float* head_kernel; // [Cout][2] softmax head (unet_2d_summary.py:221-222): emit logit / prob per pixel
   const float* head_bias;   // [2]
@@ -402,13 +422,21 @@ struct TcStripParams {
   const float* shift;
 };
 
-template <bool FUSED>
+//
+// FOLD (Cout 32 or 64, normal orientation): an MMA with N = Cout is charged like a much wider one by the tensor pipe
+// (profiles/r1_umma_rate_probe.log), so these layers are issue-rate bound at 9*K/16 MMAs per tile.  Folded mode turns
+// the loop inside out: TMEM holds a ring of 512/Cout row accumulators (one per OUTPUT row), and each INPUT halo row i
+// is multiplied ONCE per (dx, k) against the stacked weights [W(dy=+1) | W(dy=0) | W(dy=-1)] (N = 3*Cout), which
+// accumulates into the three neighbouring accumulators of output rows i-1, i, i+1 at the same time: 3x fewer MMAs,
+// every halo row is read from shared memory by 3*K/16 instead of 9*K/16 MMAs.  Output row o is complete once input
+// row o+1 has been issued.
+template <bool FUSED, bool FOLD>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                         const __grid_constant__ CUtensorMap mapT0, const __grid_constant__ CUtensorMap mapT1,
                         const __grid_constant__ CUtensorMap mapB, const TcStripParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t bar_w, row_full[ST_MAX_RING], row_empty[ST_MAX_RING], bar_tfull[4], bar_tempty[4];
+  __shared__ uint64_t bar_w, row_full[ST_MAX_RING], row_empty[ST_MAX_RING], bar_tfull[16], bar_tempty[16];
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_scale[128], s_shift[128], s_wd[128];
   __shared__ __align__(16) uint8_t s_stage[4][4096];             // transpose tiles of the swapped epilogue
@@ -427,7 +455,9 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   // Normal orientation: draining a [128 px x Cout] accumulator (TMEM load latency + convert + stores) takes a warp
   // quartet ~2x longer than the tensor pipe needs to fill it (measured, profiles/r1_strip_scaling.txt), so TWO
   // quartets drain alternate tile pairs and FOUR accumulator stages keep the pipe busy.  Swapped: 2 x 256 columns.
-  const int nacc = p.swap ? 2 : 4, nacc_sh = p.swap ? 1 : 2, nsets = p.swap ? 1 : 2;
+  // Folded: 512/Cout row accumulators.
+  const int nacc = FOLD ? 512 / p.Cout : (p.swap ? 2 : 4);
+  const int nacc_sh = FOLD ? (p.Cout == 32 ? 4 : 3) : (p.swap ? 1 : 2), nsets = p.swap ? 1 : 2;
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)(nacc * acc_cols)) tmem_cols <<= 1;
 
@@ -463,7 +493,9 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
       mbar_arrive_expect_tx(&bar_w, w_bytes);
       for (int tap = 0; tap < 9; ++tap)
         for (int kc = 0; kc < p.nkc; ++kc)
-          tma_load_2d(&mapB, &bar_w, s_w + (size_t)(tap * p.nkc + kc) * wblk_bytes, tap * K + kc * p.BK, 0);
+          tma_load_2d(&mapB, &bar_w,
+                      s_w + (size_t)(FOLD ? (kc * 3 + tap % 3) * 3 + (2 - tap / 3) : tap * p.nkc + kc) * wblk_bytes,
+                      tap * K + kc * p.BK, 0);   // folded: (kc, dx) groups of three stacked tiles, dy = +1, 0, -1
       int pos = 0; uint32_t empty_parity = 0xffffffffu;          // bit i: parity to wait for on row_empty[i]
       const int kc0 = p.C0 / p.BK;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -506,6 +538,54 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
         return ps;
       };
       uint32_t j = 0;                                            // tile counter of this CTA
+      if constexpr (FOLD) {
+        const uint32_t id0 = make_idesc_bf16(TC_BM, 0, 0, 0), idu = ((uint32_t)p.Cout >> 3) << 17;   // N field += Cout per row
+        const uint32_t nmask = (uint32_t)nacc - 1u;
+        const uint64_t dW = dbase + w16;
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+          int n, h0, rows, w0;
+          decode(item, n, h0, rows, w0);
+          for (int i = -1; i <= rows; ++i) {                     // input (halo) row h0 + i
+            const int ps = wait_next_row();
+            const bool opens = i + 1 < rows;                      // output row i+1 receives its first contribution
+            if (opens) {
+              const uint32_t jo = j + (uint32_t)(i + 1);
+              mbar_wait(&bar_tempty[jo & nmask], ((jo >> nacc_sh) & 1u) ^ 1u);
+            }
+            tc_fence_after();
+            // halo row i accumulates into output rows [o_lo, o_hi]; the weight tile of row o inside a (kc, dx) group is
+            // o - i + 1.  The accumulator ring may wrap inside the span: one or two MMAs (segments) per step.
+            const int o_lo = i - 1 < 0 ? 0 : i - 1, o_hi = i + 1 < rows ? i + 1 : rows - 1;
+            const uint32_t sa = (j + (uint32_t)o_lo) & nmask;
+            const int t0 = o_lo - i + 1;
+            const uint64_t dA = dbase + (ring16 + ps * rowb16);
+            {   // first step (kc = 0, dx = 0, k = 0): a newly opened row starts with accumulate = 0
+              const int cnt = (opens ? i : o_hi) - o_lo + 1;      // rows that are already open
+              const int run = cnt < (int)(nacc - sa) ? cnt : (int)(nacc - sa);
+              if (run > 0) umma_bf16(tmem_base + sa * (uint32_t)p.Cout, dA, dW + (uint32_t)t0 * wblk16, id0 + run * idu, 1u);
+              if (run < cnt) umma_bf16(tmem_base, dA, dW + (uint32_t)(t0 + run) * wblk16, id0 + (cnt - run) * idu, 1u);
+              if (opens)
+                umma_bf16(tmem_base + ((j + (uint32_t)(i + 1)) & nmask) * (uint32_t)p.Cout, dA, dW + 2u * wblk16, id0 + idu, 0u);
+            }
+            const int cnt = o_hi - o_lo + 1;
+            const int run = cnt < (int)(nacc - sa) ? cnt : (int)(nacc - sa);
+            const uint32_t d0 = tmem_base + sa * (uint32_t)p.Cout, idesc0 = id0 + run * idu;
+            const uint64_t dW0 = dW + (uint32_t)t0 * wblk16;
+            if (run == cnt) {
+              if (ksteps == 4) fold_issue_rest<4, false>(d0, 0, dA, dW0, 0, idesc0, 0, p.nkc, slot16, pitch16, wblk16);
+              else fold_issue_rest<2, false>(d0, 0, dA, dW0, 0, idesc0, 0, p.nkc, slot16, pitch16, wblk16);
+            } else {
+              const uint64_t dW1 = dW + (uint32_t)(t0 + run) * wblk16;
+              const uint32_t idesc1 = id0 + (cnt - run) * idu;
+              if (ksteps == 4) fold_issue_rest<4, true>(d0, tmem_base, dA, dW0, dW1, idesc0, idesc1, p.nkc, slot16, pitch16, wblk16);
+              else fold_issue_rest<2, true>(d0, tmem_base, dA, dW0, dW1, idesc0, idesc1, p.nkc, slot16, pitch16, wblk16);
+            }
+            umma_commit(&row_empty[ps]);
+            if (i >= 1) umma_commit(&bar_tfull[(j + (uint32_t)(i - 1)) & nmask]);   // output row i-1 is complete
+          }
+          j += (uint32_t)rows;
+        }
+      } else {
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         int n, h0, rows, w0;
         decode(item, n, h0, rows, w0);
@@ -531,6 +611,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
         }
         umma_commit(&row_empty[p0]);
         umma_commit(&row_empty[p1]);
+      }
       }
     }
   } else {
@@ -796,6 +877,8 @@ static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, bool fused, T
   memset(&p, 0, sizeof(p));
   p.N = g.N; p.H = g.GH; p.W = g.GW; p.C0 = C0; p.C1 = C1; p.BK = BK; p.nkc = nkc; p.Cout = Nout;
   p.ring = ring; p.slot_bytes = slot; p.swap = swap; p.wsegs = g.GW / (swap ? 256 : 128);
+  static const bool no_fold = getenv("DCB_NO_FOLD") != nullptr;
+  p.fold = (!swap && !no_fold && (Nout == 32 || Nout == 64)) ? 1 : 0;
   int R = 32;
   while (R > 8 && (long long)g.N * cdiv(g.GH, R) * p.wsegs < 4LL * sm_count()) R >>= 1;
   if (fused && (g.GH % 2 != 0)) return false;          // row pairs of the fused pool must not straddle items
@@ -847,15 +930,19 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
       }
       static bool attr_set_strip = false;
       if (!attr_set_strip) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
         if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
         attr_set_strip = true;
       }
       const int items = sp.N * sp.hchunks * sp.wsegs;
       const int grid = items < sm_count() ? items : sm_count();
-      if (fused) tapgemm_tc_strip_kernel<true><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
-      else tapgemm_tc_strip_kernel<false><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
+      if (fused && sp.fold) tapgemm_tc_strip_kernel<true, true><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
+      else if (fused) tapgemm_tc_strip_kernel<true, false><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
+      else if (sp.fold) tapgemm_tc_strip_kernel<false, true><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
+      else tapgemm_tc_strip_kernel<false, false><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
       g_launches += 1;
       DCB_LAUNCH_OK("tapgemm_tc_strip_kernel");
       return DCB_OK;

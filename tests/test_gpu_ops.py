@@ -135,7 +135,9 @@ def test_convT2x2_fwd_dgrad_wgrad(cuda, precision, case):
 @pytest.mark.parametrize('shape', [(2, 16, 128, 32, 32), (1, 6, 256, 64, 64), (1, 8, 24, 32, 32)])
 def test_conv3x3_fused_pool_and_head_equal_the_unfused_composition(cuda, precision, shape):
     """dcb_conv3x3_fwd_fused (max-pool / softmax head folded into the conv epilogue) must reproduce the separate
-    kernels exactly - including shapes where the library falls back to the unfused composition."""
+    kernels - including shapes where the library falls back to the unfused composition.  fp32: exactly.  bf16: the
+    fused and the unfused launch may pick different tensor-core schedules (pixel-major, weight-major or row-folded
+    accumulation), i.e. different fp32 summation orders, so a few outputs may differ by one bf16 rounding step."""
     from deepcalcium.engine import ops
     N, H, W, Cin, Cout = shape
     dt = DT[precision]
@@ -154,11 +156,17 @@ def test_conv3x3_fused_pool_and_head_equal_the_unfused_composition(cuda, precisi
     ops.head_fwd(y, hk, hb, logit, prob)
     y2 = torch.empty_like(y); pool2 = torch.empty_like(pool)
     ops.conv3x3_fwd_fused(x, None, wf, y2, scale, shift, True, pool_out=pool2)
-    assert torch.equal(y2, y) and torch.equal(pool2, pool)
+    def same(a, b):
+        if precision == 'fp32':
+            return torch.equal(a, b)
+        a, b = a.float(), b.float()
+        return bool(((a - b).abs() <= 2.0 ** -7 * b.abs().clamp(min=1.0)).all()) and float((a != b).float().mean()) < 5e-3
+    assert same(y2, y) and same(pool2, pool)
     y3 = torch.full_like(y, 7.0); logit3 = torch.empty_like(logit); prob3 = torch.empty_like(prob)
     ops.conv3x3_fwd_fused(x, None, wf, y3, scale, shift, True, head_kernel=hk, head_bias=hb, logit=logit3, prob=prob3,
                           need_y=False)
-    assert torch.allclose(logit3, logit, atol=1e-5, rtol=1e-5) and torch.allclose(prob3, prob, atol=1e-6)
+    atol = 1e-5 if precision == 'fp32' else 2e-2
+    assert torch.allclose(logit3, logit, atol=atol, rtol=1e-5) and torch.allclose(prob3, prob, atol=atol / 4)
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
