@@ -7,6 +7,7 @@ deep-calcium_b200/deepcalcium/_lib/libdcb200.so (git-ignored, travels to the GPU
 box with the gpurun snapshot).
 """
 import hashlib
+import shlex
 import os
 import subprocess
 import sys
@@ -19,7 +20,7 @@ LIBDIR = os.path.join(HERE, 'deepcalcium', '_lib')
 LIB = os.path.join(LIBDIR, 'libdcb200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-         '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
+         '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr'] + shlex.split(os.environ.get('DCB_NVCC_EXTRA', ''))
 
 
 def _digest(paths):

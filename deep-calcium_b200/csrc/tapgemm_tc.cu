@@ -400,13 +400,44 @@ __device__ __forceinline__ void fold_issue_rest(uint32_t d0, uint32_t d1, uint64
   }
 }
 
+// Folded mode, interior halo row whose three accumulators do not wrap around the ring: the weight descriptors are
+// loop invariant, only the row descriptor dA and the accumulator address d0 change.  First step: rows i-1, i
+// accumulate (N = 2*Cout), row i+1 is opened with accumulate = 0 (N = Cout); then N = 3*Cout.
+template <int KSTEPS>
+__device__ __forceinline__ void fold_issue_fast(uint32_t d0, uint32_t d2, uint64_t dA, uint64_t dW, uint32_t id1, uint32_t id2,
+                                                uint32_t id3, int nkc, uint32_t slot16, uint32_t pitch16, uint32_t wblk16) {
+  umma_bf16(d0, dA, dW, id2, 1u);
+  umma_bf16(d2, dA, dW + 2u * wblk16, id1, 0u);
+  for (int kc = 0; kc < nkc; ++kc) {
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+      for (int k = 0; k < KSTEPS; ++k) {
+        if (kc == 0 && dx == 0 && k == 0) continue;
+        umma_bf16(d0, dA + (kc * slot16 + dx * pitch16 + 2 * k), dW + ((uint32_t)(kc * 3 + dx) * 3u * wblk16 + 2 * k), id3, 1u);
+      }
+    }
+  }
+}
+
 constexpr int ST_MAX_RING = 12;
+
+// -DDCB_STRIP_TIMING: the folded MMA thread accumulates clock64() intervals (diagnostic builds only)
+#ifdef DCB_STRIP_TIMING
+__device__ unsigned long long g_strip_dbg[148 * 8];
+#define ST_T(var) const long long var = clock64()
+#define ST_ACC(slot, a, b) dbg_acc[slot] += (unsigned long long)((b) - (a))
+#else
+#define ST_T(var)
+#define ST_ACC(slot, a, b)
+#endif
 
 struct TcStripParams {
   int N, H, W;
   int C0, C1, BK, nkc;
   int Cout;
-  int R, ring, wsegs, hchunks;
+  int ring, wsegs;
+  int gran;                 // partition granularity in rows (2 when H is even: fused pool pairs stay inside a strip)
   int slot_bytes;           // (PX + 2) * BK * 2 rounded up to 1024
   int swap;                 // 1: 256-pixel segments, weights as the MMA A operand (see TcFwdParams::swap)
   int fold;                 // 1: the three vertical taps are folded into the MMA N dimension (see the kernel comment)
@@ -450,7 +481,6 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   uint8_t* s_ring = smem + ((w_bytes + 1023) & ~1023u);
   const uint32_t row_bytes = (uint32_t)p.nkc * p.slot_bytes;     // one halo row = nkc chunk boxes
   const uint32_t box_bytes = (uint32_t)(PX + 2) * p.BK * 2u;
-  const int num_items = p.N * p.hchunks * p.wsegs;
   const int acc_cols = p.swap ? 256 : p.Cout;
   // Normal orientation: draining a [128 px x Cout] accumulator (TMEM load latency + convert + stores) takes a warp
   // quartet ~2x longer than the tensor pipe needs to fill it (measured, profiles/r1_strip_scaling.txt), so TWO
@@ -481,10 +511,21 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  auto decode = [&](int item, int& n, int& h0, int& rows, int& w0) {
-    const int ws = item % p.wsegs; item /= p.wsegs;
-    const int hc = item % p.hchunks; n = item / p.hchunks;
-    h0 = hc * p.R; rows = p.H - h0 < p.R ? p.H - h0 : p.R; w0 = ws * PX;
+  // Balanced partition: the N * wsegs image columns (H rows each) are laid end to end and cut into gridDim.x runs of
+  // equal length (in units of `gran` rows); a CTA walks its run as one or more strips - a strip never crosses a
+  // column boundary - so every SM gets the same number of rows (+-1 unit) and one 2-row halo per strip.
+  const int units_per_col = (p.H + p.gran - 1) / p.gran;
+  const long long units = (long long)p.N * p.wsegs * units_per_col;
+  const long long u_begin = units * blockIdx.x / gridDim.x, u_end = units * (blockIdx.x + 1) / gridDim.x;
+  auto next_strip = [&](long long& u, int& n, int& h0, int& rows, int& w0) -> bool {
+    if (u >= u_end) return false;
+    const int col = (int)(u / units_per_col), hu = (int)(u - (long long)col * units_per_col);
+    long long take = units_per_col - hu;
+    if (take > u_end - u) take = u_end - u;
+    n = col / p.wsegs; w0 = (col - n * p.wsegs) * PX; h0 = hu * p.gran;
+    rows = (int)take * p.gran; if (rows > p.H - h0) rows = p.H - h0;
+    u += take;
+    return true;
   };
 
   if (warp == 0) {
@@ -498,9 +539,8 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
                       tap * K + kc * p.BK, 0);   // folded: (kc, dx) groups of three stacked tiles, dy = +1, 0, -1
       int pos = 0; uint32_t empty_parity = 0xffffffffu;          // bit i: parity to wait for on row_empty[i]
       const int kc0 = p.C0 / p.BK;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        int n, h0, rows, w0;
-        decode(item, n, h0, rows, w0);
+      long long u = u_begin;
+      for (int n, h0, rows, w0; next_strip(u, n, h0, rows, w0);) {
         for (int rr = -1; rr <= rows; ++rr) {
           mbar_wait(&row_empty[pos], (empty_parity >> pos) & 1u);
           empty_parity ^= 1u << pos;
@@ -542,11 +582,35 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
         const uint32_t id0 = make_idesc_bf16(TC_BM, 0, 0, 0), idu = ((uint32_t)p.Cout >> 3) << 17;   // N field += Cout per row
         const uint32_t nmask = (uint32_t)nacc - 1u;
         const uint64_t dW = dbase + w16;
-        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-          int n, h0, rows, w0;
-          decode(item, n, h0, rows, w0);
+#ifdef DCB_STRIP_TIMING
+        unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const long long dbg_t0 = clock64();
+#endif
+        long long u = u_begin;
+        for (int n, h0, rows, w0; next_strip(u, n, h0, rows, w0);) {
           for (int i = -1; i <= rows; ++i) {                     // input (halo) row h0 + i
+            ST_T(c0);
             const int ps = wait_next_row();
+            ST_T(c1); ST_ACC(0, c0, c1);
+            const uint32_t jm = j + (uint32_t)(i - 1);
+            if (i >= 1 && i + 1 < rows && (jm & nmask) + 2u <= nmask) {      // interior row, accumulators contiguous
+              const uint32_t jo = jm + 2u;
+              mbar_wait(&bar_tempty[jo & nmask], ((jo >> nacc_sh) & 1u) ^ 1u);
+              tc_fence_after();
+              ST_T(c2); ST_ACC(1, c1, c2);
+              const uint32_t d0 = tmem_base + (jm & nmask) * (uint32_t)p.Cout;
+              const uint64_t dA = dbase + (ring16 + ps * rowb16);
+              if (ksteps == 4) fold_issue_fast<4>(d0, d0 + 2u * p.Cout, dA, dW, id0 + idu, id0 + 2u * idu, id0 + 3u * idu, p.nkc, slot16, pitch16, wblk16);
+              else fold_issue_fast<2>(d0, d0 + 2u * p.Cout, dA, dW, id0 + idu, id0 + 2u * idu, id0 + 3u * idu, p.nkc, slot16, pitch16, wblk16);
+              ST_T(c3); ST_ACC(2, c2, c3);
+              umma_commit(&row_empty[ps]);
+              umma_commit(&bar_tfull[jm & nmask]);
+              ST_T(c4); ST_ACC(3, c3, c4); ST_ACC(4, c0, c4);
+#ifdef DCB_STRIP_TIMING
+              dbg_acc[5] += 1;
+#endif
+              continue;
+            }
             const bool opens = i + 1 < rows;                      // output row i+1 receives its first contribution
             if (opens) {
               const uint32_t jo = j + (uint32_t)(i + 1);
@@ -585,10 +649,13 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
           }
           j += (uint32_t)rows;
         }
+#ifdef DCB_STRIP_TIMING
+        dbg_acc[6] = (unsigned long long)(clock64() - dbg_t0);
+        for (int q = 0; q < 8; ++q) g_strip_dbg[blockIdx.x * 8 + q] = dbg_acc[q];
+#endif
       } else {
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        int n, h0, rows, w0;
-        decode(item, n, h0, rows, w0);
+      long long u = u_begin;
+      for (int n, h0, rows, w0; next_strip(u, n, h0, rows, w0);) {
         int p0 = wait_next_row(), p1 = wait_next_row();          // halo rows h0-1 and h0
         for (int t = 0; t < rows; ++t, ++j) {
           const int p2 = wait_next_row();                         // halo row h0+t+1
@@ -622,9 +689,8 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
 #pragma unroll
     for (int q = 0; q < 16; ++q) { pool_prev[0][q] = 0; pool_prev[1][q] = 0; }
     uint32_t j = 0;
-    for (int item = blockIdx.x; item < num_items && eset < nsets; item += gridDim.x) {
-      int n, h0, rows, w0;
-      decode(item, n, h0, rows, w0);
+    long long u = u_begin;
+    for (int n, h0, rows, w0; eset < nsets && next_strip(u, n, h0, rows, w0);) {
       for (int t = 0; t < rows; ++t, ++j) {
         if ((int)((j >> 1) & (uint32_t)(nsets - 1)) != eset) continue;
         const int acc = j & (nacc - 1);
@@ -879,10 +945,8 @@ static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, bool fused, T
   p.ring = ring; p.slot_bytes = slot; p.swap = swap; p.wsegs = g.GW / (swap ? 256 : 128);
   static const bool no_fold = getenv("DCB_NO_FOLD") != nullptr;
   p.fold = (!swap && !no_fold && (Nout == 32 || Nout == 64)) ? 1 : 0;
-  int R = 32;
-  while (R > 8 && (long long)g.N * cdiv(g.GH, R) * p.wsegs < 4LL * sm_count()) R >>= 1;
-  if (fused && (g.GH % 2 != 0)) return false;          // row pairs of the fused pool must not straddle items
-  p.R = R; p.hchunks = cdiv(g.GH, R);
+  if (fused && (g.GH % 2 != 0)) return false;          // row pairs of the fused pool must not straddle strips
+  p.gran = (g.GH % 2 == 0) ? 2 : 1;
   dyn_smem = w_bytes + (size_t)ring * nkc * slot + 1024;
   return true;
 }
@@ -937,14 +1001,25 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
         if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
         attr_set_strip = true;
       }
-      const int items = sp.N * sp.hchunks * sp.wsegs;
-      const int grid = items < sm_count() ? items : sm_count();
+      const long long units = (long long)sp.N * sp.wsegs * cdiv(sp.H, sp.gran);
+      const int grid = units < sm_count() ? (int)units : sm_count();
       if (fused && sp.fold) tapgemm_tc_strip_kernel<true, true><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
       else if (fused) tapgemm_tc_strip_kernel<true, false><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
       else if (sp.fold) tapgemm_tc_strip_kernel<false, true><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
       else tapgemm_tc_strip_kernel<false, false><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
       g_launches += 1;
       DCB_LAUNCH_OK("tapgemm_tc_strip_kernel");
+#ifdef DCB_STRIP_TIMING
+      if (sp.fold && getenv("DCB_STRIP_TIMING_PRINT")) {
+        cudaStreamSynchronize(st);
+        static unsigned long long h[148 * 8];
+        cudaMemcpyFromSymbol(h, g_strip_dbg, sizeof(h));
+        double a[8] = {0};
+        for (int b = 0; b < grid; ++b) for (int q = 0; q < 8; ++q) a[q] += (double)h[b * 8 + q] / grid;
+        fprintf(stderr, "[strip timing] per CTA: fast rows %.0f | cycles/row: row_full wait %.0f, tempty wait %.0f, issue %.0f, commit %.0f, "
+                "total %.0f | loop cycles %.0f\n", a[5], a[0] / a[5], a[1] / a[5], a[2] / a[5], a[3] / a[5], a[4] / a[5], a[6]);
+      }
+#endif
       return DCB_OK;
     }
   }
