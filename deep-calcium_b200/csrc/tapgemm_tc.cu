@@ -28,7 +28,8 @@ using namespace tc;
 constexpr int TC_BM = 128;          // pixels per tile (= UMMA M, one TMEM lane per pixel)
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_THREADS = 192;
-constexpr int ST_THREADS = 64 + 8 * 32;   // strip kernel: TMA warp, MMA warp, two epilogue quartets
+constexpr int ST_QUARTETS = 2;             // epilogue quartets of the strip kernel (normal orientation)
+constexpr int ST_THREADS = 64 + ST_QUARTETS * 4 * 32;   // TMA warp, MMA warp, epilogue quartets
 constexpr int WG_THREADS = 192;
 
 // optional epilogue fusions requested through dcb_conv3x3_fwd_fused (mirrors dcb_conv_fusion_t)
@@ -425,6 +426,7 @@ constexpr int ST_MAX_RING = 12;
 // -DDCB_STRIP_TIMING: the folded MMA thread accumulates clock64() intervals (diagnostic builds only)
 #ifdef DCB_STRIP_TIMING
 __device__ unsigned long long g_strip_dbg[148 * 8];
+__device__ unsigned long long g_strip_dbg2[148 * 16];
 #define ST_T(var) const long long var = clock64()
 #define ST_ACC(slot, a, b) dbg_acc[slot] += (unsigned long long)((b) - (a))
 #else
@@ -469,7 +471,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t bar_w, row_full[ST_MAX_RING], row_empty[ST_MAX_RING], bar_tfull[16], bar_tempty[16];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_scale[128], s_shift[128], s_wd[128];
+  __shared__ __align__(16) float s_scale[128], s_shift[128], s_wd[128];
   __shared__ __align__(16) uint8_t s_stage[4][4096];             // transpose tiles of the swapped epilogue
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int PX = p.swap ? 256 : 128;                             // pixels per tile (one image-row segment)
@@ -487,7 +489,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   // quartets drain alternate tile pairs and FOUR accumulator stages keep the pipe busy.  Swapped: 2 x 256 columns.
   // Folded: 512/Cout row accumulators.
   const int nacc = FOLD ? 512 / p.Cout : (p.swap ? 2 : 4);
-  const int nacc_sh = FOLD ? (p.Cout == 32 ? 4 : 3) : (p.swap ? 1 : 2), nsets = p.swap ? 1 : 2;
+  const int nacc_sh = FOLD ? (p.Cout == 32 ? 4 : 3) : (p.swap ? 1 : 2), nsets = p.swap ? 1 : ST_QUARTETS;
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)(nacc * acc_cols)) tmem_cols <<= 1;
 
@@ -539,13 +541,26 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
                       tap * K + kc * p.BK, 0);   // folded: (kc, dx) groups of three stacked tiles, dy = +1, 0, -1
       int pos = 0; uint32_t empty_parity = 0xffffffffu;          // bit i: parity to wait for on row_empty[i]
       const int kc0 = p.C0 / p.BK;
+#ifdef DCB_STRIP_TIMING
+      unsigned long long pr_acc[2] = {0, 0};
+#endif
+      const int rows_per_slot = FOLD ? 2 : 1;                    // folded mode: one barrier per pair of halo rows
+      const int nslots = FOLD ? p.ring >> 1 : p.ring;
       long long u = u_begin;
       for (int n, h0, rows, w0; next_strip(u, n, h0, rows, w0);) {
         for (int rr = -1; rr <= rows; ++rr) {
-          mbar_wait(&row_empty[pos], (empty_parity >> pos) & 1u);
-          empty_parity ^= 1u << pos;
-          mbar_arrive_expect_tx(&row_full[pos], p.nkc * box_bytes);
-          uint8_t* dst = s_ring + (size_t)pos * row_bytes;
+          const int sub = FOLD ? ((rr + 1) & 1) : 0;              // row inside the slot
+          if (sub == 0) {
+            ST_T(pc0);
+            mbar_wait(&row_empty[pos], (empty_parity >> pos) & 1u);
+            ST_T(pc1);
+#ifdef DCB_STRIP_TIMING
+            pr_acc[0] += (unsigned long long)(pc1 - pc0); pr_acc[1] += 1;
+#endif
+            empty_parity ^= 1u << pos;
+            mbar_arrive_expect_tx(&row_full[pos], rows_per_slot * p.nkc * box_bytes);
+          }
+          uint8_t* dst = s_ring + ((size_t)pos * rows_per_slot + sub) * row_bytes;
           for (int kc = 0; kc < p.nkc; ++kc) {
             const bool second = kc >= kc0;
             const int cc = (second ? kc - kc0 : kc) * p.BK;
@@ -554,9 +569,12 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
               tma_load_4d(second ? &mapT1 : &mapT0, &row_full[pos], dst + (size_t)kc * p.slot_bytes + 256u * p.BK * 2u, cc,
                           w0 + 255, h0 + rr, n);
           }
-          if (++pos == p.ring) pos = 0;
+          if (sub == rows_per_slot - 1 && ++pos == nslots) pos = 0;
         }
       }
+#ifdef DCB_STRIP_TIMING
+      g_strip_dbg2[blockIdx.x * 16 + 0] = pr_acc[0]; g_strip_dbg2[blockIdx.x * 16 + 1] = pr_acc[1];
+#endif
     }
   } else if (warp == 1) {
     if (elect_one()) {
@@ -579,73 +597,86 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
       };
       uint32_t j = 0;                                            // tile counter of this CTA
       if constexpr (FOLD) {
+        // Synchronisation is per PAIR of rows: every mbarrier wait / tcgen05.commit costs the issuing thread a few
+        // hundred cycles (profiles/r1_umma_overhead_probe.log), as much as the 7 MMAs of a row.  Input rows (2m-1, 2m)
+        // arrive under one row_full barrier, open the output pair P(m) = rows (2m, 2m+1) (one tempty barrier, armed by the
+        // epilogue quartet that drains that pair) and complete the pair P(m-1) (one tfull commit).
         const uint32_t id0 = make_idesc_bf16(TC_BM, 0, 0, 0), idu = ((uint32_t)p.Cout >> 3) << 17;   // N field += Cout per row
-        const uint32_t nmask = (uint32_t)nacc - 1u;
+        const uint32_t nmask = (uint32_t)nacc - 1u, pmask = ((uint32_t)nacc >> 1) - 1u;
+        const int pair_sh = nacc_sh - 1;
         const uint64_t dW = dbase + w16;
+        const uint32_t a_row_full = smem_u32_pinned(row_full), a_row_empty = smem_u32_pinned(row_empty);
+        const uint32_t a_tfull = smem_u32_pinned(bar_tfull), a_tempty = smem_u32_pinned(bar_tempty);
+        const int ring_pairs = p.ring >> 1;
+        int pp = 0; uint32_t fullpar = 0;
 #ifdef DCB_STRIP_TIMING
         unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const long long dbg_t0 = clock64();
 #endif
+        // halo row i of the current strip (rows output rows, first output row = tile j) -> output rows [i-1, i+1]
+        auto issue_row_generic = [&](int i, int rows, uint64_t dA) {
+          const bool opens = i + 1 < rows;                        // output row i+1 receives its first contribution
+          // the weight tile of output row o inside a (kc, dx) group is o - i + 1; the accumulator ring may wrap inside
+          // the span: one or two MMAs (segments) per step
+          const int o_lo = i - 1 < 0 ? 0 : i - 1, o_hi = i + 1 < rows ? i + 1 : rows - 1;
+          const uint32_t sa = (j + (uint32_t)o_lo) & nmask;
+          const int t0 = o_lo - i + 1;
+          {   // first step (kc = 0, dx = 0, k = 0): a newly opened row starts with accumulate = 0
+            const int cnt = (opens ? i : o_hi) - o_lo + 1;        // rows that are already open
+            const int run = cnt < (int)(nacc - sa) ? cnt : (int)(nacc - sa);
+            if (run > 0) umma_bf16(tmem_base + sa * (uint32_t)p.Cout, dA, dW + (uint32_t)t0 * wblk16, id0 + run * idu, 1u);
+            if (run < cnt) umma_bf16(tmem_base, dA, dW + (uint32_t)(t0 + run) * wblk16, id0 + (cnt - run) * idu, 1u);
+            if (opens)
+              umma_bf16(tmem_base + ((j + (uint32_t)(i + 1)) & nmask) * (uint32_t)p.Cout, dA, dW + 2u * wblk16, id0 + idu, 0u);
+          }
+          const int cnt = o_hi - o_lo + 1;
+          const int run = cnt < (int)(nacc - sa) ? cnt : (int)(nacc - sa);
+          const uint32_t d0 = tmem_base + sa * (uint32_t)p.Cout, idesc0 = id0 + run * idu;
+          const uint64_t dW0 = dW + (uint32_t)t0 * wblk16;
+          if (run == cnt) {
+            if (ksteps == 4) fold_issue_rest<4, false>(d0, 0, dA, dW0, 0, idesc0, 0, p.nkc, slot16, pitch16, wblk16);
+            else fold_issue_rest<2, false>(d0, 0, dA, dW0, 0, idesc0, 0, p.nkc, slot16, pitch16, wblk16);
+          } else {
+            const uint64_t dW1 = dW + (uint32_t)(t0 + run) * wblk16;
+            const uint32_t idesc1 = id0 + (cnt - run) * idu;
+            if (ksteps == 4) fold_issue_rest<4, true>(d0, tmem_base, dA, dW0, dW1, idesc0, idesc1, p.nkc, slot16, pitch16, wblk16);
+            else fold_issue_rest<2, true>(d0, tmem_base, dA, dW0, dW1, idesc0, idesc1, p.nkc, slot16, pitch16, wblk16);
+          }
+        };
         long long u = u_begin;
         for (int n, h0, rows, w0; next_strip(u, n, h0, rows, w0);) {
-          for (int i = -1; i <= rows; ++i) {                     // input (halo) row h0 + i
+          const int half = rows >> 1;                             // rows is even in folded mode
+          for (int m = 0; m <= half; ++m) {                       // input (halo) rows h0 + 2m - 1 and h0 + 2m
             ST_T(c0);
-            const int ps = wait_next_row();
+            mbar_wait_a(a_row_full + 8u * pp, (fullpar >> pp) & 1u);
+            fullpar ^= 1u << pp;
             ST_T(c1); ST_ACC(0, c0, c1);
-            const uint32_t jm = j + (uint32_t)(i - 1);
-            if (i >= 1 && i + 1 < rows && (jm & nmask) + 2u <= nmask) {      // interior row, accumulators contiguous
-              const uint32_t jo = jm + 2u;
-              mbar_wait(&bar_tempty[jo & nmask], ((jo >> nacc_sh) & 1u) ^ 1u);
-              tc_fence_after();
-              ST_T(c2); ST_ACC(1, c1, c2);
-              const uint32_t d0 = tmem_base + (jm & nmask) * (uint32_t)p.Cout;
-              const uint64_t dA = dbase + (ring16 + ps * rowb16);
-              if (ksteps == 4) fold_issue_fast<4>(d0, d0 + 2u * p.Cout, dA, dW, id0 + idu, id0 + 2u * idu, id0 + 3u * idu, p.nkc, slot16, pitch16, wblk16);
-              else fold_issue_fast<2>(d0, d0 + 2u * p.Cout, dA, dW, id0 + idu, id0 + 2u * idu, id0 + 3u * idu, p.nkc, slot16, pitch16, wblk16);
-              ST_T(c3); ST_ACC(2, c2, c3);
-              umma_commit(&row_empty[ps]);
-              umma_commit(&bar_tfull[jm & nmask]);
-              ST_T(c4); ST_ACC(3, c3, c4); ST_ACC(4, c0, c4);
+            const uint32_t jp = (j >> 1) + (uint32_t)m;           // running index of the output pair P(m)
+            if (m < half) mbar_wait_a(a_tempty + 8u * (jp & pmask), ((jp >> pair_sh) & 1u) ^ 1u);
+            tc_fence_after();
+            ST_T(c2); ST_ACC(1, c1, c2);
+            const uint64_t dA0 = dbase + (ring16 + (uint32_t)pp * 2u * rowb16), dA1 = dA0 + rowb16;
+            if (m >= 1 && m < half && (jp & pmask) != 0u) {        // interior pair, its four accumulators are contiguous
+              const uint32_t d0 = tmem_base + (((jp - 1u) & pmask) * 2u) * (uint32_t)p.Cout, C = (uint32_t)p.Cout;
+              if (ksteps == 4) {
+                fold_issue_fast<4>(d0, d0 + 2u * C, dA0, dW, id0 + idu, id0 + 2u * idu, id0 + 3u * idu, p.nkc, slot16, pitch16, wblk16);
+                fold_issue_fast<4>(d0 + C, d0 + 3u * C, dA1, dW, id0 + idu, id0 + 2u * idu, id0 + 3u * idu, p.nkc, slot16, pitch16, wblk16);
+              } else {
+                fold_issue_fast<2>(d0, d0 + 2u * C, dA0, dW, id0 + idu, id0 + 2u * idu, id0 + 3u * idu, p.nkc, slot16, pitch16, wblk16);
+                fold_issue_fast<2>(d0 + C, d0 + 3u * C, dA1, dW, id0 + idu, id0 + 2u * idu, id0 + 3u * idu, p.nkc, slot16, pitch16, wblk16);
+              }
 #ifdef DCB_STRIP_TIMING
               dbg_acc[5] += 1;
 #endif
-              continue;
-            }
-            const bool opens = i + 1 < rows;                      // output row i+1 receives its first contribution
-            if (opens) {
-              const uint32_t jo = j + (uint32_t)(i + 1);
-              mbar_wait(&bar_tempty[jo & nmask], ((jo >> nacc_sh) & 1u) ^ 1u);
-            }
-            tc_fence_after();
-            // halo row i accumulates into output rows [o_lo, o_hi]; the weight tile of row o inside a (kc, dx) group is
-            // o - i + 1.  The accumulator ring may wrap inside the span: one or two MMAs (segments) per step.
-            const int o_lo = i - 1 < 0 ? 0 : i - 1, o_hi = i + 1 < rows ? i + 1 : rows - 1;
-            const uint32_t sa = (j + (uint32_t)o_lo) & nmask;
-            const int t0 = o_lo - i + 1;
-            const uint64_t dA = dbase + (ring16 + ps * rowb16);
-            {   // first step (kc = 0, dx = 0, k = 0): a newly opened row starts with accumulate = 0
-              const int cnt = (opens ? i : o_hi) - o_lo + 1;      // rows that are already open
-              const int run = cnt < (int)(nacc - sa) ? cnt : (int)(nacc - sa);
-              if (run > 0) umma_bf16(tmem_base + sa * (uint32_t)p.Cout, dA, dW + (uint32_t)t0 * wblk16, id0 + run * idu, 1u);
-              if (run < cnt) umma_bf16(tmem_base, dA, dW + (uint32_t)(t0 + run) * wblk16, id0 + (cnt - run) * idu, 1u);
-              if (opens)
-                umma_bf16(tmem_base + ((j + (uint32_t)(i + 1)) & nmask) * (uint32_t)p.Cout, dA, dW + 2u * wblk16, id0 + idu, 0u);
-            }
-            const int cnt = o_hi - o_lo + 1;
-            const int run = cnt < (int)(nacc - sa) ? cnt : (int)(nacc - sa);
-            const uint32_t d0 = tmem_base + sa * (uint32_t)p.Cout, idesc0 = id0 + run * idu;
-            const uint64_t dW0 = dW + (uint32_t)t0 * wblk16;
-            if (run == cnt) {
-              if (ksteps == 4) fold_issue_rest<4, false>(d0, 0, dA, dW0, 0, idesc0, 0, p.nkc, slot16, pitch16, wblk16);
-              else fold_issue_rest<2, false>(d0, 0, dA, dW0, 0, idesc0, 0, p.nkc, slot16, pitch16, wblk16);
             } else {
-              const uint64_t dW1 = dW + (uint32_t)(t0 + run) * wblk16;
-              const uint32_t idesc1 = id0 + (cnt - run) * idu;
-              if (ksteps == 4) fold_issue_rest<4, true>(d0, tmem_base, dA, dW0, dW1, idesc0, idesc1, p.nkc, slot16, pitch16, wblk16);
-              else fold_issue_rest<2, true>(d0, tmem_base, dA, dW0, dW1, idesc0, idesc1, p.nkc, slot16, pitch16, wblk16);
+              issue_row_generic(2 * m - 1, rows, dA0);
+              issue_row_generic(2 * m, rows, dA1);
             }
-            umma_commit(&row_empty[ps]);
-            if (i >= 1) umma_commit(&bar_tfull[(j + (uint32_t)(i - 1)) & nmask]);   // output row i-1 is complete
+            ST_T(c3); ST_ACC(2, c2, c3);
+            umma_commit_a(a_row_empty + 8u * pp);
+            if (m >= 1) umma_commit_a(a_tfull + 8u * ((jp - 1u) & pmask));       // output pair P(m-1) is complete
+            ST_T(c4); ST_ACC(3, c3, c4); ST_ACC(4, c0, c4);
+            if (++pp == ring_pairs) pp = 0;
           }
           j += (uint32_t)rows;
         }
@@ -685,6 +716,10 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
     const int quarter = warp & 3;
     const int eset = (warp - 2) >> 2;                            // epilogue quartet: drains the tile pairs (j >> 1) % nsets == eset
     const int m = quarter * 32 + lane;
+#ifdef DCB_STRIP_TIMING
+    long long ep_last = 0;
+    unsigned long long ep_acc[5] = {0, 0, 0, 0, 0};
+#endif
     uint32_t pool_prev[2][16];                                   // previous row (bf16 pairs) for the fused 2x2 max-pool
 #pragma unroll
     for (int q = 0; q < 16; ++q) { pool_prev[0][q] = 0; pool_prev[1][q] = 0; }
@@ -692,9 +727,13 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
     long long u = u_begin;
     for (int n, h0, rows, w0; eset < nsets && next_strip(u, n, h0, rows, w0);) {
       for (int t = 0; t < rows; ++t, ++j) {
-        if ((int)((j >> 1) & (uint32_t)(nsets - 1)) != eset) continue;
+        if ((int)((j >> 1) % (uint32_t)nsets) != eset) continue;
         const int acc = j & (nacc - 1);
         const uint32_t acc_phase = (j >> nacc_sh) & 1u;
+        // folded mode: the barriers are per PAIR of tiles (see the MMA warp); wait before the even tile, arrive after the odd one
+        const int bar_i = FOLD ? (int)((j >> 1) & (uint32_t)((nacc >> 1) - 1)) : acc;
+        const uint32_t bar_phase = FOLD ? ((j >> nacc_sh) & 1u) : acc_phase;
+        const bool do_wait = !FOLD || (j & 1u) == 0u, do_arrive = !FOLD || (j & 1u) != 0u;
         if (p.swap) {
           const bool warp_valid = quarter * 32 < p.Cout;
           const float sc = warp_valid ? s_scale[quarter * 32 + lane] : 0.f, sh = warp_valid ? s_shift[quarter * 32 + lane] : 0.f;
@@ -713,13 +752,25 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
           const size_t oidx = (((size_t)n * p.H + (h0 + t)) * p.W + (w0 + m)) * p.Cout;
           __nv_bfloat16* orow = p.out + oidx;
           float* orow_f = reinterpret_cast<float*>(p.out) + oidx;
-          mbar_wait(&bar_tfull[acc], acc_phase);
+          ST_T(ec0);
+          if (do_wait) mbar_wait(&bar_tfull[bar_i], bar_phase);
           tc_fence_after();
+          ST_T(ec1);
+#ifdef DCB_STRIP_TIMING
+          ep_acc[0] += (unsigned long long)(ec1 - ec0); ep_acc[1] += 1;
+          if (ep_last) ep_acc[2] += (unsigned long long)(ec0 - ep_last);
+          ep_last = ec1;
+#endif
           const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.Cout);
           for (int c = 0; c < p.Cout; c += 32) {
             uint32_t r[32];
+            ST_T(lc0);
             tmem_ld_32x32b_x32(t_addr + c, r);
             tmem_ld_wait();
+            ST_T(lc1);
+#ifdef DCB_STRIP_TIMING
+            ep_acc[3] += (unsigned long long)(lc1 - lc0);
+#endif
             if (p.out_f32) {
   #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -732,29 +783,30 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
                 *reinterpret_cast<float4*>(orow_f + c + j) = make_float4(v[0], v[1], v[2], v[3]);
               }
             } else {
+              uint32_t pk[16];
+              bn_relu_pack32(r, s_scale + c, s_shift + c, p.relu, pk);
   #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint32_t pk[4];
-  #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const int ch = c + j + 2 * q;
-                  float v0 = fmaf(__uint_as_float(r[j + 2 * q]), s_scale[ch], s_shift[ch]);
-                  float v1 = fmaf(__uint_as_float(r[j + 2 * q + 1]), s_scale[ch + 1], s_shift[ch + 1]);
-                  if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-                  __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
-                  pk[q] = *reinterpret_cast<uint32_t*>(&b2);
-                }
-                *reinterpret_cast<uint4*>(orow + c + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              }
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(orow + c + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
             }
+#ifdef DCB_STRIP_TIMING
+            { const long long lc2 = clock64(); ep_acc[4] += (unsigned long long)(lc2 - lc1); }
+#endif
           }
         } else {
           const size_t opix = ((size_t)n * p.H + (h0 + t)) * p.W + (w0 + m);
           const size_t oidx = opix * p.Cout;
           __nv_bfloat16* orow = p.out + oidx;
           float* orow_f = reinterpret_cast<float*>(p.out) + oidx;
-          mbar_wait(&bar_tfull[acc], acc_phase);
+          ST_T(ec0);
+          if (do_wait) mbar_wait(&bar_tfull[bar_i], bar_phase);
           tc_fence_after();
+          ST_T(ec1);
+#ifdef DCB_STRIP_TIMING
+          ep_acc[0] += (unsigned long long)(ec1 - ec0); ep_acc[1] += 1;
+          if (ep_last) ep_acc[2] += (unsigned long long)(ec0 - ep_last);
+          ep_last = ec1;
+#endif
           const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.Cout);
           float zacc = p.head_kernel ? (p.head_bias[1] - p.head_bias[0]) : 0.f;
   #pragma unroll
@@ -777,19 +829,18 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
               }
             } else {
               uint32_t pk[16];
+              bn_relu_pack32(r, s_scale + c, s_shift + c, p.relu, pk);
+              if (p.head_kernel) {            // head on the rounded (stored) bf16 values, four partial sums
+                float za[4] = {0.f, 0.f, 0.f, 0.f};
   #pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                const int ch = c + 2 * q;
-                float v0 = fmaf(__uint_as_float(r[2 * q]), s_scale[ch], s_shift[ch]);
-                float v1 = fmaf(__uint_as_float(r[2 * q + 1]), s_scale[ch + 1], s_shift[ch + 1]);
-                if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-                __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
-                pk[q] = *reinterpret_cast<uint32_t*>(&b2);
-                if (p.head_kernel) {          // same operand values and order as head_fwd_kernel on the stored bf16 tensor
-                  const float2 f = __bfloat1622float2(b2);
-                  zacc = fmaf(f.x, s_wd[ch], zacc);
-                  zacc = fmaf(f.y, s_wd[ch + 1], zacc);
+                for (int g = 0; g < 8; ++g) {
+                  const float4 wd = *reinterpret_cast<const float4*>(s_wd + c + 4 * g);
+                  const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[2 * g]));
+                  const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[2 * g + 1]));
+                  za[0] = fmaf(f0.x, wd.x, za[0]); za[1] = fmaf(f0.y, wd.y, za[1]);
+                  za[2] = fmaf(f1.x, wd.z, za[2]); za[3] = fmaf(f1.y, wd.w, za[3]);
                 }
+                zacc += (za[0] + za[1]) + (za[2] + za[3]);
               }
               if (p.need_y) {
   #pragma unroll
@@ -830,9 +881,13 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+        if (lane == 0 && do_arrive) mbar_arrive(&bar_tempty[bar_i]);
       }
     }
+#ifdef DCB_STRIP_TIMING
+    if (lane == 0 && quarter == 0 && eset < 2)
+      for (int q = 0; q < 5; ++q) g_strip_dbg2[blockIdx.x * 16 + 2 + 5 * eset + q] = ep_acc[q];
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -944,7 +999,7 @@ static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, bool fused, T
   p.N = g.N; p.H = g.GH; p.W = g.GW; p.C0 = C0; p.C1 = C1; p.BK = BK; p.nkc = nkc; p.Cout = Nout;
   p.ring = ring; p.slot_bytes = slot; p.swap = swap; p.wsegs = g.GW / (swap ? 256 : 128);
   static const bool no_fold = getenv("DCB_NO_FOLD") != nullptr;
-  p.fold = (!swap && !no_fold && (Nout == 32 || Nout == 64)) ? 1 : 0;
+  p.fold = (!swap && !no_fold && (Nout == 32 || Nout == 64) && g.GH % 2 == 0 && ring >= 4) ? 1 : 0;
   if (fused && (g.GH % 2 != 0)) return false;          // row pairs of the fused pool must not straddle strips
   p.gran = (g.GH % 2 == 0) ? 2 : 1;
   dyn_smem = w_bytes + (size_t)ring * nkc * slot + 1024;
@@ -1016,6 +1071,13 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
         cudaMemcpyFromSymbol(h, g_strip_dbg, sizeof(h));
         double a[8] = {0};
         for (int b = 0; b < grid; ++b) for (int q = 0; q < 8; ++q) a[q] += (double)h[b * 8 + q] / grid;
+        static unsigned long long h2[148 * 16];
+        cudaMemcpyFromSymbol(h2, g_strip_dbg2, sizeof(h2));
+        double e[16] = {0};
+        for (int b = 0; b < grid; ++b) for (int q = 0; q < 16; ++q) e[q] += (double)h2[b * 16 + q] / grid;
+        fprintf(stderr, "[strip timing] producer: rows %.0f, row_empty wait %.0f cycles/row | epilogue quartet 0: tiles %.0f, tfull wait %.0f, "
+                "work %.0f (tmem ld %.0f, math+store %.0f) cycles/tile | quartet 1: tiles %.0f, tfull wait %.0f, work %.0f (ld %.0f, math %.0f)\n",
+                e[1], e[0] / e[1], e[3], e[2] / e[3], e[4] / e[3], e[5] / e[3], e[6] / e[3], e[8], e[7] / e[8], e[9] / e[8], e[10] / e[8], e[11] / e[8]);
         fprintf(stderr, "[strip timing] per CTA: fast rows %.0f | cycles/row: row_full wait %.0f, tempty wait %.0f, issue %.0f, commit %.0f, "
                 "total %.0f | loop cycles %.0f\n", a[5], a[0] / a[5], a[1] / a[5], a[2] / a[5], a[3] / a[5], a[4] / a[5], a[6]);
       }

@@ -46,6 +46,40 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// 32-bit shared address of `p` that the compiler cannot rematerialise (an opaque mov): the plain smem_u32() is a pure
+// expression that ptxas happily recomputes - S2R SR_CgaCtaId included - at every use inside a loop.
+__device__ __forceinline__ uint32_t smem_u32_pinned(const void* p) {
+  uint32_t a;
+  asm volatile("mov.u32 %0, %1;" : "=r"(a) : "r"(smem_u32(p)));
+  return a;
+}
+// Variants taking a precomputed 32-bit shared-memory address.  smem_u32() of a __shared__ variable re-reads
+// SR_CgaCtaId (S2UR, ~100+ cycles of latency) every time it is evaluated next to a volatile asm; a single-thread
+// producer / MMA loop that waits and commits once per tile pays for that on its critical path
+// (profiles/r1_umma_overhead_probe.log), so those loops hoist the addresses out.
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_a(bar_addr, parity)) {
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+}
 // Bounded wait: a protocol bug traps (surfacing as a CUDA error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
@@ -111,6 +145,9 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       : "memory");
 }
 // mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit_a(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -150,6 +187,40 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- epilogue math
+// packed fp32x2 FMA (sm_100): d = a * b + c on two lanes at once
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t ua, ub, uc, ud;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(uc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(ud) : "l"(ua), "l"(ub), "l"(uc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(ud));
+  return d;
+}
+
+// y = [relu](acc * scale + shift) for 32 consecutive accumulator columns, packed to 16 bf16 pairs.  scale/shift are
+// read from (16-byte aligned) shared memory as float4; ReLU is applied to the packed bf16 pairs (identical result:
+// rounding is monotonic and keeps the sign).
+__device__ __forceinline__ void bn_relu_pack32(const uint32_t (&r)[32], const float* s_sc, const float* s_sh, int relu,
+                                               uint32_t (&pk)[16]) {
+  const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float4 sc = *reinterpret_cast<const float4*>(s_sc + 4 * g);
+    const float4 sh = *reinterpret_cast<const float4*>(s_sh + 4 * g);
+    const float2 v0 = ffma2(make_float2(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1])), make_float2(sc.x, sc.y),
+                            make_float2(sh.x, sh.y));
+    const float2 v1 = ffma2(make_float2(__uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3])), make_float2(sc.z, sc.w),
+                            make_float2(sh.z, sh.w));
+    __nv_bfloat162 b0 = __float22bfloat162_rn(v0), b1 = __float22bfloat162_rn(v1);
+    if (relu) { b0 = __hmax2(b0, zero2); b1 = __hmax2(b1, zero2); }
+    pk[2 * g] = *reinterpret_cast<uint32_t*>(&b0);
+    pk[2 * g + 1] = *reinterpret_cast<uint32_t*>(&b1);
+  }
 }
 
 }  // namespace tc
