@@ -27,7 +27,7 @@ using namespace tc;
 
 constexpr int TC_BM = 128;          // pixels per tile (= UMMA M, one TMEM lane per pixel)
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 64 + 8 * 32;   // generic kernel: TMA warp, MMA warp, two epilogue quartets (one per accumulator stage)
 constexpr int ST_QUARTETS = 2;             // epilogue quartets of the strip kernel (normal orientation)
 constexpr int ST_THREADS = 64 + ST_QUARTETS * 4 * 32;   // TMA warp, MMA warp, epilogue quartets
 constexpr int WG_THREADS = 192;
@@ -118,7 +118,7 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_scale[512], s_shift[512];
+  __shared__ __align__(16) float s_scale[512], s_shift[512];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // dynamic smem: 1024-byte aligned stage buffers (swizzle atoms are address based)
@@ -228,8 +228,15 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
     // ===================================================== epilogue warps (TMEM -> regs -> global)
     const int quarter = warp & 3;                    // TMEM lanes [32*quarter, 32*quarter+32)
     const int m = quarter * 32 + lane;               // row of the tile = pixel
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    // Normal orientation: two quartets, quartet q drains accumulator stage q (every other tile) - draining a
+    // [128 x BN] accumulator takes one quartet longer than the MMAs of a short-K tile (convT: K = Cin only).
+    // Swapped orientation: one quartet (its transpose buffers are per warp), the second one idles.
+    const int eset = (warp - 2) >> 2, nsets = p.swap ? 1 : 2;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles && eset < nsets; tile += gridDim.x, ++it) {
+      if (nsets == 2 && (int)(it & 1u) != eset) continue;
+      const int acc = (int)(it & 1u);
+      const uint32_t acc_phase = (it >> 1) & 1u;
       const int nt = tile % num_ntiles, mt = tile / num_ntiles;
       const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
       if (p.swap) {
@@ -261,7 +268,6 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_tempty[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
       }
       // pixel of this row
@@ -310,26 +316,16 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
             *reinterpret_cast<float4*>(orow_f + c + j) = make_float4(v[0], v[1], v[2], v[3]);
           }
         } else if (valid) {
+          uint32_t pk[16];
+          bn_relu_pack32(r, s_scale + cbase + c, s_shift + cbase + c, p.relu, pk);
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int ch = cbase + c + j + 2 * q;
-              float v0 = fmaf(__uint_as_float(r[j + 2 * q]), s_scale[ch], s_shift[ch]);
-              float v1 = fmaf(__uint_as_float(r[j + 2 * q + 1]), s_scale[ch + 1], s_shift[ch + 1]);
-              if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-              __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
-              pk[q] = *reinterpret_cast<uint32_t*>(&b2);
-            }
-            *reinterpret_cast<uint4*>(orow + c + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(orow + c + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -1203,7 +1199,7 @@ struct TcWgradParams {
   float* part;              // [splits][ntaps][K][Nout]
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 tapgemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                         const __grid_constant__ CUtensorMap mapG, const TcWgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1665,7 +1661,7 @@ int run_tc_wgrad(const TapGeom& g, const void* s0, int C0, const void* s1, int C
   const size_t dyn_smem = w.stages * stage_bytes + 1024;
   const int num_items = cdiv(K, 128) * (Nout / w.BN) * g.ntaps * w.splits;
   const int grid = num_items < sm_count() ? num_items : sm_count();
-  tapgemm_tc_wgrad_kernel<<<grid, TC_THREADS, dyn_smem, st>>>(mA0, mA1, mG, p);
+  tapgemm_tc_wgrad_kernel<<<grid, WG_THREADS, dyn_smem, st>>>(mA0, mA1, mG, p);
   DCB_LAUNCH_OK("tapgemm_tc_wgrad_kernel");
   launch_reduce_splits(p.part, w.splits, (size_t)g.ntaps * K * Nout, dW, st);
   g_launches += 2;
