@@ -16,8 +16,8 @@ template <typename T, int COUT>
 __global__ void __launch_bounds__(256)
 conv3x3_c1_fwd_kernel(const float* __restrict__ x, int N, int H, int W, const float* __restrict__ w,
                       const float* __restrict__ scale, const float* __restrict__ shift, int relu, T* __restrict__ out) {
-  __shared__ float ws[9 * COUT];
-  __shared__ float sc[COUT], sh[COUT];
+  __shared__ __align__(16) float ws[9 * COUT];
+  __shared__ __align__(16) float sc[COUT], sh[COUT];
   constexpr int ROWB = COUT * (int)sizeof(T);                 // bytes per pixel
   constexpr int PITCH = ROWB + 16;                            // padded row: conflict-free 16-byte accesses
   __shared__ __align__(16) uint8_t stage[8][32 * PITCH];
@@ -39,19 +39,22 @@ conv3x3_c1_fwd_kernel(const float* __restrict__ x, int N, int H, int W, const fl
         const int ih = hq + t / 3 - 1, iw = wq + t % 3 - 1;
         v[t] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? img[(long long)ih * W + iw] : 0.f;
       }
+      // packed fp32x2 FMAs: two output channels per instruction (the layer is instruction-issue bound otherwise)
 #pragma unroll
       for (int c0 = 0; c0 < COUT; c0 += 4) {
-        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int t = 0; t < 9; ++t)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) a[j] = fmaf(v[t], ws[t * COUT + c0 + j], a[j]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          a[j] = fmaf(a[j], sc[c0 + j], sh[c0 + j]);
-          if (relu) a[j] = fmaxf(a[j], 0.f);
+        for (int t = 0; t < 9; ++t) {
+          const float4 wv = *reinterpret_cast<const float4*>(&ws[t * COUT + c0]);
+          const float2 vv = make_float2(v[t], v[t]);
+          a0 = ffma2(vv, make_float2(wv.x, wv.y), a0);
+          a1 = ffma2(vv, make_float2(wv.z, wv.w), a1);
         }
-        store4<T>(reinterpret_cast<T*>(st + lane * PITCH) + c0, make_float4(a[0], a[1], a[2], a[3]));
+        const float4 s4 = *reinterpret_cast<const float4*>(&sc[c0]), h4 = *reinterpret_cast<const float4*>(&sh[c0]);
+        a0 = ffma2(a0, make_float2(s4.x, s4.y), make_float2(h4.x, h4.y));
+        a1 = ffma2(a1, make_float2(s4.z, s4.w), make_float2(h4.z, h4.w));
+        if (relu) { a0.x = fmaxf(a0.x, 0.f); a0.y = fmaxf(a0.y, 0.f); a1.x = fmaxf(a1.x, 0.f); a1.y = fmaxf(a1.y, 0.f); }
+        store4<T>(reinterpret_cast<T*>(st + lane * PITCH) + c0, make_float4(a0.x, a0.y, a1.x, a1.y));
       }
     }
     __syncwarp();

@@ -195,17 +195,19 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, int splits,
   out[i] = s;
 }
 
-// many splits over a small tensor (the strip wgrad's one-partial-per-CTA layout): 32 elements x 8 split lanes
-// per CTA, lane j sums splits j, j+8, ... and the 8 lane sums are combined in a fixed order (deterministic)
+// many splits over a small tensor (the strip wgrad's one-partial-per-CTA layout): E elements x (256 / E) split
+// lanes per CTA, lane j sums splits j, j+L, ... and the L lane sums are combined in a fixed order (deterministic)
+template <int E>
 __global__ void __launch_bounds__(256)
 reduce_splits_wide_kernel(const float* __restrict__ part, int splits, size_t n, float* __restrict__ out) {
-  __shared__ float s_part[8][32];
-  const int e = threadIdx.x & 31, j = threadIdx.x >> 5;
-  const size_t i = (size_t)blockIdx.x * 32 + e;
+  constexpr int L = 256 / E;
+  __shared__ float s_part[L][E];
+  const int e = threadIdx.x % E, j = threadIdx.x / E;
+  const size_t i = (size_t)blockIdx.x * E + e;
   float a0 = 0.f, a1 = 0.f;
   if (i < n) {
     int k = j;
-    for (; k + 8 < splits; k += 16) { a0 += part[(size_t)k * n + i]; a1 += part[(size_t)(k + 8) * n + i]; }
+    for (; k + L < splits; k += 2 * L) { a0 += part[(size_t)k * n + i]; a1 += part[(size_t)(k + L) * n + i]; }
     if (k < splits) a0 += part[(size_t)k * n + i];
   }
   s_part[j][e] = a0 + a1;
@@ -213,13 +215,14 @@ reduce_splits_wide_kernel(const float* __restrict__ part, int splits, size_t n, 
   if (j == 0 && i < n) {
     float s = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) s += s_part[q][e];
+    for (int q = 0; q < L; ++q) s += s_part[q][e];
     out[i] = s;
   }
 }
 
 void launch_reduce_splits(const float* part, int splits, size_t n, float* out, cudaStream_t st) {
-  if (splits >= 16) reduce_splits_wide_kernel<<<cdiv((long long)n, 32), 256, 0, st>>>(part, splits, n, out);
+  if (splits >= 64 && n < 4096) reduce_splits_wide_kernel<8><<<cdiv((long long)n, 8), 256, 0, st>>>(part, splits, n, out);
+  else if (splits >= 16) reduce_splits_wide_kernel<32><<<cdiv((long long)n, 32), 256, 0, st>>>(part, splits, n, out);
   else reduce_splits_kernel<<<cdiv((long long)n, 256), 256, 0, st>>>(part, splits, n, out);
 }
 

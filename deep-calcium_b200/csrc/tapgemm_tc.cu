@@ -122,7 +122,9 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // dynamic smem: 1024-byte aligned stage buffers (swizzle atoms are address based)
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an offset into the __shared__ array (an integer round trip would turn every later access
+  // through this pointer into a generic-space load/store)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   // pixel tile: 128 rows (normal) or 256 rows (swapped); weight tile: BN rows (normal) or 128 rows (swapped)
   const int PX = p.swap ? 256 : TC_BM;
   const uint32_t a_bytes = PX * p.BK * 2, b_bytes = (p.swap ? 128 : p.BN) * p.BK * 2;
@@ -439,6 +441,7 @@ struct TcStripParams {
   int slot_bytes;           // (PX + 2) * BK * 2 rounded up to 1024
   int swap;                 // 1: 256-pixel segments, weights as the MMA A operand (see TcFwdParams::swap)
   int fold;                 // 1: the three vertical taps are folded into the MMA N dimension (see the kernel comment)
+  int OC, n0;               // output tensor channel pitch and first output channel of this launch (Cout = channels computed here)
   // optional epilogue fusions (normal orientation only)
   const float* head_kernel; // [Cout][2] softmax head (unet_2d_summary.py:221-222): emit logit / prob per pixel
   const float* head_bias;   // [2]
@@ -468,15 +471,18 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   __shared__ uint64_t bar_w, row_full[ST_MAX_RING], row_empty[ST_MAX_RING], bar_tfull[16], bar_tempty[16];
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_scale[128], s_shift[128], s_wd[128];
-  __shared__ __align__(16) uint8_t s_stage[4][4096];             // transpose tiles of the swapped epilogue
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int PX = p.swap ? 256 : 128;                             // pixels per tile (one image-row segment)
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an offset into the __shared__ array (an integer round trip would turn every later access
+  // through this pointer into a generic-space load/store)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int K = p.C0 + p.C1;
   const uint32_t wblk_bytes = p.Cout * p.BK * 2;                 // one (tap, kc) weight tile
   const uint32_t w_bytes = 9u * p.nkc * wblk_bytes;
   uint8_t* s_w = smem;
   uint8_t* s_ring = smem + ((w_bytes + 1023) & ~1023u);
+  const uint32_t row_bytes_ = (uint32_t)p.nkc * p.slot_bytes;
+  uint8_t* s_stage = s_ring + (size_t)p.ring * row_bytes_;       // swapped mode only: 4 x 4 KB transpose tiles behind the ring
   const uint32_t row_bytes = (uint32_t)p.nkc * p.slot_bytes;     // one halo row = nkc chunk boxes
   const uint32_t box_bytes = (uint32_t)(PX + 2) * p.BK * 2u;
   const int acc_cols = p.swap ? 256 : p.Cout;
@@ -490,8 +496,8 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   while (tmem_cols < (uint32_t)(nacc * acc_cols)) tmem_cols <<= 1;
 
   for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
-    s_scale[i] = p.scale ? p.scale[i] : 1.f;
-    s_shift[i] = p.shift ? p.shift[i] : 0.f;
+    s_scale[i] = p.scale ? p.scale[p.n0 + i] : 1.f;
+    s_shift[i] = p.shift ? p.shift[p.n0 + i] : 0.f;
     s_wd[i] = p.head_kernel ? p.head_kernel[2 * i + 1] - p.head_kernel[2 * i] : 0.f;
   }
   if (warp == 0 && lane == 0) {
@@ -534,7 +540,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
         for (int kc = 0; kc < p.nkc; ++kc)
           tma_load_2d(&mapB, &bar_w,
                       s_w + (size_t)(FOLD ? (kc * 3 + tap % 3) * 3 + (2 - tap / 3) : tap * p.nkc + kc) * wblk_bytes,
-                      tap * K + kc * p.BK, 0);   // folded: (kc, dx) groups of three stacked tiles, dy = +1, 0, -1
+                      tap * K + kc * p.BK, p.n0);   // folded: (kc, dx) groups of three stacked tiles, dy = +1, 0, -1
       int pos = 0; uint32_t empty_parity = 0xffffffffu;          // bit i: parity to wait for on row_empty[i]
       const int kc0 = p.C0 / p.BK;
 #ifdef DCB_STRIP_TIMING
@@ -733,19 +739,19 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
         if (p.swap) {
           const bool warp_valid = quarter * 32 < p.Cout;
           const float sc = warp_valid ? s_scale[quarter * 32 + lane] : 0.f, sh = warp_valid ? s_shift[quarter * 32 + lane] : 0.f;
-          const size_t row0 = (((size_t)n * p.H + (h0 + t)) * p.W + w0) * p.Cout + quarter * 32;
-          auto pix_index = [&](int mm) -> long long { return (long long)(row0 + (size_t)mm * p.Cout); };
+          const size_t row0 = (((size_t)n * p.H + (h0 + t)) * p.W + w0) * p.OC + p.n0 + quarter * 32;
+          auto pix_index = [&](int mm) -> long long { return (long long)(row0 + (size_t)mm * p.OC); };
           mbar_wait(&bar_tfull[acc], acc_phase);
           tc_fence_after();
           epilogue_swapped(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols), 256, warp_valid, sc, sh,
-                           p.relu, p.out_f32, p.out, s_stage[quarter], lane, pix_index);
+                           p.relu, p.out_f32, p.out, s_stage + quarter * 4096, lane, pix_index);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_tempty[acc]);
           continue;
         }
         if constexpr (!FUSED) {
-          const size_t oidx = (((size_t)n * p.H + (h0 + t)) * p.W + (w0 + m)) * p.Cout;
+          const size_t oidx = (((size_t)n * p.H + (h0 + t)) * p.W + (w0 + m)) * p.OC + p.n0;
           __nv_bfloat16* orow = p.out + oidx;
           float* orow_f = reinterpret_cast<float*>(p.out) + oidx;
           ST_T(ec0);
@@ -968,23 +974,27 @@ static int swap_min_cout() {
 }
 static bool swap_allowed(int Nout) { return swap_min_cout() > 0 && Nout >= swap_min_cout() && Nout <= 128; }
 
-// strip kernel plan; returns false when the layer is not eligible
-static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, bool fused, TcStripParams& p, size_t& dyn_smem) {
+// strip kernel plan for a launch that computes Nsub of the layer's Nout output channels (Nsub < Nout: the layer is
+// run as Nout / Nsub launches because the weights of all channels do not fit next to a useful halo ring);
+// returns false when the layer is not eligible
+static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, int Nsub, bool fused, TcStripParams& p, size_t& dyn_smem) {
   static const bool disabled = getenv("DCB_NO_STRIP") != nullptr;
   if (disabled) return false;
   if (g.ntaps != 9 || g.zsub > 1 || g.sy != 1) return false;
-  if (g.GW % 128 != 0 || Nout > 128 || Nout % 32 != 0) return false;
+  if (g.GW % 128 != 0 || Nsub > 128 || Nsub % 32 != 0 || Nout % Nsub != 0) return false;
   const int K = C0 + C1;
   const int BK = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
   const int nkc = K / BK;
-  const size_t w_bytes = ((size_t)9 * K * Nout * 2 + 1023) & ~(size_t)1023;
-  const size_t budget = 207 * 1024;
+  const size_t w_bytes = ((size_t)9 * K * Nsub * 2 + 1023) & ~(size_t)1023;
+  // dynamic shared memory: 224 KB minus the 1 KB alignment slack; the swapped epilogue also needs 4 x 4 KB there
+  const size_t budget_all = 223 * 1024, stage_tiles = 4 * 4096;
   // swapped orientation (256-pixel segments, N = 256 per MMA) whenever the image is wide enough
   // the fused head / pool epilogues exist for the normal orientation only
-  int swap = (!fused && swap_allowed(Nout) && g.GW % 256 == 0) ? 1 : 0;
+  int swap = (!fused && swap_allowed(Nsub) && g.GW % 256 == 0) ? 1 : 0;
   int slot = 0, ring = 0;
   for (; swap >= 0; --swap) {
     const int px = swap ? 256 : 128;
+    const size_t budget = budget_all - (swap ? stage_tiles : 0);
     slot = ((px + 2) * BK * 2 + 1023) & ~1023;
     // the MMA reads 128 weight rows starting at each (tap, kc) block: keep those reads inside the allocation
     if (w_bytes + (size_t)4 * nkc * slot <= budget) { ring = (int)((budget - w_bytes) / ((size_t)nkc * slot)); break; }
@@ -992,13 +1002,14 @@ static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, bool fused, T
   if (swap < 0) return false;
   if (ring > ST_MAX_RING) ring = ST_MAX_RING;
   memset(&p, 0, sizeof(p));
-  p.N = g.N; p.H = g.GH; p.W = g.GW; p.C0 = C0; p.C1 = C1; p.BK = BK; p.nkc = nkc; p.Cout = Nout;
+  p.N = g.N; p.H = g.GH; p.W = g.GW; p.C0 = C0; p.C1 = C1; p.BK = BK; p.nkc = nkc; p.Cout = Nsub; p.OC = Nout;
   p.ring = ring; p.slot_bytes = slot; p.swap = swap; p.wsegs = g.GW / (swap ? 256 : 128);
   static const bool no_fold = getenv("DCB_NO_FOLD") != nullptr;
-  p.fold = (!swap && !no_fold && (Nout == 32 || Nout == 64) && g.GH % 2 == 0 && ring >= 4) ? 1 : 0;
+  p.fold = (!swap && !no_fold && (Nsub == 32 || Nsub == 64) && g.GH % 2 == 0 && ring >= 4) ? 1 : 0;
   if (fused && (g.GH % 2 != 0)) return false;          // row pairs of the fused pool must not straddle strips
+  if (Nsub < Nout && !p.fold) return false;            // channel-split launches only pay with the folded issue
   p.gran = (g.GH % 2 == 0) ? 2 : 1;
-  dyn_smem = w_bytes + (size_t)ring * nkc * slot + 1024;
+  dyn_smem = w_bytes + (size_t)ring * nkc * slot + (swap ? stage_tiles : 0) + 1024;
   return true;
 }
 
@@ -1015,7 +1026,9 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
     size_t dyn = 0;
     const bool fused = fuse != nullptr;
     if (fused && (out_f32 || (fuse->pool_out && Nout > 64))) return fail(DCB_ERR_UNSUPPORTED, "fused epilogue not available for this layer");
-    const bool strip_ok = plan_strip(g, C0, C1, Nout, fused, sp, dyn);
+    bool strip_ok = plan_strip(g, C0, C1, Nout, Nout, fused, sp, dyn);
+    static const bool no_nsplit = getenv("DCB_NO_NSPLIT") != nullptr;
+    if (!strip_ok && !fused && !no_nsplit && Nout == 64) strip_ok = plan_strip(g, C0, C1, Nout, 32, fused, sp, dyn);
     if (fused && !strip_ok) return fail(DCB_ERR_UNSUPPORTED, "fused epilogue not available for this layer");
     if (strip_ok) {
       sp.relu = relu; sp.out_f32 = out_f32; sp.out = reinterpret_cast<__nv_bfloat16*>(out); sp.scale = scale; sp.shift = shift;
@@ -1040,26 +1053,28 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
         const int Ktot = 9 * (C0 + C1);
         uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)Nout};
         uint64_t str[1] = {(uint64_t)Ktot * 2};
-        uint32_t box[2] = {(uint32_t)sp.BK, (uint32_t)Nout};
+        uint32_t box[2] = {(uint32_t)sp.BK, (uint32_t)sp.Cout};
         if (int e = make_map(&mB, B, 2, dims, str, box, sp.BK * 2)) return e;
       }
       static bool attr_set_strip = false;
       if (!attr_set_strip) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
         attr_set_strip = true;
       }
       const long long units = (long long)sp.N * sp.wsegs * cdiv(sp.H, sp.gran);
       const int grid = units < sm_count() ? (int)units : sm_count();
-      if (fused && sp.fold) tapgemm_tc_strip_kernel<true, true><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
-      else if (fused) tapgemm_tc_strip_kernel<true, false><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
-      else if (sp.fold) tapgemm_tc_strip_kernel<false, true><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
-      else tapgemm_tc_strip_kernel<false, false><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
-      g_launches += 1;
-      DCB_LAUNCH_OK("tapgemm_tc_strip_kernel");
+      for (sp.n0 = 0; sp.n0 < Nout; sp.n0 += sp.Cout) {          // one launch per group of output channels
+        if (fused && sp.fold) tapgemm_tc_strip_kernel<true, true><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
+        else if (fused) tapgemm_tc_strip_kernel<true, false><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
+        else if (sp.fold) tapgemm_tc_strip_kernel<false, true><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
+        else tapgemm_tc_strip_kernel<false, false><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
+        g_launches += 1;
+        DCB_LAUNCH_OK("tapgemm_tc_strip_kernel");
+      }
 #ifdef DCB_STRIP_TIMING
       if (sp.fold && getenv("DCB_STRIP_TIMING_PRINT")) {
         cudaStreamSynchronize(st);
@@ -1206,7 +1221,9 @@ tapgemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   __shared__ uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_base_smem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an offset into the __shared__ array (an integer round trip would turn every later access
+  // through this pointer into a generic-space load/store)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int K = p.C0 + p.C1;
   const int ktiles = (K + 127) / 128, ntiles = p.Nout / p.BN;
   const int num_ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
@@ -1380,7 +1397,9 @@ tapgemm_tc_wgrad_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const _
   __shared__ uint64_t row_full[WS_RING], row_empty[WS_RING], g_full[WS_GRING], g_empty[WS_GRING], bar_done;
   __shared__ uint32_t tmem_base_smem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an offset into the __shared__ array (an integer round trip would turn every later access
+  // through this pointer into a generic-space load/store)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr uint32_t A_SLOT = 5120;                       // 66 (+ spill) rows x 64 B, 1024-aligned
   const uint32_t row_bytes = (uint32_t)p.nsrc * A_SLOT;
   const uint32_t g_slot = (uint32_t)WS_PX * p.Nout * 2;   // 4 KB or 8 KB

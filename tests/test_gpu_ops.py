@@ -50,6 +50,8 @@ CONV_CASES = [
     (1, 9, 512, 32, 32, 32),
     (2, 11, 64, 32, 0, 64),
     (4, 128, 128, 32, 32, 32),
+    (2, 6, 128, 64, 64, 64),      # weights too large for one strip launch: two launches of 32 output channels
+    (1, 4, 256, 64, 64, 64),
     # enough 256-pixel tiles for the swapped (weights-as-A) orientation of the generic kernel
     (8, 64, 64, 64, 0, 128),
     (5, 48, 80, 64, 64, 64),
