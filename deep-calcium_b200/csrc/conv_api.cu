@@ -62,9 +62,56 @@ __global__ void prep_convT_kernel(const float* __restrict__ w, int Cin, int Cout
   }
 }
 
+// all layers of a model in ONE launch (blockIdx.y = layer): the per-step refresh of the bf16 kernel-layout copies after
+// the optimizer update is ~20 tiny launches otherwise.  desc (device memory, 5 x int64 per layer):
+// {w, w_fwd (or 0), w_dgrad (or 0), Cin | Cout << 32, kind (0 conv3x3, 1 convT2x2)}
+template <typename T>
+__global__ void prep_batch_kernel(const long long* __restrict__ desc, int nmajor) {
+  const long long* d = desc + 5LL * blockIdx.y;
+  const float* w = reinterpret_cast<const float*>(d[0]);
+  T* wf = reinterpret_cast<T*>(d[1]);
+  T* wd = reinterpret_cast<T*>(d[2]);
+  const int Cin = (int)(d[3] & 0xffffffffLL), Cout = (int)(d[3] >> 32);
+  const bool convT = d[4] != 0;
+  const long long n = (convT ? 4LL : 9LL) * Cin * Cout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = w[i];
+    if (!convT) {
+      const int co = (int)(i % Cout), ci = (int)((i / Cout) % Cin), t = (int)(i / ((long long)Cout * Cin));
+      if (nmajor) {
+        if (wf) wf[((long long)co * 9 + t) * Cin + ci] = from_f32<T>(v);
+        if (wd) wd[((long long)ci * 9 + (8 - t)) * Cout + co] = from_f32<T>(v);
+      } else {
+        if (wf) wf[i] = from_f32<T>(v);
+        if (wd) wd[((long long)(8 - t) * Cout + co) * Cin + ci] = from_f32<T>(v);
+      }
+    } else {
+      const int ci = (int)(i % Cin), co = (int)((i / Cin) % Cout), t = (int)(i / ((long long)Cout * Cin));
+      if (nmajor) {
+        if (wf) wf[i] = from_f32<T>(v);
+        if (wd) wd[((long long)ci * 4 + t) * Cout + co] = from_f32<T>(v);
+      } else {
+        if (wf) wf[((long long)t * Cin + ci) * Cout + co] = from_f32<T>(v);
+        if (wd) wd[i] = from_f32<T>(v);
+      }
+    }
+  }
+}
+
 }  // namespace dcb
 
 using namespace dcb;
+
+extern "C" int dcb_prep_weights_batch(int dtype, const long long* desc_dev, int count, dcb_stream_t stream) {
+  DCB_CHECK_ARG(desc_dev && count > 0 && count <= 65535, "dcb_prep_weights_batch: bad arguments");
+  const dim3 grid(96, count);
+  if (dtype == DCB_F32) prep_batch_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(desc_dev, 0);
+  else if (dtype == DCB_BF16) prep_batch_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(desc_dev, 1);
+  else return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+  g_launches += 1;
+  DCB_LAUNCH_OK("prep_batch_kernel");
+  return DCB_OK;
+}
 
 extern "C" int dcb_prep_conv3x3_weights(int dtype, const float* w, int Cin, int Cout, void* w_fwd, void* w_dgrad,
                                         dcb_stream_t stream) {

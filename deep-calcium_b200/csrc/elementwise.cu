@@ -137,6 +137,57 @@ bn_apply_kernel(const T* __restrict__ x, long long M, int C, const float* __rest
   }
 }
 
+// Training forward in one pass over the data: every CTA derives the per-channel scale / shift from the batch sums in
+// its prologue (C <= 2048 channels: a few microseconds of fp64 per CTA instead of a separate launch per layer);
+// block 0 also publishes scale / shift / mean / rstd for the backward pass and updates the moving statistics.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+bn_finalize_apply_kernel(const T* __restrict__ x, long long M, int C, const double* __restrict__ sums, long long M_total,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+                         float* moving_mean, float* moving_var, float* scale_out, float* shift_out, float* mean_out,
+                         float* rstd_out, int relu, float p_drop, unsigned long long seed,
+                         const unsigned long long* __restrict__ seed_dev, uint32_t layer, T* __restrict__ y) {
+  extern __shared__ float s_coef[];
+  float* s_sc = s_coef; float* s_sh = s_coef + C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double mean = sums[c] / (double)M_total;
+    double var = sums[C + c] / (double)M_total - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * rstd;
+    const float sh = beta[c] - (float)mean * sc;
+    s_sc[c] = sc; s_sh[c] = sh;
+    if (blockIdx.x == 0) {
+      scale_out[c] = sc; shift_out[c] = sh; mean_out[c] = (float)mean; rstd_out[c] = rstd;
+      if (moving_mean) {   // Keras: moving <- moving*m + batch*(1-m), biased batch variance
+        moving_mean[c] = moving_mean[c] * momentum + (float)mean * (1.f - momentum);
+        moving_var[c] = moving_var[c] * momentum + (float)var * (1.f - momentum);
+      }
+    }
+  }
+  __syncthreads();
+  if (seed_dev) seed ^= *seed_dev;
+  const long long nv = M * C / VEC;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i * VEC) % C);
+    float v[VEC];
+    loadv<T, VEC>(x + i * VEC, v);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      v[j] = fmaf(v[j], s_sc[c + j], s_sh[c + j]);
+      if (relu) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (p_drop > 0.f) {
+#pragma unroll
+      for (int h = 0; h < VEC / 4; ++h) {
+        const float4 k = dropout_scale4(seed, layer, (unsigned long long)(i * (VEC / 4) + h), p_drop);
+        v[4 * h] *= k.x; v[4 * h + 1] *= k.y; v[4 * h + 2] *= k.z; v[4 * h + 3] *= k.w;
+      }
+    }
+    storev<T, VEC>(y + i * VEC, v);
+  }
+}
+
 // ---------------------------------------------------------------- BN + ReLU (+dropout) backward
 // dz = dY * keepscale * [x*scale+shift > 0];  sums[c] += dz ; sums[C+c] += dz * xhat, xhat = (x-mean)*rstd
 // 8 channels per thread, 2 independent rows in flight.
@@ -668,6 +719,30 @@ extern "C" int dcb_bn_apply(int dtype, const void* x, long long M, int C, const 
   }
   g_launches += 1;
   DCB_LAUNCH_OK("bn_apply_kernel");
+  return DCB_OK;
+}
+
+extern "C" int dcb_bn_finalize_apply(int dtype, const void* x, long long M, int C, const double* sums, long long M_total,
+                                     const float* gamma, const float* beta, float eps, float momentum, float* moving_mean,
+                                     float* moving_var, float* scale, float* shift, float* mean, float* rstd, int relu,
+                                     float p_drop, unsigned long long seed, const unsigned long long* seed_dev, unsigned layer,
+                                     void* y, dcb_stream_t stream) {
+  DCB_CHECK_ARG(x && y && sums && gamma && beta && scale && shift && mean && rstd && M > 0 && C > 0 && C % 4 == 0 && C <= 2048,
+                "dcb_bn_finalize_apply: bad arguments (C %d)", C);
+  DCB_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "dcb_bn_finalize_apply: p_drop %f outside [0, 1)", p_drop);
+  if (M_total <= 0) M_total = M;
+  const size_t coef_smem = 2 * (size_t)C * sizeof(float);
+  if (C % 8 == 0) {
+    DISPATCH_T(dtype, bn_finalize_apply_kernel<T, 8><<<ew_grid(M * C / 8, 256), 256, coef_smem, (cudaStream_t)stream>>>(
+        (const T*)x, M, C, sums, M_total, gamma, beta, eps, momentum, moving_mean, moving_var, scale, shift, mean, rstd, relu,
+        p_drop, seed, seed_dev, layer, (T*)y);)
+  } else {
+    DISPATCH_T(dtype, bn_finalize_apply_kernel<T, 4><<<ew_grid(M * C / 4, 256), 256, coef_smem, (cudaStream_t)stream>>>(
+        (const T*)x, M, C, sums, M_total, gamma, beta, eps, momentum, moving_mean, moving_var, scale, shift, mean, rstd, relu,
+        p_drop, seed, seed_dev, layer, (T*)y);)
+  }
+  g_launches += 1;
+  DCB_LAUNCH_OK("bn_finalize_apply_kernel");
   return DCB_OK;
 }
 

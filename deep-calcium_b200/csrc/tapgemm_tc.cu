@@ -722,6 +722,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
     long long ep_last = 0;
     unsigned long long ep_acc[5] = {0, 0, 0, 0, 0};
 #endif
+    const float head_b = (FUSED && p.head_kernel) ? (p.head_bias[1] - p.head_bias[0]) : 0.f;   // hoisted: two global loads
     uint32_t pool_prev[2][16];                                   // previous row (bf16 pairs) for the fused 2x2 max-pool
 #pragma unroll
     for (int q = 0; q < 16; ++q) { pool_prev[0][q] = 0; pool_prev[1][q] = 0; }
@@ -810,7 +811,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
           ep_last = ec1;
 #endif
           const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.Cout);
-          float zacc = p.head_kernel ? (p.head_bias[1] - p.head_bias[0]) : 0.f;
+          float zacc = head_b;
   #pragma unroll
           for (int cb = 0; cb < 4; ++cb) {
             const int c = cb * 32;
@@ -890,6 +891,178 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
     if (lane == 0 && quarter == 0 && eset < 2)
       for (int q = 0; q < 5; ++q) g_strip_dbg2[blockIdx.x * 16 + 2 + 5 * eset + q] = ep_acc[q];
 #endif
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+
+// ====================================================================================== flat halo-tile kernel
+// conv3x3 for NARROW images (W <= 64: every level below full resolution of a 128^2 training crop, the deep
+// levels of a 512^2 image), where a 128-pixel row segment does not exist and the generic kernel re-loads every
+// activation tile nine times (once per tap) through L2.
+//   * The image is viewed with a one-pixel zero border per row: padded width Wp = W + 2, flattened position
+//     f = y * Wp + (x + 1).  In that view EVERY tap is a constant offset: tap (dy, dx) of position f is position
+//     f + dy * Wp + dx.  A work item is NT consecutive positions of one image x 128 output channels.
+//   * Per 64-channel chunk of K the producer loads ONE pixel buffer - R whole image rows as a single TMA box
+//     [64 ch x Wp px x R rows] starting at x = -1, so the zero border (and the rows above / below the image) come
+//     from the TMA out-of-bounds fill - and the nine taps are nine row-shifted descriptors into it (the swizzle is a
+//     function of the absolute shared-memory address, profiles/r1_umma_row_shift_probe.log).
+//   * Swapped orientation: the 128 output channels are the MMA M rows (weights = A operand, streamed in groups of
+//     three taps: 3 x [128 x 64] per barrier), the NT positions are the MMA N columns (B operand), so every MMA is
+//     N = NT = 192..256 wide and one barrier wait / commit is amortised over 12 MMAs.
+//   * Border positions (x = -1, x = W) are computed and thrown away by the epilogue (2 / Wp of the work).
+struct TcFlatParams {
+  int N, H, W, Wp;
+  int C0, C1, nkc;          // K chunks of 64 channels over both sources
+  int Cout, mtiles;         // output channels, ceil(Cout / 128)
+  int NT, ptiles;           // positions per tile, tiles per image
+  int R;                    // image rows per pixel buffer
+  int wrows;                // rows of the weight box = min(Cout, 128)
+  uint32_t pbuf_bytes;      // R * Wp * 128 rounded up to 1024
+  int relu, out_f32;
+  void* out;
+  const float* scale;
+  const float* shift;
+};
+constexpr int FL_THREADS = 192;
+constexpr uint32_t FL_WSLOT = 3u * 128u * 128u;   // three [128 x 64] bf16 weight tiles
+
+__global__ void __launch_bounds__(FL_THREADS, 1)
+tapgemm_tc_flat_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                       const __grid_constant__ CUtensorMap mapB, const TcFlatParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t pb_full[2], pb_empty[2], w_full[2], w_empty[2], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_base_smem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_pb = smem;                                   // 2 pixel buffers
+  uint8_t* s_w = s_pb + 2u * p.pbuf_bytes;                // 2 weight slots
+  uint8_t* s_stage = s_w + 2u * FL_WSLOT;                 // 4 x 4 KB transpose tiles of the epilogue
+  const int K = p.C0 + p.C1;
+  const int num_items = p.N * p.ptiles * p.mtiles;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * (uint32_t)p.NT) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA0);
+    if (p.C1 > 0) tma_prefetch_desc(&mapA1);
+    tma_prefetch_desc(&mapB);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&pb_full[i], 1); mbar_init(&pb_empty[i], 1); mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1);
+      mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(&tmem_base_smem, tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  // item -> (image, position tile, channel tile); channel tiles of one position tile are neighbours (pixels stay in L2)
+  auto decode = [&](int item, int& n, int& f0, int& mt, int& y_lo) {
+    mt = item % p.mtiles; item /= p.mtiles;
+    const int pt = item % p.ptiles; n = item / p.ptiles;
+    f0 = pt * p.NT;
+    const int a = f0 - p.Wp - 1;                          // lowest position any tap of the tile reads (may be < 0)
+    y_lo = a >= 0 ? a / p.Wp : -((-a + p.Wp - 1) / p.Wp);
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const int kc0 = p.C0 / 64;
+      int pb = 0, ws = 0; uint32_t pb_par = 0, ws_par = 0;   // parities of the NEXT use of each slot's empty barrier
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int n, f0, mt, y_lo;
+        decode(item, n, f0, mt, y_lo);
+        for (int kc = 0; kc < p.nkc; ++kc) {
+          const bool second = kc >= kc0;
+          const int cc = (second ? kc - kc0 : kc) * 64;
+          mbar_wait(&pb_empty[pb], ((pb_par >> pb) & 1u) ^ 1u);
+          pb_par ^= 1u << pb;
+          mbar_arrive_expect_tx(&pb_full[pb], (uint32_t)p.R * p.Wp * 128u);
+          tma_load_4d(second ? &mapA1 : &mapA0, &pb_full[pb], s_pb + (size_t)pb * p.pbuf_bytes, cc, -1, y_lo, n);
+          pb ^= 1;
+          for (int g = 0; g < 3; ++g) {
+            mbar_wait(&w_empty[ws], ((ws_par >> ws) & 1u) ^ 1u);
+            ws_par ^= 1u << ws;
+            mbar_arrive_expect_tx(&w_full[ws], 3u * (uint32_t)p.wrows * 128u);
+            for (int t = 0; t < 3; ++t)
+              tma_load_2d(&mapB, &w_full[ws], s_w + (size_t)ws * FL_WSLOT + (size_t)t * 16384u, (g * 3 + t) * K + kc * 64, mt * 128);
+            ws ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(128, p.NT, 0, 0);
+      const uint64_t dbase = make_smem_desc(0, 16, 1024, SWZ_128B);
+      const uint32_t pb16 = smem_u32(s_pb) >> 4, w16 = smem_u32(s_w) >> 4, pbuf16 = p.pbuf_bytes >> 4;
+      int pb = 0, ws = 0; uint32_t pb_par = 0, ws_par = 0;
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        int n, f0, mt, y_lo;
+        decode(item, n, f0, mt, y_lo);
+        const uint32_t acc = it & 1u;
+        mbar_wait(&bar_tempty[acc], ((it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.NT;
+        const int base_row = f0 - y_lo * p.Wp;             // buffer row of the tile's first position (>= Wp + 1)
+        uint32_t accf = 0;
+        for (int kc = 0; kc < p.nkc; ++kc) {
+          mbar_wait(&pb_full[pb], (pb_par >> pb) & 1u);
+          pb_par ^= 1u << pb;
+          const uint32_t prow16 = pb16 + (uint32_t)pb * pbuf16 + (uint32_t)base_row * 8u;   // 128-byte rows = 8 x 16 B
+          for (int g = 0; g < 3; ++g) {
+            mbar_wait(&w_full[ws], (ws_par >> ws) & 1u);
+            ws_par ^= 1u << ws;
+            tc_fence_after();
+            const int dyo = (g - 1) * p.Wp;                // taps g*3 .. g*3+2 share dy = g - 1
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              const uint64_t da = dbase + (w16 + (uint32_t)ws * (FL_WSLOT >> 4) + (uint32_t)t * 1024u);
+              const uint64_t db = dbase + (uint32_t)((int)prow16 + (dyo + t - 1) * 8);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accf);
+                accf = 1u;
+              }
+            }
+            umma_commit(&w_empty[ws]);
+            ws ^= 1;
+          }
+          umma_commit(&pb_empty[pb]);
+          pb ^= 1;
+        }
+        umma_commit(&bar_tfull[acc]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      int n, f0, mt, y_lo;
+      decode(item, n, f0, mt, y_lo);
+      const uint32_t acc = it & 1u;
+      const int ch0 = mt * 128 + quarter * 32;             // first output channel of this warp
+      const bool warp_valid = ch0 < p.Cout;
+      const float sc = (warp_valid && p.scale) ? p.scale[ch0 + lane] : 1.f, sh = (warp_valid && p.shift) ? p.shift[ch0 + lane] : 0.f;
+      auto pix_index = [&](int mm) -> long long {
+        const int f = f0 + mm, y = f / p.Wp, xp = f - y * p.Wp;
+        if (y >= p.H || xp < 1 || xp > p.W) return -1;
+        return (long long)((((size_t)n * p.H + y) * p.W + (xp - 1)) * p.Cout + ch0);
+      };
+      mbar_wait(&bar_tfull[acc], (it >> 1) & 1u);
+      tc_fence_after();
+      epilogue_swapped(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)p.NT, p.NT, warp_valid, sc, sh, p.relu,
+                       p.out_f32, p.out, s_stage + quarter * 4096, lane, pix_index);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1013,6 +1186,68 @@ static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, int Nsub, boo
   return true;
 }
 
+
+// flat halo-tile kernel: plan + launch; returns DCB_ERR_UNSUPPORTED (nothing launched) when the layer is not eligible
+static int run_tc_flat(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* B, int Nout, void* out,
+                       const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st) {
+  static const bool disabled = getenv("DCB_NO_FLAT") != nullptr;
+  if (disabled || g.ntaps != 9 || g.zsub > 1 || g.sy != 1) return DCB_ERR_UNSUPPORTED;
+  if (C0 % 64 != 0 || C1 % 64 != 0 || Nout < 64 || g.GW > 64 || g.GW < 16) return DCB_ERR_UNSUPPORTED;
+  const int Wp = g.GW + 2;
+  const long long positions = (long long)g.GH * Wp;
+  if (positions < 512) return DCB_ERR_UNSUPPORTED;     // tiny maps: too much of a 192..256-position tile would be padding
+  TcFlatParams p;
+  memset(&p, 0, sizeof(p));
+  const size_t budget = 223 * 1024 - 2 * (size_t)FL_WSLOT - 4 * 4096;
+  int NT = 0, R = 0; uint32_t pbuf = 0;
+  for (int cand : {256, 192, 128}) {
+    R = (cand + 3 * Wp + 1 + Wp - 1) / Wp;
+    pbuf = ((uint32_t)R * Wp * 128u + 1023u) & ~1023u;
+    if (R <= 256 && 2 * (size_t)pbuf <= budget) { NT = cand; break; }
+  }
+  if (!NT) return DCB_ERR_UNSUPPORTED;
+  // Measured (scripts/one_layer.py, profiles/r1_flat_kernel_ab.txt): the coarse work items (NT positions x 128 channels x all
+  // of K) only pay when every SM gets several of them; otherwise the generic kernel's finer tiles balance better.
+  {
+    static const bool force = getenv("DCB_FLAT_ALWAYS") != nullptr;
+    const long long items = (long long)g.N * ((positions + NT - 1) / NT) * cdiv(Nout, 128);
+    if (!force && items < 4LL * sm_count()) return DCB_ERR_UNSUPPORTED;
+  }
+  p.N = g.N; p.H = g.GH; p.W = g.GW; p.Wp = Wp; p.C0 = C0; p.C1 = C1; p.nkc = (C0 + C1) / 64;
+  p.Cout = Nout; p.mtiles = cdiv(Nout, 128); p.NT = NT; p.ptiles = (int)((positions + NT - 1) / NT); p.R = R;
+  p.wrows = Nout < 128 ? Nout : 128; p.pbuf_bytes = pbuf;
+  p.relu = relu; p.out_f32 = out_f32; p.out = out; p.scale = scale; p.shift = shift;
+  CUtensorMap mA0, mA1, mB;
+  auto mk = [&](CUtensorMap* m, const void* ptr, int C) -> int {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.N};
+    uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)g.IW * C * 2, (uint64_t)g.IH * g.IW * C * 2};
+    uint32_t box[4] = {64u, (uint32_t)Wp, (uint32_t)R, 1u};
+    return make_map(m, ptr, 4, dims, str, box, 128);
+  };
+  if (int e = mk(&mA0, s0, C0)) return e;
+  if (C1 > 0) { if (int e = mk(&mA1, s1, C1)) return e; } else mA1 = mA0;
+  {
+    const int Ktot = 9 * (C0 + C1);
+    uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)Nout};
+    uint64_t str[1] = {(uint64_t)Ktot * 2};
+    uint32_t box[2] = {64u, (uint32_t)p.wrows};
+    if (int e = make_map(&mB, B, 2, dims, str, box, 128)) return e;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const size_t dyn = 2 * (size_t)pbuf + 2 * (size_t)FL_WSLOT + 4 * 4096 + 1024;
+  const int items = p.N * p.ptiles * p.mtiles;
+  const int grid = items < sm_count() ? items : sm_count();
+  tapgemm_tc_flat_kernel<<<grid, FL_THREADS, dyn, st>>>(mA0, mA1, mB, p);
+  g_launches += 1;
+  DCB_LAUNCH_OK("tapgemm_tc_flat_kernel");
+  return DCB_OK;
+}
+
 // fuse != nullptr: the caller wants the head and/or the 2x2 max-pool computed in the conv epilogue; returns
 // DCB_ERR_UNSUPPORTED (without launching) when this layer shape cannot take the fused path.
 int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* B, int Nout, void* out,
@@ -1095,6 +1330,10 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
 #endif
       return DCB_OK;
     }
+  }
+  {
+    const int e = run_tc_flat(g, s0, C0, s1, C1, B, Nout, out, scale, shift, relu, out_f32, st);
+    if (e != DCB_ERR_UNSUPPORTED) return e;
   }
   TcFwdParams p;
   memset(&p, 0, sizeof(p));

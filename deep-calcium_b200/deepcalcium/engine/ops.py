@@ -160,6 +160,12 @@ def prep_convT2x2_weights(w, w_fwd, w_dgrad, dtype):
 
 
 # ---------------------------------------------------------------- BatchNorm
+def prep_weights_batch(desc_dev, count, dtype):
+    """desc_dev: int64 CUDA tensor [count, 5] (see dcb_prep_weights_batch)."""
+    _chk(desc_dev, torch.int64)
+    call('dcb_prep_weights_batch', c_int(DT[dtype]), ptr(desc_dev), c_int(count), stream_ptr())
+
+
 def bn_fold(gamma, beta, mean, var, bias, scale, shift, eps=1e-3):
     call('dcb_bn_fold', ptr(gamma), ptr(beta), ptr(mean), ptr(var), ptr(bias), c_int(gamma.numel()), c_f(eps),
          ptr(scale), ptr(shift), stream_ptr())
@@ -179,6 +185,14 @@ def bn_apply(x, scale, shift, y, relu=True, p_drop=0., seed=0, seed_dev=None, la
     C = x.shape[-1]
     call('dcb_bn_apply', _dt(x), ptr(x), c_ll(x.numel() // C), c_int(C), ptr(scale), ptr(shift), c_int(int(relu)),
          c_f(p_drop), c_ull(seed), ptr(seed_dev), c_uint(layer), ptr(y), stream_ptr())
+
+
+def bn_finalize_apply(x, sums, M_total, gamma, beta, momentum, moving_mean, moving_var, scale, shift, mean, rstd, y,
+                      relu=True, p_drop=0., seed=0, seed_dev=None, layer=0, eps=1e-3):
+    C = x.shape[-1]
+    call('dcb_bn_finalize_apply', _dt(x), ptr(x), c_ll(x.numel() // C), c_int(C), ptr(sums), c_ll(M_total), ptr(gamma),
+         ptr(beta), c_f(eps), c_f(momentum), ptr(moving_mean), ptr(moving_var), ptr(scale), ptr(shift), ptr(mean), ptr(rstd),
+         c_int(int(relu)), c_f(p_drop), c_ull(seed), ptr(seed_dev), c_uint(layer), ptr(y), stream_ptr())
 
 
 def bn_bwd_reduce(dy, ldy, offy, x, scale, shift, mean, rstd, sums, p_drop=0., seed=0, seed_dev=None, layer=0):

@@ -39,6 +39,7 @@ class UNetEngine(object):
         self._inputs = self._wire()
         self._weights_dirty = True
         self._sessions = {}
+        self._prep_tables = {}
         self.iteration = 0
         self.launches = 0
         self.comm = None          # engine.dist.Comm for data-parallel training (None = single GPU)
@@ -149,22 +150,42 @@ class UNetEngine(object):
         self.step_state.zero_()
         self.iteration = 0
 
+    def _prep_table(self, for_training):
+        """device table for dcb_prep_weights_batch (built once per mode; the buffers are static)."""
+        tab = self._prep_tables.get(for_training)
+        if tab is None:
+            rows = []
+            for blk in self.spec.blocks:
+                if blk.kind == 'head':
+                    continue
+                n = blk.name
+                k = self.P[n + '/kernel']
+                if blk.kind == 'conv':
+                    wf = self.w_fwd[n] if self.w_fwd[n] is not k else None
+                    wd = self.w_dgrad[n] if for_training else None
+                else:
+                    wf = self.w_fwd[n]
+                    wd = self.w_dgrad[n] if (for_training and self.w_dgrad[n] is not k) else None
+                if wf is None and wd is None:
+                    continue
+                cin, cout = (k.shape[2], k.shape[3]) if blk.kind == 'conv' else (k.shape[3], k.shape[2])
+                rows.append([k.data_ptr(), wf.data_ptr() if wf is not None else 0, wd.data_ptr() if wd is not None else 0,
+                             cin | (cout << 32), 0 if blk.kind == 'conv' else 1])
+            tab = (torch.tensor(rows, dtype=torch.int64, device=self.dev), len(rows)) if rows else (None, 0)
+            self._prep_tables[for_training] = tab
+        return tab
+
     def _prepare_weights(self, for_training):
         """fold BN for inference and (re)build the kernel-layout weight copies."""
+        tab, count = self._prep_table(for_training)
+        if count:
+            ops.prep_weights_batch(tab, count, self.dtype)
+        if for_training:
+            return
         for blk in self.spec.blocks:
             if blk.kind == 'head':
                 continue
             n = blk.name
-            k = self.P[n + '/kernel']
-            if blk.kind == 'conv':
-                wf = self.w_fwd[n] if self.w_fwd[n] is not k else None
-                wd = self.w_dgrad[n] if for_training else None
-                if wf is not None or wd is not None:
-                    ops.prep_conv3x3_weights(k, wf, wd, self.dtype)
-            else:
-                wf = self.w_fwd[n]
-                wd = self.w_dgrad[n] if (for_training and self.w_dgrad[n] is not k) else None
-                ops.prep_convT2x2_weights(k, wf, wd, self.dtype)
             if not for_training:
                 ops.bn_fold(self.P[n + '/gamma'], self.P[n + '/beta'], self.P[n + '/moving_mean'],
                             self.P[n + '/moving_var'], self.P[n + '/bias'], self.inf_scale[n], self.inf_shift[n], BN_EPS)
@@ -360,10 +381,9 @@ class UNetEngine(object):
             sums = self.dbl[st['off_f']:st['off_f'] + 2 * blk.cout]
             ops.bn_stats(raw[n], sums)
             self._allreduce(sums)                       # SyncBN: statistics of the global batch
-            ops.bn_finalize(sums, M * world, self.P[n + '/gamma'], self.P[n + '/beta'], mom, self.P[n + '/moving_mean'],
-                            self.P[n + '/moving_var'], st['scale'], st['shift'], st['mean'], st['rstd'], BN_EPS)
-            ops.bn_apply(raw[n], st['scale'], st['shift'], act[n], True, self._dropout_p(n, dropout), seed_base, seed_dev,
-                         layer_id[n])
+            ops.bn_finalize_apply(raw[n], sums, M * world, self.P[n + '/gamma'], self.P[n + '/beta'], mom,
+                                  self.P[n + '/moving_mean'], self.P[n + '/moving_var'], st['scale'], st['shift'], st['mean'],
+                                  st['rstd'], act[n], True, self._dropout_p(n, dropout), seed_base, seed_dev, layer_id[n], BN_EPS)
             if n in ('enc0b', 'enc1b', 'enc2b', 'enc3b'):
                 ops.maxpool2x2(act[n], act['pool%d' % blk.level])
         # ---------------- head + loss + its gradient

@@ -131,6 +131,10 @@ int dcb_prep_conv3x3_weights(int dtype, const float* w, int Cin, int Cout, void*
                              dcb_stream_t stream);
 int dcb_prep_convT2x2_weights(int dtype, const float* w, int Cin, int Cout, void* w_fwd, void* w_dgrad,
                               dcb_stream_t stream);
+/* every layer of a model in one launch.  desc_dev: device array of `count` records of 5 x int64
+ * {w (fp32 master), w_fwd or 0, w_dgrad or 0, Cin | Cout << 32, kind: 0 = conv3x3 (HWIO), 1 = convT2x2 (2,2,Cout,Cin)};
+ * layouts written exactly as by the two single-layer calls above */
+int dcb_prep_weights_batch(int dtype, const long long* desc_dev, int count, dcb_stream_t stream);
 
 /* ---- BatchNormalization (Keras 2.0.6: eps 1e-3, biased batch variance) ---- */
 /* inference fold: scale = gamma*rsqrt(var+eps), shift = beta + (bias - mean)*scale */
@@ -148,6 +152,13 @@ int dcb_bn_finalize(const double* sums, long long M, int C, const float* gamma, 
 int dcb_bn_apply(int dtype, const void* x, long long M, int C, const float* scale, const float* shift, int relu,
                  float p_drop, unsigned long long seed, const unsigned long long* seed_dev, unsigned layer, void* y,
                  dcb_stream_t stream);
+/* dcb_bn_finalize + dcb_bn_apply in one launch (training forward): the statistics of M_total rows (0 = M; the
+ * data-parallel caller all-reduces `sums` first) become scale / shift inside the kernel */
+int dcb_bn_finalize_apply(int dtype, const void* x, long long M, int C, const double* sums, long long M_total,
+                          const float* gamma, const float* beta, float eps, float momentum, float* moving_mean,
+                          float* moving_var, float* scale, float* shift, float* mean, float* rstd, int relu,
+                          float p_drop, unsigned long long seed, const unsigned long long* seed_dev, unsigned layer,
+                          void* y, dcb_stream_t stream);
 /* backward of dropout+ReLU+BN given dy (fp32, row stride ldy, channel offset offy) and the raw conv output x:
  * reduce accumulates sums[0..C)=sum dz, sums[C..2C)=sum dz*xhat; apply writes d_raw and dgamma/dbeta.
  * Data-parallel use: all-reduce `sums` between the two calls, pass M_total = rows over all ranks

@@ -1,6 +1,8 @@
 """Per-kernel parity on the GPU through the C ABI (deepcalcium.engine.ops) against float64 CPU
 references built from the oracle's layer arithmetic (torch CPU + autograd).
 fp32 = CUDA-core check kernels (tolerance 1e-4 class), bf16 = tcgen05 kernels (bf16 tolerance)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -31,6 +33,9 @@ def tol(precision, scale=1.0):
 def nhwc_to_nchw(a):
     return torch.as_tensor(a).permute(0, 3, 1, 2).contiguous()
 
+
+# the flat halo-tile kernel is selected by a problem-size policy; the unit tests force it on for the eligible shapes
+os.environ.setdefault('DCB_FLAT_ALWAYS', '1')
 
 CONV_CASES = [
     # N, H, W, C0, C1, Cout
@@ -362,3 +367,53 @@ def test_keras_adam_kernel(cuda):
     assert state[0].item() == 3
     assert np.allclose(pd.cpu().numpy(), p, atol=2e-6)
     assert np.allclose(vd.cpu().numpy(), v, rtol=1e-4, atol=1e-12)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_bn_finalize_apply_equals_the_two_separate_calls(cuda, precision):
+    from deepcalcium.engine import ops
+    dt = DT[precision]
+    rng = np.random.default_rng(3)
+    for M, C in ((700, 32), (96, 4), (64, 512)):
+        x = dev(rng.standard_normal((M, C)) * 2 + 0.5, dt)
+        gamma = dev(rng.uniform(0.5, 1.5, C)); beta = dev(rng.standard_normal(C))
+        mm0 = rng.standard_normal(C).astype(np.float32); mv0 = rng.uniform(0.5, 1.5, C).astype(np.float32)
+        sums = torch.zeros(2 * C, dtype=torch.float64, device='cuda')
+        ops.bn_stats(x, sums)
+        outs = []
+        for fused in (False, True):
+            mm, mv = dev(mm0), dev(mv0)
+            sc, sh, mu, rs = (torch.empty(C, device='cuda') for _ in range(4))
+            y = torch.empty_like(x)
+            if fused:
+                ops.bn_finalize_apply(x, sums, M, gamma, beta, 0.99, mm, mv, sc, sh, mu, rs, y, True, 0.25, 77, None, 5)
+            else:
+                ops.bn_finalize(sums, M, gamma, beta, 0.99, mm, mv, sc, sh, mu, rs)
+                ops.bn_apply(x, sc, sh, y, True, 0.25, 77, None, 5)
+            outs.append([t.clone() for t in (y, sc, sh, mu, rs, mm, mv)])
+        for a, b in zip(*outs):
+            assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_prep_weights_batch_equals_per_layer_calls(cuda, precision):
+    from deepcalcium.engine import ops
+    dt = DT[precision]
+    rng = np.random.default_rng(4)
+    layers = [('conv', 32, 64), ('convT', 64, 32), ('conv', 1, 32), ('conv', 96, 32)]
+    rows, ref, got = [], [], []
+    for kind, cin, cout in layers:
+        if kind == 'conv':
+            w = dev(rng.standard_normal((3, 3, cin, cout)))
+            n = 9 * cin * cout
+        else:
+            w = dev(rng.standard_normal((2, 2, cout, cin)))
+            n = 4 * cin * cout
+        wf, wd, wf2, wd2 = (torch.zeros(n, dtype=dt, device='cuda') for _ in range(4))
+        (ops.prep_conv3x3_weights if kind == 'conv' else ops.prep_convT2x2_weights)(w, wf, wd, dt)
+        rows.append([w.data_ptr(), wf2.data_ptr(), wd2.data_ptr(), cin | (cout << 32), 0 if kind == 'conv' else 1])
+        ref += [wf, wd]; got += [wf2, wd2]; rows[-1].append(w)      # keep w alive
+    tab = torch.tensor([r[:5] for r in rows], dtype=torch.int64, device='cuda')
+    ops.prep_weights_batch(tab, len(rows), dt)
+    for a, b in zip(ref, got):
+        assert torch.equal(a, b)
