@@ -226,6 +226,39 @@ void launch_reduce_splits(const float* part, int splits, size_t n, float* out, c
   else reduce_splits_kernel<<<cdiv((long long)n, 256), 256, 0, st>>>(part, splits, n, out);
 }
 
+// same reduction for a partial tensor of nrows x row_len elements whose rows land out_row_stride apart in `out`
+// (a K-block of a larger dW[tap][K_total][N]): fixed-order sum over the splits
+__global__ void __launch_bounds__(256)
+reduce_splits_rows_kernel(const float* __restrict__ part, int splits, int nrows, size_t row_len, float* __restrict__ out,
+                          size_t out_row_stride) {
+  constexpr int E = 32, L = 8;
+  __shared__ float s_part[L][E];
+  const int e = threadIdx.x % E, j = threadIdx.x / E;
+  const size_t n = (size_t)nrows * row_len;
+  const size_t i = (size_t)blockIdx.x * E + e;
+  float a0 = 0.f, a1 = 0.f;
+  if (i < n) {
+    int k = j;
+    for (; k + L < splits; k += 2 * L) { a0 += part[(size_t)k * n + i]; a1 += part[(size_t)(k + L) * n + i]; }
+    if (k < splits) a0 += part[(size_t)k * n + i];
+  }
+  s_part[j][e] = a0 + a1;
+  __syncthreads();
+  if (j == 0 && i < n) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < L; ++q) s += s_part[q][e];
+    out[(i / row_len) * out_row_stride + i % row_len] = s;
+  }
+}
+
+void launch_reduce_splits_rows(const float* part, int splits, int nrows, size_t row_len, float* out, size_t out_row_stride,
+                               cudaStream_t st) {
+  if (out_row_stride == row_len) { launch_reduce_splits(part, splits, (size_t)nrows * row_len, out, st); return; }
+  reduce_splits_rows_kernel<<<cdiv((long long)((size_t)nrows * row_len), 32), 256, 0, st>>>(part, splits, nrows, row_len, out,
+                                                                                           out_row_stride);
+}
+
 void geom_conv3x3(TapGeom& g, int N, int H, int W) {
   memset(&g, 0, sizeof(g));
   g.N = N; g.IH = H; g.IW = W; g.GH = H; g.GW = W; g.sy = g.sx = 1; g.ntaps = 9;

@@ -1626,6 +1626,7 @@ struct TcWgradStripParams {
   int nsrc;                 // 1 or 2 sources of 32 channels each
   int Nout;                 // 32 (64 B rows, SWIZZLE_64B) or 64 (128 B rows, SWIZZLE_128B)
   int R, wsegs, hchunks;
+  int coff0, coff1;         // channel coordinate of each 32-channel block inside its tensor
   float* part;              // [gridDim.x][9][32 * nsrc][Nout]
 };
 
@@ -1680,7 +1681,8 @@ tapgemm_tc_wgrad_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const _
           mbar_wait(&row_empty[pos], (ep >> pos) & 1u); ep ^= 1u << pos;
           mbar_arrive_expect_tx(&row_full[pos], (uint32_t)p.nsrc * 66u * 64u);
           for (int sidx = 0; sidx < p.nsrc; ++sidx)
-            tma_load_4d(sidx ? &mapA1 : &mapA0, &row_full[pos], s_ring + (size_t)pos * row_bytes + sidx * A_SLOT, 0, w0 - 1, h0 + rr, n);
+            tma_load_4d(sidx ? &mapA1 : &mapA0, &row_full[pos], s_ring + (size_t)pos * row_bytes + sidx * A_SLOT,
+                        sidx ? p.coff1 : p.coff0, w0 - 1, h0 + rr, n);
           if (++pos == WS_RING) pos = 0;
           if (rr >= 0 && rr < rows) {
             mbar_wait(&g_empty[gpos], (gp >> gpos) & 1u); gp ^= 1u << gpos;
@@ -1767,6 +1769,7 @@ tapgemm_tc_wgrad_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const _
 }
 
 void launch_reduce_splits(const float* part, int splits, size_t n, float* out, cudaStream_t st);
+void launch_reduce_splits_rows(const float* part, int splits, int nrows, size_t row_len, float* out, size_t out_row_stride, cudaStream_t st);
 
 struct WgradPlan { int BN, splits, CB, CBG, bw, bh, bn, tiles_w, tiles_h, tiles_n, stages; size_t ws_bytes; };
 
@@ -1802,53 +1805,59 @@ static WgradPlan plan_wgrad(const TapGeom& g, int K, int C0, int C1, int Nout) {
   return w;
 }
 
+// sources are consumed as 32-channel blocks (<= 2 per launch: 3 dy x 2 blocks x Nout accumulator columns <= 512);
+// a 64-channel tensor is two blocks of the same tensor map, more than two blocks run as several launches
 static bool wgrad_strip_ok(const TapGeom& g, int C0, int C1, int Nout) {
   static const bool disabled = getenv("DCB_NO_WGRAD_STRIP") != nullptr;
-  return !disabled && g.ntaps == 9 && g.sy == 1 && C0 == 32 && (C1 == 0 || C1 == 32) && (Nout == 32 || Nout == 64) &&
-         g.GW % WS_PX == 0;
+  return !disabled && g.ntaps == 9 && g.sy == 1 && (C0 == 32 || C0 == 64) && (C1 == 0 || C1 == 32 || C1 == 64) &&
+         (Nout == 32 || Nout == 64) && g.GW % WS_PX == 0;
 }
 
 size_t tc_wgrad_workspace(const TapGeom& g, int K, int Nout) {
   // C0/C1 split does not change the split count; use a conservative plan
   size_t ws = plan_wgrad(g, K, K, 0, Nout).ws_bytes;
-  if ((K == 32 || K == 64) && wgrad_strip_ok(g, 32, K - 32, Nout)) {
-    const size_t strip = (size_t)sm_count() * 9 * K * Nout * sizeof(float);
+  if (K % 32 == 0 && K <= 128 && wgrad_strip_ok(g, 32, 0, Nout)) {
+    const size_t strip = (size_t)sm_count() * 9 * 64 * Nout * sizeof(float);   // one launch covers <= 64 channels
     if (strip > ws) ws = strip;
   }
   return ws;
 }
 
-static int run_tc_wgrad_strip(const TapGeom& g, const void* s0, const void* s1, int nsrc, const void* G, int Nout, float* dW,
-                              void* ws, size_t ws_bytes, cudaStream_t st) {
+struct WgradBlock { const void* ptr; int C; int coff; };   // a 32-channel block: tensor, its channel count, channel offset
+
+// one launch over nblk (1 or 2) blocks; the result lands in rows [k_off, k_off + 32 * nblk) of dW[9][K_total][Nout]
+static int run_tc_wgrad_strip(const TapGeom& g, const WgradBlock* blk, int nblk, const void* G, int Nout, float* dW, int k_off,
+                              int K_total, void* ws, size_t ws_bytes, cudaStream_t st) {
   TcWgradStripParams p;
   memset(&p, 0, sizeof(p));
-  p.N = g.N; p.H = g.GH; p.W = g.GW; p.nsrc = nsrc; p.Nout = Nout;
+  p.N = g.N; p.H = g.GH; p.W = g.GW; p.nsrc = nblk; p.Nout = Nout;
+  p.coff0 = blk[0].coff; p.coff1 = nblk > 1 ? blk[1].coff : 0;
   p.wsegs = g.GW / WS_PX;
   int R = 32;
   while (R > 8 && (long long)g.N * cdiv(g.GH, R) * p.wsegs < 3LL * sm_count()) R >>= 1;
   p.R = R; p.hchunks = cdiv(g.GH, R);
   const int items = p.N * p.hchunks * p.wsegs;
   const int grid = items < sm_count() ? items : sm_count();
-  const int K = 32 * nsrc;
+  const int K = 32 * nblk;
   const size_t need = (size_t)grid * 9 * K * Nout * sizeof(float);
   if (!ws || ws_bytes < need) return fail(DCB_ERR_WORKSPACE, "wgrad (bf16 strip): workspace %zu B < required %zu B", ws_bytes, need);
   p.part = reinterpret_cast<float*>(ws);
   CUtensorMap mA0, mA1, mG;
-  auto mk = [&](CUtensorMap* m, const void* ptr) -> int {
-    uint64_t dims[4] = {32, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.N};
-    uint64_t str[3] = {64, (uint64_t)g.IW * 64, (uint64_t)g.IH * g.IW * 64};
+  auto mk = [&](CUtensorMap* m, const WgradBlock& b) -> int {
+    uint64_t dims[4] = {(uint64_t)b.C, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.N};
+    uint64_t str[3] = {(uint64_t)b.C * 2, (uint64_t)g.IW * b.C * 2, (uint64_t)g.IH * g.IW * b.C * 2};
     uint32_t box[4] = {32, 66, 1, 1};
-    return make_map(m, ptr, 4, dims, str, box, 64);
+    return make_map(m, b.ptr, 4, dims, str, box, 64);
   };
-  if (int e = mk(&mA0, s0)) return e;
-  if (nsrc > 1) { if (int e = mk(&mA1, s1)) return e; } else mA1 = mA0;
+  if (int e = mk(&mA0, blk[0])) return e;
+  if (nblk > 1) { if (int e = mk(&mA1, blk[1])) return e; } else mA1 = mA0;
   {
     uint64_t dims[4] = {(uint64_t)Nout, (uint64_t)g.GW, (uint64_t)g.GH, (uint64_t)g.N};
     uint64_t str[3] = {(uint64_t)Nout * 2, (uint64_t)g.GW * Nout * 2, (uint64_t)g.GH * g.GW * Nout * 2};
     uint32_t box[4] = {(uint32_t)Nout, (uint32_t)WS_PX, 1, 1};
     if (int e = make_map(&mG, G, 4, dims, str, box, Nout * 2)) return e;
   }
-  const size_t dyn = (size_t)WS_RING * nsrc * 5120 + (size_t)WS_GRING * WS_PX * Nout * 2 + 1024;
+  const size_t dyn = (size_t)WS_RING * nblk * 5120 + (size_t)WS_GRING * WS_PX * Nout * 2 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_wgrad_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -1857,7 +1866,7 @@ static int run_tc_wgrad_strip(const TapGeom& g, const void* s0, const void* s1, 
   }
   tapgemm_tc_wgrad_strip_kernel<<<grid, WG_THREADS, dyn, st>>>(mA0, mA1, mG, p);
   DCB_LAUNCH_OK("tapgemm_tc_wgrad_strip_kernel");
-  launch_reduce_splits(p.part, grid, (size_t)9 * K * Nout, dW, st);
+  launch_reduce_splits_rows(p.part, grid, 9, K * Nout, dW + (size_t)k_off * Nout, (size_t)K_total * Nout, st);
   g_launches += 2;
   DCB_LAUNCH_OK("reduce_splits_kernel");
   return DCB_OK;
@@ -1869,7 +1878,16 @@ int run_tc_wgrad(const TapGeom& g, const void* s0, int C0, const void* s1, int C
     return fail(DCB_ERR_UNSUPPORTED, "bf16 tensor-core wgrad needs channel counts that are multiples of 32 "
                 "(got C0=%d C1=%d N=%d)", C0, C1, Nout);
   const int K = C0 + C1;
-  if (wgrad_strip_ok(g, C0, C1, Nout)) return run_tc_wgrad_strip(g, s0, s1, C1 > 0 ? 2 : 1, G, Nout, dW, ws, ws_bytes, st);
+  if (wgrad_strip_ok(g, C0, C1, Nout)) {
+    WgradBlock blocks[4]; int nb = 0;
+    for (int c = 0; c < C0; c += 32) blocks[nb++] = WgradBlock{s0, C0, c};
+    for (int c = 0; c < C1; c += 32) blocks[nb++] = WgradBlock{s1, C1, c};
+    for (int b = 0; b < nb; b += 2) {
+      const int n = nb - b < 2 ? nb - b : 2;
+      if (int e = run_tc_wgrad_strip(g, blocks + b, n, G, Nout, dW, 32 * b, K, ws, ws_bytes, st)) return e;
+    }
+    return DCB_OK;
+  }
   const WgradPlan w = plan_wgrad(g, K, C0, C1, Nout);
   if (!ws || ws_bytes < w.ws_bytes) return fail(DCB_ERR_WORKSPACE, "wgrad (bf16): workspace %zu B < required %zu B", ws_bytes, w.ws_bytes);
   const bool convT = (g.sy == 2);

@@ -57,6 +57,10 @@ CONV_CASES = [
     (4, 128, 128, 32, 32, 32),
     (2, 6, 128, 64, 64, 64),      # weights too large for one strip launch: two launches of 32 output channels
     (1, 4, 256, 64, 64, 64),
+    # 64-channel sources on 64-pixel rows: strip wgrad over two / three / four 32-channel blocks
+    (1, 16, 64, 64, 0, 64),
+    (2, 8, 64, 64, 64, 64),
+    (1, 8, 128, 64, 32, 32),
     # enough 256-pixel tiles for the swapped (weights-as-A) orientation of the generic kernel
     (8, 64, 64, 64, 0, 128),
     (5, 48, 80, 64, 64, 64),
