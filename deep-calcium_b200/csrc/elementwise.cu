@@ -312,6 +312,58 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, int ldy, int offy, const T* __
   }
 }
 
+// ---------------------------------------------------------------- nearest 2x upsampling (+dropout)
+// UpSampling2D of the non-default `upsampling_or_transpose='upsampling'` graph (unet_2d_summary.py:160-161), followed by
+// the Dropout that the reference applies to the upsampled tensor (:198-216).  y[n][2h+a][2w+b][c] = x[n][h][w][c] * keep.
+template <typename T>
+__global__ void upsample2x_kernel(const T* __restrict__ x, int N, int h, int w, int C, float p_drop, unsigned long long seed,
+                                  const unsigned long long* __restrict__ seed_dev, uint32_t layer, T* __restrict__ y) {
+  if (seed_dev) seed ^= *seed_dev;
+  const int c4n = C >> 2;
+  const long long n4 = (long long)N * (2 * h) * (2 * w) * c4n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) * 4;
+    long long r = i / c4n;
+    const int ox = (int)(r % (2 * w)); r /= 2 * w;
+    const int oy = (int)(r % (2 * h)); const int n = (int)(r / (2 * h));
+    float4 v = load4<T>(x + (((long long)n * h + (oy >> 1)) * w + (ox >> 1)) * C + c);
+    if (p_drop > 0.f) {
+      const float4 k = dropout_scale4(seed, layer, (unsigned long long)i, p_drop);
+      v.x *= k.x; v.y *= k.y; v.z *= k.z; v.w *= k.w;
+    }
+    store4<T>(y + i * 4, v);
+  }
+}
+
+// dx[n][h][w][c] = sum over the 2x2 block of dy[n][2h+a][2w+b][offy + c] * keep   (dy fp32 view, dx fp32)
+__global__ void upsample2x_bwd_kernel(const float* __restrict__ dy, int ldy, int offy, int N, int h, int w, int C, float p_drop,
+                                      unsigned long long seed, const unsigned long long* __restrict__ seed_dev, uint32_t layer,
+                                      float* __restrict__ dx) {
+  if (seed_dev) seed ^= *seed_dev;
+  const int c4n = C >> 2;
+  const long long n4 = (long long)N * h * w * c4n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) * 4;
+    long long r = i / c4n;
+    const int ix = (int)(r % w); r /= w;
+    const int iy = (int)(r % h); const int n = (int)(r / h);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const long long opix = ((long long)n * (2 * h) + (2 * iy + a)) * (2 * w) + (2 * ix + b);
+        float4 g = load4<float>(dy + opix * ldy + offy + c);
+        if (p_drop > 0.f) {   // same counter as the forward: flat index of the upsampled element / 4
+          const float4 k = dropout_scale4(seed, layer, (unsigned long long)(opix * c4n + (c >> 2)), p_drop);
+          g.x *= k.x; g.y *= k.y; g.z *= k.z; g.w *= k.w;
+        }
+        acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+      }
+    *reinterpret_cast<float4*>(dx + i * 4) = acc;
+  }
+}
+
 // ---------------------------------------------------------------- 2x2 max-pool
 template <typename T>
 __global__ void maxpool2x2_kernel(const T* __restrict__ x, int N, int H, int W, int C, T* __restrict__ y) {
@@ -785,6 +837,31 @@ extern "C" int dcb_bn_bwd_apply(int dtype, const float* dy, int ldy, int offy, c
   }
   g_launches += 1;
   DCB_LAUNCH_OK("bn_bwd_apply_kernel");
+  return DCB_OK;
+}
+
+extern "C" int dcb_upsample2x(int dtype, const void* x, int N, int h, int w, int C, float p_drop, unsigned long long seed,
+                              const unsigned long long* seed_dev, unsigned layer, void* y, dcb_stream_t stream) {
+  DCB_CHECK_ARG(x && y && N > 0 && h > 0 && w > 0 && C > 0 && C % 4 == 0, "dcb_upsample2x: bad arguments (C %d)", C);
+  DCB_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "dcb_upsample2x: p_drop %f outside [0, 1)", p_drop);
+  const long long n4 = (long long)N * 4 * h * w * (C / 4);
+  DISPATCH_T(dtype, upsample2x_kernel<T><<<ew_grid(n4, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const T*)x, N, h, w, C, p_drop, seed, seed_dev, layer, (T*)y);)
+  g_launches += 1;
+  DCB_LAUNCH_OK("upsample2x_kernel");
+  return DCB_OK;
+}
+
+extern "C" int dcb_upsample2x_bwd(const float* dy, int ldy, int offy, int N, int h, int w, int C, float p_drop,
+                                  unsigned long long seed, const unsigned long long* seed_dev, unsigned layer, float* dx,
+                                  dcb_stream_t stream) {
+  DCB_CHECK_ARG(dy && dx && N > 0 && h > 0 && w > 0 && C > 0 && C % 4 == 0 && ldy % 4 == 0 && offy % 4 == 0 && offy + C <= ldy,
+                "dcb_upsample2x_bwd: bad arguments (C %d ld %d off %d)", C, ldy, offy);
+  const long long n4 = (long long)N * h * w * (C / 4);
+  upsample2x_bwd_kernel<<<ew_grid(n4, 256), 256, 0, (cudaStream_t)stream>>>(dy, ldy, offy, N, h, w, C, p_drop, seed, seed_dev,
+                                                                            layer, dx);
+  g_launches += 1;
+  DCB_LAUNCH_OK("upsample2x_bwd_kernel");
   return DCB_OK;
 }
 

@@ -46,8 +46,12 @@ tapgemm_f32_fwd_kernel(const F32FwdParams p) {
     gw[i] = (int)(mm % g.GW); mm /= g.GW;
     gh[i] = (int)(mm % g.GH); img[i] = (int)(mm / g.GH);
   }
+  // Blocked summation (16-term chunk -> tap -> total) instead of one running fp32 sum over up to 9 * 768 terms: the
+  // check mode exists to be compared with float64, and the BatchNorm backward downstream cancels most leading digits
+  // of these sums, so the accumulation order matters (measured: per-tensor gradient error 3x lower).
   float acc[4][4] = {};
   for (int tap = 0; tap < g.ntaps; ++tap) {
+    float tacc[4][4] = {};
     size_t pixi[4];
     bool ok[4];
 #pragma unroll
@@ -76,6 +80,7 @@ tapgemm_f32_fwd_kernel(const F32FwdParams p) {
         Bs[kk][nn] = v;
       }
       __syncthreads();
+      float cacc[4][4] = {};
 #pragma unroll
       for (int kk = 0; kk < FK; ++kk) {
         float a[4], b[4];
@@ -84,10 +89,18 @@ tapgemm_f32_fwd_kernel(const F32FwdParams p) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+          for (int j = 0; j < 4; ++j) cacc[i][j] = fmaf(a[i], b[j], cacc[i][j]);
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tacc[i][j] += cacc[i][j];
       __syncthreads();
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += tacc[i][j];
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -133,7 +146,8 @@ tapgemm_f32_wgrad_kernel(const F32WgradParams p) {
   const long long M = (long long)g.N * g.GH * g.GW;
   const long long mb = (M * split) / p.splits, me = (M * (split + 1)) / p.splits;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  float acc[4][4] = {};
+  float acc[4][4] = {}, bacc[4][4] = {};     // blocked summation: 16 positions -> 1024 positions -> total
+  int chunk = 0;
   for (long long mc = mb; mc < me; mc += FK) {
     // A tile: 16 positions x 64 k ; thread loads position (tid/16), k = tx + j*16
     {
@@ -161,6 +175,7 @@ tapgemm_f32_wgrad_kernel(const F32WgradParams p) {
       }
     }
     __syncthreads();
+    float cacc[4][4] = {};
 #pragma unroll
     for (int mm = 0; mm < FK; ++mm) {
       float a[4], b[4];
@@ -169,10 +184,22 @@ tapgemm_f32_wgrad_kernel(const F32WgradParams p) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) cacc[i][j] = fmaf(a[i], b[j], cacc[i][j]);
     }
+    const bool flush = (++chunk & 63) == 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        bacc[i][j] += cacc[i][j];
+        if (flush) { acc[i][j] += bacc[i][j]; bacc[i][j] = 0.f; }
+      }
     __syncthreads();
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] += bacc[i][j];
   float* dst = p.part + ((size_t)split * g.ntaps + tap) * K * p.Nout;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

@@ -1248,6 +1248,9 @@ static int run_tc_flat(const TapGeom& g, const void* s0, int C0, const void* s1,
   return DCB_OK;
 }
 
+static int run_tc_generic(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* B, int Nout, void* out,
+                          int out_pitch, const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st);
+
 // fuse != nullptr: the caller wants the head and/or the 2x2 max-pool computed in the conv epilogue; returns
 // DCB_ERR_UNSUPPORTED (without launching) when this layer shape cannot take the fused path.
 int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* B, int Nout, void* out,
@@ -1255,7 +1258,22 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
   if (C0 % 32 != 0 || C1 % 32 != 0 || Nout % 32 != 0)
     return fail(DCB_ERR_UNSUPPORTED, "bf16 tensor-core path needs channel counts that are multiples of 32 "
                 "(got C0=%d C1=%d Cout=%d); use the fp32 check mode for other widths", C0, C1, Nout);
-  if (Nout > 512) return fail(DCB_ERR_UNSUPPORTED, "bf16 tensor-core path supports at most 512 output channels (got %d)", Nout);
+  if (Nout > 512) {
+    // wide outputs (the dgrad of a 768-channel concat in the 'upsampling' graph): slices of <= 512 channels through the
+    // generic kernel, each writing its channel range of the full-pitch output
+    if (fuse) return fail(DCB_ERR_UNSUPPORTED, "fused epilogue not available for this layer");
+    const size_t esz = out_f32 ? 4 : 2;
+    const size_t wrow = (size_t)g.ntaps * (C0 + C1) * (g.zsub > 1 ? g.zsub : 1);
+    if (g.zsub > 1) return fail(DCB_ERR_UNSUPPORTED, "bf16 convT with more than 512 output channels is not built");
+    for (int n0 = 0; n0 < Nout; n0 += 512) {
+      const int ns = Nout - n0 < 512 ? Nout - n0 : 512;
+      if (int e = run_tc_generic(g, s0, C0, s1, C1, reinterpret_cast<const __nv_bfloat16*>(B) + (size_t)n0 * wrow, ns,
+                                 reinterpret_cast<uint8_t*>(out) + (size_t)n0 * esz, Nout, scale ? scale + n0 : nullptr,
+                                 shift ? shift + n0 : nullptr, relu, out_f32, st))
+        return e;
+    }
+    return DCB_OK;
+  }
   {
     TcStripParams sp;
     size_t dyn = 0;
@@ -1335,6 +1353,12 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
     const int e = run_tc_flat(g, s0, C0, s1, C1, B, Nout, out, scale, shift, relu, out_f32, st);
     if (e != DCB_ERR_UNSUPPORTED) return e;
   }
+  return run_tc_generic(g, s0, C0, s1, C1, B, Nout, out, Nout, scale, shift, relu, out_f32, st);
+}
+
+// generic kernel: Nout output channels written with a channel pitch of out_pitch (>= Nout) starting at `out`
+static int run_tc_generic(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* B, int Nout, void* out,
+                          int out_pitch, const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st) {
   TcFwdParams p;
   memset(&p, 0, sizeof(p));
   const int ntaps = g.ntaps;
@@ -1349,7 +1373,7 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
   const int swz = p.BK * 2;
   p.Cz = Nout;
   p.Ntot = convT_fwd ? 4 * Nout : Nout;
-  p.OH = g.OH; p.OW = g.OW; p.OC = Nout;
+  p.OH = g.OH; p.OW = g.OW; p.OC = out_pitch;
   p.osy = g.osy; p.osx = g.osx; p.ody = g.ody; p.odx = g.odx;
   p.relu = relu; p.out_f32 = out_f32; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.scale = scale; p.shift = shift;
   // Swapped orientation for narrow outputs: with <= 128 output channels the normal orientation spends the

@@ -211,6 +211,18 @@ def bn_bwd_apply(dy, ldy, offy, x, scale, shift, mean, rstd, sums, draw, dgamma,
 
 
 # ---------------------------------------------------------------- pooling
+def upsample2x(x, y, p_drop=0., seed=0, seed_dev=None, layer=0):
+    N, h, w, C = x.shape
+    call('dcb_upsample2x', _dt(x), ptr(x), c_int(N), c_int(h), c_int(w), c_int(C), c_f(p_drop), c_ull(seed), ptr(seed_dev),
+         c_uint(layer), ptr(y), stream_ptr())
+
+
+def upsample2x_bwd(dy, ldy, offy, dx, p_drop=0., seed=0, seed_dev=None, layer=0):
+    N, h, w, C = dx.shape
+    call('dcb_upsample2x_bwd', ptr(dy), c_int(ldy), c_int(offy), c_int(N), c_int(h), c_int(w), c_int(C), c_f(p_drop),
+         c_ull(seed), ptr(seed_dev), c_uint(layer), ptr(dx), stream_ptr())
+
+
 def maxpool2x2(x, y):
     N, H, W, C = x.shape
     call('dcb_maxpool2x2', _dt(x), ptr(x), c_int(N), c_int(H), c_int(W), c_int(C), ptr(y), stream_ptr())

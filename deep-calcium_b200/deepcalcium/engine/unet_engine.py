@@ -27,9 +27,6 @@ class UNetEngine(object):
     def __init__(self, spec=None, precision='bf16', device=None, use_graphs=True):
         nat.require_cuda()
         self.spec = spec or GraphSpec()
-        if self.spec.up_mode != 'transpose':
-            raise NotImplementedError("upsampling_or_transpose='upsampling' is not built yet; the reference "
-                                      "default 'transpose' (unet_2d_summary.py:124) is")
         self.dtype = _PRECISIONS[precision]
         self.precision = 'bf16' if self.dtype == torch.bfloat16 else 'fp32'
         self.dev = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
@@ -124,8 +121,12 @@ class UNetEngine(object):
             inp['enc%da' % l] = ('pool%d' % (l - 1), None); inp['enc%db' % l] = ('enc%da' % l, None)
         inp['bota'] = ('pool3', None); inp['botb'] = ('bota', None)
         prev = 'botb'
+        self._ups = OrderedDict()          # 'upsampling' mode: up<l> = nearest 2x of prev (+dropout), not a weight layer
         for l in (3, 2, 1, 0):
-            inp['up%d' % l] = (prev, None)
+            if self.spec.up_mode == 'transpose':
+                inp['up%d' % l] = (prev, None)
+            else:
+                self._ups['up%d' % l] = prev
             inp['dec%da' % l] = ('up%d' % l, 'enc%db' % l)
             inp['dec%db' % l] = ('dec%da' % l, None)
             prev = 'dec%db' % l
@@ -216,6 +217,12 @@ class UNetEngine(object):
                         s['dx'][blk.name] = torch.empty(NB, h, w, blk.cin, dtype=torch.float32, device=self.dev)
                     else:
                         s['dx'][blk.name] = torch.empty(NB, h // 2, w // 2, blk.cin, dtype=torch.float32, device=self.dev)
+        for un, prev in self._ups.items():
+            l = int(un[2:])
+            c = self.spec.by_name[prev].cout
+            s['act'][un] = torch.empty(NB, H >> l, W >> l, c, **T)
+            if training:
+                s['dx'][un] = torch.empty(NB, H >> (l + 1), W >> (l + 1), c, dtype=torch.float32, device=self.dev)
         for l in range(4):
             c = self.spec.nfb << l
             s['act']['pool%d' % l] = torch.empty(NB, H >> (l + 1), W >> (l + 1), c, **T)
@@ -254,6 +261,8 @@ class UNetEngine(object):
                 continue                                  # fused into dec0b below
             a, b = self._inputs[n]
             sc, sh = self.inf_scale[n], self.inf_shift[n]
+            if a in self._ups:
+                ops.upsample2x(act[self._ups[a]], act[a])
             if blk.kind == 'conv':
                 if blk.cin == 1 and self.dtype == torch.bfloat16:
                     ops.conv3x3_c1_fwd(s['x'], self.w_fwd[n], act[n], sc, sh, True)
@@ -360,6 +369,8 @@ class UNetEngine(object):
         self.dbl.zero_()
         self._prepare_weights(for_training=True)
         layer_id = {blk.name: i for i, blk in enumerate(spec.blocks)}
+        for i, un in enumerate(self._ups):
+            layer_id[un] = len(spec.blocks) + i
         # ---------------- forward (batch-statistic BN)
         for blk in spec.blocks:
             n = blk.name
@@ -367,6 +378,8 @@ class UNetEngine(object):
                 continue
             a, b = self._inputs[n]
             bias = self.P[n + '/bias']
+            if a in self._ups:
+                ops.upsample2x(act[self._ups[a]], act[a], self._dropout_p(a, dropout), seed_base, seed_dev, layer_id[a])
             if blk.kind == 'conv':
                 if blk.cin == 1 and self.dtype == torch.bfloat16:
                     ops.conv3x3_c1_fwd(s['x'], self.w_fwd[n], raw[n], None, bias, False)
@@ -427,8 +440,12 @@ class UNetEngine(object):
                 ops.conv3x3_dgrad(draw, self.w_dgrad[n], dX)
                 if b is not None:                       # concat [up, skip]
                     c0 = act[a].shape[3]
-                    grad_of[a] = (dX, blk.cin, 0)
                     skip_grad[b] = (dX, blk.cin, c0)
+                    if a in self._ups:                  # through the dropout + nearest upsampling to the previous block
+                        ops.upsample2x_bwd(dX, blk.cin, 0, dxb[a], self._dropout_p(a, dropout), seed_base, seed_dev, layer_id[a])
+                        grad_of[self._ups[a]] = (dxb[a], c0, 0)
+                    else:
+                        grad_of[a] = (dX, blk.cin, 0)
                 elif a.startswith('pool'):
                     l = int(a[4:])
                     enc = 'enc%db' % l

@@ -173,6 +173,13 @@ int dcb_bn_bwd_apply(int dtype, const float* dy, int ldy, int offy, const void* 
                      const double* sums, long long M_total, float dgb_scale, void* draw, float* dgamma,
                      float* dbeta, dcb_stream_t stream);
 
+/* nearest-neighbour 2x upsampling (UpSampling2D of the `upsampling_or_transpose='upsampling'` graph, unet_2d_summary.py:160-161)
+ * with the Dropout the reference applies to the upsampled tensor folded in (p_drop = 0: none): x [N][h][w][C] -> y [N][2h][2w][C];
+ * backward sums the (masked) 2x2 gradient blocks of the fp32 view dy (row stride ldy, channel offset offy) into dx [N][h][w][C] */
+int dcb_upsample2x(int dtype, const void* x, int N, int h, int w, int C, float p_drop, unsigned long long seed,
+                   const unsigned long long* seed_dev, unsigned layer, void* y, dcb_stream_t stream);
+int dcb_upsample2x_bwd(const float* dy, int ldy, int offy, int N, int h, int w, int C, float p_drop, unsigned long long seed,
+                       const unsigned long long* seed_dev, unsigned layer, float* dx, dcb_stream_t stream);
 /* ---- a5: MaxPooling2D(2,2) fwd and bwd (gradient to the first maximum of the window), the bwd
  * fused with the add of the skip-connection gradient (a channel slice of a concat gradient) ---- */
 int dcb_maxpool2x2(int dtype, const void* x, int N, int H, int W, int C, void* y, dcb_stream_t stream);

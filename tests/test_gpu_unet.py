@@ -134,9 +134,10 @@ def test_forward_512_and_tta_bf16_mask_disagreement(cuda):
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 def test_train_step_nfb32_against_oracle(cuda, precision):
     """One train_on_batch (dice, dropout off): loss, every gradient tensor, BN moving statistics.
-    fp32 check mode: within 1e-2 relative L2 of the fp64 oracle for every tensor.  (The BN backward of this
+    fp32 check mode: within 3e-3 relative L2 of the fp64 oracle for every tensor.  (The BN backward of this
     random-init dice network cancels catastrophically - dz - mean(dz) - so even torch-CPU float32 autograd of the
-    oracle is 1e-3 away from its own float64 run from dec0a downwards; measured, see DESIGN.md.)
+    oracle is 1e-3 away from its own float64 run from dec0a downwards; the check-mode kernels use blocked fp32
+    summation and land at 0.7e-3 ... 1.2e-3; measured, see DESIGN.md.)
     bf16 mode: the fp64 gradient of this random-init dice network moves by 20-65 % under 2^-9
     perturbations of the stored activations (measured on CPU with the bf16-storage emulation of the
     oracle), so the criterion is: the GPU's distance from fp64 is no larger than the emulation's own
@@ -162,7 +163,7 @@ def test_train_step_nfb32_against_oracle(cuda, precision):
         got = eng.G[key].cpu().numpy().astype(np.float64)
         r = rel(got, g_ref)
         if precision == 'fp32':
-            assert r < 1e-2, (key, r)
+            assert r < 3e-3, (key, r)
         else:
             assert r <= 1.3 * rel(g_emu[key], g_ref) + 0.03, (key, r, rel(g_emu[key], g_ref))
         if r > worst[1]:
@@ -214,3 +215,49 @@ def test_reference_surface_fit_predict_evaluate(cuda, tmp_path):
     assert names == ['synthetic.00', 'synthetic.01'] and Mp[0].shape == (96, 112) and Mp[0].dtype == np.uint8
     scores = model.evaluate(paths, model_path)
     assert set(scores.keys()) == {True, False}
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_upsampling_mode_forward_and_train_step(cuda, precision):
+    """The non-default `upsampling_or_transpose='upsampling'` graph (unet_2d_summary.py:160-161): nearest 2x upsampling
+    instead of the transposed conv blocks, concat widths 768 / 384 / 192 / 96.  Forward logits and one training step
+    (dropout off) against the oracle, same criteria as the default graph."""
+    from deepcalcium.engine.graph import GraphSpec
+    from deepcalcium.engine.unet_engine import UNetEngine
+    spec = oracle.UNetSpec(32, upsampling_or_transpose='upsampling')
+    w = oracle.init_weights(spec, seed=7535)
+    assert not any(k.startswith('up') for k in w)
+    rng = np.random.default_rng(865)
+    x = rng.standard_normal((2, 64, 64)).astype(np.float32)
+    y = (rng.random((2, 64, 64)) < 0.126).astype(np.uint8)
+    ref = oracle.unet_forward(w, x, spec, dtype=torch.float64)
+    eng = UNetEngine(GraphSpec(32, upsampling_or_transpose='upsampling'), precision=precision, use_graphs=False)
+    eng.set_weights_dict(w)
+    prob, logit = eng.infer(torch.from_numpy(x).cuda())
+    err = np.abs(logit.cpu().numpy() - ref['logit'].numpy())
+    if precision == 'fp32':
+        assert err.max() < 1e-4
+    else:
+        emu = oracle.unet_forward(w, x, spec, dtype=torch.float64, emulate_bf16=True)
+        e_emu = np.abs(emu['logit'].numpy() - ref['logit'].numpy())
+        assert err.mean() <= 1.5 * e_emu.mean() + 2e-3 and err.max() <= 2.0 * e_emu.max() + 2e-2
+    L, nw, st, g, _ = oracle.train_step(w, x, y, spec=spec, loss='dice_loss')
+    m = eng.train_step(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), loss='dice_loss', dropout=False)
+    assert abs(float(m[0].item()) - L) < (1e-4 if precision == 'fp32' else 2e-3)
+    if precision == 'bf16':
+        _, _, _, g_emu, _ = oracle.train_step(w, x, y, spec=spec, loss='dice_loss', emulate_bf16=True)
+
+    def rel(a, b):
+        return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+
+    for key, g_ref in g.items():
+        if key.endswith('/bias') and not key.startswith('head'):
+            continue
+        r = rel(eng.G[key].cpu().numpy().astype(np.float64), g_ref)
+        if precision == 'fp32':
+            assert r < 3e-3, (key, r)
+        else:
+            assert r <= 1.3 * rel(g_emu[key], g_ref) + 0.03, (key, r, rel(g_emu[key], g_ref))
+    # dropout on: the upsampled tensors are masked with keep probability 1 - p and rescaled (mean preserved)
+    m2 = eng.train_step(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), loss='dice_loss', dropout=True)
+    assert np.isfinite(float(m2[0].item()))
