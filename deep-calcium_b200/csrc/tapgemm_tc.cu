@@ -830,6 +830,24 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
                 }
                 *reinterpret_cast<float4*>(orow_f + c + j) = make_float4(v[0], v[1], v[2], v[3]);
               }
+            } else if (p.head_kernel && !p.need_y && !p.pool_out) {
+              // dec0b at inference: the activation is consumed by the 1x1 head only and never stored, so it is not
+              // rounded to bf16 either: BN + ReLU + dot product stay in (packed) fp32
+              float2 za0 = make_float2(0.f, 0.f), za1 = make_float2(0.f, 0.f);
+  #pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 sc = *reinterpret_cast<const float4*>(s_scale + c + 4 * g);
+                const float4 sh = *reinterpret_cast<const float4*>(s_shift + c + 4 * g);
+                const float4 wd = *reinterpret_cast<const float4*>(s_wd + c + 4 * g);
+                float2 v0 = ffma2(make_float2(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1])), make_float2(sc.x, sc.y),
+                                  make_float2(sh.x, sh.y));
+                float2 v1 = ffma2(make_float2(__uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3])), make_float2(sc.z, sc.w),
+                                  make_float2(sh.z, sh.w));
+                if (p.relu) { v0.x = fmaxf(v0.x, 0.f); v0.y = fmaxf(v0.y, 0.f); v1.x = fmaxf(v1.x, 0.f); v1.y = fmaxf(v1.y, 0.f); }
+                za0 = ffma2(v0, make_float2(wd.x, wd.y), za0);
+                za1 = ffma2(v1, make_float2(wd.z, wd.w), za1);
+              }
+              zacc += (za0.x + za0.y) + (za1.x + za1.y);
             } else {
               uint32_t pk[16];
               bn_relu_pack32(r, s_scale + c, s_shift + c, p.relu, pk);

@@ -176,7 +176,9 @@ def test_conv3x3_fused_pool_and_head_equal_the_unfused_composition(cuda, precisi
     y3 = torch.full_like(y, 7.0); logit3 = torch.empty_like(logit); prob3 = torch.empty_like(prob)
     ops.conv3x3_fwd_fused(x, None, wf, y3, scale, shift, True, head_kernel=hk, head_bias=hb, logit=logit3, prob=prob3,
                           need_y=False)
-    atol = 1e-5 if precision == 'fp32' else 2e-2
+    # bf16: with need_y=False the fused kernel never rounds the activation to bf16 (it is not stored), the unfused
+    # composition reads the rounded tensor: 32 terms x 2^-9 relative rounding each
+    atol = 1e-5 if precision == 'fp32' else 5e-2
     assert torch.allclose(logit3, logit, atol=atol, rtol=1e-5) and torch.allclose(prob3, prob, atol=atol / 4)
 
 
