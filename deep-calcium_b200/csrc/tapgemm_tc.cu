@@ -307,22 +307,21 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
         tmem_ld_wait();
         if (valid && p.out_f32) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float v[4];
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t v[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 8; ++q) {
               const int ch = cbase + c + j + q;
-              v[q] = fmaf(__uint_as_float(r[j + q]), s_scale[ch], s_shift[ch]);
-              if (p.relu) v[q] = fmaxf(v[q], 0.f);
+              float f = fmaf(__uint_as_float(r[j + q]), s_scale[ch], s_shift[ch]);
+              if (p.relu) f = fmaxf(f, 0.f);
+              v[q] = __float_as_uint(f);
             }
-            *reinterpret_cast<float4*>(orow_f + c + j) = make_float4(v[0], v[1], v[2], v[3]);
+            st_global_v8(orow_f + c + j, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
           }
         } else if (valid) {
           uint32_t pk[16];
           bn_relu_pack32(r, s_scale + cbase + c, s_shift + cbase + c, p.relu, pk);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(orow + c + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          store_pk16(orow + c, pk);
         }
       }
       tc_fence_before();
@@ -776,21 +775,20 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
 #endif
             if (p.out_f32) {
   #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float v[4];
+              for (int j = 0; j < 32; j += 8) {
+                uint32_t v[8];
   #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  v[q] = fmaf(__uint_as_float(r[j + q]), s_scale[c + j + q], s_shift[c + j + q]);
-                  if (p.relu) v[q] = fmaxf(v[q], 0.f);
+                for (int q = 0; q < 8; ++q) {
+                  float f = fmaf(__uint_as_float(r[j + q]), s_scale[c + j + q], s_shift[c + j + q]);
+                  if (p.relu) f = fmaxf(f, 0.f);
+                  v[q] = __float_as_uint(f);
                 }
-                *reinterpret_cast<float4*>(orow_f + c + j) = make_float4(v[0], v[1], v[2], v[3]);
+                st_global_v8(orow_f + c + j, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
               }
             } else {
               uint32_t pk[16];
               bn_relu_pack32(r, s_scale + c, s_shift + c, p.relu, pk);
-  #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<uint4*>(orow + c + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              store_pk16(orow + c, pk);
             }
 #ifdef DCB_STRIP_TIMING
             { const long long lc2 = clock64(); ep_acc[4] += (unsigned long long)(lc2 - lc1); }
@@ -821,14 +819,15 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
             tmem_ld_wait();
             if (p.out_f32) {
   #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float v[4];
+              for (int j = 0; j < 32; j += 8) {
+                uint32_t v[8];
   #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  v[q] = fmaf(__uint_as_float(r[j + q]), s_scale[c + j + q], s_shift[c + j + q]);
-                  if (p.relu) v[q] = fmaxf(v[q], 0.f);
+                for (int q = 0; q < 8; ++q) {
+                  float f = fmaf(__uint_as_float(r[j + q]), s_scale[c + j + q], s_shift[c + j + q]);
+                  if (p.relu) f = fmaxf(f, 0.f);
+                  v[q] = __float_as_uint(f);
                 }
-                *reinterpret_cast<float4*>(orow_f + c + j) = make_float4(v[0], v[1], v[2], v[3]);
+                st_global_v8(orow_f + c + j, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
               }
             } else if (p.head_kernel && !p.need_y && !p.pool_out) {
               // dec0b at inference: the activation is consumed by the 1x1 head only and never stored, so it is not
@@ -864,9 +863,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
                 zacc += (za[0] + za[1]) + (za[2] + za[3]);
               }
               if (p.need_y) {
-  #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  *reinterpret_cast<uint4*>(orow + c + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                store_pk16(orow + c, pk);
               }
               if (p.pool_out && cb < 2) {
                 // 2x2 max-pool: vertical partner = the previous tile of this warp (row h0+t-1, kept in registers),
@@ -887,9 +884,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
                   }
                   if ((lane & 1) == 0) {
                     __nv_bfloat16* prow = p.pool_out + ((((size_t)n * (p.H >> 1) + ((h0 + t) >> 1)) * (p.W >> 1) + ((w0 + m) >> 1)) * p.Cout + c);
-  #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                      *reinterpret_cast<uint4*>(prow + 8 * j) = make_uint4(mx[4 * j], mx[4 * j + 1], mx[4 * j + 2], mx[4 * j + 3]);
+                    store_pk16(prow, mx);
                   }
                 }
               }
@@ -1181,7 +1176,11 @@ static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, int Nsub, boo
   const size_t budget_all = 223 * 1024, stage_tiles = 4 * 4096;
   // swapped orientation (256-pixel segments, N = 256 per MMA) whenever the image is wide enough
   // the fused head / pool epilogues exist for the normal orientation only
-  int swap = (!fused && swap_allowed(Nsub) && g.GW % 256 == 0) ? 1 : 0;
+  // Cout = 64 is faster folded (13 MMAs of N = 192 per 128 pixels) than swapped (36 MMAs of N = 256 per 256 pixels with
+  // half of the 128 M rows empty): measured 0.050/0.056 -> 0.042/0.046 ms on the 256^2 layers; swapped strips are
+  // for Cout = 128 only
+  static const bool no_fold_pref = getenv("DCB_NO_FOLD") != nullptr;
+  int swap = (!fused && swap_allowed(Nsub) && g.GW % 256 == 0 && (Nsub > 64 || no_fold_pref || g.GH % 2 != 0)) ? 1 : 0;
   int slot = 0, ring = 0;
   for (; swap >= 0; --swap) {
     const int px = swap ? 256 : 128;

@@ -189,6 +189,22 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- epilogue stores
+// 32-byte store (sm_100, PTX 8.8): one FULL 32-byte sector per lane.  The epilogues write 64 B (bf16) or 128 B (fp32)
+// per pixel and lane; as 16-byte stores every warp instruction touched 32 sectors half-filled - twice the
+// store requests for the same bytes.  p must be 32-byte aligned.
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                             uint32_t a5, uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3),
+               "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+               : "memory");
+}
+// 16 packed bf16 pairs (32 channels, 64 bytes) of one pixel
+__device__ __forceinline__ void store_pk16(void* p, const uint32_t (&pk)[16]) {
+  st_global_v8(p, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+  st_global_v8(reinterpret_cast<uint8_t*>(p) + 32, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+}
+
 // ---------------------------------------------------------------- epilogue math
 // packed fp32x2 FMA (sm_100): d = a * b + c on two lanes at once
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
