@@ -365,6 +365,26 @@ __global__ void upsample2x_bwd_kernel(const float* __restrict__ dy, int ldy, int
 }
 
 // ---------------------------------------------------------------- 2x2 max-pool
+// 8 channels (16 B of bf16) per thread: the four window loads are independent 16-byte requests
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool2x2_v8_kernel(const T* __restrict__ x, int N, int H, int W, int C, T* __restrict__ y) {
+  const int OH = H / 2, OW = W / 2, c8n = C >> 3;
+  const long long n8 = (long long)N * OH * OW * c8n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int c = (int)(t % c8n) * 8; t /= c8n;
+    const int ow = (int)(t % OW); t /= OW;
+    const int oh = (int)(t % OH); const int n = (int)(t / OH);
+    const T* p = x + (((long long)n * H + 2 * oh) * W + 2 * ow) * C + c;
+    float a[8], b[8], d[8], e[8], m[8];
+    load8<T>(p, a); load8<T>(p + C, b); load8<T>(p + (long long)W * C, d); load8<T>(p + (long long)W * C + C, e);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) m[q] = fmaxf(fmaxf(a[q], b[q]), fmaxf(d[q], e[q]));
+    store8<T>(y + i * 8, m);
+  }
+}
+
 template <typename T>
 __global__ void maxpool2x2_kernel(const T* __restrict__ x, int N, int H, int W, int C, T* __restrict__ y) {
   const int OH = H / 2, OW = W / 2, c4n = C >> 2;
@@ -867,8 +887,13 @@ extern "C" int dcb_upsample2x_bwd(const float* dy, int ldy, int offy, int N, int
 
 extern "C" int dcb_maxpool2x2(int dtype, const void* x, int N, int H, int W, int C, void* y, dcb_stream_t stream) {
   DCB_CHECK_ARG(x && y && N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "dcb_maxpool2x2: bad arguments");
-  DISPATCH_T(dtype, maxpool2x2_kernel<T><<<ew_grid((long long)N * (H / 2) * (W / 2) * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(
-      (const T*)x, N, H, W, C, (T*)y);)
+  if (C % 8 == 0) {
+    DISPATCH_T(dtype, maxpool2x2_v8_kernel<T><<<ew_grid((long long)N * (H / 2) * (W / 2) * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)x, N, H, W, C, (T*)y);)
+  } else {
+    DISPATCH_T(dtype, maxpool2x2_kernel<T><<<ew_grid((long long)N * (H / 2) * (W / 2) * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)x, N, H, W, C, (T*)y);)
+  }
   g_launches += 1;
   DCB_LAUNCH_OK("maxpool2x2_kernel");
   return DCB_OK;

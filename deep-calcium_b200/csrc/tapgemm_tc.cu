@@ -610,6 +610,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
         const uint32_t a_tfull = smem_u32_pinned(bar_tfull), a_tempty = smem_u32_pinned(bar_tempty);
         const int ring_pairs = p.ring >> 1;
         int pp = 0; uint32_t fullpar = 0;
+        asm volatile(".reg .pred p_rf, p_te;");                   // split-phase poll results, see the pair loop
 #ifdef DCB_STRIP_TIMING
         unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const long long dbg_t0 = clock64();
@@ -647,15 +648,37 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
         long long u = u_begin;
         for (int n, h0, rows, w0; next_strip(u, n, h0, rows, w0);) {
           const int half = rows >> 1;                             // rows is even in folded mode
+          // Split-phase barrier polls: a phase check costs this thread ~250 cycles of latency even when the phase is
+          // long complete, so the two checks of pair m+1 are ISSUED (non-blocking mbarrier.test_wait into the
+          // function-scope predicates p_rf / p_te) before the MMAs of pair m and only CONSUMED at the top of the next
+          // iteration; a poll that came back "not yet" falls back to the blocking wait.
+          bool pre = false, pre_te = false;
           for (int m = 0; m <= half; ++m) {                       // input (halo) rows h0 + 2m - 1 and h0 + 2m
             ST_T(c0);
-            mbar_wait_a(a_row_full + 8u * pp, (fullpar >> pp) & 1u);
-            fullpar ^= 1u << pp;
-            ST_T(c1); ST_ACC(0, c0, c1);
             const uint32_t jp = (j >> 1) + (uint32_t)m;           // running index of the output pair P(m)
-            if (m < half) mbar_wait_a(a_tempty + 8u * (jp & pmask), ((jp >> pair_sh) & 1u) ^ 1u);
+            {
+              uint32_t ok_rf = 0, ok_te = 0;
+              if (pre) {
+                asm volatile("selp.u32 %0, 1, 0, p_rf;" : "=r"(ok_rf));
+                if (pre_te) asm volatile("selp.u32 %0, 1, 0, p_te;" : "=r"(ok_te));
+              }
+              if (!ok_rf) mbar_wait_a(a_row_full + 8u * pp, (fullpar >> pp) & 1u);
+              fullpar ^= 1u << pp;
+              ST_T(c1); ST_ACC(0, c0, c1);
+              if (m < half && !ok_te) mbar_wait_a(a_tempty + 8u * (jp & pmask), ((jp >> pair_sh) & 1u) ^ 1u);
+            }
             tc_fence_after();
             ST_T(c2); ST_ACC(1, c1, c2);
+            pre = m < half;
+            pre_te = m + 1 < half;
+            if (pre) {
+              const int ppn = (pp + 1 == ring_pairs) ? 0 : pp + 1;
+              asm volatile("mbarrier.test_wait.parity.shared::cta.b64 p_rf, [%0], %1;" ::"r"(a_row_full + 8u * ppn),
+                           "r"((fullpar >> ppn) & 1u) : "memory");
+              if (pre_te)
+                asm volatile("mbarrier.test_wait.parity.shared::cta.b64 p_te, [%0], %1;" ::"r"(a_tempty + 8u * ((jp + 1u) & pmask)),
+                             "r"((((jp + 1u) >> pair_sh) & 1u) ^ 1u) : "memory");
+            }
             const uint64_t dA0 = dbase + (ring16 + (uint32_t)pp * 2u * rowb16), dA1 = dA0 + rowb16;
             if (m >= 1 && m < half && (jp & pmask) != 0u) {        // interior pair, its four accumulators are contiguous
               const uint32_t d0 = tmem_base + (((jp - 1u) & pmask) * 2u) * (uint32_t)p.Cout, C = (uint32_t)p.Cout;
