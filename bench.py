@@ -289,14 +289,14 @@ def run_ours(args):
             rows, tot_f, tot_ms = per_layer_profile(eng, sess, spec, 8, 512, 512)
             ach = tot_f / tot_ms / 1e9
             traffic = None
-            try:   # dram__bytes_read.sum + dram__bytes_write.sum over the same 21 launches, from the committed ncu capture
+            try:   # dram__bytes_read.sum + dram__bytes_write.sum over the same tensor-core launches, from the committed ncu capture
                 with open(os.path.join(ROOT, 'profiles', 'r1_conv_traffic.json')) as f:
                     traffic = json.load(f)['dram_bytes_per_step']
             except Exception:
                 pass
             line['roofline'] = {'bound': 'tensor', 'achieved': ach, 'peak': pk['tf'], 'unit': 'TFLOP/s',
                                 'frac': ach / pk['tf'], 'traffic': traffic, 'peak_source': pk['src'],
-                                'kernel': 'tcgen05 tap-GEMM conv3x3/convT2x2 (the 21 tensor-core launches of one 8-image forward)',
+                                'kernel': 'tcgen05 tap-GEMM conv3x3/convT2x2 (the 22 tensor-core launches of one 8-image forward: 21 layers, dec1a as two channel-split launches)',
                                 'flops_per_step': tot_f, 'conv_ms_per_step': tot_ms,
                                 'whole_step_frac': (8 * spec.flops_forward(512, 512) / (ms / args.steps) / 1e9) / pk['tf_sus']}
             line['per_layer'] = rows

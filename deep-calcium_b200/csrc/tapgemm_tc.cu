@@ -202,12 +202,26 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
       const uint32_t smem16 = smem_u32(smem) >> 4, stage16 = stage_bytes >> 4, a16 = a_bytes >> 4;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      // Split-phase polling of the stage barriers (see the folded strip loop): the non-blocking test of the NEXT
+      // stage's full barrier is issued before this stage's MMAs and consumed one iteration later, so its ~250 cycles
+      // of latency overlap with the MMA issue instead of adding to the 4 x 128 cycles a stage keeps the pipe busy.
+      const uint32_t a_full = smem_u32_pinned(bar_full), a_empty = smem_u32_pinned(bar_empty);
+      asm volatile(".reg .pred p_full;");
+      bool pre = false;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&bar_full[stage], phase);
+          {
+            uint32_t ok = 0;
+            if (pre) asm volatile("selp.u32 %0, 1, 0, p_full;" : "=r"(ok));
+            if (!ok) mbar_wait_a(a_full + 8u * stage, phase);
+            int ns = stage + 1; uint32_t np = phase;
+            if (ns == p.stages) { ns = 0; np ^= 1u; }
+            asm volatile("mbarrier.test_wait.parity.shared::cta.b64 p_full, [%0], %1;" ::"r"(a_full + 8u * ns), "r"(np) : "memory");
+            pre = true;
+          }
           tc_fence_after();
           // descriptors differ only in the 14-bit start-address field: one add per operand and K step keeps
           // the single issuing thread far below the ~89-128 cycles an MMA occupies the tensor pipe
@@ -219,7 +233,7 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
             // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
             if (k < ksteps) umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&bar_empty[stage]);            // smem slot free once these MMAs retire
+          umma_commit_a(a_empty + 8u * stage);       // smem slot free once these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&bar_tfull[acc]);                // accumulator ready for the epilogue
