@@ -1618,6 +1618,11 @@ tapgemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
       const uint64_t dbase_a = make_smem_desc(0, a_blk_bytes, sbo_a, swz_a), dbase_g = make_smem_desc(0, g_blk_bytes, sbo_g, swz_g);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      // hoisted shared addresses + split-phase polling of the stage barriers (see tapgemm_tc_fwd_kernel): a stage is
+      // only four MMAs, so the ~250-cycle barrier poll and the address arithmetic were most of this thread's time
+      const uint32_t smem_a = smem_u32_pinned(smem), a_full = smem_u32_pinned(bar_full), a_empty = smem_u32_pinned(bar_empty);
+      asm volatile(".reg .pred p_wfull;");
+      bool pre = false;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         int kt, nt, tap, split;
         decode(item, kt, nt, tap, split);
@@ -1627,9 +1632,17 @@ tapgemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
         for (int pt = pt0; pt < pt1; ++pt) {
-          mbar_wait(&bar_full[stage], phase);
+          {
+            uint32_t ok = 0;
+            if (pre) asm volatile("selp.u32 %0, 1, 0, p_wfull;" : "=r"(ok));
+            if (!ok) mbar_wait_a(a_full + 8u * stage, phase);
+            int ns = stage + 1; uint32_t np = phase;
+            if (ns == p.stages) { ns = 0; np ^= 1u; }
+            asm volatile("mbarrier.test_wait.parity.shared::cta.b64 p_wfull, [%0], %1;" ::"r"(a_full + 8u * ns), "r"(np) : "memory");
+            pre = true;
+          }
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sa = smem_a + (uint32_t)stage * (uint32_t)stage_bytes;
           const uint32_t sg = sa + a_bytes;
 #pragma unroll
           for (int k = 0; k < WG_P / 16; ++k) {
@@ -1638,7 +1651,7 @@ tapgemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
             const uint64_t dg = dbase_g + ((sg + k * 2 * sbo_g) >> 4);
             umma_bf16(d_tmem, da, dg, idesc, (pt > pt0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&bar_empty[stage]);
+          umma_commit_a(a_empty + 8u * stage);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&bar_tfull[acc]);
