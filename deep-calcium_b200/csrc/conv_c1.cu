@@ -20,49 +20,63 @@ conv3x3_c1_fwd_kernel(const float* __restrict__ x, int N, int H, int W, const fl
   __shared__ __align__(16) float sc[COUT], sh[COUT];
   constexpr int ROWB = COUT * (int)sizeof(T);                 // bytes per pixel
   constexpr int PITCH = ROWB + 16;                            // padded row: conflict-free 16-byte accesses
-  __shared__ __align__(16) uint8_t stage[8][32 * PITCH];
+  constexpr int U = ROWB <= 64 ? 2 : 1;                       // pixels per thread (stage tile must fit 48 KB of static smem)
+  constexpr int PXW = 32 * U;                                 // pixels per warp and iteration
+  __shared__ __align__(16) uint8_t stage[8][PXW * PITCH];
   for (int i = threadIdx.x; i < 9 * COUT; i += blockDim.x) ws[i] = w[i];
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) { sc[i] = scale ? scale[i] : 1.f; sh[i] = shift ? shift[i] : 0.f; }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint8_t* st = stage[warp];
   const long long M = (long long)N * H * W;
-  // block-uniform trip count: every warp handles 32 consecutive pixels per iteration
-  for (long long base = ((long long)blockIdx.x * 8 + warp) * 32; base < M; base += (long long)gridDim.x * 256) {
-    const long long m = base + lane;
-    if (m < M) {
-      const int wq = (int)(m % W), hq = (int)((m / W) % H);
-      const float* img = x + (m - (long long)hq * W - wq);
-      float v[9];
+  // The kernel is bound by the shared-memory pipe (ncu: l1tex 90 %): the weight broadcasts dominate, so every thread
+  // computes U = 2 pixels (lane and lane + 32 of the warp's 64) per weight load.  Block-uniform trip count.
+  for (long long base = ((long long)blockIdx.x * 8 + warp) * PXW; base < M; base += (long long)gridDim.x * 8 * PXW) {
+    float v[U][9];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long m = base + lane + 32 * u;
+      const bool mv = m < M;
+      const long long mm = mv ? m : 0;
+      const int wq = (int)(mm % W), hq = (int)((mm / W) % H);
+      const float* img = x + (mm - (long long)hq * W - wq);
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int ih = hq + t / 3 - 1, iw = wq + t % 3 - 1;
-        v[t] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? img[(long long)ih * W + iw] : 0.f;
+        v[u][t] = (mv && ih >= 0 && ih < H && iw >= 0 && iw < W) ? img[(long long)ih * W + iw] : 0.f;
       }
-      // packed fp32x2 FMAs: two output channels per instruction (the layer is instruction-issue bound otherwise)
+    }
+    // packed fp32x2 FMAs: two output channels per instruction
 #pragma unroll
-      for (int c0 = 0; c0 < COUT; c0 += 4) {
-        float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+    for (int c0 = 0; c0 < COUT; c0 += 4) {
+      float2 a[U][2];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const float4 wv = *reinterpret_cast<const float4*>(&ws[t * COUT + c0]);
-          const float2 vv = make_float2(v[t], v[t]);
-          a0 = ffma2(vv, make_float2(wv.x, wv.y), a0);
-          a1 = ffma2(vv, make_float2(wv.z, wv.w), a1);
+      for (int u = 0; u < U; ++u) { a[u][0] = make_float2(0.f, 0.f); a[u][1] = make_float2(0.f, 0.f); }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float4 wv = *reinterpret_cast<const float4*>(&ws[t * COUT + c0]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float2 vv = make_float2(v[u][t], v[u][t]);
+          a[u][0] = ffma2(vv, make_float2(wv.x, wv.y), a[u][0]);
+          a[u][1] = ffma2(vv, make_float2(wv.z, wv.w), a[u][1]);
         }
-        const float4 s4 = *reinterpret_cast<const float4*>(&sc[c0]), h4 = *reinterpret_cast<const float4*>(&sh[c0]);
-        a0 = ffma2(a0, make_float2(s4.x, s4.y), make_float2(h4.x, h4.y));
-        a1 = ffma2(a1, make_float2(s4.z, s4.w), make_float2(h4.z, h4.w));
-        if (relu) { a0.x = fmaxf(a0.x, 0.f); a0.y = fmaxf(a0.y, 0.f); a1.x = fmaxf(a1.x, 0.f); a1.y = fmaxf(a1.y, 0.f); }
-        store4<T>(reinterpret_cast<T*>(st + lane * PITCH) + c0, make_float4(a0.x, a0.y, a1.x, a1.y));
+      }
+      const float4 s4 = *reinterpret_cast<const float4*>(&sc[c0]), h4 = *reinterpret_cast<const float4*>(&sh[c0]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float2 r0 = ffma2(a[u][0], make_float2(s4.x, s4.y), make_float2(h4.x, h4.y));
+        float2 r1 = ffma2(a[u][1], make_float2(s4.z, s4.w), make_float2(h4.z, h4.w));
+        if (relu) { r0.x = fmaxf(r0.x, 0.f); r0.y = fmaxf(r0.y, 0.f); r1.x = fmaxf(r1.x, 0.f); r1.y = fmaxf(r1.y, 0.f); }
+        store4<T>(reinterpret_cast<T*>(st + (lane + 32 * u) * PITCH) + c0, make_float4(r0.x, r0.y, r1.x, r1.y));
       }
     }
     __syncwarp();
-    // 32 pixels x ROWB bytes = one contiguous block of the output
-    const long long npix = (M - base) < 32 ? (M - base) : 32;
+    // 64 pixels x ROWB bytes = one contiguous block of the output
+    const long long npix = (M - base) < PXW ? (M - base) : PXW;
     uint8_t* dst = reinterpret_cast<uint8_t*>(out + base * COUT);
 #pragma unroll
-    for (int q = 0; q < ROWB / 16; ++q) {
+    for (int q = 0; q < PXW * ROWB / 16 / 32; ++q) {
       const int idx = q * 32 + lane;                           // 16-byte chunk index within the block
       const int px = idx / (ROWB / 16), ch = idx % (ROWB / 16);
       if (px < npix)
