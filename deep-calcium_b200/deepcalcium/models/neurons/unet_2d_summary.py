@@ -399,18 +399,13 @@ class UNet2DSummary(object):
                 sl['ready'].record(copy_stream)
             sl['summ'] = summ
 
-        if len(dataset_paths):
-            stage(0)
-        for i, dsp in enumerate(dataset_paths):
+        scores = [0., 0., 0.]
+
+        def finalize(i):
+            """image i has been enqueued earlier: wait for its mask (pinned buffer) and do the host-side bookkeeping"""
+            dsp = dataset_paths[i]
             name = self.dataset_name_func(dsp)
             sl = slots[i % 2]
-            torch.cuda.current_stream(dev).wait_event(sl['ready'])
-            mask, _ = model.engine.predict_tta(sl['din'], window=window_shape[0], augmentation=augmentation,
-                                               threshold=threshold)
-            sl['hout'].copy_(mask, non_blocking=True)
-            sl['done'].record()
-            if i + 1 < len(dataset_paths):
-                stage(i + 1)                      # host work + H2D of the next image overlap the GPU work of this one
             sl['done'].synchronize()
             mp = sl['hout'].numpy().copy()
             Mp.append(mp)
@@ -419,13 +414,30 @@ class UNet2DSummary(object):
                 m = self.mask_summary_func(dsp)
                 p, r, comb = _pixel_scores(m, mp)
                 logger.info('%s: prec=%.3lf, reca=%.3lf, comb=%.3lf' % (name, p, r, comb))
-                mean_prec += p / len(dataset_paths)
-                mean_reca += r / len(dataset_paths)
-                mean_comb += comb / len(dataset_paths)
+                for k, v in enumerate((p, r, comb)):
+                    scores[k] += v / len(dataset_paths)
             if save:
                 save_path = '%s/%s_mp.npy' % (self.cpdir, name)
                 np.save(save_path, mp)
                 logger.info('Saved %s' % save_path)
+
+        if len(dataset_paths):
+            stage(0)
+        for i, dsp in enumerate(dataset_paths):
+            sl = slots[i % 2]
+            torch.cuda.current_stream(dev).wait_event(sl['ready'])
+            mask, _ = model.engine.predict_tta(sl['din'], window=window_shape[0], augmentation=augmentation,
+                                               threshold=threshold)
+            sl['hout'].copy_(mask, non_blocking=True)      # in stream order: before image i+1 overwrites the static mask
+            sl['done'].record()
+            # image i is now queued on the GPU; meanwhile collect image i-1 (frees its slot) and stage image i+1 into it
+            if i >= 1:
+                finalize(i - 1)
+            if i + 1 < len(dataset_paths):
+                stage(i + 1)
+        if len(dataset_paths):
+            finalize(len(dataset_paths) - 1)
+        mean_prec, mean_reca, mean_comb = scores
         if print_scores:
             logger.info('Mean prec=%.3lf, reca=%.3lf, comb=%.3lf' % (mean_prec, mean_reca, mean_comb))
             self.last_scores = dict(prec=mean_prec, reca=mean_reca, comb=mean_comb)
