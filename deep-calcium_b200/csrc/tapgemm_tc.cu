@@ -356,15 +356,16 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
 // conv3x3 for the wide, shallow layers (W % 128 == 0, 9*Cin*Cout*2 bytes of weights fit in smem):
 // the layers where the generic kernel is bound by re-loading the activations 9x (once per tap).
 //   * all 9 x nkc weight tiles stay resident in shared memory for the whole (persistent) CTA;
-//   * a work item is a strip of R output rows x 128 pixels; the producer streams its R+2 halo rows
-//     ([130 px x BK ch] TMA boxes, zero filled outside the image) through a ring, so every activation
-//     row is fetched once per strip (1 + 2/R instead of 9 times);
+//   * a CTA walks a strip of output rows x 128 pixels (balanced partition, see the kernel); the producer streams
+//     the strip's rows + 2 halo rows ([130 px x BK ch] TMA boxes, zero filled outside the image) through a ring,
+//     so every activation row is fetched about once instead of 9 times;
 //   * the three horizontal taps read the SAME halo row: the A descriptor simply starts dx pixels
 //     (dx * row pitch bytes) further into the swizzled tile.  The swizzle XOR is a function of the
 //     absolute smem address, so a row-shifted start address needs no base-offset correction
 //     (verified on B200: profiles/r1_umma_row_shift_probe.log);
-//   * the three vertical taps read three consecutive ring rows.
-// MMA issue of one strip tile: 9 taps x nkc channel chunks x KSTEPS MMAs.  Templated so that the single issuing
+//   * the three vertical taps read three consecutive ring rows (plain mode) or are folded into the MMA N
+//     dimension (FOLD mode, see the kernel).
+// Plain-mode MMA issue of one strip tile: 9 taps x nkc channel chunks x KSTEPS MMAs.  Templated so that the single issuing
 // thread runs straight-line code (every extra dependent instruction between two tcgen05.mma shows up directly
 // in the tensor-pipe utilisation of these short-K tiles).  Weight tiles are laid out (tap, kc)-major, so the
 // weight descriptor simply advances by one tile per step.
@@ -467,9 +468,10 @@ struct TcStripParams {
   const float* shift;
 };
 
-//
-// FOLD (Cout 32 or 64, normal orientation): an MMA with N = Cout is charged like a much wider one by the tensor pipe
-// (profiles/r1_umma_rate_probe.log), so these layers are issue-rate bound at 9*K/16 MMAs per tile.  Folded mode turns
+// Roles: warp 0 = TMA producer, warp 1 = single-thread MMA issuer, warps 2..9 = two epilogue quartets (a quartet
+// drains a pair of consecutive 128-pixel tiles, then skips the other quartet's pair).
+// FOLD (Cout 32 or 64, normal orientation): an MMA costs the issuing thread ~60 cycles whatever its N is
+// (profiles/r1_umma_fold_probe.log), so these layers are issue-rate bound at 9*K/16 MMAs per tile.  Folded mode turns
 // the loop inside out: TMEM holds a ring of 512/Cout row accumulators (one per OUTPUT row), and each INPUT halo row i
 // is multiplied ONCE per (dx, k) against the stacked weights [W(dy=+1) | W(dy=0) | W(dy=-1)] (N = 3*Cout), which
 // accumulates into the three neighbouring accumulators of output rows i-1, i, i+1 at the same time: 3x fewer MMAs,
@@ -494,9 +496,8 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   const uint32_t w_bytes = 9u * p.nkc * wblk_bytes;
   uint8_t* s_w = smem;
   uint8_t* s_ring = smem + ((w_bytes + 1023) & ~1023u);
-  const uint32_t row_bytes_ = (uint32_t)p.nkc * p.slot_bytes;
-  uint8_t* s_stage = s_ring + (size_t)p.ring * row_bytes_;       // swapped mode only: 4 x 4 KB transpose tiles behind the ring
   const uint32_t row_bytes = (uint32_t)p.nkc * p.slot_bytes;     // one halo row = nkc chunk boxes
+  uint8_t* s_stage = s_ring + (size_t)p.ring * row_bytes;        // swapped mode only: 4 x 4 KB transpose tiles behind the ring
   const uint32_t box_bytes = (uint32_t)(PX + 2) * p.BK * 2u;
   const int acc_cols = p.swap ? 256 : p.Cout;
   // Normal orientation: draining a [128 px x Cout] accumulator (TMEM load latency + convert + stores) takes a warp
