@@ -312,6 +312,31 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, int ldy, int offy, const T* __
   }
 }
 
+// ---------------------------------------------------------------- training crop sampler (device half)
+// The reference's _batch_gen (unet_2d_summary.py:434-530) draws, per crop, a dataset, a neuron-centred window with
+// jitter and a random sequence of flips / rot90s with the global numpy RNG, then slices, zero-fills and transforms the
+// window in a Python loop.  Here the host keeps the RNG stream (a handful of integers per crop) and the device does the
+// pixel work: desc[b] = {dataset, y0, x0, valid rows, valid cols, m00, m01, m10, m11, t0, t1, 0}; output pixel (i, j)
+// of crop b reads window position (wi, wj) = (m00*i + m01*j + t0, m10*i + m11*j + t1) - the composition of the
+// crop's flips / rotations as one affine index map on the square window - and is 0 outside the valid part.
+__global__ void crop_batch_kernel(const long long* __restrict__ img_ptrs, const long long* __restrict__ mask_ptrs,
+                                  const int* __restrict__ widths, const int* __restrict__ desc, int B, int n,
+                                  float* __restrict__ xo, uint8_t* __restrict__ yo) {
+  const long long total = (long long)B * n * n;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % n), i = (int)((idx / n) % n), b = (int)(idx / ((long long)n * n));
+    const int* d = desc + 12 * b;
+    const int wi = d[5] * i + d[6] * j + d[9], wj = d[7] * i + d[8] * j + d[10];
+    float v = 0.f; uint8_t m = 0;
+    if (wi >= 0 && wi < d[3] && wj >= 0 && wj < d[4]) {
+      const long long off = (long long)(d[1] + wi) * widths[d[0]] + (d[2] + wj);
+      v = reinterpret_cast<const float*>(img_ptrs[d[0]])[off];
+      m = reinterpret_cast<const uint8_t*>(mask_ptrs[d[0]])[off];
+    }
+    xo[idx] = v; yo[idx] = m;
+  }
+}
+
 // ---------------------------------------------------------------- nearest 2x upsampling (+dropout)
 // UpSampling2D of the non-default `upsampling_or_transpose='upsampling'` graph (unet_2d_summary.py:160-161), followed by
 // the Dropout that the reference applies to the upsampled tensor (:198-216).  y[n][2h+a][2w+b][c] = x[n][h][w][c] * keep.
@@ -857,6 +882,17 @@ extern "C" int dcb_bn_bwd_apply(int dtype, const float* dy, int ldy, int offy, c
   }
   g_launches += 1;
   DCB_LAUNCH_OK("bn_bwd_apply_kernel");
+  return DCB_OK;
+}
+
+extern "C" int dcb_crop_batch(const long long* img_ptrs, const long long* mask_ptrs, const int* widths, const int* desc,
+                              int B, int window, float* x_out, unsigned char* y_out, dcb_stream_t stream) {
+  DCB_CHECK_ARG(img_ptrs && mask_ptrs && widths && desc && x_out && y_out && B > 0 && window > 0, "dcb_crop_batch: bad arguments");
+  const long long total = (long long)B * window * window;
+  crop_batch_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(img_ptrs, mask_ptrs, widths, desc, B, window, x_out,
+                                                                           y_out);
+  g_launches += 1;
+  DCB_LAUNCH_OK("crop_batch_kernel");
   return DCB_OK;
 }
 

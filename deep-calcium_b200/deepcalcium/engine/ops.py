@@ -211,6 +211,12 @@ def bn_bwd_apply(dy, ldy, offy, x, scale, shift, mean, rstd, sums, draw, dgamma,
 
 
 # ---------------------------------------------------------------- pooling
+def crop_batch(img_ptrs, mask_ptrs, widths, desc, window, x_out, y_out):
+    """tables: int64 [D], int64 [D], int32 [D]; desc int32 [B, 12]; x_out fp32 [B, n, n]; y_out uint8 [B, n, n]"""
+    call('dcb_crop_batch', ptr(img_ptrs), ptr(mask_ptrs), ptr(widths), ptr(desc), c_int(desc.shape[0]), c_int(window),
+         ptr(x_out), ptr(y_out), stream_ptr())
+
+
 def upsample2x(x, y, p_drop=0., seed=0, seed_dev=None, layer=0):
     N, h, w, C = x.shape
     call('dcb_upsample2x', _dt(x), ptr(x), c_int(N), c_int(h), c_int(w), c_int(C), c_f(p_drop), c_ull(seed), ptr(seed_dev),

@@ -90,8 +90,9 @@ class UNetModel(object):
     def train_on_batch(self, x, y):
         """One optimiser step; returns [loss, F1, prec, reca, dice, dicesq, posyt, posyp]."""
         import torch
-        x = torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float32))).cuda()
-        y = torch.from_numpy(np.ascontiguousarray(np.asarray(y, dtype=np.uint8))).cuda()
+        if not (torch.is_tensor(x) and x.is_cuda):       # host batches (reference-style generators) are uploaded here
+            x = torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float32))).cuda()
+            y = torch.from_numpy(np.ascontiguousarray(np.asarray(y, dtype=np.uint8))).cuda()
         o = self.optimizer
         m = self.engine.train_step(x, y, loss=self.loss, lr=o.lr, dropout=self.dropout, beta1=o.beta_1,
                                    beta2=o.beta_2, eps=o.epsilon)
@@ -245,7 +246,13 @@ class UNet2DSummary(object):
         M_summ = [self.mask_summary_func(dsp) for dsp in dataset_paths]
         ycval = [(s.shape[0] - int(s.shape[0] * prop_val), s.shape[0]) for s in S_summ]
         yctrn = [(0, int(s.shape[0] * prop_trn)) for s in S_summ]
-        gen_trn = self._batch_gen(S_summ, M_summ, names, yctrn, batch_size_trn, nb_steps_trn, shape_trn, 15)
+        # same RNG stream and the same crops as _batch_gen, but the pixel work (slice, zero fill, flips / rot90s) runs
+        # on the GPU and the batch never visits the host (DEEP_CALCIUM_HOST_SAMPLER=1 selects the host restatement)
+        if os.environ.get('DEEP_CALCIUM_HOST_SAMPLER') == '1':
+            gen_trn = self._batch_gen(S_summ, M_summ, names, yctrn, batch_size_trn, nb_steps_trn, shape_trn, 15)
+        else:
+            gen_trn = self._batch_gen_device(S_summ, M_summ, names, yctrn, batch_size_trn, nb_steps_trn, shape_trn, 15,
+                                             device=model.engine.dev)
 
         tic = int(time())
         csv_path = '%s/%d_metrics.csv' % (self.cpdir, tic)
@@ -363,6 +370,102 @@ class UNet2DSummary(object):
                     s_batch[b_idx], m_batch[b_idx] = aug(s_batch[b_idx], m_batch[b_idx])
             nb_yields += 1
             yield s_batch, m_batch
+
+    # D4 elements of the sampler's augment_funcs as index maps on an n x n window: out[i, j] = a[M @ (i, j) + t]
+    @staticmethod
+    def _aug_maps(n):
+        return [((1, 0, 0, 1), (0, 0)),              # identity
+                ((1, 0, 0, -1), (0, n - 1)),         # a[:, ::-1]
+                ((-1, 0, 0, 1), (n - 1, 0)),         # a[::-1, :]
+                ((0, 1, -1, 0), (0, n - 1)),         # np.rot90(a, 1): out[i, j] = a[j, n-1-i]
+                ((-1, 0, 0, -1), (n - 1, n - 1)),    # np.rot90(a, 2)
+                ((0, -1, 1, 0), (n - 1, 0))]         # np.rot90(a, 3): out[i, j] = a[n-1-j, i]
+
+    def _crop_descriptors(self, S_summ, M_summ, names, y_coords, batch_size, nb_steps, window_shape,
+                          nb_max_augment=0, scores_path=None):
+        """The random half of _batch_gen (unet_2d_summary.py:434-530): yields int32 [batch, 12] crop descriptors
+        {dataset, y0, x0, valid rows, valid cols, m00, m01, m10, m11, t0, t1, 0} drawing from the global numpy RNG in
+        exactly the order _batch_gen does, so both produce the same crops from the same seed."""
+        rng = np.random
+        hw, ww = window_shape
+        assert hw == ww, 'the flips / rotations are composed on a square window'
+        maps = self._aug_maps(hw)
+        nb_yields = 0
+        neuron_locs = []
+        for ds_idx, m in enumerate(M_summ):
+            ymin, ymax = y_coords[ds_idx]
+            neuron_locs.append(list(zip(*np.where(m[ymin:ymax, :] == 1))))
+        ds_idxs = np.arange(len(S_summ))
+        ds_idxp = np.ones((len(ds_idxs))) / len(ds_idxs)
+        while True:
+            if scores_path and os.path.exists(scores_path) and (nb_yields - 1) % nb_steps == 0:
+                with open(scores_path, 'rb') as fp:
+                    names_to_scores = pickle.load(fp)
+                ds_idxp = np.array([1 - np.mean(names_to_scores[n]) for n in names])
+                ds_idxp /= np.sum(ds_idxp)
+            desc = np.zeros((batch_size, 12), dtype=np.int32)
+            for b_idx in range(batch_size):
+                ds_idx = rng.choice(np.arange(len(S_summ)), p=ds_idxp)
+                hs, ws = S_summ[ds_idx].shape
+                ymin, ymax = y_coords[ds_idx]
+                cy, cx = neuron_locs[ds_idx][rng.randint(0, len(neuron_locs[ds_idx]))]
+                cy = min(max(ymin, cy + rng.randint(-5, 5)), ymax)
+                cx = min(max(0, cx + rng.randint(-5, 5)), ws)
+                y0 = max(ymin, int(cy - (hw / 2)))
+                y1 = min(y0 + hw, ymax)
+                x0 = max(0, int(cx - (ww / 2)))
+                x1 = min(x0 + ww, ws)
+                nb_augment = rng.randint(0, nb_max_augment + 1)
+                M, t = (1, 0, 0, 1), (0, 0)
+                for k in rng.choice(len(maps), nb_augment):        # same draw as rng.choice(augment_funcs, nb_augment)
+                    (a, b, c, d), (t0, t1) = maps[int(k)]
+                    # cur = aug(prev): cur[p] = prev[Mk p + tk] = a[M (Mk p + tk) + t]
+                    t = (M[0] * t0 + M[1] * t1 + t[0], M[2] * t0 + M[3] * t1 + t[1])
+                    M = (M[0] * a + M[1] * c, M[0] * b + M[1] * d, M[2] * a + M[3] * c, M[2] * b + M[3] * d)
+                desc[b_idx] = (ds_idx, y0, x0, y1 - y0, x1 - x0, M[0], M[1], M[2], M[3], t[0], t[1], 0)
+            nb_yields += 1
+            yield desc
+
+    @staticmethod
+    def _apply_descriptors_host(S_summ, M_summ, desc, n):
+        """numpy statement of dcb_crop_batch (used by the CPU tests to pin the descriptors against _batch_gen)"""
+        B = desc.shape[0]
+        xs = np.zeros((B, n, n), np.float32); ys = np.zeros((B, n, n), np.uint8)
+        ii, jj = np.meshgrid(np.arange(n), np.arange(n), indexing='ij')
+        for b in range(B):
+            ds, y0, x0, vh, vw, m00, m01, m10, m11, t0, t1, _ = (int(v) for v in desc[b])
+            wi, wj = m00 * ii + m01 * jj + t0, m10 * ii + m11 * jj + t1
+            ok = (wi >= 0) & (wi < vh) & (wj >= 0) & (wj < vw)
+            xs[b][ok] = S_summ[ds][y0 + wi[ok], x0 + wj[ok]]
+            ys[b][ok] = M_summ[ds][y0 + wi[ok], x0 + wj[ok]]
+        return xs, ys
+
+    def _batch_gen_device(self, S_summ, M_summ, names, y_coords, batch_size, nb_steps, window_shape,
+                          nb_max_augment=0, scores_path=None, device=None):
+        """_batch_gen with the pixel work on the GPU (dcb_crop_batch): yields (x, y) CUDA tensors.  The summary images
+        and masks are uploaded once; per batch only the [batch, 12] int32 descriptors cross PCIe."""
+        import torch
+        from ...engine import ops
+        dev = device if device is not None else torch.device('cuda', torch.cuda.current_device())
+        imgs = [torch.from_numpy(np.ascontiguousarray(np.asarray(s, dtype=np.float32))).to(dev) for s in S_summ]
+        msks = [torch.from_numpy(np.ascontiguousarray(np.asarray(m, dtype=np.uint8))).to(dev) for m in M_summ]
+        iptr = torch.tensor([t.data_ptr() for t in imgs], dtype=torch.int64, device=dev)
+        mptr = torch.tensor([t.data_ptr() for t in msks], dtype=torch.int64, device=dev)
+        wid = torch.tensor([t.shape[1] for t in imgs], dtype=torch.int32, device=dev)
+        n = window_shape[0]
+        xb = torch.empty(batch_size, n, n, dtype=torch.float32, device=dev)
+        yb = torch.empty(batch_size, n, n, dtype=torch.uint8, device=dev)
+        hdesc = torch.empty(batch_size, 12, dtype=torch.int32).pin_memory()
+        ddesc = torch.empty(batch_size, 12, dtype=torch.int32, device=dev)
+        for desc in self._crop_descriptors(S_summ, M_summ, names, y_coords, batch_size, nb_steps, window_shape,
+                                           nb_max_augment, scores_path):
+            # the previous batch's kernel has consumed ddesc once the stream reaches this copy (same stream, in order);
+            # hdesc is reused only after the copy that read it has finished
+            torch.cuda.current_stream(dev).synchronize()
+            hdesc.copy_(torch.from_numpy(desc))
+            ddesc.copy_(hdesc, non_blocking=True)
+            ops.crop_batch(iptr, mptr, wid, ddesc, n, xb, yb)
+            yield xb, yb
 
     # ------------------------------------------------------------------ predict / evaluate
     def predict(self, dataset_paths, model_path, window_shape=(512, 512), print_scores=False,

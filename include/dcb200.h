@@ -173,6 +173,13 @@ int dcb_bn_bwd_apply(int dtype, const float* dy, int ldy, int offy, const void* 
                      const double* sums, long long M_total, float dgb_scale, void* draw, float* dgamma,
                      float* dbeta, dcb_stream_t stream);
 
+/* Device half of the training crop sampler (unet_2d_summary.py:434-530, _batch_gen): B crops of window x window pixels.
+ * img_ptrs / mask_ptrs / widths: device tables over the datasets (fp32 summary images, uint8 masks, row pitch in pixels).
+ * desc: device int32 [B][12] = {dataset, y0, x0, valid rows, valid cols, m00, m01, m10, m11, t0, t1, 0}: output pixel
+ * (i, j) reads window position (m00*i + m01*j + t0, m10*i + m11*j + t1) (the composed flips / rot90s), zero outside the
+ * valid rows x cols.  The host keeps the reference's RNG stream and only ships these integers. */
+int dcb_crop_batch(const long long* img_ptrs, const long long* mask_ptrs, const int* widths, const int* desc, int B,
+                   int window, float* x_out, unsigned char* y_out, dcb_stream_t stream);
 /* nearest-neighbour 2x upsampling (UpSampling2D of the `upsampling_or_transpose='upsampling'` graph, unet_2d_summary.py:160-161)
  * with the Dropout the reference applies to the upsampled tensor folded in (p_drop = 0: none): x [N][h][w][C] -> y [N][2h][2w][C];
  * backward sums the (masked) 2x2 gradient blocks of the fp32 view dy (row stride ldy, channel offset offy) into dx [N][h][w][C] */
