@@ -144,3 +144,108 @@ def nf_load_hdf5(names, datasets_dir=None):
             raise FileNotFoundError('%s/%s: no prepared dataset; download + TIFF decode (nf.py:73-127) are out '
                                     'of scope here - build one with make_dataset()' % (datasets_dir, name))
     return paths
+
+
+# ------------------------------------------------------------------------------------------------- scoring (N3)
+# datasets/nf.py:153-229 of the reference scores a predicted mask by converting both masks to connected regions
+# (skimage.measure.label, default = 8-connectivity in 2-D) and calling `neurofinder.centers` / `neurofinder.shapes`
+# (neurofinder==1.1.1 on regional==1.1.2, requirements.txt).  Neither package is importable here, so their published
+# algorithm is restated (PARITY UNPINNED, like the rest of the oracle-backed path):
+#   match(a, b, threshold): for every region s of a, in order: the nearest REMAINING region of b by centre distance
+#       (centre = mean of the pixel coordinates); it is taken (and removed from b) if that distance < threshold.
+#   centers(a, b, threshold=5) -> (recall, precision) = (#matched pairs with distance < threshold) / len(a), / len(b)
+#   shapes(a, b, threshold=5)  -> (inclusion, exclusion) = mean over the matched pairs of
+#       (|s_a & s_b| / |s_a|, |s_a & s_b| / |s_b|)  (regional.one.overlap(method='rates')); (0, 0) without pairs.
+
+def _label_regions(m):
+    """Connected components of a binary mask as a list of [k, 2] (row, col) coordinate arrays, 8-connected, numbered
+    in raster order of their first pixel (skimage.measure.label's numbering)."""
+    from scipy import ndimage
+    lbl, n = ndimage.label(np.asarray(m) != 0, structure=np.ones((3, 3), dtype=bool))
+    if n == 0:
+        return []
+    order = np.argsort(lbl.ravel(), kind='stable')
+    flat = lbl.ravel()[order]
+    starts = np.searchsorted(flat, np.arange(1, n + 2))
+    rows, cols = np.unravel_index(order, lbl.shape)
+    return [np.stack([rows[starts[k]:starts[k + 1]], cols[starts[k]:starts[k + 1]]], axis=1) for k in range(n)]
+
+
+def _match_regions(a, b, threshold):
+    """neurofinder.match: index into b (or None) for every region of a."""
+    ca = [r.mean(axis=0) for r in a]
+    targets = np.array([r.mean(axis=0) for r in b], dtype=np.float64).reshape(len(b), 2)
+    target_inds = list(range(len(b)))
+    out = []
+    for c in ca:
+        hit = None
+        if len(target_inds):
+            d = np.sqrt(((targets - c[np.newaxis]) ** 2).sum(axis=1))
+            k = int(np.argmin(d))
+            if d[k] < threshold:
+                hit = target_inds[k]
+                targets = np.delete(targets, k, axis=0)
+                del target_inds[k]
+        out.append(hit)
+    return out
+
+
+def nf_centers(a, b, threshold=5):
+    """neurofinder.centers on two region lists -> (recall, precision)."""
+    inds = _match_regions(a, b, threshold)
+    n = 0
+    for ra, ib in zip(a, inds):
+        if ib is not None and np.sqrt(((ra.mean(axis=0) - b[ib].mean(axis=0)) ** 2).sum()) < threshold:
+            n += 1
+    with np.errstate(divide='ignore', invalid='ignore'):
+        return np.float64(n) / np.float64(len(a)), np.float64(n) / np.float64(len(b))
+
+
+def nf_shapes(a, b, threshold=5):
+    """neurofinder.shapes on two region lists -> (inclusion, exclusion)."""
+    inds = _match_regions(a, b, threshold)
+    rates = []
+    for ra, ib in zip(a, inds):
+        if ib is None:
+            continue
+        sa = set(map(tuple, ra.tolist()))
+        nhit = float(sum(1 for xy in map(tuple, b[ib].tolist()) if xy in sa))
+        rates.append((nhit / len(ra), nhit / len(b[ib])))
+    if not rates:
+        return 0.0, 0.0
+    r = np.asarray(rates, dtype=np.float64).mean(axis=0)
+    return float(r[0]), float(r[1])
+
+
+def nf_mask_metrics(m, mp):
+    """datasets/nf.py:153-174: precision, recall, inclusion, exclusion and combined (F1) score of a predicted mask.
+    Single 2-D masks, overlapping neurons are not accounted for (as in the reference)."""
+    mp = np.asarray(mp)
+    if np.sum(mp.round()) == 0:
+        return 0., 0., 0., 0., 0.
+    a, b = _label_regions(m), _label_regions(mp)
+    r, p = nf_centers(a, b)
+    i, e = nf_shapes(a, b)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        f1 = np.float64(2.) * (r * p) / (r + p)
+    return (float(p), float(r), float(i), float(e), float(f1))
+
+
+def nf_submit(Mp, names, json_path):
+    """datasets/nf.py:177-217: Neurofinder submission JSON.  Kept bug-compatible with the reference: the region loop is
+    `range(1, max_label)`, i.e. the LAST connected component of every mask is not written."""
+    import json
+    logger = logging.getLogger(funcname())
+    submission = []
+    for mp, name in zip(Mp, names):
+        if name.startswith('neurofinder.'):
+            name = '.'.join(name.split('.')[1:])
+        regs = _label_regions(mp)
+        if len(regs) == 0:
+            regions = [{'coordinates': [[[0, 0]]]}]
+        else:
+            regions = [{'coordinates': [[int(y), int(x)] for y, x in r.tolist()]} for r in regs[:len(regs) - 1]]
+        submission.append({'dataset': name, 'regions': regions})
+    with open(json_path, 'w') as fp:
+        json.dump(submission, fp)
+    logger.info('Saved submission to %s.' % json_path)

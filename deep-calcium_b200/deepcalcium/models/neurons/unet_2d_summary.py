@@ -22,7 +22,7 @@ from ...utils.runtime import funcname
 from ...utils import neurons as _un
 from ...utils.neurons import (F1, prec, reca, dice, dicesq, dice_loss, dicesq_loss, posyt, posyp,
                               weighted_binary_crossentropy, binary_crossentropy)
-from ...datasets.nf import open_dataset
+from ...datasets.nf import open_dataset, nf_mask_metrics
 
 MODEL_URL_LATEST = 'https://github.com/alexklibisz/deep-calcium/releases/download/v0.0.1-weights/unet2ds_model.hdf5'
 METRIC_NAMES = ['loss', 'F1', 'prec', 'reca', 'dice', 'dicesq', 'posyt', 'posyp']   # unet_2d_summary.py:398-399
@@ -192,8 +192,8 @@ def _name_dataset(dspath):
 
 
 def _pixel_scores(m, mp):
-    """Pixel-level precision / recall / F1 (utils/neurons.py:32-50 on hard masks).  Stands in for
-    nf_mask_metrics (datasets/nf.py:153-174, third-party `neurofinder` matching) which is not built."""
+    """Pixel-level precision / recall / F1 (utils/neurons.py:32-50 on hard masks); kept as a cheap diagnostic next to
+    the region-level nf_mask_metrics the reference reports."""
     m, mp = np.asarray(m, np.float64), np.asarray(mp, np.float64)
     return float(prec(m, mp)), float(reca(m, mp)), float(F1(m, mp))
 
@@ -292,8 +292,8 @@ class UNet2DSummary(object):
 
     def _validate(self, model, S_summ, M_summ, names, y_coords, shape_val, epoch):
         """_ValidationMetricsCB.on_epoch_end (:62-120): six orientations of every dataset at the
-        validation window, scored inside the validation rows.  Scores are pixel-level (see
-        _pixel_scores) until the neurofinder matching is built."""
+        validation window, scored inside the validation rows with nf_mask_metrics (region matching of the
+        `neurofinder` package, restated in deepcalcium.datasets.nf)."""
         hw, ww = shape_val
 
         def pad(x):
@@ -310,7 +310,7 @@ class UNet2DSummary(object):
                 yy, xx = np.where(f(vm) == 1)
                 a0, a1, b0, b1 = min(yy), max(yy), min(xx), max(xx)
                 mp = self._predict_window(model, pad(fs), hw)[:fs.shape[0], :fs.shape[1]]
-                p, r, f1 = _pixel_scores(fm[a0:a1, b0:b1], mp[a0:a1, b0:b1].round())
+                p, r, _, _, f1 = nf_mask_metrics(fm[a0:a1, b0:b1], mp[a0:a1, b0:b1].round())
                 pp.append(p); rr.append(r); ff.append(f1)
         eps = 1e-4 * epoch if epoch else 0
         return {'val_nf_f1_mean': float(np.mean(ff) + eps), 'val_nf_f1_median': float(np.median(ff) + eps),
@@ -515,8 +515,8 @@ class UNet2DSummary(object):
             names.append(name)
             if print_scores:
                 m = self.mask_summary_func(dsp)
-                p, r, comb = _pixel_scores(m, mp)
-                logger.info('%s: prec=%.3lf, reca=%.3lf, comb=%.3lf' % (name, p, r, comb))
+                p, r, incl, excl, comb = nf_mask_metrics(m, mp.round())
+                logger.info('%s: prec=%.3lf, reca=%.3lf, incl=%.3lf, excl=%.3lf, comb=%.3lf' % (name, p, r, incl, excl, comb))
                 for k, v in enumerate((p, r, comb)):
                     scores[k] += v / len(dataset_paths)
             if save:

@@ -116,3 +116,41 @@ def test_weight_list_order_is_keras_get_weights_order():
     assert lst[0].shape == (3, 3, 1, 32) and lst[1].shape == (32,) and lst[-2].shape == (1, 1, 32, 2)
     back = oracle.keras_list_to_weights(lst, spec)
     assert all(np.array_equal(back[k], w[k]) for k in w)
+
+
+# ------------------------------------------------------------------ N3: neurofinder-style scoring (datasets/nf.py:153-229)
+def test_nf_mask_metrics_known_answers():
+    """Region matching of `neurofinder.centers` / `shapes` (restated, third-party package absent) on hand-computed cases."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'deep-calcium_b200'))
+    from deepcalcium.datasets.nf import nf_mask_metrics, _label_regions
+    m = np.zeros((40, 40), np.uint8)
+    m[5:10, 5:10] = 1; m[20:26, 20:26] = 1; m[30:33, 3:6] = 1
+    assert nf_mask_metrics(m, m) == (1.0, 1.0, 1.0, 1.0, 1.0)
+    assert nf_mask_metrics(m, np.zeros_like(m)) == (0., 0., 0., 0., 0.)
+    mp = np.zeros_like(m)
+    mp[6:11, 5:10] = 1          # region 1 shifted one row: overlap 20 / 25
+    mp[20:26, 22:28] = 1        # region 2 shifted two columns: overlap 24 / 36
+    p, r, i, e, f1 = nf_mask_metrics(m, mp)
+    assert p == 1.0 and abs(r - 2. / 3) < 1e-12 and abs(i - (0.8 + 2. / 3) / 2) < 1e-12 and abs(e - i) < 1e-12
+    assert abs(f1 - 0.8) < 1e-12
+    far = np.zeros_like(m); far[5:10, 15:20] = 1     # centre 10 px away: beyond the 5 px threshold -> no match
+    p, r, i, e, f1 = nf_mask_metrics(m, far)
+    assert p == 0.0 and r == 0.0 and (i, e) == (0.0, 0.0) and np.isnan(f1)
+    # 8-connectivity (skimage.measure.label default in 2-D): diagonal neighbours are one region
+    d = np.zeros((6, 6), np.uint8); d[1, 1] = d[2, 2] = d[3, 3] = 1; d[0, 5] = 1
+    regs = _label_regions(d)
+    assert [len(x) for x in regs] == [1, 3] and regs[0].tolist() == [[0, 5]]
+
+
+def test_nf_submit_is_bug_compatible(tmp_path):
+    import sys, os, json
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'deep-calcium_b200'))
+    from deepcalcium.datasets.nf import nf_submit
+    m = np.zeros((10, 10), np.uint8); m[1:3, 1:3] = 1; m[6:8, 6:9] = 1
+    path = str(tmp_path / 'sub.json')
+    nf_submit([m, np.zeros_like(m)], ['neurofinder.00.00', 'x'], path)
+    sub = json.load(open(path))
+    assert sub[0]['dataset'] == '00.00' and len(sub[0]['regions']) == 1      # range(1, max) drops the last region
+    assert sub[0]['regions'][0]['coordinates'] == [[1, 1], [1, 2], [2, 1], [2, 2]]
+    assert sub[1]['regions'] == [{'coordinates': [[[0, 0]]]}]
