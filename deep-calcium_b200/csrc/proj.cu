@@ -120,6 +120,119 @@ __global__ void proj_finalize_kernel(const double* __restrict__ psum, const floa
   max_out[p] = m;
 }
 
+// ---- int16 movies (the reference's TIFF frames are int16, datasets/nf.py:115-130): half the bytes per frame ----
+// A thread owns 8 consecutive pixels (one 16-byte load per frame).  Sums are exact: int32 over the U frames of one
+// unrolled pass (U * 32767 < 2^31), then int64; max with the packed signed-16 SIMD max.  Same CTA layout (PXT pixel
+// lanes x TG frame groups), same [split][P] double / float partial format and finalize kernel as the fp32 path.
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+template <int PXT, int TG, int U>
+__global__ void __launch_bounds__(PXT * TG)
+proj_partial_i16_kernel(const short* __restrict__ movie, int T, long long P, int t_splits, double* __restrict__ psum,
+                        float* __restrict__ pmax, float* __restrict__ mean_out, float* __restrict__ max_out, int floor0) {
+  const int px = threadIdx.x % PXT;
+  const int g = threadIdx.x / PXT;
+  const long long p0 = ((long long)blockIdx.x * PXT + px) * 8;   // first of my 8 pixels
+  const int split = blockIdx.y;
+  const int t_begin = (int)(((long long)T * split) / t_splits);
+  const int t_end = (int)(((long long)T * (split + 1)) / t_splits);
+  long long s[8];
+  uint32_t mx[4];                                                // 4 x packed (int16, int16) running max
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) mx[i] = 0x80008000u;               // (-32768, -32768)
+  if (p0 < P) {
+    const uint4* base = reinterpret_cast<const uint4*>(movie + p0);
+    const long long fstride = P / 8;                             // uint4 per frame
+    auto accumulate = [&](const uint4& v, int (&a)[8]) {
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        mx[i] = __vmaxs2(mx[i], w[i]);
+        a[2 * i] += (int)(short)(w[i] & 0xffffu);
+        a[2 * i + 1] += (int)w[i] >> 16;
+      }
+    };
+    int t = t_begin + g;
+    for (; t + (U - 1) * TG < t_end; t += U * TG) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = ldg_stream_u4(base + (long long)(t + u * TG) * fstride);
+      int a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int u = 0; u < U; ++u) accumulate(v[u], a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += a[i];
+    }
+    for (; t < t_end; t += TG) {
+      const uint4 v = ldg_stream_u4(base + (long long)t * fstride);
+      int a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      accumulate(v, a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += a[i];
+    }
+  }
+  // combine the TG frame groups of this CTA in a fixed order (integer sums: order does not matter, max neither)
+  __shared__ long long sh_sum[(TG > 1) ? (TG - 1) * PXT * 8 : 1];
+  __shared__ uint32_t sh_max[(TG > 1) ? (TG - 1) * PXT * 4 : 1];
+  if (TG > 1) {
+    if (g > 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sh_sum[((g - 1) * PXT + px) * 8 + i] = s[i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sh_max[((g - 1) * PXT + px) * 4 + i] = mx[i];
+    }
+    __syncthreads();
+    if (g == 0) {
+      for (int gg = 1; gg < TG; ++gg) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] += sh_sum[((gg - 1) * PXT + px) * 8 + i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mx[i] = __vmaxs2(mx[i], sh_max[((gg - 1) * PXT + px) * 4 + i]);
+      }
+    }
+  }
+  if (g != 0 || p0 >= P) return;
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { m[2 * i] = (float)(short)(mx[i] & 0xffffu); m[2 * i + 1] = (float)((int)mx[i] >> 16); }
+  if (t_splits == 1) {
+    const double inv = 1.0 / (double)T;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      mean_out[p0 + i] = (float)((double)s[i] * inv);
+      max_out[p0 + i] = floor0 ? fmaxf(m[i], 0.f) : m[i];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      psum[(long long)split * P + p0 + i] = (double)s[i];
+      pmax[(long long)split * P + p0 + i] = m[i];
+    }
+  }
+}
+
+__global__ void proj_scalar_i16_kernel(const short* __restrict__ movie, int T, long long P, float* __restrict__ mean_out,
+                                       float* __restrict__ max_out, int floor0) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  long long s = 0;
+  int m = -32768;
+  for (int t = 0; t < T; ++t) {
+    const int v = movie[(long long)t * P + p];
+    s += v;
+    m = v > m ? v : m;
+  }
+  if (floor0 && m < 0) m = 0;
+  mean_out[p] = (float)((double)s / (double)T);
+  max_out[p] = (float)m;
+}
+
 // generic fallback for P % 4 != 0 (never the benchmark shape): one thread per pixel
 __global__ void proj_scalar_kernel(const float* __restrict__ movie, int T, long long P,
                                    float* __restrict__ mean_out, float* __restrict__ max_out, int floor0) {
@@ -255,6 +368,55 @@ extern "C" int dcb_proj_mean_max_f32_variant(const float* movie, int T, int H, i
 extern "C" int dcb_proj_mean_max_f32(const float* movie, int T, int H, int W, float* mean, float* mx, int floor0,
                                      void* ws, size_t ws_bytes, dcb_stream_t stream) {
   return dcb_proj_mean_max_f32_variant(movie, T, H, W, mean, mx, floor0, ws, ws_bytes, -1, 0, stream);
+}
+
+template <int PXT, int TG>
+static void launch_partial_i16(const short* movie, int T, long long P, int S, double* psum, float* pmax, float* mean, float* mx,
+                               int floor0, cudaStream_t st) {
+  dim3 grid((unsigned)((P / 8 + PXT - 1) / PXT), (unsigned)S);
+  proj_partial_i16_kernel<PXT, TG, kU><<<grid, PXT * TG, 0, st>>>(movie, T, P, S, psum, pmax, mean, mx, floor0);
+}
+
+extern "C" int dcb_proj_mean_max_i16(const short* movie, int T, int H, int W, float* mean, float* mx, int floor0, void* ws,
+                                     size_t ws_bytes, dcb_stream_t stream) {
+  DCB_CHECK_ARG(movie && mean && mx, "dcb_proj_mean_max_i16: null pointer");
+  DCB_CHECK_ARG(T > 0 && H > 0 && W > 0, "dcb_proj_mean_max_i16: T,H,W must be positive (got %d,%d,%d)", T, H, W);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long P = (long long)H * W;
+  if (P % 8 != 0 || (reinterpret_cast<uintptr_t>(movie) & 15)) {
+    proj_scalar_i16_kernel<<<cdiv(P, 256), 256, 0, st>>>(movie, T, P, mean, mx, floor0);
+    g_launches += 1;
+    DCB_LAUNCH_OK("proj_scalar_i16_kernel");
+    return DCB_OK;
+  }
+  // 8 pixels per thread: half as many strips as the fp32 layout of the same variant -> twice the T splits
+  const int variant = kDefaultVariant;
+  const ProjVariant v = kVariants[variant];
+  const long long strips = (P / 8 + v.pxt - 1) / v.pxt;
+  long long S = ((long long)sm_count() * 4 * 7 + strips - 1) / strips;
+  const long long max_s = T / (v.tg * kU * 2);
+  if (S > max_s) S = max_s;
+  if (S < 1) S = 1;
+  if (S > 64) S = 64;
+  double* psum = nullptr;
+  float* pmax = nullptr;
+  if (S > 1) {
+    const size_t need = (size_t)S * P * (sizeof(double) + sizeof(float));
+    if (ws == nullptr || ws_bytes < need)
+      return fail(DCB_ERR_WORKSPACE, "dcb_proj_mean_max_i16: workspace %zu B < required %zu B", ws_bytes, need);
+    DCB_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "dcb_proj_mean_max_i16: workspace must be 16-byte aligned");
+    psum = reinterpret_cast<double*>(ws);
+    pmax = reinterpret_cast<float*>(psum + (size_t)S * P);
+  }
+  launch_partial_i16<128, 2>(movie, T, P, (int)S, psum, pmax, mean, mx, floor0, st);
+  g_launches += 1;
+  DCB_LAUNCH_OK("proj_partial_i16_kernel");
+  if (S > 1) {
+    proj_finalize_kernel<<<cdiv(P, 256), 256, 0, st>>>(psum, pmax, (int)S, T, P, mean, mx, floor0);
+    g_launches += 1;
+    DCB_LAUNCH_OK("proj_finalize_kernel");
+  }
+  return DCB_OK;
 }
 
 extern "C" int dcb_standardize_f32(const float* in, long long n, float* out, double* stats, dcb_stream_t stream) {

@@ -26,15 +26,15 @@ NEUROFINDER_NAMES = sorted([
 
 
 def summarize_movie_device(movie_dev, floor_max_at_zero=False, variant=-1, t_splits=0, out=None, workspace=None):
-    """movie_dev: float32 CUDA tensor [T,H,W].  Returns (mean, max) float32 CUDA tensors [H,W]."""
+    """movie_dev: float32 or int16 CUDA tensor [T,H,W].  Returns (mean, max) float32 CUDA tensors [H,W]."""
     import torch
     from ..engine import ops
     if movie_dev.dim() != 3:
         raise ValueError('movie must be [T,H,W], got shape %s' % (tuple(movie_dev.shape),))
     if movie_dev.shape[0] == 0:
         raise ValueError('movie has no frames')
-    if movie_dev.dtype != torch.float32 or not movie_dev.is_cuda:
-        raise TypeError('summarize_movie_device needs a float32 CUDA tensor')
+    if movie_dev.dtype not in (torch.float32, torch.int16) or not movie_dev.is_cuda:
+        raise TypeError('summarize_movie_device needs a float32 or int16 CUDA tensor')
     movie_dev = movie_dev.contiguous()
     T, H, W = movie_dev.shape
     if out is None:
@@ -56,7 +56,9 @@ def summarize_movie(movie, floor_max_at_zero=False):
     movie = np.asarray(movie)
     if movie.ndim != 3:
         raise ValueError('movie must be [T,H,W], got shape %s' % (movie.shape,))
-    dev = torch.from_numpy(np.ascontiguousarray(movie, dtype=np.float32)).cuda()
+    # int16 frames (the reference's TIFFs) go to the device as they are: half the PCIe and HBM bytes, exact sums
+    host = np.ascontiguousarray(movie) if movie.dtype == np.int16 else np.ascontiguousarray(movie, dtype=np.float32)
+    dev = torch.from_numpy(host).cuda()
     mean, mx = summarize_movie_device(dev, floor_max_at_zero)
     return mean.cpu().numpy(), mx.cpu().numpy()
 

@@ -35,8 +35,15 @@ def proj_workspace_bytes(T, H, W):
 
 
 def proj_mean_max(movie, mean, mx, workspace, floor_max_at_zero=False, variant=-1, t_splits=0):
-    _chk(movie, torch.float32); _chk(mean, torch.float32); _chk(mx, torch.float32)
+    _chk(mean, torch.float32); _chk(mx, torch.float32)
     T, H, W = movie.shape
+    if movie.dtype == torch.int16:        # the reference's raw TIFF frames: exact integer sums, half the bytes
+        _chk(movie, torch.int16)
+        call('dcb_proj_mean_max_i16', ptr(movie), c_int(T), c_int(H), c_int(W), ptr(mean), ptr(mx),
+             c_int(int(floor_max_at_zero)), ptr(workspace),
+             c_sz(workspace.numel() * workspace.element_size() if workspace is not None else 0), stream_ptr())
+        return
+    _chk(movie, torch.float32)
     call('dcb_proj_mean_max_f32_variant', ptr(movie), c_int(T), c_int(H), c_int(W), ptr(mean), ptr(mx),
          c_int(int(floor_max_at_zero)), ptr(workspace),
          c_sz(workspace.numel() * workspace.element_size() if workspace is not None else 0),

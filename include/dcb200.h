@@ -59,6 +59,10 @@ int dcb_proj_mean_max_f32_variant(const float* movie, int T, int H, int W, float
                                   int floor_max_at_zero, void* workspace, size_t workspace_bytes,
                                   int variant, int t_splits, dcb_stream_t stream);
 
+/* same projection for an int16 movie (the reference's TIFF frames, datasets/nf.py:115-130): exact integer sums, half the bytes;
+ * workspace as for the fp32 entry (dcb_proj_workspace_bytes) */
+int dcb_proj_mean_max_i16(const short* movie, int T, int H, int W, float* mean, float* mx, int floor_max_at_zero, void* workspace,
+                          size_t workspace_bytes, dcb_stream_t stream);
 /* ---- a2: unet_2d_summary.py:238-239 (_summarize_series) ----
  * out = (in - mean(in)) / std(in), population std, n = H*W elements.
  * stats (optional, 2 doubles on device) receives mean and std. */

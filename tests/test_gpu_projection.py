@@ -105,3 +105,22 @@ def test_standardize_matches_summarize_series(cuda, golden_dir):
     out = torch.empty(512, 512, device='cuda')
     ops.standardize(torch.from_numpy(img).cuda(), out)
     assert np.allclose(out.cpu().numpy(), oracle.summarize_series(img), atol=2e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize('shape', [(1, 8, 8), (5, 3, 7), (300, 16, 24), (17, 512, 512), (64, 31, 33), (1000, 64, 64)])
+def test_projection_int16_movie_is_exact(cuda, shape):
+    """int16 frames (the reference's TIFFs, nf.py:121): integer sums are exact, so the mean is the correctly rounded
+    float32 of sum/T and the max is bit-exact; signed data, extreme values, ragged shapes (scalar fallback)."""
+    rng = np.random.default_rng(sum(shape))
+    movie = rng.integers(-32768, 32768, size=shape, dtype=np.int16)
+    movie[0, 0, 0] = -32768; movie[-1, -1, -1] = 32767
+    mean, mx = _proj(movie)
+    exact = movie.astype(np.int64).sum(axis=0) / np.float64(shape[0])
+    assert np.array_equal(mx, movie.max(axis=0).astype(np.float32))
+    assert np.array_equal(mean, exact.astype(np.float32))
+    _, mx0 = _proj(-np.abs(movie.astype(np.int32)).clip(0, 32767).astype(np.int16), floor_max_at_zero=True)
+    assert np.all(mx0 >= 0)
+    # same answer through the host-buffer entry
+    from deepcalcium.datasets.nf import summarize_movie
+    mean2, mx2 = summarize_movie(movie)
+    assert np.array_equal(mean2, mean) and np.array_equal(mx2, mx)
