@@ -248,8 +248,10 @@ reduce_splits_wide_kernel(const float* __restrict__ part, int splits, size_t n, 
 }
 
 void launch_reduce_splits(const float* part, int splits, size_t n, float* out, cudaStream_t st) {
+  // split lanes per element: enough to hide the dependent-load chain, few enough that the grid stays small
   if (splits >= 64 && n < 4096) reduce_splits_wide_kernel<8><<<cdiv((long long)n, 8), 256, 0, st>>>(part, splits, n, out);
-  else if (splits >= 16) reduce_splits_wide_kernel<32><<<cdiv((long long)n, 32), 256, 0, st>>>(part, splits, n, out);
+  else if (splits >= 32) reduce_splits_wide_kernel<32><<<cdiv((long long)n, 32), 256, 0, st>>>(part, splits, n, out);
+  else if (splits >= 8) reduce_splits_wide_kernel<128><<<cdiv((long long)n, 128), 256, 0, st>>>(part, splits, n, out);
   else reduce_splits_kernel<<<cdiv((long long)n, 256), 256, 0, st>>>(part, splits, n, out);
 }
 
