@@ -233,6 +233,38 @@ __global__ void proj_scalar_i16_kernel(const short* __restrict__ movie, int T, l
   max_out[p] = (float)m;
 }
 
+// ---- streaming ingest: frames arrive in chunks (TIFF decode -> pinned buffer -> device), the running
+// per-pixel state lives on the device: exact int64 sums and the int running max, like the reference's loop at
+// datasets/nf.py:126-130 but without its float16 read-modify-write.  One thread per pixel pair group; a pixel is owned
+// by exactly one thread, so the accumulation needs no atomics.  PCIe / decode bound, not HBM bound.
+__global__ void __launch_bounds__(128)
+proj_accum_i16_kernel(const short* __restrict__ chunk, int Tc, long long P, long long* __restrict__ sum, int* __restrict__ mx) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  long long s = sum[p];
+  int m = mx[p];
+  int t = 0;
+  for (; t + 8 <= Tc; t += 8) {
+    int v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = chunk[(long long)(t + u) * P + p];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { s += v[u]; m = v[u] > m ? v[u] : m; }
+  }
+  for (; t < Tc; ++t) { const int v = chunk[(long long)t * P + p]; s += v; m = v > m ? v : m; }
+  sum[p] = s; mx[p] = m;
+}
+
+__global__ void proj_accum_finalize_kernel(const long long* __restrict__ sum, const int* __restrict__ mx, int T, long long P,
+                                           float* __restrict__ mean_out, float* __restrict__ max_out, int floor0) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  int m = mx[p];
+  if (floor0 && m < 0) m = 0;
+  mean_out[p] = (float)((double)sum[p] / (double)T);
+  max_out[p] = (float)m;
+}
+
 // generic fallback for P % 4 != 0 (never the benchmark shape): one thread per pixel
 __global__ void proj_scalar_kernel(const float* __restrict__ movie, int T, long long P,
                                    float* __restrict__ mean_out, float* __restrict__ max_out, int floor0) {
@@ -416,6 +448,25 @@ extern "C" int dcb_proj_mean_max_i16(const short* movie, int T, int H, int W, fl
     g_launches += 1;
     DCB_LAUNCH_OK("proj_finalize_kernel");
   }
+  return DCB_OK;
+}
+
+extern "C" int dcb_proj_accum_i16(const short* chunk, int Tc, int H, int W, long long* sum, int* mx, dcb_stream_t stream) {
+  DCB_CHECK_ARG(chunk && sum && mx && Tc > 0 && H > 0 && W > 0, "dcb_proj_accum_i16: bad arguments");
+  const long long P = (long long)H * W;
+  proj_accum_i16_kernel<<<cdiv(P, 128), 128, 0, (cudaStream_t)stream>>>(chunk, Tc, P, sum, mx);
+  g_launches += 1;
+  DCB_LAUNCH_OK("proj_accum_i16_kernel");
+  return DCB_OK;
+}
+
+extern "C" int dcb_proj_accum_finalize(const long long* sum, const int* mx, int T, int H, int W, float* mean, float* max_out,
+                                       int floor0, dcb_stream_t stream) {
+  DCB_CHECK_ARG(sum && mx && mean && max_out && T > 0 && H > 0 && W > 0, "dcb_proj_accum_finalize: bad arguments");
+  const long long P = (long long)H * W;
+  proj_accum_finalize_kernel<<<cdiv(P, 256), 256, 0, (cudaStream_t)stream>>>(sum, mx, T, P, mean, max_out, floor0);
+  g_launches += 1;
+  DCB_LAUNCH_OK("proj_accum_finalize_kernel");
   return DCB_OK;
 }
 

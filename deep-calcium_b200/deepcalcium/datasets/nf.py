@@ -148,6 +148,83 @@ def nf_load_hdf5(names, datasets_dir=None):
     return paths
 
 
+# ------------------------------------------------------------------------------------------------- ingest (N4)
+def _read_tiff_frame(path):
+    """One 16-bit greyscale TIFF frame as an int16 array (the reference stores `series/raw` as int16, nf.py:121)."""
+    from PIL import Image
+    with Image.open(path) as im:
+        a = np.asarray(im)
+    if a.ndim != 2:
+        raise ValueError('%s: expected a single greyscale frame, got shape %s' % (path, a.shape))
+    return a.astype(np.int16, copy=False)
+
+
+def summarize_tiff_dir(images_dir, chunk=64, floor_max_at_zero=True, pattern=('*.tiff', '*.tif')):
+    """The reference's ingest loop (datasets/nf.py:115-130) without materialising the movie: the TIFF frames of
+    `images_dir` (sorted by name) are decoded into a pinned int16 double buffer `chunk` frames at a time, copied to the
+    GPU on a side stream and folded into the device-resident running sum (exact int64) / max (dcb_proj_accum_i16) while
+    the host decodes the next chunk.  Returns (mean float32 [H,W], max float32 [H,W], number of frames).
+    floor_max_at_zero=True reproduces the reference's zero-initialised running max (nf.py:125)."""
+    import glob
+    import torch
+    from .. import _native as nat
+    from ..engine import ops
+    nat.require_cuda()
+    paths = sorted(p for pat in pattern for p in glob.glob(os.path.join(images_dir, pat)))
+    if not paths:
+        raise ValueError('no TIFF frames in %s' % images_dir)
+    first = _read_tiff_frame(paths[0])
+    H, W = first.shape
+    dev = torch.device('cuda', torch.cuda.current_device())
+    hbuf = [torch.empty(chunk, H, W, dtype=torch.int16).pin_memory() for _ in range(2)]
+    dbuf = [torch.empty(chunk, H, W, dtype=torch.int16, device=dev) for _ in range(2)]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    ssum = torch.zeros(H, W, dtype=torch.int64, device=dev)
+    smax = torch.full((H, W), -2 ** 31, dtype=torch.int32, device=dev)
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    for c, i0 in enumerate(range(0, len(paths), chunk)):
+        k = c % 2
+        done[k].synchronize()                                # chunk c-2 has been consumed: its buffers are free
+        n = min(chunk, len(paths) - i0)
+        hv = hbuf[k].numpy()
+        for j in range(n):
+            fr = first if i0 + j == 0 else _read_tiff_frame(paths[i0 + j])
+            if fr.shape != (H, W):
+                raise ValueError('%s: frame shape %s differs from %s' % (paths[i0 + j], fr.shape, (H, W)))
+            hv[j] = fr
+        with torch.cuda.stream(copy_stream):
+            dbuf[k][:n].copy_(hbuf[k][:n], non_blocking=True)
+            ready = torch.cuda.Event(); ready.record(copy_stream)
+        main.wait_event(ready)
+        ops.proj_accum_i16(dbuf[k][:n], ssum, smax)
+        done[k].record(main)
+    mean = torch.empty(H, W, dtype=torch.float32, device=dev)
+    mx = torch.empty(H, W, dtype=torch.float32, device=dev)
+    ops.proj_accum_finalize(ssum, smax, len(paths), mean, mx, floor_max_at_zero)
+    return mean.cpu().numpy(), mx.cpu().numpy(), len(paths)
+
+
+def nf_ingest(name, datasets_dir, out_path=None, chunk=64):
+    """nf.py:104-148 for one already-downloaded neurofinder dataset directory `<datasets_dir>/<name>` (images/*.tiff and,
+    for training sets, regions/regions.json): summary images through the streaming GPU projection, masks from the region
+    coordinates, written as the `.npz` container of make_dataset.  (Download / unzip stay out of scope: no network.)"""
+    import json
+    root = os.path.join(datasets_dir, name)
+    mean, mx, T = summarize_tiff_dir(os.path.join(root, 'images'), chunk=chunk)
+    masks = None
+    rj = os.path.join(root, 'regions', 'regions.json')
+    if '.test' not in name and os.path.exists(rj):
+        with open(rj) as fp:
+            regions = json.load(fp)
+        masks = np.zeros((len(regions),) + mean.shape, dtype=np.int8)
+        for idx, r in enumerate(regions):
+            yy, xx = [c[0] for c in r['coordinates']], [c[1] for c in r['coordinates']]
+            masks[idx, yy, xx] = 1
+    out_path = out_path or os.path.join(root, 'dataset.npz')
+    return make_dataset(out_path, name, mean=mean, mx=mx, masks=masks)
+
+
 # ------------------------------------------------------------------------------------------------- scoring (N3)
 # datasets/nf.py:153-229 of the reference scores a predicted mask by converting both masks to connected regions
 # (skimage.measure.label, default = 8-connectivity in 2-D) and calling `neurofinder.centers` / `neurofinder.shapes`

@@ -50,6 +50,18 @@ def proj_mean_max(movie, mean, mx, workspace, floor_max_at_zero=False, variant=-
          c_int(variant), c_int(t_splits), stream_ptr())
 
 
+def proj_accum_i16(chunk, sum_i64, max_i32):
+    _chk(chunk, torch.int16); _chk(sum_i64, torch.int64); _chk(max_i32, torch.int32)
+    Tc, H, W = chunk.shape
+    call('dcb_proj_accum_i16', ptr(chunk), c_int(Tc), c_int(H), c_int(W), ptr(sum_i64), ptr(max_i32), stream_ptr())
+
+
+def proj_accum_finalize(sum_i64, max_i32, T, mean, mx, floor_max_at_zero=False):
+    H, W = mean.shape
+    call('dcb_proj_accum_finalize', ptr(sum_i64), ptr(max_i32), c_int(T), c_int(H), c_int(W), ptr(mean), ptr(mx),
+         c_int(int(floor_max_at_zero)), stream_ptr())
+
+
 def standardize(x, out, stats=None):
     _chk(x, torch.float32); _chk(out, torch.float32)
     call('dcb_standardize_f32', ptr(x), c_ll(x.numel()), ptr(out), ptr(stats), stream_ptr())

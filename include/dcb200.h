@@ -63,6 +63,12 @@ int dcb_proj_mean_max_f32_variant(const float* movie, int T, int H, int W, float
  * workspace as for the fp32 entry (dcb_proj_workspace_bytes) */
 int dcb_proj_mean_max_i16(const short* movie, int T, int H, int W, float* mean, float* mx, int floor_max_at_zero, void* workspace,
                           size_t workspace_bytes, dcb_stream_t stream);
+/* Streaming form for ingest (frames arrive in chunks, datasets/nf.py:126-130): accumulate a chunk of Tc int16 frames into
+ * the per-pixel running state on the device - sum (int64, caller zero-initialises) and mx (int32, caller initialises to
+ * INT_MIN) - then turn the state after T frames into the float32 mean / max images */
+int dcb_proj_accum_i16(const short* chunk, int Tc, int H, int W, long long* sum, int* mx, dcb_stream_t stream);
+int dcb_proj_accum_finalize(const long long* sum, const int* mx, int T, int H, int W, float* mean, float* max_out,
+                            int floor_max_at_zero, dcb_stream_t stream);
 /* ---- a2: unet_2d_summary.py:238-239 (_summarize_series) ----
  * out = (in - mean(in)) / std(in), population std, n = H*W elements.
  * stats (optional, 2 doubles on device) receives mean and std. */

@@ -124,3 +124,30 @@ def test_projection_int16_movie_is_exact(cuda, shape):
     from deepcalcium.datasets.nf import summarize_movie
     mean2, mx2 = summarize_movie(movie)
     assert np.array_equal(mean2, mean) and np.array_equal(mx2, mx)
+
+
+def test_streaming_tiff_ingest(cuda, tmp_path):
+    """datasets/nf.py:104-148 for a dataset directory of 16-bit TIFF frames + regions.json, streamed through
+    the device-resident running sum / max in chunks (chunk size not dividing the frame count)."""
+    import json
+    from PIL import Image
+    from deepcalcium.datasets.nf import summarize_tiff_dir, nf_ingest, open_dataset
+    rng = np.random.default_rng(11)
+    T, H, W = 37, 24, 40
+    movie = rng.integers(0, 4096, size=(T, H, W)).astype(np.int16)
+    root = tmp_path / 'neurofinder.00.00'
+    (root / 'images').mkdir(parents=True); (root / 'regions').mkdir()
+    for t in range(T):
+        Image.fromarray(movie[t].astype(np.uint16)).save(str(root / 'images' / ('image%05d.tiff' % t)))
+    regions = [{'coordinates': [[2, 3], [2, 4], [3, 3]]}, {'coordinates': [[10, 20], [11, 20]]}]
+    json.dump(regions, open(str(root / 'regions' / 'regions.json'), 'w'))
+    mean, mx, n = summarize_tiff_dir(str(root / 'images'), chunk=8)
+    assert n == T
+    assert np.array_equal(mx, movie.max(axis=0).astype(np.float32))
+    assert np.array_equal(mean, (movie.astype(np.int64).sum(axis=0) / np.float64(T)).astype(np.float32))
+    path = nf_ingest('neurofinder.00.00', str(tmp_path), chunk=16)
+    ds = open_dataset(path)
+    assert np.array_equal(np.asarray(ds['series/max']), movie.max(axis=0))
+    assert np.allclose(np.asarray(ds['series/mean'], dtype=np.float32), mean, rtol=1e-3)       # stored as float16
+    mm = np.asarray(ds['masks/max'])
+    assert mm.sum() == 5 and mm[2, 3] == 1 and mm[11, 20] == 1
