@@ -9,6 +9,8 @@ torch only owns memory / streams / graphs here; there is no torch arithmetic on 
 """
 from collections import OrderedDict
 
+import os
+
 import numpy as np
 import torch
 
@@ -37,6 +39,9 @@ class UNetEngine(object):
         self._weights_dirty = True
         self._sessions = {}
         self._prep_tables = {}
+        # encoder blocks whose max-pool is folded into the conv epilogue.  Measured: pays at full resolution only
+        # (enc0b); DCB_POOL_FUSED=enc0b,enc1b made no difference for the 256^2 block (bench 1008.9 img/s either way)
+        self._pool_fused = tuple(x for x in os.environ.get('DCB_POOL_FUSED', 'enc0b').split(',') if x)
         self.iteration = 0
         self.launches = 0
         self.comm = None          # engine.dist.Comm for data-parallel training (None = single GPU)
@@ -270,12 +275,12 @@ class UNetEngine(object):
                     ops.conv3x3_fwd_fused(act[a], None, self.w_fwd[n], act[n], sc, sh, True,
                                           head_kernel=self.P['head/kernel'], head_bias=self.P['head/bias'],
                                           logit=s['logit'], prob=s['prob'], need_y=False)
-                elif n == 'enc0b':
-                    # measured: folding the pool pays at full resolution only (profiles/r1_layer_ab.txt)
-                    ops.conv3x3_fwd_fused(act[a], None, self.w_fwd[n], act[n], sc, sh, True, pool_out=act['pool0'])
+                elif n in self._pool_fused and self.dtype == torch.bfloat16:
+                    # the 2x2 max-pool rides in the conv epilogue where the layer runs on the (folded) strip kernel
+                    ops.conv3x3_fwd_fused(act[a], None, self.w_fwd[n], act[n], sc, sh, True, pool_out=act['pool%d' % blk.level])
                 else:
                     ops.conv3x3_fwd(act[a], act[b] if b else None, self.w_fwd[n], act[n], sc, sh, True)
-                    if n in ('enc1b', 'enc2b', 'enc3b'):
+                    if n in ('enc0b', 'enc1b', 'enc2b', 'enc3b'):
                         ops.maxpool2x2(act[n], act['pool%d' % blk.level])
             else:
                 ops.convT2x2_fwd(act[a], self.w_fwd[n], act[n], sc, sh, True)
