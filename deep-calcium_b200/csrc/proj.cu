@@ -11,6 +11,7 @@
 // before it reduces them.  Sums: the U frames are tree-summed in fp32 and then
 // accumulated in fp64 (keeps the mean within ~2e-7 relative of the fp64 truth
 // without paying one F2F.F64 per element).  Max uses max.NaN (numpy semantics).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace dcb {
@@ -425,8 +426,11 @@ extern "C" int dcb_proj_mean_max_i16(const short* movie, int T, int H, int W, fl
   const int variant = kDefaultVariant;
   const ProjVariant v = kVariants[variant];
   const long long strips = (P / 8 + v.pxt - 1) / v.pxt;
-  long long S = ((long long)sm_count() * 4 * 7 + strips - 1) / strips;
+  // ~3.5 waves of 4 resident CTAs per SM: more T-splits cost more partial-sum traffic than they gain in balance
+  // (sweep on B200, 3000 x 512 x 512: 4 splits 5837 GB/s, 8 -> 6214, 12 -> 6156, 17 -> 5820; scripts/proj_i16_sweep.py)
+  long long S = ((long long)sm_count() * 4 * 7 / 2 + strips / 2) / strips;
   const long long max_s = T / (v.tg * kU * 2);
+  if (const char* e = getenv("DCB_PROJ_I16_SPLITS")) { const int v = atoi(e); if (v > 0) S = v; }
   if (S > max_s) S = max_s;
   if (S < 1) S = 1;
   if (S > 64) S = 64;
