@@ -94,6 +94,56 @@ cta2_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict
   }
 }
 
+// issue rate of the pair MMA: the leader issues `iters` x 4 MMAs (M = 256, K = 16) on zeroed operands
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+cta2_rate_kernel(int Nn, int iters, long long* cycles_out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t bar_done;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  cg::cluster_group cluster = cg::this_cluster();
+  const uint32_t rank = cluster.block_rank();
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (threadIdx.x == 0) { mbar_init(&bar_done, 1); mbar_fence_init(); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  cluster.sync();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (rank == 0 && threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc_bf16(256, Nn, 0, 0);
+    const uint64_t da = make_smem_desc(smem_u32(smem), 16, 1024, SWZ_128B);
+    const uint64_t db = make_smem_desc(smem_u32(smem) + 16384, 16, 1024, SWZ_128B);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t d = tmem_base + ((it & 1) ? 256u : 0u);
+      for (int k = 0; k < 4; ++k)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d), "l"(da + (uint64_t)(2 * k)), "l"(db + (uint64_t)(2 * k)), "r"(idesc), "r"(1u) : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(&bar_done)), "h"((uint16_t)3) : "memory");
+    mbar_wait(&bar_done, 0);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0) *cycles_out = t1 - t0;
+  } else {
+    mbar_wait(&bar_done, 0);
+  }
+  tc_fence_before();
+  cluster.sync();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
 int main() {
   std::vector<__nv_bfloat16> hA(256 * K), hB(N * K);
   std::vector<float> fA(256 * K), fB(N * K), ref(256 * N), out(256 * N);
@@ -127,5 +177,20 @@ int main() {
     for (int m : {0, 127, 128, 255}) printf("  row %3d: got %g %g %g ... ref %g %g %g\n", m, out[m * N], out[m * N + 1], out[m * N + 64],
                                             ref[m * N], ref[m * N + 1], ref[m * N + 64]);
   }
-  return bad ? 2 : 0;
+  if (bad) return 2;
+  cudaFuncSetAttribute(cta2_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  long long* dc; cudaMalloc(&dc, 8);
+  for (int grid : {2, 148}) {
+    for (int Nn : {64, 128, 256}) {
+      const int iters = 2000;
+      cta2_rate_kernel<<<grid, 128, 50 * 1024>>>(Nn, iters, dc);
+      e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("CUDA error (rate): %s\n", cudaGetErrorString(e)); return 1; }
+      long long c; cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost);
+      const double per = (double)c / (iters * 4);
+      printf("grid=%3d pair MMA M=256 N=%3d K=16: %.1f cycles per MMA -> %.0f MAC/cycle/SM (each of the two SMs)\n", grid, Nn, per,
+             256.0 * Nn * 16 / per / 2);
+    }
+  }
+  return 0;
 }
