@@ -22,6 +22,15 @@ for p in (os.path.join(ROOT, 'deep-calcium_b200'), ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)
 os.environ.setdefault('DEEP_CALCIUM_HOME', '/tmp/deep-calcium-home')
+# torchrun exports OMP_NUM_THREADS=1; the CPU legs (rank 0 only) are entitled to every core this process may use, and the
+# OpenMP pool is sized when torch is first imported - so this has to happen before that import
+try:
+    _HOST_CORES = max(1, len(os.sched_getaffinity(0)))
+except Exception:   # noqa: BLE001
+    _HOST_CORES = os.cpu_count() or 1
+if int(os.environ.get('RANK', '0')) == 0:
+    os.environ['OMP_NUM_THREADS'] = str(_HOST_CORES)
+    os.environ['MKL_NUM_THREADS'] = str(_HOST_CORES)
 
 import numpy as np  # noqa: E402
 
@@ -91,10 +100,7 @@ def cpu_forward_tta(w, s, spec, n_images):
     """oracle port of predict(augmentation=True) (unet_2d_summary.py:585-595) in float32 on all host cores"""
     import torch
     import oracle
-    try:     # torchrun exports OMP_NUM_THREADS=1: the CPU arm is entitled to every core this process may use
-        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
-    except Exception:
-        pass
+    torch.set_num_threads(_HOST_CORES)
     t0 = time.perf_counter()
     for _ in range(n_images):
         oracle.tta_predict(w, s, spec, augmentation=True, dtype=torch.float32)
@@ -124,6 +130,107 @@ def run_reference(args):
                                        'graph; Keras 2.0.6/TF 1.2.1 are not installable' % args.steps},
             'e2e': {'value': val, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
+
+
+
+# ---------------------------------------------------------------------------------------------- parity (outside the timed regions)
+def parity_inference(eng, w, img_dev, precision):
+    """The benchmarked image under the exact dispatch that was timed (same engine, same captured graph) against the
+    CPU oracle: 8x-TTA mask disagreement (north star: <= 0.1 %) and logit error of the identity-transform forward
+    (north star: 1e-2 abs in 16-bit mode, 1e-4 in the fp32 check mode)."""
+    import torch
+    import oracle
+    ospec = oracle.UNetSpec(32)
+    s = img_dev.cpu().numpy()
+    mask, _ = eng.predict_tta(img_dev)
+    mask = mask.cpu().numpy().copy()
+    logit = eng._session(8, 512, 512, False)['logit'][0].cpu().numpy().copy()      # transform 0 = identity
+    omask, _ = oracle.tta_predict(w, s, ospec, dtype=torch.float32)
+    with torch.no_grad():
+        ologit = oracle.unet_forward(w, s[None], ospec, dtype=torch.float64)['logit'][0].numpy()
+    err = np.abs(logit - ologit)
+    tol = 1e-4 if precision == 'fp32' else 1e-2
+    return {'oracle': 'CPU restatement of the Keras graph (oracle/, parity unpinned)', 'image': 'benchmark image 0',
+            'mask_disagreement': float(np.mean(mask != omask)), 'mask_tolerance': 1e-3,
+            'logit_max_abs_err': float(err.max()), 'logit_mean_abs_err': float(err.mean()), 'logit_tolerance': tol,
+            'logit_range': float(np.abs(ologit).max()),
+            'pass': bool(np.mean(mask != omask) <= 1e-3 and err.max() <= tol)}
+
+
+def parity_train(precision, w, x_dev, y_dev):
+    """One train_on_batch of the benchmarked batch (dropout off) on a fresh engine under the default dispatch: loss and
+    every gradient tensor against oracle.train_step (float64); in bf16 mode also the oracle's own bf16-storage emulation
+    as the yardstick of what 8-bit mantissas can give on this network."""
+    import oracle
+    from deepcalcium.engine.graph import GraphSpec
+    from deepcalcium.engine.unet_engine import UNetEngine
+    ospec = oracle.UNetSpec(32)
+    x, y = x_dev.cpu().numpy(), y_dev.cpu().numpy()
+    L, _, _, g, _ = oracle.train_step(w, x, y, spec=ospec, loss='dice_loss')
+    eng = UNetEngine(GraphSpec(32), precision=precision)
+    eng.set_weights_dict(w)
+    m = eng.train_step(x_dev, y_dev, loss='dice_loss', lr=0.002, dropout=False)
+
+    def rel(a, b):
+        return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+    keys = [k for k in g if not (k.endswith('/bias') and not k.startswith('head'))]
+    errs = {k: rel(eng.G[k].cpu().numpy().astype(np.float64), g[k]) for k in keys}
+    worst = max(errs, key=errs.get)
+    out = {'loss': float(m[0].item()), 'oracle_loss': L, 'loss_abs_err': abs(float(m[0].item()) - L),
+           'grad_rel_l2_err_worst': errs[worst], 'grad_rel_l2_err_worst_tensor': worst,
+           'grad_rel_l2_err_median': float(np.median(list(errs.values()))), 'dropout': 'off for the parity step'}
+    if precision != 'fp32':
+        g_emu = oracle.train_step(w, x, y, spec=ospec, loss='dice_loss', emulate_bf16=True)[3]
+        emu = {k: rel(g_emu[k], g[k]) for k in keys}
+        out['bf16_storage_emulation_grad_rel_l2_err_worst'] = max(emu.values())
+        out['bf16_storage_emulation_grad_rel_l2_err_median'] = float(np.median(list(emu.values())))
+        out['pass'] = bool(out['loss_abs_err'] < 2e-3 and all(errs[k] <= 1.3 * emu[k] + 0.03 for k in keys))
+    else:
+        out['pass'] = bool(out['loss_abs_err'] < 1e-4 and errs[worst] < 3e-3)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- CPU baselines (rank 0, N = 1)
+def cpu_baselines(w, img_host):
+    """The CPU legs BASELINE.md section 3 lists, each on a bounded sample, all host cores unless stated."""
+    import torch
+    import oracle
+    ospec = oracle.UNetSpec(32)
+    out = {}
+    cores = torch.get_num_threads()
+    # 8x TTA inference (the headline metric)
+    cpu_forward_tta(w, img_host[:128, :128].copy(), ospec, 1)
+    n_cpu = 2
+    dt = cpu_forward_tta(w, img_host, ospec, n_cpu)
+    head = {'value': n_cpu / dt, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+            'sample': '%d TTA images (16 fp32 forwards) of the torch-CPU oracle port of the Keras graph' % n_cpu}
+    # training step (fwd + bwd + Keras-Adam), fp32, the C3 batch
+    rng = np.random.default_rng(865)
+    x = rng.standard_normal((32, 128, 128)).astype(np.float32)
+    y = (rng.random((32, 128, 128)) < 0.126).astype(np.uint8)
+    t0 = time.perf_counter()
+    oracle.train_step(w, x, y, spec=ospec, loss='dice_loss', dtype=torch.float32)
+    dt = time.perf_counter() - t0
+    out['train_step'] = {'value': 32 / dt, 'unit': 'crops/s', 'cores': cores, 'kind': 'port',
+                         'sample': '1 step of 32 crops 128x128 (fwd + autograd + Keras-Adam, torch-CPU fp32)'}
+    # projection: (i) numpy mean(float64)+max, 1 thread; (ii) the faithful per-frame loop of nf.py:126-130 (float16
+    # read-modify-write mean, int16 running max) on an in-memory array; (iii) a multi-threaded torch reduction
+    T = 300
+    sub = (np.random.default_rng(7535).random((T, 512, 512), dtype=np.float32) * 4096).astype(np.float32)
+    t0 = time.perf_counter(); sub.mean(0, dtype=np.float64); sub.max(0); dt = time.perf_counter() - t0
+    out['projection_numpy'] = {'value': sub.nbytes / dt / 1e9, 'unit': 'GB/s', 'cores': 1, 'kind': 'port',
+                               'sample': '%d of 3000 frames, numpy mean(float64) + max' % T}
+    sub16 = sub[:100].astype(np.int16)
+    t0 = time.perf_counter(); oracle.project_streaming_fp16(sub16); dt = time.perf_counter() - t0
+    out['projection_reference_loop'] = {'value': 100 / dt, 'unit': 'frames/s', 'cores': 1, 'kind': 'port',
+                                        'sample': '100 int16 frames through the per-frame loop of datasets/nf.py:126-130 '
+                                                  '(in-memory arrays; the reference reports ~205 frames/s with TIFF + HDF5 I/O)'}
+    tt = torch.from_numpy(sub)
+    t0 = time.perf_counter(); tt.to(torch.float64).mean(0); tt.amax(0); dt = time.perf_counter() - t0
+    out['projection_torch_mt'] = {'value': sub.nbytes / dt / 1e9, 'unit': 'GB/s', 'cores': cores, 'kind': 'port',
+                                  'sample': '%d of 3000 frames, torch float64 mean + amax' % T}
+    return head, out
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -277,7 +384,8 @@ def run_ours(args):
     # ---- multi-GPU extras (every rank takes part in the collectives)
     dist_extra = {}
     if world > 1:
-        for name, fn in (('tta_sharded', bench_tta_sharded), ('train_dp', bench_train_dp)):
+        for name, fn in (('tta_sharded', bench_tta_sharded), ('train_dp', bench_train_dp),
+                         ('projection_sharded', bench_projection_sharded)):
             try:
                 dist_extra[name] = fn(args, pk, eng, imgs, max_over_ranks, barrier)
             except Exception as ex:   # noqa: BLE001
@@ -288,20 +396,34 @@ def run_ours(args):
             sess = eng._session(8, 512, 512, False)
             rows, tot_f, tot_ms = per_layer_profile(eng, sess, spec, 8, 512, 512)
             ach = tot_f / tot_ms / 1e9
-            traffic = None
-            try:   # dram__bytes_read.sum + dram__bytes_write.sum over the same tensor-core launches, from the committed ncu capture
-                with open(os.path.join(ROOT, 'profiles', 'r1_conv_traffic.json')) as f:
-                    traffic = json.load(f)['dram_bytes_per_step']
-            except Exception:
-                pass
+            traffic, traffic_src = None, None
+            for name in ('r2_conv_traffic.json', 'r1_conv_traffic.json'):
+                try:   # dram__bytes_read.sum + dram__bytes_write.sum over the same tensor-core launches (ncu --set full capture)
+                    with open(os.path.join(ROOT, 'profiles', name)) as f:
+                        traffic = json.load(f)['dram_bytes_per_step']
+                    traffic_src = 'profiles/' + name + ' (ncu capture of this command; not re-measured in the run)'
+                    break
+                except Exception:   # noqa: BLE001
+                    pass
+            step_tf = 8 * spec.flops_forward(512, 512) / (ms / args.steps) / 1e9
             line['roofline'] = {'bound': 'tensor', 'achieved': ach, 'peak': pk['tf'], 'unit': 'TFLOP/s',
-                                'frac': ach / pk['tf'], 'traffic': traffic, 'peak_source': pk['src'],
-                                'kernel': 'tcgen05 tap-GEMM conv3x3/convT2x2 (the 22 tensor-core launches of one 8-image forward: 21 layers, dec1a as two channel-split launches)',
+                                'frac': ach / pk['tf'], 'traffic': traffic, 'traffic_source': traffic_src,
+                                'peak_source': pk['src'] + ', burst figure',
+                                'kernel': 'tcgen05 tap-GEMM conv3x3/convT2x2 launches of one 8-image forward, each timed '
+                                          'eagerly with CUDA events (per_layer)',
                                 'flops_per_step': tot_f, 'conv_ms_per_step': tot_ms,
-                                'whole_step_frac': (8 * spec.flops_forward(512, 512) / (ms / args.steps) / 1e9) / pk['tf_sus']}
+                                'whole_step_tflops': step_tf, 'whole_step_frac_of_burst_peak': step_tf / pk['tf'],
+                                'whole_step_frac_of_sustained_peak': step_tf / pk['tf_sus'],
+                                'note': 'conv_ms_per_step sums eagerly launched kernels (launch gaps included); ms_per_step is '
+                                        'the CUDA-graph replay of the whole step (all kernels incl. first layer, TTA batch/combine)'}
             line['per_layer'] = rows
         except Exception as ex:   # noqa: BLE001
             line['roofline'] = {'error': repr(ex)}
+        # ---- parity of exactly what was timed (outside the timed region)
+        try:
+            line['parity'] = {'inference': parity_inference(eng, w, imgs[0], args.precision)}
+        except Exception as ex:   # noqa: BLE001
+            line['parity'] = {'inference': {'error': repr(ex)}}
         # ---- extras: projection (C2) and training (C3)
         line['extra'] = dict(dist_extra)
         for name, fn in (('projection', bench_projection), ('train', bench_train)):
@@ -309,19 +431,16 @@ def run_ours(args):
                 line['extra'][name] = fn(args, pk)
             except Exception as ex:   # noqa: BLE001
                 line['extra'][name] = {'error': repr(ex)}
-        # ---- CPU baseline on this box's host cores (bounded sample)
-        try:
-            import oracle
-            ow = oracle.init_weights(oracle.UNetSpec(32), seed=7535)
-            s = imgs[0].cpu().numpy()
-            cpu_forward_tta(ow, s[:128, :128].copy(), oracle.UNetSpec(32), 1)
-            n_cpu = 2
-            dt = cpu_forward_tta(ow, s, oracle.UNetSpec(32), n_cpu)
-            line['cpu_baseline'] = {'value': n_cpu / dt, 'unit': 'images/s', 'cores': torch.get_num_threads(),
-                                    'kind': 'port', 'sample': '%d TTA images (16 fp32 forwards) of the torch-CPU '
-                                    'oracle port of the Keras graph' % n_cpu}
-        except Exception as ex:   # noqa: BLE001
-            line['cpu_baseline'] = {'error': repr(ex)}
+        if isinstance(line['extra'].get('train'), dict) and 'parity' in line['extra']['train']:
+            line['parity']['train'] = line['extra']['train'].pop('parity')
+        # ---- CPU baselines on this box's host cores (bounded samples; N = 1 only: at N > 1 the other ranks would idle)
+        if world == 1:
+            try:
+                line['cpu_baseline'], line['extra']['cpu_baselines'] = cpu_baselines(w, imgs[0].cpu().numpy())
+            except Exception as ex:   # noqa: BLE001
+                line['cpu_baseline'] = {'error': repr(ex)}
+        else:
+            line['cpu_baseline'] = None
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -345,8 +464,17 @@ def bench_tta_sharded(args, pk, eng, imgs, max_over_ranks, barrier):
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1)) / n
-    return {'ms_per_image': ms, 'images_per_s': 1e3 / ms, 'ranks': comm.world,
-            'note': 'strong scaling of one image: transforms k -> rank, all_gather of 1 MiB probability maps'}
+    # parity: the sharded mask / activation against the single-GPU 8x TTA of the same image on rank 0
+    mask, act = predict_tta_sharded(eng, imgs[1], comm)
+    same = None
+    if comm.rank == 0:
+        mask, act = mask.clone(), act.clone()
+        m1, a1 = eng.predict_tta(imgs[1])
+        same = bool(torch.equal(mask, m1)) and bool(torch.equal(act, a1))
+    barrier()
+    return {'ms_per_image': ms, 'images_per_s': 1e3 / ms, 'ranks': comm.world, 'bit_identical': same,
+            'nvlink_bytes_algorithmic': (8 - 8 // comm.world) * 512 * 512 * 4,
+            'note': 'strong scaling of one image: transforms k -> rank k*n/8, probability maps to rank 0, fixed-order combine'}
 
 
 def bench_train_dp(args, pk, eng_unused, imgs, max_over_ranks, barrier):
@@ -390,8 +518,87 @@ def bench_train_dp(args, pk, eng_unused, imgs, max_over_ranks, barrier):
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1)) / n
-    return {'crops_per_s': comm.world * B * 1e3 / ms, 'ms_per_step': ms, 'global_batch': comm.world * B, 'ranks': comm.world,
-            'launch': 'one CUDA graph per step, NCCL all-reduces captured' if graphs else 'eager (NCCL collectives interleaved)'}
+    res = {'crops_per_s': comm.world * B * 1e3 / ms, 'ms_per_step': ms, 'global_batch': comm.world * B, 'ranks': comm.world,
+           'launch': 'one CUDA graph per step, collectives captured' if graphs else 'eager (collectives interleaved)'}
+    del eng
+    try:
+        res.update(parity_train_dp(comm, spec))
+    except Exception as ex:   # noqa: BLE001
+        res['parity_error'] = repr(ex)
+    return res
+
+
+def parity_train_dp(comm, spec):
+    """fp32 check mode, dropout off: one data-parallel step over a global batch of 4 x world crops of 64x64 against the
+    single-device step on the concatenated batch (rank 0): loss and all-reduced gradients."""
+    import torch
+    from deepcalcium.engine.graph import he_normal_weights
+    from deepcalcium.engine.unet_engine import UNetEngine
+    from deepcalcium.engine.dist import shard_range, sync_parameters
+    w = he_normal_weights(spec, seed=7535)
+    Bg, H = 4 * comm.world, 64
+    x = np.random.default_rng(1).standard_normal((Bg, H, H)).astype(np.float32)
+    y = (np.random.default_rng(2).random((Bg, H, H)) < 0.126).astype(np.uint8)
+    f, c = shard_range(Bg, comm.world, comm.rank)
+    dp = UNetEngine(spec, precision='fp32', use_graphs=False)
+    dp.set_weights_dict(w)
+    dp.comm = comm
+    sync_parameters(dp, comm)
+    m = dp.train_step(torch.from_numpy(x[f:f + c]).cuda(), torch.from_numpy(y[f:f + c]).cuda(), loss='dice_loss', dropout=False)
+    loss_dp = float(m[0].item())
+    out = {}
+    if comm.rank == 0:
+        ref = UNetEngine(spec, precision='fp32', use_graphs=False)
+        ref.set_weights_dict(w)
+        loss_ref = float(ref.train_step(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), loss='dice_loss', dropout=False)[0].item())
+        worst = ('', 0.0)
+        for k in dp.G:
+            a_, b_ = dp.G[k].double().cpu().numpy(), ref.G[k].double().cpu().numpy()
+            nb = np.linalg.norm(b_)
+            r = float(np.linalg.norm(a_ - b_) / nb) if nb > 0 else float(np.abs(a_).max())
+            if r > worst[1]:
+                worst = (k, r)
+        wd, wr = dp.get_weights_dict(), ref.get_weights_dict()
+        stat = max(float(np.max(np.abs(wd[k] - wr[k]))) for k in wd if 'moving' in k)
+        out = {'loss_abs_err': abs(loss_dp - loss_ref), 'grad_rel_err': worst[1], 'grad_rel_err_tensor': worst[0],
+               'bn_moving_stat_max_abs_diff': stat,
+               'parity_config': 'fp32 check mode, dropout off, global batch %d of 64x64, DP vs the single-device batch' % Bg}
+    import torch.distributed as dist
+    dist.barrier()
+    return out
+
+
+def bench_projection_sharded(args, pk, eng_unused, imgs, max_over_ranks, barrier):
+    """ONE 3000x512x512 float32 movie split into row bands over the ranks (each rank holds [T, 512/n, 512]),
+    band projection without any exchange, all_gather of the 2 x [512/n, 512] maps -> GB/s over the whole movie."""
+    import torch
+    from deepcalcium.engine.dist import Comm, shard_range, summarize_movie_sharded
+    comm = Comm()
+    T, H, W = 3000, 512, 512
+    first, rows = shard_range(H, comm.world, comm.rank)
+    g = torch.Generator(device='cuda'); g.manual_seed(7535 + comm.rank)
+    band = torch.rand((T, rows, W), device='cuda', generator=g) * 4096
+    for _ in range(3):
+        mean, mx = summarize_movie_sharded(band, comm, H)
+    barrier()
+    n = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        mean, mx = summarize_movie_sharded(band, comm, H)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / n
+    # parity: this rank's rows of the gathered maps against torch reductions of its own band (max bit-exact, mean 1e-6)
+    ok = bool(torch.equal(mx[first:first + rows], band.amax(0))) and \
+        bool(((mean[first:first + rows].double() - band.double().mean(0)).abs() <= 1e-6 * band.double().mean(0).abs()).all())
+    t = torch.tensor([1.0 if ok else 0.0], device='cuda')
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
+    nbytes = T * H * W * 4 + 2 * H * W * 4
+    del band
+    return {'ms_per_movie': ms, 'movies_per_s': 1e3 / ms, 'ranks': comm.world, 'achieved_gbs_aggregate': nbytes / ms / 1e6,
+            'frac_of_aggregate_hbm_peak': nbytes / ms / 1e6 / (pk['hbm'] * comm.world), 'parity_ok_all_ranks': bool(t.item() > 0.5),
+            'collective': 'all_gather of 2 x %d x %d float32 per rank' % (rows, W)}
 
 
 def bench_projection(args, pk):
@@ -462,6 +669,7 @@ def bench_train(args, pk):
         eng.train_step(xs[i % 4], ys[i % 4], loss='dice_loss', lr=0.002, dropout=True)
     torch.cuda.synchronize()
     n = 20
+    l0 = eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(n):
@@ -470,9 +678,15 @@ def bench_train(args, pk):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     fl = B * spec.flops_train(128, 128)
-    return {'crops_per_s': B * 1e3 / ms, 'ms_per_step': ms, 'batch': B, 'crop': 128, 'loss': 'dice_loss',
-            'final_loss': float(m[0].item()), 'tflops': fl / ms / 1e9, 'frac_of_bf16_peak': fl / ms / 1e9 / pk['tf_sus'],
-            'flops_per_step': fl}
+    res = {'crops_per_s': B * 1e3 / ms, 'ms_per_step': ms, 'batch': B, 'crop': 128, 'loss': 'dice_loss',
+           'final_loss': float(m[0].item()), 'tflops': fl / ms / 1e9, 'frac_of_bf16_peak_burst': fl / ms / 1e9 / pk['tf'],
+           'frac_of_bf16_peak_sustained': fl / ms / 1e9 / pk['tf_sus'], 'flops_per_step': fl,
+           'gpu_launches_per_step': (eng.launches - l0) // n}
+    try:
+        res['parity'] = parity_train(args.precision, he_normal_weights(spec, seed=7535), xs[0], ys[0])
+    except Exception as ex:   # noqa: BLE001
+        res['parity'] = {'error': repr(ex)}
+    return res
 
 
 def main():

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
@@ -34,6 +35,8 @@ int fail(int code, const char* fmt, ...);
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 int sm_count();   // cached multiprocessor count of the current device
+int policy(int key);               // current value of a dcb_policy_key (dcb_set_policy)
+void note_kernel(const char* name); // records the contraction kernel a call dispatched to (dcb_last_kernel)
 
 // ---- device helpers ----
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
@@ -46,7 +49,9 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
 template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 

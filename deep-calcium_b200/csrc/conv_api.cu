@@ -3,6 +3,7 @@
 // (tapgemm_f32.cu), DCB_BF16 to the tcgen05/TMEM/TMA kernels (tapgemm_tc.cu).
 #include "common.cuh"
 #include "tapgeom.h"
+#include <cuda_fp16.h>
 
 namespace dcb {
 extern unsigned long long g_launches;
@@ -141,6 +142,7 @@ extern "C" int dcb_prep_weights_batch(int dtype, const long long* desc_dev, int 
   const dim3 grid(96, count);
   if (dtype == DCB_F32) prep_batch_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(desc_dev, 0);
   else if (dtype == DCB_BF16) prep_batch_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(desc_dev, 1);
+  else if (dtype == DCB_F16) prep_batch_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(desc_dev, 1);
   else return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
   g_launches += 1;
   DCB_LAUNCH_OK("prep_batch_kernel");
@@ -157,6 +159,8 @@ extern "C" int dcb_prep_conv3x3_weights(int dtype, const float* w, int Cin, int 
   else if (dtype == DCB_BF16)
     prep_conv3x3_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(w, Cin, Cout, (__nv_bfloat16*)w_fwd,
                                                                               (__nv_bfloat16*)w_dgrad, 1);
+  else if (dtype == DCB_F16)
+    prep_conv3x3_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(w, Cin, Cout, (__half*)w_fwd, (__half*)w_dgrad, 1);
   else return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
   g_launches += 1;
   DCB_LAUNCH_OK("prep_conv3x3_kernel");
@@ -173,6 +177,8 @@ extern "C" int dcb_prep_convT2x2_weights(int dtype, const float* w, int Cin, int
   else if (dtype == DCB_BF16)
     prep_convT_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(w, Cin, Cout, (__nv_bfloat16*)w_fwd,
                                                                             (__nv_bfloat16*)w_dgrad, 1);
+  else if (dtype == DCB_F16)
+    prep_convT_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(w, Cin, Cout, (__half*)w_fwd, (__half*)w_dgrad, 1);
   else return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
   g_launches += 1;
   DCB_LAUNCH_OK("prep_convT_kernel");
@@ -187,10 +193,11 @@ extern "C" int dcb_conv3x3_fwd(int dtype, const void* src0, int C0, const void* 
                 "dcb_conv3x3_fwd: bad shape N=%d H=%d W=%d C0=%d C1=%d Cout=%d", N, H, W, C0, C1, Cout);
   TapGeom g;
   geom_conv3x3(g, N, H, W);
+  g.f16 = (dtype == DCB_F16);
   if (dtype == DCB_F32)
     return run_f32_fwd(g, (const float*)src0, C0, (const float*)src1, C1, (const float*)wgt, Cout, (float*)out, scale,
                        shift, relu, (cudaStream_t)stream);
-  if (dtype == DCB_BF16)
+  if (dtype == DCB_BF16 || dtype == DCB_F16)
     return run_tc_fwd(g, src0, C0, src1, C1, wgt, Cout, out, scale, shift, relu, 0, (cudaStream_t)stream);
   return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
 }
@@ -202,9 +209,10 @@ extern "C" int dcb_conv3x3_fwd_fused(int dtype, const void* src0, int C0, const 
   DCB_CHECK_ARG(N > 0 && H > 0 && W > 0 && C0 > 0 && C1 >= 0 && Cout > 0 && (C1 == 0 || src1), "dcb_conv3x3_fwd_fused: bad shape");
   DCB_CHECK_ARG(!fuse->head_kernel || (fuse->head_bias && (fuse->logit || fuse->prob)), "dcb_conv3x3_fwd_fused: incomplete head arguments");
   DCB_CHECK_ARG(!fuse->pool_out || (H % 2 == 0 && W % 2 == 0), "dcb_conv3x3_fwd_fused: pooling needs even H and W");
-  if (dtype == DCB_BF16) {
+  if (dtype == DCB_BF16 || dtype == DCB_F16) {
     TapGeom g;
     geom_conv3x3(g, N, H, W);
+  g.f16 = (dtype == DCB_F16);
     TcFusion f = {fuse->head_kernel, fuse->head_bias, fuse->logit, fuse->prob, fuse->need_y, fuse->pool_out};
     const int rc = run_tc_fwd(g, src0, C0, src1, C1, wgt, Cout, out, scale, shift, relu, 0, (cudaStream_t)stream, &f);
     if (rc != DCB_ERR_UNSUPPORTED) return rc;
@@ -223,10 +231,11 @@ extern "C" int dcb_conv3x3_dgrad(int dtype, const void* dy, int Cout, int N, int
   DCB_CHECK_ARG(dy && wgt_dgrad && dx && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "dcb_conv3x3_dgrad: bad arguments");
   TapGeom g;
   geom_conv3x3(g, N, H, W);
+  g.f16 = (dtype == DCB_F16);
   if (dtype == DCB_F32)
     return run_f32_fwd(g, (const float*)dy, Cout, nullptr, 0, (const float*)wgt_dgrad, Cin, dx, nullptr, nullptr, 0,
                        (cudaStream_t)stream);
-  if (dtype == DCB_BF16)
+  if (dtype == DCB_BF16 || dtype == DCB_F16)
     return run_tc_fwd(g, dy, Cout, nullptr, 0, wgt_dgrad, Cin, dx, nullptr, nullptr, 0, 1, (cudaStream_t)stream);
   return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
 }
@@ -236,10 +245,11 @@ extern "C" int dcb_convT2x2_fwd(int dtype, const void* src, int Cin, int N, int 
   DCB_CHECK_ARG(src && wgt && out && N > 0 && h > 0 && w > 0 && Cin > 0 && Cout > 0, "dcb_convT2x2_fwd: bad arguments");
   TapGeom g;
   geom_convT_fwd(g, N, h, w);
+  g.f16 = (dtype == DCB_F16);
   if (dtype == DCB_F32)
     return run_f32_fwd(g, (const float*)src, Cin, nullptr, 0, (const float*)wgt, Cout, (float*)out, scale, shift, relu,
                        (cudaStream_t)stream);
-  if (dtype == DCB_BF16)
+  if (dtype == DCB_BF16 || dtype == DCB_F16)
     return run_tc_fwd(g, src, Cin, nullptr, 0, wgt, Cout, out, scale, shift, relu, 0, (cudaStream_t)stream);
   return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
 }
@@ -249,10 +259,11 @@ extern "C" int dcb_convT2x2_dgrad(int dtype, const void* dy, int Cout, int N, in
   DCB_CHECK_ARG(dy && wgt && dx && N > 0 && h > 0 && w > 0 && Cin > 0 && Cout > 0, "dcb_convT2x2_dgrad: bad arguments");
   TapGeom g;
   geom_convT_dgrad(g, N, h, w);
+  g.f16 = (dtype == DCB_F16);
   if (dtype == DCB_F32)
     return run_f32_fwd(g, (const float*)dy, Cout, nullptr, 0, (const float*)wgt, Cin, dx, nullptr, nullptr, 0,
                        (cudaStream_t)stream);
-  if (dtype == DCB_BF16)
+  if (dtype == DCB_BF16 || dtype == DCB_F16)
     return run_tc_fwd(g, dy, Cout, nullptr, 0, wgt, Cin, dx, nullptr, nullptr, 0, 1, (cudaStream_t)stream);
   return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
 }
@@ -261,6 +272,7 @@ extern "C" int dcb_conv3x3_wgrad_workspace_bytes(int dtype, int N, int H, int W,
   DCB_CHECK_ARG(bytes && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "dcb_conv3x3_wgrad_workspace_bytes: bad arguments");
   TapGeom g;
   geom_conv3x3(g, N, H, W);
+  g.f16 = (dtype == DCB_F16);
   if (dtype == DCB_F32) *bytes = (size_t)f32_wgrad_splits(g, Cin, Cout) * 9 * Cin * Cout * sizeof(float);
   else *bytes = tc_wgrad_workspace(g, Cin, Cout);
   return DCB_OK;
@@ -272,10 +284,11 @@ extern "C" int dcb_conv3x3_wgrad(int dtype, const void* src0, int C0, const void
                 "dcb_conv3x3_wgrad: bad arguments");
   TapGeom g;
   geom_conv3x3(g, N, H, W);
+  g.f16 = (dtype == DCB_F16);
   if (dtype == DCB_F32)
     return run_f32_wgrad(g, (const float*)src0, C0, (const float*)src1, C1, (const float*)dy, Cout, dW, ws, ws_bytes,
                          (cudaStream_t)stream);
-  if (dtype == DCB_BF16) return run_tc_wgrad(g, src0, C0, src1, C1, dy, Cout, dW, ws, ws_bytes, (cudaStream_t)stream);
+  if (dtype == DCB_BF16 || dtype == DCB_F16) return run_tc_wgrad(g, src0, C0, src1, C1, dy, Cout, dW, ws, ws_bytes, (cudaStream_t)stream);
   return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
 }
 
@@ -283,6 +296,7 @@ extern "C" int dcb_convT2x2_wgrad_workspace_bytes(int dtype, int N, int h, int w
   DCB_CHECK_ARG(bytes && N > 0 && h > 0 && w > 0 && Cin > 0 && Cout > 0, "dcb_convT2x2_wgrad_workspace_bytes: bad arguments");
   TapGeom g;
   geom_convT_dgrad(g, N, h, w);
+  g.f16 = (dtype == DCB_F16);
   if (dtype == DCB_F32) *bytes = (size_t)f32_wgrad_splits(g, Cout, Cin) * 4 * Cin * Cout * sizeof(float);
   else *bytes = tc_wgrad_workspace(g, Cout, Cin);
   return DCB_OK;
@@ -295,9 +309,10 @@ extern "C" int dcb_convT2x2_wgrad(int dtype, const void* x, int Cin, int N, int 
   DCB_CHECK_ARG(x && dy && dW && N > 0 && h > 0 && w > 0 && Cin > 0 && Cout > 0, "dcb_convT2x2_wgrad: bad arguments");
   TapGeom g;
   geom_convT_dgrad(g, N, h, w);
+  g.f16 = (dtype == DCB_F16);
   if (dtype == DCB_F32)
     return run_f32_wgrad(g, (const float*)dy, Cout, nullptr, 0, (const float*)x, Cin, dW, ws, ws_bytes,
                          (cudaStream_t)stream);
-  if (dtype == DCB_BF16) return run_tc_wgrad(g, dy, Cout, nullptr, 0, x, Cin, dW, ws, ws_bytes, (cudaStream_t)stream);
+  if (dtype == DCB_BF16 || dtype == DCB_F16) return run_tc_wgrad(g, dy, Cout, nullptr, 0, x, Cin, dW, ws, ws_bytes, (cudaStream_t)stream);
   return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
 }

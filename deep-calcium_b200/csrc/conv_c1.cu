@@ -171,6 +171,8 @@ extern "C" int dcb_conv3x3_c1_fwd(int dtype, const float* x, int N, int H, int W
   if (dtype == DCB_F32) return launch_c1_fwd<float>(x, N, H, W, w, Cout, scale, shift, relu, (float*)out, (cudaStream_t)stream);
   if (dtype == DCB_BF16)
     return launch_c1_fwd<__nv_bfloat16>(x, N, H, W, w, Cout, scale, shift, relu, (__nv_bfloat16*)out, (cudaStream_t)stream);
+  if (dtype == DCB_F16)
+    return launch_c1_fwd<__half>(x, N, H, W, w, Cout, scale, shift, relu, (__half*)out, (cudaStream_t)stream);
   return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
 }
 

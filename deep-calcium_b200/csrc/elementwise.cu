@@ -729,6 +729,7 @@ using namespace dcb;
 #define DISPATCH_T(dtype, ...)                                                     \
   if ((dtype) == DCB_F32) { using T = float; __VA_ARGS__ }                         \
   else if ((dtype) == DCB_BF16) { using T = __nv_bfloat16; __VA_ARGS__ }           \
+  else if ((dtype) == DCB_F16) { using T = __half; __VA_ARGS__ }                   \
   else return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", (int)(dtype));
 
 extern "C" int dcb_cast_from_f32(int dtype, const float* in, long long n, void* out, dcb_stream_t stream) {
@@ -771,7 +772,7 @@ static int bn_reduce_grid(long long M, int C) {
   const int vec = (C % 8 == 0 && 256 % (C / 8) == 0) ? 8 : 4;
   const int rows_par = 256 / (C / vec) > 0 ? 256 / (C / vec) : 1;
   long long grid = (M + 4LL * rows_par - 1) / (4LL * rows_par);
-  static const int per_sm = [] { const char* e = getenv("DCB_BN_CTAS_PER_SM"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 4; }();
+  const int per_sm = policy(DCB_POLICY_BN_CTAS_PER_SM) > 0 ? policy(DCB_POLICY_BN_CTAS_PER_SM) : 4;
   if (grid > (long long)sm_count() * per_sm) grid = (long long)sm_count() * per_sm;
   return grid < 1 ? 1 : (int)grid;
 }

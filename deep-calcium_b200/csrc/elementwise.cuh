@@ -15,7 +15,19 @@ template <> __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bf
   float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
   return make_float4(fa.x, fa.y, fb.x, fb.y);
 }
+template <> __device__ __forceinline__ float4 load4<__half>(const __half* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 fa = __half22float2(*reinterpret_cast<__half2*>(&u.x)), fb = __half22float2(*reinterpret_cast<__half2*>(&u.y));
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
 template <typename T> __device__ __forceinline__ void store4(T* p, float4 v);
+template <> __device__ __forceinline__ void store4<__half>(__half* p, float4 v) {
+  __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
 template <> __device__ __forceinline__ void store4<float>(float* p, float4 v) {
   *reinterpret_cast<float4*>(p) = v;
 }
@@ -43,7 +55,25 @@ template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bflo
   }
 }
 
+template <> __device__ __forceinline__ void load8<__half>(const __half* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
 template <typename T> __device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void store8<__half>(__half* p, const float (&v)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 b = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&b);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
 template <> __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);

@@ -256,13 +256,15 @@ proj_accum_i16_kernel(const short* __restrict__ chunk, int Tc, long long P, long
   sum[p] = s; mx[p] = m;
 }
 
+// bias: value that was subtracted from every pixel before accumulation (unsigned 16-bit frames are shifted into the
+// int16 range by -32768); it is restored here in exact integer arithmetic
 __global__ void proj_accum_finalize_kernel(const long long* __restrict__ sum, const int* __restrict__ mx, int T, long long P,
-                                           float* __restrict__ mean_out, float* __restrict__ max_out, int floor0) {
+                                           float* __restrict__ mean_out, float* __restrict__ max_out, int floor0, int bias) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
-  int m = mx[p];
+  int m = mx[p] + bias;
   if (floor0 && m < 0) m = 0;
-  mean_out[p] = (float)((double)sum[p] / (double)T);
+  mean_out[p] = (float)((double)(sum[p] + (long long)T * bias) / (double)T);
   max_out[p] = (float)m;
 }
 
@@ -430,7 +432,7 @@ extern "C" int dcb_proj_mean_max_i16(const short* movie, int T, int H, int W, fl
   // (sweep on B200, 3000 x 512 x 512: 4 splits 5837 GB/s, 8 -> 6214, 12 -> 6156, 17 -> 5820; scripts/proj_i16_sweep.py)
   long long S = ((long long)sm_count() * 4 * 7 / 2 + strips / 2) / strips;
   const long long max_s = T / (v.tg * kU * 2);
-  if (const char* e = getenv("DCB_PROJ_I16_SPLITS")) { const int v = atoi(e); if (v > 0) S = v; }
+  if (policy(DCB_POLICY_PROJ_I16_SPLITS) > 0) S = policy(DCB_POLICY_PROJ_I16_SPLITS);
   if (S > max_s) S = max_s;
   if (S < 1) S = 1;
   if (S > 64) S = 64;
@@ -464,14 +466,19 @@ extern "C" int dcb_proj_accum_i16(const short* chunk, int Tc, int H, int W, long
   return DCB_OK;
 }
 
-extern "C" int dcb_proj_accum_finalize(const long long* sum, const int* mx, int T, int H, int W, float* mean, float* max_out,
-                                       int floor0, dcb_stream_t stream) {
+extern "C" int dcb_proj_accum_finalize_biased(const long long* sum, const int* mx, int T, int H, int W, int bias, float* mean,
+                                              float* max_out, int floor0, dcb_stream_t stream) {
   DCB_CHECK_ARG(sum && mx && mean && max_out && T > 0 && H > 0 && W > 0, "dcb_proj_accum_finalize: bad arguments");
   const long long P = (long long)H * W;
-  proj_accum_finalize_kernel<<<cdiv(P, 256), 256, 0, (cudaStream_t)stream>>>(sum, mx, T, P, mean, max_out, floor0);
+  proj_accum_finalize_kernel<<<cdiv(P, 256), 256, 0, (cudaStream_t)stream>>>(sum, mx, T, P, mean, max_out, floor0, bias);
   g_launches += 1;
   DCB_LAUNCH_OK("proj_accum_finalize_kernel");
   return DCB_OK;
+}
+
+extern "C" int dcb_proj_accum_finalize(const long long* sum, const int* mx, int T, int H, int W, float* mean, float* max_out,
+                                       int floor0, dcb_stream_t stream) {
+  return dcb_proj_accum_finalize_biased(sum, mx, T, H, W, 0, mean, max_out, floor0, stream);
 }
 
 extern "C" int dcb_standardize_f32(const float* in, long long n, float* out, double* stats, dcb_stream_t stream) {

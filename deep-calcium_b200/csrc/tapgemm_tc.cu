@@ -55,6 +55,7 @@ struct TcFwdParams {
   int out_f32;              // 1: store fp32 (gradient tensors), 0: store bf16 (activations)
   int swap;                 // 1: weights are the MMA A operand (M = 128 channel rows), pixels the B operand (N = 256)
   int stages;
+  int f16;                  // 16-bit element format: 0 = bf16, 1 = fp16
   __nv_bfloat16* out;
   const float* scale;
   const float* shift;
@@ -67,7 +68,8 @@ struct TcFwdParams {
 // channel of this warp, or -1 when the pixel lies outside the tensor.
 template <typename PixFn>
 __device__ __forceinline__ void epilogue_swapped(uint32_t t_addr, int npix, bool warp_valid, float sc, float sh, int relu,
-                                                 int out_f32, void* out_base, uint8_t* stage, int lane, PixFn pix_index) {
+                                                 int out_f32, void* out_base, uint8_t* stage, int lane, PixFn pix_index,
+                                                 int f16 = 0) {
   for (int j = 0; j < npix; j += 32) {
     uint32_t r[32];
     tmem_ld_32x32b_x32(t_addr + j, r);
@@ -92,12 +94,12 @@ __device__ __forceinline__ void epilogue_swapped(uint32_t t_addr, int npix, bool
               *reinterpret_cast<const float4*>(st + px * 32 + chunk * 4);
       }
     } else {
-      __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(stage);
+      uint16_t* st = reinterpret_cast<uint16_t*>(stage);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         float v = fmaf(__uint_as_float(r[i]), sc, sh);
         if (relu) v = fmaxf(v, 0.f);
-        st[i * 32 + lane] = __float2bfloat16_rn(v);
+        st[i * 32 + lane] = cvt16(v, f16);
       }
       __syncwarp();
 #pragma unroll
@@ -105,7 +107,7 @@ __device__ __forceinline__ void epilogue_swapped(uint32_t t_addr, int npix, bool
         const int idx = lane + 32 * q, px = idx >> 2, chunk = idx & 3;
         const long long o = pix_index(j + px);
         if (o >= 0)
-          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_base) + o + chunk * 8) =
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out_base) + o + chunk * 8) =
               *reinterpret_cast<const uint4*>(st + px * 32 + chunk * 8);
       }
     }
@@ -194,7 +196,7 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
   } else if (warp == 1) {
     // ===================================================== MMA issuer (single thread)
     if (elect_one()) {
-      const uint32_t idesc = p.swap ? make_idesc_bf16(128, 256, 0, 0) : make_idesc_bf16(TC_BM, p.BN, 0, 0);
+      const uint32_t idesc = p.swap ? make_idesc_16(128, 256, 0, 0, p.f16) : make_idesc_16(TC_BM, p.BN, 0, 0, p.f16);
       const uint32_t swz = (p.BK == 64) ? SWZ_128B : SWZ_64B;
       const uint32_t sbo = 8u * p.BK * 2u;          // 8 rows of BK bf16
       const int ksteps = p.BK / 16;
@@ -280,7 +282,7 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
         mbar_wait(&bar_tfull[acc], acc_phase);
         tc_fence_after();
         epilogue_swapped(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols), 256, warp_valid, sc, sh,
-                         p.relu, p.out_f32, p.out, s_stage[quarter], lane, pix_index);
+                         p.relu, p.out_f32, p.out, s_stage[quarter], lane, pix_index, p.f16);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_tempty[acc]);
@@ -334,7 +336,7 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
           }
         } else if (valid) {
           uint32_t pk[16];
-          bn_relu_pack32(r, s_scale + cbase + c, s_shift + cbase + c, p.relu, pk);
+          bn_relu_pack32(r, s_scale + cbase + c, s_shift + cbase + c, p.relu, pk, p.f16);
           store_pk16(orow + c, pk);
         }
       }
@@ -463,6 +465,7 @@ struct TcStripParams {
   int need_y;               // 0: the activation itself is not stored (head fused, nobody else reads it)
   __nv_bfloat16* pool_out;  // 2x2 max-pooled copy [N][H/2][W/2][Cout] (unet_2d_summary.py:176-194) or null
   int relu, out_f32;
+  int f16;                  // 16-bit element format: 0 = bf16, 1 = fp16
   __nv_bfloat16* out;
   const float* scale;
   const float* shift;
@@ -594,7 +597,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      const uint32_t idesc = p.swap ? make_idesc_bf16(128, 256, 0, 0) : make_idesc_bf16(TC_BM, p.Cout, 0, 0);
+      const uint32_t idesc = p.swap ? make_idesc_16(128, 256, 0, 0, p.f16) : make_idesc_16(TC_BM, p.Cout, 0, 0, p.f16);
       const uint32_t swz = (p.BK == 64) ? SWZ_128B : SWZ_64B;
       const uint32_t pitch = p.BK * 2u, sbo = 8u * pitch;
       const int ksteps = p.BK / 16;
@@ -617,7 +620,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
         // hundred cycles (profiles/r1_umma_overhead_probe.log), as much as the 7 MMAs of a row.  Input rows (2m-1, 2m)
         // arrive under one row_full barrier, open the output pair P(m) = rows (2m, 2m+1) (one tempty barrier, armed by the
         // epilogue quartet that drains that pair) and complete the pair P(m-1) (one tfull commit).
-        const uint32_t id0 = make_idesc_bf16(TC_BM, 0, 0, 0), idu = ((uint32_t)p.Cout >> 3) << 17;   // N field += Cout per row
+        const uint32_t id0 = make_idesc_16(TC_BM, 0, 0, 0, p.f16), idu = ((uint32_t)p.Cout >> 3) << 17;   // N field += Cout per row
         const uint32_t nmask = (uint32_t)nacc - 1u, pmask = ((uint32_t)nacc >> 1) - 1u;
         const int pair_sh = nacc_sh - 1;
         const uint64_t dW = dbase + w16;
@@ -782,7 +785,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
           mbar_wait(&bar_tfull[acc], acc_phase);
           tc_fence_after();
           epilogue_swapped(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols), 256, warp_valid, sc, sh,
-                           p.relu, p.out_f32, p.out, s_stage + quarter * 4096, lane, pix_index);
+                           p.relu, p.out_f32, p.out, s_stage + quarter * 4096, lane, pix_index, p.f16);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_tempty[acc]);
@@ -825,7 +828,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
               }
             } else {
               uint32_t pk[16];
-              bn_relu_pack32(r, s_scale + c, s_shift + c, p.relu, pk);
+              bn_relu_pack32(r, s_scale + c, s_shift + c, p.relu, pk, p.f16);
               store_pk16(orow + c, pk);
             }
 #ifdef DCB_STRIP_TIMING
@@ -887,14 +890,14 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
               zacc += (za0.x + za0.y) + (za1.x + za1.y);
             } else {
               uint32_t pk[16];
-              bn_relu_pack32(r, s_scale + c, s_shift + c, p.relu, pk);
+              bn_relu_pack32(r, s_scale + c, s_shift + c, p.relu, pk, p.f16);
               if (p.head_kernel) {            // head on the rounded (stored) bf16 values, four partial sums
                 float za[4] = {0.f, 0.f, 0.f, 0.f};
   #pragma unroll
                 for (int g = 0; g < 8; ++g) {
                   const float4 wd = *reinterpret_cast<const float4*>(s_wd + c + 4 * g);
-                  const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[2 * g]));
-                  const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[2 * g + 1]));
+                  const float2 f0 = unpack16x2(pk[2 * g], p.f16);
+                  const float2 f1 = unpack16x2(pk[2 * g + 1], p.f16);
                   za[0] = fmaf(f0.x, wd.x, za[0]); za[1] = fmaf(f0.y, wd.y, za[1]);
                   za[2] = fmaf(f1.x, wd.z, za[2]); za[3] = fmaf(f1.y, wd.w, za[3]);
                 }
@@ -913,12 +916,9 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
                   uint32_t mx[16];
   #pragma unroll
                   for (int q = 0; q < 16; ++q) {
-                    __nv_bfloat162 a2 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&pk[q]),
-                                                *reinterpret_cast<__nv_bfloat162*>(&pool_prev[cb][q]));
-                    uint32_t au = *reinterpret_cast<uint32_t*>(&a2);
-                    uint32_t bu = __shfl_xor_sync(0xffffffffu, au, 1);
-                    __nv_bfloat162 m2 = __hmax2(a2, *reinterpret_cast<__nv_bfloat162*>(&bu));
-                    mx[q] = *reinterpret_cast<uint32_t*>(&m2);
+                    const uint32_t au = max16x2(pk[q], pool_prev[cb][q], p.f16);
+                    const uint32_t bu = __shfl_xor_sync(0xffffffffu, au, 1);
+                    mx[q] = max16x2(au, bu, p.f16);
                   }
                   if ((lane & 1) == 0) {
                     __nv_bfloat16* prow = p.pool_out + ((((size_t)n * (p.H >> 1) + ((h0 + t) >> 1)) * (p.W >> 1) + ((w0 + m) >> 1)) * p.Cout + c);
@@ -973,6 +973,7 @@ struct TcFlatParams {
   int wrows;                // rows of the weight box = min(Cout, 128)
   uint32_t pbuf_bytes;      // R * Wp * 128 rounded up to 1024
   int relu, out_f32;
+  int f16;                  // 16-bit element format: 0 = bf16, 1 = fp16
   void* out;
   const float* scale;
   const float* shift;
@@ -1049,7 +1050,7 @@ tapgemm_tc_flat_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(128, p.NT, 0, 0);
+      const uint32_t idesc = make_idesc_16(128, p.NT, 0, 0, p.f16);
       const uint64_t dbase = make_smem_desc(0, 16, 1024, SWZ_128B);
       const uint32_t pb16 = smem_u32(s_pb) >> 4, w16 = smem_u32(s_w) >> 4, pbuf16 = p.pbuf_bytes >> 4;
       int pb = 0, ws = 0; uint32_t pb_par = 0, ws_par = 0;
@@ -1109,7 +1110,7 @@ tapgemm_tc_flat_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
       mbar_wait(&bar_tfull[acc], (it >> 1) & 1u);
       tc_fence_after();
       epilogue_swapped(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)p.NT, p.NT, warp_valid, sc, sh, p.relu,
-                       p.out_f32, p.out, s_stage + quarter * 4096, lane, pix_index);
+                       p.out_f32, p.out, s_stage + quarter * 4096, lane, pix_index, p.f16);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[acc]);
@@ -1139,13 +1140,16 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // bf16 tensor map; dims/strides innermost first; strides[i] is the byte stride of dim i+1
+static thread_local int t_map_f16 = 0;   // element format of the maps built by the current call (set by the run_tc_* entry points)
 static int make_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, int swizzle_bytes) {
+                    const uint32_t* box, int swizzle_bytes_in) {
+  const int swizzle_bytes = swizzle_bytes_in;
+  const int f16 = t_map_f16;
   typedef std::tuple<const void*, int, std::vector<uint64_t>, std::vector<uint64_t>, std::vector<uint32_t>, int> Key;
   static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;
   Key key(ptr, rank, std::vector<uint64_t>(dims, dims + rank), std::vector<uint64_t>(strides_bytes, strides_bytes + rank - 1),
-          std::vector<uint32_t>(box, box + rank), swizzle_bytes);
+          std::vector<uint32_t>(box, box + rank), swizzle_bytes + (f16 ? 100000 : 0));
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return DCB_OK; }
@@ -1156,7 +1160,7 @@ static int make_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t*
   for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
   CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
+  CUresult r = enc(out, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1185,25 +1189,16 @@ static int pick_pow2_box(int extent, int maxbox) {
   return best;
 }
 
-// swapped orientation policy: DCB_SWAP_MIN_COUT = smallest Cout for which the swapped orientation is used
+// swapped orientation policy: DCB_POLICY_SWAP_MIN_COUT = smallest Cout for which the swapped orientation is used
 // (<= 128 always required); 0 disables.  Default chosen from per-layer measurements (profiles/).
-static int swap_min_cout() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("DCB_SWAP_MIN_COUT");
-    v = e ? atoi(e) : 64;
-    if (getenv("DCB_NO_SWAP")) v = 0;
-  }
-  return v;
-}
+static int swap_min_cout() { return policy(DCB_POLICY_SWAP_MIN_COUT); }
 static bool swap_allowed(int Nout) { return swap_min_cout() > 0 && Nout >= swap_min_cout() && Nout <= 128; }
 
 // strip kernel plan for a launch that computes Nsub of the layer's Nout output channels (Nsub < Nout: the layer is
 // run as Nout / Nsub launches because the weights of all channels do not fit next to a useful halo ring);
 // returns false when the layer is not eligible
 static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, int Nsub, bool fused, TcStripParams& p, size_t& dyn_smem) {
-  static const bool disabled = getenv("DCB_NO_STRIP") != nullptr;
-  if (disabled) return false;
+  if (!policy(DCB_POLICY_STRIP)) return false;
   if (g.ntaps != 9 || g.zsub > 1 || g.sy != 1) return false;
   if (g.GW % 128 != 0 || Nsub > 128 || Nsub % 32 != 0 || Nout % Nsub != 0) return false;
   const int K = C0 + C1;
@@ -1217,7 +1212,7 @@ static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, int Nsub, boo
   // Cout = 64 is faster folded (13 MMAs of N = 192 per 128 pixels) than swapped (36 MMAs of N = 256 per 256 pixels with
   // half of the 128 M rows empty): measured 0.050/0.056 -> 0.042/0.046 ms on the 256^2 layers; swapped strips are
   // for Cout = 128 only
-  static const bool no_fold_pref = getenv("DCB_NO_FOLD") != nullptr;
+  const bool no_fold_pref = !policy(DCB_POLICY_FOLD);
   int swap = (!fused && swap_allowed(Nsub) && g.GW % 256 == 0 && (Nsub > 64 || no_fold_pref || g.GH % 2 != 0)) ? 1 : 0;
   int slot = 0, ring = 0;
   for (; swap >= 0; --swap) {
@@ -1232,7 +1227,7 @@ static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, int Nsub, boo
   memset(&p, 0, sizeof(p));
   p.N = g.N; p.H = g.GH; p.W = g.GW; p.C0 = C0; p.C1 = C1; p.BK = BK; p.nkc = nkc; p.Cout = Nsub; p.OC = Nout;
   p.ring = ring; p.slot_bytes = slot; p.swap = swap; p.wsegs = g.GW / (swap ? 256 : 128);
-  static const bool no_fold = getenv("DCB_NO_FOLD") != nullptr;
+  const bool no_fold = !policy(DCB_POLICY_FOLD);
   p.fold = (!swap && !no_fold && (Nsub == 32 || Nsub == 64) && g.GH % 2 == 0 && ring >= 4) ? 1 : 0;
   if (fused && (g.GH % 2 != 0)) return false;          // row pairs of the fused pool must not straddle strips
   if (Nsub < Nout && !p.fold) return false;            // channel-split launches only pay with the folded issue
@@ -1245,8 +1240,8 @@ static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, int Nsub, boo
 // flat halo-tile kernel: plan + launch; returns DCB_ERR_UNSUPPORTED (nothing launched) when the layer is not eligible
 static int run_tc_flat(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* B, int Nout, void* out,
                        const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st) {
-  static const bool disabled = getenv("DCB_NO_FLAT") != nullptr;
-  if (disabled || g.ntaps != 9 || g.zsub > 1 || g.sy != 1) return DCB_ERR_UNSUPPORTED;
+  const int flat_policy = policy(DCB_POLICY_FLAT);
+  if (flat_policy == 0 || g.ntaps != 9 || g.zsub > 1 || g.sy != 1) return DCB_ERR_UNSUPPORTED;
   if (C0 % 64 != 0 || C1 % 64 != 0 || Nout < 64 || g.GW > 64 || g.GW < 16) return DCB_ERR_UNSUPPORTED;
   const int Wp = g.GW + 2;
   const long long positions = (long long)g.GH * Wp;
@@ -1264,14 +1259,14 @@ static int run_tc_flat(const TapGeom& g, const void* s0, int C0, const void* s1,
   // Measured (scripts/one_layer.py, profiles/r1_flat_kernel_ab.txt): the coarse work items (NT positions x 128 channels x all
   // of K) only pay when every SM gets several of them; otherwise the generic kernel's finer tiles balance better.
   {
-    static const bool force = getenv("DCB_FLAT_ALWAYS") != nullptr;
+    const bool force = flat_policy >= 2;
     const long long items = (long long)g.N * ((positions + NT - 1) / NT) * cdiv(Nout, 128);
     if (!force && items < 4LL * sm_count()) return DCB_ERR_UNSUPPORTED;
   }
   p.N = g.N; p.H = g.GH; p.W = g.GW; p.Wp = Wp; p.C0 = C0; p.C1 = C1; p.nkc = (C0 + C1) / 64;
   p.Cout = Nout; p.mtiles = cdiv(Nout, 128); p.NT = NT; p.ptiles = (int)((positions + NT - 1) / NT); p.R = R;
   p.wrows = Nout < 128 ? Nout : 128; p.pbuf_bytes = pbuf;
-  p.relu = relu; p.out_f32 = out_f32; p.out = out; p.scale = scale; p.shift = shift;
+  p.relu = relu; p.out_f32 = out_f32; p.out = out; p.scale = scale; p.shift = shift; p.f16 = g.f16;
   CUtensorMap mA0, mA1, mB;
   auto mk = [&](CUtensorMap* m, const void* ptr, int C) -> int {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.N};
@@ -1300,6 +1295,7 @@ static int run_tc_flat(const TapGeom& g, const void* s0, int C0, const void* s1,
   tapgemm_tc_flat_kernel<<<grid, FL_THREADS, dyn, st>>>(mA0, mA1, mB, p);
   g_launches += 1;
   DCB_LAUNCH_OK("tapgemm_tc_flat_kernel");
+  note_kernel("flat");
   return DCB_OK;
 }
 
@@ -1310,6 +1306,7 @@ static int run_tc_generic(const TapGeom& g, const void* s0, int C0, const void* 
 // DCB_ERR_UNSUPPORTED (without launching) when this layer shape cannot take the fused path.
 int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* B, int Nout, void* out,
                const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st, const TcFusion* fuse) {
+  t_map_f16 = g.f16;
   if (C0 % 32 != 0 || C1 % 32 != 0 || Nout % 32 != 0)
     return fail(DCB_ERR_UNSUPPORTED, "bf16 tensor-core path needs channel counts that are multiples of 32 "
                 "(got C0=%d C1=%d Cout=%d); use the fp32 check mode for other widths", C0, C1, Nout);
@@ -1335,11 +1332,12 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
     const bool fused = fuse != nullptr;
     if (fused && (out_f32 || (fuse->pool_out && Nout > 64))) return fail(DCB_ERR_UNSUPPORTED, "fused epilogue not available for this layer");
     bool strip_ok = plan_strip(g, C0, C1, Nout, Nout, fused, sp, dyn);
-    static const bool no_nsplit = getenv("DCB_NO_NSPLIT") != nullptr;
+    const bool no_nsplit = !policy(DCB_POLICY_NSPLIT);
     if (!strip_ok && !fused && !no_nsplit && Nout == 64) strip_ok = plan_strip(g, C0, C1, Nout, 32, fused, sp, dyn);
     if (fused && !strip_ok) return fail(DCB_ERR_UNSUPPORTED, "fused epilogue not available for this layer");
     if (strip_ok) {
       sp.relu = relu; sp.out_f32 = out_f32; sp.out = reinterpret_cast<__nv_bfloat16*>(out); sp.scale = scale; sp.shift = shift;
+      sp.f16 = g.f16;
       sp.need_y = 1;
       if (fused) {
         sp.head_kernel = fuse->head_kernel; sp.head_bias = fuse->head_bias; sp.logit = fuse->logit; sp.prob = fuse->prob;
@@ -1383,6 +1381,8 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
         g_launches += 1;
         DCB_LAUNCH_OK("tapgemm_tc_strip_kernel");
       }
+      note_kernel(sp.fold ? (fused ? "strip_fold_fused" : (sp.Cout < Nout ? "strip_fold_nsplit" : "strip_fold"))
+                          : (sp.swap ? "strip_swap" : (fused ? "strip_fused" : "strip")));
 #ifdef DCB_STRIP_TIMING
       if (sp.fold && getenv("DCB_STRIP_TIMING_PRINT")) {
         cudaStreamSynchronize(st);
@@ -1431,6 +1431,7 @@ static int run_tc_generic(const TapGeom& g, const void* s0, int C0, const void* 
   p.OH = g.OH; p.OW = g.OW; p.OC = out_pitch;
   p.osy = g.osy; p.osx = g.osx; p.ody = g.ody; p.odx = g.odx;
   p.relu = relu; p.out_f32 = out_f32; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.scale = scale; p.shift = shift;
+  p.f16 = g.f16;
   // Swapped orientation for narrow outputs: with <= 128 output channels the normal orientation spends the
   // A-operand read time (128 pixel rows per MMA) on an N of 32..128; swapped, every MMA covers 256 pixels.
   {
@@ -1508,6 +1509,7 @@ static int run_tc_generic(const TapGeom& g, const void* s0, int C0, const void* 
   tapgemm_tc_fwd_kernel<<<grid, TC_THREADS, dyn_smem, st>>>(mA0, mA1, mB, p);
   g_launches += 1;
   DCB_LAUNCH_OK("tapgemm_tc_fwd_kernel");
+  note_kernel(p.swap ? "generic_swap" : "generic");
   return DCB_OK;
 }
 
@@ -1900,8 +1902,7 @@ static WgradPlan plan_wgrad(const TapGeom& g, int K, int C0, int C1, int Nout) {
 // sources are consumed as 32-channel blocks (<= 2 per launch: 3 dy x 2 blocks x Nout accumulator columns <= 512);
 // a 64-channel tensor is two blocks of the same tensor map, more than two blocks run as several launches
 static bool wgrad_strip_ok(const TapGeom& g, int C0, int C1, int Nout) {
-  static const bool disabled = getenv("DCB_NO_WGRAD_STRIP") != nullptr;
-  return !disabled && g.ntaps == 9 && g.sy == 1 && (C0 == 32 || C0 == 64) && (C1 == 0 || C1 == 32 || C1 == 64) &&
+  return policy(DCB_POLICY_WGRAD_STRIP) && g.ntaps == 9 && g.sy == 1 && (C0 == 32 || C0 == 64) && (C1 == 0 || C1 == 32 || C1 == 64) &&
          (Nout == 32 || Nout == 64) && g.GW % WS_PX == 0;
 }
 
@@ -1961,11 +1962,14 @@ static int run_tc_wgrad_strip(const TapGeom& g, const WgradBlock* blk, int nblk,
   launch_reduce_splits_rows(p.part, grid, 9, K * Nout, dW + (size_t)k_off * Nout, (size_t)K_total * Nout, st);
   g_launches += 2;
   DCB_LAUNCH_OK("reduce_splits_kernel");
+  note_kernel("wgrad_strip");
   return DCB_OK;
 }
 
 int run_tc_wgrad(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* G, int Nout, float* dW,
                  void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (g.f16) return fail(DCB_ERR_UNSUPPORTED, "the fp16 mode is inference only: gradients are computed in bf16 (or fp32 check) mode");
+  t_map_f16 = 0;
   if (C0 % 32 != 0 || C1 % 32 != 0 || Nout % 32 != 0)
     return fail(DCB_ERR_UNSUPPORTED, "bf16 tensor-core wgrad needs channel counts that are multiples of 32 "
                 "(got C0=%d C1=%d N=%d)", C0, C1, Nout);
@@ -2034,6 +2038,7 @@ int run_tc_wgrad(const TapGeom& g, const void* s0, int C0, const void* s1, int C
   launch_reduce_splits(p.part, w.splits, (size_t)g.ntaps * K * Nout, dW, st);
   g_launches += 2;
   DCB_LAUNCH_OK("reduce_splits_kernel");
+  note_kernel("wgrad");
   return DCB_OK;
 }
 

@@ -20,4 +20,5 @@ struct TapGeom {
   int osy, osx;     // output position = g*os + od
   int ody, odx;
   int zsub;         // >1: blockIdx.z selects sub-position (ody,odx)=(z/2,z%2) and weight slice z
+  int f16;          // 16-bit element format of the tensor-core path: 0 = bf16, 1 = fp16 (DCB_F16, inference only)
 };

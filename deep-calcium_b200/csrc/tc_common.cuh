@@ -3,6 +3,7 @@
 // Written as inline PTX; the bit layouts follow the PTX ISA "tcgen05" tables.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace dcb {
@@ -184,9 +185,32 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 // Instruction descriptor for kind::f16 (PTX ISA "instruction descriptor"):
 //   [4,6) D format (1 = f32)  [7,10) A format (1 = bf16)  [10,13) B format (1 = bf16)
 //   [15] A major (0 = K, 1 = MN)  [16] B major  [17,23) N >> 3  [24,29) M >> 4
+// f16 != 0: fp16 operands (format code 0) instead of bf16 (format code 1); same MMA rate, 10 instead of 7 mantissa bits
+__host__ __device__ constexpr uint32_t make_idesc_16(int M, int N, int a_mn_major, int b_mn_major, int f16) {
+  return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  return make_idesc_16(M, N, a_mn_major, b_mn_major, 0);
+}
+
+// ---------------------------------------------------------------- 16-bit element helpers (bf16 / fp16 by a runtime flag)
+__device__ __forceinline__ uint16_t cvt16(float v, int f16) {
+  if (f16) { const __half h = __float2half_rn(v); return *reinterpret_cast<const uint16_t*>(&h); }
+  const __nv_bfloat16 b = __float2bfloat16_rn(v);
+  return *reinterpret_cast<const uint16_t*>(&b);
+}
+__device__ __forceinline__ float2 unpack16x2(uint32_t u, int f16) {
+  if (f16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+}
+__device__ __forceinline__ uint32_t max16x2(uint32_t a, uint32_t b, int f16) {
+  if (f16) {
+    const __half2 m = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&m);
+  }
+  const __nv_bfloat162 m = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&m);
 }
 
 // ---------------------------------------------------------------- epilogue stores
@@ -222,8 +246,25 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 // read from (16-byte aligned) shared memory as float4; ReLU is applied to the packed bf16 pairs (identical result:
 // rounding is monotonic and keeps the sign).
 __device__ __forceinline__ void bn_relu_pack32(const uint32_t (&r)[32], const float* s_sc, const float* s_sh, int relu,
-                                               uint32_t (&pk)[16]) {
+                                               uint32_t (&pk)[16], int f16 = 0) {
   const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+  if (f16) {
+    const __half2 hzero2 = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 sc = *reinterpret_cast<const float4*>(s_sc + 4 * g);
+      const float4 sh = *reinterpret_cast<const float4*>(s_sh + 4 * g);
+      const float2 v0 = ffma2(make_float2(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1])), make_float2(sc.x, sc.y),
+                              make_float2(sh.x, sh.y));
+      const float2 v1 = ffma2(make_float2(__uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3])), make_float2(sc.z, sc.w),
+                              make_float2(sh.z, sh.w));
+      __half2 b0 = __float22half2_rn(v0), b1 = __float22half2_rn(v1);
+      if (relu) { b0 = __hmax2(b0, hzero2); b1 = __hmax2(b1, hzero2); }
+      pk[2 * g] = *reinterpret_cast<uint32_t*>(&b0);
+      pk[2 * g + 1] = *reinterpret_cast<uint32_t*>(&b1);
+    }
+    return;
+  }
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
     const float4 sc = *reinterpret_cast<const float4*>(s_sc + 4 * g);

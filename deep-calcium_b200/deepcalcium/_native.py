@@ -19,7 +19,10 @@ c_d = ctypes.c_double
 c_p = ctypes.c_void_p
 c_sz = ctypes.c_size_t
 
-DCB_F32, DCB_BF16 = 0, 1
+DCB_F32, DCB_BF16, DCB_F16 = 0, 1, 2
+# dcb_policy_key (include/dcb200.h)
+POLICY_KEYS = {'flat': 0, 'strip': 1, 'fold': 2, 'nsplit': 3, 'swap_min_cout': 4, 'wgrad_strip': 5, 'bn_ctas_per_sm': 6,
+               'proj_i16_splits': 7, 'splitk': 8, 'fused_bn': 9}
 LOSS_IDS = {'binary_crossentropy': 0, 'weighted_binary_crossentropy': 1, 'dice_loss': 2, 'dicesq_loss': 3}
 
 
@@ -36,6 +39,7 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.dcb_last_error.restype = ctypes.c_char_p
         _lib.dcb_launch_count.restype = ctypes.c_ulonglong
+        _lib.dcb_last_kernel.restype = ctypes.c_char_p
     return _lib
 
 
@@ -53,9 +57,10 @@ def ptr(t):
     return c_p(t.data_ptr())
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """cudaStream_t of torch's current stream on `device` (default: the current device)."""
     import torch
-    return c_p(torch.cuda.current_stream().cuda_stream)
+    return c_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def call(name, *args):
@@ -65,6 +70,44 @@ def call(name, *args):
 
 def launch_count():
     return int(lib().dcb_launch_count())
+
+
+def set_policy(**kw):
+    """dcb_set_policy for each keyword (names in POLICY_KEYS), e.g. set_policy(flat=2, strip=0)."""
+    for k, v in kw.items():
+        check(lib().dcb_set_policy(c_int(POLICY_KEYS[k]), c_int(int(v))), 'dcb_set_policy')
+
+
+def get_policy(name):
+    out = c_int(0)
+    check(lib().dcb_get_policy(c_int(POLICY_KEYS[name]), ctypes.byref(out)), 'dcb_get_policy')
+    return out.value
+
+
+def reset_policy():
+    check(lib().dcb_reset_policy(), 'dcb_reset_policy')
+
+
+class policy(object):
+    """Context manager: pin a dispatch policy for the enclosed calls, restore the previous values afterwards."""
+
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __enter__(self):
+        self.saved = {k: get_policy(k) for k in self.kw}
+        set_policy(**self.kw)
+        return self
+
+    def __exit__(self, *exc):
+        set_policy(**self.saved)
+        return False
+
+
+def last_kernel():
+    """name of the contraction-kernel variant the last dcb_conv* / dcb_*wgrad call of this thread dispatched to"""
+    s = lib().dcb_last_kernel()
+    return s.decode() if s else ''
 
 
 def require_cuda():

@@ -98,7 +98,8 @@ def make_dataset(path, name, movie=None, mean=None, mx=None, masks=None):
     if movie is not None:
         mean, mx = summarize_movie(movie, floor_max_at_zero=True)
     d = {'name': np.asarray(name), 'series__mean': np.asarray(mean).astype(np.float16),
-         'series__max': np.asarray(mx).astype(np.int16)}
+         # HDF5's integer conversion saturates (the reference assigns into an int16 dataset, nf.py:124,130)
+         'series__max': np.clip(np.asarray(mx), -32768, 32767).astype(np.int16)}
     if masks is not None:
         masks = np.asarray(masks).astype(np.int8)
         d['masks__raw'] = masks
@@ -150,13 +151,22 @@ def nf_load_hdf5(names, datasets_dir=None):
 
 # ------------------------------------------------------------------------------------------------- ingest (N4)
 def _read_tiff_frame(path):
-    """One 16-bit greyscale TIFF frame as an int16 array (the reference stores `series/raw` as int16, nf.py:121)."""
+    """One 16-bit greyscale TIFF frame -> (int16 array, bias).  Neurofinder TIFFs are uint16; the reference computes
+    series/mean and series/max from the UNWRAPPED pixel values (nf.py:129-130 work on `img`, not on the int16 copy),
+    so unsigned frames are shifted into the int16 range (value - 32768 = bits ^ 0x8000) for the exact integer kernel and
+    the bias is added back after the projection.  Signed frames pass through with bias 0."""
     from PIL import Image
     with Image.open(path) as im:
         a = np.asarray(im)
     if a.ndim != 2:
         raise ValueError('%s: expected a single greyscale frame, got shape %s' % (path, a.shape))
-    return a.astype(np.int16, copy=False)
+    if a.dtype == np.uint16:
+        return (a ^ np.uint16(0x8000)).view(np.int16), 32768
+    if a.dtype == np.uint8 or a.dtype == np.int16 or a.dtype == np.int8:
+        return a.astype(np.int16, copy=False), 0
+    if np.issubdtype(a.dtype, np.integer) and a.min() >= -32768 and a.max() <= 32767:
+        return a.astype(np.int16), 0
+    raise ValueError('%s: pixel type %s does not fit the 16-bit ingest path' % (path, a.dtype))
 
 
 def summarize_tiff_dir(images_dir, chunk=64, floor_max_at_zero=True, pattern=('*.tiff', '*.tif')):
@@ -173,7 +183,7 @@ def summarize_tiff_dir(images_dir, chunk=64, floor_max_at_zero=True, pattern=('*
     paths = sorted(p for pat in pattern for p in glob.glob(os.path.join(images_dir, pat)))
     if not paths:
         raise ValueError('no TIFF frames in %s' % images_dir)
-    first = _read_tiff_frame(paths[0])
+    first, bias = _read_tiff_frame(paths[0])
     H, W = first.shape
     dev = torch.device('cuda', torch.cuda.current_device())
     hbuf = [torch.empty(chunk, H, W, dtype=torch.int16).pin_memory() for _ in range(2)]
@@ -189,9 +199,9 @@ def summarize_tiff_dir(images_dir, chunk=64, floor_max_at_zero=True, pattern=('*
         n = min(chunk, len(paths) - i0)
         hv = hbuf[k].numpy()
         for j in range(n):
-            fr = first if i0 + j == 0 else _read_tiff_frame(paths[i0 + j])
-            if fr.shape != (H, W):
-                raise ValueError('%s: frame shape %s differs from %s' % (paths[i0 + j], fr.shape, (H, W)))
+            fr, fb = (first, bias) if i0 + j == 0 else _read_tiff_frame(paths[i0 + j])
+            if fr.shape != (H, W) or fb != bias:
+                raise ValueError('%s: frame shape / pixel type %s differs from the first frame %s' % (paths[i0 + j], fr.shape, (H, W)))
             hv[j] = fr
         with torch.cuda.stream(copy_stream):
             dbuf[k][:n].copy_(hbuf[k][:n], non_blocking=True)
@@ -201,7 +211,8 @@ def summarize_tiff_dir(images_dir, chunk=64, floor_max_at_zero=True, pattern=('*
         done[k].record(main)
     mean = torch.empty(H, W, dtype=torch.float32, device=dev)
     mx = torch.empty(H, W, dtype=torch.float32, device=dev)
-    ops.proj_accum_finalize(ssum, smax, len(paths), mean, mx, floor_max_at_zero)
+    # unsigned frames were shifted by -32768: the device restores the bias in exact integer arithmetic
+    ops.proj_accum_finalize(ssum, smax, len(paths), mean, mx, floor_max_at_zero, bias)
     return mean.cpu().numpy(), mx.cpu().numpy(), len(paths)
 
 

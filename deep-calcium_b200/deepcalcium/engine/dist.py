@@ -42,6 +42,17 @@ class Comm(object):
             dist.broadcast(t, src=src, group=self.group)
         return t
 
+    def all_gather_rows(self, t, counts):
+        """every rank receives every rank's [K, rows_r, W] tensor (rows_r = counts[r], may differ by one)"""
+        pad = max(counts)
+        buf = t
+        if t.shape[1] < pad:
+            buf = torch.zeros((t.shape[0], pad) + tuple(t.shape[2:]), dtype=t.dtype, device=t.device)
+            buf[:, :t.shape[1]] = t
+        out = [torch.empty_like(buf) for _ in range(self.world)]
+        dist.all_gather(out, buf.contiguous(), group=self.group)
+        return [o[:, :c] for o, c in zip(out, counts)]
+
     def gather_to_root(self, t, counts=None):
         """Rank 0 receives every rank's tensor (in rank order) and returns them as a list; other
         ranks return None.  ``counts``: leading-dimension size per rank when shards are uneven."""
@@ -81,6 +92,31 @@ def predict_tta_sharded(engine, summ_dev, comm, window=512, threshold=0.5):
     act = torch.empty(hs, ws, dtype=torch.float64, device=summ_dev.device)
     ops.tta_combine(allp, window, hs, ws, threshold, 8, act, mask)
     return mask, act
+
+
+def summarize_movie_sharded(band, comm, H, floor_max_at_zero=False, project_fn=None):
+    """Projection of ONE movie split into row bands over the ranks (reference loop: datasets/nf.py:126-130).
+    The reduction is per pixel, so rank r projects its band ``movie[:, first:first+rows, :]`` with
+    ``(first, rows) = shard_range(H, world, r)`` without any exchange; the two [rows, W] float32 maps are then
+    all-gathered (2 x 4 x H x W / world bytes per rank) so every rank holds the full (mean, max) images.
+    ``band``: [T, rows, W] tensor on this rank's device.  ``project_fn(band, floor_max_at_zero) -> (mean, max)`` defaults
+    to the CUDA kernel (deepcalcium.datasets.nf.summarize_movie_device); the CPU tests of the host logic inject one."""
+    if project_fn is None:
+        from ..datasets.nf import summarize_movie_device
+        project_fn = summarize_movie_device
+    world, rank = comm.world, comm.rank
+    first, rows = shard_range(H, world, rank)
+    if band.dim() != 3 or band.shape[1] != rows:
+        raise ValueError('rank %d of %d holds rows [%d, %d) of %d: expected a [T, %d, W] band, got %s'
+                         % (rank, world, first, first + rows, H, rows, tuple(band.shape)))
+    mean, mx = project_fn(band, floor_max_at_zero)
+    if world == 1:
+        return mean, mx
+    both = torch.stack([mean, mx], dim=0)                         # [2, rows, W]
+    counts = [shard_range(H, world, r)[1] for r in range(world)]
+    parts = comm.all_gather_rows(both, counts)                    # list over ranks of [2, rows_r, W]
+    full = torch.cat(parts, dim=1)
+    return full[0].contiguous(), full[1].contiguous()
 
 
 def sync_parameters(engine, comm):

@@ -110,9 +110,21 @@ class GraphSpec(object):
         return f
 
 
+def _truncated_normal(rng, shape):
+    """standard normal re-drawn where |z| > 2 (tf.truncated_normal, which Keras 2.0.6's VarianceScaling(distribution=
+    'normal') - i.e. he_normal - samples from: the effective standard deviation is ~0.88 of the nominal one)"""
+    z = rng.standard_normal(shape)
+    bad = np.abs(z) > 2
+    while bad.any():
+        z[bad] = rng.standard_normal(int(bad.sum()))
+        bad = np.abs(z) > 2
+    return z
+
+
 def he_normal_weights(spec, seed=None):
-    """Fresh Keras-style initialisation: he_normal kernels (fan_in = kh*kw*shape[-2], the Keras
-    rule, which is 4*Cout for the transposed kernels), zero biases, BN gamma=1 beta=0 mean=0 var=1."""
+    """Fresh Keras-style initialisation: he_normal kernels (truncated normal, stddev sqrt(2 / fan_in) with fan_in =
+    kh*kw*shape[-2], the Keras rule, which is 4*Cout for the transposed kernels), zero biases, BN gamma=1 beta=0
+    mean=0 var=1."""
     rng = np.random.RandomState(seed)
     w = OrderedDict()
     for blk in spec.blocks:
@@ -122,7 +134,7 @@ def he_normal_weights(spec, seed=None):
             limit = np.sqrt(6. / (ks[2] + ks[3]))
             w[blk.name + '/kernel'] = rng.uniform(-limit, limit, ks).astype(np.float32)
         else:
-            w[blk.name + '/kernel'] = (rng.standard_normal(ks) * np.sqrt(2. / fan_in)).astype(np.float32)
+            w[blk.name + '/kernel'] = (_truncated_normal(rng, ks) * np.sqrt(2. / fan_in)).astype(np.float32)
         w[blk.name + '/bias'] = np.zeros(blk.cout, np.float32)
         if blk.kind != 'head':
             w[blk.name + '/gamma'] = np.ones(blk.cout, np.float32)

@@ -11,7 +11,7 @@ import torch
 from .. import _native as nat
 from .._native import c_int, c_ll, c_f, c_p, c_sz, ptr, stream_ptr, call
 
-DT = {torch.float32: nat.DCB_F32, torch.bfloat16: nat.DCB_BF16}
+DT = {torch.float32: nat.DCB_F32, torch.bfloat16: nat.DCB_BF16, torch.float16: nat.DCB_F16}
 c_ull = ctypes.c_ulonglong
 c_uint = ctypes.c_uint
 
@@ -56,10 +56,10 @@ def proj_accum_i16(chunk, sum_i64, max_i32):
     call('dcb_proj_accum_i16', ptr(chunk), c_int(Tc), c_int(H), c_int(W), ptr(sum_i64), ptr(max_i32), stream_ptr())
 
 
-def proj_accum_finalize(sum_i64, max_i32, T, mean, mx, floor_max_at_zero=False):
+def proj_accum_finalize(sum_i64, max_i32, T, mean, mx, floor_max_at_zero=False, bias=0):
     H, W = mean.shape
-    call('dcb_proj_accum_finalize', ptr(sum_i64), ptr(max_i32), c_int(T), c_int(H), c_int(W), ptr(mean), ptr(mx),
-         c_int(int(floor_max_at_zero)), stream_ptr())
+    call('dcb_proj_accum_finalize_biased', ptr(sum_i64), ptr(max_i32), c_int(T), c_int(H), c_int(W), c_int(int(bias)),
+         ptr(mean), ptr(mx), c_int(int(floor_max_at_zero)), stream_ptr())
 
 
 def standardize(x, out, stats=None):

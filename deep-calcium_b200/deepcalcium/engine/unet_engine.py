@@ -18,11 +18,23 @@ from .. import _native as nat
 from . import ops
 from .graph import GraphSpec, BN_EPS, BN_MOMENTUM_CONV, BN_MOMENTUM_UP, TRAINABLE, he_normal_weights
 
-_PRECISIONS = {'bf16': torch.bfloat16, 'fp32': torch.float32, 'f32': torch.float32}
+_PRECISIONS = {'bf16': torch.bfloat16, 'fp16': torch.float16, 'f16': torch.float16, 'fp32': torch.float32, 'f32': torch.float32}
 
 
 def _align4(n):
     return (n + 3) // 4 * 4
+
+
+def _on_engine_device(fn):
+    """run a public engine method with the engine's device current: the C-ABI wrappers enqueue on the CURRENT device's
+    stream, which must be the device that owns the engine's buffers"""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        with torch.cuda.device(self.dev):
+            return fn(self, *a, **k)
+    return wrapper
 
 
 class UNetEngine(object):
@@ -30,7 +42,10 @@ class UNetEngine(object):
         nat.require_cuda()
         self.spec = spec or GraphSpec()
         self.dtype = _PRECISIONS[precision]
-        self.precision = 'bf16' if self.dtype == torch.bfloat16 else 'fp32'
+        # 'bf16' / 'fp16': tcgen05 kernels (fp16 = inference only: same MMA rate, 10 mantissa bits instead of 7, meets the
+        # north star's 1e-2 logit tolerance where bf16 storage cannot); 'fp32': CUDA-core check mode
+        self.precision = {torch.bfloat16: 'bf16', torch.float16: 'fp16', torch.float32: 'fp32'}[self.dtype]
+        self.tc = self.dtype != torch.float32
         self.dev = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
         self.use_graphs = use_graphs
         self._build_param_storage()
@@ -90,7 +105,7 @@ class UNetEngine(object):
             nk = int(np.prod(blk.kernel_shape()))
             k = self.P[blk.name + '/kernel']
             if blk.kind == 'conv':
-                if blk.cin == 1 and self.dtype == torch.bfloat16:
+                if blk.cin == 1 and self.tc:
                     self.w_fwd[blk.name] = k                     # c1 kernel reads the fp32 master
                     self.w_dgrad[blk.name] = None
                 elif self.dtype == torch.float32:
@@ -117,7 +132,6 @@ class UNetEngine(object):
         n_dbl += 8 + 2 * self.spec.nfb + 2
         self.dbl = torch.zeros(n_dbl, dtype=torch.float64, device=self.dev)
         self.metrics = torch.zeros(8, **f32)
-        self._wgrad_ws = None
 
     def _wire(self):
         inp = OrderedDict()
@@ -242,14 +256,14 @@ class UNetEngine(object):
             for blk in self.spec.blocks:
                 h, w = H >> blk.level, W >> blk.level
                 if blk.kind == 'conv':
-                    if blk.cin == 1 and self.dtype == torch.bfloat16:
+                    if blk.cin == 1 and self.tc:
                         need = max(need, ops.conv3x3_c1_wgrad_workspace_bytes(blk.cout))
                     else:
                         need = max(need, ops.conv3x3_wgrad_workspace_bytes(self.dtype, NB, h, w, blk.cin, blk.cout))
                 elif blk.kind == 'up':
                     need = max(need, ops.convT2x2_wgrad_workspace_bytes(self.dtype, NB, h // 2, w // 2, blk.cin, blk.cout))
-            if self._wgrad_ws is None or self._wgrad_ws.numel() < need:
-                self._wgrad_ws = torch.empty(max(need, 16), dtype=torch.uint8, device=self.dev)
+            # one workspace per session: a captured training graph keeps the pointer it was recorded with
+            s['wgrad_ws'] = torch.empty(max(need, 16), dtype=torch.uint8, device=self.dev)
         self._sessions[key] = s
         return s
 
@@ -269,13 +283,13 @@ class UNetEngine(object):
             if a in self._ups:
                 ops.upsample2x(act[self._ups[a]], act[a])
             if blk.kind == 'conv':
-                if blk.cin == 1 and self.dtype == torch.bfloat16:
+                if blk.cin == 1 and self.tc:
                     ops.conv3x3_c1_fwd(s['x'], self.w_fwd[n], act[n], sc, sh, True)
                 elif n == 'dec0b':
                     ops.conv3x3_fwd_fused(act[a], None, self.w_fwd[n], act[n], sc, sh, True,
                                           head_kernel=self.P['head/kernel'], head_bias=self.P['head/bias'],
                                           logit=s['logit'], prob=s['prob'], need_y=False)
-                elif n in self._pool_fused and self.dtype == torch.bfloat16:
+                elif n in self._pool_fused and self.tc:
                     # the 2x2 max-pool rides in the conv epilogue where the layer runs on the (folded) strip kernel
                     ops.conv3x3_fwd_fused(act[a], None, self.w_fwd[n], act[n], sc, sh, True, pool_out=act['pool%d' % blk.level])
                 else:
@@ -317,6 +331,7 @@ class UNetEngine(object):
         g.replay()
         self.launches += g.dcb_launches
 
+    @_on_engine_device
     def infer(self, x_dev):
         """x_dev: fp32 CUDA tensor [NB,H,W].  Returns (prob, logit) fp32 [NB,H,W] (views of static buffers)."""
         NB, H, W = x_dev.shape
@@ -326,6 +341,7 @@ class UNetEngine(object):
         self._run_graphed(s, 'graph', lambda: self._forward_inference(s))
         return s['prob'], s['logit']
 
+    @_on_engine_device
     def predict_tta(self, summ_dev, window=512, augmentation=True, threshold=0.5, transforms=None):
         """unet_2d_summary.py:578-595 for one summary image already on the device (fp32 [hs,ws]).
         Returns (mask uint8 [hs,ws], act float64 [hs,ws]) as device tensors (static buffers).
@@ -386,7 +402,7 @@ class UNetEngine(object):
             if a in self._ups:
                 ops.upsample2x(act[self._ups[a]], act[a], self._dropout_p(a, dropout), seed_base, seed_dev, layer_id[a])
             if blk.kind == 'conv':
-                if blk.cin == 1 and self.dtype == torch.bfloat16:
+                if blk.cin == 1 and self.tc:
                     ops.conv3x3_c1_fwd(s['x'], self.w_fwd[n], raw[n], None, bias, False)
                 else:
                     ops.conv3x3_fwd(act[a], act[b] if b else None, self.w_fwd[n], raw[n], None, bias, False)
@@ -435,10 +451,10 @@ class UNetEngine(object):
                              self.G[n + '/gamma'], self.G[n + '/beta'], p, seed_base, seed_dev, layer_id[n],
                              M_total=(raw[n].numel() // blk.cout) * world, dgb_scale=1.0 / world)
             if blk.kind == 'conv':
-                if blk.cin == 1 and self.dtype == torch.bfloat16:
-                    ops.conv3x3_c1_wgrad(s['x'], draw, self.G[n + '/kernel'], self._wgrad_ws)
+                if blk.cin == 1 and self.tc:
+                    ops.conv3x3_c1_wgrad(s['x'], draw, self.G[n + '/kernel'], s['wgrad_ws'])
                 else:
-                    ops.conv3x3_wgrad(act[a], act[b] if b else None, draw, self.G[n + '/kernel'], self._wgrad_ws)
+                    ops.conv3x3_wgrad(act[a], act[b] if b else None, draw, self.G[n + '/kernel'], s['wgrad_ws'])
                 if n == 'enc0a':
                     continue
                 dX = dxb[n]
@@ -461,7 +477,7 @@ class UNetEngine(object):
                 else:
                     grad_of[a] = (dX, blk.cin, 0)
             else:
-                ops.convT2x2_wgrad(act[a], draw, self.G[n + '/kernel'], self._wgrad_ws)
+                ops.convT2x2_wgrad(act[a], draw, self.G[n + '/kernel'], s['wgrad_ws'])
                 dX = dxb[n]
                 ops.convT2x2_dgrad(draw, self.w_dgrad[n], dX)
                 grad_of[a] = (dX, blk.cin, 0)
@@ -469,9 +485,12 @@ class UNetEngine(object):
         self._allreduce(self.grads)                     # 31 MB fp32: gradient of the global-batch loss
         ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, 0., self.lr_t, beta1, beta2, eps)
 
+    @_on_engine_device
     def train_step(self, x_dev, y_dev, loss='dice_loss', lr=0.002, dropout=True, beta1=0.9, beta2=0.999, eps=1e-8):
         """One train_on_batch.  x_dev fp32 [B,h,w], y_dev uint8 [B,h,w] on the device.
         Returns the device tensor [loss, F1, prec, reca, dice, dicesq, posyt, posyp] (static buffer)."""
+        if self.dtype == torch.float16:
+            raise ValueError("precision 'fp16' is inference only (gradients underflow in fp16); train in 'bf16' or 'fp32'")
         B, H, W = x_dev.shape
         s = self._session(B, H, W, True)
         s['x'].copy_(x_dev)

@@ -246,14 +246,16 @@ class UNet2DSummary(object):
         M_summ = [self.mask_summary_func(dsp) for dsp in dataset_paths]
         ycval = [(s.shape[0] - int(s.shape[0] * prop_val), s.shape[0]) for s in S_summ]
         yctrn = [(0, int(s.shape[0] * prop_trn)) for s in S_summ]
-        # same RNG stream and the same crops as _batch_gen, but the pixel work (slice, zero fill, flips / rot90s) runs
-        # on the GPU and the batch never visits the host (DEEP_CALCIUM_HOST_SAMPLER=1 selects the host restatement)
-        if os.environ.get('DEEP_CALCIUM_HOST_SAMPLER') == '1':
-            gen_trn = self._batch_gen(S_summ, M_summ, names, yctrn, batch_size_trn, nb_steps_trn, shape_trn, 15)
-        else:
-            gen_trn = self._batch_gen_device(S_summ, M_summ, names, yctrn, batch_size_trn, nb_steps_trn, shape_trn, 15,
-                                             device=model.engine.dev)
+        # the reference's _batch_gen (:434-530) with the same global-numpy RNG stream and the same crops; the pixel work
+        # (slice, zero fill, flips / rot90s) runs on the GPU and the batch never visits the host
+        gen_trn = self._batch_gen(S_summ, M_summ, names, yctrn, batch_size_trn, nb_steps_trn, shape_trn, 15,
+                                  device=model.engine.dev)
 
+        for cb in keras_callbacks:               # Keras calls these before the first epoch
+            if hasattr(cb, 'set_model'):
+                cb.set_model(model)
+            if hasattr(cb, 'on_train_begin'):
+                cb.on_train_begin({})
         tic = int(time())
         csv_path = '%s/%d_metrics.csv' % (self.cpdir, tic)
         history = {}
@@ -270,13 +272,16 @@ class UNet2DSummary(object):
             last_path = '%s/%d_model_%02d_%.3f.npz' % (self.cpdir, tic, epoch, logs['val_nf_f1_mean'])
             model.save(last_path)
             # ReduceLROnPlateau(monitor='F1', factor=0.5, patience=5, min_lr=1e-4, mode='max') (:425-426)
+            # Keras 2.0.6 order: the patience test comes BEFORE the wait counter is incremented, so the rate is halved
+            # on the 6th non-improving epoch; after a reduction the counter restarts at 1 (wait = 0, then += 1)
             if logs['F1'] > best_f1 + 1e-4:
                 best_f1, since_best = logs['F1'], 0
             else:
+                if since_best >= 5:
+                    if model.optimizer.lr > 1e-4 + 1e-4 * 1e-4:
+                        model.optimizer.lr = max(model.optimizer.lr * 0.5, 1e-4)
+                        since_best = 0
                 since_best += 1
-                if since_best >= 5 and model.optimizer.lr > 1e-4:
-                    model.optimizer.lr = max(model.optimizer.lr * 0.5, 1e-4)
-                    since_best = 0
             for cb in keras_callbacks:
                 cb.on_epoch_end(epoch, logs)
             for k, v in logs.items():
@@ -321,56 +326,6 @@ class UNet2DSummary(object):
     def _predict_window(model, x, hw):
         return model.predict(x[np.newaxis, :, :])[0]
 
-    def _batch_gen(self, S_summ, M_summ, names, y_coords, batch_size, nb_steps, window_shape,
-                   nb_max_augment=0, scores_path=None):
-        """Crop sampler of the reference (unet_2d_summary.py:434-530): neuron-centred windows with a
-        +-5 px jitter, zero fill at the borders, 0..nb_max_augment random flips / rot90s.  Uses the
-        global numpy RNG exactly like the reference so ``np.random.seed`` reproduces its stream."""
-        rng = np.random
-        hw, ww = window_shape
-        nb_yields = 0
-        augment_funcs = [
-            lambda a, b: (a, b),
-            lambda a, b: (a[:, ::-1], b[:, ::-1]),
-            lambda a, b: (a[::-1, :], b[::-1, :]),
-            lambda a, b: (np.rot90(a, 1), np.rot90(b, 1)),
-            lambda a, b: (np.rot90(a, 2), np.rot90(b, 2)),
-            lambda a, b: (np.rot90(a, 3), np.rot90(b, 3)),
-        ]
-        neuron_locs = []
-        for ds_idx, m in enumerate(M_summ):
-            ymin, ymax = y_coords[ds_idx]
-            neuron_locs.append(list(zip(*np.where(m[ymin:ymax, :] == 1))))
-        ds_idxs = np.arange(len(S_summ))
-        ds_idxp = np.ones((len(ds_idxs))) / len(ds_idxs)
-        while True:
-            if scores_path and os.path.exists(scores_path) and (nb_yields - 1) % nb_steps == 0:
-                with open(scores_path, 'rb') as fp:
-                    names_to_scores = pickle.load(fp)
-                ds_idxp = np.array([1 - np.mean(names_to_scores[n]) for n in names])
-                ds_idxp /= np.sum(ds_idxp)
-            s_batch = np.zeros((batch_size, hw, ww), dtype=np.float32)
-            m_batch = np.zeros((batch_size, hw, ww), dtype=np.uint8)
-            for b_idx in range(batch_size):
-                ds_idx = rng.choice(np.arange(len(S_summ)), p=ds_idxp)
-                s, m = S_summ[ds_idx], M_summ[ds_idx]
-                hs, ws = s.shape
-                ymin, ymax = y_coords[ds_idx]
-                cy, cx = neuron_locs[ds_idx][rng.randint(0, len(neuron_locs[ds_idx]))]
-                cy = min(max(ymin, cy + rng.randint(-5, 5)), ymax)
-                cx = min(max(0, cx + rng.randint(-5, 5)), ws)
-                y0 = max(ymin, int(cy - (hw / 2)))
-                y1 = min(y0 + hw, ymax)
-                x0 = max(0, int(cx - (ww / 2)))
-                x1 = min(x0 + ww, ws)
-                m_batch[b_idx, :y1 - y0, :x1 - x0] = m[y0:y1, x0:x1]
-                s_batch[b_idx, :y1 - y0, :x1 - x0] = s[y0:y1, x0:x1]
-                nb_augment = rng.randint(0, nb_max_augment + 1)
-                for aug in rng.choice(augment_funcs, nb_augment):
-                    s_batch[b_idx], m_batch[b_idx] = aug(s_batch[b_idx], m_batch[b_idx])
-            nb_yields += 1
-            yield s_batch, m_batch
-
     # D4 elements of the sampler's augment_funcs as index maps on an n x n window: out[i, j] = a[M @ (i, j) + t]
     @staticmethod
     def _aug_maps(n):
@@ -383,9 +338,10 @@ class UNet2DSummary(object):
 
     def _crop_descriptors(self, S_summ, M_summ, names, y_coords, batch_size, nb_steps, window_shape,
                           nb_max_augment=0, scores_path=None):
-        """The random half of _batch_gen (unet_2d_summary.py:434-530): yields int32 [batch, 12] crop descriptors
-        {dataset, y0, x0, valid rows, valid cols, m00, m01, m10, m11, t0, t1, 0} drawing from the global numpy RNG in
-        exactly the order _batch_gen does, so both produce the same crops from the same seed."""
+        """The random half of the reference's _batch_gen (unet_2d_summary.py:434-530): yields int32 [batch, 12] crop
+        descriptors {dataset, y0, x0, valid rows, valid cols, m00, m01, m10, m11, t0, t1, 0} drawing from the global numpy
+        RNG in exactly the order the reference does (dataset, neuron, row jitter, column jitter, augmentation count,
+        augmentation picks), so the same seed gives the same crops (tests/test_sampler.py against oracle/sampler.py)."""
         rng = np.random
         hw, ww = window_shape
         assert hw == ww, 'the flips / rotations are composed on a square window'
@@ -428,7 +384,7 @@ class UNet2DSummary(object):
 
     @staticmethod
     def _apply_descriptors_host(S_summ, M_summ, desc, n):
-        """numpy statement of dcb_crop_batch (used by the CPU tests to pin the descriptors against _batch_gen)"""
+        """numpy statement of dcb_crop_batch (used by the CPU tests to pin the descriptors against the host sampler of oracle/)"""
         B = desc.shape[0]
         xs = np.zeros((B, n, n), np.float32); ys = np.zeros((B, n, n), np.uint8)
         ii, jj = np.meshgrid(np.arange(n), np.arange(n), indexing='ij')
@@ -440,10 +396,11 @@ class UNet2DSummary(object):
             ys[b][ok] = M_summ[ds][y0 + wi[ok], x0 + wj[ok]]
         return xs, ys
 
-    def _batch_gen_device(self, S_summ, M_summ, names, y_coords, batch_size, nb_steps, window_shape,
-                          nb_max_augment=0, scores_path=None, device=None):
-        """_batch_gen with the pixel work on the GPU (dcb_crop_batch): yields (x, y) CUDA tensors.  The summary images
-        and masks are uploaded once; per batch only the [batch, 12] int32 descriptors cross PCIe."""
+    def _batch_gen(self, S_summ, M_summ, names, y_coords, batch_size, nb_steps, window_shape,
+                   nb_max_augment=0, scores_path=None, device=None):
+        """The reference's crop sampler (unet_2d_summary.py:434-530) with the pixel work on the GPU (dcb_crop_batch):
+        yields (x, y) CUDA tensors.  The summary images and masks are uploaded once; per batch only the [batch, 12]
+        int32 descriptors cross PCIe."""
         import torch
         from ...engine import ops
         dev = device if device is not None else torch.device('cuda', torch.cuda.current_device())

@@ -36,7 +36,9 @@ enum dcb_status {
   DCB_ERR_UNSUPPORTED = -4
 };
 
-enum dcb_dtype { DCB_F32 = 0, DCB_BF16 = 1 };
+/* DCB_F16: fp16 activations and weights on the same tcgen05 kind::f16 MMA (same rate as bf16, 10 mantissa bits): inference
+ * only - the forward entry points, pooling, upsampling and the head accept it; the gradient entry points do not */
+enum dcb_dtype { DCB_F32 = 0, DCB_BF16 = 1, DCB_F16 = 2 };
 
 /* loss ids: unet_2d_summary.py:372-377 */
 enum dcb_loss { DCB_LOSS_BCE = 0, DCB_LOSS_WBCE = 1, DCB_LOSS_DICE = 2, DCB_LOSS_DICESQ = 3 };
@@ -45,6 +47,28 @@ int dcb_version(void);
 const char* dcb_last_error(void);
 /* number of kernels this library has launched from the calling process (bench.py's gpu_launches) */
 unsigned long long dcb_launch_count(void);
+
+/* Dispatch policy of the contraction kernels.  Process-wide, read at every call (nothing is cached, no environment
+ * variables): tests and sweeps pin a kernel variant with dcb_set_policy(), run, and dcb_reset_policy().  Defaults are the
+ * measured choices (profiles/).  dcb_last_kernel() names the variant the calling thread's last contraction call used,
+ * e.g. "strip_fold", "strip", "strip_swap", "flat", "generic", "generic_swap", "wgrad", "wgrad_strip". */
+enum dcb_policy_key {
+  DCB_POLICY_FLAT = 0,          /* flat halo-tile conv kernel: 0 never, 1 auto (size gate), 2 whenever the shape is eligible */
+  DCB_POLICY_STRIP = 1,         /* halo-strip conv kernel: 0 off, 1 on */
+  DCB_POLICY_FOLD = 2,          /* vertical-tap folding inside the strip kernel: 0 off, 1 on */
+  DCB_POLICY_NSPLIT = 3,        /* channel-split strip launches when the weights do not fit: 0 off, 1 on */
+  DCB_POLICY_SWAP_MIN_COUT = 4, /* smallest Cout that uses the weights-as-A orientation (0 = never) */
+  DCB_POLICY_WGRAD_STRIP = 5,   /* strip weight-gradient kernel: 0 off, 1 on */
+  DCB_POLICY_BN_CTAS_PER_SM = 6,
+  DCB_POLICY_PROJ_I16_SPLITS = 7, /* T splits of the int16 projection (0 = heuristic) */
+  DCB_POLICY_SPLITK = 8,        /* split-K of the generic conv kernel for small pixel counts: 0 off, 1 auto */
+  DCB_POLICY_FUSED_BN = 9,      /* training BatchNorm: 1 = single-launch kernels with a grid barrier, 0 = separate passes */
+  DCB_POLICY_COUNT = 10
+};
+int dcb_set_policy(int key, int value);
+int dcb_get_policy(int key, int* value);
+int dcb_reset_policy(void);
+const char* dcb_last_kernel(void);
 
 /* ---- a1: datasets/nf.py:115-130 (twin: examples/neurons/unet2ds_sj.py:67-85) ----
  * Per-pixel temporal mean and max of movie[T][H][W] (float32).  mean/max are
@@ -69,6 +93,10 @@ int dcb_proj_mean_max_i16(const short* movie, int T, int H, int W, float* mean, 
 int dcb_proj_accum_i16(const short* chunk, int Tc, int H, int W, long long* sum, int* mx, dcb_stream_t stream);
 int dcb_proj_accum_finalize(const long long* sum, const int* mx, int T, int H, int W, float* mean, float* max_out,
                             int floor_max_at_zero, dcb_stream_t stream);
+/* same, for frames that were shifted by -bias before accumulation (unsigned 16-bit TIFF pixels, bias = 32768: the reference
+ * computes mean / max from the unwrapped values, datasets/nf.py:129-130); the bias is restored in exact integer arithmetic */
+int dcb_proj_accum_finalize_biased(const long long* sum, const int* mx, int T, int H, int W, int bias, float* mean,
+                                   float* max_out, int floor_max_at_zero, dcb_stream_t stream);
 /* ---- a2: unet_2d_summary.py:238-239 (_summarize_series) ----
  * out = (in - mean(in)) / std(in), population std, n = H*W elements.
  * stats (optional, 2 doubles on device) receives mean and std. */

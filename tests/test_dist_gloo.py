@@ -71,6 +71,23 @@ def _worker(rank, world, port, q):
         dgamma_local = local[0] / world                             # what bn_bwd_apply writes with dgb_scale = 1/world
         comm.allreduce_sum(dgamma_local)                            # the flat-gradient all-reduce
         assert np.allclose(dgamma_local.numpy(), x_all.sum(0))
+        # --- projection of one movie split into row bands: band projection + all_gather == full projection
+        import oracle
+        from deepcalcium.engine.dist import summarize_movie_sharded
+        movie = (np.random.default_rng(5).random((13, 21, 16)) * 4096).astype(np.float32)      # 21 rows: uneven bands
+
+        def cpu_project(band, floor):                               # stand-in for the CUDA kernel in this CPU test
+            m, x = oracle.project_mean_max(band.numpy(), floor_max_at_zero=floor)
+            return torch.from_numpy(m), torch.from_numpy(x)
+        fr, nr = shard_range(21, world, rank)
+        mean, mx = summarize_movie_sharded(torch.from_numpy(movie[:, fr:fr + nr].copy()), comm, 21, project_fn=cpu_project)
+        omean, omx = oracle.project_mean_max(movie)
+        assert np.array_equal(mean.numpy(), omean) and np.array_equal(mx.numpy(), omx)
+        try:
+            summarize_movie_sharded(torch.from_numpy(movie[:, :3].copy()), comm, 21, project_fn=cpu_project)
+            raise AssertionError('a band of the wrong height must be rejected')
+        except ValueError:
+            pass
         t = torch.full((3,), float(rank + 1))
         comm.broadcast(t)
         assert torch.all(t == 1.0)

@@ -34,8 +34,19 @@ def nhwc_to_nchw(a):
     return torch.as_tensor(a).permute(0, 3, 1, 2).contiguous()
 
 
-# the flat halo-tile kernel is selected by a problem-size policy; the unit tests force it on for the eligible shapes
-os.environ.setdefault('DCB_FLAT_ALWAYS', '1')
+# Dispatch variants of the bf16 contraction kernels, pinned per call with dcb_set_policy (deepcalcium._native.policy):
+# every conv case runs under the DEFAULT policy (what bench.py and smoke() time) and under each forced variant; a
+# variant a shape is not eligible for falls through to the next kernel of the dispatch chain, which is checked as well.
+FWD_VARIANTS = [
+    ('default', {}),
+    ('generic', dict(strip=0, flat=0, swap_min_cout=0)),          # pixels-as-M generic kernel
+    ('generic_swap', dict(strip=0, flat=0)),                      # weights-as-M generic kernel where 64 <= Cout <= 128
+    ('flat', dict(strip=0, flat=2)),                              # flat halo-tile kernel wherever the shape is eligible
+    ('strip_nofold', dict(fold=0)),                               # strip kernel, plain / swapped issue
+    ('strip_plain', dict(fold=0, swap_min_cout=0)),               # strip kernel, pixels-as-M, 9 taps issued separately
+    ('strip_no_nsplit', dict(nsplit=0)),
+]
+WGRAD_VARIANTS = [('default', {}), ('generic', dict(wgrad_strip=0))]
 
 CONV_CASES = [
     # N, H, W, C0, C1, Cout
@@ -84,29 +95,72 @@ def test_conv3x3_fwd_dgrad_wgrad(cuda, precision, case):
     conv = F.conv2d(xt, wt.permute(3, 2, 0, 1), padding=1)
     ref = torch.relu(conv * torch.tensor(scale, dtype=torch.float64)[None, :, None, None]
                      + torch.tensor(shift, dtype=torch.float64)[None, :, None, None])
-    # forward (+ concat + epilogue)
+    from deepcalcium import _native as nat
     x0 = dev(x[..., :C0], dt)
     x1 = dev(x[..., C0:], dt) if C1 else None
     wm = dev(w)
     wf = torch.empty(9 * Cin * Cout, dtype=dt, device='cuda')
     wd = torch.empty(9 * Cin * Cout, dtype=dt, device='cuda')
     ops.prep_conv3x3_weights(wm, wf, wd, dt)
-    out = torch.empty(N, H, W, Cout, dtype=dt, device='cuda')
-    ops.conv3x3_fwd(x0, x1, wf, out, dev(scale), dev(shift), True)
-    got = out.float().cpu().permute(0, 3, 1, 2).double()
-    assert torch.max(torch.abs(got - ref)).item() < tol(precision, 1 + ref.abs().max().item())
-    # plain conv (no epilogue), dgrad and wgrad against autograd
     dy = q(rng.standard_normal((N, H, W, Cout)), precision)
     conv.backward(nhwc_to_nchw(dy))
-    dx = torch.empty(N, H, W, Cin, dtype=torch.float32, device='cuda')       # gradients are fp32 in both modes
-    ops.conv3x3_dgrad(dev(dy, dt), wd, dx)
-    gx = dx.float().cpu().permute(0, 3, 1, 2).double()
-    assert torch.max(torch.abs(gx - xt.grad)).item() < tol(precision, 1 + xt.grad.abs().max().item())
-    dW = torch.empty(3, 3, Cin, Cout, dtype=torch.float32, device='cuda')
-    ws = torch.empty(max(16, ops.conv3x3_wgrad_workspace_bytes(dt, N, H, W, Cin, Cout)), dtype=torch.uint8, device='cuda')
-    ops.conv3x3_wgrad(x0, x1, dev(dy, dt), dW, ws)
-    gw = dW.cpu().double()
-    assert torch.max(torch.abs(gw - wt.grad)).item() < tol(precision, 1 + wt.grad.abs().max().item())
+    dyd = dev(dy, dt)
+    seen = {}
+    for vname, pol in (FWD_VARIANTS if precision == 'bf16' else FWD_VARIANTS[:1]):
+        with nat.policy(**pol):
+            # forward (+ concat + epilogue)
+            out = torch.empty(N, H, W, Cout, dtype=dt, device='cuda')
+            ops.conv3x3_fwd(x0, x1, wf, out, dev(scale), dev(shift), True)
+            kf = nat.last_kernel()
+            got = out.float().cpu().permute(0, 3, 1, 2).double()
+            assert torch.max(torch.abs(got - ref)).item() < tol(precision, 1 + ref.abs().max().item()), (vname, kf)
+            # plain conv (no epilogue): dgrad against autograd; gradients are fp32 in both modes
+            dx = torch.empty(N, H, W, Cin, dtype=torch.float32, device='cuda')
+            ops.conv3x3_dgrad(dyd, wd, dx)
+            kd = nat.last_kernel()
+            gx = dx.float().cpu().permute(0, 3, 1, 2).double()
+            assert torch.max(torch.abs(gx - xt.grad)).item() < tol(precision, 1 + xt.grad.abs().max().item()), (vname, kd)
+            seen[vname] = (kf, kd)
+    if precision == 'bf16':
+        assert seen['generic'][0] == 'generic' and seen['generic_swap'][0] in ('generic', 'generic_swap')
+        print('conv %s kernels: %s' % (case, seen))
+    for vname, pol in (WGRAD_VARIANTS if precision == 'bf16' else WGRAD_VARIANTS[:1]):
+        with nat.policy(**pol):
+            dW = torch.empty(3, 3, Cin, Cout, dtype=torch.float32, device='cuda')
+            ws = torch.empty(max(16, ops.conv3x3_wgrad_workspace_bytes(dt, N, H, W, Cin, Cout)), dtype=torch.uint8, device='cuda')
+            ops.conv3x3_wgrad(x0, x1, dyd, dW, ws)
+            gw = dW.cpu().double()
+            assert torch.max(torch.abs(gw - wt.grad)).item() < tol(precision, 1 + wt.grad.abs().max().item()), (vname, nat.last_kernel())
+
+
+def test_policy_roundtrip_and_kernel_names(cuda):
+    """dcb_set_policy / dcb_get_policy / dcb_reset_policy and dcb_last_kernel: the variant actually launched is
+    observable, so a test can tell which kernel it has verified."""
+    from deepcalcium import _native as nat
+    from deepcalcium.engine import ops
+    nat.reset_policy()
+    assert nat.get_policy('flat') == 1 and nat.get_policy('swap_min_cout') == 64
+    with nat.policy(flat=2, strip=0):
+        assert nat.get_policy('flat') == 2 and nat.get_policy('strip') == 0
+    assert nat.get_policy('flat') == 1 and nat.get_policy('strip') == 1
+    dt = torch.bfloat16
+
+    def run(N, H, W, Cin, Cout):
+        x = torch.zeros(N, H, W, Cin, dtype=dt, device='cuda')
+        wf = torch.zeros(9 * Cin * Cout, dtype=dt, device='cuda')
+        out = torch.empty(N, H, W, Cout, dtype=dt, device='cuda')
+        ops.conv3x3_fwd(x, None, wf, out, None, None, False)
+        return nat.last_kernel()
+    assert run(1, 8, 128, 32, 32) == 'strip_fold'
+    with nat.policy(fold=0):
+        assert run(1, 4, 256, 64, 64) == 'strip_swap'
+    with nat.policy(fold=0, swap_min_cout=0):
+        assert run(1, 8, 128, 32, 32) == 'strip'
+    with nat.policy(strip=0):
+        assert run(1, 8, 128, 32, 32) == 'generic'
+    with nat.policy(flat=2):
+        assert run(2, 32, 32, 64, 64) == 'flat'
+    assert run(2, 32, 32, 64, 64) in ('generic', 'generic_swap')          # too few work items for the flat kernel
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])

@@ -151,3 +151,12 @@ def test_streaming_tiff_ingest(cuda, tmp_path):
     assert np.allclose(np.asarray(ds['series/mean'], dtype=np.float32), mean, rtol=1e-3)       # stored as float16
     mm = np.asarray(ds['masks/max'])
     assert mm.sum() == 5 and mm[2, 3] == 1 and mm[11, 20] == 1
+    # unsigned 16-bit pixels above 32767 (saturated neurofinder frames) must not wrap: the reference computes the mean and
+    # the max from the unwrapped values (nf.py:129-130); series/max saturates when stored as int16
+    big = rng.integers(0, 65536, size=(9, H, W)).astype(np.uint16)
+    (tmp_path / 'u16').mkdir()
+    for t in range(9):
+        Image.fromarray(big[t]).save(str(tmp_path / 'u16' / ('image%05d.tiff' % t)))
+    mean, mx, n = summarize_tiff_dir(str(tmp_path / 'u16'), chunk=4)
+    assert np.array_equal(mx, big.max(axis=0).astype(np.float32))
+    assert np.array_equal(mean, (big.astype(np.int64).sum(axis=0) / np.float64(9)).astype(np.float32))
