@@ -1,0 +1,533 @@
+// Training-mode BatchNorm of the UNet2DS blocks (Keras 2.0.6 BatchNormalization, unet_2d_summary.py:157,165) as
+// SINGLE-LAUNCH kernels: batch statistics are a grid-wide dependency, so the separate-pass version costs four launches
+// per layer (stats, finalize+apply, backward reduce, backward apply: 88 launches and ~40 % of a 32-crop training step).
+// Here one persistent kernel does   reduce -> grid barrier -> fixed-order cross-CTA sum -> grid barrier -> apply,
+// re-reading in the second phase what the first phase just pulled through L2 (every tensor of a 128^2 x 32 step is
+// smaller than the 126 MB L2).  The cross-CTA sum is a fixed-order tree (per-CTA partials in a workspace, each value
+// summed by one warp in a fixed pattern), so results are bit-reproducible run to run - no floating-point atomics.
+//
+// Data-parallel training (SyncBN): with `peers` set, the per-channel totals of every rank are exchanged
+// INSIDE the kernel over NVLink - each rank stores its totals into every peer's exchange slot (peer-mapped memory),
+// publishes a flag carrying the step number, waits for the peers' flags and adds the slots in rank order - instead of
+// an NCCL all-reduce between two launches.
+#include "elementwise.cuh"
+
+namespace dcb {
+extern unsigned long long g_launches;
+
+struct PeerView {
+  int world, rank;
+  double* xchg[8];              // peer p's exchange area (peer-mapped): [slot][rank][2 * C] doubles
+  unsigned long long* flags[8]; // peer p's flag area: [slot][rank]
+  long long slot_doubles;       // offset of this call's slot inside the exchange area, in doubles
+  int slot_flag;                // index of this call's slot inside the flag area (x 8 ranks)
+  const unsigned long long* epoch;   // device counter that differs between consecutive steps (dcb_step_advance state)
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// All CTAs of the grid are co-resident (the host sizes the grid from the occupancy query).  `counter` starts at 0
+// (the caller zeroes the sync words before the launch).  A protocol failure traps after ~2 s instead of hanging.
+__device__ __forceinline__ void grid_barrier(unsigned* counter) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const long long t0 = clock64();
+    while (ld_acquire_u32(counter) < gridDim.x) {
+      __nanosleep(64);
+      if (clock64() - t0 > 4000000000LL) __trap();
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// partial[cta][V] (double) -> totals[V]: value u is summed by warp (u % 8) of CTA (u / 8 % grid) - lanes take every
+// 32nd CTA's partial, then a shuffle tree - a fixed pattern, so the sum does not depend on scheduling
+__device__ __forceinline__ void reduce_partials(const double* __restrict__ partial, int V, double* __restrict__ totals) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int u = blockIdx.x * nwarps + warp; u < V; u += gridDim.x * nwarps) {
+    double acc = 0;
+    for (int g = lane; g < (int)gridDim.x; g += 32) acc += __ldcg(partial + (size_t)g * V + u);
+    acc = warp_sum(acc);
+    if (lane == 0) totals[u] = acc;
+  }
+}
+
+// SyncBN exchange of the V local totals (see the file comment).  Returns with s_tot[0..V) = sum over ranks.
+__device__ __forceinline__ void peer_exchange(const PeerView& pv, const double* __restrict__ totals, int V, double* s_tot) {
+  const unsigned long long epoch = *pv.epoch;
+  if (blockIdx.x == 0) {
+    for (int p = 0; p < pv.world; ++p) {
+      double* dst = pv.xchg[p] + pv.slot_doubles + (long long)pv.rank * V;
+      for (int i = threadIdx.x; i < V; i += blockDim.x) dst[i] = totals[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < pv.world) st_release_sys_u64(pv.flags[threadIdx.x] + pv.slot_flag * 8 + pv.rank, epoch);
+  }
+  if ((int)threadIdx.x < pv.world) {
+    const unsigned long long* f = pv.flags[pv.rank] + pv.slot_flag * 8 + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u64(f) != epoch) {
+      __nanosleep(128);
+      if (clock64() - t0 > 20000000000LL) __trap();
+    }
+  }
+  __syncthreads();
+  const double* src = pv.xchg[pv.rank] + pv.slot_doubles;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    double acc = 0;
+    for (int r = 0; r < pv.world; ++r) acc += __ldcv(src + (long long)r * V + i);
+    s_tot[i] = acc;
+  }
+  __syncthreads();
+}
+
+struct BnFwdParams {
+  const void* x; void* y; void* pool;   // raw conv output [M][C], activation out, optional 2x2 max-pooled copy
+  long long M, M_total; int C;
+  int N, H, W;                          // pixel grid (pooling only)
+  const float* gamma; const float* beta; float eps, momentum;
+  float* moving_mean; float* moving_var; float* scale; float* shift; float* mean; float* rstd;
+  int relu; float p_drop; unsigned long long seed; const unsigned long long* seed_dev; unsigned layer;
+  double* partial; double* totals; unsigned* sync;
+  PeerView pv;
+};
+
+template <typename T, int VEC, bool POOL>
+__global__ void __launch_bounds__(256)
+bn_train_fwd_kernel(const BnFwdParams p) {
+  extern __shared__ double s_dyn[];
+  const int C = p.C, V = 2 * C;
+  const T* __restrict__ x = reinterpret_cast<const T*>(p.x);
+  const int lanes_c = C / VEC, rows_par = 256 / lanes_c;
+  const int tc = threadIdx.x % lanes_c, tr = threadIdx.x / lanes_c;
+  const long long rows_per_cta = (p.M + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  long long r1 = r0 + rows_per_cta; if (r1 > p.M) r1 = p.M;
+  // ---------------- phase 1: per-CTA partial sums of x and x^2
+  {
+    float s[VEC], q[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { s[i] = 0.f; q[i] = 0.f; }
+    const T* base = x + tc * VEC;
+    long long r = r0 + tr;
+    for (; r + 3LL * rows_par < r1; r += 4LL * rows_par) {
+      float v[4][VEC];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) loadv<T, VEC>(base + (r + (long long)u * rows_par) * C, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { s[i] += v[u][i]; q[i] = fmaf(v[u][i], v[u][i], q[i]); }
+    }
+    for (; r < r1; r += rows_par) {
+      float v[VEC];
+      loadv<T, VEC>(base + r * C, v);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { s[i] += v[i]; q[i] = fmaf(v[i], v[i], q[i]); }
+    }
+    float* sh = reinterpret_cast<float*>(s_dyn);      // 256 * 2 * VEC floats
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { sh[threadIdx.x * 2 * VEC + i] = s[i]; sh[threadIdx.x * 2 * VEC + VEC + i] = q[i]; }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < lanes_c * 2 * VEC; idx += 256) {
+      const int lc = idx / (2 * VEC), comp = idx % (2 * VEC);
+      double acc = 0;
+      for (int rr = 0; rr < rows_par; ++rr) acc += (double)sh[(rr * lanes_c + lc) * 2 * VEC + comp];
+      p.partial[(size_t)blockIdx.x * V + (comp / VEC) * C + lc * VEC + (comp % VEC)] = acc;
+    }
+  }
+  grid_barrier(p.sync + 0);
+  reduce_partials(p.partial, V, p.totals);
+  grid_barrier(p.sync + 1);
+  // ---------------- per-channel coefficients (every CTA; block 0 publishes them and updates the moving statistics)
+  double* s_tot = s_dyn;                               // V doubles
+  float* s_sc = reinterpret_cast<float*>(s_dyn + V); float* s_sh = s_sc + C;
+  if (p.pv.world > 1) {
+    peer_exchange(p.pv, p.totals, V, s_tot);
+  } else {
+    for (int i = threadIdx.x; i < V; i += blockDim.x) s_tot[i] = __ldcg(p.totals + i);
+    __syncthreads();
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double mean = s_tot[c] / (double)p.M_total;
+    double var = s_tot[C + c] / (double)p.M_total - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+    const float sc = p.gamma[c] * rstd;
+    const float shv = p.beta[c] - (float)mean * sc;
+    s_sc[c] = sc; s_sh[c] = shv;
+    if (blockIdx.x == 0) {
+      p.scale[c] = sc; p.shift[c] = shv; p.mean[c] = (float)mean; p.rstd[c] = rstd;
+      if (p.moving_mean) {   // Keras: moving <- moving*m + batch*(1-m), biased batch variance
+        p.moving_mean[c] = p.moving_mean[c] * p.momentum + (float)mean * (1.f - p.momentum);
+        p.moving_var[c] = p.moving_var[c] * p.momentum + (float)var * (1.f - p.momentum);
+      }
+    }
+  }
+  __syncthreads();
+  // ---------------- phase 2: y = relu(x * scale + shift) (* dropout keep mask) [, 2x2 max-pool]
+  unsigned long long seed = p.seed;
+  if (p.seed_dev) seed ^= *p.seed_dev;
+  T* __restrict__ y = reinterpret_cast<T*>(p.y);
+  auto apply = [&](long long i, float (&v)[VEC]) {      // i = index of the VEC-channel group in the flat tensor
+    const int c = (int)((i * VEC) % C);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      v[j] = fmaf(v[j], s_sc[c + j], s_sh[c + j]);
+      if (p.relu) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (p.p_drop > 0.f) {
+#pragma unroll
+      for (int h = 0; h < VEC / 4; ++h) {
+        const float4 k = dropout_scale4(seed, p.layer, (unsigned long long)(i * (VEC / 4) + h), p.p_drop);
+        v[4 * h] *= k.x; v[4 * h + 1] *= k.y; v[4 * h + 2] *= k.z; v[4 * h + 3] *= k.w;
+      }
+    }
+  };
+  if constexpr (!POOL) {
+    // the CTA re-reads its own rows (what phase 1 just pulled through L2)
+    const long long i0 = r0 * lanes_c, i1 = r1 * lanes_c;
+    long long i = i0 + threadIdx.x;
+    for (; i + 3 * 256 < i1; i += 4 * 256) {            // four independent 16-byte loads in flight per thread
+      float v[4][VEC];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) loadv<T, VEC>(x + (i + u * 256) * VEC, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        apply(i + u * 256, v[u]);
+        storev<T, VEC>(y + (i + u * 256) * VEC, v[u]);
+      }
+    }
+    for (; i < i1; i += 256) {
+      float v[VEC];
+      loadv<T, VEC>(x + i * VEC, v);
+      apply(i, v);
+      storev<T, VEC>(y + i * VEC, v);
+    }
+  } else {
+    T* __restrict__ pool = reinterpret_cast<T*>(p.pool);
+    const int OH = p.H / 2, OW = p.W / 2;
+    const long long nq = (long long)p.N * OH * OW * lanes_c;
+    for (long long qd = (long long)blockIdx.x * 256 + threadIdx.x; qd < nq; qd += (long long)gridDim.x * 256) {
+      long long t = qd;
+      const int lc = (int)(t % lanes_c); t /= lanes_c;
+      const int ow = (int)(t % OW); t /= OW;
+      const int oh = (int)(t % OH); const int n = (int)(t / OH);
+      const long long pix00 = ((long long)n * p.H + 2 * oh) * p.W + 2 * ow;
+      float m[VEC];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long pix = pix00 + (k >> 1) * p.W + (k & 1);
+        const long long i = pix * lanes_c + lc;
+        float v[VEC];
+        loadv<T, VEC>(x + i * VEC, v);
+        apply(i, v);
+        storev<T, VEC>(y + i * VEC, v);
+        // pooling compares the STORED (rounded) activations, like the standalone kernel that reads them back
+        float rv[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) rv[j] = to_f32<T>(from_f32<T>(v[j]));
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) m[j] = k == 0 ? rv[j] : fmaxf(m[j], rv[j]);
+      }
+      storev<T, VEC>(pool + qd * VEC, m);
+    }
+  }
+}
+
+struct BnBwdParams {
+  const float* dy; int ldy, offy;       // upstream gradient (fp32 view: row stride ldy, channel offset offy)
+  const void* x; void* draw;            // raw conv output [M][C]; gradient w.r.t. it (may alias x)
+  long long M, M_total; int C;
+  const float* scale; const float* shift; const float* mean; const float* rstd;
+  float p_drop; unsigned long long seed; const unsigned long long* seed_dev; unsigned layer;
+  float dgb_scale; float* dgamma; float* dbeta;
+  double* partial; double* totals; unsigned* sync;
+  PeerView pv;
+};
+
+// dz = dY * keepscale * [x*scale+shift > 0];  totals[c] = sum dz, totals[C+c] = sum dz * xhat;
+// d_raw = scale * (dz - mean(dz) - xhat * mean(dz*xhat)) = scale*dz + k1*(x - mean) + k0
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+bn_train_bwd_kernel(const BnBwdParams p) {
+  extern __shared__ double s_dyn[];
+  const int C = p.C, V = 2 * C;
+  const T* __restrict__ x = reinterpret_cast<const T*>(p.x);
+  unsigned long long seed = p.seed;
+  if (p.seed_dev) seed ^= *p.seed_dev;
+  const int lanes_c = C / VEC, rows_par = 256 / lanes_c;
+  const int tc = threadIdx.x % lanes_c, tr = threadIdx.x / lanes_c;
+  const long long rows_per_cta = (p.M + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  long long r1 = r0 + rows_per_cta; if (r1 > p.M) r1 = p.M;
+  const int c = tc * VEC;
+  float sc[VEC], sh[VEC], mu[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { sc[i] = p.scale[c + i]; sh[i] = p.shift[c + i]; mu[i] = p.mean[c + i]; }
+  auto masked = [&](long long r, float (&g)[VEC], const float (&v)[VEC]) {
+    if (p.p_drop > 0.f) {
+      const unsigned long long i4 = (unsigned long long)((r * C + c) >> 2);
+      const float4 k0 = dropout_scale4(seed, p.layer, i4, p.p_drop);
+      g[0] *= k0.x; g[1] *= k0.y; g[2] *= k0.z; g[3] *= k0.w;
+      if constexpr (VEC == 8) {
+        const float4 k1 = dropout_scale4(seed, p.layer, i4 + 1, p.p_drop);
+        g[4] *= k1.x; g[5] *= k1.y; g[6] *= k1.z; g[7] *= k1.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+      if (fmaf(v[i], sc[i], sh[i]) <= 0.f) g[i] = 0.f;
+  };
+  // ---------------- phase 1
+  {
+    float rs[VEC], s[VEC], q[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { rs[i] = p.rstd[c + i]; s[i] = 0.f; q[i] = 0.f; }
+    auto accumulate = [&](long long r, float (&g)[VEC], const float (&v)[VEC]) {
+      masked(r, g, v);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { s[i] += g[i]; q[i] = fmaf(g[i], (v[i] - mu[i]) * rs[i], q[i]); }
+    };
+    long long r = r0 + tr;
+    for (; r + rows_par < r1; r += 2LL * rows_par) {
+      float g0[VEC], g1[VEC], v0[VEC], v1[VEC];
+      loadv<float, VEC>(p.dy + r * p.ldy + p.offy + c, g0);
+      loadv<float, VEC>(p.dy + (r + rows_par) * p.ldy + p.offy + c, g1);
+      loadv<T, VEC>(x + r * C + c, v0);
+      loadv<T, VEC>(x + (r + rows_par) * C + c, v1);
+      accumulate(r, g0, v0);
+      accumulate(r + rows_par, g1, v1);
+    }
+    for (; r < r1; r += rows_par) {
+      float g0[VEC], v0[VEC];
+      loadv<float, VEC>(p.dy + r * p.ldy + p.offy + c, g0);
+      loadv<T, VEC>(x + r * C + c, v0);
+      accumulate(r, g0, v0);
+    }
+    float* shm = reinterpret_cast<float*>(s_dyn);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { shm[threadIdx.x * 2 * VEC + i] = s[i]; shm[threadIdx.x * 2 * VEC + VEC + i] = q[i]; }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < lanes_c * 2 * VEC; idx += 256) {
+      const int lc = idx / (2 * VEC), comp = idx % (2 * VEC);
+      double acc = 0;
+      for (int rr = 0; rr < rows_par; ++rr) acc += (double)shm[(rr * lanes_c + lc) * 2 * VEC + comp];
+      p.partial[(size_t)blockIdx.x * V + (comp / VEC) * C + lc * VEC + (comp % VEC)] = acc;
+    }
+  }
+  grid_barrier(p.sync + 0);
+  reduce_partials(p.partial, V, p.totals);
+  grid_barrier(p.sync + 1);
+  double* s_tot = s_dyn;
+  if (p.pv.world > 1) {
+    peer_exchange(p.pv, p.totals, V, s_tot);
+  } else {
+    for (int i = threadIdx.x; i < V; i += blockDim.x) s_tot[i] = __ldcg(p.totals + i);
+    __syncthreads();
+  }
+  // ---------------- phase 2: this thread's channels only (same row partition as phase 1)
+  float k1[VEC], k0[VEC];
+  {
+    const double invM = 1.0 / (double)p.M_total;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const double scd = (double)sc[i], m1 = s_tot[c + i] * invM, m2 = s_tot[C + c + i] * invM;
+      k1[i] = (float)(-scd * (double)p.rstd[c + i] * m2);
+      k0[i] = (float)(-scd * m1);
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
+      if (p.dbeta) p.dbeta[cc] = (float)(s_tot[cc] * (double)p.dgb_scale);
+      if (p.dgamma) p.dgamma[cc] = (float)(s_tot[C + cc] * (double)p.dgb_scale);
+    }
+  }
+  T* __restrict__ draw = reinterpret_cast<T*>(p.draw);
+  long long r = r0 + tr;
+  for (; r + rows_par < r1; r += 2LL * rows_par) {       // two rows (2 x 48 bytes of loads) in flight per thread
+    float g0[VEC], g1[VEC], v0[VEC], v1[VEC], o[VEC];
+    loadv<float, VEC>(p.dy + r * p.ldy + p.offy + c, g0);
+    loadv<float, VEC>(p.dy + (r + rows_par) * p.ldy + p.offy + c, g1);
+    loadv<T, VEC>(x + r * C + c, v0);
+    loadv<T, VEC>(x + (r + rows_par) * C + c, v1);
+    masked(r, g0, v0);
+    masked(r + rows_par, g1, v1);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) o[j] = fmaf(sc[j], g0[j], fmaf(k1[j], v0[j] - mu[j], k0[j]));
+    storev<T, VEC>(draw + r * C + c, o);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) o[j] = fmaf(sc[j], g1[j], fmaf(k1[j], v1[j] - mu[j], k0[j]));
+    storev<T, VEC>(draw + (r + rows_par) * C + c, o);
+  }
+  for (; r < r1; r += rows_par) {
+    float g[VEC], v[VEC], o[VEC];
+    loadv<float, VEC>(p.dy + r * p.ldy + p.offy + c, g);
+    loadv<T, VEC>(x + r * C + c, v);
+    masked(r, g, v);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) o[j] = fmaf(sc[j], g[j], fmaf(k1[j], v[j] - mu[j], k0[j]));
+    storev<T, VEC>(draw + r * C + c, o);
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------
+static int fused_vec(int C) { return (C % 8 == 0 && 256 % (C / 8) == 0) ? 8 : ((C % 4 == 0 && 256 % (C / 4) == 0) ? 4 : 0); }
+
+template <typename K>
+static int coresident_limit(K kernel, size_t dyn_smem) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, dyn_smem) != cudaSuccess || per_sm < 1) return 0;
+  return per_sm * sm_count();
+}
+
+static int fused_grid(long long M, int C, int vec, int limit) {
+  const int rows_par = 256 / (C / vec);
+  long long grid = (M + 4LL * rows_par - 1) / (4LL * rows_par);
+  const int per_sm = policy(DCB_POLICY_BN_CTAS_PER_SM) > 0 ? policy(DCB_POLICY_BN_CTAS_PER_SM) : 4;
+  if (grid > (long long)sm_count() * per_sm) grid = (long long)sm_count() * per_sm;
+  if (grid > limit) grid = limit;
+  return grid < 1 ? 1 : (int)grid;
+}
+
+static size_t fused_smem(int C, int vec) {
+  const size_t phase1 = 256 * 2 * (size_t)vec * sizeof(float);
+  const size_t phase2 = 2 * (size_t)C * sizeof(double) + 2 * (size_t)C * sizeof(float);
+  return phase1 > phase2 ? phase1 : phase2;
+}
+
+static int fill_peers(PeerView& pv, const dcb_peer_exchange_t* px, int C) {
+  memset(&pv, 0, sizeof(pv));
+  pv.world = 1;
+  if (!px || px->world <= 1) return DCB_OK;
+  if (px->world > 8 || px->rank < 0 || px->rank >= px->world || !px->epoch_dev)
+    return fail(DCB_ERR_INVALID_ARGUMENT, "peer exchange: bad world/rank (%d/%d) or missing epoch counter", px->world, px->rank);
+  if ((long long)px->world * 2 * C > px->slot_doubles)
+    return fail(DCB_ERR_INVALID_ARGUMENT, "peer exchange: slot of %lld doubles too small for %d ranks x %d values", px->slot_doubles, px->world, 2 * C);
+  pv.world = px->world; pv.rank = px->rank;
+  for (int i = 0; i < px->world; ++i) {
+    if (!px->xchg[i] || !px->flags[i]) return fail(DCB_ERR_INVALID_ARGUMENT, "peer exchange: missing pointer for rank %d", i);
+    pv.xchg[i] = reinterpret_cast<double*>(px->xchg[i]);
+    pv.flags[i] = reinterpret_cast<unsigned long long*>(px->flags[i]);
+  }
+  pv.slot_doubles = (long long)px->slot * px->slot_doubles;
+  pv.slot_flag = px->slot;
+  pv.epoch = px->epoch_dev;
+  return DCB_OK;
+}
+
+}  // namespace dcb
+
+using namespace dcb;
+
+extern "C" int dcb_bn_train_workspace_bytes(int C, size_t* bytes) {
+  DCB_CHECK_ARG(bytes && C > 0, "dcb_bn_train_workspace_bytes: bad arguments");
+  // partials of at most 8 CTAs per SM + the totals
+  *bytes = ((size_t)sm_count() * 8 + 1) * 2 * (size_t)C * sizeof(double);
+  return DCB_OK;
+}
+
+#define BN_DISPATCH(dtype, ...)                                                    \
+  if ((dtype) == DCB_F32) { using T = float; __VA_ARGS__ }                         \
+  else if ((dtype) == DCB_BF16) { using T = __nv_bfloat16; __VA_ARGS__ }           \
+  else return fail(DCB_ERR_INVALID_ARGUMENT, "training BatchNorm: dtype %d unsupported", (int)(dtype));
+
+template <typename T, int VEC, bool POOL>
+static int launch_bn_fwd(BnFwdParams& p, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const size_t smem = fused_smem(p.C, VEC);
+  static int limit = 0;          // per template instance
+  if (limit == 0) limit = coresident_limit(bn_train_fwd_kernel<T, VEC, POOL>, smem > 16384 ? smem : 16384);
+  if (limit <= 0) return fail(DCB_ERR_CUDA, "occupancy query failed for the fused BatchNorm kernel");
+  const int grid = fused_grid(p.M, p.C, VEC, limit);
+  const size_t need = ((size_t)grid + 1) * 2 * p.C * sizeof(double);
+  if (!ws || ws_bytes < need) return fail(DCB_ERR_WORKSPACE, "dcb_bn_train_fwd: workspace %zu B < required %zu B", ws_bytes, need);
+  p.partial = reinterpret_cast<double*>(ws);
+  p.totals = p.partial + (size_t)grid * 2 * p.C;
+  bn_train_fwd_kernel<T, VEC, POOL><<<grid, 256, smem, st>>>(p);
+  g_launches += 1;
+  DCB_LAUNCH_OK("bn_train_fwd_kernel");
+  return DCB_OK;
+}
+
+extern "C" int dcb_bn_train_fwd(int dtype, const void* x, long long M, int C, long long M_total, const float* gamma,
+                                const float* beta, float eps, float momentum, float* moving_mean, float* moving_var,
+                                float* scale, float* shift, float* mean, float* rstd, int relu, float p_drop,
+                                unsigned long long seed, const unsigned long long* seed_dev, unsigned layer, void* y,
+                                void* pool_out, int N, int H, int W, void* workspace, size_t workspace_bytes,
+                                unsigned int* sync, const dcb_peer_exchange_t* peers, dcb_stream_t stream) {
+  DCB_CHECK_ARG(x && y && gamma && beta && scale && shift && mean && rstd && sync && M > 0, "dcb_bn_train_fwd: bad arguments");
+  DCB_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "dcb_bn_train_fwd: p_drop %f outside [0, 1)", p_drop);
+  const int vec = fused_vec(C);
+  if (!vec || C > 1024) return fail(DCB_ERR_INVALID_ARGUMENT, "dcb_bn_train_fwd: channel count %d unsupported", C);
+  DCB_CHECK_ARG(!pool_out || (N > 0 && H % 2 == 0 && W % 2 == 0 && (long long)N * H * W == M), "dcb_bn_train_fwd: pooling needs N*H*W == M and even H, W");
+  BnFwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.y = y; p.pool = pool_out; p.M = M; p.M_total = M_total > 0 ? M_total : M; p.C = C; p.N = N; p.H = H; p.W = W;
+  p.gamma = gamma; p.beta = beta; p.eps = eps; p.momentum = momentum; p.moving_mean = moving_mean; p.moving_var = moving_var;
+  p.scale = scale; p.shift = shift; p.mean = mean; p.rstd = rstd; p.relu = relu; p.p_drop = p_drop; p.seed = seed;
+  p.seed_dev = seed_dev; p.layer = layer; p.sync = sync;
+  if (int e = fill_peers(p.pv, peers, C)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec == 8) {
+    if (pool_out) { BN_DISPATCH(dtype, return (launch_bn_fwd<T, 8, true>(p, workspace, workspace_bytes, st));) }
+    else { BN_DISPATCH(dtype, return (launch_bn_fwd<T, 8, false>(p, workspace, workspace_bytes, st));) }
+  } else {
+    if (pool_out) { BN_DISPATCH(dtype, return (launch_bn_fwd<T, 4, true>(p, workspace, workspace_bytes, st));) }
+    else { BN_DISPATCH(dtype, return (launch_bn_fwd<T, 4, false>(p, workspace, workspace_bytes, st));) }
+  }
+}
+
+template <typename T, int VEC>
+static int launch_bn_bwd(BnBwdParams& p, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const size_t smem = fused_smem(p.C, VEC);
+  static int limit = 0;
+  if (limit == 0) limit = coresident_limit(bn_train_bwd_kernel<T, VEC>, smem > 16384 ? smem : 16384);
+  if (limit <= 0) return fail(DCB_ERR_CUDA, "occupancy query failed for the fused BatchNorm backward kernel");
+  const int grid = fused_grid(p.M, p.C, VEC, limit);
+  const size_t need = ((size_t)grid + 1) * 2 * p.C * sizeof(double);
+  if (!ws || ws_bytes < need) return fail(DCB_ERR_WORKSPACE, "dcb_bn_train_bwd: workspace %zu B < required %zu B", ws_bytes, need);
+  p.partial = reinterpret_cast<double*>(ws);
+  p.totals = p.partial + (size_t)grid * 2 * p.C;
+  bn_train_bwd_kernel<T, VEC><<<grid, 256, smem, st>>>(p);
+  g_launches += 1;
+  DCB_LAUNCH_OK("bn_train_bwd_kernel");
+  return DCB_OK;
+}
+
+extern "C" int dcb_bn_train_bwd(int dtype, const float* dy, int ldy, int offy, const void* x, long long M, int C,
+                                long long M_total, const float* scale, const float* shift, const float* mean,
+                                const float* rstd, float p_drop, unsigned long long seed,
+                                const unsigned long long* seed_dev, unsigned layer, float dgb_scale, void* draw,
+                                float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, unsigned int* sync,
+                                const dcb_peer_exchange_t* peers, dcb_stream_t stream) {
+  DCB_CHECK_ARG(dy && x && scale && shift && mean && rstd && draw && sync && M > 0, "dcb_bn_train_bwd: bad arguments");
+  DCB_CHECK_ARG(ldy % 4 == 0 && offy % 4 == 0 && offy + C <= ldy, "dcb_bn_train_bwd: bad dy view (ld %d off %d C %d)", ldy, offy, C);
+  DCB_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0, "dcb_bn_train_bwd: pointers must be 16-byte aligned");
+  const int vec = fused_vec(C);
+  if (!vec || C > 1024) return fail(DCB_ERR_INVALID_ARGUMENT, "dcb_bn_train_bwd: channel count %d unsupported", C);
+  BnBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.dy = dy; p.ldy = ldy; p.offy = offy; p.x = x; p.draw = draw; p.M = M; p.M_total = M_total > 0 ? M_total : M; p.C = C;
+  p.scale = scale; p.shift = shift; p.mean = mean; p.rstd = rstd; p.p_drop = p_drop; p.seed = seed; p.seed_dev = seed_dev;
+  p.layer = layer; p.dgb_scale = dgb_scale; p.dgamma = dgamma; p.dbeta = dbeta; p.sync = sync;
+  if (int e = fill_peers(p.pv, peers, C)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec == 8) { BN_DISPATCH(dtype, return (launch_bn_bwd<T, 8>(p, workspace, workspace_bytes, st));) }
+  else { BN_DISPATCH(dtype, return (launch_bn_bwd<T, 4>(p, workspace, workspace_bytes, st));) }
+}

@@ -229,6 +229,52 @@ def bn_bwd_apply(dy, ldy, offy, x, scale, shift, mean, rstd, sums, draw, dgamma,
          ptr(sums), c_ll(M_total), c_f(dgb_scale), ptr(draw), ptr(dgamma), ptr(dbeta), stream_ptr())
 
 
+class PeerExchange(ctypes.Structure):
+    """dcb_peer_exchange_t"""
+    _fields_ = [('world', c_int), ('rank', c_int), ('xchg', c_p * 8), ('flags', c_p * 8), ('slot_doubles', c_ll),
+                ('slot', c_int), ('epoch_dev', c_p)]
+
+
+def _peers_arg(peers, slot):
+    if peers is None:
+        return None
+    px = PeerExchange()
+    px.world, px.rank = peers['world'], peers['rank']
+    for i in range(peers['world']):
+        px.xchg[i] = peers['xchg'][i]
+        px.flags[i] = peers['flags'][i]
+    px.slot_doubles = peers['slot_doubles']
+    px.slot = slot
+    px.epoch_dev = peers['epoch_dev']
+    return ctypes.byref(px)
+
+
+def bn_train_workspace_bytes(C):
+    out = c_sz(0)
+    call('dcb_bn_train_workspace_bytes', c_int(C), ctypes.byref(out))
+    return out.value
+
+
+def bn_train_fwd(x, gamma, beta, momentum, moving_mean, moving_var, scale, shift, mean, rstd, y, workspace, sync,
+                 relu=True, p_drop=0., seed=0, seed_dev=None, layer=0, pool_out=None, M_total=0, eps=1e-3, peers=None, slot=0):
+    """single-launch training BatchNorm forward (+ReLU, dropout, optional 2x2 max-pool); sync: 4 zeroed int32 words"""
+    C = x.shape[-1]
+    N, H, W = (x.shape[0], x.shape[1], x.shape[2]) if x.dim() == 4 else (0, 0, 0)
+    call('dcb_bn_train_fwd', _dt(x), ptr(x), c_ll(x.numel() // C), c_int(C), c_ll(M_total), ptr(gamma), ptr(beta), c_f(eps),
+         c_f(momentum), ptr(moving_mean), ptr(moving_var), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), c_int(int(relu)),
+         c_f(p_drop), c_ull(seed), ptr(seed_dev), c_uint(layer), ptr(y), ptr(pool_out), c_int(N), c_int(H), c_int(W),
+         ptr(workspace), c_sz(workspace.numel() * workspace.element_size()), ptr(sync), _peers_arg(peers, slot), stream_ptr())
+
+
+def bn_train_bwd(dy, ldy, offy, x, scale, shift, mean, rstd, draw, dgamma, dbeta, workspace, sync, p_drop=0., seed=0,
+                 seed_dev=None, layer=0, M_total=0, dgb_scale=1.0, peers=None, slot=0):
+    C = x.shape[-1]
+    call('dcb_bn_train_bwd', _dt(x), ptr(dy), c_int(ldy), c_int(offy), ptr(x), c_ll(x.numel() // C), c_int(C), c_ll(M_total),
+         ptr(scale), ptr(shift), ptr(mean), ptr(rstd), c_f(p_drop), c_ull(seed), ptr(seed_dev), c_uint(layer), c_f(dgb_scale),
+         ptr(draw), ptr(dgamma), ptr(dbeta), ptr(workspace), c_sz(workspace.numel() * workspace.element_size()), ptr(sync),
+         _peers_arg(peers, slot), stream_ptr())
+
+
 # ---------------------------------------------------------------- pooling
 def crop_batch(img_ptrs, mask_ptrs, widths, desc, window, x_out, y_out):
     """tables: int64 [D], int64 [D], int32 [D]; desc int32 [B, 12]; x_out fp32 [B, n, n]; y_out uint8 [B, n, n]"""

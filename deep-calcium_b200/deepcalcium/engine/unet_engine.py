@@ -60,6 +60,8 @@ class UNetEngine(object):
         self.iteration = 0
         self.launches = 0
         self.comm = None          # engine.dist.Comm for data-parallel training (None = single GPU)
+        self.overlap_wgrad = True  # weight-gradient launches on a side stream (see _train_step_enqueue)
+        self._side = None
         self.set_weights_dict(he_normal_weights(self.spec, seed=0))
 
     # ------------------------------------------------------------------ parameter storage
@@ -131,6 +133,12 @@ class UNetEngine(object):
         self._off_head_dwb = n_dbl + 8
         n_dbl += 8 + 2 * self.spec.nfb + 2
         self.dbl = torch.zeros(n_dbl, dtype=torch.float64, device=self.dev)
+        # single-launch BatchNorm kernels (dcb_bn_train_fwd / _bwd): 4 barrier words per (layer, direction), zeroed at the
+        # start of every step, and one shared workspace for the per-CTA partial sums
+        self.bn_sync = torch.zeros(8 * len(self.spec.blocks), dtype=torch.int32, device=self.dev)
+        self.bn_ws = torch.empty(ops.bn_train_workspace_bytes(max(b.cout for b in self.spec.blocks)), dtype=torch.uint8,
+                                 device=self.dev)
+        self.peers = None         # dcb_peer_exchange description for in-kernel SyncBN (engine.dist.attach_peers)
         self.metrics = torch.zeros(8, **f32)
 
     def _wire(self):
@@ -373,6 +381,11 @@ class UNetEngine(object):
         return st['mask'], st['act']
 
     # ------------------------------------------------------------------ training
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        return self._side
+
     def _dropout_p(self, name, enabled):
         return float(self.spec.dropout_after().get(name, 0.)) if enabled else 0.
 
@@ -388,6 +401,11 @@ class UNetEngine(object):
         seed_dev = self.step_state[1:2]
         ops.step_advance(self.step_state, lr, beta1, beta2, self.lr_t)
         self.dbl.zero_()
+        # fused single-launch BatchNorm unless the policy says otherwise; a data-parallel run needs the peer-mapped
+        # exchange buffers for it (otherwise: separate passes with NCCL all-reduces of the sums in between)
+        fused_bn = bool(nat.get_policy('fused_bn')) and (world == 1 or self.peers is not None)
+        if fused_bn:
+            self.bn_sync.zero_()
         self._prepare_weights(for_training=True)
         layer_id = {blk.name: i for i, blk in enumerate(spec.blocks)}
         for i, un in enumerate(self._ups):
@@ -412,14 +430,24 @@ class UNetEngine(object):
                 mom = BN_MOMENTUM_UP
             st = self.bn[n]
             M = raw[n].numel() // blk.cout
+            pooled = act['pool%d' % blk.level] if n in ('enc0b', 'enc1b', 'enc2b', 'enc3b') else None
+            if fused_bn:
+                # statistics + normalise + ReLU + dropout (+ the 2x2 max-pool of the encoder blocks) in ONE launch; in
+                # data-parallel runs the per-channel sums of all ranks are exchanged inside the kernel (SyncBN over NVLink)
+                li = layer_id[n]
+                ops.bn_train_fwd(raw[n], self.P[n + '/gamma'], self.P[n + '/beta'], mom, self.P[n + '/moving_mean'],
+                                 self.P[n + '/moving_var'], st['scale'], st['shift'], st['mean'], st['rstd'], act[n], self.bn_ws,
+                                 self.bn_sync[8 * li:8 * li + 4], True, self._dropout_p(n, dropout), seed_base, seed_dev, li,
+                                 pool_out=pooled, M_total=M * world, eps=BN_EPS, peers=self.peers, slot=2 * li)
+                continue
             sums = self.dbl[st['off_f']:st['off_f'] + 2 * blk.cout]
             ops.bn_stats(raw[n], sums)
             self._allreduce(sums)                       # SyncBN: statistics of the global batch
             ops.bn_finalize_apply(raw[n], sums, M * world, self.P[n + '/gamma'], self.P[n + '/beta'], mom,
                                   self.P[n + '/moving_mean'], self.P[n + '/moving_var'], st['scale'], st['shift'], st['mean'],
                                   st['rstd'], act[n], True, self._dropout_p(n, dropout), seed_base, seed_dev, layer_id[n], BN_EPS)
-            if n in ('enc0b', 'enc1b', 'enc2b', 'enc3b'):
-                ops.maxpool2x2(act[n], act['pool%d' % blk.level])
+            if pooled is not None:
+                ops.maxpool2x2(act[n], pooled)
         # ---------------- head + loss + its gradient
         hs = self.dbl[self._off_head_sums:self._off_head_sums + 8]
         hd = self.dbl[self._off_head_dwb:self._off_head_dwb + 2 * spec.nfb + 2]
@@ -432,6 +460,22 @@ class UNetEngine(object):
         ops.head_loss_bwd(act['dec0b'], self.P['head/kernel'], s['y'], s['prob'], hs, loss_id, s['dhead'], hd, dw_out,
                           self.metrics, M_total=s['prob'].numel() * world)
         # ---------------- backward
+        # Weight gradients are off the critical path: layer L's wgrad needs only d_raw(L) and the saved input, and nothing
+        # before the optimizer reads its result, while the chain BN-bwd(L) -> dgrad(L) -> BN-bwd(L-1) ... is strictly
+        # sequential.  The wgrad launches therefore go to a side stream (forked / joined with events, so the whole step
+        # is still one CUDA graph) and overlap with the memory-bound BatchNorm / pooling kernels of the main chain.
+        main = torch.cuda.current_stream(self.dev)
+        side = self._side_stream() if self.overlap_wgrad else None
+
+        def on_wgrad_stream(fn, *args):
+            if side is None:
+                return fn(*args)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                fn(*args)
+
         grad_of = {'dec0b': (s['dhead'], spec.nfb, 0)}
         skip_grad = {}
         for blk in reversed(spec.blocks):
@@ -443,18 +487,25 @@ class UNetEngine(object):
             st = self.bn[n]
             sums = self.dbl[st['off_b']:st['off_b'] + 2 * blk.cout]
             p = self._dropout_p(n, dropout)
-            ops.bn_bwd_reduce(dy, ldy, offy, raw[n], st['scale'], st['shift'], st['mean'], st['rstd'], sums, p, seed_base,
-                              seed_dev, layer_id[n])
-            self._allreduce(sums)
             draw = raw[n]      # in place: raw is dead after this point
-            ops.bn_bwd_apply(dy, ldy, offy, raw[n], st['scale'], st['shift'], st['mean'], st['rstd'], sums, draw,
-                             self.G[n + '/gamma'], self.G[n + '/beta'], p, seed_base, seed_dev, layer_id[n],
-                             M_total=(raw[n].numel() // blk.cout) * world, dgb_scale=1.0 / world)
+            if fused_bn:
+                li = layer_id[n]
+                ops.bn_train_bwd(dy, ldy, offy, raw[n], st['scale'], st['shift'], st['mean'], st['rstd'], draw,
+                                 self.G[n + '/gamma'], self.G[n + '/beta'], self.bn_ws, self.bn_sync[8 * li + 4:8 * li + 8], p,
+                                 seed_base, seed_dev, li, M_total=(raw[n].numel() // blk.cout) * world, dgb_scale=1.0 / world,
+                                 peers=self.peers, slot=2 * li + 1)
+            else:
+                ops.bn_bwd_reduce(dy, ldy, offy, raw[n], st['scale'], st['shift'], st['mean'], st['rstd'], sums, p, seed_base,
+                                  seed_dev, layer_id[n])
+                self._allreduce(sums)
+                ops.bn_bwd_apply(dy, ldy, offy, raw[n], st['scale'], st['shift'], st['mean'], st['rstd'], sums, draw,
+                                 self.G[n + '/gamma'], self.G[n + '/beta'], p, seed_base, seed_dev, layer_id[n],
+                                 M_total=(raw[n].numel() // blk.cout) * world, dgb_scale=1.0 / world)
             if blk.kind == 'conv':
                 if blk.cin == 1 and self.tc:
-                    ops.conv3x3_c1_wgrad(s['x'], draw, self.G[n + '/kernel'], s['wgrad_ws'])
+                    on_wgrad_stream(ops.conv3x3_c1_wgrad, s['x'], draw, self.G[n + '/kernel'], s['wgrad_ws'])
                 else:
-                    ops.conv3x3_wgrad(act[a], act[b] if b else None, draw, self.G[n + '/kernel'], s['wgrad_ws'])
+                    on_wgrad_stream(ops.conv3x3_wgrad, act[a], act[b] if b else None, draw, self.G[n + '/kernel'], s['wgrad_ws'])
                 if n == 'enc0a':
                     continue
                 dX = dxb[n]
@@ -477,10 +528,14 @@ class UNetEngine(object):
                 else:
                     grad_of[a] = (dX, blk.cin, 0)
             else:
-                ops.convT2x2_wgrad(act[a], draw, self.G[n + '/kernel'], s['wgrad_ws'])
+                on_wgrad_stream(ops.convT2x2_wgrad, act[a], draw, self.G[n + '/kernel'], s['wgrad_ws'])
                 dX = dxb[n]
                 ops.convT2x2_dgrad(draw, self.w_dgrad[n], dX)
                 grad_of[a] = (dX, blk.cin, 0)
+        if side is not None:                            # join: every weight gradient is complete before the optimizer
+            ev = torch.cuda.Event()
+            ev.record(side)
+            main.wait_event(ev)
         # ---------------- Keras-form Adam over the flat parameter buffer
         self._allreduce(self.grads)                     # 31 MB fp32: gradient of the global-batch loss
         ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, 0., self.lr_t, beta1, beta2, eps)

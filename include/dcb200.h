@@ -211,6 +211,35 @@ int dcb_bn_bwd_apply(int dtype, const float* dy, int ldy, int offy, const void* 
                      const double* sums, long long M_total, float dgb_scale, void* draw, float* dgamma,
                      float* dbeta, dcb_stream_t stream);
 
+/* ---- training BatchNorm as single-launch kernels (csrc/bn_fused.cu) ----
+ * dcb_bn_train_fwd = dcb_bn_stats + dcb_bn_finalize_apply (+ dcb_maxpool2x2 when pool_out is given: N x H x W pixels,
+ * M = N*H*W) in one persistent launch with two grid barriers; dcb_bn_train_bwd = dcb_bn_bwd_reduce + dcb_bn_bwd_apply
+ * (draw may alias x).  Cross-CTA sums are fixed-order (bit-reproducible, no floating-point atomics).
+ * workspace: dcb_bn_train_workspace_bytes(C); sync: 4 uint32 words that the caller zeroes before EVERY launch.
+ * peers (optional, data-parallel SyncBN): every rank's per-channel totals are exchanged inside the kernel through
+ * peer-mapped memory (NVLink) and summed in rank order; M_total = rows over all ranks. */
+typedef struct dcb_peer_exchange {
+  int world, rank;                      /* <= 8 ranks */
+  void* xchg[8];                        /* rank p's exchange area as mapped into THIS process (doubles) */
+  void* flags[8];                       /* rank p's flag area as mapped into this process (uint64, zero-initialised) */
+  long long slot_doubles;               /* doubles per slot, >= world * 2 * C */
+  int slot;                             /* slot of this call: distinct per (layer, direction) within a step */
+  const unsigned long long* epoch_dev;  /* device word that changes every step (state[0] of dcb_step_advance) */
+} dcb_peer_exchange_t;
+int dcb_bn_train_workspace_bytes(int C, size_t* bytes);
+int dcb_bn_train_fwd(int dtype, const void* x, long long M, int C, long long M_total, const float* gamma,
+                     const float* beta, float eps, float momentum, float* moving_mean, float* moving_var,
+                     float* scale, float* shift, float* mean, float* rstd, int relu, float p_drop,
+                     unsigned long long seed, const unsigned long long* seed_dev, unsigned layer, void* y,
+                     void* pool_out, int N, int H, int W, void* workspace, size_t workspace_bytes,
+                     unsigned int* sync, const dcb_peer_exchange_t* peers, dcb_stream_t stream);
+int dcb_bn_train_bwd(int dtype, const float* dy, int ldy, int offy, const void* x, long long M, int C,
+                     long long M_total, const float* scale, const float* shift, const float* mean,
+                     const float* rstd, float p_drop, unsigned long long seed,
+                     const unsigned long long* seed_dev, unsigned layer, float dgb_scale, void* draw,
+                     float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, unsigned int* sync,
+                     const dcb_peer_exchange_t* peers, dcb_stream_t stream);
+
 /* Device half of the training crop sampler (unet_2d_summary.py:434-530, _batch_gen): B crops of window x window pixels.
  * img_ptrs / mask_ptrs / widths: device tables over the datasets (fp32 summary images, uint8 masks, row pitch in pixels).
  * desc: device int32 [B][12] = {dataset, y0, x0, valid rows, valid cols, m00, m01, m10, m11, t0, t1, 0}: output pixel

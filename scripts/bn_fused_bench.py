@@ -1,0 +1,78 @@
+"""Training BatchNorm: single-launch kernels (dcb_bn_train_fwd / _bwd) against the separate passes, per layer shape of a
+32 x 128^2 training step.  Times are per call, averaged over a loop of back-to-back launches (CUDA events around the loop).
+
+    python scripts/bn_fused_bench.py [reps]
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'deep-calcium_b200'))
+import torch  # noqa: E402
+from deepcalcium.engine import ops  # noqa: E402
+
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 50
+only = os.environ.get('BN_ONLY')          # e.g. "32,8,8,512" to run a single shape (ncu captures)
+dt = torch.bfloat16
+shapes = [(32, 128, 128, 32), (32, 64, 64, 64), (32, 32, 32, 128), (32, 16, 16, 256), (32, 8, 8, 512)]
+if only:
+    shapes = [tuple(int(v) for v in only.split(','))]
+
+
+def timed(fn):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
+for N, H, W, C in shapes:
+    M = N * H * W
+    x = torch.randn(N, H, W, C, device='cuda').to(dt)
+    y = torch.empty_like(x); pool = torch.empty(N, H // 2, W // 2, C, dtype=dt, device='cuda')
+    dy = torch.randn(M, C, device='cuda')
+    draw = torch.empty_like(x)
+    f = lambda: torch.empty(C, device='cuda')
+    gamma, beta = torch.ones(C, device='cuda'), torch.zeros(C, device='cuda')
+    sc, sh, mu, rs, dg, db = f(), f(), f(), f(), f(), f()
+    sums = torch.zeros(4 * C, dtype=torch.float64, device='cuda')
+    ws = torch.empty(ops.bn_train_workspace_bytes(C), dtype=torch.uint8, device='cuda')
+    sync = torch.zeros(8, dtype=torch.int32, device='cuda')
+    seed_dev = torch.tensor([1], dtype=torch.int64, device='cuda')
+
+    def sep_fwd():
+        sums.zero_()
+        ops.bn_stats(x, sums[:2 * C])
+        ops.bn_finalize_apply(x, sums[:2 * C], M, gamma, beta, 0.99, None, None, sc, sh, mu, rs, y, True, 0.25, 7, seed_dev, 3)
+
+    def fused_fwd():
+        sync.zero_()
+        ops.bn_train_fwd(x, gamma, beta, 0.99, None, None, sc, sh, mu, rs, y, ws, sync[:4], True, 0.25, 7, seed_dev, 3)
+
+    def fused_fwd_pool():
+        sync.zero_()
+        ops.bn_train_fwd(x, gamma, beta, 0.99, None, None, sc, sh, mu, rs, y, ws, sync[:4], True, 0.25, 7, seed_dev, 3, pool_out=pool)
+
+    def sep_bwd():
+        sums.zero_()
+        ops.bn_bwd_reduce(dy, C, 0, x, sc, sh, mu, rs, sums[2 * C:], 0.25, 7, seed_dev, 3)
+        ops.bn_bwd_apply(dy, C, 0, x, sc, sh, mu, rs, sums[2 * C:], draw, dg, db, 0.25, 7, seed_dev, 3)
+
+    def fused_bwd():
+        sync.zero_()
+        ops.bn_train_bwd(dy, C, 0, x, sc, sh, mu, rs, draw, dg, db, ws, sync[4:], 0.25, 7, seed_dev, 3)
+
+    sep_fwd()
+    mb = M * C * 2 / 1e6
+    r = dict(sep_fwd=timed(sep_fwd), fused_fwd=timed(fused_fwd), fused_fwd_pool=timed(fused_fwd_pool), sep_bwd=timed(sep_bwd),
+             fused_bwd=timed(fused_bwd), memset=timed(lambda: sync.zero_()))
+    print('%-20s %6.1f MB bf16 | fwd: separate %6.1f us, fused %6.1f us, fused+pool %6.1f us | bwd: separate %6.1f us, fused %6.1f us | '
+          'memset alone %.1f us | floors (HBM 6.5 TB/s): fwd %.1f us (R+W), bwd %.1f us (R dy fp32 + R x + W)'
+          % ((N, H, W, C), mb, r['sep_fwd'], r['fused_fwd'], r['fused_fwd_pool'], r['sep_bwd'], r['fused_bwd'], r['memset'],
+             2 * mb / 6.5, 4 * mb / 6.5))

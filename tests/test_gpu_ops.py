@@ -306,6 +306,77 @@ def test_batchnorm_train_forward_backward(cuda, precision, C):
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('shape', [(2, 16, 24, 32), (4, 32, 32, 64), (3, 8, 8, 512), (32, 128, 128, 32), (1, 2, 2, 128)])
+def test_single_launch_batchnorm_equals_the_separate_passes(cuda, precision, shape):
+    """dcb_bn_train_fwd / dcb_bn_train_bwd (one persistent launch each, grid barriers, fixed-order cross-CTA sums, optional
+    fused 2x2 max-pool) against the four separate kernels they replace (each of which is checked against autograd above);
+    and bit-for-bit run-to-run reproducibility, which the fp64-atomic version could not promise."""
+    from deepcalcium.engine import ops
+    dt = DT[precision]
+    N, H, W, C = shape
+    M = N * H * W
+    rng = np.random.default_rng(C + M)
+    x = dev(rng.standard_normal((N, H, W, C)) * 2 + 0.5, dt)
+    gamma = dev(rng.uniform(0.5, 1.5, C)); beta = dev(0.1 * rng.standard_normal(C))
+    mm0 = rng.standard_normal(C).astype(np.float32); mv0 = rng.uniform(0.5, 1.5, C).astype(np.float32)
+    f = lambda: torch.empty(C, device='cuda')
+    ws = torch.empty(ops.bn_train_workspace_bytes(C), dtype=torch.uint8, device='cuda')
+    seed_dev = torch.tensor([4242], dtype=torch.int64, device='cuda')
+    p_drop = 0.25
+    # ---- separate passes
+    sums = torch.zeros(4 * C, dtype=torch.float64, device='cuda')
+    sc0, sh0, mu0, rs0 = f(), f(), f(), f()
+    mm, mv = dev(mm0), dev(mv0)
+    y0 = torch.empty_like(x); pool0 = torch.empty(N, H // 2, W // 2, C, dtype=dt, device='cuda')
+    ops.bn_stats(x, sums[:2 * C])
+    ops.bn_finalize_apply(x, sums[:2 * C], M, gamma, beta, 0.99, mm, mv, sc0, sh0, mu0, rs0, y0, True, p_drop, 7, seed_dev, 5)
+    ops.maxpool2x2(y0, pool0)
+    # ---- single launch, twice (determinism)
+    outs = []
+    for rep in range(2):
+        sc, sh, mu, rs = f(), f(), f(), f()
+        mm1, mv1 = dev(mm0), dev(mv0)
+        y = torch.empty_like(x); pool = torch.empty_like(pool0)
+        sync = torch.zeros(4, dtype=torch.int32, device='cuda')
+        ops.bn_train_fwd(x, gamma, beta, 0.99, mm1, mv1, sc, sh, mu, rs, y, ws, sync, True, p_drop, 7, seed_dev, 5, pool_out=pool)
+        outs.append((y, pool, sc, sh, mu, rs, mm1, mv1))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    y, pool, sc, sh, mu, rs, mm1, mv1 = outs[0]
+    for a, b in ((sc, sc0), (sh, sh0), (mu, mu0), (rs, rs0), (mm1, mm), (mv1, mv)):
+        assert torch.allclose(a, b, rtol=2e-6, atol=2e-6)
+    step = 2.0 ** -7 if precision == 'bf16' else 1e-5
+    assert float(((y.float() - y0.float()).abs() > step * y0.float().abs().clamp(min=1.0)).float().mean()) == 0.0
+    assert float((y != y0).float().mean()) < 1e-3 and float((pool != pool0).float().mean()) < 1e-3
+    y_np = torch.empty_like(x)                                            # no pooling: same activations
+    sync = torch.zeros(4, dtype=torch.int32, device='cuda')
+    ops.bn_train_fwd(x, gamma, beta, 0.99, dev(mm0), dev(mv0), f(), f(), f(), f(), y_np, ws, sync, True, p_drop, 7, seed_dev, 5)
+    assert torch.equal(y_np, y)
+    # ---- backward: dy is a channel slice of a wider fp32 tensor
+    dy_wide = dev(rng.standard_normal((M, 2 * C)))
+    off = C // 2 if (C // 2) % 4 == 0 else 0
+    draw0 = torch.empty_like(x); dg0, db0 = f(), f()
+    ops.bn_bwd_reduce(dy_wide, 2 * C, off, x, sc0, sh0, mu0, rs0, sums[2 * C:], p_drop, 7, seed_dev, 5)
+    ops.bn_bwd_apply(dy_wide, 2 * C, off, x, sc0, sh0, mu0, rs0, sums[2 * C:], draw0, dg0, db0, p_drop, 7, seed_dev, 5)
+    res = []
+    for rep in range(2):
+        draw = torch.empty_like(x); dg, db = f(), f()
+        sync = torch.zeros(4, dtype=torch.int32, device='cuda')
+        ops.bn_train_bwd(dy_wide, 2 * C, off, x, sc0, sh0, mu0, rs0, draw, dg, db, ws, sync, p_drop, 7, seed_dev, 5)
+        res.append((draw, dg, db))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+    draw, dg, db = res[0]
+    scale_g = float(draw0.float().abs().max())
+    assert float((draw.float() - draw0.float()).abs().max()) <= (2.0 ** -7 if precision == 'bf16' else 1e-5) * scale_g
+    assert torch.allclose(dg, dg0, rtol=1e-5, atol=1e-4) and torch.allclose(db, db0, rtol=1e-5, atol=1e-4)
+    # in place (draw aliases x), as the engine uses it
+    x2 = x.clone(); sync = torch.zeros(4, dtype=torch.int32, device='cuda')
+    ops.bn_train_bwd(dy_wide, 2 * C, off, x2, sc0, sh0, mu0, rs0, x2, f(), f(), ws, sync, p_drop, 7, seed_dev, 5)
+    assert torch.equal(x2, draw)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 def test_dropout_is_consistent_between_forward_and_backward(cuda, precision):
     from deepcalcium.engine import ops
     dt = DT[precision]
