@@ -483,7 +483,7 @@ def bench_train_dp(args, pk, eng_unused, imgs, max_over_ranks, barrier):
     import torch
     from deepcalcium.engine.graph import GraphSpec, he_normal_weights
     from deepcalcium.engine.unet_engine import UNetEngine
-    from deepcalcium.engine.dist import Comm, sync_parameters
+    from deepcalcium.engine.dist import Comm, sync_parameters, attach_peers
     comm = Comm()
     spec = GraphSpec(32)
     # the NCCL all-reduces (torch.distributed) are captured into the step's CUDA graph together with the kernels;
@@ -498,6 +498,8 @@ def bench_train_dp(args, pk, eng_unused, imgs, max_over_ranks, barrier):
         eng = UNetEngine(spec, precision=args.precision, use_graphs=use_graphs)
         eng.set_weights_dict(he_normal_weights(spec, seed=7535))
         eng.comm = comm
+        if os.environ.get('DCB_DP_PEERS', '1') == '1':
+            attach_peers(eng, comm)          # SyncBN / loss sums exchanged inside the kernels over NVLink (no per-layer NCCL call)
         sync_parameters(eng, comm)
         for i in range(4):
             eng.train_step(x, y, loss='dice_loss', lr=0.002, dropout=True)
@@ -519,7 +521,9 @@ def bench_train_dp(args, pk, eng_unused, imgs, max_over_ranks, barrier):
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1)) / n
     res = {'crops_per_s': comm.world * B * 1e3 / ms, 'ms_per_step': ms, 'global_batch': comm.world * B, 'ranks': comm.world,
-           'launch': 'one CUDA graph per step, collectives captured' if graphs else 'eager (collectives interleaved)'}
+           'launch': 'one CUDA graph per step, collectives captured' if graphs else 'eager (collectives interleaved)',
+           'sync_bn': 'in-kernel peer exchange over NVLink (44 per step) + loss sums' if eng.peers is not None else 'NCCL all-reduce per layer',
+           'grad_allreduce': '3 NCCL buckets (decoder / bottleneck / encoder) on a side stream, overlapped with the backward pass'}
     del eng
     try:
         res.update(parity_train_dp(comm, spec))
@@ -534,7 +538,7 @@ def parity_train_dp(comm, spec):
     import torch
     from deepcalcium.engine.graph import he_normal_weights
     from deepcalcium.engine.unet_engine import UNetEngine
-    from deepcalcium.engine.dist import shard_range, sync_parameters
+    from deepcalcium.engine.dist import shard_range, sync_parameters, attach_peers
     w = he_normal_weights(spec, seed=7535)
     Bg, H = 4 * comm.world, 64
     x = np.random.default_rng(1).standard_normal((Bg, H, H)).astype(np.float32)
@@ -543,6 +547,8 @@ def parity_train_dp(comm, spec):
     dp = UNetEngine(spec, precision='fp32', use_graphs=False)
     dp.set_weights_dict(w)
     dp.comm = comm
+    if os.environ.get('DCB_DP_PEERS', '1') == '1':
+        attach_peers(dp, comm)
     sync_parameters(dp, comm)
     m = dp.train_step(torch.from_numpy(x[f:f + c]).cuda(), torch.from_numpy(y[f:f + c]).cuda(), loss='dice_loss', dropout=False)
     loss_dp = float(m[0].item())

@@ -275,6 +275,50 @@ def bn_train_bwd(dy, ldy, offy, x, scale, shift, mean, rstd, draw, dgamma, dbeta
          _peers_arg(peers, slot), stream_ptr())
 
 
+# ---------------------------------------------------------------- peer-mapped memory (csrc/peer.cu)
+def peer_alloc(nbytes):
+    """-> (device pointer, 64-byte IPC handle)"""
+    p = c_p(0)
+    h = (ctypes.c_ubyte * 64)()
+    call('dcb_peer_alloc', c_sz(nbytes), ctypes.byref(p), h)
+    return p.value, bytes(h)
+
+
+def peer_open(handle):
+    p = c_p(0)
+    h = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+    call('dcb_peer_open', h, ctypes.byref(p))
+    return p.value
+
+
+def peer_close(ptr_value):
+    call('dcb_peer_close', c_p(ptr_value))
+
+
+def peer_free(ptr_value):
+    call('dcb_peer_free', c_p(ptr_value))
+
+
+def counter_advance(counter):
+    _chk(counter, torch.int64)
+    call('dcb_counter_advance', ptr(counter), stream_ptr())
+
+
+def flag_signal(flag_addrs, epoch, offset=0):
+    """flag_addrs: list of raw device addresses (possibly peer-mapped); epoch: int64 CUDA tensor [1]"""
+    arr = (c_p * len(flag_addrs))(*flag_addrs)
+    call('dcb_flag_signal', arr, c_int(len(flag_addrs)), ptr(epoch), c_ll(offset), stream_ptr())
+
+
+def flag_wait(flags_addr, n, epoch, offset=0, at_least=False):
+    call('dcb_flag_wait', c_p(flags_addr), c_int(n), ptr(epoch), c_ll(offset), c_int(int(at_least)), stream_ptr())
+
+
+def peer_allreduce_f64(vals, peers, slot):
+    _chk(vals, torch.float64)
+    call('dcb_peer_allreduce_f64', ptr(vals), c_int(vals.numel()), _peers_arg(peers, slot), stream_ptr())
+
+
 # ---------------------------------------------------------------- pooling
 def crop_batch(img_ptrs, mask_ptrs, widths, desc, window, x_out, y_out):
     """tables: int64 [D], int64 [D], int32 [D]; desc int32 [B, 12]; x_out fp32 [B, n, n]; y_out uint8 [B, n, n]"""

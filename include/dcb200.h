@@ -240,6 +240,24 @@ int dcb_bn_train_bwd(int dtype, const float* dy, int ldy, int offy, const void* 
                      float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, unsigned int* sync,
                      const dcb_peer_exchange_t* peers, dcb_stream_t stream);
 
+/* ---- peer-mapped memory between the ranks of one NVSwitch box (csrc/peer.cu; SURVEY 8e, no reference counterpart:
+ * the reference is single-device).  dcb_peer_alloc returns a zero-filled device buffer and its 64-byte CUDA IPC handle;
+ * the other ranks map it with dcb_peer_open (the host ships the handles, e.g. with torch.distributed).  Flags are uint64
+ * words in such buffers; epochs come from device-resident counters so that captured CUDA graphs stay valid. ---- */
+int dcb_peer_alloc(size_t bytes, void** ptr, unsigned char* handle_out /* 64 bytes */);
+int dcb_peer_open(const unsigned char* handle /* 64 bytes */, void** ptr);
+int dcb_peer_close(void* ptr);
+int dcb_peer_free(void* ptr);
+int dcb_counter_advance(unsigned long long* counter, dcb_stream_t stream);
+/* every flag_ptrs[i] (i < n <= 8; pointers may be peer-mapped) = *epoch_dev + offset, after a system-scope fence */
+int dcb_flag_signal(unsigned long long* const* flag_ptrs, int n, const unsigned long long* epoch_dev, long long offset,
+                    dcb_stream_t stream);
+/* block the stream until flags[0..n) == *epoch_dev + offset (at_least != 0: >=); traps after ~10 s */
+int dcb_flag_wait(const unsigned long long* flags, int n, const unsigned long long* epoch_dev, long long offset,
+                  int at_least, dcb_stream_t stream);
+/* one-shot all-reduce (sum, rank order, bit-identical on every rank) of n doubles through the peer exchange slots */
+int dcb_peer_allreduce_f64(double* vals, int n, const dcb_peer_exchange_t* peers, dcb_stream_t stream);
+
 /* Device half of the training crop sampler (unet_2d_summary.py:434-530, _batch_gen): B crops of window x window pixels.
  * img_ptrs / mask_ptrs / widths: device tables over the datasets (fp32 summary images, uint8 masks, row pitch in pixels).
  * desc: device int32 [B][12] = {dataset, y0, x0, valid rows, valid cols, m00, m01, m10, m11, t0, t1, 0}: output pixel

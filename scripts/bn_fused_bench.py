@@ -19,20 +19,32 @@ if only:
     shapes = [tuple(int(v) for v in only.split(','))]
 
 
-def timed(fn):
+def timed(fn, inner=20):
+    """per-call device time with the launches replayed from a CUDA graph (no host launch overhead)"""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(inner):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = max(1, reps // inner)
     e0.record()
-    for _ in range(reps):
-        fn()
+    for _ in range(n):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps * 1e3
+    return e0.elapsed_time(e1) / (n * inner) * 1e3
 
 
-for N, H, W, C in shapes:
+from deepcalcium import _native as nat  # noqa: E402
+per_sm_list = [int(v) for v in os.environ.get('BN_CTAS', '4').split(',')]
+for N, H, W, C in [sh for sh in shapes for _ in per_sm_list]:
+    per_sm = per_sm_list[0]; per_sm_list = per_sm_list[1:] + per_sm_list[:1]
+    nat.set_policy(bn_ctas_per_sm=per_sm)
     M = N * H * W
     x = torch.randn(N, H, W, C, device='cuda').to(dt)
     y = torch.empty_like(x); pool = torch.empty(N, H // 2, W // 2, C, dtype=dt, device='cuda')
@@ -72,6 +84,7 @@ for N, H, W, C in shapes:
     mb = M * C * 2 / 1e6
     r = dict(sep_fwd=timed(sep_fwd), fused_fwd=timed(fused_fwd), fused_fwd_pool=timed(fused_fwd_pool), sep_bwd=timed(sep_bwd),
              fused_bwd=timed(fused_bwd), memset=timed(lambda: sync.zero_()))
+    print('ctas/SM %d ' % per_sm, end='')
     print('%-20s %6.1f MB bf16 | fwd: separate %6.1f us, fused %6.1f us, fused+pool %6.1f us | bwd: separate %6.1f us, fused %6.1f us | '
           'memset alone %.1f us | floors (HBM 6.5 TB/s): fwd %.1f us (R+W), bwd %.1f us (R dy fp32 + R x + W)'
           % ((N, H, W, C), mb, r['sep_fwd'], r['fused_fwd'], r['fused_fwd_pool'], r['sep_bwd'], r['fused_bwd'], r['memset'],

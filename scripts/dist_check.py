@@ -9,7 +9,7 @@ os.environ.setdefault('DEEP_CALCIUM_HOME', '/tmp/deep-calcium-home')
 import numpy as np, torch, torch.distributed as dist
 from deepcalcium.engine.graph import GraphSpec, he_normal_weights
 from deepcalcium.engine.unet_engine import UNetEngine
-from deepcalcium.engine.dist import Comm, predict_tta_sharded, shard_range, sync_parameters
+from deepcalcium.engine.dist import Comm, predict_tta_sharded, shard_range, sync_parameters, attach_peers
 
 local = int(os.environ.get('LOCAL_RANK', '0'))
 torch.cuda.set_device(local)
@@ -27,9 +27,10 @@ ok = True
 eng = UNetEngine(spec, precision='bf16')
 eng.set_weights_dict(w)
 s = torch.from_numpy(np.random.default_rng(865).standard_normal((500, 480)).astype(np.float32)).cuda()
-for it in range(3):     # eager, capture, replay
-    mask, act = predict_tta_sharded(eng, s, comm)
+for it in range(4):     # eager, capture, replay, replay
+    mask, act = predict_tta_sharded(eng, s if comm.rank == 0 else None, comm, shape=tuple(s.shape))
 if comm.rank == 0:
+    mask, act = mask.clone(), act.clone()
     m1, a1 = eng.predict_tta(s)
     same = bool(torch.equal(mask, m1)) and bool(torch.equal(act, a1))
     print('sharded TTA over %d ranks bit-identical to 1 GPU: %s' % (comm.world, same))
@@ -42,6 +43,8 @@ f, c = shard_range(B, comm.world, comm.rank)
 dp = UNetEngine(spec, precision='fp32', use_graphs=False)
 dp.set_weights_dict(w)
 dp.comm = comm
+if os.environ.get('DCB_DP_PEERS', '1') == '1':
+    attach_peers(dp, comm)
 sync_parameters(dp, comm)
 m = dp.train_step(torch.from_numpy(x[f:f + c]).cuda(), torch.from_numpy(y[f:f + c]).cuda(), loss='dice_loss', dropout=False)
 loss_dp = float(m[0].item())
@@ -61,8 +64,7 @@ if comm.rank == 0:
     stat = max(float(np.max(np.abs(wd[k] - wr[k]))) for k in wd if 'moving' in k)
     print('DP loss %.8f single-GPU loss %.8f; worst gradient rel. L2 diff %s %.3g; max |BN moving stat diff| %.3g'
           % (loss_dp, loss_ref, worst[0], worst[1], stat))
-    # fp32 check-mode gradients carry ~3-5e-3 relative noise of their own (BN-backward cancellation, see tests)
-    good = abs(loss_dp - loss_ref) < 1e-5 and worst[1] < 1e-2 and stat < 1e-5
+    good = abs(loss_dp - loss_ref) < 1e-5 and worst[1] < 1e-4 and stat < 1e-5
     print('data-parallel training matches the single-device batch: %s' % good)
     ok &= bool(good)
 dist.barrier()
