@@ -375,7 +375,7 @@ def run_ours(args):
 
     line = {'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': {'fp16': 'f16', 'bf16': 'bf16', 'fp32': 'f32'}[args.precision], 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'window': 512, 'tta': 8, 'batch_per_step': 8,
                        'weights': 'random-init he_normal seed 7535', 'parallelism': 'independent images per rank',
                        'l2': 'per-step activation footprint ~1.2 GB >> 126 MB L2; 4 rotating inputs'},
@@ -426,6 +426,11 @@ def run_ours(args):
             line['parity'] = {'inference': {'error': repr(ex)}}
         # ---- extras: projection (C2) and training (C3)
         line['extra'] = dict(dist_extra)
+        if args.precision == 'fp16' and world == 1:
+            try:      # the same step with bf16 storage (same MMA rate; its logit error is the reason fp16 is the default)
+                line['extra']['inference_bf16'] = bench_inference_other(args, spec, w, imgs, 'bf16')
+            except Exception as ex:   # noqa: BLE001
+                line['extra']['inference_bf16'] = {'error': repr(ex)}
         for name, fn in (('projection', bench_projection), ('train', bench_train)):
             try:
                 line['extra'][name] = fn(args, pk)
@@ -445,6 +450,25 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_inference_other(args, spec, w, imgs, precision):
+    import torch
+    from deepcalcium.engine.unet_engine import UNetEngine
+    eng = UNetEngine(spec, precision=precision)
+    eng.set_weights_dict(w)
+    for i in range(4):
+        eng.predict_tta(imgs[i % len(imgs)])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        eng.predict_tta(imgs[i % len(imgs)])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    par = parity_inference(eng, w, imgs[0], precision)
+    return {'images_per_s': 1e3 / ms, 'ms_per_step': ms, 'parity': par}
 
 
 def bench_tta_sharded(args, pk, eng, imgs, max_over_ranks, barrier):
@@ -495,7 +519,7 @@ def bench_train_dp(args, pk, eng_unused, imgs, max_over_ranks, barrier):
     y = torch.from_numpy((rng.random((B, 128, 128)) < 0.126).astype(np.uint8)).cuda()
 
     def make(use_graphs):
-        eng = UNetEngine(spec, precision=args.precision, use_graphs=use_graphs)
+        eng = UNetEngine(spec, precision=train_precision(args), use_graphs=use_graphs)
         eng.set_weights_dict(he_normal_weights(spec, seed=7535))
         eng.comm = comm
         if os.environ.get('DCB_DP_PEERS', '1') == '1':
@@ -523,7 +547,7 @@ def bench_train_dp(args, pk, eng_unused, imgs, max_over_ranks, barrier):
     res = {'crops_per_s': comm.world * B * 1e3 / ms, 'ms_per_step': ms, 'global_batch': comm.world * B, 'ranks': comm.world,
            'launch': 'one CUDA graph per step, collectives captured' if graphs else 'eager (collectives interleaved)',
            'sync_bn': 'in-kernel peer exchange over NVLink (44 per step) + loss sums' if eng.peers is not None else 'NCCL all-reduce per layer',
-           'grad_allreduce': '3 NCCL buckets (decoder / bottleneck / encoder) on a side stream, overlapped with the backward pass'}
+           'grad_allreduce': 'one NCCL all-reduce of the flat 31 MB fp32 buffer after the backward pass (inside the step graph)'}
     del eng
     try:
         res.update(parity_train_dp(comm, spec))
@@ -659,13 +683,17 @@ def bench_projection(args, pk):
     return res
 
 
+def train_precision(args):
+    return 'bf16' if args.precision == 'fp16' else args.precision      # fp16 is inference only
+
+
 def bench_train(args, pk):
-    """BASELINE config C3: 128x128 crops, batch 32, dice loss, Adam(0.002), dropout on."""
+    """BASELINE config C3: 128x128 crops, batch 32, bf16, dice loss, Adam(0.002), dropout on."""
     import torch
     from deepcalcium.engine.graph import GraphSpec, he_normal_weights
     from deepcalcium.engine.unet_engine import UNetEngine
     spec = GraphSpec(32)
-    eng = UNetEngine(spec, precision=args.precision)
+    eng = UNetEngine(spec, precision=train_precision(args))
     eng.set_weights_dict(he_normal_weights(spec, seed=7535))
     rng = np.random.default_rng(865)
     B = 32
@@ -685,11 +713,11 @@ def bench_train(args, pk):
     ms = e0.elapsed_time(e1) / n
     fl = B * spec.flops_train(128, 128)
     res = {'crops_per_s': B * 1e3 / ms, 'ms_per_step': ms, 'batch': B, 'crop': 128, 'loss': 'dice_loss',
-           'final_loss': float(m[0].item()), 'tflops': fl / ms / 1e9, 'frac_of_bf16_peak_burst': fl / ms / 1e9 / pk['tf'],
+           'dtype': train_precision(args), 'final_loss': float(m[0].item()), 'tflops': fl / ms / 1e9, 'frac_of_bf16_peak_burst': fl / ms / 1e9 / pk['tf'],
            'frac_of_bf16_peak_sustained': fl / ms / 1e9 / pk['tf_sus'], 'flops_per_step': fl,
            'gpu_launches_per_step': (eng.launches - l0) // n}
     try:
-        res['parity'] = parity_train(args.precision, he_normal_weights(spec, seed=7535), xs[0], ys[0])
+        res['parity'] = parity_train(train_precision(args), he_normal_weights(spec, seed=7535), xs[0], ys[0])
     except Exception as ex:   # noqa: BLE001
         res['parity'] = {'error': repr(ex)}
     return res
@@ -701,7 +729,10 @@ def main():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--precision', default='fp16', choices=['fp16', 'bf16', 'fp32'],
+                    help="activation / weight storage of the inference path: fp16 and bf16 run the same tcgen05 kind::f16 MMAs "
+                         "(fp32 accumulate) at the same rate; fp16 meets the north star's 1e-2 logit tolerance, bf16 cannot "
+                         "(tests/test_gpu_unet.py, DESIGN.md section 4); training extras always run in bf16 (or fp32)")
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -454,9 +454,7 @@ static int launch_bn_fwd(BnFwdParams& p, void* ws, size_t ws_bytes, cudaStream_t
   static int limit = 0;          // per template instance
   if (limit == 0) limit = coresident_limit(bn_train_fwd_kernel<T, VEC, POOL>, smem > 16384 ? smem : 16384);
   if (limit <= 0) return fail(DCB_ERR_CUDA, "occupancy query failed for the fused BatchNorm kernel");
-  // data-parallel runs share the SMs with NCCL kernels of the overlapped gradient all-reduce: claim at most half of the
-  // co-resident capacity so that the grid barrier can never wait for a CTA that has no SM to run on
-  const int grid = fused_grid(p.M, p.C, VEC, p.pv.world > 1 ? (limit + 1) / 2 : limit);
+  const int grid = fused_grid(p.M, p.C, VEC, limit);
   const size_t need = ((size_t)grid + 1) * 2 * p.C * sizeof(double);
   if (!ws || ws_bytes < need) return fail(DCB_ERR_WORKSPACE, "dcb_bn_train_fwd: workspace %zu B < required %zu B", ws_bytes, need);
   p.partial = reinterpret_cast<double*>(ws);
@@ -501,7 +499,7 @@ static int launch_bn_bwd(BnBwdParams& p, void* ws, size_t ws_bytes, cudaStream_t
   static int limit = 0;
   if (limit == 0) limit = coresident_limit(bn_train_bwd_kernel<T, VEC>, smem > 16384 ? smem : 16384);
   if (limit <= 0) return fail(DCB_ERR_CUDA, "occupancy query failed for the fused BatchNorm backward kernel");
-  const int grid = fused_grid(p.M, p.C, VEC, p.pv.world > 1 ? (limit + 1) / 2 : limit);
+  const int grid = fused_grid(p.M, p.C, VEC, limit);
   const size_t need = ((size_t)grid + 1) * 2 * p.C * sizeof(double);
   if (!ws || ws_bytes < need) return fail(DCB_ERR_WORKSPACE, "dcb_bn_train_bwd: workspace %zu B < required %zu B", ws_bytes, need);
   p.partial = reinterpret_cast<double*>(ws);

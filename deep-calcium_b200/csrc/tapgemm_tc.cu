@@ -442,9 +442,13 @@ constexpr int ST_MAX_RING = 12;
 __device__ unsigned long long g_strip_dbg[148 * 8];
 __device__ unsigned long long g_strip_dbg2[148 * 16];
 #define ST_T(var) const long long var = clock64()
+#define ST_DECL(var) long long var = 0
+#define ST_SET(var) var = clock64()
 #define ST_ACC(slot, a, b) dbg_acc[slot] += (unsigned long long)((b) - (a))
 #else
 #define ST_T(var)
+#define ST_DECL(var)
+#define ST_SET(var)
 #define ST_ACC(slot, a, b)
 #endif
 
@@ -673,6 +677,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
           bool pre = false, pre_te = false;
           for (int m = 0; m <= half; ++m) {                       // input (halo) rows h0 + 2m - 1 and h0 + 2m
             ST_T(c0);
+            ST_DECL(c1);
             const uint32_t jp = (j >> 1) + (uint32_t)m;           // running index of the output pair P(m)
             {
               uint32_t ok_rf = 0, ok_te = 0;
@@ -682,7 +687,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
               }
               if (!ok_rf) mbar_wait_a(a_row_full + 8u * pp, (fullpar >> pp) & 1u);
               fullpar ^= 1u << pp;
-              ST_T(c1); ST_ACC(0, c0, c1);
+              ST_SET(c1); ST_ACC(0, c0, c1);
               if (m < half && !ok_te) mbar_wait_a(a_tempty + 8u * (jp & pmask), ((jp >> pair_sh) & 1u) ^ 1u);
             }
             tc_fence_after();
@@ -1454,9 +1459,20 @@ static int run_tc_generic(const TapGeom& g, const void* s0, int C0, const void* 
   const int num_mtiles = p.tiles_w * p.tiles_h * p.tiles_n;
   // ---- N tiling: largest tile that still gives every SM work
   // an N tile may span several convT sub-positions (the epilogue resolves them per 32-column block)
-  int BN = p.Ntot < 256 ? p.Ntot : 256;
-  while (BN > 64 && (long long)num_mtiles * (p.Ntot / BN) < sm_count() && BN % 64 == 0) BN /= 2;
-  if (p.Ntot % BN != 0) BN = 32;
+  // Cost model from the issue-rate probes (profiles/r1_umma_rate_probe.log): one M=128 MMA occupies the tensor pipe for
+  // ~89 cycles whatever N <= 128 is, and for 128 cycles at N = 256, so a tile costs (MMAs per tile) x c(BN) and the launch
+  // costs waves x that.  Halving BN below 128 never shortens a tile; it only pays when it removes a wave.
+  int BN = 32;
+  {
+    double best = 1e30;
+    for (int cand : {256, 192, 128, 96, 64, 32}) {
+      if (cand > p.Ntot || p.Ntot % cand != 0) continue;
+      const long long tiles = (long long)num_mtiles * (p.Ntot / cand);
+      const long long waves = (tiles + sm_count() - 1) / sm_count();
+      const double cost = (double)waves * (cand <= 128 ? 89.0 : 89.0 + (cand - 128) * (39.0 / 128.0));
+      if (cost < best - 1e-9) { best = cost; BN = cand; }     // ties: the larger tile (fewer activation re-loads)
+    }
+  }
   if (p.swap) BN = p.Ntot < 128 ? p.Ntot : 128;       // rows of the weight TMA box
   p.BN = BN;
   const size_t stage_bytes = (size_t)TM * p.BK * 2 + (size_t)(p.swap ? 128 : BN) * p.BK * 2;

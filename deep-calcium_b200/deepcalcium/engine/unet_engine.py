@@ -387,22 +387,6 @@ class UNetEngine(object):
             self._side = torch.cuda.Stream(device=self.dev)
         return self._side
 
-    def _comm_stream(self):
-        if getattr(self, '_comm', None) is None:
-            self._comm = torch.cuda.Stream(device=self.dev)
-        return self._comm
-
-    def _grad_buckets(self):
-        """{name: (lo, hi, block whose entry in the backward loop means the bucket is complete)} over the flat gradient
-        buffer, which is laid out in forward (Keras) order: encoder | bottleneck | decoder + head."""
-        names = [b.name for b in self.spec.blocks]
-        ib = names.index('bota')
-        off = lambda i: self._slots[names[i] + '/kernel'][1]
-        end = self.grads.numel()
-        return {'dec': (off(ib + 2), end, names[ib + 1]),        # complete when the loop reaches botb
-                'bot': (off(ib), off(ib + 2), names[ib - 1]),    # complete when the loop reaches enc3b
-                'enc': (0, off(ib), None)}                       # complete after the loop
-
     def _dropout_p(self, name, enabled):
         return float(self.spec.dropout_after().get(name, 0.)) if enabled else 0.
 
@@ -496,31 +480,10 @@ class UNetEngine(object):
             with torch.cuda.stream(side):
                 fn(*args)
 
-        # Data-parallel gradient all-reduce in three buckets (decoder | bottleneck | encoder: 37 % / 45 % / 18 % of the
-        # parameters), each issued on a communication stream as soon as the backward pass has produced its last gradient,
-        # so NCCL overlaps with the rest of the backward pass instead of running after it.
-        buckets = self._grad_buckets() if world > 1 else {}
-        # bucket k is complete once the loop (which walks the blocks backwards) ENTERS the block preceding its first block
-        done_trigger = {prev: k for k, (lo, hi, prev) in buckets.items() if prev is not None}
-        buckets = {k: (lo, hi) for k, (lo, hi, prev) in buckets.items()}
-        comm_stream = self._comm_stream() if world > 1 else None
-
-        def launch_bucket(lo, hi):
-            evs = [torch.cuda.Event(), torch.cuda.Event()]
-            evs[0].record(main)
-            comm_stream.wait_event(evs[0])
-            if side is not None:
-                evs[1].record(side)
-                comm_stream.wait_event(evs[1])
-            with torch.cuda.stream(comm_stream):
-                self.comm.allreduce_sum(self.grads[lo:hi])
-
         grad_of = {'dec0b': (s['dhead'], spec.nfb, 0)}
         skip_grad = {}
         for blk in reversed(spec.blocks):
             n = blk.name
-            if n in done_trigger:
-                launch_bucket(*buckets[done_trigger.pop(n)])
             if blk.kind == 'head':
                 continue
             a, b = self._inputs[n]
@@ -577,12 +540,13 @@ class UNetEngine(object):
             ev = torch.cuda.Event()
             ev.record(side)
             main.wait_event(ev)
-        if world > 1:                                   # the last bucket (encoder), then join the communication stream
-            launch_bucket(*buckets['enc'])
-            ev = torch.cuda.Event()
-            ev.record(comm_stream)
-            main.wait_event(ev)
-        # ---------------- Keras-form Adam over the flat parameter buffer (gradients of the global-batch loss)
+        # ---------------- data-parallel: gradient of the global-batch loss (NCCL all-reduce of the flat 31 MB buffer).
+        # It runs AFTER the backward pass on purpose: the single-launch BatchNorm kernels spin on peers' flags while they
+        # hold their SMs, and an NCCL kernel that needs SMs on this rank while its partner waits behind such a kernel on
+        # the other rank would close a dependency cycle.  Only the (non-blocking) weight-gradient kernels ever run
+        # concurrently with the spinning kernels.
+        self._allreduce(self.grads)
+        # ---------------- Keras-form Adam over the flat parameter buffer
         ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, 0., self.lr_t, beta1, beta2, eps)
 
     @_on_engine_device

@@ -48,7 +48,7 @@ class UNetModel(object):
         assert len(window_shape) == 2
         self.window_shape = tuple(int(v) for v in window_shape)
         self.spec = spec
-        precision = precision or os.environ.get('DEEPCALCIUM_PRECISION', 'bf16')
+        precision = precision or 'bf16'          # trainable default; inference-only loads use 'fp16' (see load_model_...)
         self.engine = UNetEngine(spec, precision=precision)
         self.engine.set_weights_dict(he_normal_weights(spec, seed))
         self.optimizer = Adam(0.002)
@@ -118,7 +118,7 @@ class UNetModel(object):
             np.savez(fp, **arrays)
 
 
-def load_model_with_new_input_shape(model_path, input_shape, compile=True, precision=None, **kwargs):
+def load_model_with_new_input_shape(model_path, input_shape, compile=True, precision=None, trainable=True, **kwargs):
     """Counterpart of deepcalcium/utils/keras_helpers.py:24-68: the graph is fully convolutional, so
     the same weights simply run at another window size (no file rewriting)."""
     import torch
@@ -127,6 +127,11 @@ def load_model_with_new_input_shape(model_path, input_shape, compile=True, preci
         if cfg.get('format') != 'deepcalcium-b200-v1':
             raise ValueError('%s is not a deepcalcium-b200 model file' % model_path)
         spec = GraphSpec(cfg['nb_filters_base'], cfg['prop_dropout_base'], cfg['upsampling_or_transpose'])
+        if precision is None:
+            # predict() loads with trainable=False: inference only -> fp16 activations (same tensor-core rate as bf16, 8x
+            # smaller logit error: meets the 1e-2 tolerance); a model that will be trained is bf16.  Widths that are not
+            # multiples of 32 have no tensor-core path: fp32 check mode.
+            precision = 'fp32' if spec.nfb % 32 else ('bf16' if trainable else 'fp16')
         model = UNetModel(tuple(input_shape), spec, precision=precision)
         model.engine.set_weights_dict({k: z['w%03d' % i] for i, k in enumerate(cfg['weight_keys'])})
         model.optimizer = Adam(**cfg['optimizer'])
@@ -141,8 +146,8 @@ def load_model_with_new_input_shape(model_path, input_shape, compile=True, preci
 
 def unet(window_shape=(128, 128), nb_filters_base=32, conv_kernel_init='he_normal',
          prop_dropout_base=0.25, upsampling_or_transpose='transpose', precision=None, seed=None):
-    """Same arguments as the reference's unet() (unet_2d_summary.py:123-124).  ``precision`` selects
-    'bf16' (tcgen05 kernels, default) or 'fp32' (CUDA-core check mode)."""
+    """Same arguments as the reference's unet() (unet_2d_summary.py:123-124).  ``precision`` selects 'bf16' (tcgen05
+    kernels, default: trainable), 'fp16' (same kernels with fp16 storage, inference only) or 'fp32' (CUDA-core check mode)."""
     assert len(window_shape) == 2 and window_shape[0] == window_shape[1]
     if conv_kernel_init != 'he_normal':
         raise NotImplementedError("only conv_kernel_init='he_normal' (the reference default) is built")
@@ -431,7 +436,7 @@ class UNet2DSummary(object):
         import torch
         logger = logging.getLogger(funcname())
         model = model_path if isinstance(model_path, UNetModel) else \
-            load_model_with_new_input_shape(model_path, window_shape, compile=False)
+            load_model_with_new_input_shape(model_path, window_shape, compile=False, trainable=False)
         assert tuple(window_shape) == (512, 512), 'TODO: implement variable window sizes.'
         Mp, names = [], []
         mean_prec, mean_reca, mean_comb = 0., 0., 0.
