@@ -4,8 +4,8 @@ examples/neurons/unet2ds_sj.py:67-85) runs as one streaming CUDA kernel.
 
 ``summarize_movie`` is the projection as a function (movie in, (mean, max) out);
 ``make_dataset`` writes the reference's dataset schema (series/mean, series/max, masks/raw,
-masks/max, attr name, nf.py:39-44) into an ``.npz`` container (h5py is optional: when it is
-importable, ``*.hdf5`` / ``*.h5`` paths are read and written with the reference's layout).
+masks/max, attr name, nf.py:39-44): ``*.hdf5`` / ``*.h5`` paths in the reference's HDF5 layout (through h5py when it
+is importable, else the pure-Python classic-format writer utils/hdf5_lite.py), other paths as an ``.npz`` container.
 Neurofinder download / unzip / TIFF decode (nf.py:73-97, 126-127) are out of scope (no network).
 """
 import logging
@@ -68,22 +68,29 @@ def _is_hdf5(path):
     return path.endswith(('.hdf5', '.h5'))
 
 
+def _h5():
+    """h5py when it is importable, else the pure-Python classic-format reader / writer (utils/hdf5_lite.py)"""
+    try:
+        import h5py
+        return h5py
+    except ImportError:
+        from ..utils import hdf5_lite
+        return hdf5_lite
+
+
 def open_dataset(path):
-    """Read a dataset file into a dict {'name', 'series/mean', 'series/max', 'masks/raw', ...}."""
+    """Read a dataset file into a dict {'name', 'series/mean', 'series/max', 'masks/raw', ...}: the reference's HDF5
+    schema (datasets/nf.py:39-44; ``series/raw``, the movie itself, is not loaded) or the .npz container."""
     if _is_hdf5(path):
-        try:
-            import h5py
-        except ImportError:
-            raise ImportError('reading %s needs h5py, which is not installed; use the .npz container '
-                              '(deepcalcium.datasets.nf.make_dataset)' % path)
         out = {}
-        with h5py.File(path, 'r') as fp:
-            out['name'] = fp.attrs['name']
+        with _h5().File(path, 'r') as fp:
+            name = fp.attrs['name']
+            out['name'] = name.decode('utf8') if isinstance(name, bytes) else str(name)
             for grp in ('series', 'masks'):
                 if grp in fp:
-                    for k in fp[grp]:
+                    for k in fp[grp].keys():
                         if k != 'raw' or grp == 'masks':
-                            out['%s/%s' % (grp, k)] = fp[grp][k][...]
+                            out['%s/%s' % (grp, k)] = np.asarray(fp[grp][k][...])
         return out
     with np.load(path, allow_pickle=False) as z:
         out = {k.replace('__', '/'): z[k] for k in z.files}
@@ -105,8 +112,7 @@ def make_dataset(path, name, movie=None, mean=None, mx=None, masks=None):
         d['masks__raw'] = masks
         d['masks__max'] = masks.max(axis=0)
     if _is_hdf5(path):
-        import h5py
-        with h5py.File(path, 'w') as fp:
+        with _h5().File(path, 'w') as fp:
             fp.attrs['name'] = name
             for k, v in d.items():
                 if k != 'name':
@@ -232,7 +238,7 @@ def nf_ingest(name, datasets_dir, out_path=None, chunk=64):
         for idx, r in enumerate(regions):
             yy, xx = [c[0] for c in r['coordinates']], [c[1] for c in r['coordinates']]
             masks[idx, yy, xx] = 1
-    out_path = out_path or os.path.join(root, 'dataset.npz')
+    out_path = out_path or os.path.join(root, 'dataset.hdf5')
     return make_dataset(out_path, name, mean=mean, mx=mx, masks=masks)
 
 

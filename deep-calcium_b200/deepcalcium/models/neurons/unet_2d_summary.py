@@ -98,41 +98,79 @@ class UNetModel(object):
                                    beta2=o.beta_2, eps=o.epsilon)
         return m.cpu().numpy().tolist()
 
-    # ---- persistence: own container (h5py absent); arrays in Keras layouts and order
+    # ---- persistence.  *.hdf5 / *.h5: the Keras-2.0.6 model layout the reference writes (utils/keras_hdf5.py: readable by
+    # Keras' load_weights and by this package); anything else: an .npz container with the same arrays
     def save(self, filepath, include_optimizer=True):
         import torch
         e = self.engine
         w = e.get_weights_dict()
+        extra = {}
+        if include_optimizer:
+            torch.cuda.synchronize()
+            extra = dict(adam_m=e.adam_m.cpu().numpy(), adam_v=e.adam_v.cpu().numpy(), step_state=e.step_state.cpu().numpy())
+        if filepath.endswith(('.hdf5', '.h5')):
+            from ...utils.keras_hdf5 import write_keras_model
+            write_keras_model(filepath, self.spec, w, self.window_shape, optimizer=self.optimizer.get_config(), loss=self.loss,
+                              extra_attrs={'deepcalcium_iteration': np.int64(e.iteration)}, extra_datasets=extra)
+            return
         cfg = dict(format='deepcalcium-b200-v1', nb_filters_base=self.spec.nfb, prop_dropout_base=self.spec.drp,
                    upsampling_or_transpose=self.spec.up_mode, window_shape=list(self.window_shape),
                    optimizer=self.optimizer.get_config(), loss=self.loss, iteration=int(e.iteration),
                    weight_keys=list(w.keys()))
         arrays = {'w%03d' % i: v for i, v in enumerate(w.values())}
-        if include_optimizer:
-            torch.cuda.synchronize()
-            arrays['adam_m'] = e.adam_m.cpu().numpy()
-            arrays['adam_v'] = e.adam_v.cpu().numpy()
-            arrays['step_state'] = e.step_state.cpu().numpy()
+        arrays.update(extra)
         arrays['config'] = np.asarray(json.dumps(cfg))
         with open(filepath, 'wb') as fp:
             np.savez(fp, **arrays)
 
+    def load_weights(self, filepath):
+        """keras.Model.load_weights for a Keras-layout HDF5 file of the same graph"""
+        from ...utils.keras_hdf5 import read_keras_weights
+        spec, w, _ = read_keras_weights(filepath)
+        if (spec.nfb, spec.up_mode) != (self.spec.nfb, self.spec.up_mode):
+            raise ValueError('%s holds a %d-filter %s graph, this model is %d / %s'
+                             % (filepath, spec.nfb, spec.up_mode, self.spec.nfb, self.spec.up_mode))
+        self.engine.set_weights_dict(w)
+
+
+def _default_precision(spec, trainable):
+    # predict() loads with trainable=False: inference only -> fp16 activations (same tensor-core rate as bf16, 8x smaller
+    # logit error: meets the 1e-2 tolerance); a model that will be trained is bf16.  Widths that are not multiples of 32
+    # have no tensor-core path: fp32 check mode.
+    return 'fp32' if spec.nfb % 32 else ('bf16' if trainable else 'fp16')
+
 
 def load_model_with_new_input_shape(model_path, input_shape, compile=True, precision=None, trainable=True, **kwargs):
-    """Counterpart of deepcalcium/utils/keras_helpers.py:24-68: the graph is fully convolutional, so
-    the same weights simply run at another window size (no file rewriting)."""
+    """Counterpart of deepcalcium/utils/keras_helpers.py:24-68: the graph is fully convolutional, so the same weights
+    simply run at another window size (no file rewriting).  Reads Keras-2.x HDF5 model files (the reference's
+    checkpoints, the released unet2ds_model.hdf5) and this package's .npz containers."""
     import torch
+    from ...utils.keras_hdf5 import is_hdf5, read_keras_weights, read_extra
+    if is_hdf5(model_path):
+        spec, w, info = read_keras_weights(model_path)
+        model = UNetModel(tuple(input_shape), spec, precision=precision or _default_precision(spec, trainable))
+        model.engine.set_weights_dict(w)
+        tc = info.get('training_config') or {}
+        oc = (tc.get('optimizer_config') or {}).get('config') or {}
+        if oc:
+            model.optimizer = Adam(lr=oc.get('lr', 0.002), beta_1=oc.get('beta_1', 0.9), beta_2=oc.get('beta_2', 0.999),
+                                   epsilon=oc.get('epsilon', 1e-8))
+        if tc.get('loss') in _un.LOSS_IDS:
+            model.loss = tc['loss']
+        if compile:
+            ex = read_extra(model_path, ('adam_m', 'adam_v', 'step_state'))
+            if len(ex) == 3 and ex['adam_m'].shape == tuple(model.engine.adam_m.shape):
+                model.engine.adam_m.copy_(torch.from_numpy(ex['adam_m']))
+                model.engine.adam_v.copy_(torch.from_numpy(ex['adam_v']))
+                model.engine.step_state.copy_(torch.from_numpy(ex['step_state']))
+                model.engine.iteration = int(ex['step_state'][0])
+        return model
     with np.load(model_path, allow_pickle=False) as z:
         cfg = json.loads(str(z['config']))
         if cfg.get('format') != 'deepcalcium-b200-v1':
             raise ValueError('%s is not a deepcalcium-b200 model file' % model_path)
         spec = GraphSpec(cfg['nb_filters_base'], cfg['prop_dropout_base'], cfg['upsampling_or_transpose'])
-        if precision is None:
-            # predict() loads with trainable=False: inference only -> fp16 activations (same tensor-core rate as bf16, 8x
-            # smaller logit error: meets the 1e-2 tolerance); a model that will be trained is bf16.  Widths that are not
-            # multiples of 32 have no tensor-core path: fp32 check mode.
-            precision = 'fp32' if spec.nfb % 32 else ('bf16' if trainable else 'fp16')
-        model = UNetModel(tuple(input_shape), spec, precision=precision)
+        model = UNetModel(tuple(input_shape), spec, precision=precision or _default_precision(spec, trainable))
         model.engine.set_weights_dict({k: z['w%03d' % i] for i, k in enumerate(cfg['weight_keys'])})
         model.optimizer = Adam(**cfg['optimizer'])
         model.loss = cfg['loss']
@@ -274,7 +312,7 @@ class UNet2DSummary(object):
             logs.update(self._validate(model, S_summ, M_summ, names, ycval, shape_val, epoch))
             logs['lr'] = model.optimizer.lr
             # ModelCheckpoint every epoch (:423-424)
-            last_path = '%s/%d_model_%02d_%.3f.npz' % (self.cpdir, tic, epoch, logs['val_nf_f1_mean'])
+            last_path = '%s/%d_model_%02d_%.3f.hdf5' % (self.cpdir, tic, epoch, logs['val_nf_f1_mean'])
             model.save(last_path)
             # ReduceLROnPlateau(monitor='F1', factor=0.5, patience=5, min_lr=1e-4, mode='max') (:425-426)
             # Keras 2.0.6 order: the patience test comes BEFORE the wait counter is incremented, so the rate is halved
@@ -481,9 +519,15 @@ class UNet2DSummary(object):
                 logger.info('%s: prec=%.3lf, reca=%.3lf, incl=%.3lf, excl=%.3lf, comb=%.3lf' % (name, p, r, incl, excl, comb))
                 for k, v in enumerate((p, r, comb)):
                     scores[k] += v / len(dataset_paths)
-            if save:
-                save_path = '%s/%s_mp.npy' % (self.cpdir, name)
-                np.save(save_path, mp)
+            if save:                                   # outlined figure (:610-619): truth in blue when the dataset has masks
+                from PIL import Image
+                ds = open_dataset(dsp) if isinstance(dsp, str) and path.exists(dsp) else {}
+                if 'masks/raw' in ds:
+                    outlined = _un.mask_outlines(sl['summ'], [self.mask_summary_func(dsp), mp.round()], ['blue', 'red'])
+                else:
+                    outlined = _un.mask_outlines(sl['summ'], [mp.round()], ['red'])
+                save_path = '%s/%s_mp.png' % (self.cpdir, name)
+                Image.fromarray(outlined).save(save_path)
                 logger.info('Saved %s' % save_path)
 
         if len(dataset_paths):

@@ -390,8 +390,19 @@ def test_reference_surface_fit_predict_evaluate(cuda, tmp_path):
     assert os.path.exists(model_path) and len(hist['loss']) == 2 and 'val_nf_f1_mean' in hist
     with pytest.raises(AssertionError):
         model.predict(paths, model_path, window_shape=(256, 256))        # reference: only 512x512 (:565)
-    Mp, names = model.predict(paths, model_path, augmentation=True)
+    assert model_path.endswith('.hdf5')                # Keras-layout checkpoints, like the reference's ModelCheckpoint (:423)
+    Mp, names = model.predict(paths, model_path, augmentation=True, save=True)
     assert names == ['synthetic.00', 'synthetic.01'] and Mp[0].shape == (96, 112) and Mp[0].dtype == np.uint8
+    assert os.path.exists(str(tmp_path / 'cp' / 'synthetic.00_mp.png'))          # outlined figure (:610-619)
+    # the checkpoint is a Keras-2.0.6-layout file: same weights back, and a resumed fit keeps the optimizer state
+    from deepcalcium.utils.keras_hdf5 import read_keras_weights
+    from deepcalcium.models.neurons.unet_2d_summary import load_model_with_new_input_shape
+    spec_k, w_k, info = read_keras_weights(model_path)
+    assert spec_k.nfb == 32 and len(w_k) == 134 and info['keras_version'] == '2.0.6'
+    m2 = load_model_with_new_input_shape(model_path, (32, 32), compile=True, precision='fp32')
+    assert int(m2.engine.step_state[0].item()) == 6 and float(m2.engine.adam_v.abs().sum().item()) > 0
+    w_back = m2.engine.get_weights_dict()
+    assert all(np.array_equal(w_back[k], w_k[k]) for k in w_k)
     scores = model.evaluate(paths, model_path)
     assert set(scores.keys()) == {True, False}
 
