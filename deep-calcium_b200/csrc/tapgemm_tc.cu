@@ -57,6 +57,7 @@ struct TcFwdParams {
   int stages;
   int f16;                  // 16-bit element format: 0 = bf16, 1 = fp16
   __nv_bfloat16* out;
+  __nv_bfloat16* pool_out;  // conv3x3 only: 2x2 max-pooled copy [N][GH/2][GW/2][Ntot] written by the epilogue (or null)
   const float* scale;
   const float* shift;
 };
@@ -114,6 +115,64 @@ __device__ __forceinline__ void epilogue_swapped(uint32_t t_addr, int npix, bool
   }
 }
 
+// Swapped orientation with the 2x2 max-pool of the encoder blocks (unet_2d_summary.py:176-194) folded in: the tile holds
+// whole pairs of image rows (bw pixels wide, bw % 32 == 0), so a warp drains the 32-pixel chunk at tile position m0 (an
+// even row) together with the chunk at m0 + bw (the row below), transposes both through its 4 KB shared-memory tile and
+// writes the two activation rows plus the 16 pooled pixels.  16-bit outputs only.
+template <typename PixFn, typename PoolFn>
+__device__ __forceinline__ void epilogue_swapped_pool(uint32_t t_addr, int npix, int bw, bool warp_valid, float sc, float sh,
+                                                      int relu, void* out_base, void* pool_base, uint8_t* stage, int lane,
+                                                      PixFn pix_index, PoolFn pool_index, int f16) {
+  uint16_t* st = reinterpret_cast<uint16_t*>(stage);            // [2 rows][32 px][32 ch]
+  for (int m0 = 0; m0 < npix; m0 += 32) {
+    if ((m0 / bw) & 1) continue;                                 // odd tile rows are drained with their partner
+    uint32_t r0[32], r1[32];
+    tmem_ld_32x32b_x32(t_addr + m0, r0);
+    tmem_ld_32x32b_x32(t_addr + m0 + bw, r1);
+    tmem_ld_wait();
+    if (!warp_valid) continue;
+    __syncwarp();
+    uint16_t pooled[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      float a0 = fmaf(__uint_as_float(r0[i]), sc, sh), a1 = fmaf(__uint_as_float(r0[i + 1]), sc, sh);
+      float b0 = fmaf(__uint_as_float(r1[i]), sc, sh), b1 = fmaf(__uint_as_float(r1[i + 1]), sc, sh);
+      if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); b0 = fmaxf(b0, 0.f); b1 = fmaxf(b1, 0.f); }
+      st[i * 32 + lane] = cvt16(a0, f16);
+      st[(i + 1) * 32 + lane] = cvt16(a1, f16);
+      st[1024 + i * 32 + lane] = cvt16(b0, f16);
+      st[1024 + (i + 1) * 32 + lane] = cvt16(b1, f16);
+      // rounding is monotonic: the maximum of the rounded values is the rounded maximum
+      pooled[i >> 1] = cvt16(fmaxf(fmaxf(a0, a1), fmaxf(b0, b1)), f16);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {                                // 2 rows x 32 px x 4 chunks of 8 channels
+      const int idx = lane + 32 * q, row = idx >> 7, px = (idx >> 2) & 31, chunk = idx & 3;
+      const long long o = pix_index(m0 + row * bw + px);
+      if (o >= 0)
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out_base) + o + chunk * 8) =
+            *reinterpret_cast<const uint4*>(st + row * 1024 + px * 32 + chunk * 8);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) st[k * 32 + lane] = pooled[k];
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {                                // 16 pooled px x 4 chunks
+      const int idx = lane + 32 * q, pp = idx >> 2, chunk = idx & 3;
+      const long long o = pool_index(m0 + 2 * pp);
+      if (o >= 0)
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(pool_base) + o + chunk * 8) =
+            *reinterpret_cast<const uint4*>(st + pp * 32 + chunk * 8);
+    }
+    __syncwarp();
+  }
+}
+
+// POOL: the epilogues also write the 2x2 max-pooled copy (p.pool_out); a separate instantiation so that the plain
+// kernel keeps its register allocation (the pooled epilogue cost the plain path ~10 % when it was a runtime branch)
+template <bool POOL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                       const __grid_constant__ CUtensorMap mapB, const TcFwdParams p) {
@@ -281,8 +340,19 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
         };
         mbar_wait(&bar_tfull[acc], acc_phase);
         tc_fence_after();
-        epilogue_swapped(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols), 256, warp_valid, sc, sh,
-                         p.relu, p.out_f32, p.out, s_stage[quarter], lane, pix_index, p.f16);
+        if constexpr (POOL) {
+          // pooled index of tile position mm (even row, even column of the tile; the host guarantees even GH, GW, bw, bh)
+          auto pool_index = [&](int mm) -> long long {
+            const int gw2 = tw * p.bw + mm % p.bw, gh2 = th * p.bh + (mm / p.bw) % p.bh, n2 = tn * p.bn + mm / (p.bw * p.bh);
+            if (gw2 >= p.GW || gh2 >= p.GH || n2 >= p.N) return -1;
+            return (long long)((((size_t)n2 * (p.GH >> 1) + (gh2 >> 1)) * (p.GW >> 1) + (gw2 >> 1)) * p.OC + cw);
+          };
+          epilogue_swapped_pool(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols), 256, p.bw, warp_valid, sc,
+                                sh, p.relu, p.out, p.pool_out, s_stage[quarter], lane, pix_index, pool_index, p.f16);
+        } else {
+          epilogue_swapped(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols), 256, warp_valid, sc, sh,
+                           p.relu, p.out_f32, p.out, s_stage[quarter], lane, pix_index, p.f16);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_tempty[acc]);
@@ -334,10 +404,33 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
             }
             st_global_v8(orow_f + c + j, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
           }
-        } else if (valid) {
+        } else if (valid || POOL) {
           uint32_t pk[16];
           bn_relu_pack32(r, s_scale + cbase + c, s_shift + cbase + c, p.relu, pk, p.f16);
-          store_pk16(orow + c, pk);
+          if (valid) store_pk16(orow + c, pk);
+          if constexpr (POOL) {
+            // 2x2 max-pool folded in (unet_2d_summary.py:176-194): the tile holds whole 2x2 windows (even bw, bh and even
+            // image sizes, checked on the host).  The quartet exchanges the packed 32-channel blocks through its 8 KB of
+            // the (otherwise unused) transpose buffer; named barrier 1 + eset = the 128 threads of this quartet.
+            uint4* stg = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(s_stage) + eset * 8192);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) stg[m * 4 + q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + eset) : "memory");
+            const int lx = m % p.bw, ly = (m / p.bw) % p.bh;
+            if (valid && !(lx & 1) && !(ly & 1)) {
+              uint32_t mx[16];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 b4 = stg[(m + 1) * 4 + q], c4 = stg[(m + p.bw) * 4 + q], d4 = stg[(m + p.bw + 1) * 4 + q];
+                mx[4 * q] = max16x2(max16x2(pk[4 * q], b4.x, p.f16), max16x2(c4.x, d4.x, p.f16), p.f16);
+                mx[4 * q + 1] = max16x2(max16x2(pk[4 * q + 1], b4.y, p.f16), max16x2(c4.y, d4.y, p.f16), p.f16);
+                mx[4 * q + 2] = max16x2(max16x2(pk[4 * q + 2], b4.z, p.f16), max16x2(c4.z, d4.z, p.f16), p.f16);
+                mx[4 * q + 3] = max16x2(max16x2(pk[4 * q + 3], b4.w, p.f16), max16x2(c4.w, d4.w, p.f16), p.f16);
+              }
+              store_pk16(p.pool_out + (((size_t)n * (p.GH >> 1) + (gh >> 1)) * (p.GW >> 1) + (gw >> 1)) * p.OC + cbase + c, mx);
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + eset) : "memory");
+          }
         }
       }
       tc_fence_before();
@@ -1305,7 +1398,8 @@ static int run_tc_flat(const TapGeom& g, const void* s0, int C0, const void* s1,
 }
 
 static int run_tc_generic(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* B, int Nout, void* out,
-                          int out_pitch, const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st);
+                          int out_pitch, const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st,
+                          void* pool_out = nullptr);
 
 // fuse != nullptr: the caller wants the head and/or the 2x2 max-pool computed in the conv epilogue; returns
 // DCB_ERR_UNSUPPORTED (without launching) when this layer shape cannot take the fused path.
@@ -1335,11 +1429,17 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
     TcStripParams sp;
     size_t dyn = 0;
     const bool fused = fuse != nullptr;
-    if (fused && (out_f32 || (fuse->pool_out && Nout > 64))) return fail(DCB_ERR_UNSUPPORTED, "fused epilogue not available for this layer");
-    bool strip_ok = plan_strip(g, C0, C1, Nout, Nout, fused, sp, dyn);
+    if (fused && out_f32) return fail(DCB_ERR_UNSUPPORTED, "fused epilogue not available for this layer");
+    // a pool-only fusion that the strip kernel cannot take (more than 64 output channels, narrow images) goes to the
+    // generic kernel's pooled epilogue
+    const bool pool_only = fused && fuse->pool_out && !fuse->head_kernel;
+    bool strip_ok = !(fused && fuse->pool_out && Nout > 64) && plan_strip(g, C0, C1, Nout, Nout, fused, sp, dyn);
     const bool no_nsplit = !policy(DCB_POLICY_NSPLIT);
     if (!strip_ok && !fused && !no_nsplit && Nout == 64) strip_ok = plan_strip(g, C0, C1, Nout, 32, fused, sp, dyn);
-    if (fused && !strip_ok) return fail(DCB_ERR_UNSUPPORTED, "fused epilogue not available for this layer");
+    if (fused && !strip_ok) {
+      if (pool_only) return run_tc_generic(g, s0, C0, s1, C1, B, Nout, out, Nout, scale, shift, relu, out_f32, st, fuse->pool_out);
+      return fail(DCB_ERR_UNSUPPORTED, "fused epilogue not available for this layer");
+    }
     if (strip_ok) {
       sp.relu = relu; sp.out_f32 = out_f32; sp.out = reinterpret_cast<__nv_bfloat16*>(out); sp.scale = scale; sp.shift = shift;
       sp.f16 = g.f16;
@@ -1418,7 +1518,8 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
 
 // generic kernel: Nout output channels written with a channel pitch of out_pitch (>= Nout) starting at `out`
 static int run_tc_generic(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* B, int Nout, void* out,
-                          int out_pitch, const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st) {
+                          int out_pitch, const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st,
+                          void* pool_out) {
   TcFwdParams p;
   memset(&p, 0, sizeof(p));
   const int ntaps = g.ntaps;
@@ -1442,7 +1543,8 @@ static int run_tc_generic(const TapGeom& g, const void* s0, int C0, const void* 
   {
     const long long px = (long long)g.N * g.GH * g.GW;
     // measured (profiles/r1_layer_ab.txt): pays for conv3x3 with 64..128 output channels, not for the 1-tap convT GEMMs
-    p.swap = (p.mode == 0 && swap_allowed(Nout) && px / 256 * cdiv(p.Ntot, 128) >= sm_count() / 2) ? 1 : 0;
+    // the pooled epilogue is cheaper in the pixels-as-M orientation (two epilogue quartets; profiles/r2_pool_ab.txt)
+    p.swap = (p.mode == 0 && !pool_out && swap_allowed(Nout) && px / 256 * cdiv(p.Ntot, 128) >= sm_count() / 2) ? 1 : 0;
   }
   const int TM = p.swap ? 256 : TC_BM;
   // ---- M tiling
@@ -1457,6 +1559,12 @@ static int run_tc_generic(const TapGeom& g, const void* s0, int C0, const void* 
     p.tiles_w = cdiv(g.GW, p.bw); p.tiles_h = cdiv((long long)g.N * g.GH, p.bh); p.tiles_n = 1;
   }
   const int num_mtiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  if (pool_out) {
+    // pooled epilogue: conv3x3 only, 16-bit outputs, whole 2x2 windows inside every tile
+    if (p.mode != 0 || out_f32 || (g.GH & 1) || (g.GW & 1) || (p.bw & 1) || (p.bh & 1) || (p.swap && p.bw % 32 != 0) || out_pitch != Nout)
+      return fail(DCB_ERR_UNSUPPORTED, "fused max-pool not available for this layer shape");
+    p.pool_out = reinterpret_cast<__nv_bfloat16*>(pool_out);
+  }
   // ---- N tiling: largest tile that still gives every SM work
   // an N tile may span several convT sub-positions (the epilogue resolves them per 32-column block)
   // Cost model from the issue-rate probes (profiles/r1_umma_rate_probe.log): one M=128 MMA occupies the tensor pipe for
@@ -1516,16 +1624,18 @@ static int run_tc_generic(const TapGeom& g, const void* s0, int C0, const void* 
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
     if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const int num_tiles = num_mtiles * (p.swap ? cdiv(p.Ntot, 128) : p.Ntot / BN);
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  tapgemm_tc_fwd_kernel<<<grid, TC_THREADS, dyn_smem, st>>>(mA0, mA1, mB, p);
+  if (p.pool_out) tapgemm_tc_fwd_kernel<true><<<grid, TC_THREADS, dyn_smem, st>>>(mA0, mA1, mB, p);
+  else tapgemm_tc_fwd_kernel<false><<<grid, TC_THREADS, dyn_smem, st>>>(mA0, mA1, mB, p);
   g_launches += 1;
   DCB_LAUNCH_OK("tapgemm_tc_fwd_kernel");
-  note_kernel(p.swap ? "generic_swap" : "generic");
+  note_kernel(p.pool_out ? (p.swap ? "generic_swap_pool" : "generic_pool") : (p.swap ? "generic_swap" : "generic"));
   return DCB_OK;
 }
 

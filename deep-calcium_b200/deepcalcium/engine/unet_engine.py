@@ -54,9 +54,9 @@ class UNetEngine(object):
         self._weights_dirty = True
         self._sessions = {}
         self._prep_tables = {}
-        # encoder blocks whose max-pool is folded into the conv epilogue.  Measured: pays at full resolution only
-        # (enc0b); DCB_POOL_FUSED=enc0b,enc1b made no difference for the 256^2 block (bench 1008.9 img/s either way)
-        self._pool_fused = tuple(x for x in os.environ.get('DCB_POOL_FUSED', 'enc0b').split(',') if x)
+        # every encoder block's 2x2 max-pool is folded into the producing conv's epilogue (strip kernel: Cout <= 64 on wide
+        # rows; generic kernel: both orientations); no standalone pooling launch in inference
+        self._pool_fused = ('enc0b', 'enc1b', 'enc2b', 'enc3b')
         self.iteration = 0
         self.launches = 0
         self.comm = None          # engine.dist.Comm for data-parallel training (None = single GPU)
@@ -561,8 +561,12 @@ class UNetEngine(object):
         s['y'].copy_(y_dev)
         loss_id = nat.LOSS_IDS[loss] if isinstance(loss, str) else int(loss)
         key = ('train', loss_id, float(lr), bool(dropout), beta1, beta2, eps)
-        self._run_graphed(s['tta_graphs'], key,
-                          lambda: self._train_step_enqueue(s, loss_id, lr, dropout, beta1, beta2, eps))
+        # the weights-as-M orientation of the generic kernel pays on the 512^2 inference shapes but not on the small
+        # images of a training crop (profiles/r2_swap_sweep.txt): pinned off while the step is enqueued / captured
+        def enqueue():
+            with nat.policy(swap_min_cout=0):
+                self._train_step_enqueue(s, loss_id, lr, dropout, beta1, beta2, eps)
+        self._run_graphed(s['tta_graphs'], key, enqueue)
         self.iteration += 1
         self._weights_dirty = True
         return self.metrics

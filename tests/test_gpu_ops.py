@@ -197,7 +197,11 @@ def test_convT2x2_fwd_dgrad_wgrad(cuda, precision, case):
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
-@pytest.mark.parametrize('shape', [(2, 16, 128, 32, 32), (1, 6, 256, 64, 64), (1, 8, 24, 32, 32)])
+@pytest.mark.parametrize('shape', [(2, 16, 128, 32, 32), (1, 6, 256, 64, 64), (1, 8, 24, 32, 32),
+                                   # pooled epilogue of the generic kernel: pixels-as-M tiles (several tile shapes, an N tile
+                                   # narrower than Cout), weights-as-M tiles of 128x2 and 64x4 pixels
+                                   (2, 32, 32, 128, 128), (3, 8, 8, 256, 256), (8, 64, 64, 128, 256),
+                                   (8, 128, 128, 64, 128), (16, 64, 64, 64, 128), (1, 16, 128, 64, 128)])
 def test_conv3x3_fused_pool_and_head_equal_the_unfused_composition(cuda, precision, shape):
     """dcb_conv3x3_fwd_fused (max-pool / softmax head folded into the conv epilogue) must reproduce the separate
     kernels - including shapes where the library falls back to the unfused composition.  fp32: exactly.  bf16: the
@@ -220,7 +224,9 @@ def test_conv3x3_fused_pool_and_head_equal_the_unfused_composition(cuda, precisi
     logit = torch.empty(N, H, W, device='cuda'); prob = torch.empty(N, H, W, device='cuda')
     ops.head_fwd(y, hk, hb, logit, prob)
     y2 = torch.empty_like(y); pool2 = torch.empty_like(pool)
+    from deepcalcium import _native as nat
     ops.conv3x3_fwd_fused(x, None, wf, y2, scale, shift, True, pool_out=pool2)
+    print('fused pool %s %s -> %s' % (precision, shape, nat.last_kernel() if precision == 'bf16' else 'fp32 composition'))
     def same(a, b):
         if precision == 'fp32':
             return torch.equal(a, b)
