@@ -1,88 +1,102 @@
 // First layer of the U-Net: Conv2D(3x3,'same') on the 1-channel summary image
 // (unet_2d_summary.py:169-172).  K = 9 is far too small for the tensor pipe; the layer is
-// bound by writing its [N,H,W,Cout] output, so it runs on CUDA cores: one thread per pixel,
-// weights broadcast from shared memory, 16-byte coalesced stores.
+// bound by writing its [N,H,W,Cout] output, so it runs on CUDA cores with the weights in registers.
 #include "elementwise.cuh"
 
 namespace dcb {
 extern unsigned long long g_launches;
 void launch_reduce_splits(const float* part, int splits, size_t n, float* out, cudaStream_t st);
 
-// One thread per pixel, weights broadcast from shared memory.  A warp's 32 pixels x COUT channels form ONE
-// contiguous run of the NHWC output, so the results are staged through a per-warp shared-memory tile and written
-// with fully coalesced 16-byte stores (a direct per-thread store would issue 32 partial-sector requests per
-// instruction and is ~3x slower for this write-bound layer).
+// v2 (round 2).  The first version kept the weights in shared memory and was bound by the shared-memory pipe (ncu: l1tex
+// 90 %, 73 us for 8 x 512^2 against a 21 us HBM-write floor).  Here every thread keeps ITS weights in registers: a thread
+// owns 8 output channels (9 x 8 weights, scale, shift) of one pixel column and walks down TH rows of a [TH x TW] tile
+// whose (TH + 2) x (TW + 2) input window sits in shared memory (zero-filled outside the image = the 'same' padding);
+// the 3 x 3 input window slides down in registers (3 shared-memory loads per pixel, broadcast to the COUT / 8 threads of
+// that pixel).  The COUT / 8 threads of a pixel write 16 bytes each, so a warp stores a contiguous run of the NHWC row.
+__device__ __forceinline__ void cp_async_f32_zfill(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  const int n = valid ? 4 : 0;                                // src-size 0: nothing is read, the 4 bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+
 template <typename T, int COUT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 conv3x3_c1_fwd_kernel(const float* __restrict__ x, int N, int H, int W, const float* __restrict__ w,
                       const float* __restrict__ scale, const float* __restrict__ shift, int relu, T* __restrict__ out) {
-  __shared__ __align__(16) float ws[9 * COUT];
-  __shared__ __align__(16) float sc[COUT], sh[COUT];
-  constexpr int ROWB = COUT * (int)sizeof(T);                 // bytes per pixel
-  constexpr int PITCH = ROWB + 16;                            // padded row: conflict-free 16-byte accesses
-  constexpr int U = ROWB <= 64 ? 2 : 1;                       // pixels per thread (stage tile must fit 48 KB of static smem)
-  constexpr int PXW = 32 * U;                                 // pixels per warp and iteration
-  __shared__ __align__(16) uint8_t stage[8][PXW * PITCH];
-  for (int i = threadIdx.x; i < 9 * COUT; i += blockDim.x) ws[i] = w[i];
-  for (int i = threadIdx.x; i < COUT; i += blockDim.x) { sc[i] = scale ? scale[i] : 1.f; sh[i] = shift ? shift[i] : 0.f; }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint8_t* st = stage[warp];
-  const long long M = (long long)N * H * W;
-  // The kernel is bound by the shared-memory pipe (ncu: l1tex 90 %): the weight broadcasts dominate, so every thread
-  // computes U = 2 pixels (lane and lane + 32 of the warp's 64) per weight load.  Block-uniform trip count.
-  for (long long base = ((long long)blockIdx.x * 8 + warp) * PXW; base < M; base += (long long)gridDim.x * 8 * PXW) {
-    float v[U][9];
+  constexpr int TPP = COUT / 8;                               // threads per pixel (8 channels = one 16-byte store each)
+  constexpr int TW = 256 / TPP;                               // pixel columns per tile
+  constexpr int TH = 16;                                      // rows per tile
+  constexpr int WIN = (TH + 2) * (TW + 2);
+  // The input windows are double buffered and filled with cp.async (zero fill = the 'same' padding): the window of
+  // tile i + 1 streams in while tile i is computed.  Without it the kernel spent 30 % of its issue slots waiting for
+  // the staging loads (ncu source view, profiles/r2_c1_ncu.txt).
+  __shared__ float s_in[2][WIN];
+  const int cg = threadIdx.x % TPP, col = threadIdx.x / TPP;
+  float2 wr[9][4];                                            // this thread's 8 channels of the 9 taps, as fp32 pairs
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long m = base + lane + 32 * u;
-      const bool mv = m < M;
-      const long long mm = mv ? m : 0;
-      const int wq = (int)(mm % W), hq = (int)((mm / W) % H);
-      const float* img = x + (mm - (long long)hq * W - wq);
+  for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int ih = hq + t / 3 - 1, iw = wq + t % 3 - 1;
-        v[u][t] = (mv && ih >= 0 && ih < H && iw >= 0 && iw < W) ? img[(long long)ih * W + iw] : 0.f;
+    for (int q = 0; q < 4; ++q) wr[t][q] = make_float2(w[t * COUT + cg * 8 + 2 * q], w[t * COUT + cg * 8 + 2 * q + 1]);
+  float2 sc2[4], sh2[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    sc2[q] = scale ? make_float2(scale[cg * 8 + 2 * q], scale[cg * 8 + 2 * q + 1]) : make_float2(1.f, 1.f);
+    sh2[q] = shift ? make_float2(shift[cg * 8 + 2 * q], shift[cg * 8 + 2 * q + 1]) : make_float2(0.f, 0.f);
+  }
+  const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
+  const int num_tiles = N * tiles_h * tiles_w;
+  auto prefetch = [&](int tile, int buf) {
+    if (tile < num_tiles) {
+      const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
+      const int h0 = th * TH, w0 = tw * TW;
+      const float* img = x + (size_t)n * H * W;
+      for (int i = threadIdx.x; i < WIN; i += 256) {
+        const int r = i / (TW + 2), c = i - r * (TW + 2);
+        const int ih = h0 + r - 1, iw = w0 + c - 1;
+        const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+        cp_async_f32_zfill(&s_in[buf][i], ok ? img + (size_t)ih * W + iw : img, ok);
       }
     }
-    // packed fp32x2 FMAs: two output channels per instruction
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int buf = 0;
+  prefetch(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, buf ^= 1) {
+    prefetch(tile + gridDim.x, buf ^ 1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
+    const int h0 = th * TH, w0 = tw * TW;
+    if (w0 + col < W) {
+      const float* sp = s_in[buf] + col;                      // window columns col .. col + 2
+      float a0 = sp[0], a1 = sp[1], a2 = sp[2];               // input row h - 1
+      float b0 = sp[TW + 2], b1 = sp[TW + 3], b2 = sp[TW + 4];   // input row h
+      T* orow = out + (((size_t)n * H + h0) * W + (w0 + col)) * COUT + cg * 8;
+#pragma unroll 4
+      for (int r = 0; r < TH; ++r) {
+        if (h0 + r >= H) break;
+        const float* s2 = sp + (r + 2) * (TW + 2);
+        const float c0 = s2[0], c1 = s2[1], c2 = s2[2];       // input row h + 1
+        const float v[9] = {a0, a1, a2, b0, b1, b2, c0, c1, c2};
+        float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-    for (int c0 = 0; c0 < COUT; c0 += 4) {
-      float2 a[U][2];
+        for (int t = 0; t < 9; ++t) {
+          const float2 vv = make_float2(v[t], v[t]);
 #pragma unroll
-      for (int u = 0; u < U; ++u) { a[u][0] = make_float2(0.f, 0.f); a[u][1] = make_float2(0.f, 0.f); }
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const float4 wv = *reinterpret_cast<const float4*>(&ws[t * COUT + c0]);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const float2 vv = make_float2(v[u][t], v[u][t]);
-          a[u][0] = ffma2(vv, make_float2(wv.x, wv.y), a[u][0]);
-          a[u][1] = ffma2(vv, make_float2(wv.z, wv.w), a[u][1]);
+          for (int q = 0; q < 4; ++q) acc[q] = ffma2(vv, wr[t][q], acc[q]);
         }
-      }
-      const float4 s4 = *reinterpret_cast<const float4*>(&sc[c0]), h4 = *reinterpret_cast<const float4*>(&sh[c0]);
+        float o[8];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        float2 r0 = ffma2(a[u][0], make_float2(s4.x, s4.y), make_float2(h4.x, h4.y));
-        float2 r1 = ffma2(a[u][1], make_float2(s4.z, s4.w), make_float2(h4.z, h4.w));
-        if (relu) { r0.x = fmaxf(r0.x, 0.f); r0.y = fmaxf(r0.y, 0.f); r1.x = fmaxf(r1.x, 0.f); r1.y = fmaxf(r1.y, 0.f); }
-        store4<T>(reinterpret_cast<T*>(st + (lane + 32 * u) * PITCH) + c0, make_float4(r0.x, r0.y, r1.x, r1.y));
+        for (int q = 0; q < 4; ++q) {
+          const float2 y2 = ffma2(acc[q], sc2[q], sh2[q]);
+          o[2 * q] = relu ? fmaxf(y2.x, 0.f) : y2.x;
+          o[2 * q + 1] = relu ? fmaxf(y2.y, 0.f) : y2.y;
+        }
+        store8<T>(orow + (size_t)r * W * COUT, o);
+        a0 = b0; a1 = b1; a2 = b2; b0 = c0; b1 = c1; b2 = c2;
       }
     }
-    __syncwarp();
-    // 64 pixels x ROWB bytes = one contiguous block of the output
-    const long long npix = (M - base) < PXW ? (M - base) : PXW;
-    uint8_t* dst = reinterpret_cast<uint8_t*>(out + base * COUT);
-#pragma unroll
-    for (int q = 0; q < PXW * ROWB / 16 / 32; ++q) {
-      const int idx = q * 32 + lane;                           // 16-byte chunk index within the block
-      const int px = idx / (ROWB / 16), ch = idx % (ROWB / 16);
-      if (px < npix)
-        *reinterpret_cast<uint4*>(dst + (size_t)idx * 16) = *reinterpret_cast<const uint4*>(st + px * PITCH + ch * 16);
-    }
-    __syncwarp();
+    __syncthreads();                                          // this window may be overwritten by the prefetch after next
   }
 }
 
@@ -148,16 +162,14 @@ using namespace dcb;
 template <typename T>
 static int launch_c1_fwd(const float* x, int N, int H, int W, const float* w, int Cout, const float* scale,
                          const float* shift, int relu, T* out, cudaStream_t st) {
-  const long long M = (long long)N * H * W;
-  long long grid = (M + 255) / 256;
-  if (grid > (long long)sm_count() * 16) grid = (long long)sm_count() * 16;
+  // persistent: two 256-thread CTAs per SM walk the [16 x (2048 / Cout)]-pixel tiles
+  auto tiles = [&](int tw) { return (long long)N * cdiv(H, 16) * cdiv(W, tw); };
+  auto grid_for = [&](long long t) { const long long cap = 2LL * sm_count(); return (int)(t < cap ? t : cap); };
   switch (Cout) {
-    case 8: conv3x3_c1_fwd_kernel<T, 8><<<(int)grid, 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break;
-    case 16: conv3x3_c1_fwd_kernel<T, 16><<<(int)grid, 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break;
-    case 32: conv3x3_c1_fwd_kernel<T, 32><<<(int)grid, 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break;
-    case 64:
-      if constexpr (sizeof(T) == 2) { conv3x3_c1_fwd_kernel<T, 64><<<(int)grid, 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break; }
-      return fail(DCB_ERR_UNSUPPORTED, "dcb_conv3x3_c1_fwd: Cout=64 is built for bf16 output only");
+    case 8: conv3x3_c1_fwd_kernel<T, 8><<<grid_for(tiles(256)), 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break;
+    case 16: conv3x3_c1_fwd_kernel<T, 16><<<grid_for(tiles(128)), 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break;
+    case 32: conv3x3_c1_fwd_kernel<T, 32><<<grid_for(tiles(64)), 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break;
+    case 64: conv3x3_c1_fwd_kernel<T, 64><<<grid_for(tiles(32)), 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break;
     default: return fail(DCB_ERR_UNSUPPORTED, "dcb_conv3x3_c1_fwd: Cout=%d unsupported (8,16,32,64)", Cout);
   }
   g_launches += 1;
