@@ -606,6 +606,63 @@ head_loss_bwd_kernel(const T* __restrict__ x, long long M, int C, const float* _
   if (threadIdx.x == 0) { atomicAdd(&dwb[2 * C + 1], (double)accb); atomicAdd(&dwb[2 * C], -(double)accb); }
 }
 
+// Same contract for C == 32 (nb_filters_base = 32, the benchmarked model): every thread keeps its own 32 partial kernel
+// gradients in registers over all its pixels and the CTA reduces them ONCE through shared memory - the generic kernel
+// above pays 32 warp reductions (160 shuffles) per 32 pixels inside the loop (48 us of the 32-crop step).
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_loss_bwd_c32_kernel(const T* __restrict__ x, long long M, const float* __restrict__ w, const uint8_t* __restrict__ yt,
+                         const float* __restrict__ prob, const double* __restrict__ sums, int loss, long long M_total,
+                         float* __restrict__ dx, double* __restrict__ dwb) {
+  constexpr int C = 32;
+  __shared__ float wd[C];
+  __shared__ float red[8][C + 1];
+  if (threadIdx.x < C) wd[threadIdx.x] = w[threadIdx.x * 2 + 1] - w[threadIdx.x * 2];
+  __syncthreads();
+  const double invM = 1.0 / (double)M_total;
+  float acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.f;
+  float accb = 0.f;
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    const float p = prob[m];
+    const float g = loss_grad_wrt_p(loss, p, (float)yt[m], sums, invM);
+    const float dz1 = p * (1.f - p) * g;
+    accb += dz1;
+#pragma unroll
+    for (int c = 0; c < C; c += 8) {
+      float v[8];
+      load8<T>(x + m * C + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[c + j] = fmaf(v[j], dz1, acc[c + j]);
+      store4<float>(dx + m * C + c, make_float4(dz1 * wd[c], dz1 * wd[c + 1], dz1 * wd[c + 2], dz1 * wd[c + 3]));
+      store4<float>(dx + m * C + c + 4, make_float4(dz1 * wd[c + 4], dz1 * wd[c + 5], dz1 * wd[c + 6], dz1 * wd[c + 7]));
+    }
+  }
+  // warp reduction of the 33 partials (once per CTA), then across the 8 warps through shared memory
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float r = warp_sum(acc[c]);
+    if (lane == 0) red[warp][c] = r;
+  }
+  accb = warp_sum(accb);
+  if (lane == 0) red[warp][C] = accb;
+  __syncthreads();
+  if (threadIdx.x <= C) {
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) t += red[wv][threadIdx.x];
+    if (threadIdx.x < C) {
+      atomicAdd(&dwb[threadIdx.x * 2 + 1], (double)t);
+      atomicAdd(&dwb[threadIdx.x * 2], -(double)t);
+    } else {
+      atomicAdd(&dwb[2 * C + 1], (double)t);
+      atomicAdd(&dwb[2 * C], -(double)t);
+    }
+  }
+}
+
 // loss value + the 7 Keras batch metrics (unet_2d_summary.py:398-399) from the 8 sums -> out[8] floats:
 // [0]=loss [1]=F1 [2]=prec [3]=reca [4]=dice [5]=dicesq [6]=posyt [7]=posyp
 __global__ void head_metrics_kernel(const double* __restrict__ sums, long long M, int loss, float* __restrict__ out,
@@ -973,7 +1030,11 @@ extern "C" int dcb_head_loss_bwd(int dtype, const void* x, long long M, int C, c
                 "dcb_head_loss_bwd: bad arguments");
   DCB_CHECK_ARG(loss >= 0 && loss <= 3, "dcb_head_loss_bwd: unknown loss id %d", loss);
   int grid = ew_grid(M, 256); if (grid > sm_count() * 4) grid = sm_count() * 4;
-  DISPATCH_T(dtype, head_loss_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, M, C, w, yt, prob, sums, loss, M_total, (float*)dx, dwb_accum);)
+  if (C == 32 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    DISPATCH_T(dtype, head_loss_bwd_c32_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, M, w, yt, prob, sums, loss, M_total, (float*)dx, dwb_accum);)
+  } else {
+    DISPATCH_T(dtype, head_loss_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, M, C, w, yt, prob, sums, loss, M_total, (float*)dx, dwb_accum);)
+  }
   DCB_LAUNCH_OK("head_loss_bwd_kernel");
   head_metrics_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(sums, M_total, loss, metrics_out, dwb_accum, C, dw_out);
   g_launches += 2;

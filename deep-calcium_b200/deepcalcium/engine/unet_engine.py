@@ -407,7 +407,21 @@ class UNetEngine(object):
         fused_bn = bool(nat.get_policy('fused_bn')) and (world == 1 or self.peers is not None)
         if fused_bn:
             self.bn_sync.zero_()
-        self._prepare_weights(for_training=True)
+        # the 16-bit kernel-layout copies of the updated weights are rebuilt on the side stream while the first layer
+        # (which reads the fp32 master weights) and its BatchNorm run; the first tensor-core conv waits for them
+        main = torch.cuda.current_stream(self.dev)
+        side = self._side_stream() if self.overlap_wgrad else None
+        prep_done = None
+        if side is not None and self.tc:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                self._prepare_weights(for_training=True)
+                prep_done = torch.cuda.Event()
+                prep_done.record(side)
+        else:
+            self._prepare_weights(for_training=True)
         layer_id = {blk.name: i for i, blk in enumerate(spec.blocks)}
         for i, un in enumerate(self._ups):
             layer_id[un] = len(spec.blocks) + i
@@ -424,9 +438,15 @@ class UNetEngine(object):
                 if blk.cin == 1 and self.tc:
                     ops.conv3x3_c1_fwd(s['x'], self.w_fwd[n], raw[n], None, bias, False)
                 else:
+                    if prep_done is not None:
+                        main.wait_event(prep_done)
+                        prep_done = None
                     ops.conv3x3_fwd(act[a], act[b] if b else None, self.w_fwd[n], raw[n], None, bias, False)
                 mom = BN_MOMENTUM_CONV
             else:
+                if prep_done is not None:
+                    main.wait_event(prep_done)
+                    prep_done = None
                 ops.convT2x2_fwd(act[a], self.w_fwd[n], raw[n], None, bias, False)
                 mom = BN_MOMENTUM_UP
             st = self.bn[n]
