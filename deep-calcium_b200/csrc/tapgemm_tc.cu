@@ -380,6 +380,59 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
       mbar_wait(&bar_tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN);
+      if constexpr (!POOL) {
+        // Two 32-column blocks per step: their TMEM loads, BN / ReLU / pack arithmetic and stores are independent
+        // instruction streams (each scheduler hosts two epilogue warps, so a block-at-a-time loop is latency bound -
+        // the short-K convT tiles spend 3x longer in this epilogue than in their MMAs).  A block never straddles a
+        // convT sub-position because Cz % 32 == 0; (z, ch) = sub-position and channel of a block, advanced without divisions.
+        int z = ng0 / p.Cz, ch = ng0 - z * p.Cz;
+        const bool subpos = p.Cz < p.Ntot;
+        auto out_index = [&](int zz, int cc) -> size_t {
+          const int ody = subpos ? (zz >> 1) : p.ody, odx = subpos ? (zz & 1) : p.odx;
+          return ((orow_y + ody) * p.OW + (ocol_x + odx)) * p.OC + cc;
+        };
+        auto store_f32 = [&](const uint32_t (&r)[32], int cc, size_t o) {
+          float* orow_f = reinterpret_cast<float*>(p.out) + o;
+#pragma unroll
+          for (int q0 = 0; q0 < 32; q0 += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float f = fmaf(__uint_as_float(r[q0 + q]), s_scale[cc + q0 + q], s_shift[cc + q0 + q]);
+              if (p.relu) f = fmaxf(f, 0.f);
+              v[q] = __float_as_uint(f);
+            }
+            st_global_v8(orow_f + q0, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+          }
+        };
+        for (int c = 0; c < p.BN; c += 64) {
+          const bool two = c + 32 < p.BN;
+          const int z0 = z, ch0 = ch;
+          ch += 32; if (ch == p.Cz) { ch = 0; ++z; }
+          const int z1 = z, ch1 = ch;
+          if (two) { ch += 32; if (ch == p.Cz) { ch = 0; ++z; } }
+          const size_t o0 = out_index(z0, ch0), o1 = out_index(z1, ch1);
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(t_addr + c, r0);
+          if (two) tmem_ld_32x32b_x32(t_addr + c + 32, r1);
+          tmem_ld_wait();
+          if (!valid) continue;
+          if (p.out_f32) {
+            store_f32(r0, ch0, o0);
+            if (two) store_f32(r1, ch1, o1);
+          } else if (two) {
+            uint32_t pk0[16], pk1[16];
+            bn_relu_pack32(r0, s_scale + ch0, s_shift + ch0, p.relu, pk0, p.f16);
+            bn_relu_pack32(r1, s_scale + ch1, s_shift + ch1, p.relu, pk1, p.f16);
+            store_pk16(p.out + o0, pk0);
+            store_pk16(p.out + o1, pk1);
+          } else {
+            uint32_t pk0[16];
+            bn_relu_pack32(r0, s_scale + ch0, s_shift + ch0, p.relu, pk0, p.f16);
+            store_pk16(p.out + o0, pk0);
+          }
+        }
+      } else
       for (int c = 0; c < p.BN; c += 32) {
         // a 32-column block never straddles a sub-position because Cz % 32 == 0
         const int gcol = ng0 + c;
@@ -866,6 +919,131 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
     for (int q = 0; q < 16; ++q) { pool_prev[0][q] = 0; pool_prev[1][q] = 0; }
     uint32_t j = 0;
     long long u = u_begin;
+    if constexpr (FOLD) {
+      // Folded mode hands the epilogue PAIRS of output rows (one tfull / tempty barrier per pair, see the MMA warp), so a
+      // quartet drains both rows of its pair together: the two TMEM loads, the BN / ReLU / pack arithmetic and the stores
+      // of the two rows are independent instruction streams (twice the ILP of the row-at-a-time loop, which left each
+      // scheduler with one latency-bound warp), the per-channel scale / shift are fetched from shared memory once per
+      // pair, and the vertical half of the 2x2 max-pool is a register-to-register maximum - no state carried between rows.
+      const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t pmask = ((uint32_t)nacc >> 1) - 1u;
+      for (int n, h0, rows, w0; next_strip(u, n, h0, rows, w0);) {
+        for (int t = 0; t < rows; t += 2, j += 2) {
+          const uint32_t jp = j >> 1;
+          if ((int)(jp & 1u) != eset) continue;                  // ST_QUARTETS == 2: alternate pairs
+          const uint32_t ta = t_lane + (j & (uint32_t)(nacc - 1)) * (uint32_t)p.Cout, tb = ta + (uint32_t)p.Cout;
+          const int bar_i = (int)(jp & pmask);
+          const size_t opix_a = ((size_t)n * p.H + (h0 + t)) * p.W + (w0 + m), opix_b = opix_a + p.W;
+          const size_t oidx_a = opix_a * p.OC + p.n0, oidx_b = opix_b * p.OC + p.n0;
+          mbar_wait(&bar_tfull[bar_i], (j >> nacc_sh) & 1u);
+          tc_fence_after();
+          if (p.out_f32) {                                       // gradient tensors (dgrad): fp32 stores, row by row
+#pragma unroll 1
+            for (int rr = 0; rr < 2; ++rr) {
+              float* orow_f = reinterpret_cast<float*>(p.out) + (rr ? oidx_b : oidx_a);
+              for (int c = 0; c < p.Cout; c += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32((rr ? tb : ta) + c, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q0 = 0; q0 < 32; q0 += 8) {
+                  uint32_t v[8];
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    float f = fmaf(__uint_as_float(r[q0 + q]), s_scale[c + q0 + q], s_shift[c + q0 + q]);
+                    if (p.relu) f = fmaxf(f, 0.f);
+                    v[q] = __float_as_uint(f);
+                  }
+                  st_global_v8(orow_f + c + q0, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+                }
+              }
+            }
+          } else {
+            __nv_bfloat16* orow_a = p.out + oidx_a;
+            __nv_bfloat16* orow_b = p.out + oidx_b;
+            float zacc_a = head_b, zacc_b = head_b;
+            for (int c = 0; c < p.Cout; c += 32) {
+              uint32_t ra[32], rb[32];
+              tmem_ld_32x32b_x32(ta + c, ra);
+              tmem_ld_32x32b_x32(tb + c, rb);
+              tmem_ld_wait();
+              if (FUSED && p.head_kernel && !p.need_y && !p.pool_out) {
+                // dec0b at inference: the activation is consumed by the 1x1 head only and never stored, so it is not
+                // rounded to 16 bits either: BN + ReLU + dot product stay in (packed) fp32
+                float2 za0 = make_float2(0.f, 0.f), za1 = make_float2(0.f, 0.f), zb0 = za0, zb1 = za0;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                  const float4 sc = *reinterpret_cast<const float4*>(s_scale + c + 4 * g);
+                  const float4 sh = *reinterpret_cast<const float4*>(s_shift + c + 4 * g);
+                  const float4 wd = *reinterpret_cast<const float4*>(s_wd + c + 4 * g);
+                  const float2 sc0 = make_float2(sc.x, sc.y), sc1 = make_float2(sc.z, sc.w);
+                  const float2 sh0 = make_float2(sh.x, sh.y), sh1 = make_float2(sh.z, sh.w);
+                  float2 a0 = ffma2(make_float2(__uint_as_float(ra[4 * g]), __uint_as_float(ra[4 * g + 1])), sc0, sh0);
+                  float2 a1 = ffma2(make_float2(__uint_as_float(ra[4 * g + 2]), __uint_as_float(ra[4 * g + 3])), sc1, sh1);
+                  float2 b0 = ffma2(make_float2(__uint_as_float(rb[4 * g]), __uint_as_float(rb[4 * g + 1])), sc0, sh0);
+                  float2 b1 = ffma2(make_float2(__uint_as_float(rb[4 * g + 2]), __uint_as_float(rb[4 * g + 3])), sc1, sh1);
+                  if (p.relu) {
+                    a0.x = fmaxf(a0.x, 0.f); a0.y = fmaxf(a0.y, 0.f); a1.x = fmaxf(a1.x, 0.f); a1.y = fmaxf(a1.y, 0.f);
+                    b0.x = fmaxf(b0.x, 0.f); b0.y = fmaxf(b0.y, 0.f); b1.x = fmaxf(b1.x, 0.f); b1.y = fmaxf(b1.y, 0.f);
+                  }
+                  za0 = ffma2(a0, make_float2(wd.x, wd.y), za0);
+                  za1 = ffma2(a1, make_float2(wd.z, wd.w), za1);
+                  zb0 = ffma2(b0, make_float2(wd.x, wd.y), zb0);
+                  zb1 = ffma2(b1, make_float2(wd.z, wd.w), zb1);
+                }
+                zacc_a += (za0.x + za0.y) + (za1.x + za1.y);
+                zacc_b += (zb0.x + zb0.y) + (zb1.x + zb1.y);
+                continue;
+              }
+              uint32_t pka[16], pkb[16];
+              bn_relu_pack32_x2(ra, rb, s_scale + c, s_shift + c, p.relu, pka, pkb, p.f16);
+              if (FUSED && p.head_kernel) {     // head on the rounded (stored) values, four partial sums per row
+                float za[4] = {0.f, 0.f, 0.f, 0.f}, zb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                  const float4 wd = *reinterpret_cast<const float4*>(s_wd + c + 4 * g);
+                  const float2 f0 = unpack16x2(pka[2 * g], p.f16), f1 = unpack16x2(pka[2 * g + 1], p.f16);
+                  const float2 g0 = unpack16x2(pkb[2 * g], p.f16), g1 = unpack16x2(pkb[2 * g + 1], p.f16);
+                  za[0] = fmaf(f0.x, wd.x, za[0]); za[1] = fmaf(f0.y, wd.y, za[1]);
+                  za[2] = fmaf(f1.x, wd.z, za[2]); za[3] = fmaf(f1.y, wd.w, za[3]);
+                  zb[0] = fmaf(g0.x, wd.x, zb[0]); zb[1] = fmaf(g0.y, wd.y, zb[1]);
+                  zb[2] = fmaf(g1.x, wd.z, zb[2]); zb[3] = fmaf(g1.y, wd.w, zb[3]);
+                }
+                zacc_a += (za[0] + za[1]) + (za[2] + za[3]);
+                zacc_b += (zb[0] + zb[1]) + (zb[2] + zb[3]);
+              }
+              if (!FUSED || p.need_y) {
+                store_pk16(orow_a + c, pka);
+                store_pk16(orow_b + c, pkb);
+              }
+              if (FUSED && p.pool_out) {
+                // 2x2 max-pool (unet_2d_summary.py:176-194): the vertical partner is the other row of the pair, the
+                // horizontal partner the neighbouring lane.  The two lanes of a window split the 32 channels: each sends
+                // the half its partner will store and keeps the other one - 8 shuffles and one full 32-byte sector per lane.
+                const bool odd = (lane & 1) != 0;
+                uint32_t mx[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const uint32_t lo = max16x2(pka[q], pkb[q], p.f16), hi = max16x2(pka[8 + q], pkb[8 + q], p.f16);
+                  const uint32_t got = __shfl_xor_sync(0xffffffffu, odd ? lo : hi, 1);
+                  mx[q] = max16x2(odd ? hi : lo, got, p.f16);
+                }
+                __nv_bfloat16* prow = p.pool_out + ((((size_t)n * (p.H >> 1) + ((h0 + t) >> 1)) * (p.W >> 1) + ((w0 + m) >> 1)) * p.Cout
+                                                    + c + (odd ? 16 : 0));
+                st_global_v8(prow, mx[0], mx[1], mx[2], mx[3], mx[4], mx[5], mx[6], mx[7]);
+              }
+            }
+            if (FUSED && p.head_kernel) {
+              if (p.logit) { p.logit[opix_a] = zacc_a; p.logit[opix_b] = zacc_b; }
+              if (p.prob) { p.prob[opix_a] = 1.f / (1.f + __expf(-zacc_a)); p.prob[opix_b] = 1.f / (1.f + __expf(-zacc_b)); }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_tempty[bar_i]);
+        }
+      }
+    } else
     for (int n, h0, rows, w0; eset < nsets && next_strip(u, n, h0, rows, w0);) {
       for (int t = 0; t < rows; ++t, ++j) {
         if ((int)((j >> 1) % (uint32_t)nsets) != eset) continue;

@@ -280,5 +280,37 @@ __device__ __forceinline__ void bn_relu_pack32(const uint32_t (&r)[32], const fl
   }
 }
 
+// the same for two accumulator rows at once (the two rows of a folded strip pair): one scale / shift fetch serves both,
+// and the two rows are independent dependency chains
+__device__ __forceinline__ void bn_relu_pack32_x2(const uint32_t (&ra)[32], const uint32_t (&rb)[32], const float* s_sc,
+                                                  const float* s_sh, int relu, uint32_t (&pka)[16], uint32_t (&pkb)[16],
+                                                  int f16) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float4 sc = *reinterpret_cast<const float4*>(s_sc + 4 * g);
+    const float4 sh = *reinterpret_cast<const float4*>(s_sh + 4 * g);
+    const float2 sc0 = make_float2(sc.x, sc.y), sc1 = make_float2(sc.z, sc.w);
+    const float2 sh0 = make_float2(sh.x, sh.y), sh1 = make_float2(sh.z, sh.w);
+    const float2 a0 = ffma2(make_float2(__uint_as_float(ra[4 * g]), __uint_as_float(ra[4 * g + 1])), sc0, sh0);
+    const float2 a1 = ffma2(make_float2(__uint_as_float(ra[4 * g + 2]), __uint_as_float(ra[4 * g + 3])), sc1, sh1);
+    const float2 b0 = ffma2(make_float2(__uint_as_float(rb[4 * g]), __uint_as_float(rb[4 * g + 1])), sc0, sh0);
+    const float2 b1 = ffma2(make_float2(__uint_as_float(rb[4 * g + 2]), __uint_as_float(rb[4 * g + 3])), sc1, sh1);
+    if (f16) {
+      const __half2 z = __floats2half2_rn(0.f, 0.f);
+      __half2 ha0 = __float22half2_rn(a0), ha1 = __float22half2_rn(a1), hb0 = __float22half2_rn(b0), hb1 = __float22half2_rn(b1);
+      if (relu) { ha0 = __hmax2(ha0, z); ha1 = __hmax2(ha1, z); hb0 = __hmax2(hb0, z); hb1 = __hmax2(hb1, z); }
+      pka[2 * g] = *reinterpret_cast<uint32_t*>(&ha0); pka[2 * g + 1] = *reinterpret_cast<uint32_t*>(&ha1);
+      pkb[2 * g] = *reinterpret_cast<uint32_t*>(&hb0); pkb[2 * g + 1] = *reinterpret_cast<uint32_t*>(&hb1);
+    } else {
+      const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+      __nv_bfloat162 ha0 = __float22bfloat162_rn(a0), ha1 = __float22bfloat162_rn(a1), hb0 = __float22bfloat162_rn(b0),
+                     hb1 = __float22bfloat162_rn(b1);
+      if (relu) { ha0 = __hmax2(ha0, z); ha1 = __hmax2(ha1, z); hb0 = __hmax2(hb0, z); hb1 = __hmax2(hb1, z); }
+      pka[2 * g] = *reinterpret_cast<uint32_t*>(&ha0); pka[2 * g + 1] = *reinterpret_cast<uint32_t*>(&ha1);
+      pkb[2 * g] = *reinterpret_cast<uint32_t*>(&hb0); pkb[2 * g + 1] = *reinterpret_cast<uint32_t*>(&hb1);
+    }
+  }
+}
+
 }  // namespace tc
 }  // namespace dcb
