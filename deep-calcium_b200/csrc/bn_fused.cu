@@ -10,6 +10,7 @@
 // INSIDE the kernel over NVLink - each rank stores its totals into every peer's exchange slot (peer-mapped memory),
 // publishes a flag carrying the step number, waits for the peers' flags and adds the slots in rank order - instead of
 // an NCCL all-reduce between two launches.
+#include <cooperative_groups.h>
 #include "elementwise.cuh"
 
 namespace dcb {
@@ -283,12 +284,14 @@ bn_train_bwd_kernel(const BnBwdParams p) {
   for (int i = 0; i < VEC; ++i) { sc[i] = p.scale[c + i]; sh[i] = p.shift[c + i]; mu[i] = p.mean[c + i]; }
   auto masked = [&](long long r, float (&g)[VEC], const float (&v)[VEC]) {
     if (p.p_drop > 0.f) {
-      const unsigned long long i4 = (unsigned long long)((r * C + c) >> 2);
-      const float4 k0 = dropout_scale4(seed, p.layer, i4, p.p_drop);
-      g[0] *= k0.x; g[1] *= k0.y; g[2] *= k0.z; g[3] *= k0.w;
       if constexpr (VEC == 8) {
-        const float4 k1 = dropout_scale4(seed, p.layer, i4 + 1, p.p_drop);
-        g[4] *= k1.x; g[5] *= k1.y; g[6] *= k1.z; g[7] *= k1.w;
+        float k[8];
+        dropout_scale8(seed, p.layer, (unsigned long long)((r * C + c) >> 3), p.p_drop, k);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] *= k[i];
+      } else {
+        const float4 k0 = dropout_scale4(seed, p.layer, (unsigned long long)((r * C + c) >> 2), p.p_drop);
+        g[0] *= k0.x; g[1] *= k0.y; g[2] *= k0.z; g[3] *= k0.w;
       }
     }
 #pragma unroll
@@ -385,6 +388,353 @@ bn_train_bwd_kernel(const BnBwdParams p) {
     for (int j = 0; j < VEC; ++j) o[j] = fmaf(sc[j], g[j], fmaf(k1[j], v[j] - mu[j], k0[j]));
     storev<T, VEC>(draw + r * C + c, o);
   }
+}
+
+
+// ================================================================================ channel-slab kernels (clusters)
+// The grid-barrier kernels above pay ~2-3 us per barrier plus a global round trip of the per-CTA partials, which is
+// most of the time of the small deep-level tensors (2 - 16 MB: ~15-25 us per launch against a 1-5 us bandwidth floor).
+// Here the tensor [M][C] is cut into channel SLABS of CW channels (16 or 32 bytes per row = whole sectors) and each slab
+// into S row ranges: a thread-block CLUSTER of S CTAs owns one slab, every CTA reduces its rows, the S partial vectors
+// are summed in rank order through distributed shared memory (one hardware cluster barrier, ~0.3 us), and each CTA
+// applies the result to the rows it just read.  No global synchronisation, no workspace, bit-reproducible sums.
+// Used when the slabs are short enough (levels 1-4 of a training crop); the full-resolution level (C = 32) would need
+// sub-sector slabs and stays on the grid-barrier kernels.
+namespace cg = cooperative_groups;
+#ifndef DCB_SLAB_THREADS
+#define DCB_SLAB_THREADS 512
+#endif
+constexpr int SLAB_THREADS = DCB_SLAB_THREADS;   // 16 warps: the dropout layers are issue bound (Philox), one CTA per SM
+constexpr int SLAB_PITCH = 17;      // floats per thread in the CTA reduction buffer (16 + 1: conflict-free columns)
+
+struct SlabGeom { int CW, S; long long rows_per_cta; };
+
+// per-thread partials (8 channels x {s, q}) -> cta_tot[2*CW] doubles (channel-major: [0,CW) = s, [CW,2CW) = q)
+__device__ __forceinline__ void slab_cta_reduce(const float (&s)[8], const float (&q)[8], int CW, float* sh, double* cta_tot) {
+  const int lanes_c = CW >> 3, rows_par = SLAB_THREADS / lanes_c;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sh[threadIdx.x * SLAB_PITCH + i] = s[i]; sh[threadIdx.x * SLAB_PITCH + 8 + i] = q[i]; }
+  __syncthreads();
+  // 2*CW outputs, tpo = 256 / (2*CW) threads per output, 16 entries each, then a shuffle tree over the tpo lanes
+  const int nout = 2 * CW, tpo = SLAB_THREADS / nout;
+  const int o = threadIdx.x / tpo, k = threadIdx.x % tpo;
+  const int comp = o / CW, ch = o % CW, lc = ch >> 3, i = ch & 7;
+  double acc = 0;
+  for (int rr = k; rr < rows_par; rr += tpo) acc += (double)sh[(rr * lanes_c + lc) * SLAB_PITCH + comp * 8 + i];
+  for (int off = tpo >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (k == 0) cta_tot[o] = acc;
+}
+
+// cta_tot of every CTA of the cluster, summed in rank order -> s_tot (identical in all CTAs)
+__device__ __forceinline__ void slab_cluster_sum(cg::cluster_group& cluster, double* cta_tot, double* s_tot, int nout, int S) {
+  cluster.sync();
+  if ((int)threadIdx.x < nout) {
+    double acc = 0;
+    for (int rk = 0; rk < S; ++rk) acc += cluster.map_shared_rank(cta_tot, rk)[threadIdx.x];
+    s_tot[threadIdx.x] = acc;
+  }
+  // nobody leaves (or overwrites cta_tot) while a peer may still be reading it
+  cluster.sync();
+}
+
+template <typename T, bool POOL>
+__global__ void __launch_bounds__(SLAB_THREADS)
+bn_slab_fwd_kernel(const BnFwdParams p, const SlabGeom gm) {
+  __shared__ float sh[SLAB_THREADS * SLAB_PITCH];
+  __shared__ double cta_tot[64], s_tot[64];
+  __shared__ float s_sc[32], s_sh[32];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = p.C, CW = gm.CW, S = gm.S;
+  const int g = blockIdx.x / S, rk = blockIdx.x % S;
+  const T* __restrict__ x = reinterpret_cast<const T*>(p.x);
+  const int lanes_c = CW >> 3, rows_par = SLAB_THREADS / lanes_c;
+  const int tc = threadIdx.x % lanes_c, tr = threadIdx.x / lanes_c;
+  const int c = g * CW + tc * 8;
+  const long long r0 = (long long)rk * gm.rows_per_cta;
+  long long r1 = r0 + gm.rows_per_cta; if (r1 > p.M) r1 = p.M;
+  {
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+        long long r = r0 + tr;
+    for (; r + 3LL * rows_par < r1; r += 4LL * rows_par) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load8<T>(x + (r + (long long)u * rows_par) * C + c, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += v[u][i]; q[i] = fmaf(v[u][i], v[u][i], q[i]); }
+    }
+    for (; r < r1; r += rows_par) {
+      float v[8];
+      load8<T>(x + r * C + c, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] = fmaf(v[i], v[i], q[i]); }
+    }
+    slab_cta_reduce(s, q, CW, sh, cta_tot);
+  }
+  slab_cluster_sum(cluster, cta_tot, s_tot, 2 * CW, S);
+  __syncthreads();
+  if ((int)threadIdx.x < CW) {
+    const int ch = g * CW + threadIdx.x;
+    const double mean = s_tot[threadIdx.x] / (double)p.M_total;
+    double var = s_tot[CW + threadIdx.x] / (double)p.M_total - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+    const float sc = p.gamma[ch] * rstd;
+    const float shv = p.beta[ch] - (float)mean * sc;
+    s_sc[threadIdx.x] = sc; s_sh[threadIdx.x] = shv;
+    if (rk == 0) {
+      p.scale[ch] = sc; p.shift[ch] = shv; p.mean[ch] = (float)mean; p.rstd[ch] = rstd;
+      if (p.moving_mean) {   // Keras: moving <- moving*m + batch*(1-m), biased batch variance
+        p.moving_mean[ch] = p.moving_mean[ch] * p.momentum + (float)mean * (1.f - p.momentum);
+        p.moving_var[ch] = p.moving_var[ch] * p.momentum + (float)var * (1.f - p.momentum);
+      }
+    }
+  }
+  __syncthreads();
+  float sc[8], shv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sc[i] = s_sc[tc * 8 + i]; shv[i] = s_sh[tc * 8 + i]; }
+  unsigned long long seed = p.seed;
+  if (p.seed_dev) seed ^= *p.seed_dev;
+  T* __restrict__ y = reinterpret_cast<T*>(p.y);
+  auto apply = [&](long long r, float (&v)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = fmaf(v[j], sc[j], shv[j]);
+      if (p.relu) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (p.p_drop > 0.f) {
+      float k[8];
+      dropout_scale8(seed, p.layer, (unsigned long long)((r * C + c) >> 3), p.p_drop, k);     // same counters as the grid-barrier kernel
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= k[j];
+    }
+  };
+  if constexpr (!POOL) {
+    long long r = r0 + tr;
+    for (; r + 3LL * rows_par < r1; r += 4LL * rows_par) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load8<T>(x + (r + (long long)u * rows_par) * C + c, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        apply(r + (long long)u * rows_par, v[u]);
+        store8<T>(y + (r + (long long)u * rows_par) * C + c, v[u]);
+      }
+    }
+    for (; r < r1; r += rows_par) {
+      float v[8];
+      load8<T>(x + r * C + c, v);
+      apply(r, v);
+      store8<T>(y + r * C + c, v);
+    }
+  } else {
+    // the CTA's row range is a whole number of image-row pairs (host check): pooled pixel lp of the range = rows
+    // base, base+1, base+W, base+W+1 with base = r0 + (lp / OW) * 2W + 2 * (lp % OW); its flat pooled index is r0/4 + lp
+    T* __restrict__ pool = reinterpret_cast<T*>(p.pool);
+    const int OW = p.W >> 1;
+    const long long npool = (r1 - r0) >> 2;
+    auto window = [&](long long lp, float (&v)[4][8]) {
+      const long long base = r0 + (lp / OW) * 2LL * p.W + 2LL * (lp % OW);
+      float m[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long r = base + (k >> 1) * p.W + (k & 1);
+        apply(r, v[k]);
+        store8<T>(y + r * C + c, v[k]);
+        // pooling compares the STORED (rounded) activations, like the standalone kernel that reads them back
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float rv = to_f32<T>(from_f32<T>(v[k][j]));
+          m[j] = k == 0 ? rv : fmaxf(m[j], rv);
+        }
+      }
+      store8<T>(pool + ((r0 >> 2) + lp) * C + c, m);
+    };
+    auto fetch = [&](long long lp, float (&v)[4][8]) {
+      const long long base = r0 + (lp / OW) * 2LL * p.W + 2LL * (lp % OW);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) load8<T>(x + (base + (k >> 1) * p.W + (k & 1)) * C + c, v[k]);
+    };
+    long long lp = tr;
+    for (; lp + rows_par < npool; lp += 2LL * rows_par) {        // two windows = eight 16-byte loads in flight
+      float va[4][8], vb[4][8];
+      fetch(lp, va);
+      fetch(lp + rows_par, vb);
+      window(lp, va);
+      window(lp + rows_par, vb);
+    }
+    for (; lp < npool; lp += rows_par) {
+      float va[4][8];
+      fetch(lp, va);
+      window(lp, va);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SLAB_THREADS)
+bn_slab_bwd_kernel(const BnBwdParams p, const SlabGeom gm) {
+  __shared__ float sh[SLAB_THREADS * SLAB_PITCH];
+  __shared__ double cta_tot[64], s_tot[64];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = p.C, CW = gm.CW, S = gm.S;
+  const int g = blockIdx.x / S, rk = blockIdx.x % S;
+  const T* __restrict__ x = reinterpret_cast<const T*>(p.x);
+  unsigned long long seed = p.seed;
+  if (p.seed_dev) seed ^= *p.seed_dev;
+  const int lanes_c = CW >> 3, rows_par = SLAB_THREADS / lanes_c;
+  const int tc = threadIdx.x % lanes_c, tr = threadIdx.x / lanes_c;
+  const int c = g * CW + tc * 8;
+  const long long r0 = (long long)rk * gm.rows_per_cta;
+  long long r1 = r0 + gm.rows_per_cta; if (r1 > p.M) r1 = p.M;
+  float sc[8], shv[8], mu[8], rs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sc[i] = p.scale[c + i]; shv[i] = p.shift[c + i]; mu[i] = p.mean[c + i]; rs[i] = p.rstd[c + i]; }
+  auto masked = [&](long long r, float (&gd)[8], const float (&v)[8]) {
+    if (p.p_drop > 0.f) {
+      float k[8];
+      dropout_scale8(seed, p.layer, (unsigned long long)((r * C + c) >> 3), p.p_drop, k);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gd[j] *= k[j];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (fmaf(v[i], sc[i], shv[i]) <= 0.f) gd[i] = 0.f;
+  };
+  {
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+    long long r = r0 + tr;
+    constexpr int UB = 2;                                          // rows (48 bytes of loads each) in flight per thread
+    for (; r + (UB - 1LL) * rows_par < r1; r += (long long)UB * rows_par) {
+      float gq[UB][8], vq[UB][8];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        load8<float>(p.dy + (r + (long long)u * rows_par) * p.ldy + p.offy + c, gq[u]);
+        load8<T>(x + (r + (long long)u * rows_par) * C + c, vq[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        masked(r + (long long)u * rows_par, gq[u], vq[u]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += gq[u][i]; q[i] = fmaf(gq[u][i], (vq[u][i] - mu[i]) * rs[i], q[i]); }
+      }
+    }
+    for (; r < r1; r += rows_par) {
+      float g0[8], v0[8];
+      load8<float>(p.dy + r * p.ldy + p.offy + c, g0);
+      load8<T>(x + r * C + c, v0);
+      masked(r, g0, v0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += g0[i]; q[i] = fmaf(g0[i], (v0[i] - mu[i]) * rs[i], q[i]); }
+    }
+    slab_cta_reduce(s, q, CW, sh, cta_tot);
+  }
+  slab_cluster_sum(cluster, cta_tot, s_tot, 2 * CW, S);
+  __syncthreads();
+  float k1[8], k0[8];
+  {
+    const double invM = 1.0 / (double)p.M_total;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const double scd = (double)sc[i], m1 = s_tot[tc * 8 + i] * invM, m2 = s_tot[CW + tc * 8 + i] * invM;
+      k1[i] = (float)(-scd * (double)rs[i] * m2);
+      k0[i] = (float)(-scd * m1);
+    }
+  }
+  if (rk == 0 && (int)threadIdx.x < CW) {
+    const int ch = g * CW + threadIdx.x;
+    if (p.dbeta) p.dbeta[ch] = (float)(s_tot[threadIdx.x] * (double)p.dgb_scale);
+    if (p.dgamma) p.dgamma[ch] = (float)(s_tot[CW + threadIdx.x] * (double)p.dgb_scale);
+  }
+  T* __restrict__ draw = reinterpret_cast<T*>(p.draw);
+  long long r = r0 + tr;
+  constexpr int UB = 2;
+  for (; r + (UB - 1LL) * rows_par < r1; r += (long long)UB * rows_par) {
+    float gq[UB][8], vq[UB][8];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      load8<float>(p.dy + (r + (long long)u * rows_par) * p.ldy + p.offy + c, gq[u]);
+      load8<T>(x + (r + (long long)u * rows_par) * C + c, vq[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      float o[8];
+      masked(r + (long long)u * rows_par, gq[u], vq[u]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(sc[j], gq[u][j], fmaf(k1[j], vq[u][j] - mu[j], k0[j]));
+      store8<T>(draw + (r + (long long)u * rows_par) * C + c, o);
+    }
+  }
+  for (; r < r1; r += rows_par) {
+    float g0[8], v0[8], o[8];
+    load8<float>(p.dy + r * p.ldy + p.offy + c, g0);
+    load8<T>(x + r * C + c, v0);
+    masked(r, g0, v0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(sc[j], g0[j], fmaf(k1[j], v0[j] - mu[j], k0[j]));
+    store8<T>(draw + r * C + c, o);
+  }
+}
+
+// slab geometry for an [M][C] tensor of `esize`-byte elements; row_gran: the row ranges must be multiples of it
+// (2W for the pooled forward).  false: not eligible (slabs too long, or no row split with whole ranges).
+// Measured on B200 (profiles/r2_bn_slab_bench.txt): the slab kernels win where the fixed costs dominate - tensors up to
+// ~4 MB forward (7.6 vs 13.4 us at 2 MB, 13.4 vs 15.6 us at 4 MB) and ~2 MB backward (8.3 vs 13.4 us) - and lose on larger
+// ones, where a row-contiguous partition with four CTAs per SM streams better than one 16/32-byte column per CTA.
+// policy 2 = wherever the geometry allows (tests).
+static bool slab_geom(long long M, int C, int esize, long long row_gran, long long auto_max_bytes, SlabGeom& gm) {
+  if (!policy(DCB_POLICY_BN_SLAB) || C % 8 != 0) return false;
+  if (policy(DCB_POLICY_BN_SLAB) == 1 && M * C * esize > auto_max_bytes) return false;
+  const long long max_bytes = 160 * 1024;
+  for (int CW : {32 / esize, 16 / esize}) {                     // whole 32-byte sectors per row first, then half sectors
+    if (CW < 8 || C % CW != 0) continue;
+    const int groups = C / CW;
+    for (int S = 16; S >= 1; S >>= 1) {
+      if ((long long)groups * S > sm_count() + 16 && S > 1) continue;   // about one CTA per SM
+      if (M % S != 0 || (M / S) % row_gran != 0) continue;
+      const long long rows = M / S;
+      if (rows * CW * esize > max_bytes) break;                 // a smaller S only makes the slabs longer
+      if (rows < SLAB_THREADS / (CW / 8) && S > 1) continue;    // fewer rows than one pass of the CTA: split less
+      gm.CW = CW; gm.S = S; gm.rows_per_cta = rows;
+      return true;
+    }
+  }
+  return false;
+}
+
+template <typename K, typename P>
+static int launch_slab(K kernel, const P& p, const SlabGeom& gm, cudaStream_t st, const char* name) {
+  // clusters of 16 CTAs are "non-portable": opt in once per kernel (the template instances share one function-pointer
+  // type, so the set of prepared kernels is keyed by address)
+  static const void* prepared[8];
+  static int n_prepared = 0;
+  bool done = false;
+  for (int i = 0; i < n_prepared; ++i) done = done || prepared[i] == reinterpret_cast<const void*>(kernel);
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "cluster-size attribute for %s failed: %s", name, cudaGetErrorString(e));
+    if (n_prepared < 8) prepared[n_prepared++] = reinterpret_cast<const void*>(kernel);
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)((p.C / gm.CW) * gm.S), 1, 1);
+  cfg.blockDim = dim3(SLAB_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)gm.S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p, gm);
+  if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e));
+  g_launches += 1;
+  return DCB_OK;
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------
@@ -484,6 +834,14 @@ extern "C" int dcb_bn_train_fwd(int dtype, const void* x, long long M, int C, lo
   p.seed_dev = seed_dev; p.layer = layer; p.sync = sync;
   if (int e = fill_peers(p.pv, peers, C)) return e;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    SlabGeom gm;
+    if (p.pv.world == 1 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+        slab_geom(M, C, dtype == DCB_F32 ? 4 : 2, pool_out ? 2LL * W : 1, 5LL << 20, gm)) {
+      if (pool_out) { BN_DISPATCH(dtype, return launch_slab(bn_slab_fwd_kernel<T, true>, p, gm, st, "bn_slab_fwd_kernel");) }
+      else { BN_DISPATCH(dtype, return launch_slab(bn_slab_fwd_kernel<T, false>, p, gm, st, "bn_slab_fwd_kernel");) }
+    }
+  }
   if (vec == 8) {
     if (pool_out) { BN_DISPATCH(dtype, return (launch_bn_fwd<T, 8, true>(p, workspace, workspace_bytes, st));) }
     else { BN_DISPATCH(dtype, return (launch_bn_fwd<T, 8, false>(p, workspace, workspace_bytes, st));) }
@@ -528,6 +886,12 @@ extern "C" int dcb_bn_train_bwd(int dtype, const float* dy, int ldy, int offy, c
   p.layer = layer; p.dgb_scale = dgb_scale; p.dgamma = dgamma; p.dbeta = dbeta; p.sync = sync;
   if (int e = fill_peers(p.pv, peers, C)) return e;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    SlabGeom gm;
+    if (p.pv.world == 1 && (reinterpret_cast<uintptr_t>(draw) & 15) == 0 && slab_geom(M, C, dtype == DCB_F32 ? 4 : 2, 1, 5LL << 19, gm)) {
+      BN_DISPATCH(dtype, return launch_slab(bn_slab_bwd_kernel<T>, p, gm, st, "bn_slab_bwd_kernel");)
+    }
+  }
   if (vec == 8) { BN_DISPATCH(dtype, return (launch_bn_bwd<T, 8>(p, workspace, workspace_bytes, st));) }
   else { BN_DISPATCH(dtype, return (launch_bn_bwd<T, 4>(p, workspace, workspace_bytes, st));) }
 }

@@ -126,17 +126,29 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 
-// keep-mask scale for 4 consecutive elements starting at flat index `idx4*4`:
-// 1/keep if uniform >= p_drop else 0.   (seed, layer id) -> key; element index -> counter.
+// Dropout keep-mask: element e draws a 16-bit uniform - half-word (e % 8) of Philox4x32-10(counter = e / 8, key = seed,
+// extra counter word = layer id) - and is kept when it is >= floor(p_drop * 65536); kept elements are scaled by
+// 1 / (1 - p_drop).  One Philox call therefore serves 8 consecutive elements (one 16-byte bf16 vector): the 7 dropout
+// layers of a training step were issue bound on the generator when it served only 4 (32-bit uniforms).
+__device__ __forceinline__ void dropout_scale8(unsigned long long seed, uint32_t layer, unsigned long long idx8, float p_drop,
+                                               float (&k)[8]) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)idx8, (uint32_t)(idx8 >> 32), layer, 0u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float inv = 1.f / (1.f - p_drop);
+  const uint32_t thr = (uint32_t)(p_drop * 65536.f);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    k[2 * i] = (w[i] & 0xffffu) >= thr ? inv : 0.f;
+    k[2 * i + 1] = (w[i] >> 16) >= thr ? inv : 0.f;
+  }
+}
+// 4 consecutive elements starting at flat index idx4 * 4 (the lower or upper half of their group of 8)
 __device__ __forceinline__ float4 dropout_scale4(unsigned long long seed, uint32_t layer, unsigned long long idx4,
                                                  float p_drop) {
-  uint4 r = philox4x32_10(make_uint4((uint32_t)idx4, (uint32_t)(idx4 >> 32), layer, 0u),
-                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  const float inv = 1.f / (1.f - p_drop);
-  const float u0 = r.x * 2.3283064365386963e-10f, u1 = r.y * 2.3283064365386963e-10f;
-  const float u2 = r.z * 2.3283064365386963e-10f, u3 = r.w * 2.3283064365386963e-10f;
-  return make_float4(u0 >= p_drop ? inv : 0.f, u1 >= p_drop ? inv : 0.f, u2 >= p_drop ? inv : 0.f,
-                     u3 >= p_drop ? inv : 0.f);
+  float k[8];
+  dropout_scale8(seed, layer, idx4 >> 1, p_drop, k);
+  return (idx4 & 1ull) ? make_float4(k[4], k[5], k[6], k[7]) : make_float4(k[0], k[1], k[2], k[3]);
 }
 
 }  // namespace dcb

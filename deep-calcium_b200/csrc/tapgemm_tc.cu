@@ -56,6 +56,7 @@ struct TcFwdParams {
   int swap;                 // 1: weights are the MMA A operand (M = 128 channel rows), pixels the B operand (N = 256)
   int stages;
   int f16;                  // 16-bit element format: 0 = bf16, 1 = fp16
+  int tma_store;            // 1: normal-orientation 16-bit epilogue stages blocks in smem and stores them with TMA (mapO)
   __nv_bfloat16* out;
   __nv_bfloat16* pool_out;  // conv3x3 only: 2x2 max-pooled copy [N][GH/2][GW/2][Ntot] written by the epilogue (or null)
   const float* scale;
@@ -175,7 +176,7 @@ __device__ __forceinline__ void epilogue_swapped_pool(uint32_t t_addr, int npix,
 template <bool POOL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                      const __grid_constant__ CUtensorMap mapB, const TcFwdParams p) {
+                      const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapO, const TcFwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t bar_full[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_base_smem;
@@ -405,17 +406,43 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
             st_global_v8(orow_f + q0, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
           }
         };
+        // TMA-store mode: per quartet two 8 KB staging tiles ([128 px][32 ch], SWIZZLE_64B) behind the stage ring
+        const uint32_t stg = smem_u32(smem + (size_t)p.stages * stage_bytes) + (uint32_t)eset * 16384u;
+        const bool leader = quarter == 0 && lane == 0;
         for (int c = 0; c < p.BN; c += 64) {
           const bool two = c + 32 < p.BN;
           const int z0 = z, ch0 = ch;
           ch += 32; if (ch == p.Cz) { ch = 0; ++z; }
           const int z1 = z, ch1 = ch;
           if (two) { ch += 32; if (ch == p.Cz) { ch = 0; ++z; } }
-          const size_t o0 = out_index(z0, ch0), o1 = out_index(z1, ch1);
           uint32_t r0[32], r1[32];
           tmem_ld_32x32b_x32(t_addr + c, r0);
           if (two) tmem_ld_32x32b_x32(t_addr + c + 32, r1);
           tmem_ld_wait();
+          if (p.tma_store) {
+            uint32_t pk0[16], pk1[16];
+            bn_relu_pack32(r0, s_scale + ch0, s_shift + ch0, p.relu, pk0, p.f16);
+            if (two) bn_relu_pack32(r1, s_scale + ch1, s_shift + ch1, p.relu, pk1, p.f16);
+            if (leader) bulk_wait_read0();                       // the previous stores have read the staging tiles
+            named_bar_sync(1 + eset, 128);
+            stage_pk16_swz64(stg, m, pk0);
+            if (two) stage_pk16_swz64(stg + 8192u, m, pk1);
+            fence_proxy_async_smem();
+            named_bar_sync(1 + eset, 128);
+            if (leader) {
+              const int w0 = tw * p.bw, h0 = th * p.bh;
+              if (p.mode == 0) {
+                tma_store_4d(&mapO, smem + (size_t)p.stages * stage_bytes + eset * 16384, ch0, w0, h0, tn * p.bn);
+                if (two) tma_store_4d(&mapO, smem + (size_t)p.stages * stage_bytes + eset * 16384 + 8192, ch1, w0, h0, tn * p.bn);
+              } else {
+                tma_store_5d(&mapO, smem + (size_t)p.stages * stage_bytes + eset * 16384, ch0, z0 & 1, w0, z0 >> 1, h0);
+                if (two) tma_store_5d(&mapO, smem + (size_t)p.stages * stage_bytes + eset * 16384 + 8192, ch1, z1 & 1, w0, z1 >> 1, h0);
+              }
+              bulk_commit();
+            }
+            continue;
+          }
+          const size_t o0 = out_index(z0, ch0), o1 = out_index(z1, ch1);
           if (!valid) continue;
           if (p.out_f32) {
             store_f32(r0, ch0, o0);
@@ -490,6 +517,7 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[acc]);
     }
+    if (p.tma_store && quarter == 0 && lane == 0) bulk_wait0();   // staging tiles stay valid until the last store is done
   }
 
   tc_fence_before();
@@ -1762,11 +1790,18 @@ static int run_tc_generic(const TapGeom& g, const void* s0, int C0, const void* 
   if (p.swap) BN = p.Ntot < 128 ? p.Ntot : 128;       // rows of the weight TMA box
   p.BN = BN;
   const size_t stage_bytes = (size_t)TM * p.BK * 2 + (size_t)(p.swap ? 128 : BN) * p.BK * 2;
-  int stages = (int)((200 * 1024) / stage_bytes);
+  // 16-bit outputs of the convT forward leave through TMA stores (two 8 KB staging tiles per epilogue quartet): its
+  // scattered 64-byte runs saturate the LSU pipe as plain stores (profiles/r2_convT_ncu.txt).  The conv3x3 layers on this
+  // kernel are operand-traffic bound and lose more from the smaller stage ring than the stores gain (measured; policy 2
+  // = TMA stores there too).
+  p.tma_store = (!p.swap && !out_f32 && !pool_out && p.mode != 2 &&
+                 (policy(DCB_POLICY_TMA_STORE) >= 2 || (policy(DCB_POLICY_TMA_STORE) == 1 && p.mode == 1))) ? 1 : 0;
+  const size_t staging = p.tma_store ? 2 * 16384 : 0;
+  int stages = (int)((200 * 1024 - staging) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages < 2) return fail(DCB_ERR_UNSUPPORTED, "tile does not fit shared memory");
   p.stages = stages;
-  const size_t dyn_smem = stages * stage_bytes + 1024;
+  const size_t dyn_smem = stages * stage_bytes + staging + 1024;
 
   // ---- tensor maps
   CUtensorMap mA0, mA1, mB;
@@ -1800,6 +1835,22 @@ static int run_tc_generic(const TapGeom& g, const void* s0, int C0, const void* 
     if (int e = make_map(&mB, B, 2, dims, str, box, swz)) return e;
   }
 
+  CUtensorMap mO = mB;
+  if (p.tma_store) {
+    if (p.mode == 0) {
+      uint64_t dims[4] = {(uint64_t)Nout, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)g.N};
+      uint64_t str[3] = {(uint64_t)out_pitch * 2, (uint64_t)g.OW * out_pitch * 2, (uint64_t)g.OH * g.OW * out_pitch * 2};
+      uint32_t box[4] = {32u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+      if (int e = make_map(&mO, out, 4, dims, str, box, 64)) return e;
+    } else {
+      // convT fwd: y [N][2h][2w][C] viewed as [N*h][dy][w][dx][C] -> innermost first {C, dx, w, dy, N*h}
+      uint64_t dims[5] = {(uint64_t)Nout, 2, (uint64_t)g.GW, 2, (uint64_t)g.N * g.GH};
+      uint64_t str[4] = {(uint64_t)out_pitch * 2, (uint64_t)2 * out_pitch * 2, (uint64_t)g.OW * out_pitch * 2,
+                         (uint64_t)2 * g.OW * out_pitch * 2};
+      uint32_t box[5] = {32u, 1, (uint32_t)p.bw, 1, (uint32_t)p.bh};
+      if (int e = make_map(&mO, out, 5, dims, str, box, 64)) return e;
+    }
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
@@ -1809,8 +1860,8 @@ static int run_tc_generic(const TapGeom& g, const void* s0, int C0, const void* 
   }
   const int num_tiles = num_mtiles * (p.swap ? cdiv(p.Ntot, 128) : p.Ntot / BN);
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  if (p.pool_out) tapgemm_tc_fwd_kernel<true><<<grid, TC_THREADS, dyn_smem, st>>>(mA0, mA1, mB, p);
-  else tapgemm_tc_fwd_kernel<false><<<grid, TC_THREADS, dyn_smem, st>>>(mA0, mA1, mB, p);
+  if (p.pool_out) tapgemm_tc_fwd_kernel<true><<<grid, TC_THREADS, dyn_smem, st>>>(mA0, mA1, mB, mO, p);
+  else tapgemm_tc_fwd_kernel<false><<<grid, TC_THREADS, dyn_smem, st>>>(mA0, mA1, mB, mO, p);
   g_launches += 1;
   DCB_LAUNCH_OK("tapgemm_tc_fwd_kernel");
   note_kernel(p.pool_out ? (p.swap ? "generic_swap_pool" : "generic_pool") : (p.swap ? "generic_swap" : "generic"));

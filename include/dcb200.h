@@ -63,7 +63,9 @@ enum dcb_policy_key {
   DCB_POLICY_PROJ_I16_SPLITS = 7, /* T splits of the int16 projection (0 = heuristic) */
   DCB_POLICY_SPLITK = 8,        /* split-K of the generic conv kernel for small pixel counts: 0 off, 1 auto */
   DCB_POLICY_FUSED_BN = 9,      /* training BatchNorm: 1 = single-launch kernels with a grid barrier, 0 = separate passes */
-  DCB_POLICY_COUNT = 10
+  DCB_POLICY_TMA_STORE = 10,    /* epilogues stage 16-bit outputs in shared memory and store them with TMA: 0 off, 1 convT forward, 2 also conv3x3 on the generic kernel */
+  DCB_POLICY_BN_SLAB = 11,      /* training BatchNorm as channel-slab cluster kernels (DSMEM reduction): 0 off, 1 small tensors (measured gate), 2 wherever eligible */
+  DCB_POLICY_COUNT = 12
 };
 int dcb_set_policy(int key, int value);
 int dcb_get_policy(int key, int* value);

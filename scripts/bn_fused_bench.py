@@ -12,6 +12,7 @@ import torch  # noqa: E402
 from deepcalcium.engine import ops  # noqa: E402
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 50
+PD = float(os.environ.get('BN_PDROP', '0.25'))   # dropout rate of the timed calls (7 of the 22 layers of a step have one)
 only = os.environ.get('BN_ONLY')          # e.g. "32,8,8,512" to run a single shape (ncu captures)
 dt = torch.bfloat16
 shapes = [(32, 128, 128, 32), (32, 64, 64, 64), (32, 32, 32, 128), (32, 16, 16, 256), (32, 8, 8, 512)]
@@ -42,6 +43,7 @@ def timed(fn, inner=20):
 
 from deepcalcium import _native as nat  # noqa: E402
 per_sm_list = [int(v) for v in os.environ.get('BN_CTAS', '4').split(',')]
+nat.set_policy(bn_slab=int(os.environ.get('BN_SLAB', '1')))
 for N, H, W, C in [sh for sh in shapes for _ in per_sm_list]:
     per_sm = per_sm_list[0]; per_sm_list = per_sm_list[1:] + per_sm_list[:1]
     nat.set_policy(bn_ctas_per_sm=per_sm)
@@ -61,30 +63,30 @@ for N, H, W, C in [sh for sh in shapes for _ in per_sm_list]:
     def sep_fwd():
         sums.zero_()
         ops.bn_stats(x, sums[:2 * C])
-        ops.bn_finalize_apply(x, sums[:2 * C], M, gamma, beta, 0.99, None, None, sc, sh, mu, rs, y, True, 0.25, 7, seed_dev, 3)
+        ops.bn_finalize_apply(x, sums[:2 * C], M, gamma, beta, 0.99, None, None, sc, sh, mu, rs, y, True, PD, 7, seed_dev, 3)
 
     def fused_fwd():
         sync.zero_()
-        ops.bn_train_fwd(x, gamma, beta, 0.99, None, None, sc, sh, mu, rs, y, ws, sync[:4], True, 0.25, 7, seed_dev, 3)
+        ops.bn_train_fwd(x, gamma, beta, 0.99, None, None, sc, sh, mu, rs, y, ws, sync[:4], True, PD, 7, seed_dev, 3)
 
     def fused_fwd_pool():
         sync.zero_()
-        ops.bn_train_fwd(x, gamma, beta, 0.99, None, None, sc, sh, mu, rs, y, ws, sync[:4], True, 0.25, 7, seed_dev, 3, pool_out=pool)
+        ops.bn_train_fwd(x, gamma, beta, 0.99, None, None, sc, sh, mu, rs, y, ws, sync[:4], True, PD, 7, seed_dev, 3, pool_out=pool)
 
     def sep_bwd():
         sums.zero_()
-        ops.bn_bwd_reduce(dy, C, 0, x, sc, sh, mu, rs, sums[2 * C:], 0.25, 7, seed_dev, 3)
-        ops.bn_bwd_apply(dy, C, 0, x, sc, sh, mu, rs, sums[2 * C:], draw, dg, db, 0.25, 7, seed_dev, 3)
+        ops.bn_bwd_reduce(dy, C, 0, x, sc, sh, mu, rs, sums[2 * C:], PD, 7, seed_dev, 3)
+        ops.bn_bwd_apply(dy, C, 0, x, sc, sh, mu, rs, sums[2 * C:], draw, dg, db, PD, 7, seed_dev, 3)
 
     def fused_bwd():
         sync.zero_()
-        ops.bn_train_bwd(dy, C, 0, x, sc, sh, mu, rs, draw, dg, db, ws, sync[4:], 0.25, 7, seed_dev, 3)
+        ops.bn_train_bwd(dy, C, 0, x, sc, sh, mu, rs, draw, dg, db, ws, sync[4:], PD, 7, seed_dev, 3)
 
     sep_fwd()
     mb = M * C * 2 / 1e6
     r = dict(sep_fwd=timed(sep_fwd), fused_fwd=timed(fused_fwd), fused_fwd_pool=timed(fused_fwd_pool), sep_bwd=timed(sep_bwd),
              fused_bwd=timed(fused_bwd), memset=timed(lambda: sync.zero_()))
-    print('ctas/SM %d ' % per_sm, end='')
+    print('ctas/SM %d slab %d p_drop %.2f ' % (per_sm, nat.get_policy('bn_slab'), PD), end='')
     print('%-20s %6.1f MB bf16 | fwd: separate %6.1f us, fused %6.1f us, fused+pool %6.1f us | bwd: separate %6.1f us, fused %6.1f us | '
           'memset alone %.1f us | floors (HBM 6.5 TB/s): fwd %.1f us (R+W), bwd %.1f us (R dy fp32 + R x + W)'
           % ((N, H, W, C), mb, r['sep_fwd'], r['fused_fwd'], r['fused_fwd_pool'], r['sep_bwd'], r['fused_bwd'], r['memset'],
