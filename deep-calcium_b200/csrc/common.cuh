@@ -38,7 +38,31 @@ int sm_count();   // cached multiprocessor count of the current device
 int policy(int key);               // current value of a dcb_policy_key (dcb_set_policy)
 void note_kernel(const char* name); // records the contraction kernel a call dispatched to (dcb_last_kernel)
 
+// Kernel launch with optional PROGRAMMATIC DEPENDENT LAUNCH (policy DCB_POLICY_PDL): the kernel may be scheduled while
+// its predecessor in the stream is still running, executes its prologue (barrier / TMEM set-up, tensor-map prefetch,
+// loads of STATIC data such as weights) and blocks in pdl_wait() until the predecessor has completed and its writes
+// are visible.  Only kernels that call pdl_wait() before touching anything an earlier kernel of the stream produces
+// may be launched through this helper with pdl = true.  Captured into CUDA graphs as programmatic dependency edges.
+template <typename... ExpTypes, typename... ActTypes>
+static inline cudaError_t launch_k(void (*kernel)(ExpTypes...), int grid, int block, size_t smem, cudaStream_t st, bool pdl,
+                                   ActTypes&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1); cfg.blockDim = dim3((unsigned)block, 1, 1);
+  cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<ExpTypes>(args)...);
+}
+
 // ---- device helpers ----
+// programmatic dependent launch (see launch_k): let the next kernel of the stream start its prologue / wait for the
+// previous kernel's completion.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"

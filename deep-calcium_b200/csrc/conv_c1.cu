@@ -32,6 +32,7 @@ conv3x3_c1_fwd_kernel(const float* __restrict__ x, int N, int H, int W, const fl
   // the staging loads (ncu source view, profiles/r2_c1_ncu.txt).
   __shared__ float s_in[2][WIN];
   const int cg = threadIdx.x % TPP, col = threadIdx.x / TPP;
+  if (threadIdx.x == 0) pdl_trigger();
   float2 wr[9][4];                                            // this thread's 8 channels of the 9 taps, as fp32 pairs
 #pragma unroll
   for (int t = 0; t < 9; ++t)
@@ -45,6 +46,7 @@ conv3x3_c1_fwd_kernel(const float* __restrict__ x, int N, int H, int W, const fl
   }
   const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
   const int num_tiles = N * tiles_h * tiles_w;
+  pdl_wait();                                                 // weights / scale / shift above are static; x is not
   auto prefetch = [&](int tile, int buf) {
     if (tile < num_tiles) {
       const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
@@ -165,15 +167,17 @@ static int launch_c1_fwd(const float* x, int N, int H, int W, const float* w, in
   // persistent: two 256-thread CTAs per SM walk the [16 x (2048 / Cout)]-pixel tiles
   auto tiles = [&](int tw) { return (long long)N * cdiv(H, 16) * cdiv(W, tw); };
   auto grid_for = [&](long long t) { const long long cap = 2LL * sm_count(); return (int)(t < cap ? t : cap); };
+  const bool pdl = policy(DCB_POLICY_PDL) != 0;
+  cudaError_t le = cudaSuccess;
   switch (Cout) {
-    case 8: conv3x3_c1_fwd_kernel<T, 8><<<grid_for(tiles(256)), 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break;
-    case 16: conv3x3_c1_fwd_kernel<T, 16><<<grid_for(tiles(128)), 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break;
-    case 32: conv3x3_c1_fwd_kernel<T, 32><<<grid_for(tiles(64)), 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break;
-    case 64: conv3x3_c1_fwd_kernel<T, 64><<<grid_for(tiles(32)), 256, 0, st>>>(x, N, H, W, w, scale, shift, relu, out); break;
+    case 8: le = launch_k(conv3x3_c1_fwd_kernel<T, 8>, grid_for(tiles(256)), 256, 0, st, pdl, x, N, H, W, w, scale, shift, relu, out); break;
+    case 16: le = launch_k(conv3x3_c1_fwd_kernel<T, 16>, grid_for(tiles(128)), 256, 0, st, pdl, x, N, H, W, w, scale, shift, relu, out); break;
+    case 32: le = launch_k(conv3x3_c1_fwd_kernel<T, 32>, grid_for(tiles(64)), 256, 0, st, pdl, x, N, H, W, w, scale, shift, relu, out); break;
+    case 64: le = launch_k(conv3x3_c1_fwd_kernel<T, 64>, grid_for(tiles(32)), 256, 0, st, pdl, x, N, H, W, w, scale, shift, relu, out); break;
     default: return fail(DCB_ERR_UNSUPPORTED, "dcb_conv3x3_c1_fwd: Cout=%d unsupported (8,16,32,64)", Cout);
   }
+  if (le != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of conv3x3_c1_fwd_kernel failed: %s", cudaGetErrorString(le));
   g_launches += 1;
-  DCB_LAUNCH_OK("conv3x3_c1_fwd_kernel");
   return DCB_OK;
 }
 

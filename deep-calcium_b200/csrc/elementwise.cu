@@ -725,6 +725,8 @@ template <typename T>
 __global__ void tta_make_batch_kernel(const float* __restrict__ s, int hs, int ws, int S, int first, int count,
                                       T* __restrict__ out) {
   const long long n = (long long)count * S * S;
+  if (threadIdx.x == 0) pdl_trigger();
+  pdl_wait();
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(idx % S), i = (int)((idx / S) % S), kk = (int)(idx / ((long long)S * S));
     int si, sj;
@@ -737,6 +739,8 @@ __global__ void tta_make_batch_kernel(const float* __restrict__ s, int hs, int w
 __global__ void tta_combine_kernel(const float* __restrict__ probs, int S, int hs, int ws, float threshold, int n_aug,
                                    double* __restrict__ act, uint8_t* __restrict__ mask) {
   const long long n = (long long)hs * ws;
+  if (threadIdx.x == 0) pdl_trigger();
+  pdl_wait();
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(idx % ws), i = (int)(idx / ws);
     double acc = 0.0;
@@ -1046,10 +1050,13 @@ extern "C" int dcb_tta_make_batch(int dtype, const float* s, int hs, int ws, int
                                   dcb_stream_t stream) {
   DCB_CHECK_ARG(s && out && hs > 0 && ws > 0 && hs <= S && ws <= S, "dcb_tta_make_batch: image %dx%d does not fit window %d", hs, ws, S);
   DCB_CHECK_ARG(first >= 0 && count > 0 && first + count <= 8, "dcb_tta_make_batch: transforms [%d,%d) out of range", first, first + count);
-  DISPATCH_T(dtype, tta_make_batch_kernel<T><<<ew_grid((long long)count * S * S, 256), 256, 0, (cudaStream_t)stream>>>(
-      s, hs, ws, S, first, count, (T*)out);)
+  const bool pdl = policy(DCB_POLICY_PDL) != 0;
+  DISPATCH_T(dtype, {
+    const cudaError_t le = launch_k(tta_make_batch_kernel<T>, ew_grid((long long)count * S * S, 256), 256, 0, (cudaStream_t)stream, pdl,
+                                    s, hs, ws, S, first, count, (T*)out);
+    if (le != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of tta_make_batch_kernel failed: %s", cudaGetErrorString(le));
+  })
   g_launches += 1;
-  DCB_LAUNCH_OK("tta_make_batch_kernel");
   return DCB_OK;
 }
 
@@ -1057,9 +1064,12 @@ extern "C" int dcb_tta_combine(const float* probs, int S, int hs, int ws, float 
                                uint8_t* mask, dcb_stream_t stream) {
   DCB_CHECK_ARG(probs && mask && hs > 0 && ws > 0 && hs <= S && ws <= S, "dcb_tta_combine: bad arguments");
   DCB_CHECK_ARG(n_aug == 1 || n_aug == 8, "dcb_tta_combine: n_aug must be 1 or 8 (got %d)", n_aug);
-  tta_combine_kernel<<<ew_grid((long long)hs * ws, 256), 256, 0, (cudaStream_t)stream>>>(probs, S, hs, ws, threshold, n_aug, act, mask);
+  {
+    const cudaError_t le = launch_k(tta_combine_kernel, ew_grid((long long)hs * ws, 256), 256, 0, (cudaStream_t)stream,
+                                    policy(DCB_POLICY_PDL) != 0, probs, S, hs, ws, threshold, n_aug, act, mask);
+    if (le != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of tta_combine_kernel failed: %s", cudaGetErrorString(le));
+  }
   g_launches += 1;
-  DCB_LAUNCH_OK("tta_combine_kernel");
   return DCB_OK;
 }
 

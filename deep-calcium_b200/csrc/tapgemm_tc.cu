@@ -183,6 +183,7 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
   __shared__ __align__(16) float s_scale[512], s_shift[512];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) pdl_trigger();
   // dynamic smem: 1024-byte aligned stage buffers (swizzle atoms are address based)
   // 1024-byte alignment as an offset into the __shared__ array (an integer round trip would turn every later access
   // through this pointer into a generic-space load/store)
@@ -228,6 +229,7 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
     // ===================================================== TMA producer
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
+      pdl_wait();                                   // the activations come from the previous kernel of the stream
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int nt = tile % num_ntiles, mt = tile / num_ntiles;
         const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
@@ -668,6 +670,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_scale[128], s_shift[128], s_wd[128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) pdl_trigger();
   const int PX = p.swap ? 256 : 128;                             // pixels per tile (one image-row segment)
   // 1024-byte alignment as an offset into the __shared__ array (an integer round trip would turn every later access
   // through this pointer into a generic-space load/store)
@@ -744,6 +747,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
       const int rows_per_slot = FOLD ? 2 : 1;                    // folded mode: one barrier per pair of halo rows
       const int nslots = FOLD ? p.ring >> 1 : p.ring;
       long long u = u_begin;
+      pdl_wait();                // the weights above are static; the activation rows come from the previous kernel
       for (int n, h0, rows, w0; next_strip(u, n, h0, rows, w0);) {
         for (int rr = -1; rr <= rows; ++rr) {
           const int sub = FOLD ? ((rr + 1) & 1) : 0;              // row inside the slot
@@ -1684,13 +1688,15 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
       }
       const long long units = (long long)sp.N * sp.wsegs * cdiv(sp.H, sp.gran);
       const int grid = units < sm_count() ? (int)units : sm_count();
+      const bool pdl = policy(DCB_POLICY_PDL) != 0;
       for (sp.n0 = 0; sp.n0 < Nout; sp.n0 += sp.Cout) {          // one launch per group of output channels
-        if (fused && sp.fold) tapgemm_tc_strip_kernel<true, true><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
-        else if (fused) tapgemm_tc_strip_kernel<true, false><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
-        else if (sp.fold) tapgemm_tc_strip_kernel<false, true><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
-        else tapgemm_tc_strip_kernel<false, false><<<grid, ST_THREADS, dyn, st>>>(mA0, mA1, mT0, mT1, mB, sp);
+        cudaError_t le;
+        if (fused && sp.fold) le = launch_k(tapgemm_tc_strip_kernel<true, true>, grid, ST_THREADS, dyn, st, pdl, mA0, mA1, mT0, mT1, mB, sp);
+        else if (fused) le = launch_k(tapgemm_tc_strip_kernel<true, false>, grid, ST_THREADS, dyn, st, pdl, mA0, mA1, mT0, mT1, mB, sp);
+        else if (sp.fold) le = launch_k(tapgemm_tc_strip_kernel<false, true>, grid, ST_THREADS, dyn, st, pdl, mA0, mA1, mT0, mT1, mB, sp);
+        else le = launch_k(tapgemm_tc_strip_kernel<false, false>, grid, ST_THREADS, dyn, st, pdl, mA0, mA1, mT0, mT1, mB, sp);
+        if (le != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of tapgemm_tc_strip_kernel failed: %s", cudaGetErrorString(le));
         g_launches += 1;
-        DCB_LAUNCH_OK("tapgemm_tc_strip_kernel");
       }
       note_kernel(sp.fold ? (fused ? "strip_fold_fused" : (sp.Cout < Nout ? "strip_fold_nsplit" : "strip_fold"))
                           : (sp.swap ? "strip_swap" : (fused ? "strip_fused" : "strip")));
@@ -1756,6 +1762,8 @@ static int run_tc_generic(const TapGeom& g, const void* s0, int C0, const void* 
   // ---- M tiling
   if (p.mode == 0) {
     p.bw = pick_pow2_box(g.GW, TM);
+    // the pooled epilogue needs whole 2x2 windows inside a tile: rows wide enough for a one-row tile are split in two
+    if (pool_out && p.bw == TM && TM >= 4) p.bw = TM / 2;
     p.bh = pick_pow2_box(g.GH, TM / p.bw);
     p.bn = TM / (p.bw * p.bh);
     p.tiles_w = cdiv(g.GW, p.bw); p.tiles_h = cdiv(g.GH, p.bh); p.tiles_n = cdiv(g.N, p.bn);
@@ -1860,10 +1868,13 @@ static int run_tc_generic(const TapGeom& g, const void* s0, int C0, const void* 
   }
   const int num_tiles = num_mtiles * (p.swap ? cdiv(p.Ntot, 128) : p.Ntot / BN);
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  if (p.pool_out) tapgemm_tc_fwd_kernel<true><<<grid, TC_THREADS, dyn_smem, st>>>(mA0, mA1, mB, mO, p);
-  else tapgemm_tc_fwd_kernel<false><<<grid, TC_THREADS, dyn_smem, st>>>(mA0, mA1, mB, mO, p);
+  {
+    const bool pdl = policy(DCB_POLICY_PDL) != 0;
+    const cudaError_t le = p.pool_out ? launch_k(tapgemm_tc_fwd_kernel<true>, grid, TC_THREADS, dyn_smem, st, pdl, mA0, mA1, mB, mO, p)
+                                      : launch_k(tapgemm_tc_fwd_kernel<false>, grid, TC_THREADS, dyn_smem, st, pdl, mA0, mA1, mB, mO, p);
+    if (le != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of tapgemm_tc_fwd_kernel failed: %s", cudaGetErrorString(le));
+  }
   g_launches += 1;
-  DCB_LAUNCH_OK("tapgemm_tc_fwd_kernel");
   note_kernel(p.pool_out ? (p.swap ? "generic_swap_pool" : "generic_pool") : (p.swap ? "generic_swap" : "generic"));
   return DCB_OK;
 }

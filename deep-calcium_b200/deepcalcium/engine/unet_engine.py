@@ -61,6 +61,7 @@ class UNetEngine(object):
         self.launches = 0
         self.comm = None          # engine.dist.Comm for data-parallel training (None = single GPU)
         self.overlap_wgrad = True  # weight-gradient launches on a side stream (see _train_step_enqueue)
+        self.pdl = os.environ.get('DCB_PDL', '1') != '0'   # programmatic dependent launch in the inference forward
         self._side = None
         self.set_weights_dict(he_normal_weights(self.spec, seed=0))
 
@@ -282,6 +283,12 @@ class UNetEngine(object):
         The max-pool after each encoder block and the softmax head are folded into the producing conv's
         epilogue (dcb_conv3x3_fwd_fused) - the library falls back to the separate kernels where the fused
         epilogue does not apply."""
+        # programmatic dependent launch: every kernel of the inference forward reads only static data (weights, folded BN
+        # coefficients) before its dependency wait, so consecutive layers overlap prologue and tail
+        with nat.policy(pdl=1 if self.pdl else 0):
+            self._forward_inference_enqueue(s, prob_out)
+
+    def _forward_inference_enqueue(self, s, prob_out):
         act = s['act']
         for blk in self.spec.blocks:
             n = blk.name
@@ -371,10 +378,11 @@ class UNetEngine(object):
         st['summ'].copy_(summ_dev)
 
         def run():
-            ops.tta_make_batch(st['summ'], window, first, count, s['x'])
-            self._forward_inference(s)
-            if transforms is None:
-                ops.tta_combine(s['prob'], window, hs, ws, threshold, n_aug, st['act'], st['mask'])
+            with nat.policy(pdl=1 if self.pdl else 0):
+                ops.tta_make_batch(st['summ'], window, first, count, s['x'])
+                self._forward_inference(s)
+                if transforms is None:
+                    ops.tta_combine(s['prob'], window, hs, ws, threshold, n_aug, st['act'], st['mask'])
 
         self._run_graphed(s['tta_graphs'], key, run)
         if transforms is not None:

@@ -65,7 +65,10 @@ enum dcb_policy_key {
   DCB_POLICY_FUSED_BN = 9,      /* training BatchNorm: 1 = single-launch kernels with a grid barrier, 0 = separate passes */
   DCB_POLICY_TMA_STORE = 10,    /* epilogues stage 16-bit outputs in shared memory and store them with TMA: 0 off, 1 convT forward, 2 also conv3x3 on the generic kernel */
   DCB_POLICY_BN_SLAB = 11,      /* training BatchNorm as channel-slab cluster kernels (DSMEM reduction): 0 off, 1 small tensors (measured gate), 2 wherever eligible */
-  DCB_POLICY_COUNT = 12
+  DCB_POLICY_PDL = 12,          /* programmatic dependent launch of the forward conv / TTA kernels: 0 off, 1 on.  Turn on only while
+                                   enqueueing work whose per-channel scale / shift / weights are NOT written by kernels of the same
+                                   stream sequence (inference): prologues read them before the dependency wait */
+  DCB_POLICY_COUNT = 13
 };
 int dcb_set_policy(int key, int value);
 int dcb_get_policy(int key, int* value);
