@@ -248,11 +248,14 @@ def test_conv3x3_fused_pool_and_head_equal_the_unfused_composition(cuda, precisi
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
-def test_conv3x3_first_layer_c1(cuda, precision):
+@pytest.mark.parametrize('shape', [(2, 24, 40, 32), (3, 7, 33, 32), (1, 5, 130, 32), (4, 128, 128, 32), (2, 9, 21, 16), (1, 16, 16, 64)])
+def test_conv3x3_first_layer_c1(cuda, precision, shape):
+    """Cin = 1 layer (enc0a): CUDA-core forward; weight gradient = row-staged kernel for Cout == 32 (odd widths, one-row
+    CTAs, more CTAs than rows), pixel-range kernel otherwise."""
     from deepcalcium.engine import ops
     dt = DT[precision]
     rng = np.random.default_rng(11)
-    N, H, W, Cout = 2, 24, 40, 32
+    N, H, W, Cout = shape
     x = rng.standard_normal((N, H, W)).astype(np.float32)
     w = (rng.standard_normal((3, 3, 1, Cout)) * 0.5).astype(np.float32)
     b = rng.standard_normal(Cout).astype(np.float32)
