@@ -57,6 +57,23 @@ static inline cudaError_t launch_k(void (*kernel)(ExpTypes...), int grid, int bl
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<ExpTypes>(args)...);
 }
 
+// the same for a kernel that runs as thread-block clusters of `cluster_x` CTAs (grid must be a multiple of it)
+template <typename... ExpTypes, typename... ActTypes>
+static inline cudaError_t launch_kc(void (*kernel)(ExpTypes...), int grid, int block, size_t smem, cudaStream_t st, bool pdl,
+                                    int cluster_x, ActTypes&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1); cfg.blockDim = dim3((unsigned)block, 1, 1);
+  cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cluster_x; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<ExpTypes>(args)...);
+}
+
 // ---- device helpers ----
 // programmatic dependent launch (see launch_k): let the next kernel of the stream start its prologue / wait for the
 // previous kernel's completion.  Both are no-ops for a kernel launched without the attribute.

@@ -651,6 +651,121 @@ struct TcStripParams {
   const float* shift;
 };
 
+// Drains one PAIR of output rows of a folded strip (accumulators at TMEM addresses ta / tb, lane = pixel): BN / ReLU / pack,
+// optional fused softmax head and 2x2 max-pool, 16-bit or fp32 stores.  Both rows are processed together: the two TMEM
+// loads, the arithmetic and the stores of the two rows are independent instruction streams (twice the ILP of a
+// row-at-a-time loop, which left each scheduler with one latency-bound warp), the per-channel scale / shift are fetched
+// from shared memory once per pair, and the vertical half of the pool is a register-to-register maximum.
+// (n, row, px) = image, first row of the pair, pixel column of this thread.
+template <bool FUSED>
+__device__ __forceinline__ void strip_drain_pair(const TcStripParams& p, uint32_t ta, uint32_t tb, int n, int row, int px,
+                                                 const float* s_scale, const float* s_shift, const float* s_wd, float head_b,
+                                                 int lane) {
+  const size_t opix_a = ((size_t)n * p.H + row) * p.W + px, opix_b = opix_a + p.W;
+  const size_t oidx_a = opix_a * p.OC + p.n0, oidx_b = opix_b * p.OC + p.n0;
+  if (p.out_f32) {                                       // gradient tensors (dgrad): fp32 stores, row by row
+#pragma unroll 1
+    for (int rr = 0; rr < 2; ++rr) {
+      float* orow_f = reinterpret_cast<float*>(p.out) + (rr ? oidx_b : oidx_a);
+      for (int c = 0; c < p.Cout; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32((rr ? tb : ta) + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q0 = 0; q0 < 32; q0 += 8) {
+          uint32_t v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float f = fmaf(__uint_as_float(r[q0 + q]), s_scale[c + q0 + q], s_shift[c + q0 + q]);
+            if (p.relu) f = fmaxf(f, 0.f);
+            v[q] = __float_as_uint(f);
+          }
+          st_global_v8(orow_f + c + q0, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+        }
+      }
+    }
+  } else {
+    __nv_bfloat16* orow_a = p.out + oidx_a;
+    __nv_bfloat16* orow_b = p.out + oidx_b;
+    float zacc_a = head_b, zacc_b = head_b;
+    for (int c = 0; c < p.Cout; c += 32) {
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32b_x32(ta + c, ra);
+      tmem_ld_32x32b_x32(tb + c, rb);
+      tmem_ld_wait();
+      if (FUSED && p.head_kernel && !p.need_y && !p.pool_out) {
+        // dec0b at inference: the activation is consumed by the 1x1 head only and never stored, so it is not
+        // rounded to 16 bits either: BN + ReLU + dot product stay in (packed) fp32
+        float2 za0 = make_float2(0.f, 0.f), za1 = make_float2(0.f, 0.f), zb0 = za0, zb1 = za0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 sc = *reinterpret_cast<const float4*>(s_scale + c + 4 * g);
+          const float4 sh = *reinterpret_cast<const float4*>(s_shift + c + 4 * g);
+          const float4 wd = *reinterpret_cast<const float4*>(s_wd + c + 4 * g);
+          const float2 sc0 = make_float2(sc.x, sc.y), sc1 = make_float2(sc.z, sc.w);
+          const float2 sh0 = make_float2(sh.x, sh.y), sh1 = make_float2(sh.z, sh.w);
+          float2 a0 = ffma2(make_float2(__uint_as_float(ra[4 * g]), __uint_as_float(ra[4 * g + 1])), sc0, sh0);
+          float2 a1 = ffma2(make_float2(__uint_as_float(ra[4 * g + 2]), __uint_as_float(ra[4 * g + 3])), sc1, sh1);
+          float2 b0 = ffma2(make_float2(__uint_as_float(rb[4 * g]), __uint_as_float(rb[4 * g + 1])), sc0, sh0);
+          float2 b1 = ffma2(make_float2(__uint_as_float(rb[4 * g + 2]), __uint_as_float(rb[4 * g + 3])), sc1, sh1);
+          if (p.relu) {
+            a0.x = fmaxf(a0.x, 0.f); a0.y = fmaxf(a0.y, 0.f); a1.x = fmaxf(a1.x, 0.f); a1.y = fmaxf(a1.y, 0.f);
+            b0.x = fmaxf(b0.x, 0.f); b0.y = fmaxf(b0.y, 0.f); b1.x = fmaxf(b1.x, 0.f); b1.y = fmaxf(b1.y, 0.f);
+          }
+          za0 = ffma2(a0, make_float2(wd.x, wd.y), za0);
+          za1 = ffma2(a1, make_float2(wd.z, wd.w), za1);
+          zb0 = ffma2(b0, make_float2(wd.x, wd.y), zb0);
+          zb1 = ffma2(b1, make_float2(wd.z, wd.w), zb1);
+        }
+        zacc_a += (za0.x + za0.y) + (za1.x + za1.y);
+        zacc_b += (zb0.x + zb0.y) + (zb1.x + zb1.y);
+        continue;
+      }
+      uint32_t pka[16], pkb[16];
+      bn_relu_pack32_x2(ra, rb, s_scale + c, s_shift + c, p.relu, pka, pkb, p.f16);
+      if (FUSED && p.head_kernel) {     // head on the rounded (stored) values, four partial sums per row
+        float za[4] = {0.f, 0.f, 0.f, 0.f}, zb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 wd = *reinterpret_cast<const float4*>(s_wd + c + 4 * g);
+          const float2 f0 = unpack16x2(pka[2 * g], p.f16), f1 = unpack16x2(pka[2 * g + 1], p.f16);
+          const float2 g0 = unpack16x2(pkb[2 * g], p.f16), g1 = unpack16x2(pkb[2 * g + 1], p.f16);
+          za[0] = fmaf(f0.x, wd.x, za[0]); za[1] = fmaf(f0.y, wd.y, za[1]);
+          za[2] = fmaf(f1.x, wd.z, za[2]); za[3] = fmaf(f1.y, wd.w, za[3]);
+          zb[0] = fmaf(g0.x, wd.x, zb[0]); zb[1] = fmaf(g0.y, wd.y, zb[1]);
+          zb[2] = fmaf(g1.x, wd.z, zb[2]); zb[3] = fmaf(g1.y, wd.w, zb[3]);
+        }
+        zacc_a += (za[0] + za[1]) + (za[2] + za[3]);
+        zacc_b += (zb[0] + zb[1]) + (zb[2] + zb[3]);
+      }
+      if (!FUSED || p.need_y) {
+        store_pk16(orow_a + c, pka);
+        store_pk16(orow_b + c, pkb);
+      }
+      if (FUSED && p.pool_out) {
+        // 2x2 max-pool (unet_2d_summary.py:176-194): the vertical partner is the other row of the pair, the
+        // horizontal partner the neighbouring lane.  The two lanes of a window split the 32 channels: each sends
+        // the half its partner will store and keeps the other one - 8 shuffles and one full 32-byte sector per lane.
+        const bool odd = (lane & 1) != 0;
+        uint32_t mx[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t lo = max16x2(pka[q], pkb[q], p.f16), hi = max16x2(pka[8 + q], pkb[8 + q], p.f16);
+          const uint32_t got = __shfl_xor_sync(0xffffffffu, odd ? lo : hi, 1);
+          mx[q] = max16x2(odd ? hi : lo, got, p.f16);
+        }
+        __nv_bfloat16* prow = p.pool_out + ((((size_t)n * (p.H >> 1) + (row >> 1)) * (p.W >> 1) + (px >> 1)) * p.Cout
+                                            + c + (odd ? 16 : 0));
+        st_global_v8(prow, mx[0], mx[1], mx[2], mx[3], mx[4], mx[5], mx[6], mx[7]);
+      }
+    }
+    if (FUSED && p.head_kernel) {
+      if (p.logit) { p.logit[opix_a] = zacc_a; p.logit[opix_b] = zacc_b; }
+      if (p.prob) { p.prob[opix_a] = 1.f / (1.f + __expf(-zacc_a)); p.prob[opix_b] = 1.f / (1.f + __expf(-zacc_b)); }
+    }
+  }
+}
+
 // Roles: warp 0 = TMA producer, warp 1 = single-thread MMA issuer, warps 2..9 = two epilogue quartets (a quartet
 // drains a pair of consecutive 128-pixel tiles, then skips the other quartet's pair).
 // FOLD (Cout 32 or 64, normal orientation): an MMA costs the issuing thread ~60 cycles whatever its N is
@@ -952,11 +1067,8 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
     uint32_t j = 0;
     long long u = u_begin;
     if constexpr (FOLD) {
-      // Folded mode hands the epilogue PAIRS of output rows (one tfull / tempty barrier per pair, see the MMA warp), so a
-      // quartet drains both rows of its pair together: the two TMEM loads, the BN / ReLU / pack arithmetic and the stores
-      // of the two rows are independent instruction streams (twice the ILP of the row-at-a-time loop, which left each
-      // scheduler with one latency-bound warp), the per-channel scale / shift are fetched from shared memory once per
-      // pair, and the vertical half of the 2x2 max-pool is a register-to-register maximum - no state carried between rows.
+      // Folded mode hands the epilogue PAIRS of output rows (one tfull / tempty barrier per pair, see the MMA warp): a
+      // quartet drains both rows of its pair together (strip_drain_pair).
       const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
       const uint32_t pmask = ((uint32_t)nacc >> 1) - 1u;
       for (int n, h0, rows, w0; next_strip(u, n, h0, rows, w0);) {
@@ -965,111 +1077,9 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
           if ((int)(jp & 1u) != eset) continue;                  // ST_QUARTETS == 2: alternate pairs
           const uint32_t ta = t_lane + (j & (uint32_t)(nacc - 1)) * (uint32_t)p.Cout, tb = ta + (uint32_t)p.Cout;
           const int bar_i = (int)(jp & pmask);
-          const size_t opix_a = ((size_t)n * p.H + (h0 + t)) * p.W + (w0 + m), opix_b = opix_a + p.W;
-          const size_t oidx_a = opix_a * p.OC + p.n0, oidx_b = opix_b * p.OC + p.n0;
           mbar_wait(&bar_tfull[bar_i], (j >> nacc_sh) & 1u);
           tc_fence_after();
-          if (p.out_f32) {                                       // gradient tensors (dgrad): fp32 stores, row by row
-#pragma unroll 1
-            for (int rr = 0; rr < 2; ++rr) {
-              float* orow_f = reinterpret_cast<float*>(p.out) + (rr ? oidx_b : oidx_a);
-              for (int c = 0; c < p.Cout; c += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32((rr ? tb : ta) + c, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int q0 = 0; q0 < 32; q0 += 8) {
-                  uint32_t v[8];
-#pragma unroll
-                  for (int q = 0; q < 8; ++q) {
-                    float f = fmaf(__uint_as_float(r[q0 + q]), s_scale[c + q0 + q], s_shift[c + q0 + q]);
-                    if (p.relu) f = fmaxf(f, 0.f);
-                    v[q] = __float_as_uint(f);
-                  }
-                  st_global_v8(orow_f + c + q0, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
-                }
-              }
-            }
-          } else {
-            __nv_bfloat16* orow_a = p.out + oidx_a;
-            __nv_bfloat16* orow_b = p.out + oidx_b;
-            float zacc_a = head_b, zacc_b = head_b;
-            for (int c = 0; c < p.Cout; c += 32) {
-              uint32_t ra[32], rb[32];
-              tmem_ld_32x32b_x32(ta + c, ra);
-              tmem_ld_32x32b_x32(tb + c, rb);
-              tmem_ld_wait();
-              if (FUSED && p.head_kernel && !p.need_y && !p.pool_out) {
-                // dec0b at inference: the activation is consumed by the 1x1 head only and never stored, so it is not
-                // rounded to 16 bits either: BN + ReLU + dot product stay in (packed) fp32
-                float2 za0 = make_float2(0.f, 0.f), za1 = make_float2(0.f, 0.f), zb0 = za0, zb1 = za0;
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                  const float4 sc = *reinterpret_cast<const float4*>(s_scale + c + 4 * g);
-                  const float4 sh = *reinterpret_cast<const float4*>(s_shift + c + 4 * g);
-                  const float4 wd = *reinterpret_cast<const float4*>(s_wd + c + 4 * g);
-                  const float2 sc0 = make_float2(sc.x, sc.y), sc1 = make_float2(sc.z, sc.w);
-                  const float2 sh0 = make_float2(sh.x, sh.y), sh1 = make_float2(sh.z, sh.w);
-                  float2 a0 = ffma2(make_float2(__uint_as_float(ra[4 * g]), __uint_as_float(ra[4 * g + 1])), sc0, sh0);
-                  float2 a1 = ffma2(make_float2(__uint_as_float(ra[4 * g + 2]), __uint_as_float(ra[4 * g + 3])), sc1, sh1);
-                  float2 b0 = ffma2(make_float2(__uint_as_float(rb[4 * g]), __uint_as_float(rb[4 * g + 1])), sc0, sh0);
-                  float2 b1 = ffma2(make_float2(__uint_as_float(rb[4 * g + 2]), __uint_as_float(rb[4 * g + 3])), sc1, sh1);
-                  if (p.relu) {
-                    a0.x = fmaxf(a0.x, 0.f); a0.y = fmaxf(a0.y, 0.f); a1.x = fmaxf(a1.x, 0.f); a1.y = fmaxf(a1.y, 0.f);
-                    b0.x = fmaxf(b0.x, 0.f); b0.y = fmaxf(b0.y, 0.f); b1.x = fmaxf(b1.x, 0.f); b1.y = fmaxf(b1.y, 0.f);
-                  }
-                  za0 = ffma2(a0, make_float2(wd.x, wd.y), za0);
-                  za1 = ffma2(a1, make_float2(wd.z, wd.w), za1);
-                  zb0 = ffma2(b0, make_float2(wd.x, wd.y), zb0);
-                  zb1 = ffma2(b1, make_float2(wd.z, wd.w), zb1);
-                }
-                zacc_a += (za0.x + za0.y) + (za1.x + za1.y);
-                zacc_b += (zb0.x + zb0.y) + (zb1.x + zb1.y);
-                continue;
-              }
-              uint32_t pka[16], pkb[16];
-              bn_relu_pack32_x2(ra, rb, s_scale + c, s_shift + c, p.relu, pka, pkb, p.f16);
-              if (FUSED && p.head_kernel) {     // head on the rounded (stored) values, four partial sums per row
-                float za[4] = {0.f, 0.f, 0.f, 0.f}, zb[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                  const float4 wd = *reinterpret_cast<const float4*>(s_wd + c + 4 * g);
-                  const float2 f0 = unpack16x2(pka[2 * g], p.f16), f1 = unpack16x2(pka[2 * g + 1], p.f16);
-                  const float2 g0 = unpack16x2(pkb[2 * g], p.f16), g1 = unpack16x2(pkb[2 * g + 1], p.f16);
-                  za[0] = fmaf(f0.x, wd.x, za[0]); za[1] = fmaf(f0.y, wd.y, za[1]);
-                  za[2] = fmaf(f1.x, wd.z, za[2]); za[3] = fmaf(f1.y, wd.w, za[3]);
-                  zb[0] = fmaf(g0.x, wd.x, zb[0]); zb[1] = fmaf(g0.y, wd.y, zb[1]);
-                  zb[2] = fmaf(g1.x, wd.z, zb[2]); zb[3] = fmaf(g1.y, wd.w, zb[3]);
-                }
-                zacc_a += (za[0] + za[1]) + (za[2] + za[3]);
-                zacc_b += (zb[0] + zb[1]) + (zb[2] + zb[3]);
-              }
-              if (!FUSED || p.need_y) {
-                store_pk16(orow_a + c, pka);
-                store_pk16(orow_b + c, pkb);
-              }
-              if (FUSED && p.pool_out) {
-                // 2x2 max-pool (unet_2d_summary.py:176-194): the vertical partner is the other row of the pair, the
-                // horizontal partner the neighbouring lane.  The two lanes of a window split the 32 channels: each sends
-                // the half its partner will store and keeps the other one - 8 shuffles and one full 32-byte sector per lane.
-                const bool odd = (lane & 1) != 0;
-                uint32_t mx[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  const uint32_t lo = max16x2(pka[q], pkb[q], p.f16), hi = max16x2(pka[8 + q], pkb[8 + q], p.f16);
-                  const uint32_t got = __shfl_xor_sync(0xffffffffu, odd ? lo : hi, 1);
-                  mx[q] = max16x2(odd ? hi : lo, got, p.f16);
-                }
-                __nv_bfloat16* prow = p.pool_out + ((((size_t)n * (p.H >> 1) + ((h0 + t) >> 1)) * (p.W >> 1) + ((w0 + m) >> 1)) * p.Cout
-                                                    + c + (odd ? 16 : 0));
-                st_global_v8(prow, mx[0], mx[1], mx[2], mx[3], mx[4], mx[5], mx[6], mx[7]);
-              }
-            }
-            if (FUSED && p.head_kernel) {
-              if (p.logit) { p.logit[opix_a] = zacc_a; p.logit[opix_b] = zacc_b; }
-              if (p.prob) { p.prob[opix_a] = 1.f / (1.f + __expf(-zacc_a)); p.prob[opix_b] = 1.f / (1.f + __expf(-zacc_b)); }
-            }
-          }
+          strip_drain_pair<FUSED>(p, ta, tb, n, h0 + t, w0 + m, s_scale, s_shift, s_wd, head_b, lane);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_tempty[bar_i]);
@@ -1256,6 +1266,354 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
+
+// ====================================================================================== CTA-pair folded strip kernel
+// The folded strip loop on PAIR MMAs (tcgen05 cta_group::2, a cluster of two CTAs on neighbouring SMs): one instruction
+// multiplies M = 256 pixels - the 128-pixel halo row segment of each CTA, read from that CTA's own shared memory -
+// against N = 1..3 x Cout stacked weight rows of which each CTA holds HALF, and accumulates into both CTAs' tensor
+// memory.  A single-CTA MMA occupies the tensor pipe for 89-109 cycles whatever N <= 128 is; the pair instruction takes
+// 48 cycles at N = 64 and 64 at N = 128 for twice the rows (profiles/r1_umma_cta2_probe.log), so the N = 96 / 192 MMAs
+// of the 32- and 64-channel layers - which bound those layers once the epilogue was fixed - cost each SM about half.
+//   * The two CTAs of a pair walk the SAME rows of two neighbouring 128-pixel columns in lockstep.  Each runs its own TMA
+//     producer (its halo rows into its own ring, byte counts signalled on the LEADER's row_full barrier through the
+//     .cta_group::2 form of the bulk-tensor load) and its own epilogue quartets (arriving on the leader's tempty barrier
+//     with a cluster-scope remote arrive); the leader's single MMA thread issues for both and multicasts its commits
+//     (row_empty, tfull) to both CTAs' barriers.
+//   * Weights: for a span of `run` output rows starting at stacked tile t0 the instruction reads N/2 = run * Cout / 2
+//     rows at ONE descriptor offset from each CTA - rows [t0*Cout, +N/2) of the stack from the leader, [t0*Cout + N/2,
+//     +N/2) from the peer.  The six (t0, run) spans of the folded loop (2-row accumulate, opening row, 3-row step, and
+//     the spans at strip edges / where the accumulator ring wraps) therefore get one region each: 10 half tiles per
+//     (kc, dx) group and CTA instead of 6 - 5/3 of the single-CTA footprint, still small for Cout = 32.
+// region offset (in half tiles of Cout/2 rows) of span (t0, run) inside a (kc, dx) weight group
+__device__ __forceinline__ uint32_t st2_region(int t0, int run) {
+  return run == 3 ? 7u : (run == 2 ? (t0 == 0 ? 3u : 5u) : (uint32_t)t0);
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive / arrive.expect_tx on a barrier of any CTA of the cluster (shared::cluster address, e.g. from mapa_u32).
+// RELAXED on purpose: the release form at cluster scope compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive, i.e.
+// every epilogue warp waited for its global stores to be performed before it could hand its accumulators back (40 % of
+// all stall samples of the first version, profiles/r2_strip_pair_ncu.txt).  What the arrive has to order is the TMEM
+// reads (tcgen05.wait::ld + tcgen05.fence::before_thread_sync in front of it) / nothing at all for the producer.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t bar_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+}
+// bulk-tensor loads whose completion is signalled on a barrier of either CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t bar_addr, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.cta_group::2 [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* m, uint32_t bar_addr, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.cta_group::2 [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs once all earlier pair MMAs have completed
+__device__ __forceinline__ void umma2_commit_both(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar_addr), "h"((uint16_t)3) : "memory");
+}
+
+// interior halo row whose three accumulators are contiguous in the ring (cf. fold_issue_fast): rows i-1, i accumulate
+// (N = 2*Cout, region (0,2)), row i+1 is opened with accumulate = 0 (N = Cout, region (2,1)); then N = 3*Cout (region (0,3))
+template <int KSTEPS>
+__device__ __forceinline__ void fold2_issue_fast(uint32_t d0, uint32_t d2, uint64_t dA, uint64_t dW, uint32_t id1, uint32_t id2,
+                                                 uint32_t id3, int nkc, uint32_t slot16, uint32_t pitch16, uint32_t half16,
+                                                 uint32_t group16) {
+  umma2_bf16(d0, dA, dW + 3u * half16, id2, 1u);
+  umma2_bf16(d2, dA, dW + 2u * half16, id1, 0u);
+  const uint64_t dW3 = dW + 7u * half16;
+  for (int kc = 0; kc < nkc; ++kc) {
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+      for (int k = 0; k < KSTEPS; ++k) {
+        if (kc == 0 && dx == 0 && k == 0) continue;
+        umma2_bf16(d0, dA + (kc * slot16 + dx * pitch16 + 2 * k), dW3 + ((uint32_t)(kc * 3 + dx) * group16 + 2 * k), id3, 1u);
+      }
+    }
+  }
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(ST_THREADS, 1)
+tapgemm_tc_strip2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                         const __grid_constant__ CUtensorMap mapBh, const TcStripParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t bar_w, row_full[ST_MAX_RING / 2], row_empty[ST_MAX_RING / 2], bar_tfull[8], bar_tempty[8];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float s_scale[128], s_shift[128], s_wd[128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) pdl_trigger();
+  const uint32_t rank = cluster_ctarank();
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int K = p.C0 + p.C1;
+  const int hrows = p.Cout >> 1;                                  // rows of a half tile
+  const uint32_t half_bytes = (uint32_t)hrows * p.BK * 2u;
+  const uint32_t group_bytes = 10u * half_bytes;
+  const uint32_t w_bytes = 3u * p.nkc * group_bytes;
+  uint8_t* s_w = smem;
+  uint8_t* s_ring = smem + ((w_bytes + 1023) & ~1023u);
+  const uint32_t row_bytes = (uint32_t)p.nkc * p.slot_bytes;
+  const uint32_t box_bytes = 130u * p.BK * 2u;
+  const int nacc = 512 / p.Cout, nacc_sh = p.Cout == 32 ? 4 : 3;
+  const int ring_pairs = p.ring >> 1;
+
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
+    s_scale[i] = p.scale ? p.scale[p.n0 + i] : 1.f;
+    s_shift[i] = p.shift ? p.shift[p.n0 + i] : 0.f;
+    s_wd[i] = p.head_kernel ? p.head_kernel[2 * i + 1] - p.head_kernel[2 * i] : 0.f;
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA0);
+    if (p.C1 > 0) tma_prefetch_desc(&mapA1);
+    tma_prefetch_desc(&mapBh);
+    // the leader's copies of bar_w / row_full / tempty are the ones in use; both CTAs initialise theirs alike
+    mbar_init(&bar_w, 2);
+    for (int s = 0; s < ring_pairs; ++s) { mbar_init(&row_full[s], 2); mbar_init(&row_empty[s], 1); }
+    for (int s = 0; s < (nacc >> 1); ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 8); }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  // Balanced partition over PAIRS of neighbouring 128-pixel columns (N * wsegs is even): pair q of the grid walks its run
+  // of row pairs; CTA `rank` of the pair takes column 2 * pcol + rank
+  const int units_per_col = p.H >> 1;
+  const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+  const long long units = (long long)(p.N * p.wsegs / 2) * units_per_col;
+  const long long u_begin = units * pair / npairs, u_end = units * (pair + 1) / npairs;
+  auto next_strip = [&](long long& u, int& n, int& h0, int& rows, int& w0) -> bool {
+    if (u >= u_end) return false;
+    const int pcol = (int)(u / units_per_col), hu = (int)(u - (long long)pcol * units_per_col);
+    long long take = units_per_col - hu;
+    if (take > u_end - u) take = u_end - u;
+    const int col = 2 * pcol + (int)rank;
+    n = col / p.wsegs; w0 = (col - n * p.wsegs) * 128; h0 = hu * 2;
+    rows = (int)take * 2;
+    u += take;
+    return true;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t l_bar_w = mapa_u32(smem_u32(&bar_w), 0), l_row_full = mapa_u32(smem_u32(row_full), 0);
+      // this CTA's halves of the stacked weights: logical half tile ht of a group = rows [(ht & 1) * hrows, +hrows) of the
+      // weight matrix at tap (dy = 1 - ht / 2, dx) - stacked in the order dy = +1, 0, -1 like the single-CTA kernel
+      mbar_arrive_expect_tx_cluster(l_bar_w, w_bytes);
+      for (int kc = 0; kc < p.nkc; ++kc)
+        for (int dx = 0; dx < 3; ++dx) {
+          uint8_t* g = s_w + (size_t)(kc * 3 + dx) * group_bytes;
+          for (int t0 = 0; t0 < 3; ++t0)
+            for (int run = 1; run + t0 <= 3; ++run) {
+              if (t0 == 2 && run != 1) continue;
+              const uint32_t off = st2_region(t0, run);
+              for (int e = 0; e < run; ++e) {
+                const int ht = 2 * t0 + (int)rank * run + e;
+                const int tap = (2 - (ht >> 1)) * 3 + dx;
+                tma_load_2d_pair(&mapBh, l_bar_w, g + (size_t)(off + e) * half_bytes, tap * K + kc * p.BK, p.n0 + (ht & 1) * hrows);
+              }
+            }
+        }
+      int pos = 0; uint32_t empty_parity = 0xffffffffu;
+      const int kc0 = p.C0 / p.BK;
+      long long u = u_begin;
+      pdl_wait();                // the weights above are static; the activation rows come from the previous kernel
+      for (int n, h0, rows, w0; next_strip(u, n, h0, rows, w0);) {
+        for (int rr = -1; rr <= rows; ++rr) {
+          const int sub = (rr + 1) & 1;
+          if (sub == 0) {
+            mbar_wait(&row_empty[pos], (empty_parity >> pos) & 1u);
+            empty_parity ^= 1u << pos;
+            mbar_arrive_expect_tx_cluster(l_row_full + 8u * pos, 2u * p.nkc * box_bytes);
+          }
+          uint8_t* dst = s_ring + ((size_t)pos * 2 + sub) * row_bytes;
+          for (int kc = 0; kc < p.nkc; ++kc) {
+            const bool second = kc >= kc0;
+            const int cc = (second ? kc - kc0 : kc) * p.BK;
+            tma_load_4d_pair(second ? &mapA1 : &mapA0, l_row_full + 8u * pos, dst + (size_t)kc * p.slot_bytes, cc, w0 - 1, h0 + rr, n);
+          }
+          if (sub == 1 && ++pos == ring_pairs) pos = 0;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {
+      const uint32_t swz = (p.BK == 64) ? SWZ_128B : SWZ_64B;
+      const uint32_t pitch = p.BK * 2u, sbo = 8u * pitch;
+      const int ksteps = p.BK / 16;
+      const uint64_t dbase = make_smem_desc(0, 16, sbo, swz);
+      const uint32_t ring16 = smem_u32(s_ring) >> 4, w16 = smem_u32(s_w) >> 4, rowb16 = row_bytes >> 4;
+      const uint32_t slot16 = (uint32_t)p.slot_bytes >> 4, pitch16 = pitch >> 4, half16 = half_bytes >> 4, group16 = group_bytes >> 4;
+      const uint32_t a_row_full = smem_u32_pinned(row_full), a_row_empty = smem_u32_pinned(row_empty);
+      const uint32_t a_tfull = smem_u32_pinned(bar_tfull), a_tempty = smem_u32_pinned(bar_tempty);
+      const uint32_t id0 = make_idesc_16(256, 0, 0, 0, p.f16), idu = ((uint32_t)p.Cout >> 3) << 17;   // N field += Cout per row
+      const uint32_t nmask = (uint32_t)nacc - 1u, pmask = ((uint32_t)nacc >> 1) - 1u;
+      const int pair_sh = nacc_sh - 1;
+      const uint64_t dW = dbase + w16;
+      const uint32_t C = (uint32_t)p.Cout;
+      mbar_wait(&bar_w, 0);
+      tc_fence_after();
+      // all MMA steps of halo row i of the current strip (`rows` output rows, accumulator of output row 0 = slot j & nmask):
+      // output rows [i-1, i+1] clipped to the strip; a row that opens (i+1) starts with accumulate = 0 on the first step
+      auto issue_row = [&](int i, int rows, uint32_t j, uint64_t dA) {
+        const bool opens = i + 1 < rows;
+        const int o_lo = i - 1 < 0 ? 0 : i - 1, o_hi = i + 1 < rows ? i + 1 : rows - 1;
+        const uint32_t sa = (j + (uint32_t)o_lo) & nmask;
+        const int t0 = o_lo - i + 1;                               // stacked tile of output row o: o - i + 1
+        // a span that crosses the end of the accumulator ring is issued as two MMAs
+        auto span = [&](int cnt, uint32_t step16, uint32_t wo) {
+          if (cnt <= 0) return;
+          const int run = cnt < (int)(nacc - sa) ? cnt : (int)(nacc - sa);
+          umma2_bf16(tmem_base + sa * C, dA + step16, dW + (wo + st2_region(t0, run) * half16), id0 + run * idu, 1u);
+          if (run < cnt)
+            umma2_bf16(tmem_base, dA + step16, dW + (wo + st2_region(t0 + run, cnt - run) * half16), id0 + (cnt - run) * idu, 1u);
+        };
+        bool first = true;
+        for (int kc = 0; kc < p.nkc; ++kc)
+          for (int dx = 0; dx < 3; ++dx)
+            for (int k = 0; k < ksteps; ++k) {
+              const uint32_t step16 = kc * slot16 + dx * pitch16 + 2 * k, wo = (uint32_t)(kc * 3 + dx) * group16 + 2 * k;
+              if (first) {
+                span((opens ? i : o_hi) - o_lo + 1, step16, wo);   // the rows that are already open
+                if (opens)
+                  umma2_bf16(tmem_base + ((j + (uint32_t)(i + 1)) & nmask) * C, dA + step16, dW + (wo + st2_region(2, 1) * half16),
+                             id0 + idu, 0u);
+                first = false;
+              } else {
+                span(o_hi - o_lo + 1, step16, wo);
+              }
+            }
+      };
+      int pp = 0; uint32_t fullpar = 0;
+      uint32_t j = 0;
+      long long u = u_begin;
+      asm volatile(".reg .pred p2_rf, p2_te;");                 // split-phase poll results (see the single-CTA folded loop)
+#ifdef DCB_STRIP_TIMING
+      unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const long long dbg_t0 = clock64();
+#endif
+      for (int n, h0, rows, w0; next_strip(u, n, h0, rows, w0);) {
+        const int half = rows >> 1;
+        bool pre = false, pre_te = false;
+        for (int m = 0; m <= half; ++m) {                         // input (halo) rows h0 + 2m - 1 and h0 + 2m
+          const uint32_t jp = (j >> 1) + (uint32_t)m;             // running index of the output pair P(m)
+          ST_T(c0);
+          ST_DECL(c1);
+          {
+            uint32_t ok_rf = 0, ok_te = 0;
+            if (pre) {
+              asm volatile("selp.u32 %0, 1, 0, p2_rf;" : "=r"(ok_rf));
+              if (pre_te) asm volatile("selp.u32 %0, 1, 0, p2_te;" : "=r"(ok_te));
+            }
+            if (!ok_rf) mbar_wait_a(a_row_full + 8u * pp, (fullpar >> pp) & 1u);
+            fullpar ^= 1u << pp;
+            ST_SET(c1); ST_ACC(0, c0, c1);
+            if (m < half && !ok_te) mbar_wait_a(a_tempty + 8u * (jp & pmask), ((jp >> pair_sh) & 1u) ^ 1u);
+          }
+          tc_fence_after();
+          ST_T(c2); ST_ACC(1, c1, c2);
+          pre = m < half;
+          pre_te = m + 1 < half;
+          if (pre) {                                              // polls of pair m+1, consumed at the top of the next iteration
+            const int ppn = (pp + 1 == ring_pairs) ? 0 : pp + 1;
+            asm volatile("mbarrier.test_wait.parity.shared::cta.b64 p2_rf, [%0], %1;" ::"r"(a_row_full + 8u * ppn),
+                         "r"((fullpar >> ppn) & 1u) : "memory");
+            if (pre_te)
+              asm volatile("mbarrier.test_wait.parity.shared::cta.b64 p2_te, [%0], %1;" ::"r"(a_tempty + 8u * ((jp + 1u) & pmask)),
+                           "r"((((jp + 1u) >> pair_sh) & 1u) ^ 1u) : "memory");
+          }
+          const uint64_t dA0 = dbase + (ring16 + (uint32_t)pp * 2u * rowb16), dA1 = dA0 + rowb16;
+          if (m >= 1 && m < half && (jp & pmask) != 0u) {        // interior pair, its four accumulators are contiguous
+            const uint32_t d0 = tmem_base + (((jp - 1u) & pmask) * 2u) * C;
+            if (ksteps == 4) {
+              fold2_issue_fast<4>(d0, d0 + 2u * C, dA0, dW, id0 + idu, id0 + 2u * idu, id0 + 3u * idu, p.nkc, slot16, pitch16, half16, group16);
+              fold2_issue_fast<4>(d0 + C, d0 + 3u * C, dA1, dW, id0 + idu, id0 + 2u * idu, id0 + 3u * idu, p.nkc, slot16, pitch16, half16, group16);
+            } else {
+              fold2_issue_fast<2>(d0, d0 + 2u * C, dA0, dW, id0 + idu, id0 + 2u * idu, id0 + 3u * idu, p.nkc, slot16, pitch16, half16, group16);
+              fold2_issue_fast<2>(d0 + C, d0 + 3u * C, dA1, dW, id0 + idu, id0 + 2u * idu, id0 + 3u * idu, p.nkc, slot16, pitch16, half16, group16);
+            }
+          } else {
+            issue_row(2 * m - 1, rows, j, dA0);
+            issue_row(2 * m, rows, j, dA1);
+          }
+          ST_T(c3); ST_ACC(2, c2, c3);
+          umma2_commit_both(a_row_empty + 8u * pp);
+          if (m >= 1) umma2_commit_both(a_tfull + 8u * ((jp - 1u) & pmask));   // output pair P(m-1) is complete
+          ST_T(c4); ST_ACC(3, c3, c4); ST_ACC(4, c0, c4);
+#ifdef DCB_STRIP_TIMING
+          dbg_acc[5] += 1;
+#endif
+          if (++pp == ring_pairs) pp = 0;
+        }
+        j += (uint32_t)rows;
+      }
+#ifdef DCB_STRIP_TIMING
+      dbg_acc[6] = (unsigned long long)(clock64() - dbg_t0);
+      for (int q = 0; q < 8; ++q) g_strip_dbg[(blockIdx.x >> 1) * 8 + q] = dbg_acc[q];
+#endif
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int eset = (warp - 2) >> 2;
+    const int m = quarter * 32 + lane;
+    const float head_b = (FUSED && p.head_kernel) ? (p.head_bias[1] - p.head_bias[0]) : 0.f;
+    const uint32_t l_tempty = mapa_u32(smem_u32(bar_tempty), 0);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t pmask = ((uint32_t)nacc >> 1) - 1u;
+    uint32_t j = 0;
+    long long u = u_begin;
+    for (int n, h0, rows, w0; next_strip(u, n, h0, rows, w0);) {
+      for (int t = 0; t < rows; t += 2, j += 2) {
+        const uint32_t jp = j >> 1;
+        if ((int)(jp & 1u) != eset) continue;
+        const uint32_t ta = t_lane + (j & (uint32_t)(nacc - 1)) * (uint32_t)p.Cout, tb = ta + (uint32_t)p.Cout;
+        const int bar_i = (int)(jp & pmask);
+        mbar_wait(&bar_tfull[bar_i], (j >> nacc_sh) & 1u);
+        tc_fence_after();
+        strip_drain_pair<FUSED>(p, ta, tb, n, h0 + t, w0 + m, s_scale, s_shift, s_wd, head_b, lane);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(l_tempty + 8u * bar_i);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();          // the peer may still signal this CTA's barriers / read its shared memory until here
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
 
 // ====================================================================================== flat halo-tile kernel
 // conv3x3 for NARROW images (W <= 64: every level below full resolution of a 128^2 training crop, the deep
@@ -1686,9 +2044,61 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
         if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
         attr_set_strip = true;
       }
+      const bool pdl = policy(DCB_POLICY_PDL) != 0;
+      // CTA-pair variant of the folded loop (cta_group::2 MMAs): the stacked weights take 5/3 of the single-CTA footprint
+      // per CTA (one region per span shape); used when a ring of at least three row pairs still fits next to them
+      if (sp.fold && policy(DCB_POLICY_PAIR) && (sp.N * sp.wsegs) % 2 == 0 && sp.H % 2 == 0 && sm_count() >= 2) {
+        const size_t w2 = ((size_t)15 * sp.nkc * sp.Cout * sp.BK * 2 + 1023) & ~(size_t)1023;
+        const size_t budget = 223 * 1024;
+        const size_t rowb = (size_t)sp.nkc * sp.slot_bytes;
+        int ring2 = w2 < budget ? (int)((budget - w2) / rowb) : 0;
+        if (ring2 > ST_MAX_RING) ring2 = ST_MAX_RING;
+        ring2 &= ~1;
+        if (ring2 >= 6) {
+          CUtensorMap mBh;
+          {
+            const int Ktot = 9 * (C0 + C1);
+            uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)Nout};
+            uint64_t str[1] = {(uint64_t)Ktot * 2};
+            uint32_t box[2] = {(uint32_t)sp.BK, (uint32_t)(sp.Cout / 2)};
+            if (int e = make_map(&mBh, B, 2, dims, str, box, sp.BK * 2)) return e;
+          }
+          static bool attr_set_pair = false;
+          if (!attr_set_pair) {
+            cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_strip2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_tc_strip2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+            if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
+            attr_set_pair = true;
+          }
+          TcStripParams sp2 = sp;
+          sp2.ring = ring2;
+          const size_t dyn2 = w2 + (size_t)ring2 * rowb + 1024;
+          const long long units2 = (long long)(sp.N * sp.wsegs / 2) * (sp.H / 2);
+          const int pairs = units2 < sm_count() / 2 ? (int)units2 : sm_count() / 2;
+          for (sp2.n0 = 0; sp2.n0 < Nout; sp2.n0 += sp2.Cout) {
+            const cudaError_t le = fused ? launch_kc(tapgemm_tc_strip2_kernel<true>, 2 * pairs, ST_THREADS, dyn2, st, pdl, 2, mA0, mA1, mBh, sp2)
+                                         : launch_kc(tapgemm_tc_strip2_kernel<false>, 2 * pairs, ST_THREADS, dyn2, st, pdl, 2, mA0, mA1, mBh, sp2);
+            if (le != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of tapgemm_tc_strip2_kernel failed: %s", cudaGetErrorString(le));
+            g_launches += 1;
+          }
+          note_kernel(fused ? "strip_pair_fused" : (sp.Cout < Nout ? "strip_pair_nsplit" : "strip_pair"));
+#ifdef DCB_STRIP_TIMING
+          if (getenv("DCB_STRIP_TIMING_PRINT")) {
+            cudaStreamSynchronize(st);
+            static unsigned long long h[148 * 8];
+            cudaMemcpyFromSymbol(h, g_strip_dbg, sizeof(h));
+            double a[8] = {0};
+            for (int b = 0; b < pairs; ++b) for (int q = 0; q < 8; ++q) a[q] += (double)h[b * 8 + q] / pairs;
+            fprintf(stderr, "[strip pair timing] per leader: steps (two halo rows of both CTAs) %.0f | cycles/step: row_full wait %.0f, tempty wait "
+                    "%.0f, issue %.0f, commit %.0f, total %.0f | loop cycles %.0f\n", a[5], a[0] / a[5], a[1] / a[5], a[2] / a[5], a[3] / a[5],
+                    a[4] / a[5], a[6]);
+          }
+#endif
+          return DCB_OK;
+        }
+      }
       const long long units = (long long)sp.N * sp.wsegs * cdiv(sp.H, sp.gran);
       const int grid = units < sm_count() ? (int)units : sm_count();
-      const bool pdl = policy(DCB_POLICY_PDL) != 0;
       for (sp.n0 = 0; sp.n0 < Nout; sp.n0 += sp.Cout) {          // one launch per group of output channels
         cudaError_t le;
         if (fused && sp.fold) le = launch_k(tapgemm_tc_strip_kernel<true, true>, grid, ST_THREADS, dyn, st, pdl, mA0, mA1, mT0, mT1, mB, sp);

@@ -22,7 +22,7 @@ c_sz = ctypes.c_size_t
 DCB_F32, DCB_BF16, DCB_F16 = 0, 1, 2
 # dcb_policy_key (include/dcb200.h)
 POLICY_KEYS = {'flat': 0, 'strip': 1, 'fold': 2, 'nsplit': 3, 'swap_min_cout': 4, 'wgrad_strip': 5, 'bn_ctas_per_sm': 6,
-               'proj_i16_splits': 7, 'splitk': 8, 'fused_bn': 9, 'tma_store': 10, 'bn_slab': 11, 'pdl': 12}
+               'proj_i16_splits': 7, 'splitk': 8, 'fused_bn': 9, 'tma_store': 10, 'bn_slab': 11, 'pdl': 12, 'pair': 13}
 LOSS_IDS = {'binary_crossentropy': 0, 'weighted_binary_crossentropy': 1, 'dice_loss': 2, 'dicesq_loss': 3}
 
 

@@ -68,7 +68,8 @@ enum dcb_policy_key {
   DCB_POLICY_PDL = 12,          /* programmatic dependent launch of the forward conv / TTA kernels: 0 off, 1 on.  Turn on only while
                                    enqueueing work whose per-channel scale / shift / weights are NOT written by kernels of the same
                                    stream sequence (inference): prologues read them before the dependency wait */
-  DCB_POLICY_COUNT = 13
+  DCB_POLICY_PAIR = 13,         /* folded strip conv on CTA-pair MMAs (tcgen05 cta_group::2, clusters of two): 0 off, 1 on */
+  DCB_POLICY_COUNT = 14
 };
 int dcb_set_policy(int key, int value);
 int dcb_get_policy(int key, int* value);

@@ -4,6 +4,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'deep-calcium_b200'))
 import numpy as np, torch
 from deepcalcium.engine import ops
+from deepcalcium import _native as nat
+for kv in filter(None, os.environ.get('DCB_POLICY', '').split(',')):     # e.g. DCB_POLICY=pair=1,strip=0
+    nat.set_policy(**{kv.split('=')[0]: int(kv.split('=')[1])})
 N, H, W, Cin, Cout = (int(v) for v in sys.argv[1:6])
 mode = sys.argv[6] if len(sys.argv) > 6 else 'plain'
 dt = torch.bfloat16
@@ -32,4 +35,4 @@ e0.record()
 for _ in range(10):
     run()
 e1.record(); torch.cuda.synchronize()
-print('%s %s: %.4f ms per launch' % (sys.argv[1:6], mode, e0.elapsed_time(e1) / 10))
+print('%s %s [%s]: %.4f ms per launch' % (sys.argv[1:6], mode, nat.last_kernel(), e0.elapsed_time(e1) / 10))

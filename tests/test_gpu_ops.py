@@ -47,6 +47,8 @@ FWD_VARIANTS = [
     ('strip_no_nsplit', dict(nsplit=0)),
     ('generic_tma_store', dict(strip=0, flat=0, swap_min_cout=0, tma_store=2)),   # generic kernel, outputs through TMA stores
     ('no_tma_store', dict(tma_store=0)),
+    ('strip_pair', dict(pair=1)),                                 # folded strip loop on CTA-pair (cta_group::2) MMAs
+    ('strip_single', dict(pair=0)),
 ]
 WGRAD_VARIANTS = [('default', {}), ('generic', dict(wgrad_strip=0))]
 
@@ -74,6 +76,13 @@ CONV_CASES = [
     (1, 16, 64, 64, 0, 64),
     (2, 8, 64, 64, 64, 64),
     (1, 8, 128, 64, 32, 32),
+    # CTA-pair strip kernel: column pairs inside a row / across images, strips longer than the accumulator ring
+    # (wrapping spans), every channel combination it takes
+    (2, 8, 128, 32, 0, 32),
+    (1, 6, 256, 32, 0, 64),
+    (2, 44, 256, 64, 0, 32),
+    (1, 40, 512, 64, 0, 64),
+    (2, 36, 128, 32, 32, 64),
     # enough 256-pixel tiles for the swapped (weights-as-A) orientation of the generic kernel
     (8, 64, 64, 64, 0, 128),
     (5, 48, 80, 64, 64, 64),
@@ -202,7 +211,7 @@ def test_convT2x2_fwd_dgrad_wgrad(cuda, precision, case):
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
-@pytest.mark.parametrize('shape', [(2, 16, 128, 32, 32), (1, 6, 256, 64, 64), (1, 8, 24, 32, 32),
+@pytest.mark.parametrize('shape', [(2, 16, 128, 32, 32), (1, 6, 256, 64, 64), (1, 8, 24, 32, 32), (2, 40, 256, 32, 32), (1, 44, 512, 64, 32),
                                    # pooled epilogue of the generic kernel: pixels-as-M tiles (several tile shapes, an N tile
                                    # narrower than Cout), weights-as-M tiles of 128x2 and 64x4 pixels
                                    (2, 32, 32, 128, 128), (3, 8, 8, 256, 256), (8, 64, 64, 128, 256),
@@ -228,8 +237,14 @@ def test_conv3x3_fused_pool_and_head_equal_the_unfused_composition(cuda, precisi
     ops.maxpool2x2(y, pool)
     logit = torch.empty(N, H, W, device='cuda'); prob = torch.empty(N, H, W, device='cuda')
     ops.head_fwd(y, hk, hb, logit, prob)
-    y2 = torch.empty_like(y); pool2 = torch.empty_like(pool)
     from deepcalcium import _native as nat
+    for pair in (1, 0):          # CTA-pair / single-CTA strip kernel (where the shape takes the strip kernel at all)
+        with nat.policy(pair=pair):
+            _check_fused(ops, nat, precision, shape, x, wf, scale, shift, hk, hb, y, pool, logit, prob)
+
+
+def _check_fused(ops, nat, precision, shape, x, wf, scale, shift, hk, hb, y, pool, logit, prob):
+    y2 = torch.empty_like(y); pool2 = torch.empty_like(pool)
     ops.conv3x3_fwd_fused(x, None, wf, y2, scale, shift, True, pool_out=pool2)
     print('fused pool %s %s -> %s' % (precision, shape, nat.last_kernel() if precision == 'bf16' else 'fp32 composition'))
     def same(a, b):
