@@ -234,6 +234,55 @@ def cpu_baselines(w, img_host):
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
+def ncu_conv_traffic(precision):
+    """DRAM traffic of the conv launches of ONE 8-image forward, measured in this run: `ncu --metrics dram__bytes_*` around
+    scripts/profile_step.py (same engine, same weights, eager launches) as a subprocess, outside every timed region.
+    Returns (bytes per step, per-kernel rows, description) or None when ncu is unavailable / fails (DCB_BENCH_NCU=0 skips it)."""
+    import csv
+    import io
+    import shutil
+    import subprocess
+    if os.environ.get('DCB_BENCH_NCU', '1') == '0' or shutil.which('ncu') is None:
+        return None
+    metrics = 'dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'
+    cmd = ['ncu', '--metrics', metrics, '--clock-control', 'none', '--csv', '-k', 'regex:tapgemm_tc|conv3x3_c1_fwd',
+           sys.executable, os.path.join(ROOT, 'scripts', 'profile_step.py'), 'infer', {'fp16': 'f16'}.get(precision, precision)]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get(
+            'CUDA_VISIBLE_DEVICES', '0'))).stdout
+    except Exception:   # noqa: BLE001
+        return None
+    lines = [ln for ln in out.splitlines() if ln.startswith('"')]
+    if len(lines) < 2:
+        return None
+    rows = list(csv.DictReader(io.StringIO('\n'.join(lines))))
+    per = {}
+    order = []
+    for r in rows:
+        kid = r['ID']
+        if kid not in per:
+            per[kid] = {'kernel': r['Kernel Name'].split('(')[0].replace('void dcb::', '').replace('dcb::', '')[:40]}
+            order.append(kid)
+        v = float(r['Metric Value'].replace(',', ''))
+        u = r['Metric Unit']
+        scale = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0, 'us': 1.0, 'ns': 1e-3, 'ms': 1e3, 'msecond': 1e3, 'usecond': 1.0,
+                 'nsecond': 1e-3, 'second': 1e6}.get(u, 1.0)
+        per[kid][r['Metric Name']] = v * scale
+    if len(order) % 3 != 0:          # profile_step.py runs three identical steps
+        return None
+    last = order[-(len(order) // 3):]
+    klist, tot = [], 0.0
+    for kid in last:
+        d = per[kid]
+        rd, wr = d.get('dram__bytes_read.sum', 0.0), d.get('dram__bytes_write.sum', 0.0)
+        tot += rd + wr
+        klist.append({'kernel': d['kernel'], 'us': round(d.get('gpu__time_duration.sum', 0.0), 1), 'dram_read_MB': round(rd / 1e6, 1),
+                      'dram_write_MB': round(wr / 1e6, 1),
+                      'tensor_pipe_active_pct': round(d.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 0.0), 1)})
+    return tot, klist, ('measured in this run: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum around the %d conv launches of one '
+                        'eager 8-image forward (scripts/profile_step.py, subprocess, outside the timed regions)' % len(last))
+
+
 def per_layer_profile(eng, sess, spec, NB, H, W):
     """device time of every contraction launch of one forward pass (CUDA events on the launch stream,
     eager mode) -> (rows, total conv flops, total conv ms)."""
@@ -396,8 +445,11 @@ def run_ours(args):
             sess = eng._session(8, 512, 512, False)
             rows, tot_f, tot_ms = per_layer_profile(eng, sess, spec, 8, 512, 512)
             ach = tot_f / tot_ms / 1e9
-            traffic, traffic_src = None, None
-            for name in ('r2_conv_traffic.json', 'r1_conv_traffic.json'):
+            traffic, traffic_src, traffic_kernels = None, None, None
+            live = ncu_conv_traffic(args.precision) if world == 1 else None
+            if live is not None:
+                traffic, traffic_kernels, traffic_src = live
+            for name in (() if live is not None else ('r2_conv_traffic.json', 'r1_conv_traffic.json')):
                 try:   # dram__bytes_read.sum + dram__bytes_write.sum over the same tensor-core launches (ncu --set full capture)
                     with open(os.path.join(ROOT, 'profiles', name)) as f:
                         traffic = json.load(f)['dram_bytes_per_step']
@@ -417,6 +469,8 @@ def run_ours(args):
                                 'note': 'conv_ms_per_step sums eagerly launched kernels (launch gaps included); ms_per_step is '
                                         'the CUDA-graph replay of the whole step (all kernels incl. first layer, TTA batch/combine)'}
             line['per_layer'] = rows
+            if traffic_kernels is not None:
+                line['roofline']['ncu_launches'] = traffic_kernels
         except Exception as ex:   # noqa: BLE001
             line['roofline'] = {'error': repr(ex)}
         # ---- parity of exactly what was timed (outside the timed region)
