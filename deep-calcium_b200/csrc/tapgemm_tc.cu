@@ -613,6 +613,31 @@ __device__ __forceinline__ void fold_issue_fast(uint32_t d0, uint32_t d2, uint64
 
 constexpr int ST_MAX_RING = 12;
 
+// ---- thread-block cluster helpers (CTA-pair kernels below)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bulk-tensor load delivered to the same shared-memory offset of every CTA in ctaMask; each destination CTA's mbarrier (same
+// offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+      : "memory");
+}
+// single-CTA MMAs, completion signalled on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_mc2(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar_addr), "h"((uint16_t)3) : "memory");
+}
+
 // -DDCB_STRIP_TIMING: the folded MMA thread accumulates clock64() intervals (diagnostic builds only)
 #ifdef DCB_STRIP_TIMING
 __device__ unsigned long long g_strip_dbg[148 * 8];
@@ -638,6 +663,9 @@ struct TcStripParams {
   int swap;                 // 1: 256-pixel segments, weights as the MMA A operand (see TcFwdParams::swap)
   int fold;                 // 1: the three vertical taps are folded into the MMA N dimension (see the kernel comment)
   int OC, n0;               // output tensor channel pitch and first output channel of this launch (Cout = channels computed here)
+  int nclu;                 // 2: clusters of two CTAs compute the two Cout-channel halves of the SAME pixels (folded mode): CTA r
+                            // takes channels n0 + r*Cout.., each halo row is fetched once and TMA-multicast into both CTAs
+                            // (the two channel-split launches of a 128 -> 64 layer each read the whole input)
   // optional epilogue fusions (normal orientation only)
   const float* head_kernel; // [Cout][2] softmax head (unet_2d_summary.py:221-222): emit logit / prob per pixel
   const float* head_bias;   // [2]
@@ -660,9 +688,9 @@ struct TcStripParams {
 template <bool FUSED>
 __device__ __forceinline__ void strip_drain_pair(const TcStripParams& p, uint32_t ta, uint32_t tb, int n, int row, int px,
                                                  const float* s_scale, const float* s_shift, const float* s_wd, float head_b,
-                                                 int lane) {
+                                                 int lane, int n0) {
   const size_t opix_a = ((size_t)n * p.H + row) * p.W + px, opix_b = opix_a + p.W;
-  const size_t oidx_a = opix_a * p.OC + p.n0, oidx_b = opix_b * p.OC + p.n0;
+  const size_t oidx_a = opix_a * p.OC + n0, oidx_b = opix_b * p.OC + n0;
   if (p.out_f32) {                                       // gradient tensors (dgrad): fp32 stores, row by row
 #pragma unroll 1
     for (int rr = 0; rr < 2; ++rr) {
@@ -786,6 +814,9 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   __shared__ __align__(16) float s_scale[128], s_shift[128], s_wd[128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) pdl_trigger();
+  const int nclu = (FOLD && p.nclu > 1) ? p.nclu : 1;
+  const uint32_t crank = nclu > 1 ? cluster_ctarank() : 0u;
+  const int n0 = p.n0 + (int)crank * p.Cout;                     // first output channel of THIS CTA
   const int PX = p.swap ? 256 : 128;                             // pixels per tile (one image-row segment)
   // 1024-byte alignment as an offset into the __shared__ array (an integer round trip would turn every later access
   // through this pointer into a generic-space load/store)
@@ -809,8 +840,8 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   while (tmem_cols < (uint32_t)(nacc * acc_cols)) tmem_cols <<= 1;
 
   for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
-    s_scale[i] = p.scale ? p.scale[p.n0 + i] : 1.f;
-    s_shift[i] = p.shift ? p.shift[p.n0 + i] : 0.f;
+    s_scale[i] = p.scale ? p.scale[n0 + i] : 1.f;
+    s_shift[i] = p.shift ? p.shift[n0 + i] : 0.f;
     s_wd[i] = p.head_kernel ? p.head_kernel[2 * i + 1] - p.head_kernel[2 * i] : 0.f;
   }
   if (warp == 0 && lane == 0) {
@@ -818,13 +849,15 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
     if (p.C1 > 0) tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapB);
     mbar_init(&bar_w, 1);
-    for (int s = 0; s < p.ring; ++s) { mbar_init(&row_full[s], 1); mbar_init(&row_empty[s], 1); }
+    // a ring slot shared by a cluster is free once BOTH CTAs' MMAs have read it (each MMA thread commits to both)
+    for (int s = 0; s < p.ring; ++s) { mbar_init(&row_full[s], 1); mbar_init(&row_empty[s], nclu); }
     for (int s = 0; s < nacc; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 4); }
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(&tmem_base_smem, tmem_cols); tmem_relinquish(); }
   tc_fence_before();
-  __syncthreads();
+  if (nclu > 1) cluster_sync_all();      // the peer's barriers exist before anything is multicast into this CTA
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
@@ -833,7 +866,9 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   // column boundary - so every SM gets the same number of rows (+-1 unit) and one 2-row halo per strip.
   const int units_per_col = (p.H + p.gran - 1) / p.gran;
   const long long units = (long long)p.N * p.wsegs * units_per_col;
-  const long long u_begin = units * blockIdx.x / gridDim.x, u_end = units * (blockIdx.x + 1) / gridDim.x;
+  // (the CTAs of a cluster walk the same strips)
+  const long long part = blockIdx.x / nclu, nparts = gridDim.x / nclu;
+  const long long u_begin = units * part / nparts, u_end = units * (part + 1) / nparts;
   auto next_strip = [&](long long& u, int& n, int& h0, int& rows, int& w0) -> bool {
     if (u >= u_end) return false;
     const int col = (int)(u / units_per_col), hu = (int)(u - (long long)col * units_per_col);
@@ -853,7 +888,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
         for (int kc = 0; kc < p.nkc; ++kc)
           tma_load_2d(&mapB, &bar_w,
                       s_w + (size_t)(FOLD ? (kc * 3 + tap % 3) * 3 + (2 - tap / 3) : tap * p.nkc + kc) * wblk_bytes,
-                      tap * K + kc * p.BK, p.n0);   // folded: (kc, dx) groups of three stacked tiles, dy = +1, 0, -1
+                      tap * K + kc * p.BK, n0);   // folded: (kc, dx) groups of three stacked tiles, dy = +1, 0, -1
       int pos = 0; uint32_t empty_parity = 0xffffffffu;          // bit i: parity to wait for on row_empty[i]
       const int kc0 = p.C0 / p.BK;
 #ifdef DCB_STRIP_TIMING
@@ -880,6 +915,11 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
           for (int kc = 0; kc < p.nkc; ++kc) {
             const bool second = kc >= kc0;
             const int cc = (second ? kc - kc0 : kc) * p.BK;
+            if (nclu > 1) {      // each CTA of the pair fetches every other channel chunk and multicasts it into both
+              if ((kc & 1) == (int)crank)
+                tma_load_4d_mc(second ? &mapA1 : &mapA0, &row_full[pos], dst + (size_t)kc * p.slot_bytes, cc, w0 - 1, h0 + rr, n, 3);
+              continue;
+            }
             tma_load_4d(second ? &mapA1 : &mapA0, &row_full[pos], dst + (size_t)kc * p.slot_bytes, cc, w0 - 1, h0 + rr, n);
             if (p.swap)   // 258-pixel halo row = a 256-pixel box + a 2-pixel box (TMA boxes are limited to 256 per dim)
               tma_load_4d(second ? &mapT1 : &mapT0, &row_full[pos], dst + (size_t)kc * p.slot_bytes + 256u * p.BK * 2u, cc,
@@ -1013,7 +1053,8 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
               issue_row_generic(2 * m, rows, dA1);
             }
             ST_T(c3); ST_ACC(2, c2, c3);
-            umma_commit_a(a_row_empty + 8u * pp);
+            if (nclu > 1) umma_commit_mc2(a_row_empty + 8u * pp);                 // the slot is shared with the peer CTA
+            else umma_commit_a(a_row_empty + 8u * pp);
             if (m >= 1) umma_commit_a(a_tfull + 8u * ((jp - 1u) & pmask));       // output pair P(m-1) is complete
             ST_T(c4); ST_ACC(3, c3, c4); ST_ACC(4, c0, c4);
             if (++pp == ring_pairs) pp = 0;
@@ -1079,7 +1120,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
           const int bar_i = (int)(jp & pmask);
           mbar_wait(&bar_tfull[bar_i], (j >> nacc_sh) & 1u);
           tc_fence_after();
-          strip_drain_pair<FUSED>(p, ta, tb, n, h0 + t, w0 + m, s_scale, s_shift, s_wd, head_b, lane);
+          strip_drain_pair<FUSED>(p, ta, tb, n, h0 + t, w0 + m, s_scale, s_shift, s_wd, head_b, lane, n0);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_tempty[bar_i]);
@@ -1262,10 +1303,10 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
 #endif
   }
   tc_fence_before();
-  __syncthreads();
+  if (nclu > 1) cluster_sync_all();      // the peer may still multicast into this CTA / commit to its barriers until here
+  else __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
-
 
 // ====================================================================================== CTA-pair folded strip kernel
 // The folded strip loop on PAIR MMAs (tcgen05 cta_group::2, a cluster of two CTAs on neighbouring SMs): one instruction
@@ -1288,19 +1329,10 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
 __device__ __forceinline__ uint32_t st2_region(int t0, int run) {
   return run == 3 ? 7u : (run == 2 ? (t0 == 0 ? 3u : 5u) : (uint32_t)t0);
 }
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // arrive / arrive.expect_tx on a barrier of any CTA of the cluster (shared::cluster address, e.g. from mapa_u32).
 // RELAXED on purpose: the release form at cluster scope compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive, i.e.
@@ -1600,7 +1632,7 @@ tapgemm_tc_strip2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid
         const int bar_i = (int)(jp & pmask);
         mbar_wait(&bar_tfull[bar_i], (j >> nacc_sh) & 1u);
         tc_fence_after();
-        strip_drain_pair<FUSED>(p, ta, tb, n, h0 + t, w0 + m, s_scale, s_shift, s_wd, head_b, lane);
+        strip_drain_pair<FUSED>(p, ta, tb, n, h0 + t, w0 + m, s_scale, s_shift, s_wd, head_b, lane, p.n0);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(l_tempty + 8u * bar_i);
@@ -2099,6 +2131,18 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
       }
       const long long units = (long long)sp.N * sp.wsegs * cdiv(sp.H, sp.gran);
       const int grid = units < sm_count() ? (int)units : sm_count();
+      // channel-split layer (two groups of output channels): ONE launch of two-CTA clusters that share every halo row
+      // through TMA multicast instead of two launches that each read the whole input
+      if (sp.fold && !fused && Nout == 2 * sp.Cout && sp.nkc % 2 == 0 && policy(DCB_POLICY_NSPLIT) == 1 && sm_count() >= 2) {
+        sp.n0 = 0; sp.nclu = 2;
+        const int parts = units < sm_count() / 2 ? (int)units : sm_count() / 2;
+        const cudaError_t le = launch_kc(tapgemm_tc_strip_kernel<false, true>, 2 * parts, ST_THREADS, dyn, st, pdl, 2, mA0, mA1, mT0, mT1, mB, sp);
+        if (le != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of tapgemm_tc_strip_kernel (cluster) failed: %s", cudaGetErrorString(le));
+        g_launches += 1;
+        note_kernel("strip_fold_nsplit_cluster");
+        return DCB_OK;
+      }
+      sp.nclu = 1;
       for (sp.n0 = 0; sp.n0 < Nout; sp.n0 += sp.Cout) {          // one launch per group of output channels
         cudaError_t le;
         if (fused && sp.fold) le = launch_k(tapgemm_tc_strip_kernel<true, true>, grid, ST_THREADS, dyn, st, pdl, mA0, mA1, mT0, mT1, mB, sp);

@@ -56,7 +56,7 @@ enum dcb_policy_key {
   DCB_POLICY_FLAT = 0,          /* flat halo-tile conv kernel: 0 never, 1 auto (size gate), 2 whenever the shape is eligible */
   DCB_POLICY_STRIP = 1,         /* halo-strip conv kernel: 0 off, 1 on */
   DCB_POLICY_FOLD = 2,          /* vertical-tap folding inside the strip kernel: 0 off, 1 on */
-  DCB_POLICY_NSPLIT = 3,        /* channel-split strip launches when the weights do not fit: 0 off, 1 on */
+  DCB_POLICY_NSPLIT = 3,        /* channel-split strip conv when the weights do not fit: 0 off, 1 one launch of two-CTA clusters sharing the halo rows by TMA multicast, 2 two launches */
   DCB_POLICY_SWAP_MIN_COUT = 4, /* smallest Cout that uses the weights-as-A orientation (0 = never) */
   DCB_POLICY_WGRAD_STRIP = 5,   /* strip weight-gradient kernel: 0 off, 1 on */
   DCB_POLICY_BN_CTAS_PER_SM = 6,

@@ -45,6 +45,7 @@ FWD_VARIANTS = [
     ('strip_nofold', dict(fold=0)),                               # strip kernel, plain / swapped issue
     ('strip_plain', dict(fold=0, swap_min_cout=0)),               # strip kernel, pixels-as-M, 9 taps issued separately
     ('strip_no_nsplit', dict(nsplit=0)),
+    ('strip_nsplit_two_launches', dict(nsplit=2)),                # default 1 = one launch of two-CTA clusters (TMA multicast)
     ('generic_tma_store', dict(strip=0, flat=0, swap_min_cout=0, tma_store=2)),   # generic kernel, outputs through TMA stores
     ('no_tma_store', dict(tma_store=0)),
     ('strip_pair', dict(pair=1)),                                 # folded strip loop on CTA-pair (cta_group::2) MMAs
@@ -70,7 +71,8 @@ CONV_CASES = [
     (1, 9, 512, 32, 32, 32),
     (2, 11, 64, 32, 0, 64),
     (4, 128, 128, 32, 32, 32),
-    (2, 6, 128, 64, 64, 64),      # weights too large for one strip launch: two launches of 32 output channels
+    (2, 6, 128, 64, 64, 64),      # weights too large for one strip launch: output channels split over a CTA pair / two launches
+    (3, 38, 256, 64, 64, 64),
     (1, 4, 256, 64, 64, 64),
     # 64-channel sources on 64-pixel rows: strip wgrad over two / three / four 32-channel blocks
     (1, 16, 64, 64, 0, 64),
