@@ -113,6 +113,8 @@ template <typename T, int VEC, bool POOL>
 __global__ void __launch_bounds__(256)
 bn_train_fwd_kernel(const BnFwdParams p) {
   extern __shared__ double s_dyn[];
+  if (threadIdx.x == 0) pdl_trigger();     // programmatic dependent launch: the grid is resident when the producer finishes
+  pdl_wait();
   const int C = p.C, V = 2 * C;
   const T* __restrict__ x = reinterpret_cast<const T*>(p.x);
   const int lanes_c = C / VEC, rows_par = 256 / lanes_c;
@@ -269,6 +271,8 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 bn_train_bwd_kernel(const BnBwdParams p) {
   extern __shared__ double s_dyn[];
+  if (threadIdx.x == 0) pdl_trigger();
+  pdl_wait();
   const int C = p.C, V = 2 * C;
   const T* __restrict__ x = reinterpret_cast<const T*>(p.x);
   unsigned long long seed = p.seed;
@@ -441,6 +445,8 @@ template <typename T, bool POOL>
 __global__ void __launch_bounds__(SLAB_THREADS)
 bn_slab_fwd_kernel(const BnFwdParams p, const SlabGeom gm) {
   __shared__ float sh[SLAB_THREADS * SLAB_PITCH];
+  if (threadIdx.x == 0) pdl_trigger();
+  pdl_wait();
   __shared__ double cta_tot[64], s_tot[64];
   __shared__ float s_sc[32], s_sh[32];
   cg::cluster_group cluster = cg::this_cluster();
@@ -579,6 +585,8 @@ template <typename T>
 __global__ void __launch_bounds__(SLAB_THREADS)
 bn_slab_bwd_kernel(const BnBwdParams p, const SlabGeom gm) {
   __shared__ float sh[SLAB_THREADS * SLAB_PITCH];
+  if (threadIdx.x == 0) pdl_trigger();
+  pdl_wait();
   __shared__ double cta_tot[64], s_tot[64];
   cg::cluster_group cluster = cg::this_cluster();
   const int C = p.C, CW = gm.CW, S = gm.S;
@@ -727,10 +735,12 @@ static int launch_slab(K kernel, const P& p, const SlabGeom& gm, cudaStream_t st
   cfg.blockDim = dim3(SLAB_THREADS, 1, 1);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = (unsigned)gm.S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = policy(DCB_POLICY_PDL) != 0 ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p, gm);
   if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e));
   g_launches += 1;
@@ -809,9 +819,11 @@ static int launch_bn_fwd(BnFwdParams& p, void* ws, size_t ws_bytes, cudaStream_t
   if (!ws || ws_bytes < need) return fail(DCB_ERR_WORKSPACE, "dcb_bn_train_fwd: workspace %zu B < required %zu B", ws_bytes, need);
   p.partial = reinterpret_cast<double*>(ws);
   p.totals = p.partial + (size_t)grid * 2 * p.C;
-  bn_train_fwd_kernel<T, VEC, POOL><<<grid, 256, smem, st>>>(p);
+  {
+    const cudaError_t le = launch_k(bn_train_fwd_kernel<T, VEC, POOL>, grid, 256, smem, st, policy(DCB_POLICY_PDL) != 0, p);
+    if (le != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of bn_train_fwd_kernel failed: %s", cudaGetErrorString(le));
+  }
   g_launches += 1;
-  DCB_LAUNCH_OK("bn_train_fwd_kernel");
   return DCB_OK;
 }
 
@@ -862,9 +874,11 @@ static int launch_bn_bwd(BnBwdParams& p, void* ws, size_t ws_bytes, cudaStream_t
   if (!ws || ws_bytes < need) return fail(DCB_ERR_WORKSPACE, "dcb_bn_train_bwd: workspace %zu B < required %zu B", ws_bytes, need);
   p.partial = reinterpret_cast<double*>(ws);
   p.totals = p.partial + (size_t)grid * 2 * p.C;
-  bn_train_bwd_kernel<T, VEC><<<grid, 256, smem, st>>>(p);
+  {
+    const cudaError_t le = launch_k(bn_train_bwd_kernel<T, VEC>, grid, 256, smem, st, policy(DCB_POLICY_PDL) != 0, p);
+    if (le != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of bn_train_bwd_kernel failed: %s", cudaGetErrorString(le));
+  }
   g_launches += 1;
-  DCB_LAUNCH_OK("bn_train_bwd_kernel");
   return DCB_OK;
 }
 

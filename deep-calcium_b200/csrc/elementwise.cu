@@ -435,6 +435,8 @@ __global__ void pool_bwd_add_kernel(const float* __restrict__ skipgrad, int lds,
                                     int C, float* __restrict__ out) {
   const int OH = H / 2, OW = W / 2, c4n = C >> 2;
   const long long n4 = (long long)N * OH * OW * c4n;
+  if (threadIdx.x == 0) pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     long long t = i;
     const int c = (int)(t % c4n) * 4; t /= c4n;
@@ -1001,10 +1003,13 @@ extern "C" int dcb_pool_bwd_add(int dtype, const float* skipgrad, int lds, int o
                                 const float* dpool, int N, int H, int W, int C, float* out, dcb_stream_t stream) {
   DCB_CHECK_ARG(y && pooled && dpool && out && N > 0 && H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "dcb_pool_bwd_add: bad arguments");
   DCB_CHECK_ARG(!skipgrad || (lds % 4 == 0 && offs % 4 == 0 && offs + C <= lds), "dcb_pool_bwd_add: bad skip-gradient view");
-  DISPATCH_T(dtype, pool_bwd_add_kernel<T><<<ew_grid((long long)N * (H / 2) * (W / 2) * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(
-      (const float*)skipgrad, lds, offs, (const T*)y, (const T*)pooled, (const float*)dpool, N, H, W, C, (float*)out);)
+  DISPATCH_T(dtype, {
+    const cudaError_t le = launch_k(pool_bwd_add_kernel<T>, ew_grid((long long)N * (H / 2) * (W / 2) * (C / 4), 256), 256, 0,
+                                    (cudaStream_t)stream, policy(DCB_POLICY_PDL) != 0, (const float*)skipgrad, lds, offs, (const T*)y,
+                                    (const T*)pooled, (const float*)dpool, N, H, W, C, (float*)out);
+    if (le != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of pool_bwd_add_kernel failed: %s", cudaGetErrorString(le));
+  })
   g_launches += 1;
-  DCB_LAUNCH_OK("pool_bwd_add_kernel");
   return DCB_OK;
 }
 

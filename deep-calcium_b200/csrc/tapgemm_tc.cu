@@ -1686,6 +1686,7 @@ tapgemm_tc_flat_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
   __shared__ uint64_t pb_full[2], pb_empty[2], w_full[2], w_empty[2], bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_base_smem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) pdl_trigger();
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_pb = smem;                                   // 2 pixel buffers
   uint8_t* s_w = s_pb + 2u * p.pbuf_bytes;                // 2 weight slots
@@ -1724,6 +1725,7 @@ tapgemm_tc_flat_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
     if (elect_one()) {
       const int kc0 = p.C0 / 64;
       int pb = 0, ws = 0; uint32_t pb_par = 0, ws_par = 0;   // parities of the NEXT use of each slot's empty barrier
+      pdl_wait();                                            // the activations come from the previous kernel of the stream
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         int n, f0, mt, y_lo;
         decode(item, n, f0, mt, y_lo);
@@ -1990,9 +1992,11 @@ static int run_tc_flat(const TapGeom& g, const void* s0, int C0, const void* s1,
   const size_t dyn = 2 * (size_t)pbuf + 2 * (size_t)FL_WSLOT + 4 * 4096 + 1024;
   const int items = p.N * p.ptiles * p.mtiles;
   const int grid = items < sm_count() ? items : sm_count();
-  tapgemm_tc_flat_kernel<<<grid, FL_THREADS, dyn, st>>>(mA0, mA1, mB, p);
+  {
+    const cudaError_t le = launch_k(tapgemm_tc_flat_kernel, grid, FL_THREADS, dyn, st, policy(DCB_POLICY_PDL) != 0, mA0, mA1, mB, p);
+    if (le != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of tapgemm_tc_flat_kernel failed: %s", cudaGetErrorString(le));
+  }
   g_launches += 1;
-  DCB_LAUNCH_OK("tapgemm_tc_flat_kernel");
   note_kernel("flat");
   return DCB_OK;
 }

@@ -62,6 +62,9 @@ class UNetEngine(object):
         self.comm = None          # engine.dist.Comm for data-parallel training (None = single GPU)
         self.overlap_wgrad = True  # weight-gradient launches on a side stream (see _train_step_enqueue)
         self.pdl = os.environ.get('DCB_PDL', '1') != '0'   # programmatic dependent launch in the inference forward
+        # ... along the main chain of the training step it LOSES (2.81 -> 3.14 ms, scripts/train_time.py): the early-resident
+        # CTAs of the next main-chain kernel take the SM slots in which the weight-gradient side stream overlapped
+        self.pdl_train = os.environ.get('DCB_PDL_TRAIN', '0') != '0'
         self._side = None
         self.set_weights_dict(he_normal_weights(self.spec, seed=0))
 
@@ -591,8 +594,11 @@ class UNetEngine(object):
         key = ('train', loss_id, float(lr), bool(dropout), beta1, beta2, eps)
         # the weights-as-M orientation of the generic kernel pays on the 512^2 inference shapes but not on the small
         # images of a training crop (profiles/r2_swap_sweep.txt): pinned off while the step is enqueued / captured
+        # Programmatic dependent launch along the main chain is available (pdl_train; the conv / dgrad kernels read only the
+        # step's static data before their dependency wait, the BatchNorm / pooling kernels wait at entry) but off by default,
+        # see __init__.  Cross-stream edges (the weight-gradient side stream) are ordinary full dependencies either way.
         def enqueue():
-            with nat.policy(swap_min_cout=0):
+            with nat.policy(swap_min_cout=0, pdl=1 if self.pdl_train else 0):
                 self._train_step_enqueue(s, loss_id, lr, dropout, beta1, beta2, eps)
         self._run_graphed(s['tta_graphs'], key, enqueue)
         self.iteration += 1
