@@ -12,6 +12,7 @@
 // an NCCL all-reduce between two launches.
 #include <cooperative_groups.h>
 #include "elementwise.cuh"
+#include "stats_epilogue.cuh"
 
 namespace dcb {
 extern unsigned long long g_launches;
@@ -69,12 +70,13 @@ __device__ __forceinline__ void reduce_partials(const double* __restrict__ parti
 }
 
 // SyncBN exchange of the V local totals (see the file comment).  Returns with s_tot[0..V) = sum over ranks.
-__device__ __forceinline__ void peer_exchange(const PeerView& pv, const double* __restrict__ totals, int V, double* s_tot) {
+template <typename GetFn>
+__device__ __forceinline__ void peer_exchange_fn(const PeerView& pv, GetFn get, int V, double* s_tot) {
   const unsigned long long epoch = *pv.epoch;
   if (blockIdx.x == 0) {
     for (int p = 0; p < pv.world; ++p) {
       double* dst = pv.xchg[p] + pv.slot_doubles + (long long)pv.rank * V;
-      for (int i = threadIdx.x; i < V; i += blockDim.x) dst[i] = __ldcg(totals + i);
+      for (int i = threadIdx.x; i < V; i += blockDim.x) dst[i] = get(i);
     }
     __threadfence_system();
     __syncthreads();
@@ -98,6 +100,10 @@ __device__ __forceinline__ void peer_exchange(const PeerView& pv, const double* 
   __syncthreads();
 }
 
+__device__ __forceinline__ void peer_exchange(const PeerView& pv, const double* __restrict__ totals, int V, double* s_tot) {
+  peer_exchange_fn(pv, [&](int i) { return __ldcg(totals + i); }, V, s_tot);
+}
+
 struct BnFwdParams {
   const void* x; void* y; void* pool;   // raw conv output [M][C], activation out, optional 2x2 max-pooled copy
   long long M, M_total; int C;
@@ -106,10 +112,13 @@ struct BnFwdParams {
   float* moving_mean; float* moving_var; float* scale; float* shift; float* mean; float* rstd;
   int relu; float p_drop; unsigned long long seed; const unsigned long long* seed_dev; unsigned layer;
   double* partial; double* totals; unsigned* sync;
+  const long long* sums_q;              // PRE instantiation: fixed-point batch sums of a conv epilogue (stats_epilogue.cuh)
   PeerView pv;
 };
 
-template <typename T, int VEC, bool POOL>
+// PRE: the batch sums are already in p.totals (taken by the conv epilogue that produced x, stats_epilogue.cuh): phase 1
+// and both grid barriers disappear, the grid needs no co-residency
+template <typename T, int VEC, bool POOL, bool PRE = false>
 __global__ void __launch_bounds__(256)
 bn_train_fwd_kernel(const BnFwdParams p) {
   extern __shared__ double s_dyn[];
@@ -123,7 +132,7 @@ bn_train_fwd_kernel(const BnFwdParams p) {
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   long long r1 = r0 + rows_per_cta; if (r1 > p.M) r1 = p.M;
   // ---------------- phase 1: per-CTA partial sums of x and x^2
-  {
+  if constexpr (!PRE) {
     float s[VEC], q[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) { s[i] = 0.f; q[i] = 0.f; }
@@ -154,14 +163,21 @@ bn_train_fwd_kernel(const BnFwdParams p) {
       for (int rr = 0; rr < rows_par; ++rr) acc += (double)sh[(rr * lanes_c + lc) * 2 * VEC + comp];
       p.partial[(size_t)blockIdx.x * V + (comp / VEC) * C + lc * VEC + (comp % VEC)] = acc;
     }
+    grid_barrier(p.sync + 0);
+    reduce_partials(p.partial, V, p.totals);
+    grid_barrier(p.sync + 1);
   }
-  grid_barrier(p.sync + 0);
-  reduce_partials(p.partial, V, p.totals);
-  grid_barrier(p.sync + 1);
   // ---------------- per-channel coefficients (every CTA; block 0 publishes them and updates the moving statistics)
   double* s_tot = s_dyn;                               // V doubles
   float* s_sc = reinterpret_cast<float*>(s_dyn + V); float* s_sh = s_sc + C;
-  if (p.pv.world > 1) {
+  if constexpr (PRE) {
+    if (p.pv.world > 1) {
+      peer_exchange_fn(p.pv, [&](int i) { return (double)__ldcg(p.sums_q + i) * tc::STATS_Q_INV; }, V, s_tot);
+    } else {
+      for (int i = threadIdx.x; i < V; i += blockDim.x) s_tot[i] = (double)__ldcg(p.sums_q + i) * tc::STATS_Q_INV;
+      __syncthreads();
+    }
+  } else if (p.pv.world > 1) {
     peer_exchange(p.pv, p.totals, V, s_tot);
   } else {
     for (int i = threadIdx.x; i < V; i += blockDim.x) s_tot[i] = __ldcg(p.totals + i);
@@ -367,23 +383,29 @@ bn_train_bwd_kernel(const BnBwdParams p) {
     }
   }
   T* __restrict__ draw = reinterpret_cast<T*>(p.draw);
-  long long r = r0 + tr;
-  for (; r + rows_par < r1; r += 2LL * rows_par) {       // two rows (2 x 48 bytes of loads) in flight per thread
+  // The rows are walked BACKWARDS: phase 1 went through this CTA's range in ascending order, so its tail is what the L2
+  // still holds (dy + x of a full-resolution layer are 100 MB); an ascending second pass would start with the rows that
+  // were evicted first and push the resident ones out before reaching them.
+  const long long first = r0 + tr;
+  long long nrows = first < r1 ? (r1 - first + rows_par - 1) / rows_par : 0;
+  long long r = first + (nrows - 1) * rows_par;          // this thread's last row
+  for (; nrows >= 2; nrows -= 2, r -= 2LL * rows_par) {   // two rows (2 x 48 bytes of loads) in flight per thread
     float g0[VEC], g1[VEC], v0[VEC], v1[VEC], o[VEC];
-    loadv<float, VEC>(p.dy + r * p.ldy + p.offy + c, g0);
-    loadv<float, VEC>(p.dy + (r + rows_par) * p.ldy + p.offy + c, g1);
-    loadv<T, VEC>(x + r * C + c, v0);
-    loadv<T, VEC>(x + (r + rows_par) * C + c, v1);
-    masked(r, g0, v0);
-    masked(r + rows_par, g1, v1);
+    const long long ra = r, rb = r - rows_par;
+    loadv<float, VEC>(p.dy + ra * p.ldy + p.offy + c, g0);
+    loadv<float, VEC>(p.dy + rb * p.ldy + p.offy + c, g1);
+    loadv<T, VEC>(x + ra * C + c, v0);
+    loadv<T, VEC>(x + rb * C + c, v1);
+    masked(ra, g0, v0);
+    masked(rb, g1, v1);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) o[j] = fmaf(sc[j], g0[j], fmaf(k1[j], v0[j] - mu[j], k0[j]));
-    storev<T, VEC>(draw + r * C + c, o);
+    storev<T, VEC>(draw + ra * C + c, o);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) o[j] = fmaf(sc[j], g1[j], fmaf(k1[j], v1[j] - mu[j], k0[j]));
-    storev<T, VEC>(draw + (r + rows_par) * C + c, o);
+    storev<T, VEC>(draw + rb * C + c, o);
   }
-  for (; r < r1; r += rows_par) {
+  if (nrows == 1) {
     float g[VEC], v[VEC], o[VEC];
     loadv<float, VEC>(p.dy + r * p.ldy + p.offy + c, g);
     loadv<T, VEC>(x + r * C + c, v);
@@ -860,6 +882,48 @@ extern "C" int dcb_bn_train_fwd(int dtype, const void* x, long long M, int C, lo
   } else {
     if (pool_out) { BN_DISPATCH(dtype, return (launch_bn_fwd<T, 4, true>(p, workspace, workspace_bytes, st));) }
     else { BN_DISPATCH(dtype, return (launch_bn_fwd<T, 4, false>(p, workspace, workspace_bytes, st));) }
+  }
+}
+
+template <typename T, int VEC, bool POOL>
+static int launch_bn_fwd_sums(BnFwdParams& p, cudaStream_t st) {
+  const size_t smem = fused_smem(p.C, VEC);
+  // one pass, no barrier: enough CTAs to fill the machine, each with a few unrolled passes over its rows
+  const int rows_par = 256 / (p.C / VEC);
+  long long grid = (p.M + 8LL * rows_par - 1) / (8LL * rows_par);
+  if (grid > 8LL * sm_count()) grid = 8LL * sm_count();
+  if (grid < 1) grid = 1;
+  const cudaError_t le = launch_k(bn_train_fwd_kernel<T, VEC, POOL, true>, (int)grid, 256, smem, st, policy(DCB_POLICY_PDL) != 0, p);
+  if (le != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of bn_train_fwd_kernel (sums) failed: %s", cudaGetErrorString(le));
+  g_launches += 1;
+  return DCB_OK;
+}
+
+extern "C" int dcb_bn_train_fwd_sums(int dtype, const void* x, long long M, int C, long long M_total, const long long* sums_q,
+                                     const float* gamma, const float* beta, float eps, float momentum, float* moving_mean,
+                                     float* moving_var, float* scale, float* shift, float* mean, float* rstd, int relu,
+                                     float p_drop, unsigned long long seed, const unsigned long long* seed_dev, unsigned layer,
+                                     void* y, void* pool_out, int N, int H, int W, const dcb_peer_exchange_t* peers,
+                                     dcb_stream_t stream) {
+  DCB_CHECK_ARG(x && y && sums_q && gamma && beta && scale && shift && mean && rstd && M > 0, "dcb_bn_train_fwd_sums: bad arguments");
+  DCB_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "dcb_bn_train_fwd_sums: p_drop %f outside [0, 1)", p_drop);
+  const int vec = fused_vec(C);
+  if (!vec || C > 1024) return fail(DCB_ERR_INVALID_ARGUMENT, "dcb_bn_train_fwd_sums: channel count %d unsupported", C);
+  DCB_CHECK_ARG(!pool_out || (N > 0 && H % 2 == 0 && W % 2 == 0 && (long long)N * H * W == M), "dcb_bn_train_fwd_sums: pooling needs N*H*W == M and even H, W");
+  BnFwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.y = y; p.pool = pool_out; p.M = M; p.M_total = M_total > 0 ? M_total : M; p.C = C; p.N = N; p.H = H; p.W = W;
+  p.gamma = gamma; p.beta = beta; p.eps = eps; p.momentum = momentum; p.moving_mean = moving_mean; p.moving_var = moving_var;
+  p.scale = scale; p.shift = shift; p.mean = mean; p.rstd = rstd; p.relu = relu; p.p_drop = p_drop; p.seed = seed;
+  p.seed_dev = seed_dev; p.layer = layer; p.sums_q = sums_q;
+  if (int e = fill_peers(p.pv, peers, C)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec == 8) {
+    if (pool_out) { BN_DISPATCH(dtype, return (launch_bn_fwd_sums<T, 8, true>(p, st));) }
+    else { BN_DISPATCH(dtype, return (launch_bn_fwd_sums<T, 8, false>(p, st));) }
+  } else {
+    if (pool_out) { BN_DISPATCH(dtype, return (launch_bn_fwd_sums<T, 4, true>(p, st));) }
+    else { BN_DISPATCH(dtype, return (launch_bn_fwd_sums<T, 4, false>(p, st));) }
   }
 }
 

@@ -21,8 +21,10 @@ int run_f32_wgrad(const TapGeom& g, const float* s0, int C0, const float* s1, in
 struct TcFusion {
   const float* head_kernel; const float* head_bias; float* logit; float* prob; int need_y; void* pool_out;
 };
+struct TcStats { long long* sums; int done; };
 int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* B, int Nout, void* out,
-               const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st, const TcFusion* fuse = nullptr);
+               const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st, const TcFusion* fuse = nullptr,
+               TcStats* stats = nullptr);
 int run_tc_wgrad(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* G, int Nout, float* dW,
                  void* ws, size_t ws_bytes, cudaStream_t st);
 size_t tc_wgrad_workspace(const TapGeom& g, int K, int Nout);
@@ -224,6 +226,38 @@ extern "C" int dcb_conv3x3_fwd_fused(int dtype, const void* src0, int C0, const 
   if (fuse->head_kernel)
     if (int e = dcb_head_fwd(dtype, out, (long long)N * H * W, Cout, fuse->head_kernel, fuse->head_bias, fuse->logit, fuse->prob, stream)) return e;
   return DCB_OK;
+}
+
+extern "C" int dcb_conv3x3_fwd_stats(int dtype, const void* src0, int C0, const void* src1, int C1, int N, int H, int W,
+                                     const void* wgt, int Cout, const float* scale, const float* shift, int relu, void* out,
+                                     long long* sums_q, int* stats_done, dcb_stream_t stream) {
+  DCB_CHECK_ARG(src0 && wgt && out && sums_q && stats_done, "dcb_conv3x3_fwd_stats: null pointer");
+  DCB_CHECK_ARG(N > 0 && H > 0 && W > 0 && C0 > 0 && C1 >= 0 && Cout > 0 && (C1 == 0 || src1), "dcb_conv3x3_fwd_stats: bad shape");
+  *stats_done = 0;
+  if (dtype != DCB_BF16) return dcb_conv3x3_fwd(dtype, src0, C0, src1, C1, N, H, W, wgt, Cout, scale, shift, relu, out, stream);
+  TapGeom g;
+  geom_conv3x3(g, N, H, W);
+  g.f16 = 0;
+  TcStats stt = {sums_q, 0};
+  const int rc = run_tc_fwd(g, src0, C0, src1, C1, wgt, Cout, out, scale, shift, relu, 0, (cudaStream_t)stream, nullptr, &stt);
+  *stats_done = stt.done;
+  return rc;
+}
+
+extern "C" int dcb_convT2x2_fwd_stats(int dtype, const void* src, int Cin, int N, int h, int w, const void* wgt, int Cout,
+                                      const float* scale, const float* shift, int relu, void* out, long long* sums_q,
+                                      int* stats_done, dcb_stream_t stream) {
+  DCB_CHECK_ARG(src && wgt && out && sums_q && stats_done && N > 0 && h > 0 && w > 0 && Cin > 0 && Cout > 0,
+                "dcb_convT2x2_fwd_stats: bad arguments");
+  *stats_done = 0;
+  if (dtype != DCB_BF16) return dcb_convT2x2_fwd(dtype, src, Cin, N, h, w, wgt, Cout, scale, shift, relu, out, stream);
+  TapGeom g;
+  geom_convT_fwd(g, N, h, w);
+  g.f16 = 0;
+  TcStats stt = {sums_q, 0};
+  const int rc = run_tc_fwd(g, src, Cin, nullptr, 0, wgt, Cout, out, scale, shift, relu, 0, (cudaStream_t)stream, nullptr, &stt);
+  *stats_done = stt.done;
+  return rc;
 }
 
 extern "C" int dcb_conv3x3_dgrad(int dtype, const void* dy, int Cout, int N, int H, int W, const void* wgt_dgrad, int Cin,

@@ -2,6 +2,7 @@
 // (unet_2d_summary.py:169-172).  K = 9 is far too small for the tensor pipe; the layer is
 // bound by writing its [N,H,W,Cout] output, so it runs on CUDA cores with the weights in registers.
 #include "elementwise.cuh"
+#include "stats_epilogue.cuh"
 
 namespace dcb {
 extern unsigned long long g_launches;
@@ -19,10 +20,14 @@ __device__ __forceinline__ void cp_async_f32_zfill(float* smem_dst, const float*
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
 }
 
-template <typename T, int COUT>
+// STATS (training forward): every thread also sums its 8 channels' stored (rounded) outputs and their squares; per-CTA sums in
+// a fixed order, cross-CTA total by fixed-point integer atomics as in stats_epilogue.cuh (stat_sums[0..COUT) = sum,
+// [COUT..2 COUT) = sum of squares, 2^-20 units).
+template <typename T, int COUT, bool STATS = false>
 __global__ void __launch_bounds__(256, 2)
 conv3x3_c1_fwd_kernel(const float* __restrict__ x, int N, int H, int W, const float* __restrict__ w,
-                      const float* __restrict__ scale, const float* __restrict__ shift, int relu, T* __restrict__ out) {
+                      const float* __restrict__ scale, const float* __restrict__ shift, int relu, T* __restrict__ out,
+                      long long* stat_sums = nullptr) {
   constexpr int TPP = COUT / 8;                               // threads per pixel (8 channels = one 16-byte store each)
   constexpr int TW = 256 / TPP;                               // pixel columns per tile
   constexpr int TH = 16;                                      // rows per tile
@@ -61,6 +66,9 @@ conv3x3_c1_fwd_kernel(const float* __restrict__ x, int N, int H, int W, const fl
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  float st_s[STATS ? 8 : 1], st_q[STATS ? 8 : 1];
+#pragma unroll
+  for (int i = 0; i < (STATS ? 8 : 1); ++i) { st_s[i] = 0.f; st_q[i] = 0.f; }
   int buf = 0;
   prefetch(blockIdx.x, 0);
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, buf ^= 1) {
@@ -95,10 +103,31 @@ conv3x3_c1_fwd_kernel(const float* __restrict__ x, int N, int H, int W, const fl
           o[2 * q + 1] = relu ? fmaxf(y2.y, 0.f) : y2.y;
         }
         store8<T>(orow + (size_t)r * W * COUT, o);
+        if constexpr (STATS) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float rv = to_f32<T>(from_f32<T>(o[k]));
+            st_s[k] += rv; st_q[k] = fmaf(rv, rv, st_q[k]);
+          }
+        }
         a0 = b0; a1 = b1; a2 = b2; b0 = c0; b1 = c1; b2 = c2;
       }
     }
     __syncthreads();                                          // this window may be overwritten by the prefetch after next
+  }
+  if constexpr (STATS) {
+    // the TW pixel columns of the CTA share each channel group: column-major partials in shared memory, COUT * 2 threads
+    // add them in column order -> this CTA's row
+    __shared__ float s_red[256 * 17];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s_red[threadIdx.x * 17 + k] = st_s[k]; s_red[threadIdx.x * 17 + 8 + k] = st_q[k]; }
+    __syncthreads();
+    if (threadIdx.x < 2 * COUT) {
+      const int comp = threadIdx.x / COUT, c = threadIdx.x % COUT, g = c >> 3, k = c & 7;
+      float acc = 0.f;
+      for (int cl = 0; cl < TW; ++cl) acc += s_red[(cl * TPP + g) * 17 + comp * 8 + k];
+      tc::stats_add_q(stat_sums, comp * COUT + c, acc);
+    }
   }
 }
 
@@ -231,17 +260,27 @@ using namespace dcb;
 
 template <typename T>
 static int launch_c1_fwd(const float* x, int N, int H, int W, const float* w, int Cout, const float* scale,
-                         const float* shift, int relu, T* out, cudaStream_t st) {
+                         const float* shift, int relu, T* out, cudaStream_t st, long long* stat_sums = nullptr,
+                         int* stats_done = nullptr) {
   // persistent: two 256-thread CTAs per SM walk the [16 x (2048 / Cout)]-pixel tiles
   auto tiles = [&](int tw) { return (long long)N * cdiv(H, 16) * cdiv(W, tw); };
   auto grid_for = [&](long long t) { const long long cap = 2LL * sm_count(); return (int)(t < cap ? t : cap); };
   const bool pdl = policy(DCB_POLICY_PDL) != 0;
   cudaError_t le = cudaSuccess;
+  if (stats_done) *stats_done = 0;
+  if (stat_sums && Cout == 32) {
+    le = launch_k(conv3x3_c1_fwd_kernel<T, 32, true>, grid_for(tiles(64)), 256, 0, st, pdl, x, N, H, W, w, scale, shift, relu, out,
+                  stat_sums);
+    if (le != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of conv3x3_c1_fwd_kernel (stats) failed: %s", cudaGetErrorString(le));
+    g_launches += 1;
+    if (stats_done) *stats_done = 1;
+    return DCB_OK;
+  }
   switch (Cout) {
-    case 8: le = launch_k(conv3x3_c1_fwd_kernel<T, 8>, grid_for(tiles(256)), 256, 0, st, pdl, x, N, H, W, w, scale, shift, relu, out); break;
-    case 16: le = launch_k(conv3x3_c1_fwd_kernel<T, 16>, grid_for(tiles(128)), 256, 0, st, pdl, x, N, H, W, w, scale, shift, relu, out); break;
-    case 32: le = launch_k(conv3x3_c1_fwd_kernel<T, 32>, grid_for(tiles(64)), 256, 0, st, pdl, x, N, H, W, w, scale, shift, relu, out); break;
-    case 64: le = launch_k(conv3x3_c1_fwd_kernel<T, 64>, grid_for(tiles(32)), 256, 0, st, pdl, x, N, H, W, w, scale, shift, relu, out); break;
+    case 8: le = launch_k(conv3x3_c1_fwd_kernel<T, 8>, grid_for(tiles(256)), 256, 0, st, pdl, x, N, H, W, w, scale, shift, relu, out, (long long*)nullptr); break;
+    case 16: le = launch_k(conv3x3_c1_fwd_kernel<T, 16>, grid_for(tiles(128)), 256, 0, st, pdl, x, N, H, W, w, scale, shift, relu, out, (long long*)nullptr); break;
+    case 32: le = launch_k(conv3x3_c1_fwd_kernel<T, 32>, grid_for(tiles(64)), 256, 0, st, pdl, x, N, H, W, w, scale, shift, relu, out, (long long*)nullptr); break;
+    case 64: le = launch_k(conv3x3_c1_fwd_kernel<T, 64>, grid_for(tiles(32)), 256, 0, st, pdl, x, N, H, W, w, scale, shift, relu, out, (long long*)nullptr); break;
     default: return fail(DCB_ERR_UNSUPPORTED, "dcb_conv3x3_c1_fwd: Cout=%d unsupported (8,16,32,64)", Cout);
   }
   if (le != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of conv3x3_c1_fwd_kernel failed: %s", cudaGetErrorString(le));
@@ -258,6 +297,19 @@ extern "C" int dcb_conv3x3_c1_fwd(int dtype, const float* x, int N, int H, int W
   if (dtype == DCB_F16)
     return launch_c1_fwd<__half>(x, N, H, W, w, Cout, scale, shift, relu, (__half*)out, (cudaStream_t)stream);
   return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+}
+
+// the same + batch statistics of the stored output (training forward); *stats_done = 1 when sums were written by the
+// kernel, 0 when this configuration has no statistics epilogue (the conv itself always runs)
+extern "C" int dcb_conv3x3_c1_fwd_stats(int dtype, const float* x, int N, int H, int W, const float* w, int Cout,
+                                        const float* scale, const float* shift, int relu, void* out, long long* sums_q,
+                                        int* stats_done, dcb_stream_t stream) {
+  DCB_CHECK_ARG(x && w && out && sums_q && stats_done && N > 0 && H > 0 && W > 0, "dcb_conv3x3_c1_fwd_stats: bad arguments");
+  if (dtype == DCB_BF16)
+    return launch_c1_fwd<__nv_bfloat16>(x, N, H, W, w, Cout, scale, shift, relu, (__nv_bfloat16*)out, (cudaStream_t)stream, sums_q,
+                                        stats_done);
+  *stats_done = 0;
+  return dcb_conv3x3_c1_fwd(dtype, x, N, H, W, w, Cout, scale, shift, relu, out, stream);
 }
 
 static int c1_wgrad_ctas() { return sm_count() * 8; }

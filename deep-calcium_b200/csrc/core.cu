@@ -34,8 +34,8 @@ int sm_count() {
 // ---- dispatch policy: process-wide, read at every call (never cached), set through dcb_set_policy() ----
 static const int kPolicyDefaults[DCB_POLICY_COUNT] = {
     /* FLAT */ 1, /* STRIP */ 1, /* FOLD */ 1, /* NSPLIT */ 1, /* SWAP_MIN_COUT */ 64, /* WGRAD_STRIP */ 1,
-    /* BN_CTAS_PER_SM */ 4, /* PROJ_I16_SPLITS */ 0, /* SPLITK */ 1, /* FUSED_BN */ 1, /* TMA_STORE */ 1, /* BN_SLAB */ 1, /* PDL */ 0, /* PAIR */ 0};
-static int g_policy[DCB_POLICY_COUNT] = {1, 1, 1, 1, 64, 1, 4, 0, 1, 1, 1, 1, 0, 0};
+    /* BN_CTAS_PER_SM */ 4, /* PROJ_I16_SPLITS */ 0, /* SPLITK */ 1, /* FUSED_BN */ 2, /* TMA_STORE */ 1, /* BN_SLAB */ 1, /* PDL */ 0, /* PAIR */ 0};
+static int g_policy[DCB_POLICY_COUNT] = {1, 1, 1, 1, 64, 1, 4, 0, 1, 2, 1, 1, 0, 0};
 
 int policy(int key) { return (key >= 0 && key < DCB_POLICY_COUNT) ? g_policy[key] : 0; }
 

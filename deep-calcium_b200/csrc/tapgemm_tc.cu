@@ -19,6 +19,7 @@
 #include <tuple>
 
 #include "tc_common.cuh"
+#include "stats_epilogue.cuh"
 #include "tapgeom.h"
 
 namespace dcb {
@@ -36,6 +37,10 @@ constexpr int WG_THREADS = 192;
 struct TcFusion {
   const float* head_kernel; const float* head_bias; float* logit; float* prob; int need_y; void* pool_out;
 };
+
+// optional batch statistics of the output (training forward, stats_epilogue.cuh): sums[0..C) = sum, sums[C..2C) = sum of
+// squares; done is set to 1 when the dispatched kernel produced them (0: the caller runs a statistics pass of its own)
+struct TcStats { long long* sums; int done; };
 
 struct TcFwdParams {
   int mode;                 // 0: 4-D halo box (conv3x3)  1: 3-D merged rows (convT fwd)  2: 5-D strided (convT dgrad)
@@ -61,6 +66,8 @@ struct TcFwdParams {
   __nv_bfloat16* pool_out;  // conv3x3 only: 2x2 max-pooled copy [N][GH/2][GW/2][Ntot] written by the epilogue (or null)
   const float* scale;
   const float* shift;
+  // STATS instantiation (training forward): per-channel sums of the stored output and of its square, see stats_epilogue.cuh
+  long long* stat_sums;
 };
 
 // Epilogue of the "swapped" orientation (TMEM lane = output channel, TMEM column = pixel): each thread
@@ -68,15 +75,19 @@ struct TcFwdParams {
 // through a per-warp shared-memory tile so that global stores stay NHWC-contiguous (64 B of bf16 or
 // 128 B of fp32 per pixel and warp).  pix_index(m) returns the element index of pixel m's first
 // channel of this warp, or -1 when the pixel lies outside the tensor.
-template <typename PixFn>
+// STATS (16-bit outputs): st_s / st_q accumulate the sum and the sum of squares of this lane's channel over the VALID pixels
+// (rounded values, see stats_epilogue.cuh).
+template <bool STATS = false, typename PixFn>
 __device__ __forceinline__ void epilogue_swapped(uint32_t t_addr, int npix, bool warp_valid, float sc, float sh, int relu,
                                                  int out_f32, void* out_base, uint8_t* stage, int lane, PixFn pix_index,
-                                                 int f16 = 0) {
+                                                 int f16 = 0, float* st_s = nullptr, float* st_q = nullptr) {
   for (int j = 0; j < npix; j += 32) {
     uint32_t r[32];
     tmem_ld_32x32b_x32(t_addr + j, r);
     tmem_ld_wait();
     if (!warp_valid) continue;
+    uint32_t vmask = 0;
+    if constexpr (STATS) vmask = __ballot_sync(0xffffffffu, pix_index(j + lane) >= 0);
     __syncwarp();
     if (out_f32) {
       float* st = reinterpret_cast<float*>(stage);
@@ -101,7 +112,12 @@ __device__ __forceinline__ void epilogue_swapped(uint32_t t_addr, int npix, bool
       for (int i = 0; i < 32; ++i) {
         float v = fmaf(__uint_as_float(r[i]), sc, sh);
         if (relu) v = fmaxf(v, 0.f);
-        st[i * 32 + lane] = cvt16(v, f16);
+        const uint16_t h = cvt16(v, f16);
+        st[i * 32 + lane] = h;
+        if constexpr (STATS) {
+          const float rv = (vmask >> i) & 1u ? unpack16x2((uint32_t)h, f16).x : 0.f;
+          *st_s += rv; *st_q = fmaf(rv, rv, *st_q);
+        }
       }
       __syncwarp();
 #pragma unroll
@@ -173,7 +189,8 @@ __device__ __forceinline__ void epilogue_swapped_pool(uint32_t t_addr, int npix,
 
 // POOL: the epilogues also write the 2x2 max-pooled copy (p.pool_out); a separate instantiation so that the plain
 // kernel keeps its register allocation (the pooled epilogue cost the plain path ~10 % when it was a runtime branch)
-template <bool POOL>
+// STATS: normal orientation, 16-bit plain stores; the epilogue also accumulates the BatchNorm batch statistics
+template <bool POOL, bool STATS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                       const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapO, const TcFwdParams p) {
@@ -202,7 +219,11 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
   const int acc_cols = p.swap ? 256 : p.BN;          // TMEM columns per accumulator stage
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2u * acc_cols) tmem_cols <<= 1;
-  __shared__ __align__(16) uint8_t s_stage[4][4096];  // per-epilogue-warp transpose tiles (swapped mode)
+  __shared__ __align__(16) uint8_t s_stage[4][4096];  // per-epilogue-warp transpose tiles (swapped mode; STATS: 8 x 2 KB)
+  // STATS: this lane's sums of channel pair (lane & 15) of accumulator block bi, over all tiles of the CTA
+  float2 st_s[STATS ? 8 : 1], st_q[STATS ? 8 : 1];
+#pragma unroll
+  for (int i = 0; i < (STATS ? 8 : 1); ++i) { st_s[i] = make_float2(0.f, 0.f); st_q[i] = make_float2(0.f, 0.f); }
 
   for (int i = threadIdx.x; i < p.Cz; i += blockDim.x) {
     s_scale[i] = p.scale ? p.scale[i] : 1.f;
@@ -383,7 +404,29 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
       mbar_wait(&bar_tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN);
-      if constexpr (!POOL) {
+      if constexpr (STATS) {
+        // one 32-column block at a time: pack, store, and feed the packed block to the statistics (the shared-memory
+        // transpose of stats_block is the second instruction stream here)
+        int z = ng0 / p.Cz, ch = ng0 - z * p.Cz;
+        const bool subpos = p.Cz < p.Ntot;
+        uint32_t* scr = reinterpret_cast<uint32_t*>(&s_stage[0][0]) + (warp - 2) * STATS_SCRATCH_WORDS;
+#pragma unroll
+        for (int bi = 0; bi < 8; ++bi) {
+          if (bi * 32 < p.BN) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_addr + bi * 32, r);
+            tmem_ld_wait();
+            uint32_t pk[16];
+            bn_relu_pack32(r, s_scale + ch, s_shift + ch, p.relu, pk, p.f16);
+            if (valid) {
+              const int ody = subpos ? (z >> 1) : p.ody, odx = subpos ? (z & 1) : p.odx;
+              store_pk16(p.out + ((orow_y + ody) * p.OW + (ocol_x + odx)) * p.OC + ch, pk);
+            }
+            stats_block(pk, valid, scr, lane, p.f16, st_s[bi], st_q[bi]);
+            ch += 32; if (ch == p.Cz) { ch = 0; ++z; }
+          }
+        }
+      } else if constexpr (!POOL) {
         // Two 32-column blocks per step: their TMEM loads, BN / ReLU / pack arithmetic and stores are independent
         // instruction streams (each scheduler hosts two epilogue warps, so a block-at-a-time loop is latency bound -
         // the short-K convT tiles spend 3x longer in this epilogue than in their MMAs).  A block never straddles a
@@ -527,6 +570,22 @@ tapgemm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_co
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
+  }
+  if constexpr (STATS) {
+    // every MMA has retired: the stage ring is free and takes the per-warp accumulators ([8 warps][nblk][16][4] floats)
+    float* dump = reinterpret_cast<float*>(smem);
+    const int nblk = p.BN / 32;
+    if (warp >= 2 && lane < 16) {
+#pragma unroll
+      for (int bi = 0; bi < 8; ++bi)
+        if (bi < nblk)
+          *reinterpret_cast<float4*>(dump + ((size_t)((warp - 2) * nblk + bi) * 16 + lane) * 4) =
+              make_float4(st_s[bi].x, st_s[bi].y, st_q[bi].x, st_q[bi].y);
+    }
+    __syncthreads();
+    // the host launches a multiple of num_ntiles CTAs, so every tile of this CTA has the same N tile
+    const int nt = blockIdx.x % num_ntiles;
+    stats_cta_finish(dump, 8, nblk, [&](int bi) { return (nt * p.BN + bi * 32) % p.Cz; }, p.Cz, p.stat_sums);
   }
 }
 
@@ -677,7 +736,12 @@ struct TcStripParams {
   __nv_bfloat16* out;
   const float* scale;
   const float* shift;
+  // STATS instantiation (training forward): per-channel sums of the stored output and of its square, see stats_epilogue.cuh
+  long long* stat_sums;
 };
+
+// per-lane statistics accumulators of the strip epilogue (Cout <= 64: two 32-channel blocks) + the warp's scratch tile
+struct StripStats { float2 s[2], q[2]; uint32_t* scr; };
 
 // Drains one PAIR of output rows of a folded strip (accumulators at TMEM addresses ta / tb, lane = pixel): BN / ReLU / pack,
 // optional fused softmax head and 2x2 max-pool, 16-bit or fp32 stores.  Both rows are processed together: the two TMEM
@@ -685,12 +749,34 @@ struct TcStripParams {
 // row-at-a-time loop, which left each scheduler with one latency-bound warp), the per-channel scale / shift are fetched
 // from shared memory once per pair, and the vertical half of the pool is a register-to-register maximum.
 // (n, row, px) = image, first row of the pair, pixel column of this thread.
-template <bool FUSED>
+template <bool FUSED, bool STATS = false>
 __device__ __forceinline__ void strip_drain_pair(const TcStripParams& p, uint32_t ta, uint32_t tb, int n, int row, int px,
                                                  const float* s_scale, const float* s_shift, const float* s_wd, float head_b,
-                                                 int lane, int n0) {
+                                                 int lane, int n0, StripStats* st = nullptr) {
   const size_t opix_a = ((size_t)n * p.H + row) * p.W + px, opix_b = opix_a + p.W;
   const size_t oidx_a = opix_a * p.OC + n0, oidx_b = opix_b * p.OC + n0;
+  if constexpr (STATS) {
+    // training forward: 16-bit stores + the BatchNorm batch statistics of the stored values (every pixel of a strip is valid)
+    __nv_bfloat16* orow_a = p.out + oidx_a;
+    __nv_bfloat16* orow_b = p.out + oidx_b;
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb) {
+      const int c = cb * 32;
+      if (c < p.Cout) {
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32b_x32(ta + c, ra);
+        tmem_ld_32x32b_x32(tb + c, rb);
+        tmem_ld_wait();
+        uint32_t pka[16], pkb[16];
+        bn_relu_pack32_x2(ra, rb, s_scale + c, s_shift + c, p.relu, pka, pkb, p.f16);
+        store_pk16(orow_a + c, pka);
+        store_pk16(orow_b + c, pkb);
+        stats_block(pka, true, st->scr, lane, p.f16, st->s[cb], st->q[cb]);
+        stats_block(pkb, true, st->scr, lane, p.f16, st->s[cb], st->q[cb]);
+      }
+    }
+    return;
+  }
   if (p.out_f32) {                                       // gradient tensors (dgrad): fp32 stores, row by row
 #pragma unroll 1
     for (int rr = 0; rr < 2; ++rr) {
@@ -803,7 +889,7 @@ __device__ __forceinline__ void strip_drain_pair(const TcStripParams& p, uint32_
 // accumulates into the three neighbouring accumulators of output rows i-1, i, i+1 at the same time: 3x fewer MMAs,
 // every halo row is read from shared memory by 3*K/16 instead of 9*K/16 MMAs.  Output row o is complete once input
 // row o+1 has been issued.
-template <bool FUSED, bool FOLD>
+template <bool FUSED, bool FOLD, bool STATS = false>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                         const __grid_constant__ CUtensorMap mapT0, const __grid_constant__ CUtensorMap mapT1,
@@ -813,6 +899,8 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_scale[128], s_shift[128], s_wd[128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  StripStats sst;                                                // STATS: this lane's sums (see stats_epilogue.cuh)
+  sst.s[0] = sst.s[1] = sst.q[0] = sst.q[1] = make_float2(0.f, 0.f); sst.scr = nullptr;
   if (threadIdx.x == 0) pdl_trigger();
   const int nclu = (FOLD && p.nclu > 1) ? p.nclu : 1;
   const uint32_t crank = nclu > 1 ? cluster_ctarank() : 0u;
@@ -1110,6 +1198,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
     if constexpr (FOLD) {
       // Folded mode hands the epilogue PAIRS of output rows (one tfull / tempty barrier per pair, see the MMA warp): a
       // quartet drains both rows of its pair together (strip_drain_pair).
+      if constexpr (STATS) sst.scr = reinterpret_cast<uint32_t*>(s_stage) + (warp - 2) * STATS_SCRATCH_WORDS;
       const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
       const uint32_t pmask = ((uint32_t)nacc >> 1) - 1u;
       for (int n, h0, rows, w0; next_strip(u, n, h0, rows, w0);) {
@@ -1120,7 +1209,7 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
           const int bar_i = (int)(jp & pmask);
           mbar_wait(&bar_tfull[bar_i], (j >> nacc_sh) & 1u);
           tc_fence_after();
-          strip_drain_pair<FUSED>(p, ta, tb, n, h0 + t, w0 + m, s_scale, s_shift, s_wd, head_b, lane, n0);
+          strip_drain_pair<FUSED, STATS>(p, ta, tb, n, h0 + t, w0 + m, s_scale, s_shift, s_wd, head_b, lane, n0, &sst);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_tempty[bar_i]);
@@ -1306,6 +1395,20 @@ tapgemm_tc_strip_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
   if (nclu > 1) cluster_sync_all();      // the peer may still multicast into this CTA / commit to its barriers until here
   else __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+  if constexpr (STATS) {
+    // every MMA has retired: the halo ring takes the per-warp accumulators ([8 warps][nblk][16][4] floats)
+    float* dump = reinterpret_cast<float*>(s_ring);
+    const int nblk = p.Cout / 32;
+    if (warp >= 2 && lane < 16) {
+#pragma unroll
+      for (int bi = 0; bi < 2; ++bi)
+        if (bi < nblk)
+          *reinterpret_cast<float4*>(dump + ((size_t)((warp - 2) * nblk + bi) * 16 + lane) * 4) =
+              make_float4(sst.s[bi].x, sst.s[bi].y, sst.q[bi].x, sst.q[bi].y);
+    }
+    __syncthreads();
+    stats_cta_finish(dump, 8, nblk, [](int bi) { return bi * 32; }, p.Cout, p.stat_sums);
+  }
 }
 
 // ====================================================================================== CTA-pair folded strip kernel
@@ -1675,10 +1778,12 @@ struct TcFlatParams {
   void* out;
   const float* scale;
   const float* shift;
+  long long* stat_sums;     // STATS instantiation (training forward), see stats_epilogue.cuh
 };
 constexpr int FL_THREADS = 192;
 constexpr uint32_t FL_WSLOT = 3u * 128u * 128u;   // three [128 x 64] bf16 weight tiles
 
+template <bool STATS>
 __global__ void __launch_bounds__(FL_THREADS, 1)
 tapgemm_tc_flat_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                        const __grid_constant__ CUtensorMap mapB, const TcFlatParams p) {
@@ -1695,6 +1800,7 @@ tapgemm_tc_flat_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
   const int num_items = p.N * p.ptiles * p.mtiles;
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2u * (uint32_t)p.NT) tmem_cols <<= 1;
+  float st_s = 0.f, st_q = 0.f;                             // STATS: sums of this thread's output channel
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
@@ -1809,8 +1915,8 @@ tapgemm_tc_flat_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
       };
       mbar_wait(&bar_tfull[acc], (it >> 1) & 1u);
       tc_fence_after();
-      epilogue_swapped(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)p.NT, p.NT, warp_valid, sc, sh, p.relu,
-                       p.out_f32, p.out, s_stage + quarter * 4096, lane, pix_index, p.f16);
+      epilogue_swapped<STATS>(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)p.NT, p.NT, warp_valid, sc, sh, p.relu,
+                              p.out_f32, p.out, s_stage + quarter * 4096, lane, pix_index, p.f16, &st_s, &st_q);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[acc]);
@@ -1819,6 +1925,19 @@ tapgemm_tc_flat_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+  if constexpr (STATS) {
+    // the grid is a multiple of mtiles, so every item of this CTA has the same channel tile mt; the four epilogue warps
+    // own 32 channels each: written as four accumulator blocks of one pseudo-warp (layout of stats_cta_finish)
+    float* dump = reinterpret_cast<float*>(s_pb);
+    if (warp >= 2) {
+      const int quarter = warp & 3;
+      float* d = dump + ((size_t)(quarter * 16) + (lane >> 1)) * 4 + (lane & 1);
+      d[0] = st_s; d[2] = st_q;
+    }
+    __syncthreads();
+    const int mt = blockIdx.x % p.mtiles;
+    stats_cta_finish(dump, 1, 4, [&](int bi) { return mt * 128 + bi * 32; }, p.Cout, p.stat_sums);
+  }
 }
 
 // ---------------------------------------------------------------------------------- host side
@@ -1897,8 +2016,12 @@ static bool swap_allowed(int Nout) { return swap_min_cout() > 0 && Nout >= swap_
 // strip kernel plan for a launch that computes Nsub of the layer's Nout output channels (Nsub < Nout: the layer is
 // run as Nout / Nsub launches because the weights of all channels do not fit next to a useful halo ring);
 // returns false when the layer is not eligible
-static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, int Nsub, bool fused, TcStripParams& p, size_t& dyn_smem) {
+static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, int Nsub, bool fused, TcStripParams& p, size_t& dyn_smem,
+                       bool stats = false) {
   if (!policy(DCB_POLICY_STRIP)) return false;
+  // batch statistics in the epilogue: folded single-CTA launches over all output channels only; 8 x 2 KB of scratch
+  // tiles behind the ring (where the swapped orientation keeps its transpose tiles)
+  if (stats && (fused || Nsub != Nout || Nout > 64)) return false;
   if (g.ntaps != 9 || g.zsub > 1 || g.sy != 1) return false;
   if (g.GW % 128 != 0 || Nsub > 128 || Nsub % 32 != 0 || Nout % Nsub != 0) return false;
   const int K = C0 + C1;
@@ -1913,11 +2036,11 @@ static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, int Nsub, boo
   // half of the 128 M rows empty): measured 0.050/0.056 -> 0.042/0.046 ms on the 256^2 layers; swapped strips are
   // for Cout = 128 only
   const bool no_fold_pref = !policy(DCB_POLICY_FOLD);
-  int swap = (!fused && swap_allowed(Nsub) && g.GW % 256 == 0 && (Nsub > 64 || no_fold_pref || g.GH % 2 != 0)) ? 1 : 0;
+  int swap = (!fused && !stats && swap_allowed(Nsub) && g.GW % 256 == 0 && (Nsub > 64 || no_fold_pref || g.GH % 2 != 0)) ? 1 : 0;
   int slot = 0, ring = 0;
   for (; swap >= 0; --swap) {
     const int px = swap ? 256 : 128;
-    const size_t budget = budget_all - (swap ? stage_tiles : 0);
+    const size_t budget = budget_all - ((swap || stats) ? stage_tiles : 0);
     slot = ((px + 2) * BK * 2 + 1023) & ~1023;
     // the MMA reads 128 weight rows starting at each (tap, kc) block: keep those reads inside the allocation
     if (w_bytes + (size_t)4 * nkc * slot <= budget) { ring = (int)((budget - w_bytes) / ((size_t)nkc * slot)); break; }
@@ -1931,15 +2054,16 @@ static bool plan_strip(const TapGeom& g, int C0, int C1, int Nout, int Nsub, boo
   p.fold = (!swap && !no_fold && (Nsub == 32 || Nsub == 64) && g.GH % 2 == 0 && ring >= 4) ? 1 : 0;
   if (fused && (g.GH % 2 != 0)) return false;          // row pairs of the fused pool must not straddle strips
   if (Nsub < Nout && !p.fold) return false;            // channel-split launches only pay with the folded issue
+  if (stats && !p.fold) return false;
   p.gran = (g.GH % 2 == 0) ? 2 : 1;
-  dyn_smem = w_bytes + (size_t)ring * nkc * slot + (swap ? stage_tiles : 0) + 1024;
+  dyn_smem = w_bytes + (size_t)ring * nkc * slot + ((swap || stats) ? stage_tiles : 0) + 1024;
   return true;
 }
 
 
 // flat halo-tile kernel: plan + launch; returns DCB_ERR_UNSUPPORTED (nothing launched) when the layer is not eligible
 static int run_tc_flat(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* B, int Nout, void* out,
-                       const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st) {
+                       const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st, TcStats* stats = nullptr) {
   const int flat_policy = policy(DCB_POLICY_FLAT);
   if (flat_policy == 0 || g.ntaps != 9 || g.zsub > 1 || g.sy != 1) return DCB_ERR_UNSUPPORTED;
   if (C0 % 64 != 0 || C1 % 64 != 0 || Nout < 64 || g.GW > 64 || g.GW < 16) return DCB_ERR_UNSUPPORTED;
@@ -1985,15 +2109,32 @@ static int run_tc_flat(const TapGeom& g, const void* s0, int C0, const void* s1,
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_flat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_tc_flat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const size_t dyn = 2 * (size_t)pbuf + 2 * (size_t)FL_WSLOT + 4 * 4096 + 1024;
   const int items = p.N * p.ptiles * p.mtiles;
-  const int grid = items < sm_count() ? items : sm_count();
+  int grid = items < sm_count() ? items : sm_count();
+  // The flat kernel is bound by its four epilogue warps (one 32 x 32 transpose per 32 pixels); the statistics add ~70 % to
+  // that loop (measured 28 -> 47 us on the 64 -> 64 layer of a 32 x 64^2 batch, profiles/r2_stats_epilogue_bench.txt) - more
+  // than the BatchNorm pass they save.  Only on request (policy fused_bn = 3, the tests).
+  if (stats && !out_f32 && stats->sums && policy(DCB_POLICY_FUSED_BN) >= 3) {
+    // every CTA keeps one channel tile (its threads accumulate one channel each)
+    const int gs = grid - grid % p.mtiles;
+    if (gs >= p.mtiles) {
+      p.stat_sums = stats->sums;
+      const cudaError_t le = launch_k(tapgemm_tc_flat_kernel<true>, gs, FL_THREADS, dyn, st, policy(DCB_POLICY_PDL) != 0, mA0, mA1, mB, p);
+      if (le != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of tapgemm_tc_flat_kernel (stats) failed: %s", cudaGetErrorString(le));
+      g_launches += 1;
+      stats->done = 1;
+      note_kernel("flat_stats");
+      return DCB_OK;
+    }
+  }
   {
-    const cudaError_t le = launch_k(tapgemm_tc_flat_kernel, grid, FL_THREADS, dyn, st, policy(DCB_POLICY_PDL) != 0, mA0, mA1, mB, p);
+    const cudaError_t le = launch_k(tapgemm_tc_flat_kernel<false>, grid, FL_THREADS, dyn, st, policy(DCB_POLICY_PDL) != 0, mA0, mA1, mB, p);
     if (le != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of tapgemm_tc_flat_kernel failed: %s", cudaGetErrorString(le));
   }
   g_launches += 1;
@@ -2003,13 +2144,20 @@ static int run_tc_flat(const TapGeom& g, const void* s0, int C0, const void* s1,
 
 static int run_tc_generic(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* B, int Nout, void* out,
                           int out_pitch, const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st,
-                          void* pool_out = nullptr);
+                          void* pool_out = nullptr, TcStats* stats = nullptr);
 
 // fuse != nullptr: the caller wants the head and/or the 2x2 max-pool computed in the conv epilogue; returns
 // DCB_ERR_UNSUPPORTED (without launching) when this layer shape cannot take the fused path.
 int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* B, int Nout, void* out,
-               const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st, const TcFusion* fuse) {
+               const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st, const TcFusion* fuse, TcStats* stats) {
   t_map_f16 = g.f16;
+  if (stats) stats->done = 0;
+  if (stats && (fuse || out_f32)) return fail(DCB_ERR_INVALID_ARGUMENT, "batch statistics: plain 16-bit forward only");
+  // Small outputs keep the channel-slab BatchNorm kernel, which takes statistics and applies them in ~7 us (2 MB) - less
+  // than the one-pass kernel plus the epilogue's extra work (measured gate; policy fused_bn = 3 = wherever available)
+  if (stats && policy(DCB_POLICY_FUSED_BN) < 3 &&
+      (long long)g.N * g.OH * g.OW * Nout * 2 < (4LL << 20))
+    stats = nullptr;
   if (C0 % 32 != 0 || C1 % 32 != 0 || Nout % 32 != 0)
     return fail(DCB_ERR_UNSUPPORTED, "bf16 tensor-core path needs channel counts that are multiples of 32 "
                 "(got C0=%d C1=%d Cout=%d); use the fp32 check mode for other widths", C0, C1, Nout);
@@ -2037,7 +2185,8 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
     // a pool-only fusion that the strip kernel cannot take (more than 64 output channels, narrow images) goes to the
     // generic kernel's pooled epilogue
     const bool pool_only = fused && fuse->pool_out && !fuse->head_kernel;
-    bool strip_ok = !(fused && fuse->pool_out && Nout > 64) && plan_strip(g, C0, C1, Nout, Nout, fused, sp, dyn);
+    const bool strip_stats = stats && stats->sums && plan_strip(g, C0, C1, Nout, Nout, false, sp, dyn, true);
+    bool strip_ok = strip_stats || (!(fused && fuse->pool_out && Nout > 64) && plan_strip(g, C0, C1, Nout, Nout, fused, sp, dyn));
     const bool no_nsplit = !policy(DCB_POLICY_NSPLIT);
     if (!strip_ok && !fused && !no_nsplit && Nout == 64) strip_ok = plan_strip(g, C0, C1, Nout, 32, fused, sp, dyn);
     if (fused && !strip_ok) {
@@ -2077,13 +2226,14 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_tc_strip_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
         attr_set_strip = true;
       }
       const bool pdl = policy(DCB_POLICY_PDL) != 0;
       // CTA-pair variant of the folded loop (cta_group::2 MMAs): the stacked weights take 5/3 of the single-CTA footprint
       // per CTA (one region per span shape); used when a ring of at least three row pairs still fits next to them
-      if (sp.fold && policy(DCB_POLICY_PAIR) && (sp.N * sp.wsegs) % 2 == 0 && sp.H % 2 == 0 && sm_count() >= 2) {
+      if (sp.fold && !strip_stats && policy(DCB_POLICY_PAIR) && (sp.N * sp.wsegs) % 2 == 0 && sp.H % 2 == 0 && sm_count() >= 2) {
         const size_t w2 = ((size_t)15 * sp.nkc * sp.Cout * sp.BK * 2 + 1023) & ~(size_t)1023;
         const size_t budget = 223 * 1024;
         const size_t rowb = (size_t)sp.nkc * sp.slot_bytes;
@@ -2135,6 +2285,15 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
       }
       const long long units = (long long)sp.N * sp.wsegs * cdiv(sp.H, sp.gran);
       const int grid = units < sm_count() ? (int)units : sm_count();
+      if (strip_stats) {
+        sp.n0 = 0; sp.nclu = 1; sp.stat_sums = stats->sums;
+        const cudaError_t le = launch_k(tapgemm_tc_strip_kernel<false, true, true>, grid, ST_THREADS, dyn, st, pdl, mA0, mA1, mT0, mT1, mB, sp);
+        if (le != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of tapgemm_tc_strip_kernel (stats) failed: %s", cudaGetErrorString(le));
+        g_launches += 1;
+        stats->done = 1;
+        note_kernel("strip_fold_stats");
+        return DCB_OK;
+      }
       // channel-split layer (two groups of output channels): ONE launch of two-CTA clusters that share every halo row
       // through TMA multicast instead of two launches that each read the whole input
       if (sp.fold && !fused && Nout == 2 * sp.Cout && sp.nkc % 2 == 0 && policy(DCB_POLICY_NSPLIT) == 1 && sm_count() >= 2) {
@@ -2180,16 +2339,16 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
     }
   }
   {
-    const int e = run_tc_flat(g, s0, C0, s1, C1, B, Nout, out, scale, shift, relu, out_f32, st);
+    const int e = run_tc_flat(g, s0, C0, s1, C1, B, Nout, out, scale, shift, relu, out_f32, st, stats);
     if (e != DCB_ERR_UNSUPPORTED) return e;
   }
-  return run_tc_generic(g, s0, C0, s1, C1, B, Nout, out, Nout, scale, shift, relu, out_f32, st);
+  return run_tc_generic(g, s0, C0, s1, C1, B, Nout, out, Nout, scale, shift, relu, out_f32, st, nullptr, stats);
 }
 
 // generic kernel: Nout output channels written with a channel pitch of out_pitch (>= Nout) starting at `out`
 static int run_tc_generic(const TapGeom& g, const void* s0, int C0, const void* s1, int C1, const void* B, int Nout, void* out,
                           int out_pitch, const float* scale, const float* shift, int relu, int out_f32, cudaStream_t st,
-                          void* pool_out) {
+                          void* pool_out, TcStats* stats) {
   TcFwdParams p;
   memset(&p, 0, sizeof(p));
   const int ntaps = g.ntaps;
@@ -2214,7 +2373,7 @@ static int run_tc_generic(const TapGeom& g, const void* s0, int C0, const void* 
     const long long px = (long long)g.N * g.GH * g.GW;
     // measured (profiles/r1_layer_ab.txt): pays for conv3x3 with 64..128 output channels, not for the 1-tap convT GEMMs
     // the pooled epilogue is cheaper in the pixels-as-M orientation (two epilogue quartets; profiles/r2_pool_ab.txt)
-    p.swap = (p.mode == 0 && !pool_out && swap_allowed(Nout) && px / 256 * cdiv(p.Ntot, 128) >= sm_count() / 2) ? 1 : 0;
+    p.swap = (p.mode == 0 && !pool_out && !stats && swap_allowed(Nout) && px / 256 * cdiv(p.Ntot, 128) >= sm_count() / 2) ? 1 : 0;
   }
   const int TM = p.swap ? 256 : TC_BM;
   // ---- M tiling
@@ -2260,7 +2419,8 @@ static int run_tc_generic(const TapGeom& g, const void* s0, int C0, const void* 
   // scattered 64-byte runs saturate the LSU pipe as plain stores (profiles/r2_convT_ncu.txt).  The conv3x3 layers on this
   // kernel are operand-traffic bound and lose more from the smaller stage ring than the stores gain (measured; policy 2
   // = TMA stores there too).
-  p.tma_store = (!p.swap && !out_f32 && !pool_out && p.mode != 2 &&
+  const bool with_stats = stats && !pool_out && !out_f32 && p.mode != 2 && out_pitch == Nout && stats->sums;
+  p.tma_store = (!p.swap && !out_f32 && !pool_out && !with_stats && p.mode != 2 &&
                  (policy(DCB_POLICY_TMA_STORE) >= 2 || (policy(DCB_POLICY_TMA_STORE) == 1 && p.mode == 1))) ? 1 : 0;
   const size_t staging = p.tma_store ? 2 * 16384 : 0;
   int stages = (int)((200 * 1024 - staging) / stage_bytes);
@@ -2319,17 +2479,34 @@ static int run_tc_generic(const TapGeom& g, const void* s0, int C0, const void* 
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_tc_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tapgemm_tc_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 206 * 1024);
     if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int num_tiles = num_mtiles * (p.swap ? cdiv(p.Ntot, 128) : p.Ntot / BN);
-  const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  const int num_ntiles = p.swap ? cdiv(p.Ntot, 128) : p.Ntot / BN;
+  const int num_tiles = num_mtiles * num_ntiles;
+  int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  const bool pdl = policy(DCB_POLICY_PDL) != 0;
+  if (with_stats) {
+    // every CTA keeps ONE N tile (its register accumulators are per 32-column block of the tile): the round-robin
+    // schedule tile = blockIdx.x + i * gridDim.x does that when the grid is a multiple of the N-tile count
+    grid -= grid % num_ntiles;
+    if (grid >= num_ntiles) {
+      p.stat_sums = stats->sums;
+      const cudaError_t le = launch_k(tapgemm_tc_fwd_kernel<false, true>, grid, TC_THREADS, dyn_smem, st, pdl, mA0, mA1, mB, mO, p);
+      if (le != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of tapgemm_tc_fwd_kernel (stats) failed: %s", cudaGetErrorString(le));
+      g_launches += 1;
+      stats->done = 1;
+      note_kernel("generic_stats");
+      return DCB_OK;
+    }
+    grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  }
   {
-    const bool pdl = policy(DCB_POLICY_PDL) != 0;
-    const cudaError_t le = p.pool_out ? launch_k(tapgemm_tc_fwd_kernel<true>, grid, TC_THREADS, dyn_smem, st, pdl, mA0, mA1, mB, mO, p)
-                                      : launch_k(tapgemm_tc_fwd_kernel<false>, grid, TC_THREADS, dyn_smem, st, pdl, mA0, mA1, mB, mO, p);
+    const cudaError_t le = p.pool_out ? launch_k(tapgemm_tc_fwd_kernel<true, false>, grid, TC_THREADS, dyn_smem, st, pdl, mA0, mA1, mB, mO, p)
+                                      : launch_k(tapgemm_tc_fwd_kernel<false, false>, grid, TC_THREADS, dyn_smem, st, pdl, mA0, mA1, mB, mO, p);
     if (le != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of tapgemm_tc_fwd_kernel failed: %s", cudaGetErrorString(le));
   }
   g_launches += 1;

@@ -91,6 +91,38 @@ def conv3x3_fwd_fused(src0, src1, wgt, out, scale=None, shift=None, relu=False, 
          ptr(wgt), c_int(out.shape[3]), ptr(scale), ptr(shift), c_int(int(relu)), ptr(out), ctypes.byref(f), stream_ptr())
 
 
+def conv3x3_fwd_stats(src0, src1, wgt, out, sums_q, scale=None, shift=None, relu=False):
+    """training forward: conv3x3 whose epilogue also accumulates the BatchNorm batch sums of the stored output into
+    ``sums_q`` (int64 [2*Cout], 2^-20 fixed point, zeroed by the caller).  Returns True when the dispatched kernel did
+    (else the caller runs its own statistics pass)."""
+    N, H, W, C0 = src0.shape
+    C1 = 0 if src1 is None else src1.shape[3]
+    _chk(sums_q, torch.int64)
+    done = c_int(0)
+    call('dcb_conv3x3_fwd_stats', _dt(src0), ptr(src0), c_int(C0), ptr(src1), c_int(C1), c_int(N), c_int(H), c_int(W),
+         ptr(wgt), c_int(out.shape[3]), ptr(scale), ptr(shift), c_int(int(relu)), ptr(out), ptr(sums_q), ctypes.byref(done),
+         stream_ptr())
+    return bool(done.value)
+
+
+def convT2x2_fwd_stats(src, wgt, out, sums_q, scale=None, shift=None, relu=False):
+    N, h, w, Cin = src.shape
+    _chk(sums_q, torch.int64)
+    done = c_int(0)
+    call('dcb_convT2x2_fwd_stats', _dt(src), ptr(src), c_int(Cin), c_int(N), c_int(h), c_int(w), ptr(wgt), c_int(out.shape[3]),
+         ptr(scale), ptr(shift), c_int(int(relu)), ptr(out), ptr(sums_q), ctypes.byref(done), stream_ptr())
+    return bool(done.value)
+
+
+def conv3x3_c1_fwd_stats(x, w, out, sums_q, scale=None, shift=None, relu=False):
+    N, H, W = x.shape
+    _chk(x, torch.float32); _chk(w, torch.float32); _chk(sums_q, torch.int64)
+    done = c_int(0)
+    call('dcb_conv3x3_c1_fwd_stats', _dt(out), ptr(x), c_int(N), c_int(H), c_int(W), ptr(w), c_int(out.shape[3]), ptr(scale),
+         ptr(shift), c_int(int(relu)), ptr(out), ptr(sums_q), ctypes.byref(done), stream_ptr())
+    return bool(done.value)
+
+
 def conv3x3_dgrad(dy, wgt_dgrad, dx):
     """dy: [N,H,W,Cout] activation dtype (gradient w.r.t. the raw conv output); dx: fp32 [N,H,W,Cin]."""
     N, H, W, Cout = dy.shape
@@ -264,6 +296,18 @@ def bn_train_fwd(x, gamma, beta, momentum, moving_mean, moving_var, scale, shift
          c_f(momentum), ptr(moving_mean), ptr(moving_var), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), c_int(int(relu)),
          c_f(p_drop), c_ull(seed), ptr(seed_dev), c_uint(layer), ptr(y), ptr(pool_out), c_int(N), c_int(H), c_int(W),
          ptr(workspace), c_sz(workspace.numel() * workspace.element_size()), ptr(sync), _peers_arg(peers, slot), stream_ptr())
+
+
+def bn_train_fwd_sums(x, sums_q, gamma, beta, momentum, moving_mean, moving_var, scale, shift, mean, rstd, y, relu=True,
+                      p_drop=0., seed=0, seed_dev=None, layer=0, pool_out=None, M_total=0, eps=1e-3, peers=None, slot=0):
+    """training BatchNorm forward from known batch sums (int64, 2^-20 units: conv*_fwd_stats): one pass, no grid barrier"""
+    C = x.shape[-1]
+    N, H, W = (x.shape[0], x.shape[1], x.shape[2]) if x.dim() == 4 else (0, 0, 0)
+    _chk(sums_q, torch.int64)
+    call('dcb_bn_train_fwd_sums', _dt(x), ptr(x), c_ll(x.numel() // C), c_int(C), c_ll(M_total), ptr(sums_q), ptr(gamma),
+         ptr(beta), c_f(eps), c_f(momentum), ptr(moving_mean), ptr(moving_var), ptr(scale), ptr(shift), ptr(mean), ptr(rstd),
+         c_int(int(relu)), c_f(p_drop), c_ull(seed), ptr(seed_dev), c_uint(layer), ptr(y), ptr(pool_out), c_int(N), c_int(H),
+         c_int(W), _peers_arg(peers, slot), stream_ptr())
 
 
 def bn_train_bwd(dy, ldy, offy, x, scale, shift, mean, rstd, draw, dgamma, dbeta, workspace, sync, p_drop=0., seed=0,

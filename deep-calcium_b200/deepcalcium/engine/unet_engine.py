@@ -418,6 +418,7 @@ class UNetEngine(object):
         fused_bn = bool(nat.get_policy('fused_bn')) and (world == 1 or self.peers is not None)
         if fused_bn:
             self.bn_sync.zero_()
+        epi_stats = fused_bn and nat.get_policy('fused_bn') >= 2 and self.dtype == torch.bfloat16
         # the 16-bit kernel-layout copies of the updated weights are rebuilt on the side stream while the first layer
         # (which reads the fp32 master weights) and its BatchNorm run; the first tensor-core conv waits for them
         main = torch.cuda.current_stream(self.dev)
@@ -445,24 +446,45 @@ class UNetEngine(object):
             bias = self.P[n + '/bias']
             if a in self._ups:
                 ops.upsample2x(act[self._ups[a]], act[a], self._dropout_p(a, dropout), seed_base, seed_dev, layer_id[a])
+            st = self.bn[n]
+            # batch statistics taken by the conv epilogue (fused_bn = 2, bf16): the BatchNorm launch that follows is a single
+            # pass without grid barriers.  have_sums is decided by the library per shape (False: full single-launch kernel).
+            # (the forward slot of the fp64 scratch, zeroed at the start of the step, read as 2^-20 fixed-point int64)
+            fsums = self.dbl[st['off_f']:st['off_f'] + 2 * blk.cout].view(torch.int64)
+            have_sums = False
             if blk.kind == 'conv':
                 if blk.cin == 1 and self.tc:
-                    ops.conv3x3_c1_fwd(s['x'], self.w_fwd[n], raw[n], None, bias, False)
+                    if epi_stats:
+                        have_sums = ops.conv3x3_c1_fwd_stats(s['x'], self.w_fwd[n], raw[n], fsums, None, bias, False)
+                    else:
+                        ops.conv3x3_c1_fwd(s['x'], self.w_fwd[n], raw[n], None, bias, False)
                 else:
                     if prep_done is not None:
                         main.wait_event(prep_done)
                         prep_done = None
-                    ops.conv3x3_fwd(act[a], act[b] if b else None, self.w_fwd[n], raw[n], None, bias, False)
+                    if epi_stats:
+                        have_sums = ops.conv3x3_fwd_stats(act[a], act[b] if b else None, self.w_fwd[n], raw[n], fsums, None, bias, False)
+                    else:
+                        ops.conv3x3_fwd(act[a], act[b] if b else None, self.w_fwd[n], raw[n], None, bias, False)
                 mom = BN_MOMENTUM_CONV
             else:
                 if prep_done is not None:
                     main.wait_event(prep_done)
                     prep_done = None
-                ops.convT2x2_fwd(act[a], self.w_fwd[n], raw[n], None, bias, False)
+                if epi_stats:
+                    have_sums = ops.convT2x2_fwd_stats(act[a], self.w_fwd[n], raw[n], fsums, None, bias, False)
+                else:
+                    ops.convT2x2_fwd(act[a], self.w_fwd[n], raw[n], None, bias, False)
                 mom = BN_MOMENTUM_UP
-            st = self.bn[n]
             M = raw[n].numel() // blk.cout
             pooled = act['pool%d' % blk.level] if n in ('enc0b', 'enc1b', 'enc2b', 'enc3b') else None
+            if have_sums:
+                li = layer_id[n]
+                ops.bn_train_fwd_sums(raw[n], fsums, self.P[n + '/gamma'], self.P[n + '/beta'], mom, self.P[n + '/moving_mean'],
+                                      self.P[n + '/moving_var'], st['scale'], st['shift'], st['mean'], st['rstd'], act[n], True,
+                                      self._dropout_p(n, dropout), seed_base, seed_dev, li, pool_out=pooled, M_total=M * world,
+                                      eps=BN_EPS, peers=self.peers, slot=2 * li)
+                continue
             if fused_bn:
                 # statistics + normalise + ReLU + dropout (+ the 2x2 max-pool of the encoder blocks) in ONE launch; in
                 # data-parallel runs the per-channel sums of all ranks are exchanged inside the kernel (SyncBN over NVLink)

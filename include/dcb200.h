@@ -62,7 +62,9 @@ enum dcb_policy_key {
   DCB_POLICY_BN_CTAS_PER_SM = 6,
   DCB_POLICY_PROJ_I16_SPLITS = 7, /* T splits of the int16 projection (0 = heuristic) */
   DCB_POLICY_SPLITK = 8,        /* split-K of the generic conv kernel for small pixel counts: 0 off, 1 auto */
-  DCB_POLICY_FUSED_BN = 9,      /* training BatchNorm: 1 = single-launch kernels with a grid barrier, 0 = separate passes */
+  DCB_POLICY_FUSED_BN = 9,      /* training BatchNorm: 0 = separate passes, 1 = single-launch kernels with grid barriers, 2 = batch statistics
+                                   taken in the producing conv's epilogue where that is measured to pay (dcb_conv*_fwd_stats), 3 = wherever
+                                   a statistics epilogue exists */
   DCB_POLICY_TMA_STORE = 10,    /* epilogues stage 16-bit outputs in shared memory and store them with TMA: 0 off, 1 convT forward, 2 also conv3x3 on the generic kernel */
   DCB_POLICY_BN_SLAB = 11,      /* training BatchNorm as channel-slab cluster kernels (DSMEM reduction): 0 off, 1 small tensors (measured gate), 2 wherever eligible */
   DCB_POLICY_PDL = 12,          /* programmatic dependent launch of the forward conv / TTA kernels: 0 off, 1 on.  Turn on only while
@@ -143,6 +145,23 @@ int dcb_conv3x3_fwd_fused(int dtype, const void* src0, int C0, const void* src1,
 /* input h x w -> output 2h x 2w */
 int dcb_convT2x2_fwd(int dtype, const void* src, int Cin, int N, int h, int w, const void* wgt, int Cout,
                      const float* scale, const float* shift, int relu, void* out, dcb_stream_t stream);
+/* Training forward with the BatchNorm batch statistics taken in the conv epilogue (Keras BatchNormalization in training
+ * mode normalises with the batch mean / biased variance, unet_2d_summary.py:157,165).  sums_q[0..Cout) += sum over all
+ * output pixels of the STORED (rounded) output, sums_q[Cout..2 Cout) += sum of its squares, as 64-bit FIXED POINT in units
+ * of 2^-20: per-CTA fp32 sums (fixed order) are added with integer atomics, so the totals are bit-reproducible whatever
+ * the arrival order (range |total| < 8.8e12).  The caller ZEROES sums_q before the call.
+ * *stats_done = 1 when the dispatched kernel accumulated into sums_q; 0 when this shape / dtype has no statistics
+ * epilogue - the convolution has run all the same and the caller takes the statistics with its own pass
+ * (dcb_bn_train_fwd).  Feeds dcb_bn_train_fwd_sums. */
+int dcb_conv3x3_fwd_stats(int dtype, const void* src0, int C0, const void* src1, int C1, int N, int H, int W,
+                          const void* wgt, int Cout, const float* scale, const float* shift, int relu, void* out,
+                          long long* sums_q, int* stats_done, dcb_stream_t stream);
+int dcb_convT2x2_fwd_stats(int dtype, const void* src, int Cin, int N, int h, int w, const void* wgt, int Cout,
+                           const float* scale, const float* shift, int relu, void* out, long long* sums_q,
+                           int* stats_done, dcb_stream_t stream);
+int dcb_conv3x3_c1_fwd_stats(int dtype, const float* x, int N, int H, int W, const float* w, int Cout,
+                             const float* scale, const float* shift, int relu, void* out, long long* sums_q,
+                             int* stats_done, dcb_stream_t stream);
 /* input gradients.  dy is the gradient w.r.t. the raw conv output in the activation dtype (it feeds the
  * tensor cores); dx is ALWAYS fp32: gradient tensors stay fp32 between layers because the BatchNorm
  * backward subtracts their per-channel mean (a bf16-rounded dx would lose most of its significant bits
@@ -239,6 +258,14 @@ int dcb_bn_train_fwd(int dtype, const void* x, long long M, int C, long long M_t
                      unsigned long long seed, const unsigned long long* seed_dev, unsigned layer, void* y,
                      void* pool_out, int N, int H, int W, void* workspace, size_t workspace_bytes,
                      unsigned int* sync, const dcb_peer_exchange_t* peers, dcb_stream_t stream);
+/* dcb_bn_train_fwd with the batch sums already known (sums_q[2 C], 2^-20 fixed point, from dcb_conv*_fwd_stats): one pass
+ * over the tensor, no grid barrier, any grid size.  With peers the totals of all ranks are exchanged inside the kernel as
+ * above. */
+int dcb_bn_train_fwd_sums(int dtype, const void* x, long long M, int C, long long M_total, const long long* sums_q,
+                          const float* gamma, const float* beta, float eps, float momentum, float* moving_mean,
+                          float* moving_var, float* scale, float* shift, float* mean, float* rstd, int relu, float p_drop,
+                          unsigned long long seed, const unsigned long long* seed_dev, unsigned layer, void* y,
+                          void* pool_out, int N, int H, int W, const dcb_peer_exchange_t* peers, dcb_stream_t stream);
 int dcb_bn_train_bwd(int dtype, const float* dy, int ldy, int offy, const void* x, long long M, int C,
                      long long M_total, const float* scale, const float* shift, const float* mean,
                      const float* rstd, float p_drop, unsigned long long seed,

@@ -596,3 +596,139 @@ def test_prep_weights_batch_equals_per_layer_calls(cuda, precision):
     ops.prep_weights_batch(tab, len(rows), dt)
     for a, b in zip(ref, got):
         assert torch.equal(a, b)
+
+
+STATS_CASES = [
+    # kind, shape, policy          conv: (N, H, W, C0, C1, Cout)   convT: (N, h, w, Cin, Cout)   c1: (N, H, W, Cout)
+    ('conv', (3, 4, 4, 256, 0, 512), {}),                   # generic kernel, two N tiles
+    ('conv', (2, 8, 8, 128, 128, 128), {}),
+    ('conv', (1, 32, 32, 64, 64, 64), {}),
+    ('conv', (2, 8, 24, 64, 0, 64), {}),                    # ragged tiles: out-of-image lanes must not count
+    ('conv', (1, 2, 2, 512, 0, 512), {}),
+    ('conv', (5, 48, 80, 64, 64, 64), {}),
+    ('conv', (32, 16, 16, 128, 0, 256), {}),
+    ('conv', (1, 8, 128, 32, 0, 32), {}),                   # folded strip kernel
+    ('conv', (4, 128, 128, 32, 32, 32), {}),
+    ('conv', (2, 44, 256, 64, 0, 32), {}),
+    ('conv', (1, 6, 256, 32, 0, 64), {}),
+    ('conv', (3, 37, 128, 64, 0, 32), {}),                  # odd height: no folded strip -> statistics not available there
+    ('conv', (8, 64, 64, 64, 0, 128), dict(flat=2)),        # flat halo-tile kernel
+    ('conv', (4, 32, 32, 64, 64, 256), dict(flat=2)),       # ... two channel tiles
+    ('conv', (2, 40, 64, 64, 0, 64), dict(flat=2)),
+    ('convT', (1, 8, 8, 64, 32), {}),
+    ('convT', (2, 4, 4, 512, 256), {}),
+    ('convT', (1, 16, 16, 128, 64), {}),
+    ('convT', (3, 2, 2, 256, 128), {}),
+    ('convT', (4, 64, 64, 64, 32), {}),
+    ('convT', (2, 5, 7, 64, 32), {}),
+    ('c1', (4, 128, 128, 32), {}),
+    ('c1', (3, 7, 33, 32), {}),
+]
+
+
+@pytest.mark.parametrize('case', STATS_CASES)
+def test_conv_epilogue_batch_statistics(cuda, case):
+    """dcb_conv*_fwd_stats (training forward, bf16): the output equals the plain call's and sums = per-channel sum / sum of
+    squares of the STORED output (fp64 reference from the output itself); two runs give bit-identical sums (fixed-order fp32
+    partials, integer cross-CTA totals)."""
+    from deepcalcium import _native as nat
+    from deepcalcium.engine import ops
+    kind, shape, pol = case
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(str(case).encode()))
+    bf = torch.bfloat16
+    with nat.policy(swap_min_cout=0, fused_bn=3, **pol):
+        if kind == 'conv':
+            N, H, W, C0, C1, Cout = shape
+            x0 = dev(rng.standard_normal((N, H, W, C0)), bf)
+            x1 = dev(rng.standard_normal((N, H, W, C1)), bf) if C1 else None
+            wk = (rng.standard_normal((3, 3, C0 + C1, Cout)) * np.sqrt(2.0 / (9 * (C0 + C1)))).astype(np.float32)
+            wf = torch.empty(9 * (C0 + C1) * Cout, dtype=bf, device='cuda')
+            ops.prep_conv3x3_weights(dev(wk), wf, None, bf)
+            bias = dev(0.3 * rng.standard_normal(Cout))
+            ref = torch.empty(N, H, W, Cout, dtype=bf, device='cuda')
+            run_ref = lambda: ops.conv3x3_fwd(x0, x1, wf, ref, None, bias, False)
+            run = lambda out, sums: ops.conv3x3_fwd_stats(x0, x1, wf, out, sums, None, bias, False)
+        elif kind == 'convT':
+            N, h, w_, Cin, Cout = shape
+            x0 = dev(rng.standard_normal((N, h, w_, Cin)), bf)
+            wk = (rng.standard_normal((2, 2, Cout, Cin)) * np.sqrt(2.0 / (4 * Cin))).astype(np.float32)
+            wf = torch.empty(4 * Cin * Cout, dtype=bf, device='cuda')
+            ops.prep_convT2x2_weights(dev(wk), wf, None, bf)
+            bias = dev(0.3 * rng.standard_normal(Cout))
+            ref = torch.empty(N, 2 * h, 2 * w_, Cout, dtype=bf, device='cuda')
+            run_ref = lambda: ops.convT2x2_fwd(x0, wf, ref, None, bias, False)
+            run = lambda out, sums: ops.convT2x2_fwd_stats(x0, wf, out, sums, None, bias, False)
+        else:
+            N, H, W, Cout = shape
+            x0 = dev(rng.standard_normal((N, H, W)))
+            wk = dev((rng.standard_normal((3, 3, 1, Cout)) * 0.5).astype(np.float32))
+            bias = dev(0.3 * rng.standard_normal(Cout))
+            ref = torch.empty(N, H, W, Cout, dtype=bf, device='cuda')
+            run_ref = lambda: ops.conv3x3_c1_fwd(x0, wk, ref, None, bias, False)
+            run = lambda out, sums: ops.conv3x3_c1_fwd_stats(x0, wk, out, sums, None, bias, False)
+        run_ref()
+        results = []
+        for rep in range(2):
+            out = torch.zeros_like(ref)
+            sums_q = torch.zeros(2 * Cout, dtype=torch.int64, device='cuda')
+            done = run(out, sums_q)
+            sums = sums_q.double() / 2 ** 20
+            kern = nat.last_kernel()
+            torch.cuda.synchronize()
+            # same accumulation, possibly a different tile order: identical up to bf16 rounding of equal fp32 values
+            assert torch.max(torch.abs(out.float() - ref.float())).item() <= 2e-2 * max(1.0, ref.float().abs().max().item())
+            if done:
+                o = out.double().reshape(-1, Cout)
+                want = torch.cat([o.sum(0), (o * o).sum(0)])
+                err = (sums - want).abs() / (want.abs() + 1e-3 * o.shape[0])
+                assert err.max().item() < 2e-5, (kern, err.max().item())
+            results.append((done, sums_q.clone()))
+        assert results[0][0] == results[1][0]
+        if results[0][0]:
+            assert torch.equal(results[0][1], results[1][1])
+        print('%s %s -> %s, statistics %s' % (kind, shape, kern, 'in the epilogue' if results[0][0] else 'not available'))
+        if kind == 'conv' and shape[2] % 128 == 0 and shape[1] % 2 == 0 and Cout <= 64:
+            assert results[0][0] and kern == 'strip_fold_stats'
+        if pol.get('flat') == 2:
+            assert results[0][0] and kern == 'flat_stats'
+        if kind == 'convT':
+            assert results[0][0] and kern == 'generic_stats'
+
+
+@pytest.mark.parametrize('shape', [(2, 16, 24, 32), (4, 32, 32, 64), (3, 8, 8, 512), (8, 128, 128, 32)])
+@pytest.mark.parametrize('pool', [False, True])
+def test_batchnorm_from_known_sums_equals_the_single_launch_kernel(cuda, shape, pool):
+    """dcb_bn_train_fwd_sums (one pass from the batch sums a conv epilogue took) against dcb_bn_train_fwd on the same
+    tensor: activation, pooled copy, coefficients and moving statistics."""
+    from deepcalcium.engine import ops
+    N, H, W, C = shape
+    rng = np.random.default_rng(C + H)
+    bf = torch.bfloat16
+    x = dev(rng.standard_normal((N, H, W, C)) * 1.7 + 0.4, bf)
+    gamma, beta = dev(rng.uniform(0.5, 1.5, C)), dev(0.1 * rng.standard_normal(C))
+    f = lambda: torch.empty(C, device='cuda')
+    outs = []
+    for mode in ('fused', 'sums'):
+        mm, mv = dev(np.linspace(-1, 1, C)), dev(np.linspace(0.5, 1.5, C))
+        scale, shift, mean, rstd = f(), f(), f(), f()
+        y = torch.empty_like(x)
+        p = torch.empty(N, H // 2, W // 2, C, dtype=bf, device='cuda') if pool else None
+        if mode == 'fused':
+            wsb = torch.empty(ops.bn_train_workspace_bytes(C), dtype=torch.uint8, device='cuda')
+            sync = torch.zeros(4, dtype=torch.int32, device='cuda')
+            ops.bn_train_fwd(x, gamma, beta, 0.99, mm, mv, scale, shift, mean, rstd, y, wsb, sync, True, 0.25, 11, None, 3, pool_out=p)
+        else:
+            o = x.double().reshape(-1, C)
+            sums = torch.round(torch.cat([o.sum(0), (o * o).sum(0)]) * 2 ** 20).to(torch.int64).contiguous()
+            ops.bn_train_fwd_sums(x, sums, gamma, beta, 0.99, mm, mv, scale, shift, mean, rstd, y, True, 0.25, 11, None, 3, pool_out=p)
+        torch.cuda.synchronize()
+        outs.append((y, p, scale, shift, mean, rstd, mm, mv))
+    a, b = outs
+    for i in (2, 3, 4, 5, 6, 7):
+        assert torch.allclose(a[i], b[i], rtol=1e-5, atol=1e-6), i
+    # coefficients agree to fp32 rounding, so the 16-bit activations agree except for rare one-ulp flips
+    assert (a[0].float() - b[0].float()).abs().max().item() <= 4e-2
+    assert (a[0] != b[0]).float().mean().item() < 1e-3
+    if pool:
+        assert (a[1] != b[1]).float().mean().item() < 1e-3

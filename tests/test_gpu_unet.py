@@ -231,8 +231,9 @@ def test_forward_512_and_tta_bf16_mask_disagreement(cuda):
         assert np.mean(np.rot90(mask) != mask_r.cpu().numpy()) <= 2 * lim + 1e-5
 
 
+@pytest.mark.parametrize('fused_bn', [3, 2, 1, 0])
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
-def test_train_step_nfb32_against_oracle(cuda, precision):
+def test_train_step_nfb32_against_oracle(cuda, precision, fused_bn):
     """One train_on_batch (dice, dropout off): loss, every gradient tensor, BN moving statistics.
     fp32 check mode: within 3e-3 relative L2 of the fp64 oracle for every tensor.  (The BN backward of this
     random-init dice network cancels catastrophically - dz - mean(dz) - so even torch-CPU float32 autograd of the
@@ -247,8 +248,12 @@ def test_train_step_nfb32_against_oracle(cuda, precision):
     x = rng.standard_normal((4, 32, 32)).astype(np.float32)
     y = (rng.random((4, 32, 32)) < 0.126).astype(np.uint8)
     L, nw, st, g, _ = oracle.train_step(w, x, y, spec=spec, loss='dice_loss')
+    from deepcalcium import _native as nat
     eng = _engine(32, precision, w, use_graphs=False)
-    m = eng.train_step(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), loss='dice_loss', dropout=False)
+    # BatchNorm variants: 3 / 2 = batch statistics taken in the conv epilogues (bf16; everywhere / where it pays = the
+    # default), 1 = single-launch kernels, 0 = separate passes
+    with nat.policy(fused_bn=fused_bn):
+        m = eng.train_step(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), loss='dice_loss', dropout=False)
     assert abs(float(m[0].item()) - L) < (1e-4 if precision == 'fp32' else 2e-3)
     if precision == 'bf16':
         _, _, _, g_emu, _ = oracle.train_step(w, x, y, spec=spec, loss='dice_loss', emulate_bf16=True)
