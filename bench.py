@@ -632,21 +632,34 @@ def parity_train_dp(comm, spec):
     loss_dp = float(m[0].item())
     out = {}
     if comm.rank == 0:
-        ref = UNetEngine(spec, precision='fp32', use_graphs=False)
-        ref.set_weights_dict(w)
-        loss_ref = float(ref.train_step(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), loss='dice_loss', dropout=False)[0].item())
-        worst = ('', 0.0)
-        for k in dp.G:
-            a_, b_ = dp.G[k].double().cpu().numpy(), ref.G[k].double().cpu().numpy()
-            nb = np.linalg.norm(b_)
-            r = float(np.linalg.norm(a_ - b_) / nb) if nb > 0 else float(np.abs(a_).max())
-            if r > worst[1]:
-                worst = (k, r)
-        wd, wr = dp.get_weights_dict(), ref.get_weights_dict()
-        stat = max(float(np.max(np.abs(wd[k] - wr[k]))) for k in wd if 'moving' in k)
+        from deepcalcium import _native as nat
+
+        def single(**pol):
+            ref = UNetEngine(spec, precision='fp32', use_graphs=False)
+            ref.set_weights_dict(w)
+            with nat.policy(**pol):
+                loss = float(ref.train_step(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), loss='dice_loss', dropout=False)[0].item())
+            worst = ('', 0.0)
+            for k in dp.G:
+                a_, b_ = dp.G[k].double().cpu().numpy(), ref.G[k].double().cpu().numpy()
+                nb = np.linalg.norm(b_)
+                r = float(np.linalg.norm(a_ - b_) / nb) if nb > 0 else float(np.abs(a_).max())
+                if r > worst[1]:
+                    worst = (k, r)
+            wd, wr = dp.get_weights_dict(), ref.get_weights_dict()
+            return loss, worst, max(float(np.max(np.abs(wd[k] - wr[k]))) for k in wd if 'moving' in k)
+        # The data-parallel BatchNorm runs on the grid-barrier kernels (fixed-order sums + in-kernel rank exchange); a
+        # single device picks the channel-slab cluster kernels for small tensors, whose fp32 partial sums are grouped
+        # differently.  BatchNorm-backward sums of this network cancel to ~1e-3 of their terms, so the two groupings differ
+        # at the 1e-3 level in beta / gamma gradients (the fp32 noise floor of the quantity).  grad_rel_err
+        # compares like with like (bn_slab = 0 on the single device); the default-dispatch figure is reported beside it.
+        loss_ref, worst, stat = single(bn_slab=0)
+        _, worst_d, _ = single()
         out = {'loss_abs_err': abs(loss_dp - loss_ref), 'grad_rel_err': worst[1], 'grad_rel_err_tensor': worst[0],
                'bn_moving_stat_max_abs_diff': stat,
-               'parity_config': 'fp32 check mode, dropout off, global batch %d of 64x64, DP vs the single-device batch' % Bg}
+               'grad_rel_err_vs_default_dispatch': worst_d[1], 'grad_rel_err_vs_default_dispatch_tensor': worst_d[0],
+               'parity_config': 'fp32 check mode, dropout off, global batch %d of 64x64, DP vs the single-device batch (same BatchNorm '
+                                'kernel family: bn_slab = 0; *_vs_default_dispatch: the single device on its default kernels)' % Bg}
     import torch.distributed as dist
     dist.barrier()
     return out

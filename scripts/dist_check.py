@@ -49,9 +49,14 @@ sync_parameters(dp, comm)
 m = dp.train_step(torch.from_numpy(x[f:f + c]).cuda(), torch.from_numpy(y[f:f + c]).cuda(), loss='dice_loss', dropout=False)
 loss_dp = float(m[0].item())
 if comm.rank == 0:
+    from deepcalcium import _native as nat
     ref = UNetEngine(spec, precision='fp32', use_graphs=False)
     ref.set_weights_dict(w)
-    loss_ref = float(ref.train_step(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), loss='dice_loss', dropout=False)[0].item())
+    # like with like: the data-parallel BatchNorm uses the grid-barrier kernels, so the single device does too (its default
+    # for small tensors, the channel-slab cluster kernels, groups the fp32 partial sums differently: 1e-3 on the
+    # cancellation-prone beta / gamma gradients of this network)
+    with nat.policy(bn_slab=0):
+        loss_ref = float(ref.train_step(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), loss='dice_loss', dropout=False)[0].item())
     # Adam's first step is lr * sign(g) for every weight, so weights with |g| ~ 0 are not comparable between two
     # summation orders; the all-reduced GRADIENTS and the BN moving statistics are.
     worst = ('', 0.0)
@@ -66,6 +71,42 @@ if comm.rank == 0:
           % (loss_dp, loss_ref, worst[0], worst[1], stat))
     good = abs(loss_dp - loss_ref) < 1e-5 and worst[1] < 1e-4 and stat < 1e-5
     print('data-parallel training matches the single-device batch: %s' % good)
+    ok &= bool(good)
+# ---- 3. the same in the bf16 tensor-core mode under the default policy (batch statistics from the conv epilogues, in-kernel
+# SyncBN exchange of the fixed-point sums): against the single-device bf16 step on the concatenated batch.  The two runs
+# round the same fp32 accumulations at different tile boundaries, so the comparison is at bf16 tolerance; the BatchNorm
+# moving statistics (the exchanged sums) must agree to fp32 rounding.  B = 32 crops of 64 x 64 so that the level-0..2
+# tensors pass the size gate of the statistics epilogue.
+B, H = 32, 64
+x = np.random.default_rng(3).standard_normal((B, H, H)).astype(np.float32)
+y = (np.random.default_rng(4).random((B, H, H)) < 0.126).astype(np.uint8)
+f, c = shard_range(B, comm.world, comm.rank)
+dpb = UNetEngine(spec, precision='bf16', use_graphs=False)
+dpb.set_weights_dict(w)
+dpb.comm = comm
+attach_peers(dpb, comm)
+sync_parameters(dpb, comm)
+from deepcalcium import _native as nat
+with nat.policy(fused_bn=3):
+    m = dpb.train_step(torch.from_numpy(x[f:f + c]).cuda(), torch.from_numpy(y[f:f + c]).cuda(), loss='dice_loss', dropout=False)
+loss_dp = float(m[0].item())
+if comm.rank == 0:
+    ref = UNetEngine(spec, precision='bf16', use_graphs=False)
+    ref.set_weights_dict(w)
+    with nat.policy(fused_bn=3):
+        loss_ref = float(ref.train_step(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), loss='dice_loss', dropout=False)[0].item())
+    errs = {}
+    for k in dpb.G:
+        a_, b_ = dpb.G[k].double().cpu().numpy(), ref.G[k].double().cpu().numpy()
+        if np.linalg.norm(b_) > 0:
+            errs[k] = float(np.linalg.norm(a_ - b_) / np.linalg.norm(b_))
+    wd, wr = dpb.get_weights_dict(), ref.get_weights_dict()
+    stat = max(float(np.max(np.abs(wd[k] - wr[k]))) for k in wd if 'moving' in k)
+    worst = max(errs, key=errs.get)
+    print('bf16 DP (epilogue statistics + in-kernel SyncBN) loss %.6f single-GPU loss %.6f; gradient rel. L2 diff worst %s %.3g, median %.3g; '
+          'max |BN moving stat diff| %.3g' % (loss_dp, loss_ref, worst, errs[worst], float(np.median(list(errs.values()))), stat))
+    good = abs(loss_dp - loss_ref) < 2e-3 and stat < 2e-2
+    print('bf16 data-parallel step consistent with the single-device batch: %s' % good)
     ok &= bool(good)
 dist.barrier()
 dist.destroy_process_group()
