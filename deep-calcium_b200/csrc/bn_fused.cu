@@ -1,10 +1,10 @@
 // Training-mode BatchNorm of the UNet2DS blocks (Keras 2.0.6 BatchNormalization, unet_2d_summary.py:157,165) as
 // SINGLE-LAUNCH kernels: batch statistics are a grid-wide dependency, so the separate-pass version costs four launches
 // per layer (stats, finalize+apply, backward reduce, backward apply: 88 launches and ~40 % of a 32-crop training step).
-// Here one persistent kernel does   reduce -> grid barrier -> fixed-order cross-CTA sum -> grid barrier -> apply,
+// Here one persistent kernel does   reduce -> cross-CTA total -> grid barrier -> apply,
 // re-reading in the second phase what the first phase just pulled through L2 (every tensor of a 128^2 x 32 step is
-// smaller than the 126 MB L2).  The cross-CTA sum is a fixed-order tree (per-CTA partials in a workspace, each value
-// summed by one warp in a fixed pattern), so results are bit-reproducible run to run - no floating-point atomics.
+// smaller than the 126 MB L2).  The cross-CTA total is a sum of 64-bit FIXED-POINT integers (per-CTA fp64 partials in a
+// fixed order, integer atomics across CTAs), so results are bit-reproducible run to run - no floating-point atomics.
 //
 // Data-parallel training (SyncBN): with `peers` set, the per-channel totals of every rank are exchanged
 // INSIDE the kernel over NVLink - each rank stores its totals into every peer's exchange slot (peer-mapped memory),
@@ -55,6 +55,30 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter) {
     __threadfence();
   }
   __syncthreads();
+}
+
+// Cross-CTA totals as 64-bit FIXED-POINT integer atomics (the caller zeroes totals_q): integer addition is associative, so
+// the total does not depend on the arrival order - bit-reproducible like the fixed-order tree below, but it needs neither
+// the workspace round trip of the per-CTA partials nor the second grid barrier.  Units: 2^-20 for the forward sums of
+// activations (range 8.8e12), 2^-40 for the backward sums of gradients (range 8.4e6, resolution 9e-13).
+__device__ __forceinline__ void add_fixed(long long* totals_q, int idx, double v, double units_inv) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(totals_q) + idx, (unsigned long long)__double2ll_rn(v * units_inv));
+}
+constexpr double FWD_UNITS_INV = 1048576.0, FWD_UNITS = 1.0 / 1048576.0;                 // 2^20
+constexpr double BWD_UNITS_INV = 1099511627776.0, BWD_UNITS = 1.0 / 1099511627776.0;     // 2^40
+
+// The totals live in the caller's workspace, which is ZERO when a launch starts: after every CTA has taken its copy, the
+// last one to say so (second sync word) clears them again for the next launch that uses the workspace.
+__device__ __forceinline__ void release_totals(long long* totals_q, int V, unsigned* done_counter) {
+  __shared__ int s_last_reader;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last_reader = (atomicAdd(done_counter, 1u) == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last_reader)
+    for (int i = threadIdx.x; i < V; i += blockDim.x) totals_q[i] = 0;
 }
 
 // partial[cta][V] (double) -> totals[V]: value u is summed by warp (u % 8) of CTA (u / 8 % grid) - lanes take every
@@ -161,11 +185,9 @@ bn_train_fwd_kernel(const BnFwdParams p) {
       const int lc = idx / (2 * VEC), comp = idx % (2 * VEC);
       double acc = 0;
       for (int rr = 0; rr < rows_par; ++rr) acc += (double)sh[(rr * lanes_c + lc) * 2 * VEC + comp];
-      p.partial[(size_t)blockIdx.x * V + (comp / VEC) * C + lc * VEC + (comp % VEC)] = acc;
+      add_fixed(reinterpret_cast<long long*>(p.totals), (comp / VEC) * C + lc * VEC + (comp % VEC), acc, FWD_UNITS_INV);
     }
     grid_barrier(p.sync + 0);
-    reduce_partials(p.partial, V, p.totals);
-    grid_barrier(p.sync + 1);
   }
   // ---------------- per-channel coefficients (every CTA; block 0 publishes them and updates the moving statistics)
   double* s_tot = s_dyn;                               // V doubles
@@ -177,11 +199,15 @@ bn_train_fwd_kernel(const BnFwdParams p) {
       for (int i = threadIdx.x; i < V; i += blockDim.x) s_tot[i] = (double)__ldcg(p.sums_q + i) * tc::STATS_Q_INV;
       __syncthreads();
     }
-  } else if (p.pv.world > 1) {
-    peer_exchange(p.pv, p.totals, V, s_tot);
   } else {
-    for (int i = threadIdx.x; i < V; i += blockDim.x) s_tot[i] = __ldcg(p.totals + i);
-    __syncthreads();
+    const long long* tq = reinterpret_cast<const long long*>(p.totals);
+    if (p.pv.world > 1) {
+      peer_exchange_fn(p.pv, [&](int i) { return (double)__ldcg(tq + i) * FWD_UNITS; }, V, s_tot);
+    } else {
+      for (int i = threadIdx.x; i < V; i += blockDim.x) s_tot[i] = (double)__ldcg(tq + i) * FWD_UNITS;
+      __syncthreads();
+    }
+    release_totals(reinterpret_cast<long long*>(p.totals), V, p.sync + 1);
   }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const double mean = s_tot[c] / (double)p.M_total;
@@ -352,18 +378,20 @@ bn_train_bwd_kernel(const BnBwdParams p) {
       const int lc = idx / (2 * VEC), comp = idx % (2 * VEC);
       double acc = 0;
       for (int rr = 0; rr < rows_par; ++rr) acc += (double)shm[(rr * lanes_c + lc) * 2 * VEC + comp];
-      p.partial[(size_t)blockIdx.x * V + (comp / VEC) * C + lc * VEC + (comp % VEC)] = acc;
+      add_fixed(reinterpret_cast<long long*>(p.totals), (comp / VEC) * C + lc * VEC + (comp % VEC), acc, BWD_UNITS_INV);
     }
   }
   grid_barrier(p.sync + 0);
-  reduce_partials(p.partial, V, p.totals);
-  grid_barrier(p.sync + 1);
   double* s_tot = s_dyn;
-  if (p.pv.world > 1) {
-    peer_exchange(p.pv, p.totals, V, s_tot);
-  } else {
-    for (int i = threadIdx.x; i < V; i += blockDim.x) s_tot[i] = __ldcg(p.totals + i);
-    __syncthreads();
+  {
+    const long long* tq = reinterpret_cast<const long long*>(p.totals);
+    if (p.pv.world > 1) {
+      peer_exchange_fn(p.pv, [&](int i) { return (double)__ldcg(tq + i) * BWD_UNITS; }, V, s_tot);
+    } else {
+      for (int i = threadIdx.x; i < V; i += blockDim.x) s_tot[i] = (double)__ldcg(tq + i) * BWD_UNITS;
+      __syncthreads();
+    }
+    release_totals(reinterpret_cast<long long*>(p.totals), V, p.sync + 1);
   }
   // ---------------- phase 2: this thread's channels only (same row partition as phase 1)
   float k1[VEC], k0[VEC];
@@ -820,8 +848,8 @@ using namespace dcb;
 
 extern "C" int dcb_bn_train_workspace_bytes(int C, size_t* bytes) {
   DCB_CHECK_ARG(bytes && C > 0, "dcb_bn_train_workspace_bytes: bad arguments");
-  // partials of at most 8 CTAs per SM + the totals
-  *bytes = ((size_t)sm_count() * 8 + 1) * 2 * (size_t)C * sizeof(double);
+  // the per-channel totals (64-bit fixed point)
+  *bytes = 2 * (size_t)C * sizeof(long long);
   return DCB_OK;
 }
 
@@ -837,10 +865,10 @@ static int launch_bn_fwd(BnFwdParams& p, void* ws, size_t ws_bytes, cudaStream_t
   if (limit == 0) limit = coresident_limit(bn_train_fwd_kernel<T, VEC, POOL>, smem > 16384 ? smem : 16384);
   if (limit <= 0) return fail(DCB_ERR_CUDA, "occupancy query failed for the fused BatchNorm kernel");
   const int grid = fused_grid(p.M, p.C, VEC, limit);
-  const size_t need = ((size_t)grid + 1) * 2 * p.C * sizeof(double);
+  const size_t need = 2 * (size_t)p.C * sizeof(long long);
   if (!ws || ws_bytes < need) return fail(DCB_ERR_WORKSPACE, "dcb_bn_train_fwd: workspace %zu B < required %zu B", ws_bytes, need);
-  p.partial = reinterpret_cast<double*>(ws);
-  p.totals = p.partial + (size_t)grid * 2 * p.C;
+  p.partial = nullptr;
+  p.totals = reinterpret_cast<double*>(ws);      // 64-bit fixed-point totals, zero on entry (see release_totals)
   {
     const cudaError_t le = launch_k(bn_train_fwd_kernel<T, VEC, POOL>, grid, 256, smem, st, policy(DCB_POLICY_PDL) != 0, p);
     if (le != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of bn_train_fwd_kernel failed: %s", cudaGetErrorString(le));
@@ -934,10 +962,10 @@ static int launch_bn_bwd(BnBwdParams& p, void* ws, size_t ws_bytes, cudaStream_t
   if (limit == 0) limit = coresident_limit(bn_train_bwd_kernel<T, VEC>, smem > 16384 ? smem : 16384);
   if (limit <= 0) return fail(DCB_ERR_CUDA, "occupancy query failed for the fused BatchNorm backward kernel");
   const int grid = fused_grid(p.M, p.C, VEC, limit);
-  const size_t need = ((size_t)grid + 1) * 2 * p.C * sizeof(double);
+  const size_t need = 2 * (size_t)p.C * sizeof(long long);
   if (!ws || ws_bytes < need) return fail(DCB_ERR_WORKSPACE, "dcb_bn_train_bwd: workspace %zu B < required %zu B", ws_bytes, need);
-  p.partial = reinterpret_cast<double*>(ws);
-  p.totals = p.partial + (size_t)grid * 2 * p.C;
+  p.partial = nullptr;
+  p.totals = reinterpret_cast<double*>(ws);      // 64-bit fixed-point totals, zero on entry (see release_totals)
   {
     const cudaError_t le = launch_k(bn_train_bwd_kernel<T, VEC>, grid, 256, smem, st, policy(DCB_POLICY_PDL) != 0, p);
     if (le != cudaSuccess) return fail(DCB_ERR_CUDA, "launch of bn_train_bwd_kernel failed: %s", cudaGetErrorString(le));

@@ -138,9 +138,10 @@ class UNetEngine(object):
         n_dbl += 8 + 2 * self.spec.nfb + 2
         self.dbl = torch.zeros(n_dbl, dtype=torch.float64, device=self.dev)
         # single-launch BatchNorm kernels (dcb_bn_train_fwd / _bwd): 4 barrier words per (layer, direction), zeroed at the
-        # start of every step, and one shared workspace for the per-CTA partial sums
+        # start of every step, and one shared workspace for the fixed-point per-channel totals (zeroed once; the kernels
+        # leave it zeroed)
         self.bn_sync = torch.zeros(8 * len(self.spec.blocks), dtype=torch.int32, device=self.dev)
-        self.bn_ws = torch.empty(ops.bn_train_workspace_bytes(max(b.cout for b in self.spec.blocks)), dtype=torch.uint8,
+        self.bn_ws = torch.zeros(ops.bn_train_workspace_bytes(max(b.cout for b in self.spec.blocks)), dtype=torch.uint8,
                                  device=self.dev)
         self.peers = None         # dcb_peer_exchange description for in-kernel SyncBN (engine.dist.attach_peers)
         self.metrics = torch.zeros(8, **f32)

@@ -238,9 +238,12 @@ int dcb_bn_bwd_apply(int dtype, const float* dy, int ldy, int offy, const void* 
 
 /* ---- training BatchNorm as single-launch kernels (csrc/bn_fused.cu) ----
  * dcb_bn_train_fwd = dcb_bn_stats + dcb_bn_finalize_apply (+ dcb_maxpool2x2 when pool_out is given: N x H x W pixels,
- * M = N*H*W) in one persistent launch with two grid barriers; dcb_bn_train_bwd = dcb_bn_bwd_reduce + dcb_bn_bwd_apply
- * (draw may alias x).  Cross-CTA sums are fixed-order (bit-reproducible, no floating-point atomics).
- * workspace: dcb_bn_train_workspace_bytes(C); sync: 4 uint32 words that the caller zeroes before EVERY launch.
+ * M = N*H*W) in one persistent launch with one grid barrier; dcb_bn_train_bwd = dcb_bn_bwd_reduce + dcb_bn_bwd_apply
+ * (draw may alias x).  Cross-CTA totals are 64-bit fixed-point integer sums (bit-reproducible, no floating-point atomics;
+ * forward 2^-20 units, backward 2^-40 units).
+ * workspace: dcb_bn_train_workspace_bytes(C) bytes that the caller ZEROES ONCE before the first use - the kernels leave it
+ * zeroed, one workspace serves any number of stream-ordered launches; sync: 4 uint32 words that the caller zeroes before
+ * EVERY launch.
  * peers (optional, data-parallel SyncBN): every rank's per-channel totals are exchanged inside the kernel through
  * peer-mapped memory (NVLink) and summed in rank order; M_total = rows over all ranks. */
 typedef struct dcb_peer_exchange {

@@ -56,7 +56,7 @@ for N, H, W, C in [sh for sh in shapes for _ in per_sm_list]:
     gamma, beta = torch.ones(C, device='cuda'), torch.zeros(C, device='cuda')
     sc, sh, mu, rs, dg, db = f(), f(), f(), f(), f(), f()
     sums = torch.zeros(4 * C, dtype=torch.float64, device='cuda')
-    ws = torch.empty(ops.bn_train_workspace_bytes(C), dtype=torch.uint8, device='cuda')
+    ws = torch.zeros(ops.bn_train_workspace_bytes(C), dtype=torch.uint8, device='cuda')
     sync = torch.zeros(8, dtype=torch.int32, device='cuda')
     seed_dev = torch.tensor([1], dtype=torch.int64, device='cuda')
 

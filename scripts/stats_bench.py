@@ -45,7 +45,7 @@ LAYERS = [('conv', 32, 128, 32, 0, 32), ('conv', 32, 128, 32, 32, 32), ('conv', 
           ('conv', 32, 16, 128, 0, 256), ('conv', 32, 16, 256, 0, 256), ('conv', 32, 16, 256, 256, 256), ('conv', 32, 8, 256, 0, 512),
           ('conv', 32, 8, 512, 0, 512), ('convT', 32, 8, 512, 256), ('convT', 32, 16, 256, 128), ('convT', 32, 32, 128, 64),
           ('convT', 32, 64, 64, 32), ('c1', 32, 128, 32)]
-ws_bn = torch.empty(ops.bn_train_workspace_bytes(512), dtype=torch.uint8, device='cuda')
+ws_bn = torch.zeros(ops.bn_train_workspace_bytes(512), dtype=torch.uint8, device='cuda')
 for L in LAYERS:
     kind = L[0]
     if kind == 'conv':

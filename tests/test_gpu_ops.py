@@ -361,7 +361,7 @@ def _check_single_launch_batchnorm(precision, shape):
     gamma = dev(rng.uniform(0.5, 1.5, C)); beta = dev(0.1 * rng.standard_normal(C))
     mm0 = rng.standard_normal(C).astype(np.float32); mv0 = rng.uniform(0.5, 1.5, C).astype(np.float32)
     f = lambda: torch.empty(C, device='cuda')
-    ws = torch.empty(ops.bn_train_workspace_bytes(C), dtype=torch.uint8, device='cuda')
+    ws = torch.zeros(ops.bn_train_workspace_bytes(C), dtype=torch.uint8, device='cuda')
     seed_dev = torch.tensor([4242], dtype=torch.int64, device='cuda')
     p_drop = 0.25
     # ---- separate passes
@@ -715,7 +715,7 @@ def test_batchnorm_from_known_sums_equals_the_single_launch_kernel(cuda, shape, 
         y = torch.empty_like(x)
         p = torch.empty(N, H // 2, W // 2, C, dtype=bf, device='cuda') if pool else None
         if mode == 'fused':
-            wsb = torch.empty(ops.bn_train_workspace_bytes(C), dtype=torch.uint8, device='cuda')
+            wsb = torch.zeros(ops.bn_train_workspace_bytes(C), dtype=torch.uint8, device='cuda')
             sync = torch.zeros(4, dtype=torch.int32, device='cuda')
             ops.bn_train_fwd(x, gamma, beta, 0.99, mm, mv, scale, shift, mean, rstd, y, wsb, sync, True, 0.25, 11, None, 3, pool_out=p)
         else:
