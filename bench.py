@@ -285,7 +285,7 @@ def ncu_conv_traffic(precision):
 
 def per_layer_profile(eng, sess, spec, NB, H, W):
     """device time of every contraction launch of one forward pass (CUDA events on the launch stream,
-    eager mode) -> (rows, total conv flops, total conv ms)."""
+    eager mode, average of 5 passes) -> (rows, total conv flops, total conv ms)."""
     import torch
     from deepcalcium.engine import ops
     rows = []
@@ -307,17 +307,20 @@ def per_layer_profile(eng, sess, spec, NB, H, W):
 
     for n in names:
         wrap(n)
+    passes = []                      # 2 warm-up passes, then the per-launch AVERAGE over 5 passes
     try:
-        for _ in range(3):
+        for it in range(7):
             del events[:]
             eng._forward_inference(sess)
             torch.cuda.synchronize()
+            if it >= 2:
+                passes.append([e0.elapsed_time(e1) for _, _, e0, e1 in events])
     finally:
         for n, f in orig.items():
             setattr(ops, n, f)
     tot_f, tot_ms = 0.0, 0.0
-    for name, a, e0, e1 in events:
-        ms = e0.elapsed_time(e1)
+    for li, (name, a, e0, e1) in enumerate(events):
+        ms = float(np.mean([p[li] for p in passes]))
         fl = 0.0
         if name in ('conv3x3_fwd', 'conv3x3_fwd_fused'):
             src0, src1, wgt, out = a[0], a[1], a[2], a[3]
@@ -412,7 +415,7 @@ def run_ours(args):
     api = UNet2DSummary(cpdir='/tmp/deep-calcium-bench-cp-%d' % rank, dataset_name_func=lambda p: p,
                         series_summary_func=lambda p: host_imgs[p])
     paths = [('img%d' % (i % n_img)) for i in range(args.steps)]
-    api.predict(paths[:3], model, augmentation=True)
+    api.predict(paths[:6], model, augmentation=True)      # both pipeline slots warm (eager pass + graph capture each)
     barrier()
     t0 = time.perf_counter()
     Mp, _ = api.predict(paths, model, augmentation=True)

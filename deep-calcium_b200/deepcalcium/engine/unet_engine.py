@@ -361,25 +361,39 @@ class UNetEngine(object):
         self._run_graphed(s, 'graph', lambda: self._forward_inference(s))
         return s['prob'], s['logit']
 
-    @_on_engine_device
-    def predict_tta(self, summ_dev, window=512, augmentation=True, threshold=0.5, transforms=None):
-        """unet_2d_summary.py:578-595 for one summary image already on the device (fp32 [hs,ws]).
-        Returns (mask uint8 [hs,ws], act float64 [hs,ws]) as device tensors (static buffers).
-        ``transforms`` = (first, count) restricts the batch to a slice of the 8 transforms and skips
-        the combine (multi-GPU sharding, returns the raw probabilities [count,S,S])."""
-        hs, ws = summ_dev.shape
+    def _tta_state(self, hs, ws, window, augmentation, threshold, transforms, slot):
         n_aug = 8 if augmentation else 1
         first, count = transforms if transforms is not None else (0, n_aug)
         s = self._session(count, window, window, False)
-        self._ensure_inference_ready()
-        key = (hs, ws, n_aug, first, count, float(threshold), transforms is None)
+        key = (hs, ws, n_aug, first, count, float(threshold), transforms is None, slot)
         st = s['tta_graphs'].get(('bufs',) + key)
         if st is None:
             st = dict(summ=torch.zeros(hs, ws, dtype=torch.float32, device=self.dev),
                       mask=torch.zeros(hs, ws, dtype=torch.uint8, device=self.dev),
                       act=torch.zeros(hs, ws, dtype=torch.float64, device=self.dev))
             s['tta_graphs'][('bufs',) + key] = st
-        st['summ'].copy_(summ_dev)
+        return s, key, st, n_aug, first, count
+
+    @_on_engine_device
+    def tta_buffers(self, shape, window=512, augmentation=True, threshold=0.5, slot=0):
+        """the static input / output buffers of predict_tta for (shape, slot): a caller that pipelines images copies the
+        next summary image straight into ``summ`` of the OTHER slot (and reads ``mask`` of a finished one) while a step
+        runs; predict_tta(buffers['summ'], ..., slot=slot) then skips its device-to-device input copy."""
+        return self._tta_state(shape[0], shape[1], window, augmentation, threshold, None, slot)[2]
+
+    @_on_engine_device
+    def predict_tta(self, summ_dev, window=512, augmentation=True, threshold=0.5, transforms=None, slot=0):
+        """unet_2d_summary.py:578-595 for one summary image already on the device (fp32 [hs,ws]).
+        Returns (mask uint8 [hs,ws], act float64 [hs,ws]) as device tensors (static buffers).
+        ``transforms`` = (first, count) restricts the batch to a slice of the 8 transforms and skips
+        the combine (multi-GPU sharding, returns the raw probabilities [count,S,S]).
+        ``slot`` selects one of several independent sets of static input / output buffers (and captured graphs) that
+        share the activation buffers: see tta_buffers."""
+        hs, ws = summ_dev.shape
+        s, key, st, n_aug, first, count = self._tta_state(hs, ws, window, augmentation, threshold, transforms, slot)
+        self._ensure_inference_ready()
+        if summ_dev.data_ptr() != st['summ'].data_ptr():
+            st['summ'].copy_(summ_dev)
 
         def run():
             with nat.policy(pdl=1 if self.pdl else 0):

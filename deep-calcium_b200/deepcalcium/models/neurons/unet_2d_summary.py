@@ -478,18 +478,21 @@ class UNet2DSummary(object):
         assert tuple(window_shape) == (512, 512), 'TODO: implement variable window sizes.'
         Mp, names = [], []
         mean_prec, mean_reca, mean_comb = 0., 0., 0.
-        # Two-deep software pipeline over the datasets: while the GPU runs image i, the host loads / standardises
-        # image i+1 and its host->device copy runs on a side stream from pinned memory; masks come back through
-        # pinned buffers.  Results are identical to the serial loop of the reference (:578-595).
+        # Two-deep software pipeline over the datasets: while the GPU runs image i, the host loads / standardises image
+        # i+1 and copies it from pinned memory STRAIGHT INTO the engine's static input buffer of the other slot (upload
+        # stream); the mask of image i leaves through a pinned buffer on a download stream.  The compute stream carries
+        # nothing but the captured step (no staging copies between two steps).  Results are identical to the serial loop
+        # of the reference (:578-595).
         dev = model.engine.dev
-        # the copy stream and the pinned staging buffers live on the engine and are reused by later predict() calls: pinned
+        # the streams and the pinned staging buffers live on the engine and are reused by later predict() calls: pinned
         # allocations are slow (cudaHostAlloc maps the pages for every visible GPU - ~75 ms per call with 2 ranks on an
         # 8-GPU box, which was the whole difference between the device-timed and the end-to-end number at N >= 2)
         cache = model.engine.__dict__.setdefault('_predict_staging', {})
-        if 'stream' not in cache:
-            cache['stream'] = torch.cuda.Stream(device=dev)
+        if 'up' not in cache:
+            cache['up'] = torch.cuda.Stream(device=dev)
+            cache['down'] = torch.cuda.Stream(device=dev)
             cache['slots'] = [{}, {}]
-        copy_stream, slots = cache['stream'], cache['slots']
+        up_stream, down_stream, slots = cache['up'], cache['down'], cache['slots']
 
         def stage(i):
             dsp = dataset_paths[i]
@@ -497,15 +500,19 @@ class UNet2DSummary(object):
             if summ.shape[0] > window_shape[0] or summ.shape[1] > window_shape[1]:
                 raise ValueError('summary image %s larger than the window %s' % (summ.shape, window_shape))
             sl = slots[i % 2]
-            if sl.get('shape') != summ.shape:
-                sl.update(shape=summ.shape, hin=torch.empty(summ.shape, dtype=torch.float32).pin_memory(),
-                          din=torch.empty(summ.shape, dtype=torch.float32, device=dev),
+            cfg = (summ.shape, bool(augmentation), float(threshold))
+            if sl.get('cfg') != cfg:
+                bufs = model.engine.tta_buffers(summ.shape, window=window_shape[0], augmentation=augmentation,
+                                                threshold=threshold, slot=i % 2)
+                sl.update(cfg=cfg, hin=torch.empty(summ.shape, dtype=torch.float32).pin_memory(),
+                          din=bufs['summ'], dmask=bufs['mask'],
                           hout=torch.empty(summ.shape, dtype=torch.uint8).pin_memory(),
-                          ready=torch.cuda.Event(), done=torch.cuda.Event())
+                          ready=torch.cuda.Event(), computed=torch.cuda.Event(), done=torch.cuda.Event())
             sl['hin'].copy_(torch.from_numpy(summ))
-            with torch.cuda.stream(copy_stream):
+            # the previous user of this slot's device buffers (image i - 2) was collected before this call
+            with torch.cuda.stream(up_stream):
                 sl['din'].copy_(sl['hin'], non_blocking=True)
-                sl['ready'].record(copy_stream)
+                sl['ready'].record(up_stream)
             sl['summ'] = summ
 
         scores = [0., 0., 0.]
@@ -540,11 +547,15 @@ class UNet2DSummary(object):
             stage(0)
         for i, dsp in enumerate(dataset_paths):
             sl = slots[i % 2]
-            torch.cuda.current_stream(dev).wait_event(sl['ready'])
-            mask, _ = model.engine.predict_tta(sl['din'], window=window_shape[0], augmentation=augmentation,
-                                               threshold=threshold)
-            sl['hout'].copy_(mask, non_blocking=True)      # in stream order: before image i+1 overwrites the static mask
-            sl['done'].record()
+            main = torch.cuda.current_stream(dev)
+            main.wait_event(sl['ready'])
+            model.engine.predict_tta(sl['din'], window=window_shape[0], augmentation=augmentation, threshold=threshold,
+                                     slot=i % 2)
+            sl['computed'].record(main)
+            with torch.cuda.stream(down_stream):           # this slot's mask buffer is not touched again before finalize(i)
+                down_stream.wait_event(sl['computed'])
+                sl['hout'].copy_(sl['dmask'], non_blocking=True)
+                sl['done'].record(down_stream)
             # image i is now queued on the GPU; meanwhile collect image i-1 (frees its slot) and stage image i+1 into it
             if i >= 1:
                 finalize(i - 1)

@@ -15,7 +15,7 @@ model = UNetModel.__new__(UNetModel)
 model.window_shape, model.spec, model.engine = (512, 512), spec, eng
 api = UNet2DSummary(cpdir='/tmp/deep-calcium-bench-cp-x', dataset_name_func=lambda p: p, series_summary_func=lambda p: host_imgs[p])
 paths = [('img%d' % (i % 4)) for i in range(20)]
-api.predict(paths[:3], model, augmentation=True)
+api.predict(paths[:6], model, augmentation=True)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 api.predict(paths, model, augmentation=True)

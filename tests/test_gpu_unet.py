@@ -412,6 +412,29 @@ def test_reference_surface_fit_predict_evaluate(cuda, tmp_path):
     assert set(scores.keys()) == {True, False}
 
 
+def test_pipelined_predict_equals_the_serial_engine_calls(cuda, tmp_path):
+    """UNet2DSummary.predict overlaps upload / step / download of consecutive images over two buffer slots
+    (unet_2d_summary.py:578-595 is a serial loop): seven different images of two shapes, with and without TTA, must come
+    back exactly as engine.predict_tta computes them one at a time, in order."""
+    from deepcalcium.models.neurons import UNet2DSummary
+    from deepcalcium.models.neurons.unet_2d_summary import UNetModel
+    spec, w, _ = _nfb32_case()
+    eng = _engine(32, 'fp16', w)
+    rng = np.random.default_rng(5)
+    imgs = {('img%d' % i): rng.standard_normal((500, 480) if i % 3 else (512, 512)).astype(np.float32) for i in range(7)}
+    model = UNetModel.__new__(UNetModel)
+    model.window_shape, model.spec, model.engine = (512, 512), spec, eng
+    api = UNet2DSummary(cpdir=str(tmp_path / 'cp'), dataset_name_func=lambda p: p, series_summary_func=lambda p: imgs[p])
+    paths = list(imgs.keys())
+    for aug in (True, False):
+        for rep in range(2):                     # second pass: every slot replays its captured graph
+            Mp, names = api.predict(paths, model, augmentation=aug)
+            assert names == paths
+            for p_, mp in zip(paths, Mp):
+                m1, _ = eng.predict_tta(torch.from_numpy(imgs[p_]).cuda(), augmentation=aug)
+                assert np.array_equal(mp, m1.cpu().numpy()), (aug, rep, p_)
+
+
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 def test_upsampling_mode_forward_and_train_step(cuda, precision):
     """The non-default `upsampling_or_transpose='upsampling'` graph (unet_2d_summary.py:160-161): nearest 2x upsampling
