@@ -1778,9 +1778,11 @@ struct TcFlatParams {
   void* out;
   const float* scale;
   const float* shift;
+  int stile;                // bytes of one epilogue warp's transpose tile: 2048 (16-bit outputs) or 4096 (fp32)
   long long* stat_sums;     // STATS instantiation (training forward), see stats_epilogue.cuh
 };
-constexpr int FL_THREADS = 192;
+constexpr int FL_QUARTETS = 2;                              // epilogue quartets: quartet q drains accumulator stage q (every other item)
+constexpr int FL_THREADS = 64 + FL_QUARTETS * 4 * 32;
 constexpr uint32_t FL_WSLOT = 3u * 128u * 128u;   // three [128 x 64] bf16 weight tiles
 
 template <bool STATS>
@@ -1795,7 +1797,7 @@ tapgemm_tc_flat_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_pb = smem;                                   // 2 pixel buffers
   uint8_t* s_w = s_pb + 2u * p.pbuf_bytes;                // 2 weight slots
-  uint8_t* s_stage = s_w + 2u * FL_WSLOT;                 // 4 x 4 KB transpose tiles of the epilogue
+  uint8_t* s_stage = s_w + 2u * FL_WSLOT;                 // one 4 KB transpose tile per epilogue warp
   const int K = p.C0 + p.C1;
   const int num_items = p.N * p.ptiles * p.mtiles;
   uint32_t tmem_cols = 32;
@@ -1899,9 +1901,13 @@ tapgemm_tc_flat_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
       }
     }
   } else {
-    const int quarter = warp & 3;
+    // Draining a [128 ch x NT] accumulator through the per-warp transpose tiles takes one quartet longer than the MMAs of
+    // a 64 .. 128-channel K take (the statistics experiment: +70 % epilogue work = +70 % kernel time), so two quartets
+    // alternate: quartet q owns accumulator stage q.
+    const int quarter = warp & 3, eset = (warp - 2) >> 2;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      if ((int)(it & 1u) != eset) continue;
       int n, f0, mt, y_lo;
       decode(item, n, f0, mt, y_lo);
       const uint32_t acc = it & 1u;
@@ -1916,7 +1922,7 @@ tapgemm_tc_flat_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
       mbar_wait(&bar_tfull[acc], (it >> 1) & 1u);
       tc_fence_after();
       epilogue_swapped<STATS>(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)p.NT, p.NT, warp_valid, sc, sh, p.relu,
-                              p.out_f32, p.out, s_stage + quarter * 4096, lane, pix_index, p.f16, &st_s, &st_q);
+                              p.out_f32, p.out, s_stage + (eset * 4 + quarter) * p.stile, lane, pix_index, p.f16, &st_s, &st_q);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[acc]);
@@ -1927,16 +1933,16 @@ tapgemm_tc_flat_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
   if constexpr (STATS) {
     // the grid is a multiple of mtiles, so every item of this CTA has the same channel tile mt; the four epilogue warps
-    // own 32 channels each: written as four accumulator blocks of one pseudo-warp (layout of stats_cta_finish)
+    // of a quartet own 32 channels each: written as four accumulator blocks per quartet (layout of stats_cta_finish)
     float* dump = reinterpret_cast<float*>(s_pb);
     if (warp >= 2) {
-      const int quarter = warp & 3;
-      float* d = dump + ((size_t)(quarter * 16) + (lane >> 1)) * 4 + (lane & 1);
+      const int quarter = warp & 3, eset = (warp - 2) >> 2;
+      float* d = dump + ((size_t)((eset * 4 + quarter) * 16) + (lane >> 1)) * 4 + (lane & 1);
       d[0] = st_s; d[2] = st_q;
     }
     __syncthreads();
     const int mt = blockIdx.x % p.mtiles;
-    stats_cta_finish(dump, 1, 4, [&](int bi) { return mt * 128 + bi * 32; }, p.Cout, p.stat_sums);
+    stats_cta_finish(dump, FL_QUARTETS, 4, [&](int bi) { return mt * 128 + bi * 32; }, p.Cout, p.stat_sums);
   }
 }
 
@@ -2072,7 +2078,8 @@ static int run_tc_flat(const TapGeom& g, const void* s0, int C0, const void* s1,
   if (positions < 512) return DCB_ERR_UNSUPPORTED;     // tiny maps: too much of a 192..256-position tile would be padding
   TcFlatParams p;
   memset(&p, 0, sizeof(p));
-  const size_t budget = 223 * 1024 - 2 * (size_t)FL_WSLOT - 4 * 4096;
+  const size_t stile = out_f32 ? 4096 : 2048;            // per-warp transpose tile of the epilogue
+  const size_t budget = 223 * 1024 - 2 * (size_t)FL_WSLOT - FL_QUARTETS * 4 * stile;
   int NT = 0, R = 0; uint32_t pbuf = 0;
   for (int cand : {256, 192, 128}) {
     R = (cand + 3 * Wp + 1 + Wp - 1) / Wp;
@@ -2089,7 +2096,7 @@ static int run_tc_flat(const TapGeom& g, const void* s0, int C0, const void* s1,
   }
   p.N = g.N; p.H = g.GH; p.W = g.GW; p.Wp = Wp; p.C0 = C0; p.C1 = C1; p.nkc = (C0 + C1) / 64;
   p.Cout = Nout; p.mtiles = cdiv(Nout, 128); p.NT = NT; p.ptiles = (int)((positions + NT - 1) / NT); p.R = R;
-  p.wrows = Nout < 128 ? Nout : 128; p.pbuf_bytes = pbuf;
+  p.wrows = Nout < 128 ? Nout : 128; p.pbuf_bytes = pbuf; p.stile = (int)stile;
   p.relu = relu; p.out_f32 = out_f32; p.out = out; p.scale = scale; p.shift = shift; p.f16 = g.f16;
   CUtensorMap mA0, mA1, mB;
   auto mk = [&](CUtensorMap* m, const void* ptr, int C) -> int {
@@ -2114,7 +2121,7 @@ static int run_tc_flat(const TapGeom& g, const void* s0, int C0, const void* s1,
     if (e != cudaSuccess) return fail(DCB_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const size_t dyn = 2 * (size_t)pbuf + 2 * (size_t)FL_WSLOT + 4 * 4096 + 1024;
+  const size_t dyn = 2 * (size_t)pbuf + 2 * (size_t)FL_WSLOT + FL_QUARTETS * 4 * stile + 1024;
   const int items = p.N * p.ptiles * p.mtiles;
   int grid = items < sm_count() ? items : sm_count();
   // The flat kernel is bound by its four epilogue warps (one 32 x 32 transpose per 32 pixels); the statistics add ~70 % to
@@ -2338,7 +2345,11 @@ int run_tc_fwd(const TapGeom& g, const void* s0, int C0, const void* s1, int C1,
       return DCB_OK;
     }
   }
-  {
+  // A training forward that wants its batch statistics goes to the generic kernel (statistics in the epilogue, +2 us)
+  // rather than to the flat kernel (no statistics at the default policy): what the flat kernel gains on the conv (~20 %
+  // on 64-pixel rows) is less than the separate statistics pass it would leave to the BatchNorm kernel
+  // (scripts/train_time.py flat=0 / 1: 2.589 vs 2.609 ms per step before this rule).
+  if (!(stats && stats->sums && policy(DCB_POLICY_FUSED_BN) == 2)) {
     const int e = run_tc_flat(g, s0, C0, s1, C1, B, Nout, out, scale, shift, relu, out_f32, st, stats);
     if (e != DCB_ERR_UNSUPPORTED) return e;
   }
