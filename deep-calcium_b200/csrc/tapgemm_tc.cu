@@ -2898,7 +2898,9 @@ static WgradPlan plan_wgrad(const TapGeom& g, int K, int C0, int C1, int Nout) {
   }
   const int num_ptiles = w.tiles_w * w.tiles_h * w.tiles_n;
   const int base_items = cdiv(K, 128) * (Nout / w.BN) * g.ntaps;
-  int splits = cdiv(2 * sm_count(), base_items);
+  // two items per CTA, never a partial third wave: with the split count rounded UP, 9 x 33 = 297 items on 148 CTAs gave
+  // one CTA three items and the launch the length of three (the static round-robin schedule has no stealing)
+  int splits = (2 * sm_count()) / base_items;
   if (splits > num_ptiles) splits = num_ptiles;
   if (splits > 64) splits = 64;
   if (splits < 1) splits = 1;
