@@ -508,6 +508,11 @@ class UNet2DSummary(object):
                           din=bufs['summ'], dmask=bufs['mask'],
                           hout=torch.empty(summ.shape, dtype=torch.uint8).pin_memory(),
                           ready=torch.cuda.Event(), computed=torch.cuda.Event(), done=torch.cuda.Event())
+                # buffers that were just created belong to the compute stream (their zero fill is queued there, and the
+                # allocator may have handed out memory that queued work still reads): the first upload waits for it
+                fresh = torch.cuda.Event()
+                fresh.record(torch.cuda.current_stream(dev))
+                up_stream.wait_event(fresh)
             sl['hin'].copy_(torch.from_numpy(summ))
             # the previous user of this slot's device buffers (image i - 2) was collected before this call
             with torch.cuda.stream(up_stream):
