@@ -513,7 +513,9 @@ class UNet2DSummary(object):
                 fresh = torch.cuda.Event()
                 fresh.record(torch.cuda.current_stream(dev))
                 up_stream.wait_event(fresh)
-            sl['hin'].copy_(torch.from_numpy(summ))
+            # plain memcpy into the pinned buffer: torch's CPU copy_ goes through the OpenMP pool, and a pool as wide as the
+            # machine next to another busy process (a second rank) turned this 1 MB copy into milliseconds
+            np.copyto(sl['hin'].numpy(), summ)
             # the previous user of this slot's device buffers (image i - 2) was collected before this call
             with torch.cuda.stream(up_stream):
                 sl['din'].copy_(sl['hin'], non_blocking=True)

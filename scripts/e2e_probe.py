@@ -2,6 +2,11 @@ import os, sys, time, cProfile, pstats
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/deep-calcium_b200')
 os.environ.setdefault('DEEP_CALCIUM_HOME', '/tmp/deep-calcium-home')
 import numpy as np, torch
+if 'WORLD_SIZE' in os.environ:      # under torchrun: one rank per GPU, NCCL initialised like bench.py does
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0'))))
+    dist.barrier()
 from deepcalcium.engine.graph import GraphSpec, he_normal_weights
 from deepcalcium.engine.unet_engine import UNetEngine
 from deepcalcium.models.neurons import UNet2DSummary
