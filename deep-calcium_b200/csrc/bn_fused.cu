@@ -11,6 +11,7 @@
 // publishes a flag carrying the step number, waits for the peers' flags and adds the slots in rank order - instead of
 // an NCCL all-reduce between two launches.
 #include <cooperative_groups.h>
+#include <type_traits>
 #include "elementwise.cuh"
 #include "stats_epilogue.cuh"
 
@@ -66,6 +67,32 @@ __device__ __forceinline__ void add_fixed(long long* totals_q, int idx, double v
 }
 constexpr double FWD_UNITS_INV = 1048576.0, FWD_UNITS = 1.0 / 1048576.0;                 // 2^20
 constexpr double BWD_UNITS_INV = 1099511627776.0, BWD_UNITS = 1.0 / 1099511627776.0;     // 2^40
+// The backward sums (sum dz, sum dz * xhat) cancel to ~1e-3 of their terms in this network, so ANY change in how fp32
+// partial sums are grouped (CTA partition, batch split over ranks, kernel variant) showed up as 1e-3 .. 5e-3 relative
+// differences in the beta / gamma gradients.  They are therefore accumulated EXACTLY: every element is converted to 2^-40
+// fixed point (one fp32 multiply by a power of two - exact - and one round-to-integer, the same for an element wherever
+// it is processed) and all additions are 64-bit integer additions: the totals are independent of thread / CTA / rank
+// partition and of the order of arrival, bit for bit.
+__device__ __forceinline__ long long to_q40(float v) { return __float2ll_rn(v * 1099511627776.f); }
+// The 64-bit conversions cost the 16-bit training mode 6 % of its step (16 per row and thread in a memory-bound kernel),
+// where the comparison between two runs is at 16-bit tolerance anyway: EXACT per-element accumulation in the fp32 check
+// mode (the mode parity is judged in), fp32 per-thread partials converted once per thread otherwise - the sums across
+// threads / CTAs / ranks are integer sums in both.
+__device__ __forceinline__ long long to_q20(float v) { return __float2ll_rn(v * 1048576.f); }
+template <bool EXACT, bool Q40> struct FixAcc;
+template <bool Q40> struct FixAcc<true, Q40> {
+  long long v = 0;
+  __device__ __forceinline__ void add(float x) { v += Q40 ? to_q40(x) : to_q20(x); }
+  __device__ __forceinline__ long long fixed() const { return v; }
+};
+template <bool Q40> struct FixAcc<false, Q40> {
+  float v = 0.f;
+  __device__ __forceinline__ void add(float x) { v += x; }
+  __device__ __forceinline__ long long fixed() const { return Q40 ? to_q40(v) : to_q20(v); }
+};
+template <bool EXACT> using BwdAcc = FixAcc<EXACT, true>;    // gradient sums, 2^-40 units
+template <bool EXACT> using FwdAcc = FixAcc<EXACT, false>;   // activation sums, 2^-20 units (the forward statistics of the check
+                                                             // mode are exact for the same reason: partition-independent)
 
 // The totals live in the caller's workspace, which is ZERO when a launch starts: after every CTA has taken its copy, the
 // last one to say so (second sync word) clears them again for the next launch that uses the workspace.
@@ -157,9 +184,7 @@ bn_train_fwd_kernel(const BnFwdParams p) {
   long long r1 = r0 + rows_per_cta; if (r1 > p.M) r1 = p.M;
   // ---------------- phase 1: per-CTA partial sums of x and x^2
   if constexpr (!PRE) {
-    float s[VEC], q[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) { s[i] = 0.f; q[i] = 0.f; }
+    FwdAcc<std::is_same<T, float>::value> s[VEC], q[VEC];
     const T* base = x + tc * VEC;
     long long r = r0 + tr;
     for (; r + 3LL * rows_par < r1; r += 4LL * rows_par) {
@@ -169,23 +194,23 @@ bn_train_fwd_kernel(const BnFwdParams p) {
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) { s[i] += v[u][i]; q[i] = fmaf(v[u][i], v[u][i], q[i]); }
+        for (int i = 0; i < VEC; ++i) { s[i].add(v[u][i]); q[i].add(v[u][i] * v[u][i]); }
     }
     for (; r < r1; r += rows_par) {
       float v[VEC];
       loadv<T, VEC>(base + r * C, v);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) { s[i] += v[i]; q[i] = fmaf(v[i], v[i], q[i]); }
+      for (int i = 0; i < VEC; ++i) { s[i].add(v[i]); q[i].add(v[i] * v[i]); }
     }
-    float* sh = reinterpret_cast<float*>(s_dyn);      // 256 * 2 * VEC floats
+    long long* sh = reinterpret_cast<long long*>(s_dyn);      // 256 * 2 * VEC int64
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) { sh[threadIdx.x * 2 * VEC + i] = s[i]; sh[threadIdx.x * 2 * VEC + VEC + i] = q[i]; }
+    for (int i = 0; i < VEC; ++i) { sh[threadIdx.x * 2 * VEC + i] = s[i].fixed(); sh[threadIdx.x * 2 * VEC + VEC + i] = q[i].fixed(); }
     __syncthreads();
     for (int idx = threadIdx.x; idx < lanes_c * 2 * VEC; idx += 256) {
       const int lc = idx / (2 * VEC), comp = idx % (2 * VEC);
-      double acc = 0;
-      for (int rr = 0; rr < rows_par; ++rr) acc += (double)sh[(rr * lanes_c + lc) * 2 * VEC + comp];
-      add_fixed(reinterpret_cast<long long*>(p.totals), (comp / VEC) * C + lc * VEC + (comp % VEC), acc, FWD_UNITS_INV);
+      long long acc = 0;
+      for (int rr = 0; rr < rows_par; ++rr) acc += sh[(rr * lanes_c + lc) * 2 * VEC + comp];
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.totals) + (comp / VEC) * C + lc * VEC + (comp % VEC), (unsigned long long)acc);
     }
     grid_barrier(p.sync + 0);
   }
@@ -344,15 +369,16 @@ bn_train_bwd_kernel(const BnBwdParams p) {
     for (int i = 0; i < VEC; ++i)
       if (fmaf(v[i], sc[i], sh[i]) <= 0.f) g[i] = 0.f;
   };
-  // ---------------- phase 1
+  // ---------------- phase 1: exact fixed-point sums (see to_q40)
   {
-    float rs[VEC], s[VEC], q[VEC];
+    float rs[VEC];
+    BwdAcc<std::is_same<T, float>::value> s[VEC], q[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) { rs[i] = p.rstd[c + i]; s[i] = 0.f; q[i] = 0.f; }
+    for (int i = 0; i < VEC; ++i) rs[i] = p.rstd[c + i];
     auto accumulate = [&](long long r, float (&g)[VEC], const float (&v)[VEC]) {
       masked(r, g, v);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) { s[i] += g[i]; q[i] = fmaf(g[i], (v[i] - mu[i]) * rs[i], q[i]); }
+      for (int i = 0; i < VEC; ++i) { s[i].add(g[i]); q[i].add(g[i] * ((v[i] - mu[i]) * rs[i])); }
     };
     long long r = r0 + tr;
     for (; r + rows_par < r1; r += 2LL * rows_par) {
@@ -370,15 +396,15 @@ bn_train_bwd_kernel(const BnBwdParams p) {
       loadv<T, VEC>(x + r * C + c, v0);
       accumulate(r, g0, v0);
     }
-    float* shm = reinterpret_cast<float*>(s_dyn);
+    long long* shm = reinterpret_cast<long long*>(s_dyn);      // 256 * 2 * VEC int64
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) { shm[threadIdx.x * 2 * VEC + i] = s[i]; shm[threadIdx.x * 2 * VEC + VEC + i] = q[i]; }
+    for (int i = 0; i < VEC; ++i) { shm[threadIdx.x * 2 * VEC + i] = s[i].fixed(); shm[threadIdx.x * 2 * VEC + VEC + i] = q[i].fixed(); }
     __syncthreads();
     for (int idx = threadIdx.x; idx < lanes_c * 2 * VEC; idx += 256) {
       const int lc = idx / (2 * VEC), comp = idx % (2 * VEC);
-      double acc = 0;
-      for (int rr = 0; rr < rows_par; ++rr) acc += (double)shm[(rr * lanes_c + lc) * 2 * VEC + comp];
-      add_fixed(reinterpret_cast<long long*>(p.totals), (comp / VEC) * C + lc * VEC + (comp % VEC), acc, BWD_UNITS_INV);
+      long long acc = 0;
+      for (int rr = 0; rr < rows_par; ++rr) acc += shm[(rr * lanes_c + lc) * 2 * VEC + comp];
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.totals) + (comp / VEC) * C + lc * VEC + (comp % VEC), (unsigned long long)acc);
     }
   }
   grid_barrier(p.sync + 0);
@@ -480,6 +506,37 @@ __device__ __forceinline__ void slab_cta_reduce(const float (&s)[8], const float
 }
 
 // cta_tot of every CTA of the cluster, summed in rank order -> s_tot (identical in all CTAs)
+// fixed-point thread partials (8 channels x {s, q}) -> cluster totals as doubles: lanes with the same channel group
+// (lane % lanes_c) meet by shuffles, the 16 warps through shared memory, the S CTAs of the cluster through DSMEM - integer
+// additions throughout, so the totals do not depend on how rows were distributed.  sh: >= 8 KB of shared memory.
+__device__ __forceinline__ void slab_reduce_fixed(cg::cluster_group& cluster, long long (&s)[8], long long (&q)[8], int CW, int S,
+                                                  float* sh, long long* cta_tot_q, double* s_tot, double units) {
+  const int lanes_c = CW >> 3, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int off = 16; off >= lanes_c; off >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] += __shfl_xor_sync(0xffffffffu, s[i], off); q[i] += __shfl_xor_sync(0xffffffffu, q[i], off); }
+  }
+  long long* shq = reinterpret_cast<long long*>(sh);            // [16 warps][lanes_c <= 4][16]
+  if (lane < lanes_c) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { shq[(warp * 4 + lane) * 16 + i] = s[i]; shq[(warp * 4 + lane) * 16 + 8 + i] = q[i]; }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < 2 * CW) {
+    const int comp = threadIdx.x / CW, ch = threadIdx.x % CW, lc = ch >> 3, i = ch & 7;
+    long long acc = 0;
+    for (int w = 0; w < SLAB_THREADS / 32; ++w) acc += shq[(w * 4 + lc) * 16 + comp * 8 + i];
+    cta_tot_q[threadIdx.x] = acc;
+  }
+  cluster.sync();
+  if ((int)threadIdx.x < 2 * CW) {
+    long long acc = 0;
+    for (int k = 0; k < S; ++k) acc += cluster.map_shared_rank(cta_tot_q, k)[threadIdx.x];
+    s_tot[threadIdx.x] = (double)acc * units;
+  }
+  cluster.sync();             // nobody leaves (or overwrites cta_tot_q) while a peer may still be reading it
+}
+
 __device__ __forceinline__ void slab_cluster_sum(cg::cluster_group& cluster, double* cta_tot, double* s_tot, int nout, int S) {
   cluster.sync();
   if ((int)threadIdx.x < nout) {
@@ -494,10 +551,11 @@ __device__ __forceinline__ void slab_cluster_sum(cg::cluster_group& cluster, dou
 template <typename T, bool POOL>
 __global__ void __launch_bounds__(SLAB_THREADS)
 bn_slab_fwd_kernel(const BnFwdParams p, const SlabGeom gm) {
-  __shared__ float sh[SLAB_THREADS * SLAB_PITCH];
+  __shared__ __align__(16) float sh[2048];                        // 8 KB: the warps' fixed-point partials
   if (threadIdx.x == 0) pdl_trigger();
   pdl_wait();
-  __shared__ double cta_tot[64], s_tot[64];
+  __shared__ double s_tot[64];
+  __shared__ long long cta_tot_q[64];
   __shared__ float s_sc[32], s_sh[32];
   cg::cluster_group cluster = cg::this_cluster();
   const int C = p.C, CW = gm.CW, S = gm.S;
@@ -509,10 +567,8 @@ bn_slab_fwd_kernel(const BnFwdParams p, const SlabGeom gm) {
   const long long r0 = (long long)rk * gm.rows_per_cta;
   long long r1 = r0 + gm.rows_per_cta; if (r1 > p.M) r1 = p.M;
   {
-    float s[8], q[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
-        long long r = r0 + tr;
+    FwdAcc<std::is_same<T, float>::value> sa[8], qa[8];
+    long long r = r0 + tr;
     for (; r + 3LL * rows_par < r1; r += 4LL * rows_par) {
       float v[4][8];
 #pragma unroll
@@ -520,17 +576,19 @@ bn_slab_fwd_kernel(const BnFwdParams p, const SlabGeom gm) {
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { s[i] += v[u][i]; q[i] = fmaf(v[u][i], v[u][i], q[i]); }
+        for (int i = 0; i < 8; ++i) { sa[i].add(v[u][i]); qa[i].add(v[u][i] * v[u][i]); }
     }
     for (; r < r1; r += rows_par) {
       float v[8];
       load8<T>(x + r * C + c, v);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] = fmaf(v[i], v[i], q[i]); }
+      for (int i = 0; i < 8; ++i) { sa[i].add(v[i]); qa[i].add(v[i] * v[i]); }
     }
-    slab_cta_reduce(s, q, CW, sh, cta_tot);
+    long long s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = sa[i].fixed(); q[i] = qa[i].fixed(); }
+    slab_reduce_fixed(cluster, s, q, CW, S, sh, cta_tot_q, s_tot, FWD_UNITS);
   }
-  slab_cluster_sum(cluster, cta_tot, s_tot, 2 * CW, S);
   __syncthreads();
   if ((int)threadIdx.x < CW) {
     const int ch = g * CW + threadIdx.x;
@@ -634,10 +692,11 @@ bn_slab_fwd_kernel(const BnFwdParams p, const SlabGeom gm) {
 template <typename T>
 __global__ void __launch_bounds__(SLAB_THREADS)
 bn_slab_bwd_kernel(const BnBwdParams p, const SlabGeom gm) {
-  __shared__ float sh[SLAB_THREADS * SLAB_PITCH];
+  __shared__ __align__(16) float sh[2048];                        // 8 KB: the warps' fixed-point partials
   if (threadIdx.x == 0) pdl_trigger();
   pdl_wait();
-  __shared__ double cta_tot[64], s_tot[64];
+  __shared__ double s_tot[64];
+  __shared__ long long cta_tot_q[64];
   cg::cluster_group cluster = cg::this_cluster();
   const int C = p.C, CW = gm.CW, S = gm.S;
   const int g = blockIdx.x / S, rk = blockIdx.x % S;
@@ -664,9 +723,8 @@ bn_slab_bwd_kernel(const BnBwdParams p, const SlabGeom gm) {
       if (fmaf(v[i], sc[i], shv[i]) <= 0.f) gd[i] = 0.f;
   };
   {
-    float s[8], q[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+    // exact fixed-point sums (see to_q40): the same totals, bit for bit, as the grid-barrier kernel or any rank split
+    BwdAcc<std::is_same<T, float>::value> sa[8], qa[8];
     long long r = r0 + tr;
     constexpr int UB = 2;                                          // rows (48 bytes of loads each) in flight per thread
     for (; r + (UB - 1LL) * rows_par < r1; r += (long long)UB * rows_par) {
@@ -680,7 +738,7 @@ bn_slab_bwd_kernel(const BnBwdParams p, const SlabGeom gm) {
       for (int u = 0; u < UB; ++u) {
         masked(r + (long long)u * rows_par, gq[u], vq[u]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { s[i] += gq[u][i]; q[i] = fmaf(gq[u][i], (vq[u][i] - mu[i]) * rs[i], q[i]); }
+        for (int i = 0; i < 8; ++i) { sa[i].add(gq[u][i]); qa[i].add(gq[u][i] * ((vq[u][i] - mu[i]) * rs[i])); }
       }
     }
     for (; r < r1; r += rows_par) {
@@ -689,11 +747,13 @@ bn_slab_bwd_kernel(const BnBwdParams p, const SlabGeom gm) {
       load8<T>(x + r * C + c, v0);
       masked(r, g0, v0);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { s[i] += g0[i]; q[i] = fmaf(g0[i], (v0[i] - mu[i]) * rs[i], q[i]); }
+      for (int i = 0; i < 8; ++i) { sa[i].add(g0[i]); qa[i].add(g0[i] * ((v0[i] - mu[i]) * rs[i])); }
     }
-    slab_cta_reduce(s, q, CW, sh, cta_tot);
+    long long s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = sa[i].fixed(); q[i] = qa[i].fixed(); }
+    slab_reduce_fixed(cluster, s, q, CW, S, sh, cta_tot_q, s_tot, BWD_UNITS);
   }
-  slab_cluster_sum(cluster, cta_tot, s_tot, 2 * CW, S);
   __syncthreads();
   float k1[8], k0[8];
   {
@@ -817,7 +877,7 @@ static int fused_grid(long long M, int C, int vec, int limit) {
 }
 
 static size_t fused_smem(int C, int vec) {
-  const size_t phase1 = 256 * 2 * (size_t)vec * sizeof(float);
+  const size_t phase1 = 256 * 2 * (size_t)vec * sizeof(long long);   // the backward kernel stages 64-bit partials
   const size_t phase2 = 2 * (size_t)C * sizeof(double) + 2 * (size_t)C * sizeof(float);
   return phase1 > phase2 ? phase1 : phase2;
 }
