@@ -65,28 +65,50 @@ __global__ void prep_convT_kernel(const float* __restrict__ w, int Cin, int Cout
   }
 }
 
-// all layers of a model in ONE launch (blockIdx.y = layer): the per-step refresh of the bf16 kernel-layout copies after
-// the optimizer update is ~20 tiny launches otherwise.  desc (device memory, 5 x int64 per layer):
+// all layers of a model in ONE launch: the per-step refresh of the bf16 kernel-layout copies after the optimizer update is
+// ~20 tiny launches otherwise.  desc (device memory, 5 x int64 per layer):
 // {w, w_fwd (or 0), w_dgrad (or 0), Cin | Cout << 32, kind (0 conv3x3, 1 convT2x2)}
+// Work items = 32 x 32 tiles (or 1024-element runs of a layer that has no such tiles) numbered across ALL layers, walked
+// grid-stride: a launch shaped (96 CTAs, layer) gave the 2.4 M-element bottom layers 24 tiles per CTA and left most CTAs
+// of the small layers idle (67 us for 62 MB of traffic).
+constexpr int PREP_MAX_LAYERS = 64;
 template <typename T>
 __global__ void __launch_bounds__(256)
-prep_batch_kernel(const long long* __restrict__ desc, int nmajor) {
-  const long long* d = desc + 5LL * blockIdx.y;
-  const float* w = reinterpret_cast<const float*>(d[0]);
-  T* wf = reinterpret_cast<T*>(d[1]);
-  T* wd = reinterpret_cast<T*>(d[2]);
-  const int Cin = (int)(d[3] & 0xffffffffLL), Cout = (int)(d[3] >> 32);
-  const bool convT = d[4] != 0;
-  const int taps = convT ? 4 : 9;
-  // The source is [tap][R][C] with C contiguous (conv: R = Cin, C = Cout; convT: R = Cout, C = Cin).  One of the two
-  // bf16 copies keeps C innermost, the other one has R innermost: 32 x 32 tiles go through shared memory so that both
-  // are written with contiguous runs (the naive element-wise version scattered 2-byte stores: 109 us per step).
-  const int R = convT ? Cout : Cin, C = convT ? Cin : Cout;
-  if (nmajor && R % 32 == 0 && C % 32 == 0) {
-    __shared__ float tile[32][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
-    const int tr = R / 32, tc = C / 32, ntiles = taps * tr * tc;
-    for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+prep_batch_kernel(const long long* __restrict__ desc, int count, int nmajor) {
+  __shared__ int s_first[PREP_MAX_LAYERS + 1];          // first work item of every layer
+  __shared__ float tile[32][33];
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int l = 0; l < count; ++l) {
+      const long long* d = desc + 5LL * l;
+      const int Cin = (int)(d[3] & 0xffffffffLL), Cout = (int)(d[3] >> 32);
+      const bool convT = d[4] != 0;
+      const int taps = convT ? 4 : 9, R = convT ? Cout : Cin, C = convT ? Cin : Cout;
+      s_first[l] = acc;
+      acc += (nmajor && R % 32 == 0 && C % 32 == 0) ? taps * (R / 32) * (C / 32) : (taps * Cin * Cout + 1023) / 1024;
+    }
+    s_first[count] = acc;
+  }
+  __syncthreads();
+  const int total = s_first[count];
+  int l = 0;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    while (item >= s_first[l + 1]) ++l;                  // items are visited in ascending order
+    const long long* d = desc + 5LL * l;
+    const float* w = reinterpret_cast<const float*>(d[0]);
+    T* wf = reinterpret_cast<T*>(d[1]);
+    T* wd = reinterpret_cast<T*>(d[2]);
+    const int Cin = (int)(d[3] & 0xffffffffLL), Cout = (int)(d[3] >> 32);
+    const bool convT = d[4] != 0;
+    const int taps = convT ? 4 : 9;
+    // The source is [tap][R][C] with C contiguous (conv: R = Cin, C = Cout; convT: R = Cout, C = Cin).  One of the two
+    // bf16 copies keeps C innermost, the other one has R innermost: 32 x 32 tiles go through shared memory so that both
+    // are written with contiguous runs (the naive element-wise version scattered 2-byte stores: 109 us per step).
+    const int R = convT ? Cout : Cin, C = convT ? Cin : Cout;
+    const int tl = item - s_first[l];
+    if (nmajor && R % 32 == 0 && C % 32 == 0) {
+      const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+      const int tr = R / 32, tc = C / 32;
       const int t = tl / (tr * tc), r0 = (tl / tc) % tr * 32, c0 = (tl % tc) * 32;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -107,29 +129,29 @@ prep_batch_kernel(const long long* __restrict__ desc, int nmajor) {
         else if (wd) wd[((long long)c * 4 + t) * R + r] = from_f32<T>(v);
       }
       __syncthreads();
+      continue;
     }
-    return;
-  }
-  const long long n = (long long)taps * Cin * Cout;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float v = w[i];
-    if (!convT) {
-      const int co = (int)(i % Cout), ci = (int)((i / Cout) % Cin), t = (int)(i / ((long long)Cout * Cin));
-      if (nmajor) {
-        if (wf) wf[((long long)co * 9 + t) * Cin + ci] = from_f32<T>(v);
-        if (wd) wd[((long long)ci * 9 + (8 - t)) * Cout + co] = from_f32<T>(v);
+    const long long n = (long long)taps * Cin * Cout;
+    for (long long i = (long long)tl * 1024 + threadIdx.x; i < n && i < (long long)(tl + 1) * 1024; i += blockDim.x) {
+      const float v = w[i];
+      if (!convT) {
+        const int co = (int)(i % Cout), ci = (int)((i / Cout) % Cin), t = (int)(i / ((long long)Cout * Cin));
+        if (nmajor) {
+          if (wf) wf[((long long)co * 9 + t) * Cin + ci] = from_f32<T>(v);
+          if (wd) wd[((long long)ci * 9 + (8 - t)) * Cout + co] = from_f32<T>(v);
+        } else {
+          if (wf) wf[i] = from_f32<T>(v);
+          if (wd) wd[((long long)(8 - t) * Cout + co) * Cin + ci] = from_f32<T>(v);
+        }
       } else {
-        if (wf) wf[i] = from_f32<T>(v);
-        if (wd) wd[((long long)(8 - t) * Cout + co) * Cin + ci] = from_f32<T>(v);
-      }
-    } else {
-      const int ci = (int)(i % Cin), co = (int)((i / Cin) % Cout), t = (int)(i / ((long long)Cout * Cin));
-      if (nmajor) {
-        if (wf) wf[i] = from_f32<T>(v);
-        if (wd) wd[((long long)ci * 4 + t) * Cout + co] = from_f32<T>(v);
-      } else {
-        if (wf) wf[((long long)t * Cin + ci) * Cout + co] = from_f32<T>(v);
-        if (wd) wd[i] = from_f32<T>(v);
+        const int ci = (int)(i % Cin), co = (int)((i / Cin) % Cout), t = (int)(i / ((long long)Cout * Cin));
+        if (nmajor) {
+          if (wf) wf[i] = from_f32<T>(v);
+          if (wd) wd[((long long)ci * 4 + t) * Cout + co] = from_f32<T>(v);
+        } else {
+          if (wf) wf[((long long)t * Cin + ci) * Cout + co] = from_f32<T>(v);
+          if (wd) wd[i] = from_f32<T>(v);
+        }
       }
     }
   }
@@ -140,11 +162,11 @@ prep_batch_kernel(const long long* __restrict__ desc, int nmajor) {
 using namespace dcb;
 
 extern "C" int dcb_prep_weights_batch(int dtype, const long long* desc_dev, int count, dcb_stream_t stream) {
-  DCB_CHECK_ARG(desc_dev && count > 0 && count <= 65535, "dcb_prep_weights_batch: bad arguments");
-  const dim3 grid(96, count);
-  if (dtype == DCB_F32) prep_batch_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(desc_dev, 0);
-  else if (dtype == DCB_BF16) prep_batch_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(desc_dev, 1);
-  else if (dtype == DCB_F16) prep_batch_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(desc_dev, 1);
+  DCB_CHECK_ARG(desc_dev && count > 0 && count <= PREP_MAX_LAYERS, "dcb_prep_weights_batch: bad arguments (at most %d layers)", PREP_MAX_LAYERS);
+  const int grid = 8 * sm_count();
+  if (dtype == DCB_F32) prep_batch_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(desc_dev, count, 0);
+  else if (dtype == DCB_BF16) prep_batch_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(desc_dev, count, 1);
+  else if (dtype == DCB_F16) prep_batch_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(desc_dev, count, 1);
   else return fail(DCB_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
   g_launches += 1;
   DCB_LAUNCH_OK("prep_batch_kernel");
