@@ -2692,13 +2692,15 @@ tapgemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_
         tmem_ld_32x32b_x32(t_addr + c, r);
         tmem_ld_wait();
         if (kg < K) {
+          // 32-byte stores: one full sector per lane and instruction (a lane owns an accumulator row, so a warp store
+          // touches 32 different lines either way; as 16-byte stores the dump needed twice the requests)
           if (pt1 > pt0) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<uint4*>(dst + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+            for (int j = 0; j < 32; j += 8)
+              st_global_v8(dst + c + j, r[j], r[j + 1], r[j + 2], r[j + 3], r[j + 4], r[j + 5], r[j + 6], r[j + 7]);
           } else {                                   // empty split: nothing was accumulated
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(dst + c + j) = make_uint4(0, 0, 0, 0);
+            for (int j = 0; j < 32; j += 8) st_global_v8(dst + c + j, 0, 0, 0, 0, 0, 0, 0, 0);
           }
         }
       }
