@@ -102,8 +102,12 @@ if comm.rank == 0:
     wd, wr = dpb.get_weights_dict(), ref.get_weights_dict()
     stat = max(float(np.max(np.abs(wd[k] - wr[k]))) for k in wd if 'moving' in k)
     worst = max(errs, key=errs.get)
-    print('bf16 DP (epilogue statistics + in-kernel SyncBN) loss %.6f single-GPU loss %.6f; gradient rel. L2 diff worst %s %.3g, median %.3g; '
-          'max |BN moving stat diff| %.3g' % (loss_dp, loss_ref, worst, errs[worst], float(np.median(list(errs.values()))), stat))
+    # (two 16-bit evaluations of this random-init dice network that round differently anywhere - here: other kernels for the
+    # smaller per-rank tensors - differ by tens of percent in the gradients, like each of them differs from fp64: DESIGN.md 4
+    # "bf16 numerics"; loss and BatchNorm statistics are the meaningful agreement in this mode)
+    print('bf16 DP (epilogue statistics + in-kernel SyncBN) loss %.6f single-GPU loss %.6f; gradient rel. L2 diff worst %s %.3g, median %.3g '
+          '(16-bit noise floor of this network); max |BN moving stat diff| %.3g'
+          % (loss_dp, loss_ref, worst, errs[worst], float(np.median(list(errs.values()))), stat))
     good = abs(loss_dp - loss_ref) < 2e-3 and stat < 2e-2
     print('bf16 data-parallel step consistent with the single-device batch: %s' % good)
     ok &= bool(good)
