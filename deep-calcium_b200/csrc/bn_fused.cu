@@ -59,12 +59,9 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter) {
 }
 
 // Cross-CTA totals as 64-bit FIXED-POINT integer atomics (the caller zeroes totals_q): integer addition is associative, so
-// the total does not depend on the arrival order - bit-reproducible like the fixed-order tree below, but it needs neither
+// the total does not depend on the arrival order - bit-reproducible like a fixed-order tree, but it needs neither
 // the workspace round trip of the per-CTA partials nor the second grid barrier.  Units: 2^-20 for the forward sums of
 // activations (range 8.8e12), 2^-40 for the backward sums of gradients (range 8.4e6, resolution 9e-13).
-__device__ __forceinline__ void add_fixed(long long* totals_q, int idx, double v, double units_inv) {
-  atomicAdd(reinterpret_cast<unsigned long long*>(totals_q) + idx, (unsigned long long)__double2ll_rn(v * units_inv));
-}
 constexpr double FWD_UNITS_INV = 1048576.0, FWD_UNITS = 1.0 / 1048576.0;                 // 2^20
 constexpr double BWD_UNITS_INV = 1099511627776.0, BWD_UNITS = 1.0 / 1099511627776.0;     // 2^40
 // The backward sums (sum dz, sum dz * xhat) cancel to ~1e-3 of their terms in this network, so ANY change in how fp32
@@ -106,18 +103,6 @@ __device__ __forceinline__ void release_totals(long long* totals_q, int V, unsig
   __syncthreads();
   if (s_last_reader)
     for (int i = threadIdx.x; i < V; i += blockDim.x) totals_q[i] = 0;
-}
-
-// partial[cta][V] (double) -> totals[V]: value u is summed by warp (u % 8) of CTA (u / 8 % grid) - lanes take every
-// 32nd CTA's partial, then a shuffle tree - a fixed pattern, so the sum does not depend on scheduling
-__device__ __forceinline__ void reduce_partials(const double* __restrict__ partial, int V, double* __restrict__ totals) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int u = blockIdx.x * nwarps + warp; u < V; u += gridDim.x * nwarps) {
-    double acc = 0;
-    for (int g = lane; g < (int)gridDim.x; g += 32) acc += __ldcg(partial + (size_t)g * V + u);
-    acc = warp_sum(acc);
-    if (lane == 0) totals[u] = acc;
-  }
 }
 
 // SyncBN exchange of the V local totals (see the file comment).  Returns with s_tot[0..V) = sum over ranks.
@@ -162,7 +147,7 @@ struct BnFwdParams {
   const float* gamma; const float* beta; float eps, momentum;
   float* moving_mean; float* moving_var; float* scale; float* shift; float* mean; float* rstd;
   int relu; float p_drop; unsigned long long seed; const unsigned long long* seed_dev; unsigned layer;
-  double* partial; double* totals; unsigned* sync;
+  double* totals; unsigned* sync;           // totals: 64-bit fixed-point integers (2 * C), zero on entry
   const long long* sums_q;              // PRE instantiation: fixed-point batch sums of a conv epilogue (stats_epilogue.cuh)
   PeerView pv;
 };
@@ -328,7 +313,7 @@ struct BnBwdParams {
   const float* scale; const float* shift; const float* mean; const float* rstd;
   float p_drop; unsigned long long seed; const unsigned long long* seed_dev; unsigned layer;
   float dgb_scale; float* dgamma; float* dbeta;
-  double* partial; double* totals; unsigned* sync;
+  double* totals; unsigned* sync;           // totals: 64-bit fixed-point integers (2 * C), zero on entry
   PeerView pv;
 };
 
@@ -472,7 +457,7 @@ bn_train_bwd_kernel(const BnBwdParams p) {
 
 
 // ================================================================================ channel-slab kernels (clusters)
-// The grid-barrier kernels above pay ~2-3 us per barrier plus a global round trip of the per-CTA partials, which is
+// The grid-barrier kernels above pay ~2-3 us for their barrier and a round of atomics, which is
 // most of the time of the small deep-level tensors (2 - 16 MB: ~15-25 us per launch against a 1-5 us bandwidth floor).
 // Here the tensor [M][C] is cut into channel SLABS of CW channels (16 or 32 bytes per row = whole sectors) and each slab
 // into S row ranges: a thread-block CLUSTER of S CTAs owns one slab, every CTA reduces its rows, the S partial vectors
@@ -485,27 +470,9 @@ namespace cg = cooperative_groups;
 #define DCB_SLAB_THREADS 512
 #endif
 constexpr int SLAB_THREADS = DCB_SLAB_THREADS;   // 16 warps: the dropout layers are issue bound (Philox), one CTA per SM
-constexpr int SLAB_PITCH = 17;      // floats per thread in the CTA reduction buffer (16 + 1: conflict-free columns)
 
 struct SlabGeom { int CW, S; long long rows_per_cta; };
 
-// per-thread partials (8 channels x {s, q}) -> cta_tot[2*CW] doubles (channel-major: [0,CW) = s, [CW,2CW) = q)
-__device__ __forceinline__ void slab_cta_reduce(const float (&s)[8], const float (&q)[8], int CW, float* sh, double* cta_tot) {
-  const int lanes_c = CW >> 3, rows_par = SLAB_THREADS / lanes_c;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { sh[threadIdx.x * SLAB_PITCH + i] = s[i]; sh[threadIdx.x * SLAB_PITCH + 8 + i] = q[i]; }
-  __syncthreads();
-  // 2*CW outputs, tpo = 256 / (2*CW) threads per output, 16 entries each, then a shuffle tree over the tpo lanes
-  const int nout = 2 * CW, tpo = SLAB_THREADS / nout;
-  const int o = threadIdx.x / tpo, k = threadIdx.x % tpo;
-  const int comp = o / CW, ch = o % CW, lc = ch >> 3, i = ch & 7;
-  double acc = 0;
-  for (int rr = k; rr < rows_par; rr += tpo) acc += (double)sh[(rr * lanes_c + lc) * SLAB_PITCH + comp * 8 + i];
-  for (int off = tpo >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if (k == 0) cta_tot[o] = acc;
-}
-
-// cta_tot of every CTA of the cluster, summed in rank order -> s_tot (identical in all CTAs)
 // fixed-point thread partials (8 channels x {s, q}) -> cluster totals as doubles: lanes with the same channel group
 // (lane % lanes_c) meet by shuffles, the 16 warps through shared memory, the S CTAs of the cluster through DSMEM - integer
 // additions throughout, so the totals do not depend on how rows were distributed.  sh: >= 8 KB of shared memory.
@@ -537,16 +504,6 @@ __device__ __forceinline__ void slab_reduce_fixed(cg::cluster_group& cluster, lo
   cluster.sync();             // nobody leaves (or overwrites cta_tot_q) while a peer may still be reading it
 }
 
-__device__ __forceinline__ void slab_cluster_sum(cg::cluster_group& cluster, double* cta_tot, double* s_tot, int nout, int S) {
-  cluster.sync();
-  if ((int)threadIdx.x < nout) {
-    double acc = 0;
-    for (int rk = 0; rk < S; ++rk) acc += cluster.map_shared_rank(cta_tot, rk)[threadIdx.x];
-    s_tot[threadIdx.x] = acc;
-  }
-  // nobody leaves (or overwrites cta_tot) while a peer may still be reading it
-  cluster.sync();
-}
 
 template <typename T, bool POOL>
 __global__ void __launch_bounds__(SLAB_THREADS)
@@ -927,7 +884,6 @@ static int launch_bn_fwd(BnFwdParams& p, void* ws, size_t ws_bytes, cudaStream_t
   const int grid = fused_grid(p.M, p.C, VEC, limit);
   const size_t need = 2 * (size_t)p.C * sizeof(long long);
   if (!ws || ws_bytes < need) return fail(DCB_ERR_WORKSPACE, "dcb_bn_train_fwd: workspace %zu B < required %zu B", ws_bytes, need);
-  p.partial = nullptr;
   p.totals = reinterpret_cast<double*>(ws);      // 64-bit fixed-point totals, zero on entry (see release_totals)
   {
     const cudaError_t le = launch_k(bn_train_fwd_kernel<T, VEC, POOL>, grid, 256, smem, st, policy(DCB_POLICY_PDL) != 0, p);
@@ -1024,7 +980,6 @@ static int launch_bn_bwd(BnBwdParams& p, void* ws, size_t ws_bytes, cudaStream_t
   const int grid = fused_grid(p.M, p.C, VEC, limit);
   const size_t need = 2 * (size_t)p.C * sizeof(long long);
   if (!ws || ws_bytes < need) return fail(DCB_ERR_WORKSPACE, "dcb_bn_train_bwd: workspace %zu B < required %zu B", ws_bytes, need);
-  p.partial = nullptr;
   p.totals = reinterpret_cast<double*>(ws);      // 64-bit fixed-point totals, zero on entry (see release_totals)
   {
     const cudaError_t le = launch_k(bn_train_bwd_kernel<T, VEC>, grid, 256, smem, st, policy(DCB_POLICY_PDL) != 0, p);
