@@ -1,7 +1,7 @@
 // Batch statistics of a training-mode conv output taken INSIDE the conv epilogue (Keras BatchNormalization in training
 // mode, unet_2d_summary.py:157,165: per-channel mean / biased variance over the batch): the epilogue already holds every
 // output value in registers, so the per-channel sums (x, x^2) cost a shared-memory transpose instead of another pass over
-// the tensor and two grid barriers (the single-launch BatchNorm kernel of bn_fused.cu).
+// the tensor and a grid barrier (the single-launch BatchNorm kernel of bn_fused.cu).
 //
 //   per 32 px x 32 ch block : stats_block()       - the packed 16-bit block a warp is about to store goes through a
 //                                                   2 KB per-warp scratch tile; lane l sums channel pair (l & 15) over
@@ -10,8 +10,8 @@
 //                                                   64-bit fixed point -> integer atomics into sums_q[0..C) = sum x,
 //                                                   sums_q[C..2C) = sum x^2
 // Every floating-point sum has a fixed order (lane, block, warp) and the cross-CTA total is an INTEGER sum, so the totals
-// are bit-reproducible run to run; there are no floating-point atomics.  The statistics are taken over the ROUNDED (stored) values - exactly what a separate
-// statistics pass over the stored tensor would see.
+// are bit-reproducible run to run; there are no floating-point atomics.  The statistics are taken over the ROUNDED (stored)
+// values - exactly what a separate statistics pass over the stored tensor would see.
 #pragma once
 #include "tc_common.cuh"
 
