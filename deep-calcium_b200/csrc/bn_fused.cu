@@ -308,6 +308,7 @@ bn_train_fwd_kernel(const BnFwdParams p) {
 
 struct BnBwdParams {
   const float* dy; int ldy, offy;       // upstream gradient (fp32 view: row stride ldy, channel offset offy)
+  const float* gpix; const float* wd;   // or (gpix != null) the rank-1 gradient of the softmax head: dy[r][c] = gpix[r] * wd[c]
   const void* x; void* draw;            // raw conv output [M][C]; gradient w.r.t. it (may alias x)
   long long M, M_total; int C;
   const float* scale; const float* shift; const float* mean; const float* rstd;
@@ -354,6 +355,18 @@ bn_train_bwd_kernel(const BnBwdParams p) {
     for (int i = 0; i < VEC; ++i)
       if (fmaf(v[i], sc[i], sh[i]) <= 0.f) g[i] = 0.f;
   };
+  float wdv[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) wdv[i] = p.gpix ? p.wd[c + i] : 0.f;
+  auto load_dy = [&](long long r, float (&g)[VEC]) {
+    if (p.gpix) {
+      const float gp = p.gpix[r];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) g[i] = gp * wdv[i];
+    } else {
+      loadv<float, VEC>(p.dy + r * p.ldy + p.offy + c, g);
+    }
+  };
   // ---------------- phase 1: exact fixed-point sums (see to_q40)
   {
     float rs[VEC];
@@ -368,8 +381,8 @@ bn_train_bwd_kernel(const BnBwdParams p) {
     long long r = r0 + tr;
     for (; r + rows_par < r1; r += 2LL * rows_par) {
       float g0[VEC], g1[VEC], v0[VEC], v1[VEC];
-      loadv<float, VEC>(p.dy + r * p.ldy + p.offy + c, g0);
-      loadv<float, VEC>(p.dy + (r + rows_par) * p.ldy + p.offy + c, g1);
+      load_dy(r, g0);
+      load_dy(r + rows_par, g1);
       loadv<T, VEC>(x + r * C + c, v0);
       loadv<T, VEC>(x + (r + rows_par) * C + c, v1);
       accumulate(r, g0, v0);
@@ -377,7 +390,7 @@ bn_train_bwd_kernel(const BnBwdParams p) {
     }
     for (; r < r1; r += rows_par) {
       float g0[VEC], v0[VEC];
-      loadv<float, VEC>(p.dy + r * p.ldy + p.offy + c, g0);
+      load_dy(r, g0);
       loadv<T, VEC>(x + r * C + c, v0);
       accumulate(r, g0, v0);
     }
@@ -431,8 +444,8 @@ bn_train_bwd_kernel(const BnBwdParams p) {
   for (; nrows >= 2; nrows -= 2, r -= 2LL * rows_par) {   // two rows (2 x 48 bytes of loads) in flight per thread
     float g0[VEC], g1[VEC], v0[VEC], v1[VEC], o[VEC];
     const long long ra = r, rb = r - rows_par;
-    loadv<float, VEC>(p.dy + ra * p.ldy + p.offy + c, g0);
-    loadv<float, VEC>(p.dy + rb * p.ldy + p.offy + c, g1);
+    load_dy(ra, g0);
+    load_dy(rb, g1);
     loadv<T, VEC>(x + ra * C + c, v0);
     loadv<T, VEC>(x + rb * C + c, v1);
     masked(ra, g0, v0);
@@ -446,7 +459,7 @@ bn_train_bwd_kernel(const BnBwdParams p) {
   }
   if (nrows == 1) {
     float g[VEC], v[VEC], o[VEC];
-    loadv<float, VEC>(p.dy + r * p.ldy + p.offy + c, g);
+    load_dy(r, g);
     loadv<T, VEC>(x + r * C + c, v);
     masked(r, g, v);
 #pragma unroll
@@ -989,27 +1002,55 @@ static int launch_bn_bwd(BnBwdParams& p, void* ws, size_t ws_bytes, cudaStream_t
   return DCB_OK;
 }
 
+static int bn_train_bwd_impl(int dtype, const float* dy, int ldy, int offy, const float* gpix, const float* wd, const void* x,
+                             long long M, int C, long long M_total, const float* scale, const float* shift, const float* mean,
+                             const float* rstd, float p_drop, unsigned long long seed, const unsigned long long* seed_dev,
+                             unsigned layer, float dgb_scale, void* draw, float* dgamma, float* dbeta, void* workspace,
+                             size_t workspace_bytes, unsigned int* sync, const dcb_peer_exchange_t* peers, dcb_stream_t stream);
+
 extern "C" int dcb_bn_train_bwd(int dtype, const float* dy, int ldy, int offy, const void* x, long long M, int C,
                                 long long M_total, const float* scale, const float* shift, const float* mean,
                                 const float* rstd, float p_drop, unsigned long long seed,
                                 const unsigned long long* seed_dev, unsigned layer, float dgb_scale, void* draw,
                                 float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, unsigned int* sync,
                                 const dcb_peer_exchange_t* peers, dcb_stream_t stream) {
-  DCB_CHECK_ARG(dy && x && scale && shift && mean && rstd && draw && sync && M > 0, "dcb_bn_train_bwd: bad arguments");
+  DCB_CHECK_ARG(dy, "dcb_bn_train_bwd: bad arguments");
   DCB_CHECK_ARG(ldy % 4 == 0 && offy % 4 == 0 && offy + C <= ldy, "dcb_bn_train_bwd: bad dy view (ld %d off %d C %d)", ldy, offy, C);
-  DCB_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0, "dcb_bn_train_bwd: pointers must be 16-byte aligned");
+  DCB_CHECK_ARG((reinterpret_cast<uintptr_t>(dy) & 15) == 0, "dcb_bn_train_bwd: pointers must be 16-byte aligned");
+  return bn_train_bwd_impl(dtype, dy, ldy, offy, nullptr, nullptr, x, M, C, M_total, scale, shift, mean, rstd, p_drop, seed, seed_dev,
+                           layer, dgb_scale, draw, dgamma, dbeta, workspace, workspace_bytes, sync, peers, stream);
+}
+
+extern "C" int dcb_bn_train_bwd_rank1(int dtype, const float* gpix, const float* wd, const void* x, long long M, int C,
+                                      long long M_total, const float* scale, const float* shift, const float* mean,
+                                      const float* rstd, float p_drop, unsigned long long seed,
+                                      const unsigned long long* seed_dev, unsigned layer, float dgb_scale, void* draw,
+                                      float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, unsigned int* sync,
+                                      const dcb_peer_exchange_t* peers, dcb_stream_t stream) {
+  DCB_CHECK_ARG(gpix && wd, "dcb_bn_train_bwd_rank1: bad arguments");
+  return bn_train_bwd_impl(dtype, nullptr, 0, 0, gpix, wd, x, M, C, M_total, scale, shift, mean, rstd, p_drop, seed, seed_dev, layer,
+                           dgb_scale, draw, dgamma, dbeta, workspace, workspace_bytes, sync, peers, stream);
+}
+
+static int bn_train_bwd_impl(int dtype, const float* dy, int ldy, int offy, const float* gpix, const float* wd, const void* x,
+                             long long M, int C, long long M_total, const float* scale, const float* shift, const float* mean,
+                             const float* rstd, float p_drop, unsigned long long seed, const unsigned long long* seed_dev,
+                             unsigned layer, float dgb_scale, void* draw, float* dgamma, float* dbeta, void* workspace,
+                             size_t workspace_bytes, unsigned int* sync, const dcb_peer_exchange_t* peers, dcb_stream_t stream) {
+  DCB_CHECK_ARG(x && scale && shift && mean && rstd && draw && sync && M > 0, "dcb_bn_train_bwd: bad arguments");
+  DCB_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0, "dcb_bn_train_bwd: pointers must be 16-byte aligned");
   const int vec = fused_vec(C);
   if (!vec || C > 1024) return fail(DCB_ERR_INVALID_ARGUMENT, "dcb_bn_train_bwd: channel count %d unsupported", C);
   BnBwdParams p;
   memset(&p, 0, sizeof(p));
-  p.dy = dy; p.ldy = ldy; p.offy = offy; p.x = x; p.draw = draw; p.M = M; p.M_total = M_total > 0 ? M_total : M; p.C = C;
+  p.dy = dy; p.ldy = ldy; p.offy = offy; p.gpix = gpix; p.wd = wd; p.x = x; p.draw = draw; p.M = M; p.M_total = M_total > 0 ? M_total : M; p.C = C;
   p.scale = scale; p.shift = shift; p.mean = mean; p.rstd = rstd; p.p_drop = p_drop; p.seed = seed; p.seed_dev = seed_dev;
   p.layer = layer; p.dgb_scale = dgb_scale; p.dgamma = dgamma; p.dbeta = dbeta; p.sync = sync;
   if (int e = fill_peers(p.pv, peers, C)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   {
     SlabGeom gm;
-    if (p.pv.world == 1 && (reinterpret_cast<uintptr_t>(draw) & 15) == 0 && slab_geom(M, C, dtype == DCB_F32 ? 4 : 2, 1, 5LL << 19, gm)) {
+    if (!gpix && p.pv.world == 1 && (reinterpret_cast<uintptr_t>(draw) & 15) == 0 && slab_geom(M, C, dtype == DCB_F32 ? 4 : 2, 1, 5LL << 19, gm)) {
       BN_DISPATCH(dtype, return launch_slab(bn_slab_bwd_kernel<T>, p, gm, st, "bn_slab_bwd_kernel");)
     }
   }

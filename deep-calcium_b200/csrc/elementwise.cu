@@ -615,11 +615,16 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 head_loss_bwd_c32_kernel(const T* __restrict__ x, long long M, const float* __restrict__ w, const uint8_t* __restrict__ yt,
                          const float* __restrict__ prob, const double* __restrict__ sums, int loss, long long M_total,
-                         float* __restrict__ dx, double* __restrict__ dwb) {
+                         float* __restrict__ dx, double* __restrict__ dwb, float* __restrict__ gpix, float* __restrict__ wd_out) {
+  // gpix != null: dL/dx is the rank-1 product gpix[m] * wd[c] - only its two factors are written (4 bytes per pixel instead of
+  // 128), the BatchNorm backward of the last block rebuilds it on the fly (dcb_bn_train_bwd_rank1)
   constexpr int C = 32;
   __shared__ float wd[C];
   __shared__ float red[8][C + 1];
-  if (threadIdx.x < C) wd[threadIdx.x] = w[threadIdx.x * 2 + 1] - w[threadIdx.x * 2];
+  if (threadIdx.x < C) {
+    wd[threadIdx.x] = w[threadIdx.x * 2 + 1] - w[threadIdx.x * 2];
+    if (wd_out && blockIdx.x == 0) wd_out[threadIdx.x] = wd[threadIdx.x];
+  }
   __syncthreads();
   const double invM = 1.0 / (double)M_total;
   float acc[C];
@@ -631,14 +636,17 @@ head_loss_bwd_c32_kernel(const T* __restrict__ x, long long M, const float* __re
     const float g = loss_grad_wrt_p(loss, p, (float)yt[m], sums, invM);
     const float dz1 = p * (1.f - p) * g;
     accb += dz1;
+    if (gpix) gpix[m] = dz1;
 #pragma unroll
     for (int c = 0; c < C; c += 8) {
       float v[8];
       load8<T>(x + m * C + c, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[c + j] = fmaf(v[j], dz1, acc[c + j]);
-      store4<float>(dx + m * C + c, make_float4(dz1 * wd[c], dz1 * wd[c + 1], dz1 * wd[c + 2], dz1 * wd[c + 3]));
-      store4<float>(dx + m * C + c + 4, make_float4(dz1 * wd[c + 4], dz1 * wd[c + 5], dz1 * wd[c + 6], dz1 * wd[c + 7]));
+      if (!gpix) {
+        store4<float>(dx + m * C + c, make_float4(dz1 * wd[c], dz1 * wd[c + 1], dz1 * wd[c + 2], dz1 * wd[c + 3]));
+        store4<float>(dx + m * C + c + 4, make_float4(dz1 * wd[c + 4], dz1 * wd[c + 5], dz1 * wd[c + 6], dz1 * wd[c + 7]));
+      }
     }
   }
   // warp reduction of the 33 partials (once per CTA), then across the 8 warps through shared memory
@@ -1040,10 +1048,28 @@ extern "C" int dcb_head_loss_bwd(int dtype, const void* x, long long M, int C, c
   DCB_CHECK_ARG(loss >= 0 && loss <= 3, "dcb_head_loss_bwd: unknown loss id %d", loss);
   int grid = ew_grid(M, 256); if (grid > sm_count() * 4) grid = sm_count() * 4;
   if (C == 32 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-    DISPATCH_T(dtype, head_loss_bwd_c32_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, M, w, yt, prob, sums, loss, M_total, (float*)dx, dwb_accum);)
+    DISPATCH_T(dtype, head_loss_bwd_c32_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, M, w, yt, prob, sums, loss, M_total, (float*)dx, dwb_accum, nullptr, nullptr);)
   } else {
     DISPATCH_T(dtype, head_loss_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, M, C, w, yt, prob, sums, loss, M_total, (float*)dx, dwb_accum);)
   }
+  DCB_LAUNCH_OK("head_loss_bwd_kernel");
+  head_metrics_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(sums, M_total, loss, metrics_out, dwb_accum, C, dw_out);
+  g_launches += 2;
+  DCB_LAUNCH_OK("head_metrics_kernel");
+  return DCB_OK;
+}
+
+extern "C" int dcb_head_loss_bwd_rank1(int dtype, const void* x, long long M, int C, const float* w, const uint8_t* yt,
+                                       const float* prob, const double* sums, int loss, long long M_total, float* gpix,
+                                       float* wd_out, double* dwb_accum, float* dw_out, float* metrics_out, dcb_stream_t stream) {
+  if (M_total <= 0) M_total = M;
+  DCB_CHECK_ARG(x && w && yt && prob && sums && gpix && wd_out && dwb_accum && dw_out && metrics_out && M > 0,
+                "dcb_head_loss_bwd_rank1: bad arguments");
+  DCB_CHECK_ARG(loss >= 0 && loss <= 3, "dcb_head_loss_bwd_rank1: unknown loss id %d", loss);
+  if (C != 32 || (reinterpret_cast<uintptr_t>(x) & 15) != 0)
+    return fail(DCB_ERR_UNSUPPORTED, "dcb_head_loss_bwd_rank1: 32 input channels only (got %d); use dcb_head_loss_bwd", C);
+  int grid = ew_grid(M, 256); if (grid > sm_count() * 4) grid = sm_count() * 4;
+  DISPATCH_T(dtype, head_loss_bwd_c32_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, M, w, yt, prob, sums, loss, M_total, nullptr, dwb_accum, gpix, wd_out);)
   DCB_LAUNCH_OK("head_loss_bwd_kernel");
   head_metrics_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(sums, M_total, loss, metrics_out, dwb_accum, C, dw_out);
   g_launches += 2;

@@ -319,6 +319,16 @@ def bn_train_bwd(dy, ldy, offy, x, scale, shift, mean, rstd, draw, dgamma, dbeta
          _peers_arg(peers, slot), stream_ptr())
 
 
+def bn_train_bwd_rank1(gpix, wd, x, scale, shift, mean, rstd, draw, dgamma, dbeta, workspace, sync, p_drop=0., seed=0,
+                       seed_dev=None, layer=0, M_total=0, dgb_scale=1.0, peers=None, slot=0):
+    """bn_train_bwd whose upstream gradient is the rank-1 product gpix[r] * wd[c] (head_loss_bwd_rank1)"""
+    C = x.shape[-1]
+    call('dcb_bn_train_bwd_rank1', _dt(x), ptr(gpix), ptr(wd), ptr(x), c_ll(x.numel() // C), c_int(C), c_ll(M_total),
+         ptr(scale), ptr(shift), ptr(mean), ptr(rstd), c_f(p_drop), c_ull(seed), ptr(seed_dev), c_uint(layer), c_f(dgb_scale),
+         ptr(draw), ptr(dgamma), ptr(dbeta), ptr(workspace), c_sz(workspace.numel() * workspace.element_size()), ptr(sync),
+         _peers_arg(peers, slot), stream_ptr())
+
+
 # ---------------------------------------------------------------- peer-mapped memory (csrc/peer.cu)
 def peer_alloc(nbytes):
     """-> (device pointer, 64-byte IPC handle)"""
@@ -411,6 +421,15 @@ def head_loss_bwd(x, w, yt, prob, sums, loss_id, dx, dwb_accum, dw_out, metrics_
     C = x.shape[-1]
     call('dcb_head_loss_bwd', _dt(x), ptr(x), c_ll(x.numel() // C), c_int(C), ptr(w), ptr(yt), ptr(prob), ptr(sums),
          c_int(loss_id), c_ll(M_total), ptr(dx), ptr(dwb_accum), ptr(dw_out), ptr(metrics_out), stream_ptr())
+
+
+def head_loss_bwd_rank1(x, w, yt, prob, sums, loss_id, gpix, wd_out, dwb_accum, dw_out, metrics_out, M_total=0):
+    """head_loss_bwd that writes the two factors of the rank-1 gradient dL/dx[m][c] = gpix[m] * wd[c] instead of dL/dx
+    (32 input channels)"""
+    C = x.shape[-1]
+    _chk(gpix, torch.float32); _chk(wd_out, torch.float32)
+    call('dcb_head_loss_bwd_rank1', _dt(x), ptr(x), c_ll(x.numel() // C), c_int(C), ptr(w), ptr(yt), ptr(prob), ptr(sums),
+         c_int(loss_id), c_ll(M_total), ptr(gpix), ptr(wd_out), ptr(dwb_accum), ptr(dw_out), ptr(metrics_out), stream_ptr())
 
 
 # ---------------------------------------------------------------- TTA

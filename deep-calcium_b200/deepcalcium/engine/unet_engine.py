@@ -61,6 +61,8 @@ class UNetEngine(object):
         self.launches = 0
         self.comm = None          # engine.dist.Comm for data-parallel training (None = single GPU)
         self.overlap_wgrad = True  # weight-gradient launches on a side stream (see _train_step_enqueue)
+        self.rank1_head_grad = True   # the softmax head's input gradient stays factored (see _train_step_enqueue)
+        self.head_wd = torch.zeros(self.spec.nfb, dtype=torch.float32, device=self.dev)
         self.pdl = os.environ.get('DCB_PDL', '1') != '0'   # programmatic dependent launch in the inference forward
         # ... along the main chain of the training step it LOSES (2.81 -> 3.14 ms, scripts/train_time.py): the early-resident
         # CTAs of the next main-chain kernel take the SM slots in which the weight-gradient side stream overlapped
@@ -265,6 +267,7 @@ class UNetEngine(object):
         if training:
             s['y'] = torch.zeros(NB, H, W, dtype=torch.uint8, device=self.dev)
             s['dhead'] = torch.empty(NB, H, W, self.spec.nfb, dtype=torch.float32, device=self.dev)
+            s['gpix'] = torch.empty(NB, H, W, dtype=torch.float32, device=self.dev)     # rank-1 head gradient: per-pixel factor
             need = 0
             for blk in self.spec.blocks:
                 h, w = H >> blk.level, W >> blk.level
@@ -529,8 +532,16 @@ class UNetEngine(object):
         off_k = self._slots['head/kernel'][1]
         dw_out = self.grads[off_k:off_k + 2 * spec.nfb + 2]
         assert self._slots['head/bias'][1] == off_k + 2 * spec.nfb
-        ops.head_loss_bwd(act['dec0b'], self.P['head/kernel'], s['y'], s['prob'], hs, loss_id, s['dhead'], hd, dw_out,
-                          self.metrics, M_total=s['prob'].numel() * world)
+        # dL/d(dec0b) = gpix[pixel] * wd[channel] is never materialised when the single-launch BatchNorm backward follows: the
+        # head kernel writes the two factors, dec0b's BatchNorm backward rebuilds the product while it reads (134 MB less to
+        # write and 2 x 67 MB less to read for a 32 x 128^2 batch)
+        rank1 = fused_bn and self.rank1_head_grad and spec.nfb == 32
+        if rank1:
+            ops.head_loss_bwd_rank1(act['dec0b'], self.P['head/kernel'], s['y'], s['prob'], hs, loss_id, s['gpix'], self.head_wd,
+                                    hd, dw_out, self.metrics, M_total=s['prob'].numel() * world)
+        else:
+            ops.head_loss_bwd(act['dec0b'], self.P['head/kernel'], s['y'], s['prob'], hs, loss_id, s['dhead'], hd, dw_out,
+                              self.metrics, M_total=s['prob'].numel() * world)
         # ---------------- backward
         # Weight gradients are off the critical path: layer L's wgrad needs only d_raw(L) and the saved input, and nothing
         # before the optimizer reads its result, while the chain BN-bwd(L) -> dgrad(L) -> BN-bwd(L-1) ... is strictly
@@ -548,7 +559,7 @@ class UNetEngine(object):
             with torch.cuda.stream(side):
                 fn(*args)
 
-        grad_of = {'dec0b': (s['dhead'], spec.nfb, 0)}
+        grad_of = {'dec0b': ((s['gpix'], self.head_wd) if rank1 else s['dhead'], spec.nfb, 0)}
         skip_grad = {}
         for blk in reversed(spec.blocks):
             n = blk.name
@@ -560,7 +571,13 @@ class UNetEngine(object):
             sums = self.dbl[st['off_b']:st['off_b'] + 2 * blk.cout]
             p = self._dropout_p(n, dropout)
             draw = raw[n]      # in place: raw is dead after this point
-            if fused_bn:
+            if fused_bn and isinstance(dy, tuple):      # rank-1 gradient of the softmax head (dec0b)
+                li = layer_id[n]
+                ops.bn_train_bwd_rank1(dy[0], dy[1], raw[n], st['scale'], st['shift'], st['mean'], st['rstd'], draw,
+                                       self.G[n + '/gamma'], self.G[n + '/beta'], self.bn_ws, self.bn_sync[8 * li + 4:8 * li + 8], p,
+                                       seed_base, seed_dev, li, M_total=(raw[n].numel() // blk.cout) * world, dgb_scale=1.0 / world,
+                                       peers=self.peers, slot=2 * li + 1)
+            elif fused_bn:
                 li = layer_id[n]
                 ops.bn_train_bwd(dy, ldy, offy, raw[n], st['scale'], st['shift'], st['mean'], st['rstd'], draw,
                                  self.G[n + '/gamma'], self.G[n + '/beta'], self.bn_ws, self.bn_sync[8 * li + 4:8 * li + 8], p,

@@ -275,6 +275,14 @@ int dcb_bn_train_bwd(int dtype, const float* dy, int ldy, int offy, const void* 
                      const unsigned long long* seed_dev, unsigned layer, float dgb_scale, void* draw,
                      float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, unsigned int* sync,
                      const dcb_peer_exchange_t* peers, dcb_stream_t stream);
+/* the same with the upstream gradient given as the rank-1 product dy[r][c] = gpix[r] * wd[c] (dcb_head_loss_bwd_rank1): the
+ * BatchNorm backward of the block in front of the softmax head never reads (and nobody writes) a materialised dL/dx */
+int dcb_bn_train_bwd_rank1(int dtype, const float* gpix, const float* wd, const void* x, long long M, int C,
+                           long long M_total, const float* scale, const float* shift, const float* mean,
+                           const float* rstd, float p_drop, unsigned long long seed,
+                           const unsigned long long* seed_dev, unsigned layer, float dgb_scale, void* draw,
+                           float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, unsigned int* sync,
+                           const dcb_peer_exchange_t* peers, dcb_stream_t stream);
 
 /* ---- peer-mapped memory between the ranks of one NVSwitch box (csrc/peer.cu; SURVEY 8e, no reference counterpart:
  * the reference is single-device).  dcb_peer_alloc returns a zero-filled device buffer and its 64-byte CUDA IPC handle;

@@ -412,6 +412,28 @@ def test_reference_surface_fit_predict_evaluate(cuda, tmp_path):
     assert set(scores.keys()) == {True, False}
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_factored_head_gradient_equals_the_materialised_one(cuda, precision):
+    """dL/d(dec0b) = gpix[pixel] * wd[channel] kept as its two factors (dcb_head_loss_bwd_rank1 + dcb_bn_train_bwd_rank1, the
+    default) against the materialised [N, H, W, 32] gradient: the same products in the same summation order - up to the
+    compiler contracting gpix * wd into the multiply-adds that consume it, one fp32 rounding that the cancelling BatchNorm
+    sums of this network amplify to ~1e-4 - so: same loss, every gradient tensor within 1e-3 relative L2."""
+    spec, w, _ = _nfb32_case()
+    rng = np.random.default_rng(11)
+    x = torch.from_numpy(rng.standard_normal((4, 64, 64)).astype(np.float32)).cuda()
+    y = torch.from_numpy((rng.random((4, 64, 64)) < 0.126).astype(np.uint8)).cuda()
+    grads = {}
+    for rank1 in (True, False):
+        eng = _engine(32, precision, w, use_graphs=False)
+        eng.rank1_head_grad = rank1
+        m = eng.train_step(x, y, loss='dice_loss', dropout=True)
+        grads[rank1] = (float(m[0].item()), {k: v.clone() for k, v in eng.G.items()})
+    assert abs(grads[True][0] - grads[False][0]) < 1e-6
+    for k in grads[True][1]:
+        a, b = grads[True][1][k].double(), grads[False][1][k].double()
+        assert float((a - b).norm() / (b.norm() + 1e-30)) < 1e-3, k
+
+
 def test_pipelined_predict_equals_the_serial_engine_calls(cuda, tmp_path):
     """UNet2DSummary.predict overlaps upload / step / download of consecutive images over two buffer slots
     (unet_2d_summary.py:578-595 is a serial loop): seven different images of two shapes, with and without TTA, must come
